@@ -1,0 +1,183 @@
+/*
+ * mgb.h - C ABI of libmgb.so: B200 (sm_100a) implementation of the MaternGaBO hot path.
+ *
+ * The reference (NoemieJaquier/MaternGaBO) is pure Python: its "FFI" for this path is the body of
+ * each gpytorch Kernel.forward, a composition of torch ops.  Every entry point below replaces one
+ * such composition; the comment above it cites the reference lines (relative to
+ * /root/reference/BoManifolds).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all matrices row-major float64 with an explicit leading
+ *     dimension (elements, not bytes);
+ *   - "device" entry points take device pointers and a cudaStream_t (passed as void*); they never
+ *     allocate, never synchronise and never throw; they return MGB_OK or an error code, and
+ *     mgb_last_error() returns a static message for the calling thread;
+ *   - "_host" entry points take HOST pointers, stage through device memory internally (host<->device
+ *     copies included) and synchronise before returning;
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef MGB_H_
+#define MGB_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGB_OK 0
+#define MGB_ERR_ARG 1      /* invalid argument (null pointer, bad size, unsupported width ...) */
+#define MGB_ERR_CUDA 2     /* a CUDA runtime call or kernel launch failed */
+#define MGB_ERR_NO_DEVICE 3
+
+#define MGB_BASIS_MONOMIAL 0   /* p(u) = sum_k c_k u^k, Horner */
+#define MGB_BASIS_CHEBYSHEV 1  /* p(u) = sum_k c_k T_k(u), Clenshaw */
+
+#define MGB_MAX_FACTORS 16
+#define MGB_MAX_TERMS 256
+
+const char* mgb_last_error(void);
+int mgb_version(void);
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+long long mgb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Spectral-series Gram matrix (sphere S^d, SO(3), circle, torus T^d)
+ *
+ *   K[i][j] = prod_{f < n_factors} p_f( clamp(scale * <x1[i][f*W : (f+1)*W], x2[j][f*W : (f+1)*W]> + shift, lo, hi) )
+ *   p_f(u)  = sum_{k < n_terms} coef[f*n_terms + k] * phi_k(u),  phi_k = u^k or T_k(u)
+ *
+ * replaces sphere_distance_torch + gegenbauer_polynomial + the term loop of
+ *   kernel_utils/kernels_sphere.py:102-139 (Matern), :188-224 (heat), :343-384 (integrated Matern),
+ *   :443-472 / :551-614 (circle; Jacobi theta_3 series), kernel_utils/kernels_torus.py:61-90,142-177
+ *   (product over circles), kernel_utils/kernels_so.py:305-362 and :149-177 with dim = 3
+ *   (W = 9, scale = 0.5, shift = -0.5, clamp +-(1-1e-8)).
+ * The hyper-parameter dependence lives entirely in coef (host side, torch autograd).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int n_factors;    /* F >= 1 */
+  int factor_width; /* W >= 1; rows of x1/x2 are F*W wide */
+  int n_terms;      /* T in [1, MGB_MAX_TERMS] */
+  int basis;        /* MGB_BASIS_* */
+  double scale, shift, lo, hi;
+} mgb_series_desc;
+
+int mgb_series_gram_fwd(const mgb_series_desc* desc, const double* x1, long long m, long long ld1,
+                        const double* x2, long long n, long long ld2, const double* coef,
+                        double* K, long long ldk, void* stream);
+
+/* Backward of the above for L = sum(K * G):
+ *   gcoef[f*T + k] += dL/dcoef (accumulated with atomics: caller zeroes it),
+ *   gx1 (m x F*W, ld = F*W) = dL/dx1 (overwritten; may be NULL), gx2 likewise (may be NULL).
+ * Pairs where the clamp is active get zero input gradient, as torch.clamp does in the reference
+ * (Riemannian_utils/sphere_utils_torch.py:57).  G is addressed as G[i*ldg_row + j*ldg_col]. */
+int mgb_series_gram_bwd(const mgb_series_desc* desc, const double* x1, long long m, long long ld1,
+                        const double* x2, long long n, long long ld2, const double* coef,
+                        const double* G, long long ldg_row, long long ldg_col,
+                        double* gcoef, double* gx1, double* gx2, void* stream);
+
+/* Second-order support for trust-region Hessian-vector products (pymanopt_addons/tools/autodiff/
+ * _pytorch.py:92-116): same contraction as gx1 of the backward but with the k-th derivative of p_f,
+ *   out1[i][:] = sum_j G[i][j] * p^(order)(u_ij) * mask_ij * scale^order * x2[j][:]   (n_factors == 1)
+ * order in {1, 2}.  out2 is the x2-side sum (may be NULL). */
+int mgb_series_gram_dx(const mgb_series_desc* desc, int order, const double* x1, long long m, long long ld1,
+                       const double* x2, long long n, long long ld2, const double* coef,
+                       const double* G, long long ldg_row, long long ldg_col,
+                       double* out1, double* out2, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Quadrature Gram matrices.
+ *
+ * Hyperbolic space H^dim in Lorentz coordinates (rows dim+1 wide), dim in {1,2,3}:
+ *   d_ij = 2 asinh( sqrt(max(0, <D,D>_L) + 1e-8) / 2 ),  D = x1_i - x2_j
+ *            (Riemannian_utils/hyperbolic_utils_torch.py:11-60)
+ *   K_ij = sum_{a < Pt} tcoef[a] * heat(d_ij, tval[a])
+ *   heat(d, t) = exp(-d^2/(4t))                                       dim 1 (kernels_hyperbolic.py:258-275)
+ *              = exp(-d^2/(4t)) (d+1e-8)/sinh(d+1e-8)                 dim 3 (:306-330)
+ *              = trapz_s  s exp(-s^2/(4t)) / sqrt(cosh s - cosh d),  s = s0 + k*ds + d, k < Ps   dim 2 (:281-304)
+ * The integrated Matern kernel (:336-389) is this with tval = its t grid and
+ * tcoef[a] = trapezoid weight * t^(nu-1) exp(-2 nu t / kappa^2) / normaliser (host side);
+ * the heat kernel (:58-88) is the same with Pt = 1, tval[0] = kappa^2 / 2.
+ * mgb_hyperbolic_heat_nodes writes heat(dist[e], tval[a]) to out[e*Pt + a] for given distances
+ * (used for the normaliser at d = 0 and for tests).
+ * ------------------------------------------------------------------------------------------------ */
+int mgb_hyperbolic_gram_fwd(int dim, const double* x1, long long m, long long ld1, const double* x2,
+                            long long n, long long ld2, const double* tval, const double* tcoef, int Pt,
+                            double s0, double ds, int Ps, double* K, long long ldk, void* stream);
+/* gtcoef[a] += sum_ij G_ij heat(d_ij, tval[a]) (caller zeroes) */
+int mgb_hyperbolic_gram_bwd_coef(int dim, const double* x1, long long m, long long ld1, const double* x2,
+                                 long long n, long long ld2, const double* tval, int Pt, double s0, double ds,
+                                 int Ps, const double* G, long long ldg, double* gtcoef, void* stream);
+int mgb_hyperbolic_heat_nodes(int dim, const double* dist, long long count, const double* tval, int Pt,
+                              double s0, double ds, int Ps, double* out, void* stream);
+
+/* SPD(2) in Mandel coordinates (rows 3 wide: s11, s22, sqrt2*s12)
+ *   (Riemannian_utils/spd_utils_torch.py:336-371; kernel_utils/kernels_spd.py:200-289 and :65-136)
+ *   H1 >= H2 = log singular values of A_i B_j^{-1}; A, B = the matrices (use_cholesky = 0, Matern :230-243)
+ *   or their lower Cholesky factors (use_cholesky = 1, heat kernel :90-102); Delta = H1-H2, r2 = H1^2+H2^2
+ *   K_ij = sum_a tcoef[a] exp(-r2 * rscale[a]) * sum_b bw[b] (2 b_b + Delta) exp(-b_b (b_b + Delta) * bscale[a])
+ *                                                     / sqrt(sinh b_b * sinh(b_b + Delta))
+ *   Matern: rscale[a] = 1/(4 t_a), bscale[a] = 1/(2 t_a); heat: Pt = 1, rscale = 1/(2 k^2), bscale = 1/k^2. */
+int mgb_spd2_gram_fwd(int use_cholesky, const double* x1, long long m, long long ld1, const double* x2,
+                      long long n, long long ld2, const double* tcoef, const double* rscale,
+                      const double* bscale, int Pt, const double* bval, const double* bw, int Pb,
+                      double* K, long long ldk, void* stream);
+int mgb_spd2_gram_bwd_coef(int use_cholesky, const double* x1, long long m, long long ld1, const double* x2,
+                           long long n, long long ld2, const double* rscale, const double* bscale, int Pt,
+                           const double* bval, const double* bw, int Pb, const double* G, long long ldg,
+                           double* gtcoef, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Exact-GP posterior for a block of candidates (gpytorch ExactGP prediction + botorch call sites:
+ * examples/bo_manifolds_benchmark_examples/bo_sphere.py:215-233,265;
+ * manifold_optimization/manifold_optimize.py:195,254,337)
+ *
+ *   Kc    = outputscale * K(Xc, Xtrain)                      (m x n, written by the caller with
+ *                                                             mgb_series_gram_fwd etc. into Kc, ld = ldk)
+ *   mean_c = mean_const + sum_j Kc[c][j] alpha[j]
+ *   var_c  = kss[c] - sum_i ( sum_{j<=i} Rinv[i][j] Kc[c][j] )^2,   Rinv = L^{-1}, L = chol(s K + noise I)
+ *
+ * mgb_posterior_pack builds, once per GP fit, the packed factor: lower triangle of Rinv padded with zeros
+ * to (n+1 rounded up to 128) x (n rounded up to 16) doubles, row n holding alpha (so the mean falls out of
+ * the same tiles).  mgb_posterior_reduce is the fused triangular product + square-sum + mean on FP64
+ * tensor-core DMMA tiles; Kc is consumed, V = Rinv Kc^T is never written to memory.
+ * Kc must be 16-byte aligned with an even ldk >= n.  kss: m values (k(x_c, x_c) * outputscale).
+ * ------------------------------------------------------------------------------------------------ */
+long long mgb_posterior_pack_bytes(long long n);
+int mgb_posterior_pack(const double* Rinv, long long n, long long ldr, const double* alpha, double* packed,
+                       void* stream);
+int mgb_posterior_reduce(const double* Kc, long long m, long long n, long long ldk, const double* packed,
+                         const double* kss, double mean_const, double* mean, double* var, void* stream);
+/* scratch mgb_series_posterior needs for `chunk` candidates x n training points (bytes) */
+long long mgb_posterior_workspace_bytes(long long chunk, long long n);
+
+/* Whole posterior for a series kernel, candidates in device memory, processed `chunk` rows at a time
+ * through `workspace` (16-byte aligned, >= mgb_posterior_workspace_bytes(chunk, n)): Gram chunk -> reduce.
+ * coef already contains outputscale / normaliser.  kss_value: k(x, x) * outputscale (the kernels are
+ * stationary and normalised: one number). */
+int mgb_series_posterior(const mgb_series_desc* desc, const double* xc, long long m, long long ldc,
+                         const double* xtrain, long long n, long long ldt, const double* coef,
+                         const double* packed, double kss_value, double mean_const, double* mean,
+                         double* var, void* workspace, long long workspace_bytes, long long chunk,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer entry points (the reference-facing calls: numpy / CPU tensors in, numpy out).
+ * ------------------------------------------------------------------------------------------------ */
+int mgb_series_gram_host(const mgb_series_desc* desc, const double* x1, long long m, const double* x2,
+                         long long n, const double* coef, double* K, int device);
+/* Rinv: n x n row-major (lower triangle used), alpha: n.  Candidates stream through pinned staging
+ * buffers in blocks of `chunk` rows; copies overlap the kernels on a second stream. */
+int mgb_series_posterior_host(const mgb_series_desc* desc, const double* xc, long long m,
+                              const double* xtrain, long long n, const double* coef, const double* Rinv,
+                              const double* alpha, double kss_value, double mean_const, double* mean,
+                              double* var, long long chunk, int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * Measurement helpers (bench.py): register-resident FP64 peak micro-benchmarks, result in TFLOP/s.
+ * kind 0 = DFMA chains, 1 = DMMA m8n8k4 chains.  Synchronises.
+ * ------------------------------------------------------------------------------------------------ */
+int mgb_fp64_peak(int kind, int repeats, double* tflops, double* elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGB_H_ */

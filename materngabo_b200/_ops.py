@@ -1,0 +1,331 @@
+"""torch.autograd bindings of the C-ABI kernels (device pointers + current stream via ctypes).
+
+Autograd structure: the device ops are functions of (x1, x2, w) where ``w`` is the tiny coefficient /
+node-weight tensor computed by ``_weights`` from the hyper-parameters.  ``backward`` returns dL/dw (a few
+dozen numbers reduced on the device) and dL/dx1, dL/dx2; torch autograd carries dL/dw on to
+``raw_lengthscale`` / ``raw_nu``.  First-order input gradients are themselves differentiable for
+single-factor series kernels (``SeriesGramGradX``), which is what the trust-region Hessian-vector products
+of the reference need (pymanopt_addons/tools/autodiff/_pytorch.py:92-116).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+F64 = torch.float64
+
+
+@dataclass(frozen=True)
+class SeriesSpec:
+    n_factors: int
+    factor_width: int
+    basis: int
+    scale: float = 1.0
+    shift: float = 0.0
+    lo: float = -1.0
+    hi: float = 1.0
+
+    def desc(self, n_terms: int) -> _lib.SeriesDesc:
+        return _lib.SeriesDesc(self.n_factors, self.factor_width, n_terms, self.basis,
+                               self.scale, self.shift, self.lo, self.hi)
+
+
+def _c2d(t: torch.Tensor) -> torch.Tensor:
+    t = t.contiguous()
+    assert t.dim() == 2
+    return t
+
+
+# --------------------------------------------------------------------------------------------------
+# spectral series
+# --------------------------------------------------------------------------------------------------
+def _series_fwd_raw(spec, x1, x2, coef):
+    lib = _lib.load()
+    m, n = x1.shape[0], x2.shape[0]
+    k = torch.empty((m, n), dtype=F64, device=x1.device)
+    d = spec.desc(coef.shape[-1])
+    with torch.cuda.device(x1.device):
+        rc = lib.mgb_series_gram_fwd(C.byref(d), _lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0),
+                                     _lib.ptr(coef), _lib.ptr(k), max(n, 1), _lib.stream_ptr(x1.device))
+    _lib.check(rc, "mgb_series_gram_fwd")
+    return k
+
+
+def _series_bwd_raw(spec, x1, x2, coef, g, want_coef, want_x1, want_x2):
+    lib = _lib.load()
+    m, n = x1.shape[0], x2.shape[0]
+    dwidth = spec.n_factors * spec.factor_width
+    gcoef = torch.zeros_like(coef) if want_coef else None
+    gx1 = torch.empty((m, dwidth), dtype=F64, device=x1.device) if want_x1 else None
+    gx2 = torch.empty((n, dwidth), dtype=F64, device=x1.device) if want_x2 else None
+    d = spec.desc(coef.shape[-1])
+    with torch.cuda.device(x1.device):
+        rc = lib.mgb_series_gram_bwd(C.byref(d), _lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0),
+                                     _lib.ptr(coef), _lib.ptr(g), g.stride(0), g.stride(1), _lib.ptr(gcoef),
+                                     _lib.ptr(gx1), _lib.ptr(gx2), _lib.stream_ptr(x1.device))
+    _lib.check(rc, "mgb_series_gram_bwd")
+    return gcoef, gx1, gx2
+
+
+def _series_dx_raw(spec, order, x1, x2, coef, g, want1, want2):
+    lib = _lib.load()
+    m, n = x1.shape[0], x2.shape[0]
+    dwidth = spec.n_factors * spec.factor_width
+    o1 = torch.empty((m, dwidth), dtype=F64, device=x1.device) if want1 else None
+    o2 = torch.empty((n, dwidth), dtype=F64, device=x1.device) if want2 else None
+    d = spec.desc(coef.shape[-1])
+    with torch.cuda.device(x1.device):
+        rc = lib.mgb_series_gram_dx(C.byref(d), order, _lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0),
+                                    _lib.ptr(coef), _lib.ptr(g), g.stride(0), g.stride(1), _lib.ptr(o1), _lib.ptr(o2),
+                                    _lib.stream_ptr(x1.device))
+    _lib.check(rc, "mgb_series_gram_dx")
+    return o1, o2
+
+
+class SeriesGramGradX(torch.autograd.Function):
+    """(x1, x2, coef, G) -> (dL/dcoef, dL/dx1, dL/dx2) of L = sum(K * G); differentiable again with respect
+    to x1 and G (single-factor kernels) so that Hessian-vector products through the kernel work."""
+
+    @staticmethod
+    def forward(ctx, spec, x1, x2, coef, g, want_coef, want_x1, want_x2):
+        gcoef, gx1, gx2 = _series_bwd_raw(spec, x1, x2, coef, g, want_coef, want_x1, want_x2)
+        ctx.spec = spec
+        ctx.save_for_backward(x1, x2, coef, g)
+        ctx.mark_non_differentiable(*[t for t in (gcoef, gx2) if t is not None])
+        outs = tuple(t if t is not None else torch.zeros((), dtype=F64, device=x1.device)
+                     for t in (gcoef, gx1, gx2))
+        return outs
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _v_coef, v1, _v2):
+        spec = ctx.spec
+        x1, x2, coef, g = ctx.saved_tensors
+        if spec.n_factors != 1:
+            raise NotImplementedError("second-order input gradients are implemented for single-factor kernels")
+        if v1 is None or v1.dim() != 2:
+            return (None,) * 8
+        v1 = v1.contiguous()
+        proj = v1 @ x2.t()                                  # (x2_j . v_i)
+        # d/dG_ij = p'(u_ij) mask scale (x2_j . v_i): first-derivative weights come from the dx kernel with
+        # G = one-hot is wasteful; instead use the identity  sum_k v_ik gx1_ik = sum_j G_ij p' s (x2_j.v_i)
+        # and differentiate it with respect to G through a derivative-Gram evaluated by the order-1 kernel.
+        gG = _derivative_gram(spec, x1, x2, coef) * proj if ctx.needs_input_grad[4] else None
+        gx1 = None
+        if ctx.needs_input_grad[1]:
+            gx1, _ = _series_dx_raw(spec, 2, x1, x2, coef, (g * proj).contiguous(), True, False)
+        return None, gx1, None, None, gG, None, None, None
+
+
+def _derivative_gram(spec, x1, x2, coef):
+    """Matrix p'(u_ij) * scale * [lo <= raw u <= hi] built from the order-1 contraction kernel applied to the
+    canonical basis of the (small) x2 block: cheap for the acquisition sizes (n = training points)."""
+    # one column at a time would be n launches; instead exploit linearity in x2 rows: for D-wide rows the
+    # contraction out1[i,:] = sum_j G_ij d_ij x2_j.  Choosing G = diag-selector is O(n) launches, so we use the
+    # closed form on the host instead: d_ij via autograd-free polynomial derivative in torch (n is small).
+    u_raw = (x1 @ x2.t()) * spec.scale + spec.shift
+    u = u_raw.clamp(spec.lo, spec.hi)
+    c = coef.reshape(-1)
+    t = c.shape[0]
+    if spec.basis == _lib.BASIS_MONOMIAL:
+        d = torch.zeros_like(u)
+        for k in range(t - 1, 0, -1):
+            d = d * u + k * c[k]
+    else:
+        # sum_k c_k T_k'(u) = sum_k c_k k U_{k-1}(u)
+        d = torch.zeros_like(u)
+        u_prev, u_cur = torch.zeros_like(u), torch.ones_like(u)  # U_{-1}, U_0
+        for k in range(1, t):
+            d = d + c[k] * k * u_cur
+            u_prev, u_cur = u_cur, 2 * u * u_cur - u_prev
+    inside = (u_raw >= spec.lo) & (u_raw <= spec.hi)
+    return d * spec.scale * inside
+
+
+class SeriesGram(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, x1, x2, coef):
+        ctx.spec = spec
+        ctx.save_for_backward(x1, x2, coef)
+        return _series_fwd_raw(spec, x1, x2, coef)
+
+    @staticmethod
+    def backward(ctx, g):
+        spec = ctx.spec
+        x1, x2, coef = ctx.saved_tensors
+        need_x1, need_x2, need_c = ctx.needs_input_grad[1], ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        if not (need_x1 or need_x2 or need_c):
+            return None, None, None, None
+        if not g.is_contiguous() and not (g.dim() == 2 and g.stride(1) in (0, 1)):
+            g = g.contiguous()
+        if g.stride(0) == 0 or g.stride(1) == 0:
+            g = g.contiguous()
+        gcoef, gx1, gx2 = SeriesGramGradX.apply(spec, x1, x2, coef, g, need_c, need_x1, need_x2)
+        return None, (gx1 if need_x1 else None), (gx2 if need_x2 else None), (gcoef if need_c else None)
+
+
+def series_gram(spec: SeriesSpec, x1: torch.Tensor, x2: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
+    """K (m x n) for 2-D inputs."""
+    _lib.require_cuda_f64(x1, x2, coef)
+    return SeriesGram.apply(spec, _c2d(x1), _c2d(x2), coef.contiguous())
+
+
+# --------------------------------------------------------------------------------------------------
+# quadrature kernels
+# --------------------------------------------------------------------------------------------------
+class HyperbolicGram(torch.autograd.Function):
+    """K = sum_a tcoef[a] heat(d_ij, tval[a]); differentiable with respect to tcoef (hyper-parameters)."""
+
+    @staticmethod
+    def forward(ctx, dim, x1, x2, tval, tcoef, s0, ds, ps):
+        lib = _lib.load()
+        m, n = x1.shape[0], x2.shape[0]
+        k = torch.empty((m, n), dtype=F64, device=x1.device)
+        with torch.cuda.device(x1.device):
+            rc = lib.mgb_hyperbolic_gram_fwd(dim, _lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0),
+                                             _lib.ptr(tval), _lib.ptr(tcoef), tval.shape[0], s0, ds, ps,
+                                             _lib.ptr(k), max(n, 1), _lib.stream_ptr(x1.device))
+        _lib.check(rc, "mgb_hyperbolic_gram_fwd")
+        ctx.args = (dim, s0, ds, ps)
+        ctx.save_for_backward(x1, x2, tval)
+        return k
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise NotImplementedError("input gradients of the hyperbolic quadrature kernels are not implemented yet")
+        if not ctx.needs_input_grad[4]:
+            return (None,) * 8
+        lib = _lib.load()
+        dim, s0, ds, ps = ctx.args
+        x1, x2, tval = ctx.saved_tensors
+        g = g.contiguous()
+        out = torch.zeros_like(tval)
+        with torch.cuda.device(x1.device):
+            rc = lib.mgb_hyperbolic_gram_bwd_coef(dim, _lib.ptr(x1), x1.shape[0], x1.stride(0), _lib.ptr(x2),
+                                                  x2.shape[0], x2.stride(0), _lib.ptr(tval), tval.shape[0], s0, ds,
+                                                  ps, _lib.ptr(g), g.stride(0), _lib.ptr(out),
+                                                  _lib.stream_ptr(x1.device))
+        _lib.check(rc, "mgb_hyperbolic_gram_bwd_coef")
+        return None, None, None, None, out, None, None, None
+
+
+def hyperbolic_gram(dim, x1, x2, tval, tcoef, s0, ds, ps):
+    _lib.require_cuda_f64(x1, x2, tval, tcoef)
+    return HyperbolicGram.apply(dim, _c2d(x1), _c2d(x2), tval.contiguous(), tcoef.contiguous(), float(s0), float(ds), int(ps))
+
+
+def hyperbolic_heat_nodes(dim, dist, tval, s0, ds, ps):
+    """heat(dist[e], tval[a]) -> (E, Pt) tensor (no autograd)."""
+    _lib.require_cuda_f64(dist, tval)
+    lib = _lib.load()
+    dist = dist.contiguous().reshape(-1)
+    out = torch.empty((dist.shape[0], tval.shape[0]), dtype=F64, device=dist.device)
+    with torch.cuda.device(dist.device):
+        rc = lib.mgb_hyperbolic_heat_nodes(dim, _lib.ptr(dist), dist.shape[0], _lib.ptr(tval.contiguous()), tval.shape[0],
+                                           float(s0), float(ds), int(ps), _lib.ptr(out), _lib.stream_ptr(dist.device))
+    _lib.check(rc, "mgb_hyperbolic_heat_nodes")
+    return out
+
+
+class Spd2Gram(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, use_chol, x1, x2, tcoef, rscale, bscale, bval, bw):
+        lib = _lib.load()
+        m, n = x1.shape[0], x2.shape[0]
+        k = torch.empty((m, n), dtype=F64, device=x1.device)
+        with torch.cuda.device(x1.device):
+            rc = lib.mgb_spd2_gram_fwd(use_chol, _lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0),
+                                       _lib.ptr(tcoef), _lib.ptr(rscale), _lib.ptr(bscale), tcoef.shape[0],
+                                       _lib.ptr(bval), _lib.ptr(bw), bval.shape[0], _lib.ptr(k), max(n, 1),
+                                       _lib.stream_ptr(x1.device))
+        _lib.check(rc, "mgb_spd2_gram_fwd")
+        ctx.use_chol = use_chol
+        ctx.save_for_backward(x1, x2, rscale, bscale, bval, bw)
+        return k
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise NotImplementedError("input gradients of the SPD quadrature kernels are not implemented yet")
+        if any(ctx.needs_input_grad[i] for i in (4, 5)):
+            raise NotImplementedError("gradient with respect to the SPD node scales")
+        if not ctx.needs_input_grad[3]:
+            return (None,) * 8
+        lib = _lib.load()
+        x1, x2, rscale, bscale, bval, bw = ctx.saved_tensors
+        g = g.contiguous()
+        out = torch.zeros_like(rscale)
+        with torch.cuda.device(x1.device):
+            rc = lib.mgb_spd2_gram_bwd_coef(ctx.use_chol, _lib.ptr(x1), x1.shape[0], x1.stride(0), _lib.ptr(x2),
+                                            x2.shape[0], x2.stride(0), _lib.ptr(rscale), _lib.ptr(bscale),
+                                            rscale.shape[0], _lib.ptr(bval), _lib.ptr(bw), bval.shape[0], _lib.ptr(g),
+                                            g.stride(0), _lib.ptr(out), _lib.stream_ptr(x1.device))
+        _lib.check(rc, "mgb_spd2_gram_bwd_coef")
+        return None, None, None, out, None, None, None, None
+
+
+def spd2_gram(use_chol, x1, x2, tcoef, rscale, bscale, bval, bw):
+    _lib.require_cuda_f64(x1, x2, tcoef, rscale, bscale, bval, bw)
+    return Spd2Gram.apply(int(use_chol), _c2d(x1), _c2d(x2), tcoef.contiguous(), rscale.contiguous(),
+                          bscale.contiguous(), bval.contiguous(), bw.contiguous())
+
+
+# --------------------------------------------------------------------------------------------------
+# pair-batch plumbing shared by the Kernel.forward overrides
+# --------------------------------------------------------------------------------------------------
+def _is_broadcast_of_2d(t: torch.Tensor) -> bool:
+    return t.dim() > 2 and all(s == 0 or sz == 1 for s, sz in zip(t.stride()[:-2], t.shape[:-2]))
+
+
+def pairwise(fn2d, x1: torch.Tensor, x2: torch.Tensor, diag: bool = False) -> torch.Tensor:
+    """Apply a 2-D Gram function over gpytorch-style batch dimensions.
+
+    * no batch dims: one launch;
+    * x2 a broadcast of one N x D block (botorch's posterior layout b x q x D against the expanded training
+      inputs): one launch on (b*q) x D against N x D;
+    * otherwise one launch per batch element.
+    ``diag=True`` returns the per-row kernel k(x1_i, x2_i) (shape ... x N)."""
+    if diag:
+        if x1.shape != x2.shape:
+            raise RuntimeError("diag=True requires x1 and x2 of the same shape")
+        flat1 = x1.reshape(-1, 1, x1.shape[-1])
+        flat2 = x2.reshape(-1, 1, x2.shape[-1])
+        rows = flat1.shape[0]
+        out = torch.empty(rows, dtype=F64, device=x1.device)
+        blk = 2048
+        pieces = []
+        for s in range(0, rows, blk):
+            k = fn2d(flat1[s:s + blk, 0], flat2[s:s + blk, 0])
+            pieces.append(torch.diagonal(k))
+        out = torch.cat(pieces) if pieces else out
+        return out.reshape(x1.shape[:-1])
+    if x1.dim() == 2 and x2.dim() == 2:
+        return fn2d(x1, x2)
+    if x1.dim() < x2.dim():
+        x1 = x1.expand(*x2.shape[:-2], *x1.shape[-2:])
+    elif x2.dim() < x1.dim():
+        x2 = x2.expand(*x1.shape[:-2], *x2.shape[-2:])
+    batch = torch.broadcast_shapes(x1.shape[:-2], x2.shape[:-2])
+    x1 = x1.expand(*batch, *x1.shape[-2:])
+    x2 = x2.expand(*batch, *x2.shape[-2:])
+    m, n = x1.shape[-2], x2.shape[-2]
+    if _is_broadcast_of_2d(x2):
+        base = x2[(0,) * len(batch)]
+        k = fn2d(x1.reshape(-1, x1.shape[-1]), base)
+        return k.reshape(*batch, m, n)
+    if _is_broadcast_of_2d(x1):
+        base = x1[(0,) * len(batch)]
+        k = fn2d(base, x2.reshape(-1, x2.shape[-1]))          # m x (B*n)
+        return k.reshape(m, *batch, n).movedim(0, -2)
+    f1 = x1.reshape(-1, m, x1.shape[-1])
+    f2 = x2.reshape(-1, n, x2.shape[-1])
+    out = torch.stack([fn2d(f1[b], f2[b]) for b in range(f1.shape[0])]) if f1.shape[0] else \
+        torch.empty((0, m, n), dtype=F64, device=x1.device)
+    return out.reshape(*batch, m, n)

@@ -1,0 +1,266 @@
+"""Host-side (torch, float64, autograd) computation of the tiny hyper-parameter-dependent vectors the CUDA
+kernels consume: series coefficients and quadrature node weights.
+
+Every reference kernel is ``K_ij = sum_n w_n(kappa, nu) * phi_n(pair scalar)``; all hyper-parameter
+dependence lives in ``w`` (a few dozen numbers), so lengthscale / smoothness gradients come back from the
+device as ``dL/dw`` and flow through the formulas below by ordinary torch autograd.  The formulas mirror
+the reference line by line (cited per function, paths relative to /root/reference/BoManifolds),
+including its ``.item()`` detachments of the quadrature grids and the dtype of its constants.
+"""
+from __future__ import annotations
+
+import math
+from fractions import Fraction
+from functools import lru_cache
+
+import numpy as np
+import torch
+
+from . import _lib
+
+F64 = torch.float64
+MONOMIAL_MAX_TERMS = 12  # Horner in the monomial basis up to here (error <= ~1e-12 of max|K|), Chebyshev beyond
+
+
+# --------------------------------------------------------------------------------------------------
+# basis-change tables (pure numbers, cached)
+# --------------------------------------------------------------------------------------------------
+def gegenbauer_monomial_row(n: int, alpha: float):
+    """Coefficients of u^k in C_n^alpha(u), the same float64 numbers the reference's power sum uses
+    (math_utils/gegenbauer_polynomials.py:31-33).  math.gamma(0) raises ValueError for alpha = 0."""
+    row = [0.0] * (n + 1)
+    ga = math.gamma(alpha)
+    for i in range(n // 2 + 1):
+        coef = math.gamma(n - i + alpha) / (ga * math.factorial(i) * math.factorial(n - 2 * i))
+        row[n - 2 * i] = math.pow(-1, i) * coef * math.pow(2.0, n - 2 * i)
+    return row
+
+
+@lru_cache(maxsize=None)
+def gegenbauer_to_monomial(terms: int, alpha: float) -> np.ndarray:
+    m = np.zeros((terms, terms))
+    for n in range(terms):
+        m[n, :n + 1] = gegenbauer_monomial_row(n, alpha)
+    return m
+
+
+@lru_cache(maxsize=None)
+def gegenbauer_to_chebyshev(terms: int, two_alpha: int) -> np.ndarray:
+    """C_n^alpha(cos t) = sum_j (alpha)_j (alpha)_{n-j} / (j! (n-j)!) cos((n-2j) t), exact rationals."""
+    alpha = Fraction(two_alpha, 2)
+    math.gamma(float(alpha))  # same ValueError as the reference for S^1
+
+    def poch(a, k):
+        r = Fraction(1)
+        for i in range(k):
+            r *= a + i
+        return r
+
+    m = np.zeros((terms, terms))
+    for n in range(terms):
+        acc = [Fraction(0)] * (n + 1)
+        for j in range(n + 1):
+            acc[abs(n - 2 * j)] += poch(alpha, j) * poch(alpha, n - j) / (math.factorial(j) * math.factorial(n - j))
+        m[n, :n + 1] = [float(v) for v in acc]
+    return m
+
+
+@lru_cache(maxsize=None)
+def chebyshev_to_monomial(terms: int) -> np.ndarray:
+    """Integer coefficients of T_m(u)."""
+    rows = [[1], [0, 1]]
+    for m in range(2, terms):
+        prev, prev2 = rows[m - 1], rows[m - 2]
+        cur = [0] * (m + 1)
+        for k, v in enumerate(prev):
+            cur[k + 1] += 2 * v
+        for k, v in enumerate(prev2):
+            cur[k] -= v
+        rows.append(cur)
+    out = np.zeros((terms, terms))
+    for m in range(terms):
+        out[m, :m + 1] = rows[m]
+    return out
+
+
+def _t(x, like):
+    return torch.as_tensor(x, dtype=F64, device=like.device)
+
+
+def choose_basis(terms: int) -> int:
+    return _lib.BASIS_MONOMIAL if terms <= MONOMIAL_MAX_TERMS else _lib.BASIS_CHEBYSHEV
+
+
+def _logspace(lo, hi, steps, device):
+    """The reference builds its grids with torch.logspace on the CPU in the DEFAULT dtype and then moves
+    them (e.g. kernels_hyperbolic.py:368-369): same here, so the node values agree bit for bit."""
+    return torch.logspace(lo, hi, steps).to(device=device, dtype=F64)
+
+
+def trapz_weights(nodes: torch.Tensor) -> torch.Tensor:
+    """w with trapz(f, nodes) == sum(w * f)."""
+    d = nodes[1:] - nodes[:-1]
+    w = torch.zeros_like(nodes)
+    w[:-1] += 0.5 * d
+    w[1:] += 0.5 * d
+    return w
+
+
+# --------------------------------------------------------------------------------------------------
+# sphere S^d  (kernels_sphere.py)
+# --------------------------------------------------------------------------------------------------
+def sphere_constants(dim: int, terms: int):
+    """cst_nd and zero_gpolynomials as Python lists of 1-element tensors IN THE DEFAULT DTYPE, exactly as
+    kernels_sphere.py:84,87 / :387-406 build them (float32-rounded unless the caller set float64)."""
+    from .math_utils import gegenbauer_polynomial
+
+    alpha = (dim - 1.0) / 2.0
+    zero_g = [gegenbauer_polynomial(n, alpha, torch.ones(1)) for n in range(terms)]
+    cst = []
+    for n in range(terms):
+        dn = (2 * n + dim - 1) * math.gamma(n + dim - 1) / math.gamma(dim) / math.gamma(n + 1)
+        cst.append(dn * math.gamma(alpha) / (2 * math.pow(math.pi, alpha) * zero_g[n]))
+    return cst, zero_g
+
+
+def _sphere_finish(a: torch.Tensor, zero_g: torch.Tensor, dim: int):
+    """a_n (Gegenbauer weights) -> normalised device coefficients + basis."""
+    terms = a.shape[-1]
+    w = a / (a * zero_g).sum()
+    basis = choose_basis(terms)
+    if basis == _lib.BASIS_MONOMIAL:
+        mat = gegenbauer_to_monomial(terms, (dim - 1.0) / 2.0)
+    else:
+        mat = gegenbauer_to_chebyshev(terms, dim - 1)
+    return (w.reshape(1, terms) @ _t(mat, w)).contiguous(), basis
+
+
+def sphere_matern_coef(lengthscale, nu, dim, cst, zero_g):
+    """kernels_sphere.py:126-139."""
+    ls, nu = lengthscale.reshape(()).to(F64), nu.reshape(()).to(F64)
+    terms = len(cst)
+    n = torch.arange(terms, dtype=F64, device=ls.device)
+    base = 2 * nu / ls ** 2
+    e0 = torch.pow(base, -(nu + dim / 2))
+    e = torch.pow(base + n * (n + dim - 1), -(nu + dim / 2)) / e0
+    c = torch.cat([v.reshape(1) for v in cst]).to(device=ls.device, dtype=F64)
+    g = torch.cat([v.reshape(1) for v in zero_g]).to(device=ls.device, dtype=F64)
+    return _sphere_finish(e * c, g, dim)
+
+
+def sphere_gaussian_coef(lengthscale, dim, cst, zero_g):
+    """kernels_sphere.py:212-224."""
+    ls = lengthscale.reshape(()).to(F64)
+    terms = len(cst)
+    n = torch.arange(terms, dtype=F64, device=ls.device)
+    e = torch.exp(-ls ** 2 / 2.0 * n * (n + dim - 1))
+    c = torch.cat([v.reshape(1) for v in cst]).to(device=ls.device, dtype=F64)
+    g = torch.cat([v.reshape(1) for v in zero_g]).to(device=ls.device, dtype=F64)
+    return _sphere_finish(e * c, g, dim)
+
+
+def sphere_integrated_matern_coef(lengthscale, nu, dim, cst, zero_g, nb_points):
+    """kernels_sphere.py:318-384: the t-trapezoid of the heat series collapses into the series weights."""
+    ls, nu = lengthscale.reshape(()).to(F64), nu.reshape(()).to(F64)
+    terms = len(cst)
+    shift = torch.log10(ls).item()
+    t = _logspace(-4 + shift, 3 + shift, nb_points, ls.device)
+    wt = trapz_weights(t)
+    n = torch.arange(terms, dtype=F64, device=ls.device)
+    front = wt * torch.pow(t, nu + dim / 2 - 1.0) * torch.exp(-2.0 * nu / ls ** 2 * t)      # (P,)
+    heat = torch.exp(-t.unsqueeze(-1) * (n * (n + dim - 1)).unsqueeze(0))                    # (P, T)
+    c = torch.cat([v.reshape(1) for v in cst]).to(device=ls.device, dtype=F64)
+    g = torch.cat([v.reshape(1) for v in zero_g]).to(device=ls.device, dtype=F64)
+    return _sphere_finish((front.unsqueeze(-1) * heat).sum(0) * c, g, dim)
+
+
+# --------------------------------------------------------------------------------------------------
+# circle S^1 / torus  (kernels_sphere.py:443-472, 551-614; kernels_torus.py)
+# --------------------------------------------------------------------------------------------------
+THETA3_TERMS = 200  # hard-wired in the reference (math_utils/jacobi_theta_functions.py:16)
+_TRUNC = 1e-20      # cosine terms below this fraction of the constant term cannot change a float64 result
+
+
+def _truncate(c: torch.Tensor) -> int:
+    mag = (c.detach().abs() / c.detach().abs()[0]).cpu()
+    keep = torch.nonzero(mag > _TRUNC).max().item() + 1
+    return max(int(keep), 2)
+
+
+def circle_gaussian_coef(lengthscale):
+    """theta_3(phi/2, q) / theta_3(0, q), q = exp(-2 pi^2 kappa^2)  ->  Chebyshev series in cos(phi):
+    c_0 = 1, c_n = 2 q^(n^2)."""
+    ls = lengthscale.reshape(()).to(F64)
+    q = torch.exp(-2 * math.pi ** 2 * ls ** 2)
+    n = torch.arange(0, THETA3_TERMS + 1, dtype=F64, device=ls.device)
+    c = 2.0 * torch.pow(q, n ** 2)
+    c = torch.cat([torch.ones(1, dtype=F64, device=ls.device), c[1:]])
+    c = c / c.sum()
+    return c[:_truncate(c)]
+
+
+def circle_integrated_matern_coef(lengthscale, nu, nb_points):
+    """trapz_t t^(nu-1/2) exp(-2 nu t/kappa^2) theta_3(phi/2, exp(-4 pi^2 t)), normalised at phi = 0."""
+    ls, nu = lengthscale.reshape(()).to(F64), nu.reshape(()).to(F64)
+    shift = torch.log10(ls).item()
+    t = _logspace(-3 + shift, 1 + shift, nb_points, ls.device)
+    wt = trapz_weights(t)
+    front = wt * torch.pow(t, nu + 0.5 - 1.0) * torch.exp(-2.0 * nu / ls ** 2 * t)          # (P,)
+    n = torch.arange(0, THETA3_TERMS + 1, dtype=F64, device=ls.device)
+    qn = torch.exp(-4 * math.pi ** 2 * t.unsqueeze(-1) * (n ** 2).unsqueeze(0))              # (P, 201)
+    c = (front.unsqueeze(-1) * qn).sum(0)
+    c = torch.cat([c[:1], 2.0 * c[1:]])
+    c = c / c.sum()
+    return c[:_truncate(c)]
+
+
+def stack_factor_coefs(coefs):
+    """Per-factor Chebyshev coefficient vectors -> zero-padded (F, T) matrix."""
+    t = max(int(c.shape[0]) for c in coefs)
+    rows = [torch.cat([c, torch.zeros(t - c.shape[0], dtype=F64, device=c.device)]) for c in coefs]
+    return torch.stack(rows).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# SO(3)  (kernels_so.py with dim = 3)
+# --------------------------------------------------------------------------------------------------
+def _so3_finish(lam: torch.Tensor):
+    """lam_l already holds the representation dimension (2l+1).  Character chi_l = 1 + 2 sum_{m<=l} cos(m theta):
+    Chebyshev weights v_0 = sum_l lam_l, v_m = 2 sum_{l>=m} lam_l; normaliser = series at theta = 0 =
+    sum_l lam_l (2l+1) (the 1/sum lam^2 prefactor of kernels_so.py:283 cancels against :360-362)."""
+    terms = lam.shape[0]
+    l = torch.arange(terms, dtype=F64, device=lam.device)
+    tail = torch.flip(torch.cumsum(torch.flip(lam, [0]), 0), [0])
+    v = torch.cat([tail[:1], 2.0 * tail[1:]]) / (lam * (2 * l + 1)).sum()
+    basis = choose_basis(terms)
+    if basis == _lib.BASIS_MONOMIAL:
+        v = v.reshape(1, terms) @ _t(chebyshev_to_monomial(terms), v)
+    return v.reshape(1, terms).contiguous(), basis
+
+
+def so3_matern_coef(lengthscale, nu, summands):
+    """(2 nu/kappa^2 + l(l+1))^(-nu - 3/2) (2l+1); kernels_so.py:264-273 (so_dim = 3)."""
+    ls, nu = lengthscale.reshape(()).to(F64), nu.reshape(()).to(F64)
+    l = torch.arange(summands, dtype=F64, device=ls.device)
+    return _so3_finish(torch.pow(2 * nu / ls ** 2 + l * (l + 1), -nu - 1.5) * (2 * l + 1))
+
+
+def so3_gaussian_coef(lengthscale, summands):
+    """exp(-l(l+1) kappa^2 / 2) (2l+1); kernels_so.py:101."""
+    ls = lengthscale.reshape(()).to(F64)
+    l = torch.arange(summands, dtype=F64, device=ls.device)
+    return _so3_finish(torch.exp(-l * (l + 1) * ls ** 2 / 2) * (2 * l + 1))
+
+
+# --------------------------------------------------------------------------------------------------
+# quadrature kernels: node grids (detached, as the reference's .item()) and differentiable node weights
+# --------------------------------------------------------------------------------------------------
+def matern_t_nodes(lengthscale, nu, lo_exp, hi_exp, nb_points, power_offset=1.0):
+    """t grid logspace(lo+log10 kappa, hi+log10 kappa, P) and the weights
+    trapz_w * t^(nu - power_offset) * exp(-2 nu t / kappa^2)
+    (kernels_hyperbolic.py:367-375, kernels_spd.py:262-264, kernels_euclidean.py:186-190)."""
+    ls, nu = lengthscale.reshape(()).to(F64), nu.reshape(()).to(F64)
+    shift = torch.log10(ls).item()
+    t = _logspace(lo_exp + shift, hi_exp + shift, nb_points, ls.device)
+    w = trapz_weights(t) * torch.pow(t, nu - power_offset) * torch.exp(-2.0 * nu / ls ** 2 * t)
+    return t, w

@@ -1,0 +1,399 @@
+// Quadrature Gram kernels: hyperbolic space H^n (Lorentz model, n = 1,2,3) and SPD(2).
+// Reference: kernel_utils/kernels_hyperbolic.py:58-88,258-389, Riemannian_utils/hyperbolic_utils_torch.py:11-60,
+//            kernel_utils/kernels_spd.py:65-136,200-289, Riemannian_utils/spd_utils_torch.py:336-371.
+//
+// Mapping: ONE WARP PER MATRIX ENTRY.  The outer quadrature (t nodes) is spread over the lanes, the
+// inner quadrature (s or b nodes) is a register loop fed by per-warp tables in shared memory, and the
+// t-sum is a warp-shuffle reduction.  Pair geometry (Lorentz distance, 2x2 singular values) is
+// recomputed in registers from the two input rows.
+//
+// H^2: the reference evaluates exp(-(b_k + d)^2 / 4t) at Ps x Pt nodes per entry.  Because the s grid is
+// uniform (b_k = s0 + k ds), exp(-(b_k+d)^2/4t) = E[a][k] * g_a(d) * r_a(d)^k with a pair-independent
+// table E[a][k] = exp(-b_k^2/4t_a) (shared memory) and two exponentials per (entry, t node); the powers
+// r^k come from a running product re-anchored with an exact exp every 16 steps (relative error < 1e-14).
+// cosh(b_k + d) - cosh(d) is formed as cosh(d)(cosh b_k - 1) + sinh(d) sinh(b_k): all terms positive, no
+// cancellation.
+#include "mgb_common.cuh"
+
+namespace mgb {
+
+constexpr int QTHREADS = 256;
+constexpr int QWARPS = QTHREADS / 32;
+constexpr int QMAXP = 1024;   // max inner nodes
+constexpr int QMAXT = 128;    // max outer nodes (4 per lane)
+
+enum QuadMode { Q_FWD = 0, Q_BWD_COEF = 1, Q_NODES = 2 };
+
+// d = 2 asinh( sqrt(max(0, -D0^2 + sum_k Dk^2) + 1e-8) / 2 ), reference operation order, no FMA contraction
+__device__ __forceinline__ double lorentz_dist(const double* a, const double* b, int dim) {
+  const double d0 = __dsub_rn(a[0], b[0]);
+  double neg = -__dmul_rn(d0, d0);
+  double s = 0.0;
+  for (int k = 1; k <= dim; ++k) {
+    const double dk = __dsub_rn(a[k], b[k]);
+    s = (k == 1) ? __dmul_rn(dk, dk) : __dadd_rn(s, __dmul_rn(dk, dk));
+  }
+  const double mink = __dadd_rn(neg, s);
+  const double nrm = sqrt(__dadd_rn(fmax(0.0, mink), 1e-8));
+  return 2.0 * asinh(0.5 * nrm);
+}
+
+struct HypParams {
+  int dim, mode;
+  const double* x1; long long m, ld1;
+  const double* x2; long long n, ld2;
+  const double* dist; long long count;        // Q_NODES
+  const double* tval; const double* tcoef; int Pt;
+  double s0, ds; int Ps;
+  const double* G; long long ldg;
+  double* K; long long ldk;                    // Q_FWD
+  double* out;                                 // Q_BWD_COEF: gtcoef[Pt]; Q_NODES: out[count*Pt]
+};
+
+__global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
+  extern __shared__ __align__(16) double sm[];
+  // layout: E [Ps*Pt] | cm1 [Ps] | sh [Ps] | wq [Ps] | bk [Ps] | per-warp qw [QWARPS][Ps]
+  double* Es = sm;
+  const int nE = (p.dim == 2) ? p.Ps * p.Pt : 0;
+  const int nP = (p.dim == 2) ? p.Ps : 0;
+  double* cm1 = Es + nE;
+  double* sh = cm1 + nP;
+  double* wq = sh + nP;
+  double* qw_all = wq + nP;
+  // pair-independent tables, rebuilt per CTA (Ps*Pt exponentials: negligible next to the entry loop)
+  for (int e = threadIdx.x; e < nE; e += blockDim.x) {
+    const int k = e / p.Pt, a = e - k * p.Pt;
+    const double b = p.s0 + k * p.ds;
+    Es[e] = exp(-(b * b) / (4.0 * p.tval[a]));  // E[k][a] = exp(-b_k^2 / (4 t_a))
+  }
+  for (int e = threadIdx.x; e < nP; e += blockDim.x) {
+    const double b = p.s0 + e * p.ds;
+    const double hs = sinh(0.5 * b);
+    cm1[e] = 2.0 * hs * hs;  // cosh(b) - 1 without cancellation
+    sh[e] = sinh(b);
+    wq[e] = (e == 0 || e == p.Ps - 1) ? 0.5 * p.ds : p.ds;  // trapezoid weights of the uniform s grid
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* qw = qw_all + warp * nP;
+  const long long total = (p.mode == Q_NODES) ? p.count : p.m * p.n;
+  const long long wstride = (long long)gridDim.x * QWARPS;
+
+  // per-lane outer nodes a = lane + 32 q
+  double tv[QMAXT / 32], tc[QMAXT / 32], gacc[QMAXT / 32];
+#pragma unroll
+  for (int q = 0; q < QMAXT / 32; ++q) {
+    const int a = lane + 32 * q;
+    tv[q] = (a < p.Pt) ? p.tval[a] : 1.0;
+    tc[q] = (a < p.Pt && p.tcoef != nullptr) ? p.tcoef[a] : 0.0;
+    gacc[q] = 0.0;
+  }
+
+  for (long long e = (long long)blockIdx.x * QWARPS + warp; e < total; e += wstride) {
+    double d;
+    long long i = 0, j = 0;
+    if (p.mode == Q_NODES) {
+      d = p.dist[e];
+    } else {
+      i = e / p.n;
+      j = e - i * p.n;
+      d = lorentz_dist(p.x1 + i * p.ld1, p.x2 + j * p.ld2, p.dim);
+    }
+    double h[QMAXT / 32];
+    if (p.dim == 2) {
+      const double chd = cosh(d), shd = sinh(d);
+      __syncwarp();
+      for (int k = lane; k < p.Ps; k += 32) {
+        const double bk = p.s0 + k * p.ds;
+        const double den = fma(chd, cm1[k], shd * sh[k]);
+        qw[k] = wq[k] * (bk + d) * rsqrt(den);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < QMAXT / 32; ++q) {
+        const int a = lane + 32 * q;
+        h[q] = 0.0;
+        if (a < p.Pt) {
+          const double inv2t = 0.5 / tv[q];
+          const double g = exp(-(d * d + 2.0 * p.s0 * d) * 0.5 * inv2t);
+          const double r = exp(-p.ds * d * inv2t);
+          double acc = 0.0, pw = 1.0;
+          for (int k0 = 0; k0 < p.Ps; k0 += 16) {
+            if (k0 > 0) pw = exp(-(k0 * p.ds) * d * inv2t);  // re-anchor the running power
+            const int k1 = min(k0 + 16, p.Ps);
+            for (int k = k0; k < k1; ++k) {
+              acc = fma(qw[k] * Es[k * p.Pt + a], pw, acc);
+              pw *= r;
+            }
+          }
+          h[q] = g * acc;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < QMAXT / 32; ++q) {
+        const int a = lane + 32 * q;
+        h[q] = 0.0;
+        if (a < p.Pt) {
+          double v = exp(-(d * d) / (4.0 * tv[q]));
+          if (p.dim == 3) v = v * (d + 1e-8) / sinh(d + 1e-8);
+          h[q] = v;
+        }
+      }
+    }
+    if (p.mode == Q_FWD) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < QMAXT / 32; ++q) s = fma(tc[q], h[q], s);
+      s = warp_sum(s);
+      if (lane == 0) st_stream(p.K + i * p.ldk + j, s);
+    } else if (p.mode == Q_BWD_COEF) {
+      const double g = p.G[i * p.ldg + j];
+#pragma unroll
+      for (int q = 0; q < QMAXT / 32; ++q) gacc[q] = fma(g, h[q], gacc[q]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < QMAXT / 32; ++q) {
+        const int a = lane + 32 * q;
+        if (a < p.Pt) p.out[e * p.Pt + a] = h[q];
+      }
+    }
+  }
+  if (p.mode == Q_BWD_COEF) {
+#pragma unroll
+    for (int q = 0; q < QMAXT / 32; ++q) {
+      const int a = lane + 32 * q;
+      if (a < p.Pt) atomicAdd(p.out + a, gacc[q]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SPD(2)
+// ------------------------------------------------------------------------------------------------
+struct SpdParams {
+  int use_chol, mode;
+  const double* x1; long long m, ld1;
+  const double* x2; long long n, ld2;
+  const double* tcoef; const double* rscale; const double* bscale; int Pt;
+  const double* bval; const double* bw; int Pb;
+  const double* G; long long ldg;
+  double* K; long long ldk;
+  double* out;
+};
+
+// Mandel (s11, s22, sqrt2 s12) -> 2x2 (optionally its lower Cholesky factor); returns a,b,c,d row-major
+__device__ __forceinline__ void spd2_load(const double* v, int chol, double& a, double& b, double& c, double& d) {
+  const double s11 = v[0], s22 = v[1], s12 = v[2] / 1.4142135623730951;
+  if (!chol) {
+    a = s11; b = s12; c = s12; d = s22;
+  } else {
+    a = sqrt(s11);
+    b = 0.0;
+    c = s12 / a;
+    d = sqrt(s22 - c * c);
+  }
+}
+
+// log singular values (H1 >= H2) of P = A * B^{-1}
+__device__ __forceinline__ void spd2_logsv(const double* va, const double* vb, int chol, double& H1, double& H2) {
+  double a, b, c, d, e, f, g, h;
+  spd2_load(va, chol, a, b, c, d);
+  spd2_load(vb, chol, e, f, g, h);
+  const double det = e * h - f * g;
+  const double i11 = h / det, i12 = -f / det, i21 = -g / det, i22 = e / det;
+  const double p11 = a * i11 + b * i21, p12 = a * i12 + b * i22;
+  const double p21 = c * i11 + d * i21, p22 = c * i12 + d * i22;
+  const double q1 = hypot(p11 + p22, p12 - p21), q2 = hypot(p11 - p22, p12 + p21);
+  const double s1 = 0.5 * (q1 + q2);
+  const double s2 = fabs(p11 * p22 - p12 * p21) / s1;
+  H1 = log(s1);
+  H2 = log(s2);
+}
+
+__global__ void __launch_bounds__(QTHREADS) spd2_gram_kernel(SpdParams p) {
+  extern __shared__ __align__(16) double sm[];
+  // layout: bval [Pb] | bw [Pb] | sinh b [Pb] | cosh b [Pb] | per-warp (qb [Pb], cb [Pb])
+  double* bv = sm;
+  double* bw = bv + p.Pb;
+  double* shb = bw + p.Pb;
+  double* chb = shb + p.Pb;
+  double* scratch = chb + p.Pb;
+  for (int e = threadIdx.x; e < p.Pb; e += blockDim.x) {
+    const double b = p.bval[e];
+    bv[e] = b;
+    bw[e] = p.bw[e];
+    shb[e] = sinh(b);
+    chb[e] = cosh(b);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* qb = scratch + (size_t)warp * 2 * p.Pb;
+  double* cb = qb + p.Pb;
+  const long long total = p.m * p.n;
+  const long long wstride = (long long)gridDim.x * QWARPS;
+
+  double tc[QMAXT / 32], rs[QMAXT / 32], bs[QMAXT / 32], gacc[QMAXT / 32];
+#pragma unroll
+  for (int q = 0; q < QMAXT / 32; ++q) {
+    const int a = lane + 32 * q;
+    tc[q] = (a < p.Pt && p.tcoef != nullptr) ? p.tcoef[a] : 0.0;
+    rs[q] = (a < p.Pt) ? p.rscale[a] : 0.0;
+    bs[q] = (a < p.Pt) ? p.bscale[a] : 0.0;
+    gacc[q] = 0.0;
+  }
+
+  for (long long e = (long long)blockIdx.x * QWARPS + warp; e < total; e += wstride) {
+    const long long i = e / p.n, j = e - i * p.n;
+    double H1, H2;
+    spd2_logsv(p.x1 + i * p.ld1, p.x2 + j * p.ld2, p.use_chol, H1, H2);
+    const double delta = H1 - H2, r2 = H1 * H1 + H2 * H2;
+    const double shd = sinh(delta), chd = cosh(delta);
+    __syncwarp();
+    for (int k = lane; k < p.Pb; k += 32) {
+      const double b = bv[k];
+      const double sbd = fma(shb[k], chd, chb[k] * shd);  // sinh(b + delta)
+      qb[k] = bw[k] * (2.0 * b + delta) * rsqrt(shb[k] * sbd);
+      cb[k] = b * (b + delta);
+    }
+    __syncwarp();
+    double h[QMAXT / 32];
+#pragma unroll
+    for (int q = 0; q < QMAXT / 32; ++q) {
+      const int a = lane + 32 * q;
+      h[q] = 0.0;
+      if (a < p.Pt) {
+        const double sc = -bs[q];
+        double acc = 0.0;
+        for (int k = 0; k < p.Pb; ++k) acc = fma(qb[k], exp(cb[k] * sc), acc);
+        h[q] = acc * exp(-r2 * rs[q]);
+      }
+    }
+    if (p.mode == Q_FWD) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < QMAXT / 32; ++q) s = fma(tc[q], h[q], s);
+      s = warp_sum(s);
+      if (lane == 0) st_stream(p.K + i * p.ldk + j, s);
+    } else {
+      const double g = p.G[i * p.ldg + j];
+#pragma unroll
+      for (int q = 0; q < QMAXT / 32; ++q) gacc[q] = fma(g, h[q], gacc[q]);
+    }
+  }
+  if (p.mode == Q_BWD_COEF) {
+#pragma unroll
+    for (int q = 0; q < QMAXT / 32; ++q) {
+      const int a = lane + 32 * q;
+      if (a < p.Pt) atomicAdd(p.out + a, gacc[q]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static int g_sms = 0;
+static int sm_count() {
+  if (g_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_sms = 148;
+  }
+  return g_sms;
+}
+
+static int hyp_launch(HypParams p, cudaStream_t s) {
+  if (p.dim < 1 || p.dim > 3) return fail(MGB_ERR_ARG, "hyperbolic: dim must be 1, 2 or 3 (NotImplementedError in the reference)");
+  if (p.Pt < 1 || p.Pt > QMAXT) return fail(MGB_ERR_ARG, "hyperbolic: Pt out of range [1,128]");
+  if (p.dim == 2 && (p.Ps < 2 || p.Ps > QMAXP)) return fail(MGB_ERR_ARG, "hyperbolic: Ps out of range [2,1024]");
+  const long long total = (p.mode == Q_NODES) ? p.count : p.m * p.n;
+  if (total == 0) return MGB_OK;
+  size_t smem = 0;
+  if (p.dim == 2) {
+    const size_t nE = (size_t)p.Ps * p.Pt;
+    smem = sizeof(double) * (nE + 3 * (size_t)p.Ps + (size_t)QWARPS * p.Ps);
+    if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "hyperbolic: Ps*Pt table exceeds shared memory");
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(hyp_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute"));
+  }
+  long long blocks = (total + QWARPS - 1) / QWARPS;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  hyp_gram_kernel<<<(unsigned)blocks, QTHREADS, smem, s>>>(p);
+  return after_launch("hyp_gram_kernel");
+}
+
+static int spd_launch(SpdParams p, cudaStream_t s) {
+  if (p.Pt < 1 || p.Pt > QMAXT) return fail(MGB_ERR_ARG, "spd2: Pt out of range [1,128]");
+  if (p.Pb < 2 || p.Pb > QMAXP) return fail(MGB_ERR_ARG, "spd2: Pb out of range [2,1024]");
+  const long long total = p.m * p.n;
+  if (total == 0) return MGB_OK;
+  const size_t smem = sizeof(double) * (4 * (size_t)p.Pb + (size_t)QWARPS * 2 * p.Pb);
+  MGB_TRY(check_cuda(cudaFuncSetAttribute(spd2_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                     "cudaFuncSetAttribute"));
+  long long blocks = (total + QWARPS - 1) / QWARPS;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  spd2_gram_kernel<<<(unsigned)blocks, QTHREADS, smem, s>>>(p);
+  return after_launch("spd2_gram_kernel");
+}
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" int mgb_hyperbolic_gram_fwd(int dim, const double* x1, long long m, long long ld1, const double* x2,
+                                       long long n, long long ld2, const double* tval, const double* tcoef, int Pt,
+                                       double s0, double ds, int Ps, double* K, long long ldk, void* stream) {
+  if (!x1 || !x2 || !tval || !tcoef || !K) return fail(MGB_ERR_ARG, "hyperbolic_gram_fwd: null pointer");
+  if (m < 0 || n < 0 || ld1 < dim + 1 || ld2 < dim + 1 || ldk < n) return fail(MGB_ERR_ARG, "hyperbolic_gram_fwd: bad sizes");
+  HypParams p{};
+  p.dim = dim; p.mode = Q_FWD; p.x1 = x1; p.m = m; p.ld1 = ld1; p.x2 = x2; p.n = n; p.ld2 = ld2;
+  p.tval = tval; p.tcoef = tcoef; p.Pt = Pt; p.s0 = s0; p.ds = ds; p.Ps = Ps; p.K = K; p.ldk = ldk;
+  return hyp_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mgb_hyperbolic_gram_bwd_coef(int dim, const double* x1, long long m, long long ld1, const double* x2,
+                                            long long n, long long ld2, const double* tval, int Pt, double s0, double ds,
+                                            int Ps, const double* G, long long ldg, double* gtcoef, void* stream) {
+  if (!x1 || !x2 || !tval || !G || !gtcoef) return fail(MGB_ERR_ARG, "hyperbolic_gram_bwd_coef: null pointer");
+  if (m < 0 || n < 0 || ld1 < dim + 1 || ld2 < dim + 1 || ldg < n) return fail(MGB_ERR_ARG, "hyperbolic_gram_bwd_coef: bad sizes");
+  HypParams p{};
+  p.dim = dim; p.mode = Q_BWD_COEF; p.x1 = x1; p.m = m; p.ld1 = ld1; p.x2 = x2; p.n = n; p.ld2 = ld2;
+  p.tval = tval; p.tcoef = nullptr; p.Pt = Pt; p.s0 = s0; p.ds = ds; p.Ps = Ps; p.G = G; p.ldg = ldg; p.out = gtcoef;
+  return hyp_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mgb_hyperbolic_heat_nodes(int dim, const double* dist, long long count, const double* tval, int Pt,
+                                         double s0, double ds, int Ps, double* out, void* stream) {
+  if (!dist || !tval || !out || count < 0) return fail(MGB_ERR_ARG, "hyperbolic_heat_nodes: bad argument");
+  HypParams p{};
+  p.dim = dim; p.mode = Q_NODES; p.dist = dist; p.count = count; p.tval = tval; p.Pt = Pt;
+  p.s0 = s0; p.ds = ds; p.Ps = Ps; p.out = out;
+  return hyp_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mgb_spd2_gram_fwd(int use_cholesky, const double* x1, long long m, long long ld1, const double* x2,
+                                 long long n, long long ld2, const double* tcoef, const double* rscale,
+                                 const double* bscale, int Pt, const double* bval, const double* bw, int Pb, double* K,
+                                 long long ldk, void* stream) {
+  if (!x1 || !x2 || !tcoef || !rscale || !bscale || !bval || !bw || !K) return fail(MGB_ERR_ARG, "spd2_gram_fwd: null pointer");
+  if (m < 0 || n < 0 || ld1 < 3 || ld2 < 3 || ldk < n) return fail(MGB_ERR_ARG, "spd2_gram_fwd: bad sizes");
+  SpdParams p{};
+  p.use_chol = use_cholesky; p.mode = Q_FWD; p.x1 = x1; p.m = m; p.ld1 = ld1; p.x2 = x2; p.n = n; p.ld2 = ld2;
+  p.tcoef = tcoef; p.rscale = rscale; p.bscale = bscale; p.Pt = Pt; p.bval = bval; p.bw = bw; p.Pb = Pb; p.K = K; p.ldk = ldk;
+  return spd_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mgb_spd2_gram_bwd_coef(int use_cholesky, const double* x1, long long m, long long ld1, const double* x2,
+                                      long long n, long long ld2, const double* rscale, const double* bscale, int Pt,
+                                      const double* bval, const double* bw, int Pb, const double* G, long long ldg,
+                                      double* gtcoef, void* stream) {
+  if (!x1 || !x2 || !rscale || !bscale || !bval || !bw || !G || !gtcoef) return fail(MGB_ERR_ARG, "spd2_gram_bwd_coef: null pointer");
+  if (m < 0 || n < 0 || ld1 < 3 || ld2 < 3 || ldg < n) return fail(MGB_ERR_ARG, "spd2_gram_bwd_coef: bad sizes");
+  SpdParams p{};
+  p.use_chol = use_cholesky; p.mode = Q_BWD_COEF; p.x1 = x1; p.m = m; p.ld1 = ld1; p.x2 = x2; p.n = n; p.ld2 = ld2;
+  p.tcoef = nullptr; p.rscale = rscale; p.bscale = bscale; p.Pt = Pt; p.bval = bval; p.bw = bw; p.Pb = Pb;
+  p.G = G; p.ldg = ldg; p.out = gtcoef;
+  return spd_launch(p, static_cast<cudaStream_t>(stream));
+}

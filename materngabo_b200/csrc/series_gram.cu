@@ -1,0 +1,516 @@
+// Spectral-series Gram kernels: K_ij = prod_f p_f(clamp(scale <x1_i[f], x2_j[f]> + shift)).
+//
+// One kernel family serves the sphere S^d (Gegenbauer series re-expanded on the host), SO(3)
+// (character sum = Chebyshev series in cos(theta)), the circle and the torus T^d (product of
+// cosine series).  Reference: kernel_utils/kernels_sphere.py:102-139,188-224,443-472,551-614,
+// kernels_so.py:305-362, kernels_torus.py:142-177 (see include/mgb.h).
+//
+// Data layout / tiling (B200: 148 SMs, HBM3e write-bound at 8 B per entry):
+//   - a CTA owns a 128-row x 64-column tile of K; 8 warps, warp w owns rows [16w, 16w+16);
+//   - lane l owns columns 2l, 2l+1 of the tile: one 16-byte streaming store per row, a warp writes
+//     512 contiguous bytes = 4 full 128-byte lines;
+//   - the x1 row panel (128 x D doubles, contiguous in HBM) is staged in shared memory by ONE
+//     cp.async.bulk (TMA engine, mbarrier completion) and read back as warp-wide broadcasts;
+//   - the two x2 rows of a lane live in registers for the whole tile (fast path) or in a
+//     transposed shared-memory panel (general path);
+//   - inner products, clamp and the polynomial are evaluated in registers: D + T + 3 DFMA per entry
+//     (monomial/Horner, T <= 12) or D + 2T + 3 (Chebyshev three-term recurrence).
+#include "mgb_common.cuh"
+
+namespace mgb {
+
+constexpr int kTM = 128;   // rows per tile
+constexpr int kTN = 64;    // cols per tile
+constexpr int kThreads = 256;
+constexpr int kRowsPerWarp = kTM / (kThreads / 32);
+
+struct SeriesParams {
+  const double* x1; long long m, ld1;
+  const double* x2; long long n, ld2;
+  const double* coef;
+  double* K; long long ldk;
+  int F, W, T;
+  double scale, shift, lo, hi;
+  long long ncc;  // column chunks
+};
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// Stage rows [row0, row0+rows) of x (ld == D contiguous case uses one bulk copy) into dst[r*D + k].
+__device__ __forceinline__ void stage_panel(double* dst, const double* x, long long row0, int rows, int D,
+                                            long long ld, uint64_t* bar) {
+  const double* src = x + row0 * ld;
+  const uint32_t bytes = static_cast<uint32_t>(rows) * D * 8u;
+  const bool bulk = (ld == D) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && ((bytes & 15u) == 0);
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(dst, src, bytes, bar);
+    }
+    while (!mbar_try_wait(bar, 0)) {
+    }
+  } else {
+    for (int e = threadIdx.x; e < rows * D; e += blockDim.x) {
+      int r = e / D, k = e - r * D;
+      dst[e] = src[(long long)r * ld + k];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path: one factor, width W compile-time, monomial basis with T <= TREG coefficients in registers.
+// ---------------------------------------------------------------------------------------------
+template <int W, int TREG>
+__global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams p) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t bar;
+  double* x1s = smem;  // kTM * W
+
+  const long long tile = blockIdx.x;
+  const long long cc = tile % p.ncc;
+  const long long rp = tile / p.ncc;
+  const long long row0 = rp * kTM;
+  const int rows = (int)min((long long)kTM, p.m - row0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // coefficients -> registers (zero padded)
+  double c[TREG];
+#pragma unroll
+  for (int k = 0; k < TREG; ++k) c[k] = (k < p.T) ? __ldg(p.coef + k) : 0.0;
+
+  // this lane's two x2 rows -> registers
+  const long long col = cc * kTN + 2 * lane;
+  double xa[W], xb[W];
+  {
+    const bool va = col < p.n, vb = col + 1 < p.n;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      xa[k] = va ? __ldg(p.x2 + col * p.ld2 + k) : 0.0;
+      xb[k] = vb ? __ldg(p.x2 + (col + 1) * p.ld2 + k) : 0.0;
+    }
+  }
+  stage_panel(x1s, p.x1, row0, rows, W, p.ld1, &bar);
+
+  const bool vec_ok = (col + 1 < p.n) && ((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0);
+  const int r_begin = warp * kRowsPerWarp;
+  const int r_end = min(r_begin + kRowsPerWarp, rows);
+#pragma unroll 4
+  for (int r = r_begin; r < r_end; ++r) {
+    const double* xr = x1s + r * W;
+    double da = 0.0, db = 0.0;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      const double v = xr[k];  // warp-wide broadcast
+      da = fma(v, xa[k], da);
+      db = fma(v, xb[k], db);
+    }
+    double ua = fmin(fmax(fma(da, p.scale, p.shift), p.lo), p.hi);
+    double ub = fmin(fmax(fma(db, p.scale, p.shift), p.lo), p.hi);
+    double pa = c[TREG - 1], pb = c[TREG - 1];
+#pragma unroll
+    for (int k = TREG - 2; k >= 0; --k) {
+      pa = fma(pa, ua, c[k]);
+      pb = fma(pb, ub, c[k]);
+    }
+    double* out = p.K + (row0 + r) * p.ldk + col;
+    if (vec_ok) {
+      st_stream2(out, pa, pb);
+    } else {
+      if (col < p.n) st_stream(out, pa);
+      if (col + 1 < p.n) st_stream(out + 1, pb);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// General path: F factors of runtime width W, T terms per factor, either basis; coefficients and the
+// transposed x2 panel in shared memory.  Each thread evaluates 2 columns x 2 rows per coefficient read.
+// ---------------------------------------------------------------------------------------------
+template <int BASIS>
+__device__ __forceinline__ void eval4(const double* __restrict__ cf, int T, const double (&u)[4], double (&s)[4]) {
+  if (BASIS == MGB_BASIS_MONOMIAL) {
+    double c = cf[T - 1];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[q] = c;
+    for (int k = T - 2; k >= 0; --k) {
+      c = cf[k];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[q] = fma(s[q], u[q], c);
+    }
+  } else {
+    // forward Chebyshev recurrence T_k = 2u T_{k-1} - T_{k-2}, accumulated on the fly
+    double t0[4], t1[4], u2[4];
+    const double c0 = cf[0], c1 = (T > 1) ? cf[1] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      t0[q] = 1.0;
+      t1[q] = u[q];
+      u2[q] = 2.0 * u[q];
+      s[q] = fma(c1, u[q], c0);
+    }
+    for (int k = 2; k < T; ++k) {
+      const double c = cf[k];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double t2 = fma(u2[q], t1[q], -t0[q]);
+        s[q] = fma(c, t2, s[q]);
+        t0[q] = t1[q];
+        t1[q] = t2;
+      }
+    }
+  }
+}
+
+template <int BASIS>
+__global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_general(SeriesParams p) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const int D = p.F * p.W;
+  double* x1s = smem;                 // kTM * D
+  double* x2t = x1s + kTM * D;        // D * kTN (transposed: [k][col])
+  double* cfs = x2t + D * kTN;        // F * T
+
+  const long long tile = blockIdx.x;
+  const long long cc = tile % p.ncc;
+  const long long rp = tile / p.ncc;
+  const long long row0 = rp * kTM;
+  const int rows = (int)min((long long)kTM, p.m - row0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int e = threadIdx.x; e < p.F * p.T; e += blockDim.x) cfs[e] = p.coef[e];
+  for (int e = threadIdx.x; e < D * kTN; e += blockDim.x) {
+    const int cidx = e / D, k = e - cidx * D;
+    const long long gc = cc * kTN + cidx;
+    x2t[k * kTN + cidx] = (gc < p.n) ? p.x2[gc * p.ld2 + k] : 0.0;
+  }
+  stage_panel(x1s, p.x1, row0, rows, D, p.ld1, &bar);
+  __syncthreads();
+
+  const long long col = cc * kTN + 2 * lane;
+  const bool vec_ok = (col + 1 < p.n) && ((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0);
+  const int r_begin = warp * kRowsPerWarp;
+  for (int rr = 0; rr < kRowsPerWarp; rr += 2) {
+    const int r0 = r_begin + rr;
+    if (r0 >= rows) break;
+    const int r1 = min(r0 + 1, rows - 1);
+    double prod[4] = {1.0, 1.0, 1.0, 1.0};
+    for (int f = 0; f < p.F; ++f) {
+      double d[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int k = 0; k < p.W; ++k) {
+        const int kk = f * p.W + k;
+        const double2 xc = *reinterpret_cast<const double2*>(x2t + kk * kTN + 2 * lane);
+        const double v0 = x1s[r0 * D + kk], v1 = x1s[r1 * D + kk];
+        d[0] = fma(v0, xc.x, d[0]);
+        d[1] = fma(v0, xc.y, d[1]);
+        d[2] = fma(v1, xc.x, d[2]);
+        d[3] = fma(v1, xc.y, d[3]);
+      }
+      double u[4], s[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) u[q] = fmin(fmax(fma(d[q], p.scale, p.shift), p.lo), p.hi);
+      eval4<BASIS>(cfs + f * p.T, p.T, u, s);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) prod[q] *= s[q];
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = (h == 0) ? r0 : r0 + 1;
+      if (r >= rows) break;
+      double* out = p.K + (row0 + r) * p.ldk + col;
+      if (vec_ok) {
+        st_stream2(out, prod[2 * h], prod[2 * h + 1]);
+      } else {
+        if (col < p.n) st_stream(out, prod[2 * h]);
+        if (col + 1 < p.n) st_stream(out + 1, prod[2 * h + 1]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward.  One thread per (row i, 32-column strip) walks its strip; per-coefficient sums are reduced
+// warp -> block -> one atomicAdd per coefficient per CTA; input gradients are reduced along the row.
+// Sizes here are GP-fit sizes (N <= a few thousand): latency-bound, kept simple and exact.
+//   order = 1 : standard backward (gcoef and gx1 with p')
+//   order = 2 : gx1-like contraction with p'' (Hessian-vector support), gcoef untouched
+// G is addressed with two strides so that the x2-side gradient is the same kernel with roles swapped.
+// ---------------------------------------------------------------------------------------------
+struct SeriesBwdParams {
+  const double* xa; long long ma, lda;   // "row" side
+  const double* xb; long long nb, ldb;   // "column" side
+  const double* coef;
+  const double* G; long long gs_row, gs_col;
+  double* gcoef;   // may be null
+  double* gxa;     // may be null, ma x D contiguous
+  int F, W, T, basis, order;
+  double scale, shift, lo, hi;
+};
+
+constexpr int kBwdThreads = 128;
+constexpr int kBwdMaxW = 32;
+
+// grid = (row groups, factors).  Block (g, f): warp w handles row i = 4g + w for factor f.
+template <int TACC>
+__global__ void __launch_bounds__(kBwdThreads) series_gram_bwd_kernel(SeriesBwdParams p) {
+  extern __shared__ double sm[];
+  const int D = p.F * p.W;
+  const int f = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* cfs = sm;                          // F*T
+  double* gc_blk = cfs + p.F * p.T;          // T
+  double* xrows = gc_blk + p.T;              // warps * D
+  for (int e = threadIdx.x; e < p.F * p.T; e += blockDim.x) cfs[e] = p.coef[e];
+  for (int e = threadIdx.x; e < p.T; e += blockDim.x) gc_blk[e] = 0.0;
+  const long long i = (long long)blockIdx.x * (kBwdThreads / 32) + warp;
+  const bool row_ok = i < p.ma;
+  double* xi = xrows + warp * D;
+  if (row_ok)
+    for (int k = lane; k < D; k += 32) xi[k] = p.xa[i * p.lda + k];
+  __syncthreads();
+
+  double acc[TACC];
+#pragma unroll
+  for (int k = 0; k < TACC; ++k) acc[k] = 0.0;
+  double gx[kBwdMaxW];
+#pragma unroll
+  for (int k = 0; k < kBwdMaxW; ++k) gx[k] = 0.0;
+  const bool want_coef = (p.gcoef != nullptr) && (p.order == 1);
+  const double* cf = cfs + f * p.T;
+
+  if (row_ok) {
+    for (long long j0 = 0; j0 < p.nb; j0 += 32) {
+      const long long j = j0 + lane;
+      const bool valid = j < p.nb;
+      const long long jj = valid ? j : 0;
+      double go = valid ? p.G[i * p.gs_row + jj * p.gs_col] : 0.0;
+      const double* xj = p.xb + jj * p.ldb;
+      // product of the other factors' values
+      for (int h = 0; h < p.F; ++h) {
+        if (h == f) continue;
+        double dot = 0.0;
+        for (int k = 0; k < p.W; ++k) dot = fma(xi[h * p.W + k], xj[h * p.W + k], dot);
+        const double u = fmin(fmax(fma(dot, p.scale, p.shift), p.lo), p.hi);
+        const double* ch = cfs + h * p.T;
+        double s;
+        if (p.basis == MGB_BASIS_MONOMIAL) {
+          s = ch[p.T - 1];
+          for (int k = p.T - 2; k >= 0; --k) s = fma(s, u, ch[k]);
+        } else {
+          double t0 = 1.0, t1 = u;
+          s = ch[0] + ((p.T > 1) ? ch[1] * u : 0.0);
+          for (int k = 2; k < p.T; ++k) {
+            const double t2 = fma(2.0 * u, t1, -t0);
+            s = fma(ch[k], t2, s);
+            t0 = t1;
+            t1 = t2;
+          }
+        }
+        go *= s;
+      }
+      // this factor: basis values (for gcoef) and the order-th derivative (for gx)
+      double dot = 0.0;
+      for (int k = 0; k < p.W; ++k) dot = fma(xi[f * p.W + k], xj[f * p.W + k], dot);
+      const double raw = fma(dot, p.scale, p.shift);
+      const double u = fmin(fmax(raw, p.lo), p.hi);
+      const bool inside = (raw >= p.lo) && (raw <= p.hi);  // torch.clamp passes gradient on the boundary
+      double d1 = 0.0, d2 = 0.0;
+      if (p.basis == MGB_BASIS_MONOMIAL) {
+        double pw = 1.0, pw1 = 0.0, pw2 = 0.0;  // u^k, u^(k-1), u^(k-2)
+#pragma unroll
+        for (int k = 0; k < TACC; ++k) {
+          if (k < p.T) {
+            if (want_coef) acc[k] = fma(go, pw, acc[k]);
+            d1 = fma((double)k * cf[k], pw1, d1);
+            d2 = fma((double)(k * (k - 1)) * cf[k], pw2, d2);
+            pw2 = pw1;
+            pw1 = pw;
+            pw *= u;
+            if (k == 0) pw1 = 1.0;
+            if (k == 1) pw2 = 1.0;
+          }
+        }
+      } else {
+        double t0 = 1.0, t1 = u, a0 = 0.0, a1 = 1.0, b0 = 0.0, b1 = 0.0;
+        if (want_coef) {
+          acc[0] += go;
+          if (p.T > 1) acc[1] = fma(go, u, acc[1]);
+        }
+        d1 = (p.T > 1) ? cf[1] : 0.0;
+#pragma unroll
+        for (int k = 2; k < TACC; ++k) {
+          if (k < p.T) {
+            const double t2 = fma(2.0 * u, t1, -t0);
+            const double a2 = fma(2.0 * u, a1, 2.0 * t1 - a0);
+            const double b2 = fma(2.0 * u, b1, 4.0 * a1 - b0);
+            if (want_coef) acc[k] = fma(go, t2, acc[k]);
+            d1 = fma(cf[k], a2, d1);
+            d2 = fma(cf[k], b2, d2);
+            t0 = t1; t1 = t2; a0 = a1; a1 = a2; b0 = b1; b1 = b2;
+          }
+        }
+      }
+      if (p.gxa != nullptr && inside) {
+        const double w = go * ((p.order == 1) ? d1 * p.scale : d2 * p.scale * p.scale);
+#pragma unroll
+        for (int k = 0; k < kBwdMaxW; ++k)
+          if (k < p.W) gx[k] = fma(w, xj[f * p.W + k], gx[k]);
+      }
+    }
+    if (want_coef) {
+#pragma unroll
+      for (int k = 0; k < TACC; ++k) {
+        if (k < p.T) {
+          const double v = warp_sum(acc[k]);
+          if (lane == 0) atomicAdd(gc_blk + k, v);
+        }
+      }
+    }
+    if (p.gxa != nullptr) {
+#pragma unroll
+      for (int k = 0; k < kBwdMaxW; ++k) {
+        if (k < p.W) {
+          const double v = warp_sum(gx[k]);
+          if (lane == 0) p.gxa[i * D + f * p.W + k] = v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (want_coef)
+    for (int e = threadIdx.x; e < p.T; e += blockDim.x) atomicAdd(p.gcoef + f * p.T + e, gc_blk[e]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------
+static int validate(const mgb_series_desc* d, const void* x1, long long m, long long ld1, const void* x2, long long n,
+                    long long ld2, const void* coef) {
+  if (!d || !x1 || !x2 || !coef) return fail(MGB_ERR_ARG, "series_gram: null pointer");
+  if (d->n_factors < 1 || d->n_factors > MGB_MAX_FACTORS) return fail(MGB_ERR_ARG, "series_gram: n_factors out of range");
+  if (d->factor_width < 1) return fail(MGB_ERR_ARG, "series_gram: factor_width < 1");
+  if (d->n_terms < 1 || d->n_terms > MGB_MAX_TERMS) return fail(MGB_ERR_ARG, "series_gram: n_terms out of range");
+  if (d->basis != MGB_BASIS_MONOMIAL && d->basis != MGB_BASIS_CHEBYSHEV) return fail(MGB_ERR_ARG, "series_gram: bad basis");
+  const long long D = (long long)d->n_factors * d->factor_width;
+  if (m < 0 || n < 0 || ld1 < D || ld2 < D) return fail(MGB_ERR_ARG, "series_gram: bad sizes / leading dimensions");
+  if (!(d->lo <= d->hi)) return fail(MGB_ERR_ARG, "series_gram: lo > hi");
+  return MGB_OK;
+}
+
+template <int W, int TREG>
+static int launch_fast(const SeriesParams& p, long long tiles, cudaStream_t s) {
+  const size_t smem = sizeof(double) * kTM * W;
+  series_gram_fwd_fast<W, TREG><<<(unsigned)tiles, kThreads, smem, s>>>(p);
+  return after_launch("series_gram_fwd_fast");
+}
+
+template <int TREG>
+static int dispatch_fast(const SeriesParams& p, long long tiles, cudaStream_t s, bool* handled) {
+  *handled = true;
+  switch (p.W) {
+    case 2: return launch_fast<2, TREG>(p, tiles, s);
+    case 3: return launch_fast<3, TREG>(p, tiles, s);
+    case 4: return launch_fast<4, TREG>(p, tiles, s);
+    case 5: return launch_fast<5, TREG>(p, tiles, s);
+    case 6: return launch_fast<6, TREG>(p, tiles, s);
+    case 9: return launch_fast<9, TREG>(p, tiles, s);
+    case 11: return launch_fast<11, TREG>(p, tiles, s);
+    default: *handled = false; return MGB_OK;
+  }
+}
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" int mgb_series_gram_fwd(const mgb_series_desc* d, const double* x1, long long m, long long ld1,
+                                   const double* x2, long long n, long long ld2, const double* coef, double* K,
+                                   long long ldk, void* stream) {
+  MGB_TRY(validate(d, x1, m, ld1, x2, n, ld2, coef));
+  if (!K || ldk < n) return fail(MGB_ERR_ARG, "series_gram_fwd: bad K / ldk");
+  if (m == 0 || n == 0) return MGB_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SeriesParams p{x1, m, ld1, x2, n, ld2, coef, K, ldk, d->n_factors, d->factor_width, d->n_terms,
+                 d->scale, d->shift, d->lo, d->hi, (n + kTN - 1) / kTN};
+  const long long tiles = p.ncc * ((m + kTM - 1) / kTM);
+  if (tiles > 0x7fffffffLL) return fail(MGB_ERR_ARG, "series_gram_fwd: too many tiles for one launch");
+  if (d->n_factors == 1 && d->basis == MGB_BASIS_MONOMIAL && d->n_terms <= 12) {
+    bool handled = false;
+    int rc = (d->n_terms <= 10) ? dispatch_fast<10>(p, tiles, s, &handled) : dispatch_fast<12>(p, tiles, s, &handled);
+    if (handled) return rc;
+  }
+  const int D = d->n_factors * d->factor_width;
+  const size_t smem = sizeof(double) * ((size_t)kTM * D + (size_t)D * kTN + (size_t)d->n_factors * d->n_terms);
+  if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "series_gram_fwd: row width too large for the shared-memory panels");
+  if (d->basis == MGB_BASIS_MONOMIAL) {
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(series_gram_fwd_general<MGB_BASIS_MONOMIAL>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
+    series_gram_fwd_general<MGB_BASIS_MONOMIAL><<<(unsigned)tiles, kThreads, smem, s>>>(p);
+  } else {
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(series_gram_fwd_general<MGB_BASIS_CHEBYSHEV>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
+    series_gram_fwd_general<MGB_BASIS_CHEBYSHEV><<<(unsigned)tiles, kThreads, smem, s>>>(p);
+  }
+  return after_launch("series_gram_fwd_general");
+}
+
+static int launch_bwd(const mgb_series_desc* d, int order, const double* xa, long long ma, long long lda,
+                      const double* xb, long long nb, long long ldb, const double* coef, const double* G,
+                      long long gs_row, long long gs_col, double* gcoef, double* gxa, cudaStream_t s) {
+  if (ma == 0) return MGB_OK;
+  SeriesBwdParams p{xa, ma, lda, xb, nb, ldb, coef, G, gs_row, gs_col, gcoef, gxa,
+                    d->n_factors, d->factor_width, d->n_terms, d->basis, order, d->scale, d->shift, d->lo, d->hi};
+  const int D = d->n_factors * d->factor_width;
+  const size_t smem = sizeof(double) * ((size_t)d->n_factors * d->n_terms + d->n_terms + (size_t)(kBwdThreads / 32) * D);
+  const long long blocks = (ma + (kBwdThreads / 32) - 1) / (kBwdThreads / 32);
+  dim3 grid((unsigned)blocks, (unsigned)d->n_factors);
+  if (smem > 48 * 1024) return fail(MGB_ERR_ARG, "series_gram_bwd: F*T too large");
+  if (d->n_terms <= 16) series_gram_bwd_kernel<16><<<grid, kBwdThreads, smem, s>>>(p);
+  else if (d->n_terms <= 64) series_gram_bwd_kernel<64><<<grid, kBwdThreads, smem, s>>>(p);
+  else series_gram_bwd_kernel<MGB_MAX_TERMS><<<grid, kBwdThreads, smem, s>>>(p);
+  return after_launch("series_gram_bwd_kernel");
+}
+
+extern "C" int mgb_series_gram_bwd(const mgb_series_desc* d, const double* x1, long long m, long long ld1,
+                                   const double* x2, long long n, long long ld2, const double* coef, const double* G,
+                                   long long ldg_row, long long ldg_col, double* gcoef, double* gx1, double* gx2,
+                                   void* stream) {
+  MGB_TRY(validate(d, x1, m, ld1, x2, n, ld2, coef));
+  if (!G) return fail(MGB_ERR_ARG, "series_gram_bwd: null G");
+  if (d->factor_width > kBwdMaxW) return fail(MGB_ERR_ARG, "series_gram_bwd: factor width > 32");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (m == 0 || n == 0) return MGB_OK;
+  if (gcoef || gx1) MGB_TRY(launch_bwd(d, 1, x1, m, ld1, x2, n, ld2, coef, G, ldg_row, ldg_col, gcoef, gx1, s));
+  if (gx2) MGB_TRY(launch_bwd(d, 1, x2, n, ld2, x1, m, ld1, coef, G, ldg_col, ldg_row, nullptr, gx2, s));
+  return MGB_OK;
+}
+
+extern "C" int mgb_series_gram_dx(const mgb_series_desc* d, int order, const double* x1, long long m, long long ld1,
+                                  const double* x2, long long n, long long ld2, const double* coef, const double* G,
+                                  long long ldg_row, long long ldg_col, double* out1, double* out2, void* stream) {
+  MGB_TRY(validate(d, x1, m, ld1, x2, n, ld2, coef));
+  if (!G) return fail(MGB_ERR_ARG, "series_gram_dx: null G");
+  if (order != 1 && order != 2) return fail(MGB_ERR_ARG, "series_gram_dx: order must be 1 or 2");
+  if (d->n_factors != 1) return fail(MGB_ERR_ARG, "series_gram_dx: single-factor kernels only");
+  if (d->factor_width > kBwdMaxW) return fail(MGB_ERR_ARG, "series_gram_dx: factor width > 32");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (m == 0 || n == 0) return MGB_OK;
+  if (out1) MGB_TRY(launch_bwd(d, order, x1, m, ld1, x2, n, ld2, coef, G, ldg_row, ldg_col, nullptr, out1, s));
+  if (out2) MGB_TRY(launch_bwd(d, order, x2, n, ld2, x1, m, ld1, coef, G, ldg_col, ldg_row, nullptr, out2, s));
+  return MGB_OK;
+}

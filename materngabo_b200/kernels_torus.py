@@ -1,0 +1,66 @@
+"""Torus kernels: drop-in for BoManifolds/kernel_utils/kernels_torus.py
+(TorusProductOfManifoldsRiemannianGaussianKernel :15-90, ...MaternKernel :93-177).
+
+T^d is a product of d circles.  The parameter layout of the reference is kept (``self.torus_kernel`` is a
+ProductKernel of circle kernels with ``active_dims=(2i, 2i+1)``, each with its own lengthscale / nu), but
+the product is evaluated by ONE launch of the multi-factor series kernel instead of d separate Gram
+matrices multiplied together.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, _ops, _weights
+from .gpytorch_compat import Kernel, ProductKernel
+from .kernels_sphere import (CircleRiemannianGaussianKernel, CircleRiemannianIntegratedMaternKernel, _CLAMP,
+                             _check_batch)
+
+
+class _TorusKernel(Kernel):
+    has_lengthscale = True
+
+    def _to_circles(self, x):
+        """angles (width dim) -> interleaved (cos, sin) pairs (kernels_torus.py:162-173)."""
+        if x.shape[-1] == self.dim:
+            return torch.stack([torch.cos(x), torch.sin(x)], dim=-1).reshape(*x.shape[:-1], 2 * self.dim)
+        return x
+
+    def series(self):
+        coef = _weights.stack_factor_coefs([k._coef() for k in self.torus_kernel.kernels])
+        if self.dim > _lib.MAX_FACTORS:
+            raise NotImplementedError("T^d with d > %d" % _lib.MAX_FACTORS)
+        return _ops.SeriesSpec(self.dim, 2, _lib.BASIS_CHEBYSHEV, 1.0, 0.0, -_CLAMP, _CLAMP), coef
+
+    def forward(self, x1, x2, diag=False, **params):
+        _check_batch(self)
+        x1c, x2c = self._to_circles(x1), self._to_circles(x2)
+        if x1c.shape[-1] != 2 * self.dim or x2c.shape[-1] != 2 * self.dim:
+            raise RuntimeError("T^%d points must be %d angles or %d circle coordinates" % (self.dim, self.dim, 2 * self.dim))
+        spec, coef = self.series()
+        coef = coef.to(x1c.device)
+        return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1c, x2c, diag=diag)
+
+
+class TorusProductOfManifoldsRiemannianGaussianKernel(_TorusKernel):
+    def __init__(self, dim, **kwargs):
+        self.has_lengthscale = True
+        super().__init__(has_lengthscale=True, ard_num_dims=None, **kwargs)
+        self.dim = dim
+        kernels = [CircleRiemannianGaussianKernel(active_dims=torch.tensor(list(range(2 * i, 2 * i + 2))))
+                   for i in range(self.dim)]
+        self.torus_kernel = ProductKernel(*kernels)
+
+
+class TorusProductOfManifoldsRiemannianMaternKernel(_TorusKernel):
+    def __init__(self, dim, nu=None, nu_prior=None, **kwargs):
+        self.has_lengthscale = True
+        super().__init__(has_lengthscale=True, ard_num_dims=None, **kwargs)
+        self.dim = dim
+        if not isinstance(nu, (list, tuple)):
+            nu = [nu for _ in range(self.dim)]
+        if not isinstance(nu_prior, (list, tuple)):
+            nu_prior = [nu_prior for _ in range(self.dim)]
+        kernels = [CircleRiemannianIntegratedMaternKernel(nu=nu[i], nu_prior=nu_prior[i],
+                                                          active_dims=torch.tensor(list(range(2 * i, 2 * i + 2))))
+                   for i in range(self.dim)]
+        self.torus_kernel = ProductKernel(*kernels)

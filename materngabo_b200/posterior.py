@@ -1,0 +1,246 @@
+"""Exact-GP posterior on the device + analytic EI + row-sharding over the GPUs of one box.
+
+What this replaces in the reference's BO loop (all unvendored gpytorch / botorch arithmetic):
+``SingleTaskGP(x, y, covar_module=ScaleKernel(manifold_kernel))`` in eval mode called through
+``ExpectedImprovement(model, best_f, maximize=False)(X)`` with ``X`` of shape ``b x 1 x D``
+(examples/bo_manifolds_benchmark_examples/bo_sphere.py:211-233,265; manifold_optimization/
+manifold_optimize.py:195,254,337).  The arithmetic is
+
+    mean = m + s K(X*, X) alpha,            alpha = (s K + noise I)^-1 (y - m)
+    var  = s k(x*, x*) - || L^-1 s K(X*, X)^T ||^2,   L = chol(s K + noise I)
+
+``fit`` does the one-off N x N work with torch.linalg (cuSOLVER) and packs L^-1 and alpha for the fused
+kernel; ``posterior`` streams candidates through ``mgb_series_posterior`` (Gram chunk -> DMMA triangular
+product + square-sum, csrc/posterior.cu) and never materialises K(X*, X) beyond one L2/HBM-resident chunk.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Optional
+
+import torch
+
+from . import _lib, _ops
+
+F64 = torch.float64
+DEFAULT_CHUNK = 37888  # 2 waves of 128-candidate tiles on 148 SMs
+
+
+def _self_kernel_value(spec: _ops.SeriesSpec, coef: torch.Tensor) -> torch.Tensor:
+    """k(x, x) for on-manifold x: every factor's pair scalar clamps to ``hi`` (unit vectors, rotations)."""
+    c = coef.detach().to("cpu", F64)
+    u = spec.hi
+    val = 1.0
+    for f in range(c.shape[0]):
+        if spec.basis == _lib.BASIS_MONOMIAL:
+            s = 0.0
+            for k in range(c.shape[1] - 1, -1, -1):
+                s = s * u + float(c[f, k])
+        else:
+            theta = math.acos(u)
+            s = sum(float(c[f, k]) * math.cos(k * theta) for k in range(c.shape[1]))
+        val *= s
+    return val
+
+
+class ExactGPPosterior:
+    """Constant-mean exact GP over a series kernel (sphere, SO(3), circle, torus).
+
+    ``kernel`` is one of the drop-in classes exposing ``series() -> (SeriesSpec, coef)``.
+    """
+
+    def __init__(self, kernel, train_x: torch.Tensor, train_y: torch.Tensor, outputscale: float = 1.0,
+                 noise: float = 1e-2, mean_const: float = 0.0, chunk: int = DEFAULT_CHUNK):
+        _lib.require_cuda_f64(train_x, train_y)
+        self.kernel = kernel
+        self.train_x = train_x.contiguous()
+        self.train_y = train_y.contiguous().reshape(-1)
+        self.outputscale = float(outputscale)
+        self.noise = float(noise)
+        self.mean_const = float(mean_const)
+        self.chunk = int(chunk)
+        self.device = train_x.device
+        self._packed = None
+        self._ws = None
+        self.spec = None
+        self.coef = None
+        self.kss_value = None
+
+    # ---- one-off N x N work ------------------------------------------------------------------
+    @torch.no_grad()
+    def fit(self):
+        x = self._prepared(self.train_x)
+        n = x.shape[0]
+        spec, coef = self.kernel.series()
+        coef = (coef.detach().to(self.device, F64) * self._factor_scale(spec)).contiguous()
+        k = _ops.series_gram(spec, x, x, coef)
+        k.diagonal().add_(self.noise)
+        L = torch.linalg.cholesky(k)
+        self.alpha = torch.cholesky_solve((self.train_y - self.mean_const).unsqueeze(-1), L).squeeze(-1).contiguous()
+        self.rinv = torch.linalg.solve_triangular(L, torch.eye(n, dtype=F64, device=self.device), upper=False).contiguous()
+        self.spec, self.coef = spec, coef
+        self.kss_value = _self_kernel_value(spec, coef)
+        self.train_prepared = x
+        self._pack()
+        return self
+
+    def _factor_scale(self, spec):
+        # outputscale multiplies the product of factors once: put it on factor 0 only
+        s = torch.ones(spec.n_factors, 1, dtype=F64, device=self.device)
+        s[0, 0] = self.outputscale
+        return s
+
+    def _prepared(self, x):
+        """Torus kernels accept angles: convert exactly as their forward does."""
+        prep = getattr(self.kernel, "_to_circles", None)
+        x = prep(x) if prep is not None else x
+        return x.contiguous()
+
+    def _pack(self):
+        lib = _lib.load()
+        n = self.rinv.shape[0]
+        nbytes = lib.mgb_posterior_pack_bytes(n)
+        self._packed = torch.empty(nbytes // 8, dtype=F64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = lib.mgb_posterior_pack(_lib.ptr(self.rinv), n, self.rinv.stride(0), _lib.ptr(self.alpha),
+                                        _lib.ptr(self._packed), _lib.stream_ptr(self.device))
+        _lib.check(rc, "mgb_posterior_pack")
+
+    # ---- state exchange for the sharded path ---------------------------------------------------
+    def state(self):
+        """Tensors a peer rank needs to evaluate the posterior (what NCCL broadcasts after a fit)."""
+        return {"train": self.train_prepared, "packed": self._packed, "coef": self.coef}
+
+    def load_state(self, spec, train, packed, coef, kss_value):
+        self.spec, self.train_prepared, self._packed, self.coef, self.kss_value = spec, train, packed, coef, kss_value
+        return self
+
+    # ---- candidates ----------------------------------------------------------------------------
+    @torch.no_grad()
+    def posterior(self, x: torch.Tensor):
+        """x: (M, D) or botorch's (b, 1, D).  Returns (mean, var), each (M,) / (b,)."""
+        if self._packed is None:
+            raise RuntimeError("call fit() (or load_state) first")
+        _lib.require_cuda_f64(x)
+        if x.dim() == 3:
+            if x.shape[-2] != 1:
+                raise NotImplementedError("q > 1 joint posteriors are not provided by the analytic acquisition path")
+            x = x.squeeze(-2)
+        x = self._prepared(x)
+        m, n = x.shape[0], self.train_prepared.shape[0]
+        mean = torch.empty(m, dtype=F64, device=self.device)
+        var = torch.empty(m, dtype=F64, device=self.device)
+        if m == 0:
+            return mean, var
+        lib = _lib.load()
+        chunk = min(self.chunk, (m + 127) // 128 * 128)
+        need = lib.mgb_posterior_workspace_bytes(chunk, n)
+        if self._ws is None or self._ws.numel() * 8 < need:
+            self._ws = torch.empty((need + 7) // 8, dtype=F64, device=self.device)
+        d = self.spec.desc(self.coef.shape[-1])
+        with torch.cuda.device(self.device):
+            rc = lib.mgb_series_posterior(C.byref(d), _lib.ptr(x), m, x.stride(0), _lib.ptr(self.train_prepared), n,
+                                          self.train_prepared.stride(0), _lib.ptr(self.coef), _lib.ptr(self._packed),
+                                          self.kss_value, self.mean_const, _lib.ptr(mean), _lib.ptr(var),
+                                          _lib.ptr(self._ws), self._ws.numel() * 8, chunk,
+                                          _lib.stream_ptr(self.device))
+        _lib.check(rc, "mgb_series_posterior")
+        return mean, var
+
+
+class ExpectedImprovement:
+    """Analytic EI with botorch's call convention: ``acq(X)`` with ``X`` of shape ``b x 1 x D`` -> ``b``."""
+
+    def __init__(self, model: ExactGPPosterior, best_f, maximize: bool = True):
+        self.model = model
+        self.best_f = float(best_f)
+        self.maximize = maximize
+
+    def __call__(self, x):
+        mean, var = self.model.posterior(x)
+        return expected_improvement(mean, var, self.best_f, self.maximize)
+
+
+def expected_improvement(mean, var, best_f, maximize=True):
+    sigma = var.clamp_min(1e-9).sqrt()
+    u = (mean - best_f) / sigma
+    if not maximize:
+        u = -u
+    pdf = torch.exp(-0.5 * u * u) / math.sqrt(2 * math.pi)
+    cdf = 0.5 * torch.erfc(-u / math.sqrt(2.0))
+    return sigma * (pdf + u * cdf)
+
+
+# --------------------------------------------------------------------------------------------------
+# multi-GPU: rows of X* sharded over ranks, state broadcast once, results all-gathered
+# --------------------------------------------------------------------------------------------------
+def shard_bounds(m: int, world: int, rank: int):
+    """Contiguous row block of rank ``rank``: sizes differ by at most one."""
+    base, rem = divmod(m, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ShardedPosterior:
+    """One process per GPU.  The rank that did the fit (``src``) broadcasts X_train, the packed factor
+    (L^-1 and alpha) and the series coefficients; every rank evaluates its contiguous block of candidate
+    rows with no data-path collective; mean / variance are all-gathered (or left sharded).
+
+    ``compute`` is injectable so that the partition / collective logic can be exercised with the gloo backend
+    on CPU (tests/test_sharding_gloo.py) - the product default is the CUDA posterior."""
+
+    def __init__(self, group=None, compute: Optional[Callable] = None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.compute = compute
+
+    def broadcast_state(self, tensors: dict, src: int = 0):
+        """Broadcast a dict of same-shaped-on-every-rank tensors from ``src`` (shapes are exchanged first)."""
+        dist = self.dist
+        if self.world == 1:
+            return tensors
+        names = sorted(tensors.keys()) if self.rank == src else None
+        meta = [names, {k: (tuple(tensors[k].shape), str(tensors[k].dtype)) for k in names}] if self.rank == src else [None, None]
+        dist.broadcast_object_list(meta, src=src, group=self.group)
+        names, shapes = meta
+        out = {}
+        for k in names:
+            shape, dtype = shapes[k]
+            if self.rank == src:
+                t = tensors[k].contiguous()
+            else:
+                like = next(iter(tensors.values())) if tensors else None
+                dev = like.device if like is not None else self._default_device()
+                t = torch.empty(shape, dtype=getattr(torch, dtype.split(".")[-1]), device=dev)
+            dist.broadcast(t, src=src, group=self.group)
+            out[k] = t
+        return out
+
+    def _default_device(self):
+        return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+
+    def evaluate(self, x_local: torch.Tensor, gather: bool = True, sizes=None):
+        """x_local: this rank's rows.  Returns (mean, var) for all rows (gather=True) or the local block."""
+        mean, var = self.compute(x_local)
+        if not gather or self.world == 1:
+            return mean, var
+        dist = self.dist
+        if sizes is None:
+            cnt = torch.tensor([x_local.shape[0]], dtype=torch.int64, device=mean.device)
+            allc = [torch.zeros_like(cnt) for _ in range(self.world)]
+            dist.all_gather(allc, cnt, group=self.group)
+            sizes = [int(c.item()) for c in allc]
+        packed = torch.stack([mean, var])                       # one collective for both
+        pad = max(sizes)
+        buf = torch.zeros((2, pad), dtype=packed.dtype, device=packed.device)
+        buf[:, :packed.shape[1]] = packed
+        parts = [torch.empty_like(buf) for _ in range(self.world)]
+        dist.all_gather(parts, buf, group=self.group)
+        mean_all = torch.cat([p[0, :s] for p, s in zip(parts, sizes)])
+        var_all = torch.cat([p[1, :s] for p, s in zip(parts, sizes)])
+        return mean_all, var_all

@@ -1,0 +1,146 @@
+"""-m gpu: fused exact-GP posterior (Gram chunk -> DMMA triangular product + square-sum) against the oracle's
+plain-torch exact GP (Cholesky of sK + noise I), device and host-buffer entry points."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _unit(x):
+    return x / x.norm(dim=-1, keepdim=True)
+
+
+def _setup(dim, n, m, seed, outputscale=1.3, noise=1e-2, mean_const=0.2):
+    from materngabo_b200 import kernels_sphere as ks
+    from materngabo_b200.posterior import ExactGPPosterior
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(seed)
+    xt = _unit(torch.randn(n, dim + 1, generator=gen))
+    xc = _unit(torch.randn(m, dim + 1, generator=gen))
+    y = torch.sin(3 * xt[:, 0]) + 0.1 * torch.randn(n, generator=gen)
+    k = ks.SphereRiemannianMaternKernel(dim=dim, nu=2.5)
+    k.lengthscale = 0.5
+    gp = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=outputscale, noise=noise, mean_const=mean_const).fit()
+    kfn = lambda a, b: R.sphere_matern(a, b, dim, 2.5, 0.5)  # noqa: E731
+    ref = R.gp_posterior(kfn, xt, y, xc, outputscale=outputscale, noise=noise, mean_const=mean_const)
+    return gp, xc, ref, (xt, y, k)
+
+
+@pytest.mark.parametrize("dim,n,m", [(3, 100, 500), (10, 333, 1000), (2, 17, 5), (3, 128, 129), (10, 1000, 300)])
+def test_posterior_matches_oracle(dim, n, m):
+    gp, xc, (mean_ref, var_ref), _ = _setup(dim, n, m, seed=dim * 7 + n)
+    mean, var = gp.posterior(xc.to(DEV))
+    assert rel_err(mean, mean_ref) < 1e-10
+    # variance: absolute agreement relative to the prior variance (values near 0 where candidates hit training points)
+    assert float((var.cpu() - var_ref).abs().max()) < 1e-9 * gp.outputscale
+
+
+def test_botorch_layout_and_ei():
+    from materngabo_b200.posterior import ExpectedImprovement
+    from oracle import restated as R
+
+    gp, xc, (mean_ref, var_ref), (xt, y, _) = _setup(3, 100, 100, seed=1)
+    acq = ExpectedImprovement(gp, best_f=float(y.min()), maximize=False)
+    ei = acq(xc.to(DEV).unsqueeze(-2))                       # b x 1 x D, as manifold_optimize.py:323-339
+    ref = R.expected_improvement(mean_ref, var_ref, float(y.min()), maximize=False)
+    assert ei.shape == (100,)
+    assert float((ei.cpu() - ref).abs().max()) < 1e-9
+
+
+def test_split_path_equals_single_path():
+    """Few candidates -> row tiles are dealt to several CTAs (atomics); many -> one CTA per tile.  Same numbers."""
+    gp, xc, (mean_ref, var_ref), _ = _setup(10, 700, 40000, seed=3)
+    mean_big, var_big = gp.posterior(xc.to(DEV))            # chunk 37888 + remainder: both paths exercised
+    mean_small, var_small = gp.posterior(xc[:200].to(DEV))
+    assert rel_err(mean_big[:200], mean_small) < 1e-13
+    assert float((var_big[:200] - var_small).abs().max()) < 1e-12
+    assert rel_err(mean_big, mean_ref) < 1e-10
+    assert float((var_big.cpu() - var_ref).abs().max()) < 1e-9 * gp.outputscale
+    assert (var_big > -1e-9).all()
+
+
+def test_posterior_at_training_points_reproduces_noise_level():
+    """Property: at a training input, var = s k** - k*^T (sK+noise I)^-1 k*  is below the noise level and >= 0."""
+    gp, _, _, (xt, y, _) = _setup(3, 200, 10, seed=5, outputscale=1.0, noise=1e-2, mean_const=0.0)
+    mean, var = gp.posterior(xt.to(DEV))
+    assert (var >= -1e-10).all() and (var <= 1e-2 + 1e-9).all()
+
+
+def test_host_entry_point_matches_device_path():
+    from materngabo_b200 import _lib
+
+    gp, xc, (mean_ref, var_ref), _ = _setup(10, 257, 5000, seed=9)
+    lib = _lib.load()
+    xc_h = xc.contiguous().pin_memory()
+    xt_h = gp.train_prepared.cpu().contiguous()
+    coef_h = gp.coef.cpu().contiguous()
+    rinv_h = gp.rinv.cpu().contiguous()
+    alpha_h = gp.alpha.cpu().contiguous()
+    mean_h = torch.empty(5000, dtype=torch.float64).pin_memory()
+    var_h = torch.empty(5000, dtype=torch.float64).pin_memory()
+    d = gp.spec.desc(coef_h.shape[-1])
+    rc = lib.mgb_series_posterior_host(C.byref(d), _lib.ptr(xc_h), 5000, _lib.ptr(xt_h), 257, _lib.ptr(coef_h),
+                                       _lib.ptr(rinv_h), _lib.ptr(alpha_h), gp.kss_value, gp.mean_const,
+                                       _lib.ptr(mean_h), _lib.ptr(var_h), 2048, 0)
+    _lib.check(rc, "mgb_series_posterior_host")
+    assert rel_err(mean_h, mean_ref) < 1e-10
+    assert float((var_h - var_ref).abs().max()) < 1e-9 * gp.outputscale
+
+
+def test_gram_host_entry_point():
+    from materngabo_b200 import _lib, kernels_so as kso
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(2)
+    q, _ = torch.linalg.qr(torch.randn(300, 3, 3, generator=gen))
+    q[:, :, 0] *= torch.sign(torch.linalg.det(q)).unsqueeze(-1)
+    x = q.reshape(300, 9).contiguous()
+    k = kso.SORiemannianMaternKernel(dim=3, nu=2.5)
+    k.lengthscale = 0.5
+    spec, coef = k.series()
+    coef = coef.detach().contiguous()
+    out = torch.empty(300, 211, dtype=torch.float64)
+    d = spec.desc(coef.shape[-1])
+    rc = _lib.load().mgb_series_gram_host(C.byref(d), _lib.ptr(x), 300, _lib.ptr(x[:211].contiguous()), 211,
+                                          _lib.ptr(coef), _lib.ptr(out), 0)
+    _lib.check(rc, "mgb_series_gram_host")
+    assert rel_err(out, R.so3_matern(x, x[:211], 2.5, 0.5)) < 1e-10
+
+
+def test_torus_posterior():
+    from materngabo_b200 import kernels_torus as kt
+    from materngabo_b200.posterior import ExactGPPosterior
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(4)
+    at, ac = torch.rand(60, 3, generator=gen) * 6.28, torch.rand(200, 3, generator=gen) * 6.28
+    y = torch.cos(at).sum(-1)
+    k = kt.TorusProductOfManifoldsRiemannianMaternKernel(dim=3, nu=2.5)
+    for kk in k.torus_kernel.kernels:
+        kk.lengthscale = 0.5
+    gp = ExactGPPosterior(k, at.to(DEV), y.to(DEV), outputscale=2.0, noise=1e-3).fit()
+    mean, var = gp.posterior(ac.to(DEV))
+    kfn = lambda a, b: R.torus_matern(a, b, 3, 2.5, 0.5)  # noqa: E731
+    mean_ref, var_ref = R.gp_posterior(kfn, at, y, ac, outputscale=2.0, noise=1e-3)
+    assert rel_err(mean, mean_ref) < 1e-9
+    assert float((var.cpu() - var_ref).abs().max()) < 1e-8
+
+
+def test_bad_arguments_return_errors():
+    from materngabo_b200 import _lib
+
+    lib = _lib.load()
+    d = _lib.SeriesDesc(1, 3, 0, 0, 1.0, 0.0, -1.0, 1.0)  # n_terms = 0
+    x = torch.zeros(4, 3, device=DEV, dtype=torch.float64)
+    k = torch.zeros(4, 4, device=DEV, dtype=torch.float64)
+    rc = lib.mgb_series_gram_fwd(C.byref(d), _lib.ptr(x), 4, 3, _lib.ptr(x), 4, 3, _lib.ptr(x), _lib.ptr(k), 4, None)
+    assert rc == 1 and b"n_terms" in lib.mgb_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc, "mgb_series_gram_fwd")

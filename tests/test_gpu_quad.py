@@ -1,0 +1,115 @@
+"""-m gpu: quadrature kernels (hyperbolic H^1/H^2/H^3, SPD(2)) against golden vectors from the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import TOL, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.tensor(np.asarray(a), dtype=torch.float64, device=DEV)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_hyperbolic_matern(dim):
+    from materngabo_b200 import kernels_hyperbolic as kh
+
+    g = load_golden("hyperbolic_matern_H%d" % dim)
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=dim, nu=2.5, nb_points_integral=int(g["P"]))
+    k.lengthscale = float(g["lengthscale"])
+    out = k.forward(_t(g["x1"]), _t(g["x2"]))
+    assert rel_err(out, g["K"]) < TOL
+    # hyper-parameter gradient (node weights are differentiable, the grid is detached as in the reference)
+    k.raw_lengthscale.requires_grad_(True)
+    out = k.forward(_t(g["x1"]), _t(g["x2"]))
+    (gl,) = torch.autograd.grad((out * _t(g["G"])).sum(), [k.raw_lengthscale])
+    assert rel_err(gl.reshape(-1), g["g_raw_lengthscale"].reshape(-1)) < 1e-9
+
+
+def test_hyperbolic_matern_self_distance():
+    from materngabo_b200 import kernels_hyperbolic as kh
+
+    g = load_golden("hyperbolic_matern_H2_self")
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=64)
+    k.lengthscale = 1.0
+    assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_hyperbolic_heat(dim):
+    from materngabo_b200 import kernels_hyperbolic as kh
+
+    g = load_golden("hyperbolic_heat_H%d" % dim)
+    k = kh.HyperbolicRiemannianMillsonGaussianKernel(dim=dim, nb_points_integral=int(g["P"]))
+    k.lengthscale = float(g["lengthscale"])
+    assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
+
+
+def test_hyperbolic_unsupported_dim():
+    from materngabo_b200 import kernels_hyperbolic as kh
+
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=4, nu=2.5)
+    with pytest.raises(NotImplementedError):
+        k.forward(torch.zeros(2, 5, device=DEV), torch.zeros(2, 5, device=DEV))
+
+
+@pytest.mark.parametrize("name", ["spd2_matern", "spd2_matern_self"])
+def test_spd2_matern(name):
+    from materngabo_b200 import kernels_spd as ksp
+
+    g = load_golden(name)
+    k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5, nb_points_integral_b=int(g["Pb"]), nb_points_integral_t=int(g["Pt"]))
+    k.lengthscale = float(g["lengthscale"])
+    assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
+
+
+def test_spd2_heat():
+    from materngabo_b200 import kernels_spd as ksp
+
+    g = load_golden("spd2_heat")
+    k = ksp.SpdRiemannianGaussianKernel(2, nb_points_integral=int(g["Pb"]))
+    k.lengthscale = float(g["lengthscale"])
+    assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
+
+
+def test_spd_dim3_raises_like_reference():
+    from materngabo_b200 import kernels_spd as ksp
+
+    with pytest.raises(NotImplementedError):
+        ksp.SpdRiemannianIntegratedMaternKernel(3, nu=2.5)
+
+
+def test_h2_config4_block_vs_oracle():
+    """BASELINE config 4 geometry (H^2, 64 x 64 nodes) on a block the oracle finishes in seconds."""
+    from materngabo_b200 import kernels_hyperbolic as kh
+    from oracle import restated as R
+
+    torch.manual_seed(0)
+    z = torch.randn(2000, 2)
+    x = torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1)
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=64)
+    k.lengthscale = 1.0
+    full = k.forward(x.to(DEV), x.to(DEV))                       # 2k x 2k, 4096 nodes per entry
+    ref = R.hyperbolic_integrated_matern(x[:96], x[:80], 2, 2.5, 1.0, 64)
+    assert rel_err(full[:96, :80], ref) < TOL
+    assert rel_err(full, full.t()) < 1e-12
+    assert torch.isfinite(full).all()
+
+
+def test_spd2_config4_block_vs_oracle():
+    from materngabo_b200 import kernels_spd as ksp
+    from oracle import restated as R
+
+    torch.manual_seed(0)
+    a = torch.randn(512, 2, 2)
+    s = a @ a.transpose(-1, -2) + 0.5 * torch.eye(2)
+    v = torch.stack([s[:, 0, 0], s[:, 1, 1], s[:, 0, 1] * 2 ** 0.5], -1)
+    k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5, nb_points_integral_b=64, nb_points_integral_t=64)
+    k.lengthscale = 1.0
+    full = k.forward(v.to(DEV), v.to(DEV))
+    ref = R.spd2_integrated_matern(v[:48], v[:40], 2.5, 1.0, 64, 64)
+    assert rel_err(full[:48, :40], ref) < TOL
+    assert rel_err(full, full.t()) < 1e-10

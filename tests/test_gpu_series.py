@@ -1,0 +1,284 @@
+"""-m gpu: the CUDA series kernels (through the C-ABI) against the golden vectors generated from the unmodified
+reference and against the restated oracle, forward and backward, plus the shapes / edge cases the drop-in
+boundary has to accept.  Tolerance: 1e-10 relative to max|K_ref| (float64)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import TOL, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.tensor(np.asarray(a), dtype=torch.float64, device=DEV)
+
+
+def _sphere(name, cls, g, **kw):
+    from materngabo_b200 import kernels_sphere as ks
+
+    k = getattr(ks, cls)(dim=int(g["dim"]), **kw)
+    k.lengthscale = float(g["lengthscale"])
+    return k
+
+
+@pytest.mark.parametrize("name", ["sphere_matern_S2", "sphere_matern_S3", "sphere_matern_S10", "sphere_matern_S2_self",
+                                  "sphere_matern_S3_example"])
+def test_sphere_matern_forward(name):
+    g = load_golden(name)
+    k = _sphere(name, "SphereRiemannianMaternKernel", g, nu=float(g["nu"]))
+    out = k.forward(_t(g["x1"]), _t(g["x2"]))
+    assert out.shape == g["K"].shape
+    assert rel_err(out, g["K"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["sphere_gaussian_S2", "sphere_gaussian_S3", "sphere_gaussian_S10"])
+def test_sphere_gaussian_forward(name):
+    g = load_golden(name)
+    k = _sphere(name, "SphereRiemannianGaussianKernel", g)
+    assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
+
+
+def test_sphere_integrated_matern():
+    g = load_golden("sphere_intmatern_S3")
+    k = _sphere("", "SphereRiemannianIntegratedMaternKernel", g, nu=2.5)
+    assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
+
+
+def _grad_case(kernel, g, params):
+    x1 = _t(g["x1"]).requires_grad_(True)
+    x2 = _t(g["x2"]).requires_grad_(True)
+    out = kernel.forward(x1, x2)
+    plist = [getattr(kernel, p) for p in params]
+    for p in plist:
+        p.requires_grad_(True)
+    res = torch.autograd.grad((out * _t(g["G"])).sum(), [x1, x2] + plist)
+    assert rel_err(out, g["K"]) < TOL
+    assert rel_err(res[0], g["gx1"]) < 1e-9
+    assert rel_err(res[1], g["gx2"]) < 1e-9
+    for name, val in zip(params, res[2:]):
+        assert rel_err(val.reshape(-1), g["g_" + name].reshape(-1)) < 1e-9, name
+
+
+@pytest.mark.parametrize("name", ["sphere_matern_S2", "sphere_matern_S3", "sphere_matern_S10"])
+def test_sphere_matern_backward(name):
+    g = load_golden(name)
+    _grad_case(_sphere(name, "SphereRiemannianMaternKernel", g, nu=float(g["nu"])), g, ["raw_lengthscale"])
+
+
+def test_sphere_matern_nu_gradient():
+    from materngabo_b200 import kernels_sphere as ks
+
+    g = load_golden("sphere_matern_S2_nugrad")
+    k = ks.SphereRiemannianMaternKernel(dim=2, nu=None)
+    k.lengthscale = float(g["lengthscale"])
+    k.nu = float(g["nu"])
+    _grad_case(k, g, ["raw_lengthscale", "raw_nu"])
+
+
+def test_sphere_gaussian_backward():
+    g = load_golden("sphere_gaussian_S3")
+    _grad_case(_sphere("", "SphereRiemannianGaussianKernel", g), g, ["raw_lengthscale"])
+
+
+def test_circle_kernels():
+    from materngabo_b200 import kernels_sphere as ks
+
+    g = load_golden("circle_gaussian")
+    k = ks.CircleRiemannianGaussianKernel()
+    k.lengthscale = float(g["lengthscale"])
+    _grad_case(k, g, ["raw_lengthscale"])
+    g = load_golden("circle_intmatern")
+    k = ks.CircleRiemannianIntegratedMaternKernel(nu=2.5)
+    k.lengthscale = float(g["lengthscale"])
+    _grad_case(k, g, ["raw_lengthscale"])
+
+
+@pytest.mark.parametrize("dim", [3, 10])
+def test_torus(dim):
+    from materngabo_b200 import kernels_torus as kt
+
+    for kind, cls in (("matern", "TorusProductOfManifoldsRiemannianMaternKernel"),
+                      ("gaussian", "TorusProductOfManifoldsRiemannianGaussianKernel")):
+        g = load_golden("torus_%s_T%d" % (kind, dim))
+        k = getattr(kt, cls)(dim=dim, **({"nu": 2.5} if kind == "matern" else {}))
+        for c, kk in enumerate(k.torus_kernel.kernels):
+            kk.lengthscale = float(g["lengthscales"][c])
+        out = k.forward(_t(g["x1"]), _t(g["x2"]))          # angle inputs
+        assert rel_err(out, g["K"]) < TOL
+        x1c = k._to_circles(_t(g["x1"]))                    # (cos, sin) inputs give the same matrix
+        assert rel_err(k.forward(x1c, k._to_circles(_t(g["x2"]))), g["K"]) < TOL
+
+
+def test_torus_backward_matches_oracle_autograd():
+    from materngabo_b200 import kernels_torus as kt
+    from oracle import restated as R
+
+    torch.manual_seed(3)
+    a1, a2 = torch.rand(9, 3) * 6.28, torch.rand(7, 3) * 6.28
+    G = torch.randn(9, 7)
+    ls = [0.4, 0.5, 0.6]
+    k = kt.TorusProductOfManifoldsRiemannianMaternKernel(dim=3, nu=2.5)
+    for c, kk in enumerate(k.torus_kernel.kernels):
+        kk.lengthscale = ls[c]
+    c1 = k._to_circles(a1).to(DEV).requires_grad_(True)
+    c2 = k._to_circles(a2).to(DEV)
+    out = k.forward(c1, c2)
+    params = [kk.raw_lengthscale for kk in k.torus_kernel.kernels]
+    res = torch.autograd.grad((out * G.to(DEV)).sum(), [c1] + params)
+    # oracle: same thing through torch autograd on CPU
+    raw = [kk.raw_lengthscale.detach().clone().requires_grad_(True) for kk in k.torus_kernel.kernels]
+    oc1 = k._to_circles(a1).requires_grad_(True)
+    ref = R.torus_matern(oc1, k._to_circles(a2), 3, 2.5, [torch.nn.functional.softplus(r) for r in raw])
+    rres = torch.autograd.grad((ref * G).sum(), [oc1] + raw)
+    assert rel_err(out, ref) < TOL
+    assert rel_err(res[0], rres[0]) < 1e-9
+    for a, b in zip(res[1:], rres[1:]):
+        assert rel_err(a, b) < 1e-9
+
+
+@pytest.mark.parametrize("name,cls", [("so3_matern", "SORiemannianMaternKernel"), ("so3_gaussian", "SORiemannianGaussianKernel"),
+                                      ("so3_matern_self", "SORiemannianMaternKernel")])
+def test_so3(name, cls):
+    from materngabo_b200 import kernels_so as kso
+
+    g = load_golden(name)
+    k = getattr(kso, cls)(dim=3, **({"nu": 2.5} if "Matern" in cls else {}))
+    k.lengthscale = float(g["lengthscale"])
+    if "G" in g:
+        _grad_case(k, g, ["raw_lengthscale"])
+    else:
+        assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
+
+
+def test_so_other_dims_raise():
+    from materngabo_b200 import kernels_so as kso
+
+    k = kso.SORiemannianMaternKernel(dim=4, nu=2.5)
+    with pytest.raises(NotImplementedError):
+        k.forward(torch.zeros(2, 16, device=DEV), torch.zeros(2, 16, device=DEV))
+
+
+def test_circle_dimension_raises_like_reference():
+    from materngabo_b200 import kernels_sphere as ks
+
+    with pytest.raises(ValueError):  # math.gamma(0), as in the reference for S^1 via the Gegenbauer classes
+        ks.SphereRiemannianMaternKernel(dim=1, nu=2.5)
+
+
+# ---- shapes the gpytorch / botorch callers use ---------------------------------------------------
+def test_batch_layouts_and_diag():
+    from materngabo_b200 import kernels_sphere as ks
+    from oracle import restated as R
+
+    torch.manual_seed(0)
+    k = ks.SphereRiemannianMaternKernel(dim=3, nu=2.5)
+    k.lengthscale = 0.5
+    xb = torch.nn.functional.normalize(torch.randn(17, 1, 4), dim=-1)
+    xt = torch.nn.functional.normalize(torch.randn(23, 4), dim=-1)
+    ref = R.sphere_matern(xb, xt.expand(17, 23, 4), 3, 2.5, 0.5)
+    out = k.forward(xb.to(DEV), xt.to(DEV).expand(17, 23, 4))      # botorch posterior layout b x 1 x D vs b x N x D
+    assert out.shape == (17, 1, 23) and rel_err(out, ref) < TOL
+    x3 = torch.nn.functional.normalize(torch.randn(3, 5, 4), dim=-1)  # genuinely batched
+    y3 = torch.nn.functional.normalize(torch.randn(3, 6, 4), dim=-1)
+    assert rel_err(k.forward(x3.to(DEV), y3.to(DEV)), R.sphere_matern(x3, y3, 3, 2.5, 0.5)) < TOL
+    d = k.forward(xt.to(DEV), xt.to(DEV), diag=True)
+    assert d.shape == (23,) and rel_err(d, R.sphere_matern(xt, xt, 3, 2.5, 0.5, diag=True).reshape(-1)) < TOL
+    kk = k(xt.to(DEV))                                             # Kernel.__call__ with x2 = None
+    assert rel_err(kk, R.sphere_matern(xt, xt, 3, 2.5, 0.5)) < TOL
+
+
+@pytest.mark.parametrize("m,n", [(0, 5), (5, 0), (1, 1), (129, 65), (257, 3), (64, 127), (1, 1001)])
+def test_ragged_sizes(m, n):
+    from materngabo_b200 import kernels_sphere as ks
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(m * 1000 + n)
+    k = ks.SphereRiemannianMaternKernel(dim=2, nu=2.5)
+    k.lengthscale = 0.5
+    x1 = torch.nn.functional.normalize(torch.randn(max(m, 1), 3, generator=gen), dim=-1)[:m]
+    x2 = torch.nn.functional.normalize(torch.randn(max(n, 1), 3, generator=gen), dim=-1)[:n]
+    out = k.forward(x1.to(DEV), x2.to(DEV))
+    assert out.shape == (m, n)
+    if m and n:
+        assert rel_err(out, R.sphere_matern(x1, x2, 2, 2.5, 0.5)) < TOL
+
+
+def test_non_contiguous_and_strided_inputs():
+    from materngabo_b200 import kernels_sphere as ks
+    from oracle import restated as R
+
+    torch.manual_seed(5)
+    big = torch.nn.functional.normalize(torch.randn(40, 4), dim=-1)
+    k = ks.SphereRiemannianMaternKernel(dim=3, nu=2.5)
+    k.lengthscale = 0.5
+    x1 = big.to(DEV)[::2]            # row-strided view
+    x2 = big.to(DEV)[1:, :]          # offset view: base pointer not 16-byte aligned relative to the panel
+    assert rel_err(k.forward(x1, x2), R.sphere_matern(big[::2], big[1:], 3, 2.5, 0.5)) < TOL
+
+
+def test_generic_width_and_many_terms_use_general_kernel():
+    from materngabo_b200 import kernels_sphere as ks
+    from oracle import restated as R
+
+    torch.manual_seed(6)
+    x = torch.nn.functional.normalize(torch.randn(50, 8), dim=-1)   # S^7: no register-resident specialisation
+    k = ks.SphereRiemannianMaternKernel(dim=7, nu=1.5)
+    k.lengthscale = 0.7
+    assert rel_err(k.forward(x.to(DEV), x[:30].to(DEV)), R.sphere_matern(x, x[:30], 7, 1.5, 0.7)) < TOL
+    k = ks.SphereRiemannianMaternKernel(dim=2, nu=2.5, serie_nb_terms=20)  # T > 12 -> Chebyshev basis
+    k.lengthscale = 0.3
+    y = torch.nn.functional.normalize(torch.randn(40, 3), dim=-1)
+    assert rel_err(k.forward(y.to(DEV), y.to(DEV)), R.sphere_matern(y, y, 2, 2.5, 0.3, terms=20)) < TOL
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    from materngabo_b200 import kernels_sphere as ks
+    from materngabo_b200._lib import MgbError
+
+    k = ks.SphereRiemannianMaternKernel(dim=2, nu=2.5)
+    x = torch.nn.functional.normalize(torch.randn(4, 3), dim=-1)
+    with pytest.raises(MgbError):
+        k.forward(x, x)
+
+
+def test_config1_full_size_vs_oracle():
+    """BASELINE config 1: S^2 Matern nu=2.5 kappa=0.5, 1000 x 1000, seed 0."""
+    from materngabo_b200 import kernels_sphere as ks
+    from oracle import restated as R
+
+    torch.manual_seed(0)
+    x = torch.randn(1000, 3)
+    x = x / x.norm(dim=-1, keepdim=True)
+    k = ks.SphereRiemannianMaternKernel(dim=2, nu=2.5)
+    k.lengthscale = 0.5
+    out = k.forward(x.to(DEV), x.to(DEV))
+    assert rel_err(out, R.sphere_matern(x, x, 2, 2.5, 0.5)) < TOL
+    assert rel_err(out, out.t()) < 1e-14                     # symmetry
+    assert torch.linalg.eigvalsh(out + 1e-8 * torch.eye(1000, device=DEV)).min() > 0  # PD (kernels_so.py:365-400 style check)
+
+
+def test_large_gram_properties():
+    """Size-independent checks at a size the oracle cannot reach: row blocks of a 200k x 2k SO(3) Gram agree with
+    the same rows computed alone, and a sampled set of entries agrees with the oracle."""
+    from materngabo_b200 import kernels_so as kso
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(11)
+    q, r = torch.linalg.qr(torch.randn(2000, 3, 3, generator=gen))
+    q = q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1)).unsqueeze(-2)
+    q[:, :, 0] *= torch.sign(torch.linalg.det(q)).unsqueeze(-1)
+    base = q.reshape(2000, 9)
+    idx = torch.randint(0, 2000, (200000,), generator=gen)
+    xc = base[idx].to(DEV)
+    k = kso.SORiemannianMaternKernel(dim=3, nu=2.5)
+    k.lengthscale = 0.5
+    big = k.forward(xc, base.to(DEV))
+    assert big.shape == (200000, 2000)
+    rows = torch.tensor([0, 1, 127, 128, 99999, 199999])
+    small = k.forward(xc[rows.to(DEV)], base.to(DEV))
+    assert torch.equal(big[rows.to(DEV)], small)              # tiling does not change values
+    ref = R.so3_matern(base[idx[rows]], base[:300], 2.5, 0.5)
+    assert rel_err(big[rows.to(DEV)][:, :300], ref) < TOL
+    assert torch.isfinite(big).all()
