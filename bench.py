@@ -1,0 +1,583 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the hot path (see BASELINE.json / SURVEY.md section 8d).
+
+Default workload (BASELINE.json configs[4]): S^10 Riemannian Matern (nu=2.5, kappa=0.5, 10 terms) exact-GP
+posterior mean/variance for 10M candidates x 5k training points, candidate rows sharded over the N GPUs of
+one box (strong scaling, one process per GPU, NCCL only for the state broadcast and the mean/var all-gather).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA, sm_100a)
+  python bench.py --impl reference ...                          the reference's CPU algorithm (oracle port)
+  python bench.py --workload gram-so3|gram-s2|gram-s10|gram-t10|gram-h2|gram-spd2   Gram-matrix workloads
+
+Rank 0 prints ONE JSON line.  ``value`` = candidates/s with inputs resident in HBM; ``e2e`` = the same through
+the host-buffer C-ABI call (pinned host inputs, H2D + D2H inside the timed region).  The oracle is used only
+by the cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+F64 = torch.float64
+NOMINAL_FP64_TFLOPS = 37.2   # 148 SM x 64 FMA/clk x 2 x 1.965 GHz
+
+
+# ---------------------------------------------------------------------------------------------------
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="posterior-s10")
+    ap.add_argument("--m", type=int, default=None, help="override candidate / row count")
+    ap.add_argument("--n", type=int, default=None, help="override training / column count")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # samples under load only (idle samples before/after the region would drag the median down)
+        loaded = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] if power else sm
+        return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def unit_rows(m, d, gen, device):
+    x = torch.randn(m, d, generator=gen, device=device, dtype=F64)
+    return x / x.norm(dim=-1, keepdim=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# posterior workload
+# ---------------------------------------------------------------------------------------------------
+def posterior_problem(n, device, seed=0):
+    """Training set + fit for S^10 (SURVEY.md 8d cfg 5): kappa=0.5, nu=2.5, T=10, noise 1e-2, outputscale 1."""
+    from materngabo_b200 import kernels_sphere
+    from materngabo_b200.posterior import ExactGPPosterior
+
+    gen = torch.Generator(device=device).manual_seed(seed)
+    xt = unit_rows(n, 11, gen, device)
+    y = torch.sin(3.0 * xt[:, 0]) + 0.5 * xt[:, 1] * xt[:, 2]
+    k = kernels_sphere.SphereRiemannianMaternKernel(dim=10, nu=2.5)
+    k.lengthscale = 0.5
+    gp = ExactGPPosterior(k, xt, y, outputscale=1.0, noise=1e-2, mean_const=0.0)
+    return gp, k
+
+
+def flops_per_candidate(n):
+    """N*78 (kernel row) + 2N (mean) + N^2 (triangular L^-1 k*, N^2/2 FMA) + 2N (norm)."""
+    return n * 78.0 + 2.0 * n + float(n) * n + 2.0 * n
+
+
+def run_posterior(args, rank, world, local):
+    import torch.distributed as dist
+    from materngabo_b200 import _lib
+    from materngabo_b200.posterior import ExactGPPosterior, ShardedPosterior, shard_bounds
+
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    lib = _lib.load()
+    m_total = args.m or 10_000_000
+    n = args.n or 5000
+    lo, hi = shard_bounds(m_total, world, rank)
+    m_local = hi - lo
+
+    # rank 0 owns the fit; the other ranks receive the state every step (as after a refit in the BO loop)
+    gp, kernel = posterior_problem(n, device)
+    if rank == 0:
+        gp.fit()
+    sh = ShardedPosterior(compute=None) if world > 1 else None
+    gen = torch.Generator(device=device).manual_seed(1234 + rank)
+    xc = unit_rows(m_local, 11, gen, device)                      # this rank's candidate rows, HBM resident
+    spec, coef0 = kernel.series()
+
+    def step():
+        if world > 1:
+            state = sh.broadcast_state(gp.state() if rank == 0 else {"like": xc[:0]}, src=0)
+            if rank != 0:
+                gp.load_state(spec, state["train"], state["packed"], state["coef"],
+                              _self_k(spec, state["coef"]))
+        mean, var = gp.posterior(xc)
+        if world > 1:
+            sizes = [shard_bounds(m_total, world, r)[1] - shard_bounds(m_total, world, r)[0] for r in range(world)]
+            sh.compute = lambda _x: (mean, var)
+            mean, var = sh.evaluate(xc, gather=True, sizes=sizes)
+        return mean, var
+
+    def _self_k(spec_, coef_):
+        from materngabo_b200.posterior import _self_kernel_value
+        return _self_kernel_value(spec_, coef_)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    launches0 = lib.mgb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        mean, var = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.mgb_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms, float(launches)], dtype=F64, device=device)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, launches = float(tmax[0]), int(tsum[1])
+    ms_per_step = ms / args.steps
+    value = m_total / (ms_per_step * 1e-3)
+    checksum = float(mean[: min(1000, mean.numel())].sum() + var[: min(1000, var.numel())].sum())
+
+    # ---- per-kernel roofline pass (rank 0): events around every posterior_reduce launch -----------
+    roof = None
+    if rank == 0:
+        roof = posterior_roofline(gp, xc, n, lib)
+
+    # ---- end to end through the host-buffer C-ABI call -------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = posterior_e2e(args, gp, rank, world, local, m_total, m_local, n, xc, dist)
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": "posterior_cands_per_sec", "value": value, "unit": "candidates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "S^10 Riemannian Matern nu=2.5 kappa=0.5 T=10 exact-GP posterior mean/var, "
+                                   "%d candidates x %d training points, candidate rows sharded over %d GPU(s); "
+                                   "BASELINE.json configs[4]" % (m_total, n, world),
+                       "candidates": m_total, "train": n, "chunk": gp.chunk,
+                       "l2_policy": "inputs larger than L2: every step streams %.1f GB of Gram chunks through HBM "
+                                    "(chunk buffer %.2f GB > 126 MB L2)" % (8e-9 * m_total * n / world,
+                                                                            8e-9 * gp.chunk * n)},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e,
+            "checksum": checksum,
+        }
+    return out
+
+
+def posterior_roofline(gp, xc, n, lib):
+    """Average duration of posterior_reduce_kernel launches (the FLOP-dominant kernel), CUDA events on the
+    launching stream, against the FP64 tensor (DMMA) peak micro-benchmarked in this same run."""
+    from materngabo_b200 import _lib
+
+    chunk = gp.chunk
+    reps = min(6, max(1, xc.shape[0] // chunk))
+    if xc.shape[0] < chunk:
+        chunk = xc.shape[0]
+        reps = 1
+    ldk = (n + 15) // 16 * 16
+    kc = torch.empty((chunk, ldk), dtype=F64, device=xc.device)
+    kss = torch.full((chunk,), gp.kss_value, dtype=F64, device=xc.device)
+    mean = torch.empty(chunk, dtype=F64, device=xc.device)
+    var = torch.empty(chunk, dtype=F64, device=xc.device)
+    d = gp.spec.desc(gp.coef.shape[-1])
+    st = _lib.stream_ptr(xc.device)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(reps + 1)]
+    for i in range(reps + 1):      # first pass warms up
+        x = xc[(i % reps) * chunk:(i % reps) * chunk + chunk]
+        ev[i][0].record()
+        _lib.check(lib.mgb_series_gram_fwd(C.byref(d), _lib.ptr(x), chunk, x.stride(0), _lib.ptr(gp.train_prepared), n,
+                                           gp.train_prepared.stride(0), _lib.ptr(gp.coef), _lib.ptr(kc), ldk, st), "gram")
+        ev[i][1].record()
+        _lib.check(lib.mgb_posterior_reduce(_lib.ptr(kc), chunk, n, ldk, _lib.ptr(gp._packed), _lib.ptr(kss),
+                                            gp.mean_const, _lib.ptr(mean), _lib.ptr(var), st), "reduce")
+        ev[i][2].record()
+    torch.cuda.synchronize()
+    gram_ms = statistics.mean(ev[i][0].elapsed_time(ev[i][1]) for i in range(1, reps + 1))
+    red_ms = statistics.mean(ev[i][1].elapsed_time(ev[i][2]) for i in range(1, reps + 1))
+    tf, pk_ms = C.c_double(), C.c_double()
+    _lib.check(lib.mgb_fp64_peak(1, 3, C.byref(tf), C.byref(pk_ms)), "mgb_fp64_peak")
+    tf_dfma = C.c_double()
+    _lib.check(lib.mgb_fp64_peak(0, 3, C.byref(tf_dfma), None), "mgb_fp64_peak")
+    alg_flops = chunk * (float(n) * n + 4.0 * n)      # triangular product + mean + norm, per launch
+    achieved = alg_flops / (red_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "posterior_reduce_kernel (FP64 DMMA m8n8k4)", "achieved": achieved,
+            "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value, "traffic": None,
+            "peak_source": "FP64 DMMA register-resident micro-benchmark measured in this run "
+                           "(MEASURED_PEAKS.json has no FP64 figure; nominal %.1f; DFMA micro-benchmark %.1f)"
+                           % (NOMINAL_FP64_TFLOPS, tf_dfma.value),
+            "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
+            "launch_ms": red_ms, "algorithmic_flops_per_launch": alg_flops, "candidates_per_launch": chunk,
+            "gram_kernel": {"launch_ms": gram_ms, "achieved_GBps": 8.0 * chunk * n / (gram_ms * 1e-3) / 1e9,
+                            "hbm_peak_GBps": measured_peaks().get("hbm_gbs"), "bytes_per_entry": 8}}
+
+
+def posterior_e2e(args, gp, rank, world, local, m_total, m_local, n, xc, dist):
+    """Same metric through mgb_series_posterior_host: pinned HOST candidates / factor in, HOST mean/var out."""
+    from materngabo_b200 import _lib
+
+    lib = _lib.load()
+    device = torch.device("cuda", local)
+    if world > 1 and rank != 0:
+        # every rank needs the fitted state on the host: rank 0 broadcasts, then all move to pinned memory
+        pass
+    state = {}
+    if world > 1:
+        from materngabo_b200.posterior import ShardedPosterior
+        sh = ShardedPosterior(compute=None)
+        full = sh.broadcast_state({"train": gp.train_prepared, "coef": gp.coef, "rinv": gp.rinv, "alpha": gp.alpha}
+                                  if rank == 0 else {"like": xc[:0]}, src=0)
+        state = full
+    else:
+        state = {"train": gp.train_prepared, "coef": gp.coef, "rinv": gp.rinv, "alpha": gp.alpha}
+    xc_h = xc.cpu().pin_memory()
+    xt_h = state["train"].cpu().pin_memory()
+    coef_h = state["coef"].cpu().contiguous()
+    rinv_h = state["rinv"].cpu().pin_memory()
+    alpha_h = state["alpha"].cpu().pin_memory()
+    mean_h = torch.empty(m_local, dtype=F64).pin_memory()
+    var_h = torch.empty(m_local, dtype=F64).pin_memory()
+    spec = gp.spec
+    if spec is None:
+        spec, _ = gp.kernel.series()
+    from materngabo_b200.posterior import _self_kernel_value
+    kss = _self_kernel_value(spec, coef_h)
+    d = spec.desc(coef_h.shape[-1])
+
+    def call():
+        _lib.check(lib.mgb_series_posterior_host(C.byref(d), _lib.ptr(xc_h), m_local, _lib.ptr(xt_h), n, _lib.ptr(coef_h),
+                                                 _lib.ptr(rinv_h), _lib.ptr(alpha_h), kss, gp.mean_const,
+                                                 _lib.ptr(mean_h), _lib.ptr(var_h), gp.chunk, local), "posterior_host")
+
+    steps = max(1, min(args.steps, 2))
+    call()  # warm-up (allocations, page faults)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=F64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t[0])
+    h2d = 8 * (m_local * 11 + n * 11 + n * n + n + coef_h.numel())
+    d2h = 8 * 2 * m_local
+    return {"value": m_total / (dt / steps), "unit": "candidates/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "steps": steps,
+            "api": "mgb_series_posterior_host (C-ABI, pinned host buffers, per rank)",
+            "sample_mean0": float(mean_h[0]), "timer": "host wall clock around the synchronous C-ABI call, max over ranks"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# Gram workloads (single GPU or row-sharded, weak scaling: rows per GPU fixed)
+# ---------------------------------------------------------------------------------------------------
+def gram_setup(name, device, m, n):
+    from materngabo_b200 import kernels_hyperbolic, kernels_so, kernels_spd, kernels_sphere, kernels_torus
+
+    gen = torch.Generator(device=device).manual_seed(0)
+    if name in ("gram-s2", "gram-s10"):
+        dim = 2 if name == "gram-s2" else 10
+        k = kernels_sphere.SphereRiemannianMaternKernel(dim=dim, nu=2.5)
+        k.lengthscale = 0.5
+        x1, x2 = unit_rows(m, dim + 1, gen, device), unit_rows(n, dim + 1, gen, device)
+        flops = 2 * (dim + 1) + 2 + 6 * 8 + 6
+    elif name == "gram-so3":
+        k = kernels_so.SORiemannianMaternKernel(dim=3, nu=2.5)
+        k.lengthscale = 0.5
+
+        def rot(cnt):
+            q, r = torch.linalg.qr(torch.randn(cnt, 3, 3, generator=gen, device=device, dtype=F64))
+            q = q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1)).unsqueeze(-2)
+            q[:, :, 0] = q[:, :, 0] * torch.sign(torch.linalg.det(q)).unsqueeze(-1)
+            return q.reshape(cnt, 9).contiguous()
+        x1, x2 = rot(m), rot(n)
+        flops = 62
+    elif name == "gram-t10":
+        k = kernels_torus.TorusProductOfManifoldsRiemannianMaternKernel(dim=10, nu=2.5)
+        for kk in k.torus_kernel.kernels:
+            kk.lengthscale = 0.5
+        x1 = k._to_circles(torch.rand(m, 10, generator=gen, device=device, dtype=F64) * 6.283185307179586)
+        x2 = k._to_circles(torch.rand(n, 10, generator=gen, device=device, dtype=F64) * 6.283185307179586)
+        flops = None
+    elif name == "gram-h2":
+        k = kernels_hyperbolic.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=64)
+        k.lengthscale = 1.0
+
+        def lor(cnt):
+            z = torch.randn(cnt, 2, generator=gen, device=device, dtype=F64)
+            return torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1).contiguous()
+        x1, x2 = lor(m), lor(n)
+        flops = 4096 * 32
+    elif name == "gram-spd2":
+        k = kernels_spd.SpdRiemannianIntegratedMaternKernel(2, nu=2.5, nb_points_integral_b=64, nb_points_integral_t=64)
+        k.lengthscale = 1.0
+
+        def spd(cnt):
+            a = torch.randn(cnt, 2, 2, generator=gen, device=device, dtype=F64)
+            s = a @ a.transpose(-1, -2) + 0.5 * torch.eye(2, device=device, dtype=F64)
+            return torch.stack([s[:, 0, 0], s[:, 1, 1], s[:, 0, 1] * 2 ** 0.5], -1).contiguous()
+        x1, x2 = spd(m), spd(n)
+        flops = 4096 * 32
+    else:
+        raise SystemExit("unknown workload %s" % name)
+    return k, x1, x2, flops
+
+
+GRAM_DEFAULTS = {"gram-s2": (1_000_000, 2000), "gram-s10": (1_000_000, 2000), "gram-so3": (1_000_000, 2000),
+                 "gram-t10": (1_000_000, 2000), "gram-h2": (2000, 2000), "gram-spd2": (2000, 2000)}
+
+
+def run_gram(args, rank, world, local):
+    import torch.distributed as dist
+    from materngabo_b200 import _lib
+
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    lib = _lib.load()
+    m, n = GRAM_DEFAULTS[args.workload]
+    m, n = args.m or m, args.n or n
+    kernel, x1, x2, flops = gram_setup(args.workload, device, m, n)
+
+    def step():
+        with torch.no_grad():
+            return kernel.forward(x1, x2)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step()
+        del out
+    barrier()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    launches0 = lib.mgb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.mgb_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms, float(launches)], dtype=F64, device=device)
+    if world > 1:
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, launches = float(tmax[0]), int(tsum[1])
+    ms_per_step = ms / args.steps
+    entries = float(m) * n * world
+    value = entries / (ms_per_step * 1e-3)
+    if rank != 0:
+        return None
+    peaks = measured_peaks()
+    quad = args.workload in ("gram-h2", "gram-spd2", "gram-t10")
+    if quad:
+        tf = C.c_double()
+        _lib.check(lib.mgb_fp64_peak(0, 3, C.byref(tf), None), "mgb_fp64_peak")
+        ach = (flops or 0) * float(m) * n / (ms_per_step * 1e-3) / 1e12 if flops else None
+        roof = {"bound": "fp64", "achieved": ach, "peak": tf.value, "unit": "TFLOP/s",
+                "frac": (ach / tf.value) if ach else None, "traffic": None,
+                "note": "algorithmic convention of SURVEY.md 8d: 32 flops per quadrature node (one exp = 28); the kernel "
+                        "executes fewer (factorised exponentials), so frac can exceed what the pipe sustains",
+                "peak_source": "DFMA micro-benchmark in this run"}
+    else:
+        ach = 8.0 * m * n / (ms_per_step * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
+                "frac": ach / peaks.get("hbm_gbs", 6650.0), "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "bytes_per_entry": 8}
+    return {"metric": "kernel_entries_per_sec", "value": value, "unit": "entries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s K(X*, X) %d x %d per GPU" % (args.workload, m, n), "rows": m, "cols": n,
+                       "l2_policy": "output %.2f GB per step >> L2" % (8e-9 * m * n)},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": None,
+            "checksum": float(out[:8, :8].sum())}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU legs (oracle port = the reference's torch algorithm on the host cores)
+# ---------------------------------------------------------------------------------------------------
+def cpu_posterior_state(n):
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(0)
+    xt = torch.randn(n, 11, generator=gen, dtype=F64)
+    xt = xt / xt.norm(dim=-1, keepdim=True)
+    y = torch.sin(3.0 * xt[:, 0]) + 0.5 * xt[:, 1] * xt[:, 2]
+    kfn = lambda a, b: R.sphere_matern(a, b, 10, 2.5, 0.5)  # noqa: E731
+    return R, kfn, xt, y
+
+
+_CPU_FIT = {}
+
+
+def cpu_posterior_rate(n, sample, chunk=512):
+    """candidates/s of the oracle port (reference algorithm, torch CPU ops, all host threads).  The fit
+    (Cholesky of n x n) is done once outside the timed region, like rank 0's fit in our arm."""
+    R, kfn, xt, y = cpu_posterior_state(n)
+    if n not in _CPU_FIT:
+        _CPU_FIT[n] = R.gp_fit(kfn, xt, y, outputscale=1.0, noise=1e-2, mean_const=0.0)
+    L, alpha = _CPU_FIT[n]
+    gen = torch.Generator().manual_seed(1)
+    xc = torch.randn(sample, 11, generator=gen, dtype=F64)
+    xc = xc / xc.norm(dim=-1, keepdim=True)
+    t0 = time.perf_counter()
+    mean, var = R.gp_predict(kfn, xt, L, alpha, xc, outputscale=1.0, mean_const=0.0, chunk=chunk)
+    dt = time.perf_counter() - t0
+    return sample / dt, dt, float(mean[0])
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    torch.set_default_dtype(F64)
+    n = args.n or 5000
+    sample = 1024
+    cores = torch.get_num_threads()
+    for _ in range(min(args.warmup, 1)):
+        cpu_posterior_rate(n, 256)
+    t0 = time.perf_counter()
+    rates = []
+    for _ in range(args.steps):
+        r, dt, _ = cpu_posterior_rate(n, sample)
+        rates.append(r)
+    total = time.perf_counter() - t0
+    value = statistics.mean(rates)
+    desc = ("oracle port (oracle/restated.py: the reference's torch operator sequence) on %d host threads; each step = "
+            "posterior (Gram rows + triangular solve) of a %d-candidate sample of the S^10 workload against %d training "
+            "points; fit outside the timed region" % (cores, sample, n))
+    return {"impl": "reference", "metric": "posterior_cands_per_sec", "value": value, "unit": "candidates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "S^10 Riemannian Matern nu=2.5 kappa=0.5 T=10 exact-GP posterior mean/var, "
+                                   "%d training points; bounded sample of %d candidates per step" % (n, sample),
+                       "train": n, "sample_candidates": sample},
+            "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank, world, local = dist_env()
+    torch.set_default_dtype(F64)
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: the product path has no CPU fallback")
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        if args.workload == "posterior-s10":
+            out = run_posterior(args, rank, world, local)
+        else:
+            out = run_gram(args, rank, world, local)
+        if rank == 0:
+            if not args.no_cpu_baseline and args.workload == "posterior-s10":
+                n = args.n or 5000
+                sample = 2048
+                rate, dt, _ = cpu_posterior_rate(n, sample)
+                out["cpu_baseline"] = {"value": rate, "unit": "candidates/s", "cores": torch.get_num_threads(),
+                                       "kind": "port",
+                                       "sample": "oracle port (reference's torch CPU algorithm): posterior of %d "
+                                                 "candidates x %d training points, %.1f s (fit excluded)" % (sample, n, dt)}
+            elif "cpu_baseline" not in out:
+                out["cpu_baseline"] = None
+            print(json.dumps(out), flush=True)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

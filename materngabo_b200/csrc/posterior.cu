@@ -136,12 +136,18 @@ __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParam
 
   const int frow = lane >> 2, fk = lane & 3;
   int stage = 0;
+  // Factor rows are dealt to the four row-warps in interleaved groups of 8: fragment b of warp wi holds tile
+  // rows 32 b + 8 wi + [0, 8).  Every warp therefore sees the same share of (a) the zero upper triangle of a
+  // diagonal tile and (b) the zero padding rows of the last tile, and skips those DMMAs in lock step.
   for (int t = split; t < p.n_tiles; t += p.splits) {
     const int nch = chunks_of(t);
+    const long long row_base = (long long)t * PT + 8 * wi;   // first row of fragment 0
+    // fragments whose first row is beyond row n (alpha) are all zero
+    int b_hi = 4;
+    while (b_hi > 0 && row_base + 32 * (b_hi - 1) > p.n) --b_hi;
     for (int ch = 0; ch < nch; ++ch) {
       cp_async_wait<PSTAGES - 2>();
       __syncthreads();
-      // refill the stage consumed in the previous iteration
       {
         const int fill = (stage + PSTAGES - 1) % PSTAGES;
         if (!p_done) {
@@ -150,27 +156,47 @@ __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParam
         }
         cp_async_commit();
       }
+      // fragment b is needed for this column chunk iff its last row >= first column of the chunk
+      const long long j0 = (long long)ch * PK;
+      int b_lo = 0;
+      while (b_lo < b_hi && row_base + 32 * b_lo + 7 < j0) ++b_lo;
       const double* at = As + ((size_t)stage * PT + wc * 64 + frow) * PLD + fk;
-      const double* bt = Bs + ((size_t)stage * PT + wi * 32 + frow) * PLD + fk;
+      const double* bt = Bs + ((size_t)stage * PT + 8 * wi + frow) * PLD + fk;
+      if (b_lo == 0 && b_hi == 4) {
 #pragma unroll
-      for (int k4 = 0; k4 < PK / 4; ++k4) {
-        double af[8], bf[4];
+        for (int k4 = 0; k4 < PK / 4; ++k4) {
+          double af[8], bf[4];
 #pragma unroll
-        for (int a = 0; a < 8; ++a) af[a] = at[(a * 8) * PLD + k4 * 4];
+          for (int a = 0; a < 8; ++a) af[a] = at[(a * 8) * PLD + k4 * 4];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) bf[b] = bt[(b * 8) * PLD + k4 * 4];
+          for (int b = 0; b < 4; ++b) bf[b] = bt[(b * 32) * PLD + k4 * 4];
 #pragma unroll
-        for (int a = 0; a < 8; ++a)
+          for (int a = 0; a < 8; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) dmma(acc0[a][b], acc1[a][b], af[a], bf[b]);
+            for (int b = 0; b < 4; ++b) dmma(acc0[a][b], acc1[a][b], af[a], bf[b]);
+        }
+      } else if (b_lo < b_hi) {
+#pragma unroll
+        for (int k4 = 0; k4 < PK / 4; ++k4) {
+          double af[8];
+#pragma unroll
+          for (int a = 0; a < 8; ++a) af[a] = at[(a * 8) * PLD + k4 * 4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            if (b >= b_lo && b < b_hi) {
+              const double bfv = bt[(b * 32) * PLD + k4 * 4];
+#pragma unroll
+              for (int a = 0; a < 8; ++a) dmma(acc0[a][b], acc1[a][b], af[a], bfv);
+            }
+          }
+        }
       }
       stage = (stage + 1) % PSTAGES;
     }
     // ---- tile epilogue: square-sum (rows i < n), mean (row i == n) -------------------------
-    const long long i_base = (long long)t * PT + wi * 32 + 2 * fk;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const long long i0 = i_base + b * 8;
+      const long long i0 = row_base + 32 * b + 2 * fk;
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
         const double v0 = acc0[a][b], v1 = acc1[a][b];
@@ -191,7 +217,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParam
   __syncthreads();
   const long long alpha_tile = p.n / PT;  // row tile holding row n
   const bool owns_mean = (alpha_tile % p.splits) == split;
-  const int mean_wi = (int)((p.n % PT) / 32), mean_fk = (int)((p.n % 8) / 2);
+  const int mean_wi = (int)((p.n % 32) / 8), mean_fk = (int)((p.n % 8) / 2);
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
     double s = sumsq[a];

@@ -16,6 +16,8 @@
 //   - inner products, clamp and the polynomial are evaluated in registers: D + T + 3 DFMA per entry
 //     (monomial/Horner, T <= 12) or D + 2T + 3 (Chebyshev three-term recurrence).
 #include "mgb_common.cuh"
+#include <cstring>
+#include <cmath>
 
 namespace mgb {
 
@@ -31,7 +33,8 @@ struct SeriesParams {
   double* K; long long ldk;
   int F, W, T;
   double scale, shift, lo, hi;
-  long long ncc;  // column chunks
+  long long ncc;        // column chunks
+  unsigned clamp_word;  // high 32 bits of min(|lo|, |hi|): |u| below this word can never need clamping
 };
 
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
@@ -75,9 +78,19 @@ __device__ __forceinline__ void stage_panel(double* dst, const double* x, long l
 
 // ---------------------------------------------------------------------------------------------
 // Fast path: one factor, width W compile-time, monomial basis with T <= TREG coefficients in registers.
+//   - scale is folded into the x2 registers and shift is the initial value of the dot accumulator;
+//   - RB rows x 2 columns = 2*RB independent Horner chains per thread (DFMA latency hiding);
+//   - the clamp costs two integer instructions per entry: a pair can only need clamping when the high
+//     word of |u| reaches the high word of the bound, which is tested on the integer pipe; the exact
+//     (torch.clamp-equivalent) clamp runs in a rarely taken slow path.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double clamp_exact(double u, double lo, double hi) {
+  return (u < lo) ? lo : ((u > hi) ? hi : u);  // NaN stays NaN, like torch.clamp
+}
+
 template <int W, int TREG>
 __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams p) {
+  constexpr int RB = (W <= 6) ? 4 : 2;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t bar;
   double* x1s = smem;  // kTM * W
@@ -89,51 +102,86 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
   const int rows = (int)min((long long)kTM, p.m - row0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  // coefficients -> registers (zero padded)
   double c[TREG];
 #pragma unroll
   for (int k = 0; k < TREG; ++k) c[k] = (k < p.T) ? __ldg(p.coef + k) : 0.0;
 
-  // this lane's two x2 rows -> registers
   const long long col = cc * kTN + 2 * lane;
   double xa[W], xb[W];
   {
     const bool va = col < p.n, vb = col + 1 < p.n;
 #pragma unroll
     for (int k = 0; k < W; ++k) {
-      xa[k] = va ? __ldg(p.x2 + col * p.ld2 + k) : 0.0;
-      xb[k] = vb ? __ldg(p.x2 + (col + 1) * p.ld2 + k) : 0.0;
+      xa[k] = va ? p.scale * __ldg(p.x2 + col * p.ld2 + k) : 0.0;
+      xb[k] = vb ? p.scale * __ldg(p.x2 + (col + 1) * p.ld2 + k) : 0.0;
     }
   }
   stage_panel(x1s, p.x1, row0, rows, W, p.ld1, &bar);
 
   const bool vec_ok = (col + 1 < p.n) && ((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0);
+  const bool va = col < p.n, vb = col + 1 < p.n;
   const int r_begin = warp * kRowsPerWarp;
-  const int r_end = min(r_begin + kRowsPerWarp, rows);
-#pragma unroll 4
-  for (int r = r_begin; r < r_end; ++r) {
-    const double* xr = x1s + r * W;
-    double da = 0.0, db = 0.0;
+  const unsigned thr = p.clamp_word;
+#pragma unroll 1
+  for (int r = r_begin; r < r_begin + kRowsPerWarp; r += RB) {
+    if (r >= rows) break;
+    double v[RB * W];
+    if constexpr ((RB * W) % 2 == 0) {
+      const double2* src = reinterpret_cast<const double2*>(x1s + r * W);  // r % RB == 0 -> 16-byte aligned
 #pragma unroll
-    for (int k = 0; k < W; ++k) {
-      const double v = xr[k];  // warp-wide broadcast
-      da = fma(v, xa[k], da);
-      db = fma(v, xb[k], db);
+      for (int i = 0; i < RB * W / 2; ++i) {
+        const double2 t = src[i];  // warp-wide broadcast
+        v[2 * i] = t.x;
+        v[2 * i + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < RB * W; ++i) v[i] = x1s[r * W + i];
     }
-    double ua = fmin(fmax(fma(da, p.scale, p.shift), p.lo), p.hi);
-    double ub = fmin(fmax(fma(db, p.scale, p.shift), p.lo), p.hi);
-    double pa = c[TREG - 1], pb = c[TREG - 1];
+    double ua[RB], ub[RB];
+    unsigned need = 0;
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      double da = p.shift, db = p.shift;
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        da = fma(v[q * W + k], xa[k], da);
+        db = fma(v[q * W + k], xb[k], db);
+      }
+      ua[q] = da;
+      ub[q] = db;
+      need |= (unsigned)(((unsigned)__double2hiint(da) & 0x7fffffffu) >= thr);
+      need |= (unsigned)(((unsigned)__double2hiint(db) & 0x7fffffffu) >= thr);
+    }
+    if (need) {
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        ua[q] = clamp_exact(ua[q], p.lo, p.hi);
+        ub[q] = clamp_exact(ub[q], p.lo, p.hi);
+      }
+    }
+    double pa[RB], pb[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) pa[q] = pb[q] = c[TREG - 1];
 #pragma unroll
     for (int k = TREG - 2; k >= 0; --k) {
-      pa = fma(pa, ua, c[k]);
-      pb = fma(pb, ub, c[k]);
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        pa[q] = fma(pa[q], ua[q], c[k]);
+        pb[q] = fma(pb[q], ub[q], c[k]);
+      }
     }
-    double* out = p.K + (row0 + r) * p.ldk + col;
-    if (vec_ok) {
-      st_stream2(out, pa, pb);
-    } else {
-      if (col < p.n) st_stream(out, pa);
-      if (col + 1 < p.n) st_stream(out + 1, pb);
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      if (r + q < rows) {
+        double* out = p.K + (row0 + r + q) * p.ldk + col;
+        if (vec_ok) {
+          st_stream2(out, pa[q], pb[q]);
+        } else {
+          if (va) st_stream(out, pa[q]);
+          if (vb) st_stream(out + 1, pb[q]);
+        }
+      }
     }
   }
 }
@@ -222,8 +270,16 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_general(SeriesPar
         d[3] = fma(v1, xc.y, d[3]);
       }
       double u[4], s[4];
+      unsigned need = 0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) u[q] = fmin(fmax(fma(d[q], p.scale, p.shift), p.lo), p.hi);
+      for (int q = 0; q < 4; ++q) {
+        u[q] = fma(d[q], p.scale, p.shift);
+        need |= (unsigned)(((unsigned)__double2hiint(u[q]) & 0x7fffffffu) >= p.clamp_word);
+      }
+      if (need) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u[q] = clamp_exact(u[q], p.lo, p.hi);
+      }
       eval4<BASIS>(cfs + f * p.T, p.T, u, s);
 #pragma unroll
       for (int q = 0; q < 4; ++q) prod[q] *= s[q];
@@ -446,7 +502,13 @@ extern "C" int mgb_series_gram_fwd(const mgb_series_desc* d, const double* x1, l
   if (m == 0 || n == 0) return MGB_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SeriesParams p{x1, m, ld1, x2, n, ld2, coef, K, ldk, d->n_factors, d->factor_width, d->n_terms,
-                 d->scale, d->shift, d->lo, d->hi, (n + kTN - 1) / kTN};
+                 d->scale, d->shift, d->lo, d->hi, (n + kTN - 1) / kTN, 0u};
+  if (d->lo < 0.0 && d->hi > 0.0) {
+    const double bound = fmin(-d->lo, d->hi);
+    unsigned long long bits;
+    memcpy(&bits, &bound, sizeof(bits));
+    p.clamp_word = (unsigned)(bits >> 32);
+  }
   const long long tiles = p.ncc * ((m + kTM - 1) / kTM);
   if (tiles > 0x7fffffffLL) return fail(MGB_ERR_ARG, "series_gram_fwd: too many tiles for one launch");
   if (d->n_factors == 1 && d->basis == MGB_BASIS_MONOMIAL && d->n_terms <= 12) {

@@ -160,7 +160,8 @@ def main():
         cases["hyperbolic_heat_H%d" % dim] = dict(_run(k, h1, h2, gen), dim=dim, lengthscale=1.3, P=1000)
     k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=64)
     k.lengthscale = 1.0
-    cases["hyperbolic_matern_H2_self"] = dict(_run(k, h1[:9], h1[:9], gen, grads=False), dim=2, nu=2.5,
+    h1 = _lorentz(9, 2, gen)
+    cases["hyperbolic_matern_H2_self"] = dict(_run(k, h1, h1, gen, grads=False), dim=2, nu=2.5,
                                               lengthscale=1.0, P=64)
 
     # ---- SPD(2) ---------------------------------------------------------------------------

@@ -416,14 +416,16 @@ def euclidean_integrated_matern(x1, x2, nu, lengthscale, nb_points=100):
 # ----------------------------------------------------------------------------------------------
 # exact GP posterior + analytic EI (gpytorch / botorch arithmetic; unvendored - see SURVEY 8c)
 # ----------------------------------------------------------------------------------------------
-def gp_posterior(kernel_fn, x_train, y_train, x_cand, outputscale=1.0, noise=1e-2, mean_const=0.0,
-                 chunk=4096):
-    """mean = m + s K* (sK + noise I)^-1 (y - m);  var = s k** - || L^-1 s K*^T ||^2 with
-    L = chol(s K + noise I).  Call sites: examples/.../bo_sphere.py:215-233,265;
-    manifold_optimization/manifold_optimize.py:195,254,337."""
+def gp_fit(kernel_fn, x_train, y_train, outputscale=1.0, noise=1e-2, mean_const=0.0):
+    """L = chol(s K + noise I), alpha = (s K + noise I)^-1 (y - m)."""
     ktt = outputscale * kernel_fn(x_train, x_train) + noise * torch.eye(x_train.shape[0], dtype=F64)
     L = torch.linalg.cholesky(ktt)
     alpha = torch.cholesky_solve((y_train - mean_const).unsqueeze(-1), L).squeeze(-1)
+    return L, alpha
+
+
+def gp_predict(kernel_fn, x_train, L, alpha, x_cand, outputscale=1.0, mean_const=0.0, chunk=4096):
+    """mean = m + s K* alpha;  var = s k** - || L^-1 s K*^T ||^2."""
     means, vars_ = [], []
     for s in range(0, x_cand.shape[0], chunk):
         xc = x_cand[s:s + chunk]
@@ -434,6 +436,14 @@ def gp_posterior(kernel_fn, x_train, y_train, x_cand, outputscale=1.0, noise=1e-
         means.append(mean_const + ks @ alpha)
         vars_.append(kss - (v * v).sum(0))
     return torch.cat(means), torch.cat(vars_)
+
+
+def gp_posterior(kernel_fn, x_train, y_train, x_cand, outputscale=1.0, noise=1e-2, mean_const=0.0,
+                 chunk=4096):
+    """Exact-GP posterior mean / variance with a constant mean, as gpytorch's ExactGP prediction computes it.
+    Call sites: examples/.../bo_sphere.py:215-233,265; manifold_optimization/manifold_optimize.py:195,254,337."""
+    L, alpha = gp_fit(kernel_fn, x_train, y_train, outputscale, noise, mean_const)
+    return gp_predict(kernel_fn, x_train, L, alpha, x_cand, outputscale, mean_const, chunk)
 
 
 def expected_improvement(mean, var, best_f, maximize=False):

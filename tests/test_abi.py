@@ -1,0 +1,47 @@
+"""not gpu: the C-ABI shared library loads and exports every symbol include/mgb.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+from materngabo_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "mgb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mgb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_typed():
+    names = _declared()
+    assert len(names) >= 19
+    lib = ctypes.CDLL(build.build())
+    for n in names:
+        assert hasattr(lib, n), "libmgb.so does not export %s" % n
+        assert n in _lib.PROTOTYPES, "no ctypes prototype for %s" % n
+    assert sorted(_lib.PROTOTYPES) == names
+
+
+def test_loader_and_version():
+    lib = _lib.load()
+    assert lib.mgb_version() == 100
+    assert lib.mgb_launch_count() >= 0
+    assert lib.mgb_posterior_pack_bytes(5000) == 5120 * 5008 * 8
+    assert lib.mgb_posterior_workspace_bytes(128, 100) == (128 * 112 + 128) * 8
+
+
+def test_series_desc_layout_matches_header():
+    d = _lib.SeriesDesc(1, 3, 10, 0, 1.0, 0.0, -1.0, 1.0)
+    assert ctypes.sizeof(d) == 4 * 4 + 4 * 8
+    assert (d.n_factors, d.factor_width, d.n_terms, d.basis) == (1, 3, 10, 0)
+
+
+def test_product_has_no_oracle_dependency():
+    """The product package must never import oracle/ (SURVEY scope rule: the oracle is the checker only)."""
+    pkg = os.path.join(ROOT, "materngabo_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn

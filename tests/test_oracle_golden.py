@@ -1,0 +1,123 @@
+"""not gpu: the restated oracle (oracle/restated.py) against the golden vectors generated from the UNMODIFIED
+reference (oracle/make_golden.py), values and autograd gradients.  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restated as R
+from tests.conftest import load_golden, rel_err
+
+PIN = 1e-13  # restatement vs reference: rounding-level agreement
+
+
+def _t(a, grad=False):
+    return torch.tensor(np.asarray(a), dtype=torch.float64, requires_grad=grad)
+
+
+def _ls(raw_free):  # softplus(raw) parametrisation used by the reference (gpytorch Positive)
+    return torch.nn.functional.softplus(raw_free)
+
+
+def _inv_softplus(v):
+    v = torch.tensor(float(v))
+    return (v + torch.log(-torch.expm1(-v))).reshape(1, 1).requires_grad_(True)
+
+
+CASES = {
+    "sphere_matern_S2": lambda g, ls: R.sphere_matern(g["x1"], g["x2"], 2, 2.5, ls),
+    "sphere_matern_S3": lambda g, ls: R.sphere_matern(g["x1"], g["x2"], 3, 2.5, ls),
+    "sphere_matern_S10": lambda g, ls: R.sphere_matern(g["x1"], g["x2"], 10, 2.5, ls),
+    "sphere_gaussian_S2": lambda g, ls: R.sphere_gaussian(g["x1"], g["x2"], 2, ls),
+    "sphere_gaussian_S3": lambda g, ls: R.sphere_gaussian(g["x1"], g["x2"], 3, ls),
+    "sphere_gaussian_S10": lambda g, ls: R.sphere_gaussian(g["x1"], g["x2"], 10, ls),
+    "sphere_intmatern_S3": lambda g, ls: R.sphere_integrated_matern(g["x1"], g["x2"], 3, 2.5, ls),
+    "circle_gaussian": lambda g, ls: R.circle_gaussian(g["x1"], g["x2"], ls),
+    "circle_intmatern": lambda g, ls: R.circle_integrated_matern(g["x1"], g["x2"], 2.5, ls),
+    "so3_matern": lambda g, ls: R.so3_matern(g["x1"], g["x2"], 2.5, ls),
+    "so3_gaussian": lambda g, ls: R.so3_gaussian(g["x1"], g["x2"], ls),
+    "hyperbolic_matern_H1": lambda g, ls: R.hyperbolic_integrated_matern(g["x1"], g["x2"], 1, 2.5, ls, 64),
+    "hyperbolic_matern_H2": lambda g, ls: R.hyperbolic_integrated_matern(g["x1"], g["x2"], 2, 2.5, ls, 64),
+    "hyperbolic_matern_H3": lambda g, ls: R.hyperbolic_integrated_matern(g["x1"], g["x2"], 3, 2.5, ls, 64),
+    "hyperbolic_heat_H1": lambda g, ls: R.hyperbolic_heat(g["x1"], g["x2"], 1, ls),
+    "hyperbolic_heat_H2": lambda g, ls: R.hyperbolic_heat(g["x1"], g["x2"], 2, ls),
+    "hyperbolic_heat_H3": lambda g, ls: R.hyperbolic_heat(g["x1"], g["x2"], 3, ls),
+    "euclidean_intmatern": lambda g, ls: R.euclidean_integrated_matern(g["x1"], g["x2"], 2.5, ls),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_value_and_gradients(name):
+    raw = load_golden(name)
+    g = {"x1": _t(raw["x1"], True), "x2": _t(raw["x2"], True)}
+    raw_ls = _inv_softplus(raw["lengthscale"])
+    k = CASES[name](g, _ls(raw_ls))
+    assert rel_err(k, raw["K"]) < PIN
+    res = torch.autograd.grad((k * _t(raw["G"])).sum(), [g["x1"], g["x2"], raw_ls])
+    assert rel_err(res[0], raw["gx1"]) < 1e-11
+    assert rel_err(res[1], raw["gx2"]) < 1e-11
+    assert rel_err(res[2].reshape(-1), raw["g_raw_lengthscale"].reshape(-1)) < 1e-11
+
+
+VALUE_ONLY = {
+    "sphere_matern_S3_example": lambda g: R.sphere_matern(g["x1"], g["x2"], 3, 2.5, 0.5),
+    "sphere_matern_S2_self": lambda g: R.sphere_matern(g["x1"], g["x2"], 2, 2.5, 0.5),
+    "so3_matern_self": lambda g: R.so3_matern(g["x1"], g["x2"], 2.5, 0.5),
+    "hyperbolic_matern_H2_self": lambda g: R.hyperbolic_integrated_matern(g["x1"], g["x2"], 2, 2.5, 1.0, 64),
+    "spd2_matern": lambda g: R.spd2_integrated_matern(g["x1"], g["x2"], 2.5, 1.0, 64, 64),
+    "spd2_matern_self": lambda g: R.spd2_integrated_matern(g["x1"], g["x2"], 2.5, 1.0, 64, 64),
+    "spd2_heat": lambda g: R.spd2_heat(g["x1"], g["x2"], 1.4, 50),
+}
+
+
+@pytest.mark.parametrize("name", sorted(VALUE_ONLY))
+def test_value_only(name):
+    raw = load_golden(name)
+    g = {"x1": _t(raw["x1"]), "x2": _t(raw["x2"])}
+    assert rel_err(VALUE_ONLY[name](g), raw["K"]) < PIN
+
+
+@pytest.mark.parametrize("dim", [3, 10])
+def test_torus(dim):
+    raw = load_golden("torus_matern_T%d" % dim)
+    k = R.torus_matern(_t(raw["x1"]), _t(raw["x2"]), dim, 2.5, [float(v) for v in raw["lengthscales"]])
+    assert rel_err(k, raw["K"]) < PIN
+    raw = load_golden("torus_gaussian_T%d" % dim)
+    k = R.torus_gaussian(_t(raw["x1"]), _t(raw["x2"]), dim, [float(v) for v in raw["lengthscales"]])
+    assert rel_err(k, raw["K"]) < PIN
+
+
+def test_nu_gradient():
+    raw = load_golden("sphere_matern_S2_nugrad")
+    raw_ls, raw_nu = _inv_softplus(raw["lengthscale"]), _inv_softplus(raw["nu"])
+    k = R.sphere_matern(_t(raw["x1"]), _t(raw["x2"]), 2, _ls(raw_nu), _ls(raw_ls))
+    assert rel_err(k, raw["K"]) < PIN
+    res = torch.autograd.grad((k * _t(raw["G"])).sum(), [raw_ls, raw_nu])
+    assert rel_err(res[0].reshape(-1), raw["g_raw_lengthscale"].reshape(-1)) < 1e-11
+    assert rel_err(res[1].reshape(-1), raw["g_raw_nu"].reshape(-1)) < 1e-11
+
+
+def test_known_structure():
+    """Known answers independent of the fixtures: unit diagonal up to the reference's clamps (SURVEY.md section 5:
+    S^d ~ 1, SO(3) diag = 1 - O(1e-8) because of the 1-1e-8 clip), symmetry, positive definiteness."""
+    torch.manual_seed(0)
+    x = torch.nn.functional.normalize(torch.randn(40, 3), dim=-1)
+    k = R.sphere_matern(x, x, 2, 2.5, 0.5)
+    assert float((k.diagonal() - 1).abs().max()) < 1e-12
+    assert torch.linalg.eigvalsh(k).min() > 0
+    q, _ = torch.linalg.qr(torch.randn(12, 3, 3))
+    q[:, :, 0] *= torch.sign(torch.linalg.det(q)).unsqueeze(-1)
+    k3 = R.so3_matern(q.reshape(12, 9), q.reshape(12, 9), 2.5, 0.5)
+    assert 1e-9 < float((1 - k3.diagonal()).max()) < 1e-6
+    assert rel_err(k3, k3.t()) < 1e-12
+
+
+def test_gp_posterior_identities():
+    torch.manual_seed(1)
+    xt = torch.nn.functional.normalize(torch.randn(30, 4), dim=-1)
+    y = torch.sin(xt[:, 0] * 3)
+    kfn = lambda a, b: R.sphere_matern(a, b, 3, 2.5, 0.5)  # noqa: E731
+    mean, var = R.gp_posterior(kfn, xt, y, xt, outputscale=1.0, noise=1e-6)
+    assert float((mean - y).abs().max()) < 1e-3          # interpolates when the noise vanishes
+    assert float(var.abs().max()) < 1e-4
+    far = R.gp_posterior(kfn, xt[:1], y[:1], -xt[:1], outputscale=2.0, noise=1e-2, mean_const=0.3)
+    assert abs(float(far[1]) - 2.0) < 0.2                 # antipodal point: nearly the prior variance
