@@ -241,7 +241,8 @@ def posterior_roofline(gp, xc, n, lib):
         chunk = xc.shape[0]
         reps = 1
     ldk = (n + 15) // 16 * 16
-    kc = torch.empty((chunk, ldk), dtype=F64, device=xc.device)
+    kc = torch.zeros((chunk, ldk), dtype=F64, device=xc.device)
+    part = torch.empty(max(1, lib.mgb_posterior_reduce_workspace_bytes(chunk, n) // 8), dtype=F64, device=xc.device)
     kss = torch.full((chunk,), gp.kss_value, dtype=F64, device=xc.device)
     mean = torch.empty(chunk, dtype=F64, device=xc.device)
     var = torch.empty(chunk, dtype=F64, device=xc.device)
@@ -256,7 +257,8 @@ def posterior_roofline(gp, xc, n, lib):
                                            gp.train_prepared.stride(0), _lib.ptr(gp.coef), _lib.ptr(kc), ldk, st), "gram")
         ev[i][1].record()
         _lib.check(lib.mgb_posterior_reduce(_lib.ptr(kc), chunk, n, ldk, _lib.ptr(gp._packed), _lib.ptr(kss),
-                                            gp.mean_const, _lib.ptr(mean), _lib.ptr(var), st), "reduce")
+                                            gp.mean_const, _lib.ptr(mean), _lib.ptr(var), _lib.ptr(part),
+                                            part.numel() * 8, st), "reduce")
         ev[i][2].record()
     torch.cuda.synchronize()
     gram_ms = statistics.mean(ev[i][0].elapsed_time(ev[i][1]) for i in range(1, reps + 1))

@@ -139,13 +139,18 @@ int mgb_spd2_gram_bwd_coef(int use_cholesky, const double* x1, long long m, long
  * to (n+1 rounded up to 128) x (n rounded up to 16) doubles, row n holding alpha (so the mean falls out of
  * the same tiles).  mgb_posterior_reduce is the fused triangular product + square-sum + mean on FP64
  * tensor-core DMMA tiles; Kc is consumed, V = Rinv Kc^T is never written to memory.
- * Kc must be 16-byte aligned with an even ldk >= n.  kss: m values (k(x_c, x_c) * outputscale).
+ * Kc must be 16-byte aligned with an even ldk >= n rounded up to 16; the padding columns [n, ldk) are read (and
+ * multiplied by zeros of the packed factor), so they must hold finite values.  kss: m values
+ * (k(x_c, x_c) * outputscale).  Results are deterministic (fixed summation order).
  * ------------------------------------------------------------------------------------------------ */
 long long mgb_posterior_pack_bytes(long long n);
 int mgb_posterior_pack(const double* Rinv, long long n, long long ldr, const double* alpha, double* packed,
                        void* stream);
+/* bytes of scratch mgb_posterior_reduce needs for m candidates (0 when one CTA per candidate tile suffices) */
+long long mgb_posterior_reduce_workspace_bytes(long long m, long long n);
 int mgb_posterior_reduce(const double* Kc, long long m, long long n, long long ldk, const double* packed,
-                         const double* kss, double mean_const, double* mean, double* var, void* stream);
+                         const double* kss, double mean_const, double* mean, double* var, void* workspace,
+                         long long workspace_bytes, void* stream);
 /* scratch mgb_series_posterior needs for `chunk` candidates x n training points (bytes) */
 long long mgb_posterior_workspace_bytes(long long chunk, long long n);
 

@@ -4,43 +4,60 @@
 //   mean[c]  = mean_const + sum_j Kc[c][j] * alpha[j]  (alpha rides along as row n of the packed factor)
 //
 // This is the FLOP-dominant stage of the acquisition posterior (n^2 per candidate):
-// FP64-bound, so the design goal is to keep the DMMA pipe busy:
-//   - CTA tile 128 candidates x 128 factor rows, 8 warps as 2 x 4, warp tile 64 x 32
-//     (8 x 4 DMMA fragments, 64 accumulator doubles per lane);
-//   - one CTA walks ALL row tiles of the packed factor for its 128 candidates (triangular: row tile t
-//     only needs columns j < 128 (t+1)), so the square-sum stays in registers and is stored once;
-//   - operands stream through a 4-stage cp.async pipeline of 128 x 16 double panels, stored with a
-//     row pitch of 20 doubles so that every fragment load is bank-conflict free;
-//   - the (tile, column-chunk) loop is flattened so the pipeline never drains between row tiles.
+// FP64-bound, so the design goal is to keep the DMMA (FP64 tensor) pipe busy:
+//   - CTA tile 128 candidates x 128 factor rows, 8 DMMA warps as 2 x 4, warp tile 64 x 32
+//     (8 x 4 m8n8k4 fragments, 64 accumulator doubles per lane) + 1 producer warp;
+//   - the producer streams 128 x 16 double operand panels with cp.async.bulk (TMA engine, one 128-byte row
+//     per copy, completion counted in bytes on a per-stage `full` mbarrier) into a 5-stage ring stored with a
+//     row pitch of 20 doubles, so that every fragment load is bank-conflict free; consumers release stages
+//     through `empty` mbarriers - there is no CTA-wide barrier in the main loop;
+//   - a CTA walks a balanced subset of the row tiles of the packed factor for its 128 candidates
+//     (triangular: row tile t only needs columns j < 128 (t+1)); square-sums stay in registers;
+//   - the CTAs that share a candidate tile are adjacent in launch order and share its Gram panel through L2
+//     (otherwise each panel would be re-streamed from HBM once per row tile); their partial sums are combined
+//     in a fixed order by posterior_finalize_kernel (deterministic, no atomics).
 // The packed factor (mgb_posterior_pack) is the lower triangle of Rinv padded with zeros to
 // (n+1 rounded up to 128) x (n rounded up to 16), row n holding alpha.
 #include "mgb_common.cuh"
+#include <cmath>
 
 namespace mgb {
 
 constexpr int PT = 128;       // tile edge (candidates and factor rows)
 constexpr int PK = 16;        // columns per pipeline stage
 constexpr int PLD = PK + 4;   // smem row pitch in doubles (bank-conflict-free fragment loads)
-constexpr int PSTAGES = 4;
-constexpr int PTHREADS = 256;
-constexpr size_t kPostSmem = sizeof(double) * (size_t)PSTAGES * 2 * PT * PLD;
+constexpr int PSTAGES = 5;
+constexpr int PCONSUMERS = 8;                       // DMMA warps
+constexpr int PTHREADS = (PCONSUMERS + 4) * 32;     // + one producer warpgroup (one warp of it issues copies)
+constexpr int PREGS_PRODUCER = 40;                  // setmaxnreg budgets: 4*32*40 + 8*32*232 = 64512 <= 65536
+constexpr int PREGS_CONSUMER = 232;
+constexpr size_t kPostSmem = sizeof(double) * (size_t)PSTAGES * 2 * PT * PLD + 2 * PSTAGES * sizeof(uint64_t);
+constexpr uint32_t kStageBytes = 2u * PT * PK * sizeof(double);
 
 __host__ __device__ inline long long round_up(long long v, long long q) { return (v + q - 1) / q * q; }
-
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_test(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 struct PostParams {
@@ -49,117 +66,125 @@ struct PostParams {
   const double* kss;
   double mean_const;
   double* mean; double* var;
-  int n_tiles;   // row tiles of the packed factor
-  int splits;    // CTAs sharing one candidate tile (row tiles dealt round-robin)
+  double* partial;   // [splits][m] square-sum partials when splits > 1
+  int n_tiles;       // row tiles of the packed factor
+  int splits;        // CTAs sharing one candidate tile (they share its Gram panel through L2)
 };
 
-__global__ void posterior_init_kernel(const double* kss, double* var, long long m) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) var[i] = kss[i];
+// Row tile handled in round j by split r of S: tiles sorted by work (descending = index descending) and
+// dealt in snake order so that every split gets the same amount of work to within one tile.
+__device__ __forceinline__ int tile_of(int j, int r, int S, int n_tiles) {
+  const int idx = j * S + ((j & 1) ? (S - 1 - r) : r);
+  return (idx < n_tiles) ? (n_tiles - 1 - idx) : -1;
 }
 
+// Warp-specialised: warp 8 streams 128 x 16 operand panels with cp.async.bulk (TMA engine) into a 5-stage
+// ring, signalling per-stage `full` mbarriers by transaction bytes; warps 0-7 wait, issue DMMAs and release the
+// stage through `empty` mbarriers.  No CTA-wide barrier in the main loop: warps may drift by up to 4 stages.
 __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParams p) {
   extern __shared__ __align__(16) double smem[];
   double* As = smem;                               // [stage][PT][PLD]
   double* Bs = smem + (size_t)PSTAGES * PT * PLD;  // [stage][PT][PLD]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)PSTAGES * 2 * PT * PLD);
+  uint64_t* empty = full + PSTAGES;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wc = warp >> 2;   // 0..1 : candidate half
-  const int wi = warp & 3;    // 0..3 : factor-row quarter
-  const long long c0 = (long long)blockIdx.x * PT;
-  const int split = blockIdx.y;
-
-  // ---- flattened (row tile, column chunk) schedule for this CTA ------------------------------
-  // tile t has chunks_t = min(128 (t+1), n_pad) / PK column chunks
+  const int S = p.splits;
+  const long long ctile = blockIdx.x / S;
+  const int split = (int)(blockIdx.x % S);
+  const long long c0 = ctile * PT;
   const long long n_pad = p.ldp;
+  const int rounds = (p.n_tiles + S - 1) / S;
   auto chunks_of = [&](int t) -> int {
     long long cols = (long long)(t + 1) * PT;
     if (cols > n_pad) cols = n_pad;
     return (int)(cols / PK);
   };
 
-  // loader mapping: thread -> (row = tid / 2, half = tid & 1) : 8 doubles = four 16-byte cp.async
-  const int lrow = tid >> 1, lhalf = tid & 1;
-  const long long a_row = c0 + lrow;
-  const bool a_valid = a_row < p.m;
-  const double* a_src_row = p.Kc + (a_valid ? a_row : 0) * p.ldk;
+  if (tid == 0) {
+    for (int s = 0; s < PSTAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, PCONSUMERS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
 
-  auto issue = [&](int stage, int t, int ch) {
-    const long long j0 = (long long)ch * PK + lhalf * 8;
-    double* ad = As + ((size_t)stage * PT + lrow) * PLD + lhalf * 8;
-    double* bd = Bs + ((size_t)stage * PT + lrow) * PLD + lhalf * 8;
-    const double* bs = p.Rp + ((long long)t * PT + lrow) * p.ldp + j0;
+  if (warp >= PCONSUMERS) {
+    // ===================== producer warpgroup =====================
+    // hands its registers to the DMMA warps (168 per thread at launch: 384 threads), one warp issues copies
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PREGS_PRODUCER));
+    if (warp != PCONSUMERS) return;
+    int stage = 0;
+    uint32_t phase = 0;
+    // each lane owns rows lane, lane+32, lane+64, lane+96 of both panels
+    const double* a_src[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const long long j = j0 + 2 * q;
-      int bytes = 0;
-      if (a_valid) {
-        long long rem = p.n - j;
-        bytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
-      }
-      cp_async16(ad + 2 * q, a_src_row + (bytes ? j : 0), bytes);
-      cp_async16(bd + 2 * q, bs + 2 * q, 16);
+      long long row = c0 + lane + 32 * q;
+      if (row >= p.m) row = p.m - 1;   // rows past the end read a valid row; their results are never stored
+      a_src[q] = p.Kc + row * p.ldk;
     }
-  };
-
-  // iteration state for the producer side
-  int pt = split, pch = 0;
-  bool p_done = pt >= p.n_tiles;
-  auto advance_producer = [&]() {
-    if (++pch >= chunks_of(pt)) {
-      pch = 0;
-      pt += p.splits;
-      if (pt >= p.n_tiles) p_done = true;
-    }
-  };
-
+    for (int j = 0; j < rounds; ++j) {
+      const int t = tile_of(j, split, S, p.n_tiles);
+      if (t < 0) continue;
+      const int nch = chunks_of(t);
+      const double* b_row0 = p.Rp + ((long long)t * PT + lane) * p.ldp;
+      for (int ch = 0; ch < nch; ++ch) {
+        mbar_spin(empty + stage, phase ^ 1u);
+        if (lane == 0) mbar_expect_tx(full + stage, kStageBytes);
+        __syncwarp();
+        double* ad = As + ((size_t)stage * PT + lane) * PLD;
+        double* bd = Bs + ((size_t)stage * PT + lane) * PLD;
+        const long long j0 = (long long)ch * PK;
 #pragma unroll
-  for (int s = 0; s < PSTAGES - 1; ++s) {
-    if (!p_done) {
-      issue(s, pt, pch);
-      advance_producer();
+        for (int q = 0; q < 4; ++q) {
+          bulk_g2s(ad + (size_t)32 * q * PLD, a_src[q] + j0, PK * sizeof(double), full + stage);
+          bulk_g2s(bd + (size_t)32 * q * PLD, b_row0 + (long long)32 * q * p.ldp + j0, PK * sizeof(double), full + stage);
+        }
+        if (++stage == PSTAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
     }
-    cp_async_commit();
+    return;
   }
 
+  // ===================== consumer warps =====================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PREGS_CONSUMER));
+  const int wc = warp >> 2;   // 0..1 : candidate half
+  const int wi = warp & 3;    // 0..3 : interleaved factor-row group
   double acc0[8][4], acc1[8][4];
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc0[a][b] = acc1[a][b] = 0.0;
-  double sumsq[8];
+  double sumsq[8], meanv[8];
 #pragma unroll
-  for (int a = 0; a < 8; ++a) sumsq[a] = 0.0;
-  double meanv[8];
-#pragma unroll
-  for (int a = 0; a < 8; ++a) meanv[a] = 0.0;
+  for (int a = 0; a < 8; ++a) sumsq[a] = meanv[a] = 0.0;
 
   const int frow = lane >> 2, fk = lane & 3;
   int stage = 0;
+  uint32_t phase = 0;
+  bool owns_mean = false;
   // Factor rows are dealt to the four row-warps in interleaved groups of 8: fragment b of warp wi holds tile
   // rows 32 b + 8 wi + [0, 8).  Every warp therefore sees the same share of (a) the zero upper triangle of a
   // diagonal tile and (b) the zero padding rows of the last tile, and skips those DMMAs in lock step.
-  for (int t = split; t < p.n_tiles; t += p.splits) {
+  for (int j = 0; j < rounds; ++j) {
+    const int t = tile_of(j, split, S, p.n_tiles);
+    if (t < 0) continue;
     const int nch = chunks_of(t);
     const long long row_base = (long long)t * PT + 8 * wi;   // first row of fragment 0
-    // fragments whose first row is beyond row n (alpha) are all zero
-    int b_hi = 4;
+    if ((long long)t * PT <= p.n && p.n < (long long)(t + 1) * PT) owns_mean = true;
+    int b_hi = 4;                                            // fragments starting beyond row n are all zero
     while (b_hi > 0 && row_base + 32 * (b_hi - 1) > p.n) --b_hi;
     for (int ch = 0; ch < nch; ++ch) {
-      cp_async_wait<PSTAGES - 2>();
-      __syncthreads();
-      {
-        const int fill = (stage + PSTAGES - 1) % PSTAGES;
-        if (!p_done) {
-          issue(fill, pt, pch);
-          advance_producer();
-        }
-        cp_async_commit();
-      }
       // fragment b is needed for this column chunk iff its last row >= first column of the chunk
       const long long j0 = (long long)ch * PK;
       int b_lo = 0;
       while (b_lo < b_hi && row_base + 32 * b_lo + 7 < j0) ++b_lo;
+      mbar_spin(full + stage, phase);
       const double* at = As + ((size_t)stage * PT + wc * 64 + frow) * PLD + fk;
       const double* bt = Bs + ((size_t)stage * PT + 8 * wi + frow) * PLD + fk;
       if (b_lo == 0 && b_hi == 4) {
@@ -191,7 +216,12 @@ __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParam
           }
         }
       }
-      stage = (stage + 1) % PSTAGES;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + stage);   // this warp is done reading the stage
+      if (++stage == PSTAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
     }
     // ---- tile epilogue: square-sum (rows i < n), mean (row i == n) -------------------------
 #pragma unroll
@@ -207,16 +237,12 @@ __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParam
       }
     }
   }
-  cp_async_wait<0>();
-  __syncthreads();
+  // all stages this CTA ever requested have been consumed by every warp that reaches this barrier
+  asm volatile("bar.sync 1, %0;" ::"n"(PCONSUMERS * 32) : "memory");
 
-  // ---- CTA reduction: 4 lanes per fragment row, then the 4 row-quarter warps ------------------
+  // ---- CTA reduction: 4 lanes per fragment row, then the 4 row-group warps -------------------------
   double* red = smem;            // [4][PT] sums, then [PT] means
   double* mred = smem + 4 * PT;
-  for (int e = tid; e < PT; e += PTHREADS) mred[e] = 0.0;
-  __syncthreads();
-  const long long alpha_tile = p.n / PT;  // row tile holding row n
-  const bool owns_mean = (alpha_tile % p.splits) == split;
   const int mean_wi = (int)((p.n % 32) / 8), mean_fk = (int)((p.n % 8) / 2);
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
@@ -227,19 +253,25 @@ __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParam
     if (fk == 0) red[wi * PT + cl] = s;
     if (owns_mean && wi == mean_wi && fk == mean_fk) mred[cl] = meanv[a];
   }
-  __syncthreads();
-  for (int e = tid; e < PT; e += PTHREADS) {
-    const long long c = c0 + e;
+  asm volatile("bar.sync 1, %0;" ::"n"(PCONSUMERS * 32) : "memory");
+  if (tid < PT) {
+    const long long c = c0 + tid;
     if (c < p.m) {
-      const double tot = (red[e] + red[PT + e]) + (red[2 * PT + e] + red[3 * PT + e]);
-      if (p.splits == 1) {
-        p.var[c] = p.kss[c] - tot;
-      } else {
-        atomicAdd(p.var + c, -tot);
-      }
-      if (owns_mean) p.mean[c] = p.mean_const + mred[e];
+      const double tot = (red[tid] + red[PT + tid]) + (red[2 * PT + tid] + red[3 * PT + tid]);
+      if (S == 1) p.var[c] = p.kss[c] - tot;
+      else p.partial[(long long)split * p.m + c] = tot;
+      if (owns_mean) p.mean[c] = p.mean_const + mred[tid];
     }
   }
+}
+
+// var[c] = kss[c] - sum_s partial[s][c], fixed summation order (deterministic)
+__global__ void posterior_finalize_kernel(const double* kss, const double* partial, int splits, long long m, double* var) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m) return;
+  double tot = 0.0;
+  for (int s = 0; s < splits; ++s) tot += partial[(long long)s * m + c];
+  var[c] = kss[c] - tot;
 }
 
 // Pack Rinv (lower triangle) + alpha into the padded operand.
@@ -278,47 +310,81 @@ extern "C" int mgb_posterior_pack(const double* Rinv, long long n, long long ldr
   return after_launch("posterior_pack_kernel");
 }
 
+static int g_post_sms = 0;
+static int post_sm_count() {
+  if (g_post_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_post_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      g_post_sms = 148;
+  }
+  return g_post_sms;
+}
+
+// How many CTAs share one 128-candidate tile.  (a) Few candidates: split so that the grid fills the SMs.
+// (b) Many: the 128 x n Gram panel of a candidate tile is re-read once per row tile; CTAs working on the SAME
+// panel at the same time share it through L2, so enough splits are used that the panels of all concurrently
+// resident CTAs fit in a ~40 MB slice of the 126 MB L2 (the factor streams through the rest).
+static int choose_splits(long long m, long long n) {
+  const int sms = post_sm_count();
+  const long long ctiles = (m + PT - 1) / PT;
+  const int n_tiles = (int)(round_up(n + 1, PT) / PT);
+  const double panel_bytes = (double)PT * (double)round_up(n, PK) * 8.0;
+  long long s_l2 = (long long)ceil(sms * panel_bytes / (40.0 * 1024 * 1024));
+  long long s_fill = (2LL * sms + ctiles - 1) / ctiles;
+  long long s = s_l2 > s_fill ? s_l2 : s_fill;
+  if (s < 1) s = 1;
+  if (s > n_tiles) s = n_tiles;
+  return (int)s;
+}
+
+extern "C" long long mgb_posterior_reduce_workspace_bytes(long long m, long long n) {
+  if (m <= 0 || n <= 0) return 0;
+  const int s = choose_splits(m, n);
+  return s > 1 ? (long long)s * m * (long long)sizeof(double) : 0;
+}
+
 extern "C" int mgb_posterior_reduce(const double* Kc, long long m, long long n, long long ldk, const double* packed,
-                                    const double* kss, double mean_const, double* mean, double* var, void* stream) {
+                                    const double* kss, double mean_const, double* mean, double* var, void* workspace,
+                                    long long workspace_bytes, void* stream) {
   if (!Kc || !packed || !kss || !mean || !var) return fail(MGB_ERR_ARG, "posterior_reduce: null pointer");
-  if (m < 0 || n < 1 || ldk < n) return fail(MGB_ERR_ARG, "posterior_reduce: bad sizes");
-  if ((ldk & 1) || (reinterpret_cast<uintptr_t>(Kc) & 15u)) return fail(MGB_ERR_ARG, "posterior_reduce: Kc must be 16-byte aligned with even ldk");
+  if (m < 0 || n < 1) return fail(MGB_ERR_ARG, "posterior_reduce: bad sizes");
+  if (ldk < round_up(n, PK) || (ldk & 1) || (reinterpret_cast<uintptr_t>(Kc) & 15u))
+    return fail(MGB_ERR_ARG, "posterior_reduce: Kc must be 16-byte aligned with even ldk >= n rounded up to 16 (finite padding)");
   if (m == 0) return MGB_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    MGB_TRY(check_cuda(cudaGetDevice(&dev), "cudaGetDevice"));
-    MGB_TRY(check_cuda(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute"));
+  static bool attr_set = false;
+  if (!attr_set) {
     MGB_TRY(check_cuda(cudaFuncSetAttribute(posterior_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)kPostSmem), "cudaFuncSetAttribute"));
+    attr_set = true;
   }
   PostParams p;
   p.Kc = Kc; p.m = m; p.n = n; p.ldk = ldk;
   p.Rp = packed; p.rows_p = round_up(n + 1, PT); p.ldp = round_up(n, PK);
   p.kss = kss; p.mean_const = mean_const; p.mean = mean; p.var = var;
   p.n_tiles = (int)(p.rows_p / PT);
+  p.splits = choose_splits(m, n);
+  p.partial = nullptr;
+  if (p.splits > 1) {
+    if (!workspace || workspace_bytes < (long long)p.splits * m * (long long)sizeof(double))
+      return fail(MGB_ERR_ARG, "posterior_reduce: workspace smaller than mgb_posterior_reduce_workspace_bytes(m, n)");
+    p.partial = static_cast<double*>(workspace);
+  }
   const long long ctiles = (m + PT - 1) / PT;
-  int splits = 1;
-  if (ctiles < 2LL * sm_count) {
-    splits = (int)((2LL * sm_count + ctiles - 1) / ctiles);
-    if (splits > p.n_tiles) splits = p.n_tiles;
+  if (ctiles * p.splits > 0x7fffffffLL) return fail(MGB_ERR_ARG, "posterior_reduce: m too large for one launch");
+  posterior_reduce_kernel<<<(unsigned)(ctiles * p.splits), PTHREADS, kPostSmem, s>>>(p);
+  MGB_TRY(after_launch("posterior_reduce_kernel"));
+  if (p.splits > 1) {
+    posterior_finalize_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(kss, p.partial, p.splits, m, var);
+    MGB_TRY(after_launch("posterior_finalize_kernel"));
   }
-  p.splits = splits;
-  if (ctiles > 0x7fffffffLL) return fail(MGB_ERR_ARG, "posterior_reduce: m too large for one launch");
-  if (splits > 1) {
-    posterior_init_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(kss, var, m);
-    MGB_TRY(after_launch("posterior_init_kernel"));
-  }
-  dim3 grid((unsigned)ctiles, (unsigned)splits);
-  posterior_reduce_kernel<<<grid, PTHREADS, kPostSmem, s>>>(p);
-  return after_launch("posterior_reduce_kernel");
+  return MGB_OK;
 }
 
 extern "C" long long mgb_posterior_workspace_bytes(long long chunk, long long n) {
   if (chunk < 0 || n < 0) return 0;
-  // Kc chunk (ld = n rounded up to 16) + kss chunk
-  return (chunk * round_up(n, PK) + chunk) * (long long)sizeof(double);
+  // Gram chunk (ld = n rounded up to 16) + self-kernel values + split partials
+  return (chunk * round_up(n, PK) + chunk) * (long long)sizeof(double) + mgb_posterior_reduce_workspace_bytes(chunk, n);
 }
 
 extern "C" int mgb_series_posterior(const mgb_series_desc* desc, const double* xc, long long m, long long ldc,
@@ -333,12 +399,17 @@ extern "C" int mgb_series_posterior(const mgb_series_desc* desc, const double* x
   const long long ldk = round_up(n, PK);
   double* Kc = static_cast<double*>(workspace);
   double* kss = Kc + chunk * ldk;
+  double* part = kss + chunk;
+  const long long part_bytes = mgb_posterior_reduce_workspace_bytes(chunk, n);
+  // padding columns [n, ldk) of the Gram chunk are read by the bulk copies (multiplied by zeros of the factor):
+  // they must hold finite values, so the chunk buffer is cleared once per call
+  if (ldk != n) MGB_TRY(check_cuda(cudaMemsetAsync(Kc, 0, sizeof(double) * (size_t)(chunk < m ? chunk : m) * ldk, s), "cudaMemsetAsync"));
   fill_kernel<<<(unsigned)((chunk + 255) / 256), 256, 0, s>>>(kss, kss_value, chunk);
   MGB_TRY(after_launch("fill_kernel"));
   for (long long c0 = 0; c0 < m; c0 += chunk) {
     const long long mc = (m - c0 < chunk) ? (m - c0) : chunk;
     MGB_TRY(mgb_series_gram_fwd(desc, xc + c0 * ldc, mc, ldc, xtrain, n, ldt, coef, Kc, ldk, stream));
-    MGB_TRY(mgb_posterior_reduce(Kc, mc, n, ldk, packed, kss, mean_const, mean + c0, var + c0, stream));
+    MGB_TRY(mgb_posterior_reduce(Kc, mc, n, ldk, packed, kss, mean_const, mean + c0, var + c0, part, part_bytes, stream));
   }
   return MGB_OK;
 }

@@ -90,7 +90,8 @@ __device__ __forceinline__ double clamp_exact(double u, double lo, double hi) {
 
 template <int W, int TREG>
 __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams p) {
-  constexpr int RB = (W <= 6) ? 4 : 2;
+  constexpr int RB = 4;                       // rows per iteration: 8 independent chains per thread
+  constexpr bool kRowsInRegs = (W <= 6);      // small rows are fetched with 16-byte broadcasts up front
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t bar;
   double* x1s = smem;  // kTM * W
@@ -125,8 +126,11 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
 #pragma unroll 1
   for (int r = r_begin; r < r_begin + kRowsPerWarp; r += RB) {
     if (r >= rows) break;
-    double v[RB * W];
-    if constexpr ((RB * W) % 2 == 0) {
+    double ua[RB], ub[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) ua[q] = ub[q] = p.shift;
+    if constexpr (kRowsInRegs) {
+      double v[RB * W];
       const double2* src = reinterpret_cast<const double2*>(x1s + r * W);  // r % RB == 0 -> 16-byte aligned
 #pragma unroll
       for (int i = 0; i < RB * W / 2; ++i) {
@@ -134,24 +138,32 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
         v[2 * i] = t.x;
         v[2 * i + 1] = t.y;
       }
-    } else {
 #pragma unroll
-      for (int i = 0; i < RB * W; ++i) v[i] = x1s[r * W + i];
+      for (int k = 0; k < W; ++k) {
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+          ua[q] = fma(v[q * W + k], xa[k], ua[q]);
+          ub[q] = fma(v[q * W + k], xb[k], ub[q]);
+        }
+      }
+    } else {
+      // wide rows: k-outer, operands straight from shared memory (broadcast), 2*RB chains in flight
+      const double* xr = x1s + r * W;
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+          const double v = xr[q * W + k];
+          ua[q] = fma(v, xa[k], ua[q]);
+          ub[q] = fma(v, xb[k], ub[q]);
+        }
+      }
     }
-    double ua[RB], ub[RB];
     unsigned need = 0;
 #pragma unroll
     for (int q = 0; q < RB; ++q) {
-      double da = p.shift, db = p.shift;
-#pragma unroll
-      for (int k = 0; k < W; ++k) {
-        da = fma(v[q * W + k], xa[k], da);
-        db = fma(v[q * W + k], xb[k], db);
-      }
-      ua[q] = da;
-      ub[q] = db;
-      need |= (unsigned)(((unsigned)__double2hiint(da) & 0x7fffffffu) >= thr);
-      need |= (unsigned)(((unsigned)__double2hiint(db) & 0x7fffffffu) >= thr);
+      need |= (unsigned)(((unsigned)__double2hiint(ua[q]) & 0x7fffffffu) >= thr);
+      need |= (unsigned)(((unsigned)__double2hiint(ub[q]) & 0x7fffffffu) >= thr);
     }
     if (need) {
 #pragma unroll
@@ -457,7 +469,7 @@ __global__ void __launch_bounds__(kBwdThreads) series_gram_bwd_kernel(SeriesBwdP
 // ---------------------------------------------------------------------------------------------
 static int validate(const mgb_series_desc* d, const void* x1, long long m, long long ld1, const void* x2, long long n,
                     long long ld2, const void* coef) {
-  if (!d || !x1 || !x2 || !coef) return fail(MGB_ERR_ARG, "series_gram: null pointer");
+  if (!d || !coef || (m > 0 && !x1) || (n > 0 && !x2)) return fail(MGB_ERR_ARG, "series_gram: null pointer");
   if (d->n_factors < 1 || d->n_factors > MGB_MAX_FACTORS) return fail(MGB_ERR_ARG, "series_gram: n_factors out of range");
   if (d->factor_width < 1) return fail(MGB_ERR_ARG, "series_gram: factor_width < 1");
   if (d->n_terms < 1 || d->n_terms > MGB_MAX_TERMS) return fail(MGB_ERR_ARG, "series_gram: n_terms out of range");
@@ -498,8 +510,8 @@ extern "C" int mgb_series_gram_fwd(const mgb_series_desc* d, const double* x1, l
                                    const double* x2, long long n, long long ld2, const double* coef, double* K,
                                    long long ldk, void* stream) {
   MGB_TRY(validate(d, x1, m, ld1, x2, n, ld2, coef));
-  if (!K || ldk < n) return fail(MGB_ERR_ARG, "series_gram_fwd: bad K / ldk");
   if (m == 0 || n == 0) return MGB_OK;
+  if (!K || ldk < n) return fail(MGB_ERR_ARG, "series_gram_fwd: bad K / ldk");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SeriesParams p{x1, m, ld1, x2, n, ld2, coef, K, ldk, d->n_factors, d->factor_width, d->n_terms,
                  d->scale, d->shift, d->lo, d->hi, (n + kTN - 1) / kTN, 0u};

@@ -196,7 +196,7 @@ class ScaleKernel(Kernel):
         kwargs.setdefault("batch_shape", getattr(base_kernel, "batch_shape", torch.Size([])))
         super().__init__(**kwargs)
         self.base_kernel = base_kernel
-        self.register_parameter("raw_outputscale", nn.Parameter(torch.zeros(*self.batch_shape)))
+        self.register_parameter("raw_outputscale", nn.Parameter(torch.zeros(self.batch_shape)))
         self.register_constraint("raw_outputscale",
                                  Positive() if outputscale_constraint is None else outputscale_constraint)
         if outputscale_prior is not None:

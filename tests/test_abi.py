@@ -29,7 +29,8 @@ def test_loader_and_version():
     assert lib.mgb_version() == 100
     assert lib.mgb_launch_count() >= 0
     assert lib.mgb_posterior_pack_bytes(5000) == 5120 * 5008 * 8
-    assert lib.mgb_posterior_workspace_bytes(128, 100) == (128 * 112 + 128) * 8
+    assert lib.mgb_posterior_workspace_bytes(128, 100) == (128 * 112 + 128) * 8 + lib.mgb_posterior_reduce_workspace_bytes(128, 100)
+    assert lib.mgb_posterior_reduce_workspace_bytes(0, 100) == 0
 
 
 def test_series_desc_layout_matches_header():

@@ -1,0 +1,72 @@
+"""not gpu: the N > 1 host logic (row partition, state broadcast, mean/var all-gather) with world_size = 2 over
+gloo on CPU.  The per-rank compute is injected (the oracle's plain-torch posterior) so the collective plumbing is
+exercised exactly as on the GPU box, where the injected function is the CUDA posterior."""
+import os
+import socket
+
+import torch
+import torch.multiprocessing as mp
+
+from materngabo_b200.posterior import shard_bounds
+
+
+def test_shard_bounds_cover_everything():
+    for m in (0, 1, 7, 8, 10_000_001):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(m, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == m
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, m, out_dir):
+    import torch.distributed as dist
+
+    from materngabo_b200.posterior import ShardedPosterior
+    from oracle import restated as R
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_default_dtype(torch.float64)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gen = torch.Generator().manual_seed(0)
+        xt = torch.nn.functional.normalize(torch.randn(40, 4, generator=gen), dim=-1)
+        y = torch.sin(3 * xt[:, 0])
+        xc = torch.nn.functional.normalize(torch.randn(m, 4, generator=gen), dim=-1)
+        kfn = lambda a, b: R.sphere_matern(a, b, 3, 2.5, 0.5)  # noqa: E731
+        sh = ShardedPosterior()
+        # rank 0 "did the fit"; the others start empty and receive the state
+        if rank == 0:
+            L, alpha = R.gp_fit(kfn, xt, y, 1.0, 1e-2, 0.0)
+            state = {"train": xt, "L": L, "alpha": alpha}
+        else:
+            state = {"like": torch.zeros(0)}
+        state = sh.broadcast_state(state, src=0)
+        sh.compute = lambda x: R.gp_predict(kfn, state["train"], state["L"], state["alpha"], x, 1.0, 0.0)
+        lo, hi = shard_bounds(m, world, rank)
+        mean, var = sh.evaluate(xc[lo:hi], gather=True)
+        local_mean, _ = sh.evaluate(xc[lo:hi], gather=False)
+        assert local_mean.shape[0] == hi - lo
+        full_mean, full_var = R.gp_posterior(kfn, xt, y, xc, 1.0, 1e-2, 0.0)
+        assert mean.shape == (m,) and torch.allclose(mean, full_mean, rtol=0, atol=1e-13)
+        assert torch.allclose(var, full_var, rtol=0, atol=1e-13)
+        torch.save(mean, os.path.join(out_dir, "mean_%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    world, m = 2, 101          # odd count: uneven shards
+    mp.spawn(_worker, args=(world, _free_port(), m, str(tmp_path)), nprocs=world, join=True)
+    a = torch.load(os.path.join(str(tmp_path), "mean_0.pt"))
+    b = torch.load(os.path.join(str(tmp_path), "mean_1.pt"))
+    assert torch.equal(a, b)   # every rank ends with the same gathered vector
