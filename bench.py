@@ -240,8 +240,7 @@ def posterior_roofline(gp, xc, n, lib):
     if xc.shape[0] < chunk:
         chunk = xc.shape[0]
         reps = 1
-    ldk = (n + 15) // 16 * 16
-    kc = torch.zeros((chunk, ldk), dtype=F64, device=xc.device)
+    kb = torch.zeros(lib.mgb_posterior_tiled_bytes(chunk, n) // 8, dtype=F64, device=xc.device)
     part = torch.empty(max(1, lib.mgb_posterior_reduce_workspace_bytes(chunk, n) // 8), dtype=F64, device=xc.device)
     kss = torch.full((chunk,), gp.kss_value, dtype=F64, device=xc.device)
     mean = torch.empty(chunk, dtype=F64, device=xc.device)
@@ -253,10 +252,10 @@ def posterior_roofline(gp, xc, n, lib):
     for i in range(reps + 1):      # first pass warms up
         x = xc[(i % reps) * chunk:(i % reps) * chunk + chunk]
         ev[i][0].record()
-        _lib.check(lib.mgb_series_gram_fwd(C.byref(d), _lib.ptr(x), chunk, x.stride(0), _lib.ptr(gp.train_prepared), n,
-                                           gp.train_prepared.stride(0), _lib.ptr(gp.coef), _lib.ptr(kc), ldk, st), "gram")
+        _lib.check(lib.mgb_series_gram_tiled(C.byref(d), _lib.ptr(x), chunk, x.stride(0), _lib.ptr(gp.train_prepared), n,
+                                             gp.train_prepared.stride(0), _lib.ptr(gp.coef), _lib.ptr(kb), st), "gram")
         ev[i][1].record()
-        _lib.check(lib.mgb_posterior_reduce(_lib.ptr(kc), chunk, n, ldk, _lib.ptr(gp._packed), _lib.ptr(kss),
+        _lib.check(lib.mgb_posterior_reduce(_lib.ptr(kb), chunk, n, _lib.ptr(gp._packed), _lib.ptr(kss),
                                             gp.mean_const, _lib.ptr(mean), _lib.ptr(var), _lib.ptr(part),
                                             part.numel() * 8, st), "reduce")
         ev[i][2].record()

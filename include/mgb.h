@@ -137,19 +137,27 @@ int mgb_spd2_gram_bwd_coef(int use_cholesky, const double* x1, long long m, long
  *
  * mgb_posterior_pack builds, once per GP fit, the packed factor: lower triangle of Rinv padded with zeros
  * to (n+1 rounded up to 128) x (n rounded up to 16) doubles, row n holding alpha (so the mean falls out of
- * the same tiles).  mgb_posterior_reduce is the fused triangular product + square-sum + mean on FP64
- * tensor-core DMMA tiles; Kc is consumed, V = Rinv Kc^T is never written to memory.
- * Kc must be 16-byte aligned with an even ldk >= n rounded up to 16; the padding columns [n, ldk) are read (and
- * multiplied by zeros of the packed factor), so they must hold finite values.  kss: m values
- * (k(x_c, x_c) * outputscale).  Results are deterministic (fixed summation order).
+ * the same tiles), stored tile-major: 128 x 16 blocks [row tile][column chunk][row][16], the eight 16-byte
+ * pieces of a block row XOR-swizzled by 2*(row & 3).  One block = one 16 KB TMA bulk copy into shared memory,
+ * after which the DMMA fragment loads are bank-conflict free.
+ * mgb_series_gram_tiled writes K(Xc, Xtrain) for a block of candidates in the same layout
+ * ([candidate tile][column chunk][row][16], mgb_posterior_tiled_bytes(m, n) bytes, 16-byte aligned; rows beyond
+ * m and columns beyond n are not written and must hold finite values - clear the buffer once).
+ * mgb_posterior_reduce is the fused triangular product + square-sum + mean on FP64 tensor-core DMMA tiles;
+ * V = Rinv Kc^T is never written to memory.  kss: m values (k(x_c, x_c) * outputscale).
+ * Results are deterministic (fixed summation order).
  * ------------------------------------------------------------------------------------------------ */
 long long mgb_posterior_pack_bytes(long long n);
 int mgb_posterior_pack(const double* Rinv, long long n, long long ldr, const double* alpha, double* packed,
                        void* stream);
+long long mgb_posterior_tiled_bytes(long long m, long long n);
+int mgb_series_gram_tiled(const mgb_series_desc* desc, const double* x1, long long m, long long ld1,
+                          const double* x2, long long n, long long ld2, const double* coef, double* Kb,
+                          void* stream);
 /* bytes of scratch mgb_posterior_reduce needs for m candidates (0 when one CTA per candidate tile suffices) */
 long long mgb_posterior_reduce_workspace_bytes(long long m, long long n);
-int mgb_posterior_reduce(const double* Kc, long long m, long long n, long long ldk, const double* packed,
-                         const double* kss, double mean_const, double* mean, double* var, void* workspace,
+int mgb_posterior_reduce(const double* Kb, long long m, long long n, const double* packed, const double* kss,
+                         double mean_const, double* mean, double* var, void* workspace,
                          long long workspace_bytes, void* stream);
 /* scratch mgb_series_posterior needs for `chunk` candidates x n training points (bytes) */
 long long mgb_posterior_workspace_bytes(long long chunk, long long n);

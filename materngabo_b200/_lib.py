@@ -47,7 +47,9 @@ PROTOTYPES = {
     "mgb_posterior_pack_bytes": (_LL, [_LL]),
     "mgb_posterior_pack": (_I, [_P, _LL, _LL, _P, _P, _P]),
     "mgb_posterior_reduce_workspace_bytes": (_LL, [_LL, _LL]),
-    "mgb_posterior_reduce": (_I, [_P, _LL, _LL, _LL, _P, _P, _D, _P, _P, _P, _LL, _P]),
+    "mgb_posterior_tiled_bytes": (_LL, [_LL, _LL]),
+    "mgb_series_gram_tiled": (_I, [_DESC, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P]),
+    "mgb_posterior_reduce": (_I, [_P, _LL, _LL, _P, _P, _D, _P, _P, _P, _LL, _P]),
     "mgb_posterior_workspace_bytes": (_LL, [_LL, _LL]),
     "mgb_series_posterior": (_I, [_DESC, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _D, _D, _P, _P, _P, _LL, _LL, _P]),
     "mgb_series_gram_host": (_I, [_DESC, _P, _LL, _P, _LL, _P, _P, _I]),

@@ -25,14 +25,14 @@ namespace mgb {
 
 constexpr int PT = 128;       // tile edge (candidates and factor rows)
 constexpr int PK = 16;        // columns per pipeline stage
-constexpr int PLD = PK + 4;   // smem row pitch in doubles (bank-conflict-free fragment loads)
-constexpr int PSTAGES = 5;
+constexpr int PBLK = PT * PK;  // doubles per 128 x 16 operand block (16 KB), tile-major + swizzled in HBM
+constexpr int PSTAGES = 6;
 constexpr int PCONSUMERS = 8;                       // DMMA warps
 constexpr int PTHREADS = (PCONSUMERS + 4) * 32;     // + one producer warpgroup (one warp of it issues copies)
 constexpr int PREGS_PRODUCER = 40;                  // setmaxnreg budgets: 4*32*40 + 8*32*232 = 64512 <= 65536
 constexpr int PREGS_CONSUMER = 232;
-constexpr size_t kPostSmem = sizeof(double) * (size_t)PSTAGES * 2 * PT * PLD + 2 * PSTAGES * sizeof(uint64_t);
-constexpr uint32_t kStageBytes = 2u * PT * PK * sizeof(double);
+constexpr size_t kPostSmem = sizeof(double) * (size_t)PSTAGES * 2 * PBLK + 2 * PSTAGES * sizeof(uint64_t);
+constexpr uint32_t kBlockBytes = PBLK * sizeof(double);
 
 __host__ __device__ inline long long round_up(long long v, long long q) { return (v + q - 1) / q * q; }
 
@@ -61,8 +61,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 struct PostParams {
-  const double* Kc; long long m, n, ldk;
-  const double* Rp; long long rows_p, ldp;   // packed factor
+  const double* Kb; long long m, n;           // Gram chunk, tiled layout [ctile][chunk][128][16] (swizzled)
+  const double* Rp; long long rows_p, ldp;   // packed factor, tiled layout [row tile][chunk][128][16] (swizzled)
   const double* kss;
   double mean_const;
   double* mean; double* var;
@@ -83,9 +83,9 @@ __device__ __forceinline__ int tile_of(int j, int r, int S, int n_tiles) {
 // stage through `empty` mbarriers.  No CTA-wide barrier in the main loop: warps may drift by up to 4 stages.
 __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParams p) {
   extern __shared__ __align__(16) double smem[];
-  double* As = smem;                               // [stage][PT][PLD]
-  double* Bs = smem + (size_t)PSTAGES * PT * PLD;  // [stage][PT][PLD]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)PSTAGES * 2 * PT * PLD);
+  double* As = smem;                            // [stage][PT][PK]
+  double* Bs = smem + (size_t)PSTAGES * PBLK;   // [stage][PT][PK]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)PSTAGES * 2 * PBLK);
   uint64_t* empty = full + PSTAGES;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -117,34 +117,23 @@ __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParam
     if (warp != PCONSUMERS) return;
     int stage = 0;
     uint32_t phase = 0;
-    // each lane owns rows lane, lane+32, lane+64, lane+96 of both panels
-    const double* a_src[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      long long row = c0 + lane + 32 * q;
-      if (row >= p.m) row = p.m - 1;   // rows past the end read a valid row; their results are never stored
-      a_src[q] = p.Kc + row * p.ldk;
-    }
-    for (int j = 0; j < rounds; ++j) {
-      const int t = tile_of(j, split, S, p.n_tiles);
-      if (t < 0) continue;
-      const int nch = chunks_of(t);
-      const double* b_row0 = p.Rp + ((long long)t * PT + lane) * p.ldp;
-      for (int ch = 0; ch < nch; ++ch) {
-        mbar_spin(empty + stage, phase ^ 1u);
-        if (lane == 0) mbar_expect_tx(full + stage, kStageBytes);
-        __syncwarp();
-        double* ad = As + ((size_t)stage * PT + lane) * PLD;
-        double* bd = Bs + ((size_t)stage * PT + lane) * PLD;
-        const long long j0 = (long long)ch * PK;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          bulk_g2s(ad + (size_t)32 * q * PLD, a_src[q] + j0, PK * sizeof(double), full + stage);
-          bulk_g2s(bd + (size_t)32 * q * PLD, b_row0 + (long long)32 * q * p.ldp + j0, PK * sizeof(double), full + stage);
-        }
-        if (++stage == PSTAGES) {
-          stage = 0;
-          phase ^= 1u;
+    const long long nch_all = n_pad / PK;
+    const double* a_blocks = p.Kb + ctile * nch_all * PBLK;
+    if (lane == 0) {
+      for (int j = 0; j < rounds; ++j) {
+        const int t = tile_of(j, split, S, p.n_tiles);
+        if (t < 0) continue;
+        const int nch = chunks_of(t);
+        const double* b_blocks = p.Rp + (long long)t * nch_all * PBLK;
+        for (int ch = 0; ch < nch; ++ch) {
+          mbar_spin(empty + stage, phase ^ 1u);
+          mbar_expect_tx(full + stage, 2u * kBlockBytes);
+          bulk_g2s(As + (size_t)stage * PBLK, a_blocks + (long long)ch * PBLK, kBlockBytes, full + stage);
+          bulk_g2s(Bs + (size_t)stage * PBLK, b_blocks + (long long)ch * PBLK, kBlockBytes, full + stage);
+          if (++stage == PSTAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -165,6 +154,11 @@ __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParam
   for (int a = 0; a < 8; ++a) sumsq[a] = meanv[a] = 0.0;
 
   const int frow = lane >> 2, fk = lane & 3;
+  // element (row, col = 4 k4 + fk) of a block lives at row*16 + ((chunk ^ 2 (row & 3)) * 2 + (col & 1)), chunk = col / 2;
+  // all fragment rows of this lane are congruent to frow modulo 4
+  int koff[PK / 4];
+#pragma unroll
+  for (int k4 = 0; k4 < PK / 4; ++k4) koff[k4] = (((2 * k4 + (fk >> 1)) ^ ((frow & 3) << 1)) << 1) | (fk & 1);
   int stage = 0;
   uint32_t phase = 0;
   bool owns_mean = false;
@@ -185,16 +179,16 @@ __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParam
       int b_lo = 0;
       while (b_lo < b_hi && row_base + 32 * b_lo + 7 < j0) ++b_lo;
       mbar_spin(full + stage, phase);
-      const double* at = As + ((size_t)stage * PT + wc * 64 + frow) * PLD + fk;
-      const double* bt = Bs + ((size_t)stage * PT + 8 * wi + frow) * PLD + fk;
+      const double* at = As + ((size_t)stage * PT + wc * 64 + frow) * PK;
+      const double* bt = Bs + ((size_t)stage * PT + 8 * wi + frow) * PK;
       if (b_lo == 0 && b_hi == 4) {
 #pragma unroll
         for (int k4 = 0; k4 < PK / 4; ++k4) {
           double af[8], bf[4];
 #pragma unroll
-          for (int a = 0; a < 8; ++a) af[a] = at[(a * 8) * PLD + k4 * 4];
+          for (int a = 0; a < 8; ++a) af[a] = at[(a * 8) * PK + koff[k4]];
 #pragma unroll
-          for (int b = 0; b < 4; ++b) bf[b] = bt[(b * 32) * PLD + k4 * 4];
+          for (int b = 0; b < 4; ++b) bf[b] = bt[(b * 32) * PK + koff[k4]];
 #pragma unroll
           for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -205,11 +199,11 @@ __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParam
         for (int k4 = 0; k4 < PK / 4; ++k4) {
           double af[8];
 #pragma unroll
-          for (int a = 0; a < 8; ++a) af[a] = at[(a * 8) * PLD + k4 * 4];
+          for (int a = 0; a < 8; ++a) af[a] = at[(a * 8) * PK + koff[k4]];
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             if (b >= b_lo && b < b_hi) {
-              const double bfv = bt[(b * 32) * PLD + k4 * 4];
+              const double bfv = bt[(b * 32) * PK + koff[k4]];
 #pragma unroll
               for (int a = 0; a < 8; ++a) dmma(acc0[a][b], acc1[a][b], af[a], bfv);
             }
@@ -274,7 +268,7 @@ __global__ void posterior_finalize_kernel(const double* kss, const double* parti
   var[c] = kss[c] - tot;
 }
 
-// Pack Rinv (lower triangle) + alpha into the padded operand.
+// Pack Rinv (lower triangle) + alpha into the padded, tile-major, swizzled operand.
 __global__ void posterior_pack_kernel(const double* Rinv, long long n, long long ldr, const double* alpha,
                                       double* Rp, long long rows_p, long long ldp) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,7 +277,9 @@ __global__ void posterior_pack_kernel(const double* Rinv, long long n, long long
   double v = 0.0;
   if (i < n && j <= i) v = Rinv[i * ldr + j];
   else if (i == n && j < n) v = alpha[j];
-  Rp[i * ldp + j] = v;
+  const long long t = i >> 7, ch = j >> 4;
+  const int r = (int)(i & 127), chunk = (int)(j & 15) >> 1;
+  Rp[((((t * (ldp >> 4) + ch) << 7) + r) << 4) + (((chunk ^ ((r & 3) << 1)) << 1) | (int)(j & 1))] = v;
 }
 
 __global__ void fill_kernel(double* dst, double v, long long count) {
@@ -328,7 +324,7 @@ static int choose_splits(long long m, long long n) {
   const int sms = post_sm_count();
   const long long ctiles = (m + PT - 1) / PT;
   const int n_tiles = (int)(round_up(n + 1, PT) / PT);
-  const double panel_bytes = (double)PT * (double)round_up(n, PK) * 8.0;
+  const double panel_bytes = (double)PT * (double)round_up(n, PK) * 8.0;  // one candidate tile's Gram panel
   long long s_l2 = (long long)ceil(sms * panel_bytes / (40.0 * 1024 * 1024));
   long long s_fill = (2LL * sms + ctiles - 1) / ctiles;
   long long s = s_l2 > s_fill ? s_l2 : s_fill;
@@ -343,13 +339,12 @@ extern "C" long long mgb_posterior_reduce_workspace_bytes(long long m, long long
   return s > 1 ? (long long)s * m * (long long)sizeof(double) : 0;
 }
 
-extern "C" int mgb_posterior_reduce(const double* Kc, long long m, long long n, long long ldk, const double* packed,
+extern "C" int mgb_posterior_reduce(const double* Kb, long long m, long long n, const double* packed,
                                     const double* kss, double mean_const, double* mean, double* var, void* workspace,
                                     long long workspace_bytes, void* stream) {
-  if (!Kc || !packed || !kss || !mean || !var) return fail(MGB_ERR_ARG, "posterior_reduce: null pointer");
+  if (!Kb || !packed || !kss || !mean || !var) return fail(MGB_ERR_ARG, "posterior_reduce: null pointer");
   if (m < 0 || n < 1) return fail(MGB_ERR_ARG, "posterior_reduce: bad sizes");
-  if (ldk < round_up(n, PK) || (ldk & 1) || (reinterpret_cast<uintptr_t>(Kc) & 15u))
-    return fail(MGB_ERR_ARG, "posterior_reduce: Kc must be 16-byte aligned with even ldk >= n rounded up to 16 (finite padding)");
+  if (reinterpret_cast<uintptr_t>(Kb) & 15u) return fail(MGB_ERR_ARG, "posterior_reduce: Kb must be 16-byte aligned");
   if (m == 0) return MGB_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   static bool attr_set = false;
@@ -359,7 +354,7 @@ extern "C" int mgb_posterior_reduce(const double* Kc, long long m, long long n, 
     attr_set = true;
   }
   PostParams p;
-  p.Kc = Kc; p.m = m; p.n = n; p.ldk = ldk;
+  p.Kb = Kb; p.m = m; p.n = n;
   p.Rp = packed; p.rows_p = round_up(n + 1, PT); p.ldp = round_up(n, PK);
   p.kss = kss; p.mean_const = mean_const; p.mean = mean; p.var = var;
   p.n_tiles = (int)(p.rows_p / PT);
@@ -383,8 +378,9 @@ extern "C" int mgb_posterior_reduce(const double* Kc, long long m, long long n, 
 
 extern "C" long long mgb_posterior_workspace_bytes(long long chunk, long long n) {
   if (chunk < 0 || n < 0) return 0;
-  // Gram chunk (ld = n rounded up to 16) + self-kernel values + split partials
-  return (chunk * round_up(n, PK) + chunk) * (long long)sizeof(double) + mgb_posterior_reduce_workspace_bytes(chunk, n);
+  // tiled Gram chunk + self-kernel values + split partials
+  return round_up(chunk, PT) * round_up(n, PK) * (long long)sizeof(double) + round_up(chunk, 2) * (long long)sizeof(double) +
+         mgb_posterior_reduce_workspace_bytes(chunk, n);
 }
 
 extern "C" int mgb_series_posterior(const mgb_series_desc* desc, const double* xc, long long m, long long ldc,
@@ -396,20 +392,22 @@ extern "C" int mgb_series_posterior(const mgb_series_desc* desc, const double* x
   if (workspace_bytes < mgb_posterior_workspace_bytes(chunk, n)) return fail(MGB_ERR_ARG, "series_posterior: workspace too small");
   if (reinterpret_cast<uintptr_t>(workspace) & 15u) return fail(MGB_ERR_ARG, "series_posterior: workspace must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const long long ldk = round_up(n, PK);
-  double* Kc = static_cast<double*>(workspace);
-  double* kss = Kc + chunk * ldk;
-  double* part = kss + chunk;
+  double* Kb = static_cast<double*>(workspace);
+  const long long kb_doubles = round_up(chunk, PT) * round_up(n, PK);
+  double* kss = Kb + kb_doubles;
+  double* part = kss + round_up(chunk, 2);
   const long long part_bytes = mgb_posterior_reduce_workspace_bytes(chunk, n);
-  // padding columns [n, ldk) of the Gram chunk are read by the bulk copies (multiplied by zeros of the factor):
-  // they must hold finite values, so the chunk buffer is cleared once per call
-  if (ldk != n) MGB_TRY(check_cuda(cudaMemsetAsync(Kc, 0, sizeof(double) * (size_t)(chunk < m ? chunk : m) * ldk, s), "cudaMemsetAsync"));
+  // Rows past the last candidate of a tile and the padding columns [n, n rounded up to 16) of the tiled chunk are
+  // read by the bulk copies (and multiplied by zeros of the factor / never stored): they must be finite, so the
+  // part of the buffer this call uses is cleared once.
+  const long long used_rows = round_up(chunk < m ? chunk : m, PT);
+  MGB_TRY(check_cuda(cudaMemsetAsync(Kb, 0, sizeof(double) * (size_t)used_rows * round_up(n, PK), s), "cudaMemsetAsync"));
   fill_kernel<<<(unsigned)((chunk + 255) / 256), 256, 0, s>>>(kss, kss_value, chunk);
   MGB_TRY(after_launch("fill_kernel"));
   for (long long c0 = 0; c0 < m; c0 += chunk) {
     const long long mc = (m - c0 < chunk) ? (m - c0) : chunk;
-    MGB_TRY(mgb_series_gram_fwd(desc, xc + c0 * ldc, mc, ldc, xtrain, n, ldt, coef, Kc, ldk, stream));
-    MGB_TRY(mgb_posterior_reduce(Kc, mc, n, ldk, packed, kss, mean_const, mean + c0, var + c0, part, part_bytes, stream));
+    MGB_TRY(mgb_series_gram_tiled(desc, xc + c0 * ldc, mc, ldc, xtrain, n, ldt, coef, Kb, stream));
+    MGB_TRY(mgb_posterior_reduce(Kb, mc, n, packed, kss, mean_const, mean + c0, var + c0, part, part_bytes, stream));
   }
   return MGB_OK;
 }

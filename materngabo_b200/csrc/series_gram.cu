@@ -35,7 +35,27 @@ struct SeriesParams {
   double scale, shift, lo, hi;
   long long ncc;        // column chunks
   unsigned clamp_word;  // high 32 bits of min(|lo|, |hi|): |u| below this word can never need clamping
+  int tiled;            // 1: write the tile-major swizzled layout consumed by posterior_reduce_kernel
+  long long nch;        // tiled: 16-column chunks per row (n rounded up to 16, / 16)
 };
+
+// Address of K[grow][col].  Row-major, or the posterior's operand layout: 128 x 16 blocks stored
+// [candidate tile][column chunk][row][16], each row's eight 16-byte chunks XOR-swizzled by 2*(row & 3) so that the
+// DMMA fragment loads of the consumer are bank-conflict free after ONE 16 KB bulk copy per block.
+__device__ __forceinline__ double* out_ptr(const SeriesParams& p, long long grow, long long col) {
+  if (!p.tiled) return p.K + grow * p.ldk + col;
+  const long long ctile = grow >> 7;
+  const int r = (int)(grow & 127);
+  const long long ch = col >> 4;
+  const int chunk = (int)(col & 15) >> 1;
+  return p.K + ((((ctile * p.nch + ch) << 7) + r) << 4) + (((chunk ^ ((r & 3) << 1)) << 1) | (int)(col & 1));
+}
+
+// row-major results are write-once (evict-first); the tiled chunk is re-read right away by the posterior kernel
+__device__ __forceinline__ void st_keep2(double* p, double a, double b, int keep) {
+  if (keep) *reinterpret_cast<double2*>(p) = make_double2(a, b);
+  else st_stream2(p, a, b);
+}
 
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -119,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
   }
   stage_panel(x1s, p.x1, row0, rows, W, p.ld1, &bar);
 
-  const bool vec_ok = (col + 1 < p.n) && ((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0);
+  const bool vec_ok = (col + 1 < p.n) && (p.tiled || (((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0)));
   const bool va = col < p.n, vb = col + 1 < p.n;
   const int r_begin = warp * kRowsPerWarp;
   const unsigned thr = p.clamp_word;
@@ -186,9 +206,9 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
 #pragma unroll
     for (int q = 0; q < RB; ++q) {
       if (r + q < rows) {
-        double* out = p.K + (row0 + r + q) * p.ldk + col;
+        double* out = out_ptr(p, row0 + r + q, col);
         if (vec_ok) {
-          st_stream2(out, pa[q], pb[q]);
+          st_keep2(out, pa[q], pb[q], p.tiled);
         } else {
           if (va) st_stream(out, pa[q]);
           if (vb) st_stream(out + 1, pb[q]);
@@ -263,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_general(SeriesPar
   __syncthreads();
 
   const long long col = cc * kTN + 2 * lane;
-  const bool vec_ok = (col + 1 < p.n) && ((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0);
+  const bool vec_ok = (col + 1 < p.n) && (p.tiled || (((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0)));
   const int r_begin = warp * kRowsPerWarp;
   for (int rr = 0; rr < kRowsPerWarp; rr += 2) {
     const int r0 = r_begin + rr;
@@ -300,9 +320,9 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_general(SeriesPar
     for (int h = 0; h < 2; ++h) {
       const int r = (h == 0) ? r0 : r0 + 1;
       if (r >= rows) break;
-      double* out = p.K + (row0 + r) * p.ldk + col;
+      double* out = out_ptr(p, row0 + r, col);
       if (vec_ok) {
-        st_stream2(out, prod[2 * h], prod[2 * h + 1]);
+        st_keep2(out, prod[2 * h], prod[2 * h + 1], p.tiled);
       } else {
         if (col < p.n) st_stream(out, prod[2 * h]);
         if (col + 1 < p.n) st_stream(out + 1, prod[2 * h + 1]);
@@ -506,15 +526,16 @@ static int dispatch_fast(const SeriesParams& p, long long tiles, cudaStream_t s,
 
 using namespace mgb;
 
-extern "C" int mgb_series_gram_fwd(const mgb_series_desc* d, const double* x1, long long m, long long ld1,
-                                   const double* x2, long long n, long long ld2, const double* coef, double* K,
-                                   long long ldk, void* stream) {
+static int series_fwd_impl(const mgb_series_desc* d, const double* x1, long long m, long long ld1, const double* x2,
+                           long long n, long long ld2, const double* coef, double* K, long long ldk, int tiled,
+                           void* stream) {
   MGB_TRY(validate(d, x1, m, ld1, x2, n, ld2, coef));
   if (m == 0 || n == 0) return MGB_OK;
-  if (!K || ldk < n) return fail(MGB_ERR_ARG, "series_gram_fwd: bad K / ldk");
+  if (!K || (!tiled && ldk < n)) return fail(MGB_ERR_ARG, "series_gram_fwd: bad K / ldk");
+  if (tiled && (reinterpret_cast<uintptr_t>(K) & 15u)) return fail(MGB_ERR_ARG, "series_gram_tiled: K must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SeriesParams p{x1, m, ld1, x2, n, ld2, coef, K, ldk, d->n_factors, d->factor_width, d->n_terms,
-                 d->scale, d->shift, d->lo, d->hi, (n + kTN - 1) / kTN, 0u};
+                 d->scale, d->shift, d->lo, d->hi, (n + kTN - 1) / kTN, 0u, tiled, (n + 15) / 16};
   if (d->lo < 0.0 && d->hi > 0.0) {
     const double bound = fmin(-d->lo, d->hi);
     unsigned long long bits;
@@ -541,6 +562,23 @@ extern "C" int mgb_series_gram_fwd(const mgb_series_desc* d, const double* x1, l
     series_gram_fwd_general<MGB_BASIS_CHEBYSHEV><<<(unsigned)tiles, kThreads, smem, s>>>(p);
   }
   return after_launch("series_gram_fwd_general");
+}
+
+extern "C" int mgb_series_gram_fwd(const mgb_series_desc* d, const double* x1, long long m, long long ld1,
+                                   const double* x2, long long n, long long ld2, const double* coef, double* K,
+                                   long long ldk, void* stream) {
+  return series_fwd_impl(d, x1, m, ld1, x2, n, ld2, coef, K, ldk, 0, stream);
+}
+
+extern "C" long long mgb_posterior_tiled_bytes(long long m, long long n) {
+  if (m < 0 || n < 0) return 0;
+  return ((m + 127) / 128 * 128) * ((n + 15) / 16 * 16) * (long long)sizeof(double);
+}
+
+extern "C" int mgb_series_gram_tiled(const mgb_series_desc* d, const double* x1, long long m, long long ld1,
+                                     const double* x2, long long n, long long ld2, const double* coef, double* Kb,
+                                     void* stream) {
+  return series_fwd_impl(d, x1, m, ld1, x2, n, ld2, coef, Kb, 0, 1, stream);
 }
 
 static int launch_bwd(const mgb_series_desc* d, int order, const double* xa, long long ma, long long lda,
