@@ -35,6 +35,7 @@ struct SeriesParams {
   double scale, shift, lo, hi;
   long long ncc;        // column chunks
   unsigned clamp_word;  // high 32 bits of min(|lo|, |hi|): |u| below this word can never need clamping
+  int row_splits;       // CTAs per column chunk; CTA s walks row panels s, s + row_splits, ...
   int tiled;            // 1: write the tile-major swizzled layout consumed by posterior_reduce_kernel
   long long nch;        // tiled: 16-column chunks per row (n rounded up to 16, / 16)
 };
@@ -69,31 +70,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Stage rows [row0, row0+rows) of x (ld == D contiguous case uses one bulk copy) into dst[r*D + k].
-__device__ __forceinline__ void stage_panel(double* dst, const double* x, long long row0, int rows, int D,
-                                            long long ld, uint64_t* bar) {
+// Start staging rows [row0, row0+rows) of x into dst[r*D + k].  Contiguous, 16-byte aligned panels go through ONE
+// cp.async.bulk (TMA engine) that completes on `bar` (returns true: the consumer must wait on the barrier);
+// anything else is copied with plain loads (returns false: visible after the next __syncthreads()).
+__device__ __forceinline__ bool stage_panel_async(double* dst, const double* x, long long row0, int rows, int D,
+                                                  long long ld, uint64_t* bar) {
   const double* src = x + row0 * ld;
   const uint32_t bytes = static_cast<uint32_t>(rows) * D * 8u;
   const bool bulk = (ld == D) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && ((bytes & 15u) == 0);
   if (bulk) {
     if (threadIdx.x == 0) {
-      mbar_init(bar, 1);
-      fence_mbar_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
       mbar_expect_tx(bar, bytes);
       bulk_g2s(dst, src, bytes, bar);
-    }
-    while (!mbar_try_wait(bar, 0)) {
     }
   } else {
     for (int e = threadIdx.x; e < rows * D; e += blockDim.x) {
       int r = e / D, k = e - r * D;
       dst[e] = src[(long long)r * ld + k];
     }
-    __syncthreads();
   }
+  return bulk;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -113,14 +109,12 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
   constexpr int RB = 4;                       // rows per iteration: 8 independent chains per thread
   constexpr bool kRowsInRegs = (W <= 6);      // small rows are fetched with 16-byte broadcasts up front
   extern __shared__ __align__(16) double smem[];
-  __shared__ __align__(8) uint64_t bar;
-  double* x1s = smem;  // kTM * W
+  __shared__ __align__(8) uint64_t bars[2];
+  // two x1 panels (kTM * W doubles each): panel i+1 is in flight while panel i is evaluated
 
-  const long long tile = blockIdx.x;
-  const long long cc = tile % p.ncc;
-  const long long rp = tile / p.ncc;
-  const long long row0 = rp * kTM;
-  const int rows = (int)min((long long)kTM, p.m - row0);
+  const long long cc = blockIdx.x % p.ncc;
+  const int split = (int)(blockIdx.x / p.ncc);
+  const long long npanels = (p.m + kTM - 1) / kTM;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   double c[TREG];
@@ -137,12 +131,40 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
       xb[k] = vb ? p.scale * __ldg(p.x2 + (col + 1) * p.ld2 + k) : 0.0;
     }
   }
-  stage_panel(x1s, p.x1, row0, rows, W, p.ld1, &bar);
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
 
   const bool vec_ok = (col + 1 < p.n) && (p.tiled || (((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0)));
   const bool va = col < p.n, vb = col + 1 < p.n;
   const int r_begin = warp * kRowsPerWarp;
   const unsigned thr = p.clamp_word;
+
+  long long rp = split;
+  if (rp >= npanels) return;
+  unsigned parity = 0;   // bit b = phase parity of bars[b]
+  bool bulk_cur = stage_panel_async(smem, p.x1, rp * kTM, (int)min((long long)kTM, p.m - rp * kTM), W, p.ld1, &bars[0]);
+  for (int it = 0; rp < npanels; rp += p.row_splits, ++it) {
+    const int buf = it & 1;
+    double* x1s = smem + buf * (kTM * W);
+    const long long row0 = rp * kTM;
+    const int rows = (int)min((long long)kTM, p.m - row0);
+    // prefetch the next panel into the other buffer (every thread left it at the barrier ending iteration it-1)
+    const long long rp_next = rp + p.row_splits;
+    bool bulk_next = false;
+    if (rp_next < npanels)
+      bulk_next = stage_panel_async(smem + (buf ^ 1) * (kTM * W), p.x1, rp_next * kTM,
+                                    (int)min((long long)kTM, p.m - rp_next * kTM), W, p.ld1, &bars[buf ^ 1]);
+    if (bulk_cur) {
+      while (!mbar_try_wait(&bars[buf], (parity >> buf) & 1u)) {
+      }
+      parity ^= 1u << buf;
+    } else if (it == 0) {
+      __syncthreads();   // plain-load staging of the very first panel
+    }
 #pragma unroll 1
   for (int r = r_begin; r < r_begin + kRowsPerWarp; r += RB) {
     if (r >= rows) break;
@@ -216,6 +238,9 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
       }
     }
   }
+    __syncthreads();     // everyone is done with x1s[buf]; plain-load staging of the next panel is visible
+    bulk_cur = bulk_next;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -266,68 +291,83 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_general(SeriesPar
   double* x2t = x1s + kTM * D;        // D * kTN (transposed: [k][col])
   double* cfs = x2t + D * kTN;        // F * T
 
-  const long long tile = blockIdx.x;
-  const long long cc = tile % p.ncc;
-  const long long rp = tile / p.ncc;
-  const long long row0 = rp * kTM;
-  const int rows = (int)min((long long)kTM, p.m - row0);
+  const long long cc = blockIdx.x % p.ncc;
+  const int split = (int)(blockIdx.x / p.ncc);
+  const long long npanels = (p.m + kTM - 1) / kTM;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+  // staged once per CTA: coefficients and the transposed x2 panel of this column chunk
   for (int e = threadIdx.x; e < p.F * p.T; e += blockDim.x) cfs[e] = p.coef[e];
   for (int e = threadIdx.x; e < D * kTN; e += blockDim.x) {
     const int cidx = e / D, k = e - cidx * D;
     const long long gc = cc * kTN + cidx;
     x2t[k * kTN + cidx] = (gc < p.n) ? p.x2[gc * p.ld2 + k] : 0.0;
   }
-  stage_panel(x1s, p.x1, row0, rows, D, p.ld1, &bar);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
   __syncthreads();
 
   const long long col = cc * kTN + 2 * lane;
   const bool vec_ok = (col + 1 < p.n) && (p.tiled || (((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0)));
   const int r_begin = warp * kRowsPerWarp;
-  for (int rr = 0; rr < kRowsPerWarp; rr += 2) {
-    const int r0 = r_begin + rr;
-    if (r0 >= rows) break;
-    const int r1 = min(r0 + 1, rows - 1);
-    double prod[4] = {1.0, 1.0, 1.0, 1.0};
-    for (int f = 0; f < p.F; ++f) {
-      double d[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int k = 0; k < p.W; ++k) {
-        const int kk = f * p.W + k;
-        const double2 xc = *reinterpret_cast<const double2*>(x2t + kk * kTN + 2 * lane);
-        const double v0 = x1s[r0 * D + kk], v1 = x1s[r1 * D + kk];
-        d[0] = fma(v0, xc.x, d[0]);
-        d[1] = fma(v0, xc.y, d[1]);
-        d[2] = fma(v1, xc.x, d[2]);
-        d[3] = fma(v1, xc.y, d[3]);
+  unsigned parity = 0;
+  for (long long rp = split; rp < npanels; rp += p.row_splits) {
+    const long long row0 = rp * kTM;
+    const int rows = (int)min((long long)kTM, p.m - row0);
+    if (stage_panel_async(x1s, p.x1, row0, rows, D, p.ld1, &bar)) {
+      while (!mbar_try_wait(&bar, parity)) {
       }
-      double u[4], s[4];
-      unsigned need = 0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        u[q] = fma(d[q], p.scale, p.shift);
-        need |= (unsigned)(((unsigned)__double2hiint(u[q]) & 0x7fffffffu) >= p.clamp_word);
-      }
-      if (need) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) u[q] = clamp_exact(u[q], p.lo, p.hi);
-      }
-      eval4<BASIS>(cfs + f * p.T, p.T, u, s);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) prod[q] *= s[q];
+      parity ^= 1u;
+    } else {
+      __syncthreads();
     }
+    for (int rr = 0; rr < kRowsPerWarp; rr += 2) {
+      const int r0 = r_begin + rr;
+      if (r0 >= rows) break;
+      const int r1 = min(r0 + 1, rows - 1);
+      double prod[4] = {1.0, 1.0, 1.0, 1.0};
+      for (int f = 0; f < p.F; ++f) {
+        double d[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k < p.W; ++k) {
+          const int kk = f * p.W + k;
+          const double2 xc = *reinterpret_cast<const double2*>(x2t + kk * kTN + 2 * lane);
+          const double v0 = x1s[r0 * D + kk], v1 = x1s[r1 * D + kk];
+          d[0] = fma(v0, xc.x, d[0]);
+          d[1] = fma(v0, xc.y, d[1]);
+          d[2] = fma(v1, xc.x, d[2]);
+          d[3] = fma(v1, xc.y, d[3]);
+        }
+        double u[4], s[4];
+        unsigned need = 0;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int r = (h == 0) ? r0 : r0 + 1;
-      if (r >= rows) break;
-      double* out = out_ptr(p, row0 + r, col);
-      if (vec_ok) {
-        st_keep2(out, prod[2 * h], prod[2 * h + 1], p.tiled);
-      } else {
-        if (col < p.n) st_stream(out, prod[2 * h]);
-        if (col + 1 < p.n) st_stream(out + 1, prod[2 * h + 1]);
+        for (int q = 0; q < 4; ++q) {
+          u[q] = fma(d[q], p.scale, p.shift);
+          need |= (unsigned)(((unsigned)__double2hiint(u[q]) & 0x7fffffffu) >= p.clamp_word);
+        }
+        if (need) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) u[q] = clamp_exact(u[q], p.lo, p.hi);
+        }
+        eval4<BASIS>(cfs + f * p.T, p.T, u, s);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) prod[q] *= s[q];
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = (h == 0) ? r0 : r0 + 1;
+        if (r >= rows) break;
+        double* out = out_ptr(p, row0 + r, col);
+        if (vec_ok) {
+          st_keep2(out, prod[2 * h], prod[2 * h + 1], p.tiled);
+        } else {
+          if (col < p.n) st_stream(out, prod[2 * h]);
+          if (col + 1 < p.n) st_stream(out + 1, prod[2 * h + 1]);
+        }
       }
     }
+    __syncthreads();   // x1s is restaged for the next panel
   }
 }
 
@@ -502,7 +542,7 @@ static int validate(const mgb_series_desc* d, const void* x1, long long m, long 
 
 template <int W, int TREG>
 static int launch_fast(const SeriesParams& p, long long tiles, cudaStream_t s) {
-  const size_t smem = sizeof(double) * kTM * W;
+  const size_t smem = sizeof(double) * 2 * kTM * W;
   series_gram_fwd_fast<W, TREG><<<(unsigned)tiles, kThreads, smem, s>>>(p);
   return after_launch("series_gram_fwd_fast");
 }
@@ -526,6 +566,16 @@ static int dispatch_fast(const SeriesParams& p, long long tiles, cudaStream_t s,
 
 using namespace mgb;
 
+static int series_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 148;
+  }
+  return sms;
+}
+
 static int series_fwd_impl(const mgb_series_desc* d, const double* x1, long long m, long long ld1, const double* x2,
                            long long n, long long ld2, const double* coef, double* K, long long ldk, int tiled,
                            void* stream) {
@@ -535,14 +585,21 @@ static int series_fwd_impl(const mgb_series_desc* d, const double* x1, long long
   if (tiled && (reinterpret_cast<uintptr_t>(K) & 15u)) return fail(MGB_ERR_ARG, "series_gram_tiled: K must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SeriesParams p{x1, m, ld1, x2, n, ld2, coef, K, ldk, d->n_factors, d->factor_width, d->n_terms,
-                 d->scale, d->shift, d->lo, d->hi, (n + kTN - 1) / kTN, 0u, tiled, (n + 15) / 16};
+                 d->scale, d->shift, d->lo, d->hi, (n + kTN - 1) / kTN, 0u, 1, tiled, (n + 15) / 16};
   if (d->lo < 0.0 && d->hi > 0.0) {
     const double bound = fmin(-d->lo, d->hi);
     unsigned long long bits;
     memcpy(&bits, &bound, sizeof(bits));
     p.clamp_word = (unsigned)(bits >> 32);
   }
-  const long long tiles = p.ncc * ((m + kTM - 1) / kTM);
+  // persistent over row panels: about 8 CTAs per SM in total, each walking a strided set of 128-row panels of
+  // its 64-column chunk with the x2 rows / coefficients resident in registers
+  const long long npanels = (m + kTM - 1) / kTM;
+  long long splits = (8LL * series_sm_count() + p.ncc - 1) / p.ncc;
+  if (splits > npanels) splits = npanels;
+  if (splits < 1) splits = 1;
+  p.row_splits = (int)splits;
+  const long long tiles = p.ncc * splits;
   if (tiles > 0x7fffffffLL) return fail(MGB_ERR_ARG, "series_gram_fwd: too many tiles for one launch");
   if (d->n_factors == 1 && d->basis == MGB_BASIS_MONOMIAL && d->n_terms <= 12) {
     bool handled = false;

@@ -13,7 +13,7 @@ import torch
 
 from . import _ops, _weights
 from .gpytorch_compat import Kernel
-from .kernels_sphere import _NuMixin, _check_batch
+from .kernels_sphere import _NuMixin, _check_batch, _series_on
 
 _SO3_CLIP = 1.0 - 1e-8  # kernels_so.py:325
 
@@ -35,8 +35,7 @@ class _SOSeriesKernel(Kernel):
             raise NotImplementedError("SO(n) for n != 3 is not implemented on the CUDA path yet")
         if x1.shape[-1] != 9 or x2.shape[-1] != 9:
             raise RuntimeError("SO(3) points must be flattened 3x3 rotation matrices (9 coordinates)")
-        spec, coef = self.series()
-        coef = coef.to(x1.device)
+        spec, coef = _series_on(self, x1.device)
         return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1, x2, diag=diag)
 
 

@@ -48,6 +48,25 @@ class _NuMixin:
         self.initialize(raw_nu=self.raw_nu_constraint.inverse_transform(value))
 
 
+def _series_on(kernel, device):
+    """(spec, coef on ``device``).  When no hyper-parameter needs a gradient the pair is cached against the
+    parameters' version counters, so repeated posterior / acquisition calls with fixed hyper-parameters do not
+    recompute the weights on the host nor pay a synchronising host-to-device copy per call."""
+    params = list(kernel.parameters())
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        spec, coef = kernel.series()
+        return spec, coef.to(device)
+    key = (str(device), torch.get_default_dtype(),) + tuple((p._version, p.data_ptr()) for p in params)
+    cached = kernel.__dict__.get("_series_cache")
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    with torch.no_grad():
+        spec, coef = kernel.series()
+        val = (spec, coef.to(device).contiguous())
+    kernel.__dict__["_series_cache"] = (key, val)
+    return val
+
+
 def _check_batch(kernel):
     if len(kernel.batch_shape) != 0:
         raise NotImplementedError("batched hyper-parameters (batch_shape != []) are not supported by the CUDA path")
@@ -75,10 +94,9 @@ class _SphereSeriesKernel(Kernel):
 
     def forward(self, x1, x2, diag=False, **params):
         _check_batch(self)
-        spec, coef = self.series()
         if x1.shape[-1] != self.dim + 1 or x2.shape[-1] != self.dim + 1:
             raise RuntimeError("S^%d points must have %d coordinates" % (self.dim, self.dim + 1))
-        coef = coef.to(x1.device)
+        spec, coef = _series_on(self, x1.device)
         return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1, x2, diag=diag)
 
 
@@ -135,10 +153,9 @@ class _CircleSeriesKernel(Kernel):
 
     def forward(self, x1, x2, diag=False, **params):
         _check_batch(self)
-        spec, coef = self.series()
         if x1.shape[-1] != 2 or x2.shape[-1] != 2:
             raise RuntimeError("S^1 points must have 2 coordinates")
-        coef = coef.to(x1.device)
+        spec, coef = _series_on(self, x1.device)
         return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1, x2, diag=diag)
 
 

@@ -13,7 +13,7 @@ import torch
 from . import _lib, _ops, _weights
 from .gpytorch_compat import Kernel, ProductKernel
 from .kernels_sphere import (CircleRiemannianGaussianKernel, CircleRiemannianIntegratedMaternKernel, _CLAMP,
-                             _check_batch)
+                             _check_batch, _series_on)
 
 
 class _TorusKernel(Kernel):
@@ -36,8 +36,7 @@ class _TorusKernel(Kernel):
         x1c, x2c = self._to_circles(x1), self._to_circles(x2)
         if x1c.shape[-1] != 2 * self.dim or x2c.shape[-1] != 2 * self.dim:
             raise RuntimeError("T^%d points must be %d angles or %d circle coordinates" % (self.dim, self.dim, 2 * self.dim))
-        spec, coef = self.series()
-        coef = coef.to(x1c.device)
+        spec, coef = _series_on(self, x1c.device)
         return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1c, x2c, diag=diag)
 
 

@@ -282,3 +282,57 @@ def test_large_gram_properties():
     ref = R.so3_matern(base[idx[rows]], base[:300], 2.5, 0.5)
     assert rel_err(big[rows.to(DEV)][:, :300], ref) < TOL
     assert torch.isfinite(big).all()
+
+
+def test_second_order_input_gradient_matches_oracle():
+    """Trust-region Hessian-vector products differentiate the input gradient again
+    (pymanopt_addons/tools/autodiff/_pytorch.py:92-116): d/dx1 [ (d/dx1 sum(K*G)) . v ]."""
+    from materngabo_b200 import kernels_sphere as ks
+    from oracle import restated as R
+
+    torch.manual_seed(8)
+    x1 = torch.nn.functional.normalize(torch.randn(6, 4), dim=-1)
+    x2 = torch.nn.functional.normalize(torch.randn(9, 4), dim=-1)
+    G, v = torch.randn(6, 9), torch.randn(6, 4)
+    k = ks.SphereRiemannianMaternKernel(dim=3, nu=2.5)
+    k.lengthscale = 0.5
+
+    def hvp(fn, a, b, g, vec):
+        a = a.clone().requires_grad_(True)
+        out = fn(a, b)
+        (ga,) = torch.autograd.grad((out * g).sum(), [a], create_graph=True)
+        (h,) = torch.autograd.grad((ga * vec).sum(), [a])
+        return ga.detach(), h
+
+    g_ref, h_ref = hvp(lambda a, b: R.sphere_matern(a, b, 3, 2.5, 0.5), x1, x2, G, v)
+    g_dev, h_dev = hvp(lambda a, b: k.forward(a, b), x1.to(DEV), x2.to(DEV), G.to(DEV), v.to(DEV))
+    assert rel_err(g_dev, g_ref) < 1e-9
+    assert rel_err(h_dev, h_ref) < 1e-8
+
+
+def test_gradient_through_scaled_sum_of_kernels():
+    """Autograd composition as gpytorch uses it: ScaleKernel(base)(X) + noise, scalar loss, hyper-gradients."""
+    from materngabo_b200 import kernels_sphere as ks
+    from materngabo_b200.gpytorch_compat import ScaleKernel
+    from oracle import restated as R
+
+    torch.manual_seed(9)
+    x = torch.nn.functional.normalize(torch.randn(50, 4), dim=-1)
+    y = torch.sin(2 * x[:, 0])
+    base = ks.SphereRiemannianMaternKernel(dim=3, nu=2.5)
+    sk = ScaleKernel(base)
+    sk.outputscale = 1.7
+
+    def nll(kmat, yv):
+        L = torch.linalg.cholesky(kmat + 1e-2 * torch.eye(kmat.shape[0], device=kmat.device))
+        a = torch.cholesky_solve(yv.unsqueeze(-1), L).squeeze(-1)
+        return 0.5 * (yv * a).sum() + torch.log(torch.diagonal(L)).sum()
+
+    loss = nll(sk(x.to(DEV)), y.to(DEV))
+    grads = torch.autograd.grad(loss, [base.raw_lengthscale, sk.raw_outputscale])
+    raw_ls = base.raw_lengthscale.detach().clone().requires_grad_(True)
+    raw_os = sk.raw_outputscale.detach().clone().requires_grad_(True)
+    kref = torch.nn.functional.softplus(raw_os) * R.sphere_matern(x, x, 3, 2.5, torch.nn.functional.softplus(raw_ls))
+    ref = torch.autograd.grad(nll(kref, y), [raw_ls, raw_os])
+    assert abs(float(loss) - float(nll(kref, y))) < 1e-9
+    assert rel_err(grads[0], ref[0]) < 1e-8 and rel_err(grads[1].reshape(-1), ref[1].reshape(-1)) < 1e-8

@@ -3,6 +3,8 @@ import ctypes as C
 import json
 import time
 
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 torch.set_default_dtype(torch.float64)
