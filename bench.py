@@ -43,8 +43,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="posterior-s10")
-    ap.add_argument("--m", type=int, default=None, help="override candidate / row count")
-    ap.add_argument("--n", type=int, default=None, help="override training / column count")
+    ap.add_argument("--cands", dest="m", type=int, default=None, help="override candidate / row count")
+    ap.add_argument("--train", dest="n", type=int, default=None, help="override training / column count")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

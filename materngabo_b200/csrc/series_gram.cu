@@ -17,6 +17,7 @@
 //     (monomial/Horner, T <= 12) or D + 2T + 3 (Chebyshev three-term recurrence).
 #include "mgb_common.cuh"
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 
 namespace mgb {
@@ -239,6 +240,140 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
     }
   }
     __syncthreads();     // everyone is done with x1s[buf]; plain-load staging of the next panel is visible
+    bulk_cur = bulk_next;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-pipe variant of the fast path: the W-wide inner products run as FP64 DMMA m8n8k4 fragments (x2 columns
+// resident in registers as B fragments, x1 rows fetched from the shared-memory panel as A fragments, k padded
+// with zeros to a multiple of 4), which moves W of the W + T + 1 FMAs per entry off the FP64 DFMA pipe: DMMA
+// issues on the tensor pipe and overlaps the Horner chains.  Warp w owns rows [16w, 16w+16) of the panel as two
+// 8-row fragments x eight 8-column fragments; a lane ends up with columns 8b + 2(lane%4), +1 of row lane/4:
+// 16-byte stores again.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int W, int TREG>
+__global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_mma(SeriesParams p) {
+  constexpr int KS = (W + 3) / 4;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+
+  const long long cc = blockIdx.x % p.ncc;
+  const int split = (int)(blockIdx.x / p.ncc);
+  const long long npanels = (p.m + kTM - 1) / kTM;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int frow = lane >> 2, fk = lane & 3;
+
+  double c[TREG];
+#pragma unroll
+  for (int k = 0; k < TREG; ++k) c[k] = (k < p.T) ? __ldg(p.coef + k) : 0.0;
+
+  // B fragments: element (k = 4 s + fk, n = frow) of column fragment b is scale * x2[col0 + 8 b + frow][k]
+  const long long col0 = cc * kTN;
+  double bf[8][KS];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const long long cj = col0 + 8 * b + frow;
+#pragma unroll
+    for (int sidx = 0; sidx < KS; ++sidx) {
+      const int k = 4 * sidx + fk;
+      bf[b][sidx] = (cj < p.n && k < W) ? p.scale * __ldg(p.x2 + cj * p.ld2 + k) : 0.0;
+    }
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const bool aligned = p.tiled || (((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0));
+  const unsigned thr = p.clamp_word;
+
+  long long rp = split;
+  if (rp >= npanels) return;
+  unsigned parity = 0;
+  bool bulk_cur = stage_panel_async(smem, p.x1, rp * kTM, (int)min((long long)kTM, p.m - rp * kTM), W, p.ld1, &bars[0]);
+  for (int it = 0; rp < npanels; rp += p.row_splits, ++it) {
+    const int buf = it & 1;
+    const double* x1s = smem + buf * (kTM * W);
+    const long long row0 = rp * kTM;
+    const int rows = (int)min((long long)kTM, p.m - row0);
+    const long long rp_next = rp + p.row_splits;
+    bool bulk_next = false;
+    if (rp_next < npanels)
+      bulk_next = stage_panel_async(smem + (buf ^ 1) * (kTM * W), p.x1, rp_next * kTM,
+                                    (int)min((long long)kTM, p.m - rp_next * kTM), W, p.ld1, &bars[buf ^ 1]);
+    if (bulk_cur) {
+      while (!mbar_try_wait(&bars[buf], (parity >> buf) & 1u)) {
+      }
+      parity ^= 1u << buf;
+    } else if (it == 0) {
+      __syncthreads();
+    }
+#pragma unroll 1
+    for (int a = 0; a < 2; ++a) {
+      const int r = warp * kRowsPerWarp + 8 * a + frow;    // this lane's row within the panel
+      if (warp * kRowsPerWarp + 8 * a >= rows) break;
+      double af[KS];
+#pragma unroll
+      for (int sidx = 0; sidx < KS; ++sidx) {
+        const int k = 4 * sidx + fk;
+        af[sidx] = (k < W) ? x1s[r * W + k] : 0.0;
+      }
+      double u0[8], u1[8];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        u0[b] = p.shift;
+        u1[b] = p.shift;
+#pragma unroll
+        for (int sidx = 0; sidx < KS; ++sidx) dmma884(u0[b], u1[b], af[sidx], bf[b][sidx]);
+      }
+      unsigned need = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        need |= (unsigned)(((unsigned)__double2hiint(u0[b]) & 0x7fffffffu) >= thr);
+        need |= (unsigned)(((unsigned)__double2hiint(u1[b]) & 0x7fffffffu) >= thr);
+      }
+      if (need) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          u0[b] = clamp_exact(u0[b], p.lo, p.hi);
+          u1[b] = clamp_exact(u1[b], p.lo, p.hi);
+        }
+      }
+      double p0[8], p1[8];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) p0[b] = p1[b] = c[TREG - 1];
+#pragma unroll
+      for (int k = TREG - 2; k >= 0; --k) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          p0[b] = fma(p0[b], u0[b], c[k]);
+          p1[b] = fma(p1[b], u1[b], c[k]);
+        }
+      }
+      if (r < rows) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const long long col = col0 + 8 * b + 2 * fk;
+          double* out = out_ptr(p, row0 + r, col);
+          if (aligned && col + 1 < p.n) {
+            st_keep2(out, p0[b], p1[b], p.tiled);
+          } else {
+            if (col < p.n) st_stream(out, p0[b]);
+            if (col + 1 < p.n) st_stream(out + 1, p1[b]);
+          }
+        }
+      }
+    }
+    __syncthreads();
     bulk_cur = bulk_next;
   }
 }
@@ -547,9 +682,37 @@ static int launch_fast(const SeriesParams& p, long long tiles, cudaStream_t s) {
   return after_launch("series_gram_fwd_fast");
 }
 
+template <int W, int TREG>
+static int launch_mma(const SeriesParams& p, long long tiles, cudaStream_t s) {
+  const size_t smem = sizeof(double) * 2 * kTM * W;
+  series_gram_fwd_mma<W, TREG><<<(unsigned)tiles, kThreads, smem, s>>>(p);
+  return after_launch("series_gram_fwd_mma");
+}
+
+// 0 = DFMA inner products, 1 = DMMA inner products.  Default: DMMA for the wide rows (S^10, SO(3)), where the
+// FP64 pipe, not HBM, bounds the DFMA variant (profiles/).  MGB_SERIES_PATH=dfma|mma overrides (tuning knob).
+static int series_path(int W) {
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("MGB_SERIES_PATH");
+    forced = (e == nullptr) ? -1 : (strcmp(e, "mma") == 0 ? 1 : (strcmp(e, "dfma") == 0 ? 0 : -1));
+  }
+  if (forced >= 0) return forced;
+  return W >= 8 ? 1 : 0;
+}
+
 template <int TREG>
 static int dispatch_fast(const SeriesParams& p, long long tiles, cudaStream_t s, bool* handled) {
   *handled = true;
+  if (series_path(p.W) == 1) {
+    switch (p.W) {
+      case 3: return launch_mma<3, TREG>(p, tiles, s);
+      case 4: return launch_mma<4, TREG>(p, tiles, s);
+      case 9: return launch_mma<9, TREG>(p, tiles, s);
+      case 11: return launch_mma<11, TREG>(p, tiles, s);
+      default: break;
+    }
+  }
   switch (p.W) {
     case 2: return launch_fast<2, TREG>(p, tiles, s);
     case 3: return launch_fast<3, TREG>(p, tiles, s);

@@ -149,6 +149,29 @@ class ExactGPPosterior:
         return mean, var
 
 
+    # ---- differentiable path for the trust-region inner loop -------------------------------------
+    def posterior_autograd(self, x: torch.Tensor):
+        """Mean / variance for a SMALL block of candidates with autograd to ``x`` (first and, for single-factor
+        kernels, second order).  This is what the reference's pymanopt cost / egrad / ehess closures differentiate
+        (manifold_optimization/manifold_optimize.py:184-197; pymanopt_addons/tools/autodiff/_pytorch.py:89-116):
+        the kernel row goes through the CUDA series op (custom backward + double backward), the N x N algebra
+        through torch.  Use ``posterior`` (fused, no autograd) for scoring large candidate sets."""
+        if self._packed is None:
+            raise RuntimeError("call fit() (or load_state) first")
+        _lib.require_cuda_f64(x)
+        squeeze = x.dim() == 3
+        if squeeze:
+            if x.shape[-2] != 1:
+                raise NotImplementedError("q > 1 joint posteriors are not provided by the analytic acquisition path")
+            x = x.squeeze(-2)
+        xp = self._prepared(x)
+        ks = _ops.series_gram(self.spec, xp, self.train_prepared, self.coef)     # already scaled by outputscale
+        mean = self.mean_const + ks @ self.alpha
+        v = ks @ self.rinv.t()                                                    # (L^-1 k*)^T, rinv is lower triangular
+        var = self.kss_value - (v * v).sum(-1)
+        return mean, var
+
+
 class ExpectedImprovement:
     """Analytic EI with botorch's call convention: ``acq(X)`` with ``X`` of shape ``b x 1 x D`` -> ``b``."""
 
@@ -158,7 +181,10 @@ class ExpectedImprovement:
         self.maximize = maximize
 
     def __call__(self, x):
-        mean, var = self.model.posterior(x)
+        if torch.is_grad_enabled() and x.requires_grad:
+            mean, var = self.model.posterior_autograd(x)     # trust-region inner loop: value + gradient (+ HVP)
+        else:
+            mean, var = self.model.posterior(x)              # scoring: fused kernels, no autograd
         return expected_improvement(mean, var, self.best_f, self.maximize)
 
 

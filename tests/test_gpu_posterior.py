@@ -144,3 +144,39 @@ def test_bad_arguments_return_errors():
     assert rc == 1 and b"n_terms" in lib.mgb_last_error()
     with pytest.raises(ValueError):
         _lib.check(rc, "mgb_series_gram_fwd")
+
+
+def test_acquisition_gradient_and_hessian_vector_product():
+    """the trust-region inner loop differentiates -EI(x) once (egrad) and twice (ehess)
+    with respect to ONE candidate in the b x 1 x D layout; compare with torch autograd through the oracle on CPU."""
+    from materngabo_b200.posterior import ExpectedImprovement
+    from oracle import restated as R
+
+    gp, xc, _, (xt, y, _) = _setup(3, 60, 8, seed=21, outputscale=1.0, noise=1e-2, mean_const=0.0)
+    best = float(y.min())
+    acq = ExpectedImprovement(gp, best_f=best, maximize=False)
+    vec = torch.randn(5, 1, 4, generator=torch.Generator().manual_seed(3))
+
+    def cost_dev(x):
+        return -acq(x).sum()
+
+    def cost_ref(x):
+        kfn = lambda a, b: R.sphere_matern(a, b, 3, 2.5, 0.5)  # noqa: E731
+        L, alpha = R.gp_fit(kfn, xt, y, 1.0, 1e-2, 0.0)
+        xs = x.squeeze(-2)
+        ks = kfn(xs, xt)
+        mean = ks @ alpha
+        v = torch.linalg.solve_triangular(L, ks.t(), upper=False)
+        var = kfn(xs[:1], xs[:1]).reshape(()).detach() - (v * v).sum(0)
+        return -R.expected_improvement(mean, var, best, maximize=False).sum()
+
+    outs = []
+    for fn, dev in ((cost_dev, DEV), (cost_ref, "cpu")):
+        x = xc[:5].unsqueeze(-2).to(dev).clone().requires_grad_(True)
+        c = fn(x)
+        (g,) = torch.autograd.grad(c, [x], create_graph=True)
+        (h,) = torch.autograd.grad((g * vec.to(dev)).sum(), [x])
+        outs.append((float(c), g.detach().cpu(), h.cpu()))
+    assert abs(outs[0][0] - outs[1][0]) < 1e-9
+    assert rel_err(outs[0][1], outs[1][1]) < 1e-8
+    assert rel_err(outs[0][2], outs[1][2]) < 1e-7

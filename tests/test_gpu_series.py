@@ -320,7 +320,7 @@ def test_gradient_through_scaled_sum_of_kernels():
     x = torch.nn.functional.normalize(torch.randn(50, 4), dim=-1)
     y = torch.sin(2 * x[:, 0])
     base = ks.SphereRiemannianMaternKernel(dim=3, nu=2.5)
-    sk = ScaleKernel(base)
+    sk = ScaleKernel(base).to(DEV)          # as SingleTaskGP.to(train_X) does: hyper-parameters live on the GPU
     sk.outputscale = 1.7
 
     def nll(kmat, yv):
@@ -330,8 +330,8 @@ def test_gradient_through_scaled_sum_of_kernels():
 
     loss = nll(sk(x.to(DEV)), y.to(DEV))
     grads = torch.autograd.grad(loss, [base.raw_lengthscale, sk.raw_outputscale])
-    raw_ls = base.raw_lengthscale.detach().clone().requires_grad_(True)
-    raw_os = sk.raw_outputscale.detach().clone().requires_grad_(True)
+    raw_ls = base.raw_lengthscale.detach().cpu().clone().requires_grad_(True)
+    raw_os = sk.raw_outputscale.detach().cpu().clone().requires_grad_(True)
     kref = torch.nn.functional.softplus(raw_os) * R.sphere_matern(x, x, 3, 2.5, torch.nn.functional.softplus(raw_ls))
     ref = torch.autograd.grad(nll(kref, y), [raw_ls, raw_os])
     assert abs(float(loss) - float(nll(kref, y))) < 1e-9
