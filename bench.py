@@ -495,9 +495,18 @@ def cpu_posterior_state(n):
 _CPU_FIT = {}
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core."""
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        torch.set_num_threads(os.cpu_count() or 1)
+
+
 def cpu_posterior_rate(n, sample, chunk=512):
     """candidates/s of the oracle port (reference algorithm, torch CPU ops, all host threads).  The fit
     (Cholesky of n x n) is done once outside the timed region, like rank 0's fit in our arm."""
+    use_all_host_threads()
     R, kfn, xt, y = cpu_posterior_state(n)
     if n not in _CPU_FIT:
         _CPU_FIT[n] = R.gp_fit(kfn, xt, y, outputscale=1.0, noise=1e-2, mean_const=0.0)
@@ -517,6 +526,7 @@ def run_reference(args, rank, world):
     torch.set_default_dtype(F64)
     n = args.n or 5000
     sample = 1024
+    use_all_host_threads()
     cores = torch.get_num_threads()
     for _ in range(min(args.warmup, 1)):
         cpu_posterior_rate(n, 256)

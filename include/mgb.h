@@ -109,6 +109,15 @@ int mgb_hyperbolic_gram_bwd_coef(int dim, const double* x1, long long m, long lo
 int mgb_hyperbolic_heat_nodes(int dim, const double* dist, long long count, const double* tval, int Pt,
                               double s0, double ds, int Ps, double* out, void* stream);
 
+/* Euclidean factor of the SPD product kernels (kernel_utils/kernels_euclidean.py:82-89,162-207):
+ *   K_ij = sum_a tcoef[a] exp(-|x1_i - x2_j|^2 / (4 tval[a])), rows `width` wide. */
+int mgb_euclidean_gram_fwd(const double* x1, long long m, long long ld1, const double* x2, long long n,
+                           long long ld2, int width, const double* tval, const double* tcoef, int Pt,
+                           double* K, long long ldk, void* stream);
+int mgb_euclidean_gram_bwd_coef(const double* x1, long long m, long long ld1, const double* x2, long long n,
+                                long long ld2, int width, const double* tval, int Pt, const double* G,
+                                long long ldg, double* gtcoef, void* stream);
+
 /* SPD(2) in Mandel coordinates (rows 3 wide: s11, s22, sqrt2*s12)
  *   (Riemannian_utils/spd_utils_torch.py:336-371; kernel_utils/kernels_spd.py:200-289 and :65-136)
  *   H1 >= H2 = log singular values of A_i B_j^{-1}; A, B = the matrices (use_cholesky = 0, Matern :230-243)

@@ -42,6 +42,8 @@ PROTOTYPES = {
     "mgb_hyperbolic_gram_fwd": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _I, _D, _D, _I, _P, _LL, _P]),
     "mgb_hyperbolic_gram_bwd_coef": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _I, _D, _D, _I, _P, _LL, _P, _P]),
     "mgb_hyperbolic_heat_nodes": (_I, [_I, _P, _LL, _P, _I, _D, _D, _I, _P, _P]),
+    "mgb_euclidean_gram_fwd": (_I, [_P, _LL, _LL, _P, _LL, _LL, _I, _P, _P, _I, _P, _LL, _P]),
+    "mgb_euclidean_gram_bwd_coef": (_I, [_P, _LL, _LL, _P, _LL, _LL, _I, _P, _I, _P, _LL, _P, _P]),
     "mgb_spd2_gram_fwd": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P, _I, _P, _P, _I, _P, _LL, _P]),
     "mgb_spd2_gram_bwd_coef": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _I, _P, _P, _I, _P, _LL, _P, _P]),
     "mgb_posterior_pack_bytes": (_LL, [_LL]),

@@ -233,6 +233,46 @@ def hyperbolic_heat_nodes(dim, dist, tval, s0, ds, ps):
     return out
 
 
+class EuclideanGram(torch.autograd.Function):
+    """K = sum_a tcoef[a] exp(-|x1_i - x2_j|^2 / (4 tval[a])); differentiable with respect to tcoef."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, tval, tcoef):
+        lib = _lib.load()
+        m, n = x1.shape[0], x2.shape[0]
+        k = torch.empty((m, n), dtype=F64, device=x1.device)
+        with torch.cuda.device(x1.device):
+            rc = lib.mgb_euclidean_gram_fwd(_lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0), x1.shape[1],
+                                            _lib.ptr(tval), _lib.ptr(tcoef), tval.shape[0], _lib.ptr(k), max(n, 1),
+                                            _lib.stream_ptr(x1.device))
+        _lib.check(rc, "mgb_euclidean_gram_fwd")
+        ctx.save_for_backward(x1, x2, tval)
+        return k
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            raise NotImplementedError("input gradients of the Euclidean integrated Matern kernel are not implemented yet")
+        if not ctx.needs_input_grad[3]:
+            return None, None, None, None
+        lib = _lib.load()
+        x1, x2, tval = ctx.saved_tensors
+        g = g.contiguous()
+        out = torch.zeros_like(tval)
+        with torch.cuda.device(x1.device):
+            rc = lib.mgb_euclidean_gram_bwd_coef(_lib.ptr(x1), x1.shape[0], x1.stride(0), _lib.ptr(x2), x2.shape[0],
+                                                 x2.stride(0), x1.shape[1], _lib.ptr(tval), tval.shape[0], _lib.ptr(g),
+                                                 g.stride(0), _lib.ptr(out), _lib.stream_ptr(x1.device))
+        _lib.check(rc, "mgb_euclidean_gram_bwd_coef")
+        return None, None, None, out
+
+
+def euclidean_gram(x1, x2, tval, tcoef):
+    _lib.require_cuda_f64(x1, x2, tval, tcoef)
+    return EuclideanGram.apply(_c2d(x1), _c2d(x2), tval.contiguous(), tcoef.contiguous())
+
+
 class Spd2Gram(torch.autograd.Function):
     @staticmethod
     def forward(ctx, use_chol, x1, x2, tcoef, rscale, bscale, bval, bw):

@@ -40,6 +40,7 @@ __device__ __forceinline__ double lorentz_dist(const double* a, const double* b,
 
 struct HypParams {
   int dim, mode;
+  int geom, width;   // geom 1: Euclidean rows of `width` doubles, heat(d, t) = exp(-|x1 - x2|^2 / (4 t))
   const double* x1; long long m, ld1;
   const double* x2; long long n, ld2;
   const double* dist; long long count;        // Q_NODES
@@ -52,7 +53,7 @@ struct HypParams {
 
 __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
   extern __shared__ __align__(16) double sm[];
-  // layout: E [Ps*Pt] | cm1 [Ps] | sh [Ps] | wq [Ps] | bk [Ps] | per-warp qw [QWARPS][Ps]
+  // layout: E [Ps*Pt] | cm1 [Ps] | sh [Ps] | wq [Ps] | per-warp qw [2 * QWARPS][Ps] (two entries in flight)
   double* Es = sm;
   const int nE = (p.dim == 2) ? p.Ps * p.Pt : 0;
   const int nP = (p.dim == 2) ? p.Ps : 0;
@@ -90,73 +91,126 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
     gacc[q] = 0.0;
   }
 
-  for (long long e = (long long)blockIdx.x * QWARPS + warp; e < total; e += wstride) {
-    double d;
-    long long i = 0, j = 0;
-    if (p.mode == Q_NODES) {
-      d = p.dist[e];
-    } else {
-      i = e / p.n;
-      j = e - i * p.n;
-      d = lorentz_dist(p.x1 + i * p.ld1, p.x2 + j * p.ld2, p.dim);
-    }
-    double h[QMAXT / 32];
-    if (p.dim == 2) {
-      const double chd = cosh(d), shd = sinh(d);
-      __syncwarp();
-      for (int k = lane; k < p.Ps; k += 32) {
-        const double bk = p.s0 + k * p.ds;
-        const double den = fma(chd, cm1[k], shd * sh[k]);
-        qw[k] = wq[k] * (bk + d) * rsqrt(den);
+  // Two entries per warp iteration: the pair-independent table values E[k][a] are fetched once and used for both.
+  double* qw0 = qw;
+  double* qw1 = qw_all + (QWARPS + warp) * nP;
+  for (long long e0 = (long long)blockIdx.x * QWARPS + warp; e0 < total; e0 += 2 * wstride) {
+    const long long e1 = e0 + wstride;
+    const bool has1 = e1 < total;
+    long long ei[2] = {e0, has1 ? e1 : e0};
+    long long ii[2] = {0, 0}, jj[2] = {0, 0};
+    double dd[2], dsq[2];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      dsq[s2] = 0.0;
+      if (p.mode == Q_NODES) {
+        dd[s2] = p.dist[ei[s2]];
+      } else {
+        ii[s2] = ei[s2] / p.n;
+        jj[s2] = ei[s2] - ii[s2] * p.n;
+        if (p.geom == 1) {
+          const double* xa = p.x1 + ii[s2] * p.ld1;
+          const double* xb = p.x2 + jj[s2] * p.ld2;
+          for (int k = 0; k < p.width; ++k) {
+            const double df = xa[k] - xb[k];
+            dsq[s2] = fma(df, df, dsq[s2]);
+          }
+          dd[s2] = 0.0;
+        } else {
+          dd[s2] = lorentz_dist(p.x1 + ii[s2] * p.ld1, p.x2 + jj[s2] * p.ld2, p.dim);
+        }
       }
+      if (p.geom != 1) dsq[s2] = dd[s2] * dd[s2];
+    }
+    double h[2][QMAXT / 32];
+    if (p.dim == 2 && p.geom != 1) {
       __syncwarp();
 #pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const double chd = cosh(dd[s2]), shd = sinh(dd[s2]);
+        double* dst = s2 ? qw1 : qw0;
+        for (int k = lane; k < p.Ps; k += 32) {
+          const double bk = p.s0 + k * p.ds;
+          const double den = fma(chd, cm1[k], shd * sh[k]);
+          dst[k] = wq[k] * (bk + dd[s2]) * rsqrt(den);
+        }
+      }
+      __syncwarp();
+      double g[2][QMAXT / 32], r[2][QMAXT / 32], acc[2][QMAXT / 32], pw[2][QMAXT / 32], i2t[QMAXT / 32];
+#pragma unroll
       for (int q = 0; q < QMAXT / 32; ++q) {
-        const int a = lane + 32 * q;
-        h[q] = 0.0;
-        if (a < p.Pt) {
-          const double inv2t = 0.5 / tv[q];
-          const double g = exp(-(d * d + 2.0 * p.s0 * d) * 0.5 * inv2t);
-          const double r = exp(-p.ds * d * inv2t);
-          double acc = 0.0, pw = 1.0;
-          for (int k0 = 0; k0 < p.Ps; k0 += 16) {
-            if (k0 > 0) pw = exp(-(k0 * p.ds) * d * inv2t);  // re-anchor the running power
-            const int k1 = min(k0 + 16, p.Ps);
-            for (int k = k0; k < k1; ++k) {
-              acc = fma(qw[k] * Es[k * p.Pt + a], pw, acc);
-              pw *= r;
+        i2t[q] = 0.5 / tv[q];
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          g[s2][q] = exp(-(dsq[s2] + 2.0 * p.s0 * dd[s2]) * 0.5 * i2t[q]);
+          r[s2][q] = exp(-p.ds * dd[s2] * i2t[q]);
+          acc[s2][q] = 0.0;
+          pw[s2][q] = 1.0;
+        }
+      }
+      const int nq = (p.Pt + 31) / 32;
+      for (int k0 = 0; k0 < p.Ps; k0 += 16) {
+        if (k0 > 0) {   // re-anchor the running powers with an exact exponential
+#pragma unroll
+          for (int q = 0; q < QMAXT / 32; ++q)
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2)
+              if (q < nq) pw[s2][q] = exp(-(k0 * p.ds) * dd[s2] * i2t[q]);
+        }
+        const int k1 = min(k0 + 16, p.Ps);
+        for (int k = k0; k < k1; ++k) {
+          const double w0 = qw0[k], w1 = qw1[k];
+#pragma unroll
+          for (int q = 0; q < QMAXT / 32; ++q) {
+            if (q < nq) {
+              const int a = lane + 32 * q;
+              const double ev = (a < p.Pt) ? Es[k * p.Pt + a] : 0.0;
+              acc[0][q] = fma(w0 * ev, pw[0][q], acc[0][q]);
+              acc[1][q] = fma(w1 * ev, pw[1][q], acc[1][q]);
+              pw[0][q] *= r[0][q];
+              pw[1][q] *= r[1][q];
             }
           }
-          h[q] = g * acc;
         }
       }
+#pragma unroll
+      for (int q = 0; q < QMAXT / 32; ++q)
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) h[s2][q] = (lane + 32 * q < p.Pt) ? g[s2][q] * acc[s2][q] : 0.0;
     } else {
 #pragma unroll
-      for (int q = 0; q < QMAXT / 32; ++q) {
-        const int a = lane + 32 * q;
-        h[q] = 0.0;
-        if (a < p.Pt) {
-          double v = exp(-(d * d) / (4.0 * tv[q]));
-          if (p.dim == 3) v = v * (d + 1e-8) / sinh(d + 1e-8);
-          h[q] = v;
+      for (int s2 = 0; s2 < 2; ++s2) {
+#pragma unroll
+        for (int q = 0; q < QMAXT / 32; ++q) {
+          const int a = lane + 32 * q;
+          h[s2][q] = 0.0;
+          if (a < p.Pt) {
+            double v = exp(-dsq[s2] / (4.0 * tv[q]));
+            if (p.dim == 3 && p.geom != 1) v = v * (dd[s2] + 1e-8) / sinh(dd[s2] + 1e-8);
+            h[s2][q] = v;
+          }
         }
       }
     }
-    if (p.mode == Q_FWD) {
-      double s = 0.0;
 #pragma unroll
-      for (int q = 0; q < QMAXT / 32; ++q) s = fma(tc[q], h[q], s);
-      s = warp_sum(s);
-      if (lane == 0) st_stream(p.K + i * p.ldk + j, s);
-    } else if (p.mode == Q_BWD_COEF) {
-      const double g = p.G[i * p.ldg + j];
+    for (int s2 = 0; s2 < 2; ++s2) {
+      if (s2 == 1 && !has1) break;
+      if (p.mode == Q_FWD) {
+        double sum = 0.0;
 #pragma unroll
-      for (int q = 0; q < QMAXT / 32; ++q) gacc[q] = fma(g, h[q], gacc[q]);
-    } else {
+        for (int q = 0; q < QMAXT / 32; ++q) sum = fma(tc[q], h[s2][q], sum);
+        sum = warp_sum(sum);
+        if (lane == 0) st_stream(p.K + ii[s2] * p.ldk + jj[s2], sum);
+      } else if (p.mode == Q_BWD_COEF) {
+        const double gg = p.G[ii[s2] * p.ldg + jj[s2]];
 #pragma unroll
-      for (int q = 0; q < QMAXT / 32; ++q) {
-        const int a = lane + 32 * q;
-        if (a < p.Pt) p.out[e * p.Pt + a] = h[q];
+        for (int q = 0; q < QMAXT / 32; ++q) gacc[q] = fma(gg, h[s2][q], gacc[q]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < QMAXT / 32; ++q) {
+          const int a = lane + 32 * q;
+          if (a < p.Pt) p.out[ei[s2] * p.Pt + a] = h[s2][q];
+        }
       }
     }
   }
@@ -311,7 +365,7 @@ static int hyp_launch(HypParams p, cudaStream_t s) {
   size_t smem = 0;
   if (p.dim == 2) {
     const size_t nE = (size_t)p.Ps * p.Pt;
-    smem = sizeof(double) * (nE + 3 * (size_t)p.Ps + (size_t)QWARPS * p.Ps);
+    smem = sizeof(double) * (nE + 3 * (size_t)p.Ps + (size_t)2 * QWARPS * p.Ps);
     if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "hyperbolic: Ps*Pt table exceeds shared memory");
     MGB_TRY(check_cuda(cudaFuncSetAttribute(hyp_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "cudaFuncSetAttribute"));
@@ -370,6 +424,28 @@ extern "C" int mgb_hyperbolic_heat_nodes(int dim, const double* dist, long long 
   HypParams p{};
   p.dim = dim; p.mode = Q_NODES; p.dist = dist; p.count = count; p.tval = tval; p.Pt = Pt;
   p.s0 = s0; p.ds = ds; p.Ps = Ps; p.out = out;
+  return hyp_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mgb_euclidean_gram_fwd(const double* x1, long long m, long long ld1, const double* x2, long long n,
+                                      long long ld2, int width, const double* tval, const double* tcoef, int Pt,
+                                      double* K, long long ldk, void* stream) {
+  if (!x1 || !x2 || !tval || !tcoef || !K) return fail(MGB_ERR_ARG, "euclidean_gram_fwd: null pointer");
+  if (m < 0 || n < 0 || width < 1 || ld1 < width || ld2 < width || ldk < n) return fail(MGB_ERR_ARG, "euclidean_gram_fwd: bad sizes");
+  HypParams p{};
+  p.dim = 1; p.geom = 1; p.width = width; p.mode = Q_FWD; p.x1 = x1; p.m = m; p.ld1 = ld1; p.x2 = x2; p.n = n; p.ld2 = ld2;
+  p.tval = tval; p.tcoef = tcoef; p.Pt = Pt; p.K = K; p.ldk = ldk;
+  return hyp_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mgb_euclidean_gram_bwd_coef(const double* x1, long long m, long long ld1, const double* x2, long long n,
+                                           long long ld2, int width, const double* tval, int Pt, const double* G,
+                                           long long ldg, double* gtcoef, void* stream) {
+  if (!x1 || !x2 || !tval || !G || !gtcoef) return fail(MGB_ERR_ARG, "euclidean_gram_bwd_coef: null pointer");
+  if (m < 0 || n < 0 || width < 1 || ld1 < width || ld2 < width || ldg < n) return fail(MGB_ERR_ARG, "euclidean_gram_bwd_coef: bad sizes");
+  HypParams p{};
+  p.dim = 1; p.geom = 1; p.width = width; p.mode = Q_BWD_COEF; p.x1 = x1; p.m = m; p.ld1 = ld1; p.x2 = x2; p.n = n; p.ld2 = ld2;
+  p.tval = tval; p.Pt = Pt; p.G = G; p.ldg = ldg; p.out = gtcoef;
   return hyp_launch(p, static_cast<cudaStream_t>(stream));
 }
 

@@ -223,6 +223,18 @@ class ScaleKernel(Kernel):
         return k * s
 
 
+class RBFKernel(Kernel):
+    """exp(-|x - y|^2 / (2 l^2)): gpytorch's own RBF kernel, used by the reference only as the Euclidean factor of
+    the SPD product heat kernels (kernel_utils/kernels_spd.py:346,606).  Plain torch ops on the inputs' device."""
+
+    has_lengthscale = True
+
+    def forward(self, x1, x2, diag=False, **params):
+        ls = self.lengthscale.to(x1)
+        d2 = self.covar_dist(x1 / ls, x2 / ls, diag=diag, square_dist=True)
+        return torch.exp(-0.5 * d2)
+
+
 class ProductKernel(Kernel):
     def __init__(self, *kernels):
         super().__init__()
@@ -238,5 +250,5 @@ class ProductKernel(Kernel):
 
 if HAVE_GPYTORCH:  # pragma: no cover
     from gpytorch.constraints import GreaterThan, Interval, Positive  # noqa: F811,F401
-    from gpytorch.kernels import Kernel, ProductKernel, ScaleKernel  # noqa: F811,F401
+    from gpytorch.kernels import Kernel, ProductKernel, RBFKernel, ScaleKernel  # noqa: F811,F401
     from gpytorch import Module  # noqa: F811,F401

@@ -1,16 +1,25 @@
 """SPD kernels: drop-in for the intrinsic SPD(2) kernels of BoManifolds/kernel_utils/kernels_spd.py
 (SpdRiemannianGaussianKernel :24-136, SpdRiemannianIntegratedMaternKernel :139-289), evaluated by the
 warp-per-entry quadrature kernel (csrc/quad_gram.cu).  Inputs are Mandel 3-vectors (s11, s22, sqrt2 s12).
-As in the reference, dim != 2 raises NotImplementedError.  The product kernels (R x S, R x SO) and the
-approximate / log-Euclidean kernels of the reference file are not part of this round.
+As in the reference, dim != 2 raises NotImplementedError.
+
+The product kernels (SpdProductOfRSManifolds... :292-549, SpdProductOfRSOManifolds... :552-774) are compositions
+of the Euclidean factor with a sphere / circle / SO(3) factor through ProductKernel, exactly as in the reference;
+they accept the pre-decomposed inputs (``spd_input=False``: eigenvalues followed by the sphere point or the
+flattened rotation).  ``spd_input=True`` needs the eigen-decomposition front-end built on the removed
+``torch.symeig`` (Riemannian_utils/spd_utils_torch.py:293-333) and raises NotImplementedError.  The approximate /
+log-Euclidean kernels are out of scope.
 """
 from __future__ import annotations
 
 import torch
 
 from . import _ops, _weights
-from .gpytorch_compat import Kernel
-from .kernels_sphere import _NuMixin, _check_batch
+from .gpytorch_compat import Kernel, RBFKernel
+from .kernels_euclidean import EuclideanIntegratedMaternKernel
+from .kernels_so import SORiemannianGaussianKernel, SORiemannianMaternKernel
+from .kernels_sphere import (CircleRiemannianGaussianKernel, CircleRiemannianIntegratedMaternKernel,
+                             SphereRiemannianGaussianKernel, SphereRiemannianMaternKernel, _NuMixin, _check_batch)
 
 F64 = torch.float64
 
@@ -72,3 +81,93 @@ class SpdRiemannianIntegratedMaternKernel(_NuMixin, Kernel):
         tcoef, rscale, bscale, b, bw = self.nodes(x1.device)
         fn = lambda a, c: _ops.spd2_gram(0, a, c, tcoef, rscale, bscale, b, bw)  # noqa: E731
         return _ops.pairwise(fn, x1, x2, diag=diag)
+
+
+class _SpdProductKernel(Kernel):
+    has_lengthscale = True
+
+    def forward(self, x1, x2, diag=False, **params):
+        if self.spd_input:
+            raise NotImplementedError("spd_input=True needs the SPD eigen-decomposition front-end (torch.symeig in the "
+                                      "reference); pass eigenvalues + sphere/rotation coordinates (spd_input=False)")
+        return self.spd_kernel.forward(x1, x2, diag=diag)
+
+
+def _sphere_dim(dim):
+    if dim == 2:
+        return 1
+    if dim == 3:
+        return 3
+    raise NotImplementedError
+
+
+class SpdProductOfRSManifoldsRiemannianGaussianKernel(_SpdProductKernel):
+    def __init__(self, dim, spd_input=False, **kwargs):
+        self.has_lengthscale = True
+        super().__init__(has_lengthscale=True, ard_num_dims=None, **kwargs)
+        self.dim = dim
+        self.dim_sphere = _sphere_dim(dim)
+        self.spd_input = spd_input
+        self.Euclidean_kernel = RBFKernel(active_dims=torch.tensor(list(range(0, self.dim))))
+        sdims = torch.tensor(list(range(self.dim, self.dim + self.dim_sphere + 1)))
+        if self.dim_sphere == 1:
+            self.sphere_kernel = CircleRiemannianGaussianKernel(active_dims=sdims)
+        else:
+            self.sphere_kernel = SphereRiemannianGaussianKernel(dim=self.dim_sphere, active_dims=sdims)
+        self.spd_kernel = self.Euclidean_kernel * self.sphere_kernel
+
+
+class SpdProductOfRSManifoldsRiemannianMaternKernel(_SpdProductKernel):
+    def __init__(self, dim, nu=None, nu_sphere=None, nu_prior_sphere=None, nu_euclidean=None, nu_prior_euclidean=None,
+                 spd_input=False, **kwargs):
+        self.has_lengthscale = True
+        super().__init__(has_lengthscale=True, ard_num_dims=None, **kwargs)
+        self.dim = dim
+        self.dim_sphere = _sphere_dim(dim)
+        if nu:
+            nu_euclidean = nu
+            nu_sphere = nu
+        self.spd_input = spd_input
+        self.Euclidean_kernel = EuclideanIntegratedMaternKernel(self.dim, nu=nu_euclidean, nu_prior=nu_prior_euclidean,
+                                                                active_dims=torch.tensor(list(range(0, self.dim))))
+        sdims = torch.tensor(list(range(self.dim, self.dim + self.dim_sphere + 1)))
+        if self.dim_sphere == 1:
+            self.sphere_kernel = CircleRiemannianIntegratedMaternKernel(nu=nu_sphere, nu_prior=nu_prior_sphere,
+                                                                        active_dims=sdims)
+        else:
+            self.sphere_kernel = SphereRiemannianMaternKernel(dim=self.dim_sphere, nu=nu_sphere, nu_prior=nu_prior_sphere,
+                                                              active_dims=sdims)
+        self.spd_kernel = self.Euclidean_kernel * self.sphere_kernel
+
+
+class SpdProductOfRSOManifoldsRiemannianGaussianKernel(_SpdProductKernel):
+    def __init__(self, dim, spd_input=False, **kwargs):
+        self.has_lengthscale = True
+        super().__init__(has_lengthscale=True, ard_num_dims=None, **kwargs)
+        self.dim = dim
+        if self.dim > 6:
+            raise NotImplementedError
+        self.spd_input = spd_input
+        self.Euclidean_kernel = RBFKernel(active_dims=torch.tensor(list(range(0, self.dim))))
+        self.so_kernel = SORiemannianGaussianKernel(dim=self.dim,
+                                                    active_dims=torch.tensor(list(range(self.dim, self.dim + self.dim ** 2))))
+        self.spd_kernel = self.Euclidean_kernel * self.so_kernel
+
+
+class SpdProductOfRSOManifoldsRiemannianMaternKernel(_SpdProductKernel):
+    def __init__(self, dim, nu=None, nu_so=None, nu_prior_so=None, nu_euclidean=None, nu_prior_euclidean=None,
+                 spd_input=False, **kwargs):
+        self.has_lengthscale = True
+        super().__init__(has_lengthscale=True, ard_num_dims=None, **kwargs)
+        self.dim = dim
+        if self.dim > 6:
+            raise NotImplementedError
+        if nu:
+            nu_euclidean = nu
+            nu_so = nu
+        self.spd_input = spd_input
+        self.Euclidean_kernel = EuclideanIntegratedMaternKernel(self.dim, nu=nu_euclidean, nu_prior=nu_prior_euclidean,
+                                                                active_dims=torch.tensor(list(range(0, self.dim))))
+        self.so_kernel = SORiemannianMaternKernel(dim=self.dim, nu=nu_so, nu_prior=nu_prior_so,
+                                                  active_dims=torch.tensor(list(range(self.dim, self.dim + self.dim ** 2))))
+        self.spd_kernel = self.Euclidean_kernel * self.so_kernel

@@ -180,6 +180,33 @@ def main():
     k.lengthscale = 0.7
     cases["euclidean_intmatern"] = dict(_run(k, e1, e2, gen), dim=3, nu=2.5, lengthscale=0.7)
 
+    # ---- SPD product kernels on pre-decomposed inputs (eigenvalues | rotation or sphere point) -----------
+    def _eig(n_):
+        return 0.5 + 2.0 * torch.rand(n_, 3, generator=gen)
+
+    def _quat(n_):
+        return _unit(torch.randn(n_, 4, generator=gen))
+
+    p1 = torch.cat([_eig(14), _rotations(14, gen)], -1)
+    p2 = torch.cat([_eig(10), _rotations(10, gen)], -1)
+    with rl.quiet():
+        k = ksp.SpdProductOfRSOManifoldsRiemannianMaternKernel(dim=3, nu=2.5, spd_input=False)
+    k.Euclidean_kernel.lengthscale = 1.2
+    k.so_kernel.lengthscale = 0.6
+    cases["spd3_product_rso_matern"] = dict(_run(k, p1, p2, gen, grads=False), nu=2.5, ls_euclidean=1.2, ls_manifold=0.6)
+    q1 = torch.cat([_eig(13), _quat(13)], -1)
+    q2 = torch.cat([_eig(9), _quat(9)], -1)
+    k = ksp.SpdProductOfRSManifoldsRiemannianMaternKernel(dim=3, nu=2.5, spd_input=False)
+    k.Euclidean_kernel.lengthscale = 0.9
+    k.sphere_kernel.lengthscale = 0.5
+    cases["spd3_product_rs_matern"] = dict(_run(k, q1, q2, gen, grads=False), nu=2.5, ls_euclidean=0.9, ls_manifold=0.5)
+    c1 = torch.cat([_eig(11)[:, :2], _unit(torch.randn(11, 2, generator=gen))], -1)
+    c2 = torch.cat([_eig(8)[:, :2], _unit(torch.randn(8, 2, generator=gen))], -1)
+    k = ksp.SpdProductOfRSManifoldsRiemannianMaternKernel(dim=2, nu=1.5, spd_input=False)
+    k.Euclidean_kernel.lengthscale = 1.1
+    k.sphere_kernel.lengthscale = 0.4
+    cases["spd2_product_rs_matern"] = dict(_run(k, c1, c2, gen, grads=False), nu=1.5, ls_euclidean=1.1, ls_manifold=0.4)
+
     for name, payload in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **{k_: np.asarray(v) for k_, v in payload.items()})
         print("%-32s K%s max|K|=%.3f" % (name, payload["K"].shape, np.abs(payload["K"]).max()))

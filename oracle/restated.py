@@ -413,6 +413,25 @@ def euclidean_integrated_matern(x1, x2, nu, lengthscale, nb_points=100):
     return k / nrm
 
 
+def spd_product_matern(x1, x2, dim, nu, ls_euclidean, ls_manifold, manifold):
+    """Product kernels on pre-decomposed SPD inputs (spd_input=False): Euclidean integrated Matern on the first
+    ``dim`` columns (eigenvalues) times the sphere / circle / SO(dim) Matern kernel on the remaining ones;
+    kernels_spd.py:415-549 (R x S: S^1 for dim 2, S^3 for dim 3) and :658-774 (R x SO)."""
+    ke = euclidean_integrated_matern(x1[..., :dim], x2[..., :dim], nu, ls_euclidean)
+    a, b = x1[..., dim:], x2[..., dim:]
+    if manifold == "so":
+        if dim != 3:
+            raise NotImplementedError
+        km = so3_matern(a, b, nu, ls_manifold)
+    elif dim == 2:
+        km = circle_integrated_matern(a, b, nu, ls_manifold)
+    elif dim == 3:
+        km = sphere_matern(a, b, 3, nu, ls_manifold)
+    else:
+        raise NotImplementedError
+    return ke * km
+
+
 # ----------------------------------------------------------------------------------------------
 # exact GP posterior + analytic EI (gpytorch / botorch arithmetic; unvendored - see SURVEY 8c)
 # ----------------------------------------------------------------------------------------------

@@ -113,3 +113,33 @@ def test_spd2_config4_block_vs_oracle():
     ref = R.spd2_integrated_matern(v[:48], v[:40], 2.5, 1.0, 64, 64)
     assert rel_err(full[:48, :40], ref) < TOL
     assert rel_err(full, full.t()) < 1e-10
+
+
+def test_euclidean_integrated_matern():
+    from materngabo_b200 import kernels_euclidean as ke
+
+    g = load_golden("euclidean_intmatern")
+    k = ke.EuclideanIntegratedMaternKernel(3, nu=2.5)
+    k.lengthscale = float(g["lengthscale"])
+    k.raw_lengthscale.requires_grad_(True)
+    out = k.forward(_t(g["x1"]), _t(g["x2"]))
+    assert rel_err(out, g["K"]) < TOL
+    (gl,) = torch.autograd.grad((out * _t(g["G"])).sum(), [k.raw_lengthscale])
+    assert rel_err(gl.reshape(-1), g["g_raw_lengthscale"].reshape(-1)) < 1e-9
+
+
+@pytest.mark.parametrize("name,cls,dim,nu", [("spd3_product_rso_matern", "SpdProductOfRSOManifoldsRiemannianMaternKernel", 3, 2.5),
+                                             ("spd3_product_rs_matern", "SpdProductOfRSManifoldsRiemannianMaternKernel", 3, 2.5),
+                                             ("spd2_product_rs_matern", "SpdProductOfRSManifoldsRiemannianMaternKernel", 2, 1.5)])
+def test_spd_product_kernels(name, cls, dim, nu):
+    """SPD(3) as R^3 x SO(3) / R^3 x S^3 and SPD(2) as R^2 x S^1 on pre-decomposed inputs."""
+    from materngabo_b200 import kernels_spd as ksp
+
+    g = load_golden(name)
+    k = getattr(ksp, cls)(dim=dim, nu=nu, spd_input=False)
+    k.Euclidean_kernel.lengthscale = float(g["ls_euclidean"])
+    manifold_kernel = k.so_kernel if "RSO" in cls else k.sphere_kernel
+    manifold_kernel.lengthscale = float(g["ls_manifold"])
+    assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
+    with pytest.raises(NotImplementedError):
+        getattr(ksp, cls)(dim=dim, nu=nu, spd_input=True).forward(_t(g["x1"]), _t(g["x2"]))

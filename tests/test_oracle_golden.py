@@ -59,6 +59,9 @@ def test_value_and_gradients(name):
 
 
 VALUE_ONLY = {
+    "spd3_product_rso_matern": lambda g: R.spd_product_matern(g["x1"], g["x2"], 3, 2.5, 1.2, 0.6, "so"),
+    "spd3_product_rs_matern": lambda g: R.spd_product_matern(g["x1"], g["x2"], 3, 2.5, 0.9, 0.5, "sphere"),
+    "spd2_product_rs_matern": lambda g: R.spd_product_matern(g["x1"], g["x2"], 2, 1.5, 1.1, 0.4, "sphere"),
     "sphere_matern_S3_example": lambda g: R.sphere_matern(g["x1"], g["x2"], 3, 2.5, 0.5),
     "sphere_matern_S2_self": lambda g: R.sphere_matern(g["x1"], g["x2"], 2, 2.5, 0.5),
     "so3_matern_self": lambda g: R.so3_matern(g["x1"], g["x2"], 2.5, 0.5),
