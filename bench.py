@@ -458,10 +458,18 @@ def run_gram(args, rank, world, local):
                 "peak_source": "DFMA micro-benchmark in this run"}
     else:
         ach = 8.0 * m * n / (ms_per_step * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
-                "frac": ach / peaks.get("hbm_gbs", 6650.0), "traffic": None,
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        tf = C.c_double()
+        _lib.check(lib.mgb_fp64_peak(1, 3, C.byref(tf), None), "mgb_fp64_peak")
+        hbm_roof = hbm * 1e9 / 8.0                                  # entries/s at 8 B per entry
+        fp64_roof = tf.value * 1e12 / flops if flops else None      # SURVEY.md 8d algorithmic flops per entry
+        lower = min(hbm_roof, fp64_roof) if fp64_roof else hbm_roof
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "bytes_per_entry": 8}
+                "bytes_per_entry": 8,
+                "survey_8d": {"algorithmic_flops_per_entry": flops, "hbm_roof_entries_per_s": hbm_roof,
+                              "fp64_roof_entries_per_s": fp64_roof, "fp64_peak_tflops_measured": tf.value,
+                              "frac_of_lower_roof": value / lower}}
     return {"metric": "kernel_entries_per_sec", "value": value, "unit": "entries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

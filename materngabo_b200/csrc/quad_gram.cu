@@ -51,6 +51,7 @@ struct HypParams {
   double* out;                                 // Q_BWD_COEF: gtcoef[Pt]; Q_NODES: out[count*Pt]
 };
 
+template <int NQ>
 __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
   extern __shared__ __align__(16) double sm[];
   // layout: E [Ps*Pt] | cm1 [Ps] | sh [Ps] | wq [Ps] | per-warp qw [2 * QWARPS][Ps] (two entries in flight)
@@ -82,9 +83,9 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
   const long long wstride = (long long)gridDim.x * QWARPS;
 
   // per-lane outer nodes a = lane + 32 q
-  double tv[QMAXT / 32], tc[QMAXT / 32], gacc[QMAXT / 32];
+  double tv[NQ], tc[NQ], gacc[NQ];
 #pragma unroll
-  for (int q = 0; q < QMAXT / 32; ++q) {
+  for (int q = 0; q < NQ; ++q) {
     const int a = lane + 32 * q;
     tv[q] = (a < p.Pt) ? p.tval[a] : 1.0;
     tc[q] = (a < p.Pt && p.tcoef != nullptr) ? p.tcoef[a] : 0.0;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
       }
       if (p.geom != 1) dsq[s2] = dd[s2] * dd[s2];
     }
-    double h[2][QMAXT / 32];
+    double h[2][NQ];
     if (p.dim == 2 && p.geom != 1) {
       __syncwarp();
 #pragma unroll
@@ -136,9 +137,9 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
         }
       }
       __syncwarp();
-      double g[2][QMAXT / 32], r[2][QMAXT / 32], acc[2][QMAXT / 32], pw[2][QMAXT / 32], i2t[QMAXT / 32];
+      double g[2][NQ], r[2][NQ], acc[2][NQ], pw[2][NQ], i2t[NQ];
 #pragma unroll
-      for (int q = 0; q < QMAXT / 32; ++q) {
+      for (int q = 0; q < NQ; ++q) {
         i2t[q] = 0.5 / tv[q];
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2) {
@@ -148,40 +149,37 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
           pw[s2][q] = 1.0;
         }
       }
-      const int nq = (p.Pt + 31) / 32;
       for (int k0 = 0; k0 < p.Ps; k0 += 16) {
         if (k0 > 0) {   // re-anchor the running powers with an exact exponential
 #pragma unroll
-          for (int q = 0; q < QMAXT / 32; ++q)
+          for (int q = 0; q < NQ; ++q)
 #pragma unroll
             for (int s2 = 0; s2 < 2; ++s2)
-              if (q < nq) pw[s2][q] = exp(-(k0 * p.ds) * dd[s2] * i2t[q]);
+              pw[s2][q] = exp(-(k0 * p.ds) * dd[s2] * i2t[q]);
         }
         const int k1 = min(k0 + 16, p.Ps);
         for (int k = k0; k < k1; ++k) {
           const double w0 = qw0[k], w1 = qw1[k];
 #pragma unroll
-          for (int q = 0; q < QMAXT / 32; ++q) {
-            if (q < nq) {
-              const int a = lane + 32 * q;
-              const double ev = (a < p.Pt) ? Es[k * p.Pt + a] : 0.0;
-              acc[0][q] = fma(w0 * ev, pw[0][q], acc[0][q]);
-              acc[1][q] = fma(w1 * ev, pw[1][q], acc[1][q]);
-              pw[0][q] *= r[0][q];
-              pw[1][q] *= r[1][q];
-            }
+          for (int q = 0; q < NQ; ++q) {
+            const int a = lane + 32 * q;
+            const double ev = (a < p.Pt) ? Es[k * p.Pt + a] : 0.0;
+            acc[0][q] = fma(w0 * ev, pw[0][q], acc[0][q]);
+            acc[1][q] = fma(w1 * ev, pw[1][q], acc[1][q]);
+            pw[0][q] *= r[0][q];
+            pw[1][q] *= r[1][q];
           }
         }
       }
 #pragma unroll
-      for (int q = 0; q < QMAXT / 32; ++q)
+      for (int q = 0; q < NQ; ++q)
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2) h[s2][q] = (lane + 32 * q < p.Pt) ? g[s2][q] * acc[s2][q] : 0.0;
     } else {
 #pragma unroll
       for (int s2 = 0; s2 < 2; ++s2) {
 #pragma unroll
-        for (int q = 0; q < QMAXT / 32; ++q) {
+        for (int q = 0; q < NQ; ++q) {
           const int a = lane + 32 * q;
           h[s2][q] = 0.0;
           if (a < p.Pt) {
@@ -198,16 +196,16 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
       if (p.mode == Q_FWD) {
         double sum = 0.0;
 #pragma unroll
-        for (int q = 0; q < QMAXT / 32; ++q) sum = fma(tc[q], h[s2][q], sum);
+        for (int q = 0; q < NQ; ++q) sum = fma(tc[q], h[s2][q], sum);
         sum = warp_sum(sum);
         if (lane == 0) st_stream(p.K + ii[s2] * p.ldk + jj[s2], sum);
       } else if (p.mode == Q_BWD_COEF) {
         const double gg = p.G[ii[s2] * p.ldg + jj[s2]];
 #pragma unroll
-        for (int q = 0; q < QMAXT / 32; ++q) gacc[q] = fma(gg, h[s2][q], gacc[q]);
+        for (int q = 0; q < NQ; ++q) gacc[q] = fma(gg, h[s2][q], gacc[q]);
       } else {
 #pragma unroll
-        for (int q = 0; q < QMAXT / 32; ++q) {
+        for (int q = 0; q < NQ; ++q) {
           const int a = lane + 32 * q;
           if (a < p.Pt) p.out[ei[s2] * p.Pt + a] = h[s2][q];
         }
@@ -216,7 +214,7 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
   }
   if (p.mode == Q_BWD_COEF) {
 #pragma unroll
-    for (int q = 0; q < QMAXT / 32; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const int a = lane + 32 * q;
       if (a < p.Pt) atomicAdd(p.out + a, gacc[q]);
     }
@@ -367,13 +365,23 @@ static int hyp_launch(HypParams p, cudaStream_t s) {
     const size_t nE = (size_t)p.Ps * p.Pt;
     smem = sizeof(double) * (nE + 3 * (size_t)p.Ps + (size_t)2 * QWARPS * p.Ps);
     if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "hyperbolic: Ps*Pt table exceeds shared memory");
-    MGB_TRY(check_cuda(cudaFuncSetAttribute(hyp_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                       "cudaFuncSetAttribute"));
   }
   long long blocks = (total + QWARPS - 1) / QWARPS;
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  hyp_gram_kernel<<<(unsigned)blocks, QTHREADS, smem, s>>>(p);
+  const int nq = (p.Pt + 31) / 32;
+#define MGB_HYP_LAUNCH(NQV)                                                                                             \
+  do {                                                                                                                  \
+    if (smem > 48 * 1024)                                                                                               \
+      MGB_TRY(check_cuda(cudaFuncSetAttribute(hyp_gram_kernel<NQV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                              (int)smem), "cudaFuncSetAttribute"));                                     \
+    hyp_gram_kernel<NQV><<<(unsigned)blocks, QTHREADS, smem, s>>>(p);                                                   \
+  } while (0)
+  if (nq == 1) MGB_HYP_LAUNCH(1);
+  else if (nq == 2) MGB_HYP_LAUNCH(2);
+  else if (nq == 3) MGB_HYP_LAUNCH(3);
+  else MGB_HYP_LAUNCH(4);
+#undef MGB_HYP_LAUNCH
   return after_launch("hyp_gram_kernel");
 }
 

@@ -248,9 +248,9 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
 // Tensor-pipe variant of the fast path: the W-wide inner products run as FP64 DMMA m8n8k4 fragments (x2 columns
 // resident in registers as B fragments, x1 rows fetched from the shared-memory panel as A fragments, k padded
 // with zeros to a multiple of 4), which moves W of the W + T + 1 FMAs per entry off the FP64 DFMA pipe: DMMA
-// issues on the tensor pipe and overlaps the Horner chains.  Warp w owns rows [16w, 16w+16) of the panel as two
-// 8-row fragments x eight 8-column fragments; a lane ends up with columns 8b + 2(lane%4), +1 of row lane/4:
-// 16-byte stores again.
+// issues on the tensor pipe and overlaps the Horner chains.  The 8 warps tile the 128 x 64 panel as 4 x 2; a warp
+// owns four 8-row fragments x four 8-column fragments and a lane ends up with columns 8b + 2(lane%4), +1 of row
+// lane/4: 16-byte stores again.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -261,6 +261,8 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 template <int W, int TREG>
 __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_mma(SeriesParams p) {
   constexpr int KS = (W + 3) / 4;
+  constexpr int NB = 4;   // 8-column fragments per warp (32 columns)
+  constexpr int NA = 4;   // 8-row fragments per warp (32 rows)
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t bars[2];
 
@@ -269,16 +271,18 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_mma(SeriesParams 
   const long long npanels = (p.m + kTM - 1) / kTM;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int frow = lane >> 2, fk = lane & 3;
+  const int wr = warp >> 1;   // rows [32 wr, 32 wr + 32) of the panel
+  const int wq = warp & 1;    // columns [32 wq, 32 wq + 32) of the chunk
 
   double c[TREG];
 #pragma unroll
   for (int k = 0; k < TREG; ++k) c[k] = (k < p.T) ? __ldg(p.coef + k) : 0.0;
 
   // B fragments: element (k = 4 s + fk, n = frow) of column fragment b is scale * x2[col0 + 8 b + frow][k]
-  const long long col0 = cc * kTN;
-  double bf[8][KS];
+  const long long col0 = cc * kTN + 32 * wq;
+  double bf[NB][KS];
 #pragma unroll
-  for (int b = 0; b < 8; ++b) {
+  for (int b = 0; b < NB; ++b) {
     const long long cj = col0 + 8 * b + frow;
 #pragma unroll
     for (int sidx = 0; sidx < KS; ++sidx) {
@@ -317,51 +321,58 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_mma(SeriesParams 
     } else if (it == 0) {
       __syncthreads();
     }
-#pragma unroll 1
-    for (int a = 0; a < 2; ++a) {
-      const int r = warp * kRowsPerWarp + 8 * a + frow;    // this lane's row within the panel
-      if (warp * kRowsPerWarp + 8 * a >= rows) break;
+    // software pipeline over the four 8-row fragments: the DMMAs (tensor pipe) of fragment a+1 are issued before
+    // the Horner chains (FP64 pipe) of fragment a, so both pipes stay busy inside one warp
+    double u0[2][NB], u1[2][NB];
+    auto inner_products = [&](int a, double (&o0)[NB], double (&o1)[NB]) {
+      const int r = 32 * wr + 8 * a + frow;
       double af[KS];
 #pragma unroll
       for (int sidx = 0; sidx < KS; ++sidx) {
         const int k = 4 * sidx + fk;
         af[sidx] = (k < W) ? x1s[r * W + k] : 0.0;
       }
-      double u0[8], u1[8];
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        u0[b] = p.shift;
-        u1[b] = p.shift;
+      for (int b = 0; b < NB; ++b) {
+        o0[b] = p.shift;
+        o1[b] = p.shift;
 #pragma unroll
-        for (int sidx = 0; sidx < KS; ++sidx) dmma884(u0[b], u1[b], af[sidx], bf[b][sidx]);
+        for (int sidx = 0; sidx < KS; ++sidx) dmma884(o0[b], o1[b], af[sidx], bf[b][sidx]);
       }
+    };
+    inner_products(0, u0[0], u1[0]);
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const int cur = a & 1;
+      if (a + 1 < NA) inner_products(a + 1, u0[cur ^ 1], u1[cur ^ 1]);
       unsigned need = 0;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        need |= (unsigned)(((unsigned)__double2hiint(u0[b]) & 0x7fffffffu) >= thr);
-        need |= (unsigned)(((unsigned)__double2hiint(u1[b]) & 0x7fffffffu) >= thr);
+      for (int b = 0; b < NB; ++b) {
+        need |= (unsigned)(((unsigned)__double2hiint(u0[cur][b]) & 0x7fffffffu) >= thr);
+        need |= (unsigned)(((unsigned)__double2hiint(u1[cur][b]) & 0x7fffffffu) >= thr);
       }
       if (need) {
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          u0[b] = clamp_exact(u0[b], p.lo, p.hi);
-          u1[b] = clamp_exact(u1[b], p.lo, p.hi);
+        for (int b = 0; b < NB; ++b) {
+          u0[cur][b] = clamp_exact(u0[cur][b], p.lo, p.hi);
+          u1[cur][b] = clamp_exact(u1[cur][b], p.lo, p.hi);
         }
       }
-      double p0[8], p1[8];
+      double p0[NB], p1[NB];
 #pragma unroll
-      for (int b = 0; b < 8; ++b) p0[b] = p1[b] = c[TREG - 1];
+      for (int b = 0; b < NB; ++b) p0[b] = p1[b] = c[TREG - 1];
 #pragma unroll
       for (int k = TREG - 2; k >= 0; --k) {
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          p0[b] = fma(p0[b], u0[b], c[k]);
-          p1[b] = fma(p1[b], u1[b], c[k]);
+        for (int b = 0; b < NB; ++b) {
+          p0[b] = fma(p0[b], u0[cur][b], c[k]);
+          p1[b] = fma(p1[b], u1[cur][b], c[k]);
         }
       }
+      const int r = 32 * wr + 8 * a + frow;
       if (r < rows) {
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
+        for (int b = 0; b < NB; ++b) {
           const long long col = col0 + 8 * b + 2 * fk;
           double* out = out_ptr(p, row0 + r, col);
           if (aligned && col + 1 < p.n) {

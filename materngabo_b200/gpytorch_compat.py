@@ -176,9 +176,10 @@ class Kernel(Module):
     def __call__(self, x1, x2=None, diag=False, last_dim_is_batch=False, **params):
         x1_, x2_ = x1, x2
         if self.active_dims is not None:
-            x1_ = x1_.index_select(-1, self.active_dims)
+            dims = self.active_dims.to(x1_.device)
+            x1_ = x1_.index_select(-1, dims)
             if x2_ is not None:
-                x2_ = x2_.index_select(-1, self.active_dims)
+                x2_ = x2_.index_select(-1, dims)
         if x1_.ndimension() == 1:
             x1_ = x1_.unsqueeze(1)
         if x2_ is None:
