@@ -106,8 +106,15 @@ int mgb_hyperbolic_gram_fwd(int dim, const double* x1, long long m, long long ld
 int mgb_hyperbolic_gram_bwd_coef(int dim, const double* x1, long long m, long long ld1, const double* x2,
                                  long long n, long long ld2, const double* tval, int Pt, double s0, double ds,
                                  int Ps, const double* G, long long ldg, double* gtcoef, void* stream);
-int mgb_hyperbolic_heat_nodes(int dim, const double* dist, long long count, const double* tval, int Pt,
-                              double s0, double ds, int Ps, double* out, void* stream);
+/* gtval[a] += sum_ij G_ij tcoef[a] d heat(d_ij, t)/dt at t = tval[a] (caller zeroes): lengthscale gradient of the
+ * heat kernels, whose t = kappa^2 / 2 is differentiable (the integrated Matern grids are detached in the reference) */
+int mgb_hyperbolic_gram_bwd_tval(int dim, const double* x1, long long m, long long ld1, const double* x2,
+                                 long long n, long long ld2, const double* tval, const double* tcoef, int Pt,
+                                 double s0, double ds, int Ps, const double* G, long long ldg, double* gtval,
+                                 void* stream);
+/* derivative != 0: d heat / d t instead of heat */
+int mgb_hyperbolic_heat_nodes(int dim, int derivative, const double* dist, long long count, const double* tval,
+                              int Pt, double s0, double ds, int Ps, double* out, void* stream);
 
 /* Euclidean factor of the SPD product kernels (kernel_utils/kernels_euclidean.py:82-89,162-207):
  *   K_ij = sum_a tcoef[a] exp(-|x1_i - x2_j|^2 / (4 tval[a])), rows `width` wide. */
@@ -129,6 +136,12 @@ int mgb_spd2_gram_fwd(int use_cholesky, const double* x1, long long m, long long
                       long long n, long long ld2, const double* tcoef, const double* rscale,
                       const double* bscale, int Pt, const double* bval, const double* bw, int Pb,
                       double* K, long long ldk, void* stream);
+/* g_rscale[a] += dL/drscale[a], g_bscale[a] += dL/dbscale[a] (caller zeroes): lengthscale gradient of the SPD(2) heat
+ * kernel, whose scales 1/(2 kappa^2), 1/kappa^2 are differentiable */
+int mgb_spd2_gram_bwd_scales(int use_cholesky, const double* x1, long long m, long long ld1, const double* x2,
+                             long long n, long long ld2, const double* tcoef, const double* rscale,
+                             const double* bscale, int Pt, const double* bval, const double* bw, int Pb,
+                             const double* G, long long ldg, double* g_rscale, double* g_bscale, void* stream);
 int mgb_spd2_gram_bwd_coef(int use_cholesky, const double* x1, long long m, long long ld1, const double* x2,
                            long long n, long long ld2, const double* rscale, const double* bscale, int Pt,
                            const double* bval, const double* bw, int Pb, const double* G, long long ldg,

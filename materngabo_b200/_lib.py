@@ -41,10 +41,12 @@ PROTOTYPES = {
     "mgb_series_gram_dx": (_I, [_DESC, _I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _LL, _LL, _P, _P, _P]),
     "mgb_hyperbolic_gram_fwd": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _I, _D, _D, _I, _P, _LL, _P]),
     "mgb_hyperbolic_gram_bwd_coef": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _I, _D, _D, _I, _P, _LL, _P, _P]),
-    "mgb_hyperbolic_heat_nodes": (_I, [_I, _P, _LL, _P, _I, _D, _D, _I, _P, _P]),
+    "mgb_hyperbolic_gram_bwd_tval": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _I, _D, _D, _I, _P, _LL, _P, _P]),
+    "mgb_hyperbolic_heat_nodes": (_I, [_I, _I, _P, _LL, _P, _I, _D, _D, _I, _P, _P]),
     "mgb_euclidean_gram_fwd": (_I, [_P, _LL, _LL, _P, _LL, _LL, _I, _P, _P, _I, _P, _LL, _P]),
     "mgb_euclidean_gram_bwd_coef": (_I, [_P, _LL, _LL, _P, _LL, _LL, _I, _P, _I, _P, _LL, _P, _P]),
     "mgb_spd2_gram_fwd": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P, _I, _P, _P, _I, _P, _LL, _P]),
+    "mgb_spd2_gram_bwd_scales": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P, _I, _P, _P, _I, _P, _LL, _P, _P, _P]),
     "mgb_spd2_gram_bwd_coef": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _I, _P, _P, _I, _P, _LL, _P, _P]),
     "mgb_posterior_pack_bytes": (_LL, [_LL]),
     "mgb_posterior_pack": (_I, [_P, _LL, _LL, _P, _P, _P]),

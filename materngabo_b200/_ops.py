@@ -178,7 +178,7 @@ def series_gram(spec: SeriesSpec, x1: torch.Tensor, x2: torch.Tensor, coef: torc
 # quadrature kernels
 # --------------------------------------------------------------------------------------------------
 class HyperbolicGram(torch.autograd.Function):
-    """K = sum_a tcoef[a] heat(d_ij, tval[a]); differentiable with respect to tcoef (hyper-parameters)."""
+    """K = sum_a tcoef[a] heat(d_ij, tval[a]); differentiable with respect to tcoef and tval (hyper-parameters)."""
 
     @staticmethod
     def forward(ctx, dim, x1, x2, tval, tcoef, s0, ds, ps):
@@ -191,7 +191,7 @@ class HyperbolicGram(torch.autograd.Function):
                                              _lib.ptr(k), max(n, 1), _lib.stream_ptr(x1.device))
         _lib.check(rc, "mgb_hyperbolic_gram_fwd")
         ctx.args = (dim, s0, ds, ps)
-        ctx.save_for_backward(x1, x2, tval)
+        ctx.save_for_backward(x1, x2, tval, tcoef)
         return k
 
     @staticmethod
@@ -199,20 +199,30 @@ class HyperbolicGram(torch.autograd.Function):
     def backward(ctx, g):
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             raise NotImplementedError("input gradients of the hyperbolic quadrature kernels are not implemented yet")
-        if not ctx.needs_input_grad[4]:
+        need_t, need_c = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        if not (need_t or need_c):
             return (None,) * 8
         lib = _lib.load()
         dim, s0, ds, ps = ctx.args
-        x1, x2, tval = ctx.saved_tensors
+        x1, x2, tval, tcoef = ctx.saved_tensors
         g = g.contiguous()
-        out = torch.zeros_like(tval)
+        gc = gt = None
         with torch.cuda.device(x1.device):
-            rc = lib.mgb_hyperbolic_gram_bwd_coef(dim, _lib.ptr(x1), x1.shape[0], x1.stride(0), _lib.ptr(x2),
-                                                  x2.shape[0], x2.stride(0), _lib.ptr(tval), tval.shape[0], s0, ds,
-                                                  ps, _lib.ptr(g), g.stride(0), _lib.ptr(out),
-                                                  _lib.stream_ptr(x1.device))
-        _lib.check(rc, "mgb_hyperbolic_gram_bwd_coef")
-        return None, None, None, None, out, None, None, None
+            if need_c:
+                gc = torch.zeros_like(tval)
+                rc = lib.mgb_hyperbolic_gram_bwd_coef(dim, _lib.ptr(x1), x1.shape[0], x1.stride(0), _lib.ptr(x2),
+                                                      x2.shape[0], x2.stride(0), _lib.ptr(tval), tval.shape[0], s0, ds,
+                                                      ps, _lib.ptr(g), g.stride(0), _lib.ptr(gc),
+                                                      _lib.stream_ptr(x1.device))
+                _lib.check(rc, "mgb_hyperbolic_gram_bwd_coef")
+            if need_t:
+                gt = torch.zeros_like(tval)
+                rc = lib.mgb_hyperbolic_gram_bwd_tval(dim, _lib.ptr(x1), x1.shape[0], x1.stride(0), _lib.ptr(x2),
+                                                      x2.shape[0], x2.stride(0), _lib.ptr(tval), _lib.ptr(tcoef),
+                                                      tval.shape[0], s0, ds, ps, _lib.ptr(g), g.stride(0), _lib.ptr(gt),
+                                                      _lib.stream_ptr(x1.device))
+                _lib.check(rc, "mgb_hyperbolic_gram_bwd_tval")
+        return None, None, None, gt, gc, None, None, None
 
 
 def hyperbolic_gram(dim, x1, x2, tval, tcoef, s0, ds, ps):
@@ -220,17 +230,37 @@ def hyperbolic_gram(dim, x1, x2, tval, tcoef, s0, ds, ps):
     return HyperbolicGram.apply(dim, _c2d(x1), _c2d(x2), tval.contiguous(), tcoef.contiguous(), float(s0), float(ds), int(ps))
 
 
-def hyperbolic_heat_nodes(dim, dist, tval, s0, ds, ps):
-    """heat(dist[e], tval[a]) -> (E, Pt) tensor (no autograd)."""
-    _lib.require_cuda_f64(dist, tval)
+def _heat_nodes_raw(dim, derivative, dist, tval, s0, ds, ps):
     lib = _lib.load()
-    dist = dist.contiguous().reshape(-1)
     out = torch.empty((dist.shape[0], tval.shape[0]), dtype=F64, device=dist.device)
     with torch.cuda.device(dist.device):
-        rc = lib.mgb_hyperbolic_heat_nodes(dim, _lib.ptr(dist), dist.shape[0], _lib.ptr(tval.contiguous()), tval.shape[0],
+        rc = lib.mgb_hyperbolic_heat_nodes(dim, int(derivative), _lib.ptr(dist), dist.shape[0], _lib.ptr(tval), tval.shape[0],
                                            float(s0), float(ds), int(ps), _lib.ptr(out), _lib.stream_ptr(dist.device))
     _lib.check(rc, "mgb_hyperbolic_heat_nodes")
     return out
+
+
+class HeatNodes(torch.autograd.Function):
+    """heat(dist[e], tval[a]) -> (E, Pt); differentiable with respect to tval (normaliser of the heat kernels)."""
+
+    @staticmethod
+    def forward(ctx, dim, dist, tval, s0, ds, ps):
+        ctx.args = (dim, s0, ds, ps)
+        ctx.save_for_backward(dist, tval)
+        return _heat_nodes_raw(dim, 0, dist, tval, s0, ds, ps)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        dim, s0, ds, ps = ctx.args
+        dist, tval = ctx.saved_tensors
+        gt = (g * _heat_nodes_raw(dim, 1, dist, tval, s0, ds, ps)).sum(0) if ctx.needs_input_grad[2] else None
+        return None, None, gt, None, None, None
+
+
+def hyperbolic_heat_nodes(dim, dist, tval, s0, ds, ps):
+    _lib.require_cuda_f64(dist, tval)
+    return HeatNodes.apply(dim, dist.contiguous().reshape(-1), tval.contiguous(), float(s0), float(ds), int(ps))
 
 
 class EuclideanGram(torch.autograd.Function):
@@ -286,7 +316,7 @@ class Spd2Gram(torch.autograd.Function):
                                        _lib.stream_ptr(x1.device))
         _lib.check(rc, "mgb_spd2_gram_fwd")
         ctx.use_chol = use_chol
-        ctx.save_for_backward(x1, x2, rscale, bscale, bval, bw)
+        ctx.save_for_backward(x1, x2, tcoef, rscale, bscale, bval, bw)
         return k
 
     @staticmethod
@@ -294,21 +324,30 @@ class Spd2Gram(torch.autograd.Function):
     def backward(ctx, g):
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             raise NotImplementedError("input gradients of the SPD quadrature kernels are not implemented yet")
-        if any(ctx.needs_input_grad[i] for i in (4, 5)):
-            raise NotImplementedError("gradient with respect to the SPD node scales")
-        if not ctx.needs_input_grad[3]:
+        need_c, need_s = ctx.needs_input_grad[3], (ctx.needs_input_grad[4] or ctx.needs_input_grad[5])
+        if not (need_c or need_s):
             return (None,) * 8
         lib = _lib.load()
-        x1, x2, rscale, bscale, bval, bw = ctx.saved_tensors
+        x1, x2, tcoef, rscale, bscale, bval, bw = ctx.saved_tensors
         g = g.contiguous()
-        out = torch.zeros_like(rscale)
+        gc = gr = gb = None
         with torch.cuda.device(x1.device):
-            rc = lib.mgb_spd2_gram_bwd_coef(ctx.use_chol, _lib.ptr(x1), x1.shape[0], x1.stride(0), _lib.ptr(x2),
-                                            x2.shape[0], x2.stride(0), _lib.ptr(rscale), _lib.ptr(bscale),
-                                            rscale.shape[0], _lib.ptr(bval), _lib.ptr(bw), bval.shape[0], _lib.ptr(g),
-                                            g.stride(0), _lib.ptr(out), _lib.stream_ptr(x1.device))
-        _lib.check(rc, "mgb_spd2_gram_bwd_coef")
-        return None, None, None, out, None, None, None, None
+            if need_c:
+                gc = torch.zeros_like(rscale)
+                rc = lib.mgb_spd2_gram_bwd_coef(ctx.use_chol, _lib.ptr(x1), x1.shape[0], x1.stride(0), _lib.ptr(x2),
+                                                x2.shape[0], x2.stride(0), _lib.ptr(rscale), _lib.ptr(bscale),
+                                                rscale.shape[0], _lib.ptr(bval), _lib.ptr(bw), bval.shape[0], _lib.ptr(g),
+                                                g.stride(0), _lib.ptr(gc), _lib.stream_ptr(x1.device))
+                _lib.check(rc, "mgb_spd2_gram_bwd_coef")
+            if need_s:
+                gr, gb = torch.zeros_like(rscale), torch.zeros_like(bscale)
+                rc = lib.mgb_spd2_gram_bwd_scales(ctx.use_chol, _lib.ptr(x1), x1.shape[0], x1.stride(0), _lib.ptr(x2),
+                                                  x2.shape[0], x2.stride(0), _lib.ptr(tcoef), _lib.ptr(rscale),
+                                                  _lib.ptr(bscale), rscale.shape[0], _lib.ptr(bval), _lib.ptr(bw),
+                                                  bval.shape[0], _lib.ptr(g), g.stride(0), _lib.ptr(gr), _lib.ptr(gb),
+                                                  _lib.stream_ptr(x1.device))
+                _lib.check(rc, "mgb_spd2_gram_bwd_scales")
+        return None, None, None, gc, gr, gb, None, None
 
 
 def spd2_gram(use_chol, x1, x2, tcoef, rscale, bscale, bval, bw):

@@ -22,7 +22,7 @@ constexpr int QWARPS = QTHREADS / 32;
 constexpr int QMAXP = 1024;   // max inner nodes
 constexpr int QMAXT = 128;    // max outer nodes (4 per lane)
 
-enum QuadMode { Q_FWD = 0, Q_BWD_COEF = 1, Q_NODES = 2 };
+enum QuadMode { Q_FWD = 0, Q_BWD_COEF = 1, Q_NODES = 2, Q_BWD_TVAL = 3, Q_BWD_SCALES = 4 };
 
 // d = 2 asinh( sqrt(max(0, -D0^2 + sum_k Dk^2) + 1e-8) / 2 ), reference operation order, no FMA contraction
 __device__ __forceinline__ double lorentz_dist(const double* a, const double* b, int dim) {
@@ -41,6 +41,7 @@ __device__ __forceinline__ double lorentz_dist(const double* a, const double* b,
 struct HypParams {
   int dim, mode;
   int geom, width;   // geom 1: Euclidean rows of `width` doubles, heat(d, t) = exp(-|x1 - x2|^2 / (4 t))
+  int deriv;         // 1: evaluate d heat / d t instead of heat (Q_NODES with derivative, Q_BWD_TVAL)
   const double* x1; long long m, ld1;
   const double* x2; long long n, ld2;
   const double* dist; long long count;        // Q_NODES
@@ -133,7 +134,8 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
         for (int k = lane; k < p.Ps; k += 32) {
           const double bk = p.s0 + k * p.ds;
           const double den = fma(chd, cm1[k], shd * sh[k]);
-          dst[k] = wq[k] * (bk + dd[s2]) * rsqrt(den);
+          const double sk = bk + dd[s2];
+          dst[k] = wq[k] * sk * rsqrt(den) * (p.deriv ? sk * sk : 1.0);   // d/dt brings down s^2 / (4 t^2)
         }
       }
       __syncwarp();
@@ -174,7 +176,8 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
 #pragma unroll
       for (int q = 0; q < NQ; ++q)
 #pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) h[s2][q] = (lane + 32 * q < p.Pt) ? g[s2][q] * acc[s2][q] : 0.0;
+        for (int s2 = 0; s2 < 2; ++s2)
+          h[s2][q] = (lane + 32 * q < p.Pt) ? g[s2][q] * acc[s2][q] * (p.deriv ? i2t[q] * i2t[q] : 1.0) : 0.0;
     } else {
 #pragma unroll
       for (int s2 = 0; s2 < 2; ++s2) {
@@ -185,6 +188,7 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
           if (a < p.Pt) {
             double v = exp(-dsq[s2] / (4.0 * tv[q]));
             if (p.dim == 3 && p.geom != 1) v = v * (dd[s2] + 1e-8) / sinh(dd[s2] + 1e-8);
+            if (p.deriv) v = v * dsq[s2] / (4.0 * tv[q] * tv[q]);
             h[s2][q] = v;
           }
         }
@@ -203,6 +207,10 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
         const double gg = p.G[ii[s2] * p.ldg + jj[s2]];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) gacc[q] = fma(gg, h[s2][q], gacc[q]);
+      } else if (p.mode == Q_BWD_TVAL) {
+        const double gg = p.G[ii[s2] * p.ldg + jj[s2]];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) gacc[q] = fma(gg * tc[q], h[s2][q], gacc[q]);
       } else {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
@@ -212,7 +220,7 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
       }
     }
   }
-  if (p.mode == Q_BWD_COEF) {
+  if (p.mode == Q_BWD_COEF || p.mode == Q_BWD_TVAL) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int a = lane + 32 * q;
@@ -233,6 +241,7 @@ struct SpdParams {
   const double* G; long long ldg;
   double* K; long long ldk;
   double* out;
+  double* out2;
 };
 
 // Mandel (s11, s22, sqrt2 s12) -> 2x2 (optionally its lower Cholesky factor); returns a,b,c,d row-major
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(QTHREADS) spd2_gram_kernel(SpdParams p) {
   const long long total = p.m * p.n;
   const long long wstride = (long long)gridDim.x * QWARPS;
 
-  double tc[QMAXT / 32], rs[QMAXT / 32], bs[QMAXT / 32], gacc[QMAXT / 32];
+  double tc[QMAXT / 32], rs[QMAXT / 32], bs[QMAXT / 32], gacc[QMAXT / 32], gacc2[QMAXT / 32];
 #pragma unroll
   for (int q = 0; q < QMAXT / 32; ++q) {
     const int a = lane + 32 * q;
@@ -294,6 +303,7 @@ __global__ void __launch_bounds__(QTHREADS) spd2_gram_kernel(SpdParams p) {
     rs[q] = (a < p.Pt) ? p.rscale[a] : 0.0;
     bs[q] = (a < p.Pt) ? p.bscale[a] : 0.0;
     gacc[q] = 0.0;
+    gacc2[q] = 0.0;
   }
 
   for (long long e = (long long)blockIdx.x * QWARPS + warp; e < total; e += wstride) {
@@ -310,16 +320,27 @@ __global__ void __launch_bounds__(QTHREADS) spd2_gram_kernel(SpdParams p) {
       cb[k] = b * (b + delta);
     }
     __syncwarp();
-    double h[QMAXT / 32];
+    double h[QMAXT / 32], hc[QMAXT / 32];
 #pragma unroll
     for (int q = 0; q < QMAXT / 32; ++q) {
       const int a = lane + 32 * q;
       h[q] = 0.0;
+      hc[q] = 0.0;
       if (a < p.Pt) {
         const double sc = -bs[q];
-        double acc = 0.0;
-        for (int k = 0; k < p.Pb; ++k) acc = fma(qb[k], exp(cb[k] * sc), acc);
-        h[q] = acc * exp(-r2 * rs[q]);
+        double acc = 0.0, accc = 0.0;
+        if (p.mode == Q_BWD_SCALES) {
+          for (int k = 0; k < p.Pb; ++k) {
+            const double ev = qb[k] * exp(cb[k] * sc);
+            acc += ev;
+            accc = fma(cb[k], ev, accc);   // sum_b q_b c_b exp(-c_b bscale)
+          }
+        } else {
+          for (int k = 0; k < p.Pb; ++k) acc = fma(qb[k], exp(cb[k] * sc), acc);
+        }
+        const double er = exp(-r2 * rs[q]);
+        h[q] = acc * er;
+        hc[q] = accc * er;
       }
     }
     if (p.mode == Q_FWD) {
@@ -328,17 +349,28 @@ __global__ void __launch_bounds__(QTHREADS) spd2_gram_kernel(SpdParams p) {
       for (int q = 0; q < QMAXT / 32; ++q) s = fma(tc[q], h[q], s);
       s = warp_sum(s);
       if (lane == 0) st_stream(p.K + i * p.ldk + j, s);
-    } else {
+    } else if (p.mode == Q_BWD_COEF) {
       const double g = p.G[i * p.ldg + j];
 #pragma unroll
       for (int q = 0; q < QMAXT / 32; ++q) gacc[q] = fma(g, h[q], gacc[q]);
+    } else {
+      // dK/drscale_a = -r2 tcoef_a h_a ; dK/dbscale_a = -tcoef_a exp(-r2 rscale_a) sum_b q_b c_b exp(-c_b bscale_a)
+      const double g = p.G[i * p.ldg + j];
+#pragma unroll
+      for (int q = 0; q < QMAXT / 32; ++q) {
+        gacc[q] = fma(-g * tc[q] * r2, h[q], gacc[q]);
+        gacc2[q] = fma(-g * tc[q], hc[q], gacc2[q]);
+      }
     }
   }
-  if (p.mode == Q_BWD_COEF) {
+  if (p.mode == Q_BWD_COEF || p.mode == Q_BWD_SCALES) {
 #pragma unroll
     for (int q = 0; q < QMAXT / 32; ++q) {
       const int a = lane + 32 * q;
-      if (a < p.Pt) atomicAdd(p.out + a, gacc[q]);
+      if (a < p.Pt) {
+        atomicAdd(p.out + a, gacc[q]);
+        if (p.mode == Q_BWD_SCALES) atomicAdd(p.out2 + a, gacc2[q]);
+      }
     }
   }
 }
@@ -426,10 +458,23 @@ extern "C" int mgb_hyperbolic_gram_bwd_coef(int dim, const double* x1, long long
   return hyp_launch(p, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int mgb_hyperbolic_heat_nodes(int dim, const double* dist, long long count, const double* tval, int Pt,
-                                         double s0, double ds, int Ps, double* out, void* stream) {
+extern "C" int mgb_hyperbolic_gram_bwd_tval(int dim, const double* x1, long long m, long long ld1, const double* x2,
+                                            long long n, long long ld2, const double* tval, const double* tcoef, int Pt,
+                                            double s0, double ds, int Ps, const double* G, long long ldg, double* gtval,
+                                            void* stream) {
+  if (!x1 || !x2 || !tval || !tcoef || !G || !gtval) return fail(MGB_ERR_ARG, "hyperbolic_gram_bwd_tval: null pointer");
+  if (m < 0 || n < 0 || ld1 < dim + 1 || ld2 < dim + 1 || ldg < n) return fail(MGB_ERR_ARG, "hyperbolic_gram_bwd_tval: bad sizes");
+  HypParams p{};
+  p.dim = dim; p.mode = Q_BWD_TVAL; p.deriv = 1; p.x1 = x1; p.m = m; p.ld1 = ld1; p.x2 = x2; p.n = n; p.ld2 = ld2;
+  p.tval = tval; p.tcoef = tcoef; p.Pt = Pt; p.s0 = s0; p.ds = ds; p.Ps = Ps; p.G = G; p.ldg = ldg; p.out = gtval;
+  return hyp_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mgb_hyperbolic_heat_nodes(int dim, int derivative, const double* dist, long long count, const double* tval,
+                                         int Pt, double s0, double ds, int Ps, double* out, void* stream) {
   if (!dist || !tval || !out || count < 0) return fail(MGB_ERR_ARG, "hyperbolic_heat_nodes: bad argument");
   HypParams p{};
+  p.deriv = derivative ? 1 : 0;
   p.dim = dim; p.mode = Q_NODES; p.dist = dist; p.count = count; p.tval = tval; p.Pt = Pt;
   p.s0 = s0; p.ds = ds; p.Ps = Ps; p.out = out;
   return hyp_launch(p, static_cast<cudaStream_t>(stream));
@@ -466,6 +511,20 @@ extern "C" int mgb_spd2_gram_fwd(int use_cholesky, const double* x1, long long m
   SpdParams p{};
   p.use_chol = use_cholesky; p.mode = Q_FWD; p.x1 = x1; p.m = m; p.ld1 = ld1; p.x2 = x2; p.n = n; p.ld2 = ld2;
   p.tcoef = tcoef; p.rscale = rscale; p.bscale = bscale; p.Pt = Pt; p.bval = bval; p.bw = bw; p.Pb = Pb; p.K = K; p.ldk = ldk;
+  return spd_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mgb_spd2_gram_bwd_scales(int use_cholesky, const double* x1, long long m, long long ld1, const double* x2,
+                                        long long n, long long ld2, const double* tcoef, const double* rscale,
+                                        const double* bscale, int Pt, const double* bval, const double* bw, int Pb,
+                                        const double* G, long long ldg, double* g_rscale, double* g_bscale, void* stream) {
+  if (!x1 || !x2 || !tcoef || !rscale || !bscale || !bval || !bw || !G || !g_rscale || !g_bscale)
+    return fail(MGB_ERR_ARG, "spd2_gram_bwd_scales: null pointer");
+  if (m < 0 || n < 0 || ld1 < 3 || ld2 < 3 || ldg < n) return fail(MGB_ERR_ARG, "spd2_gram_bwd_scales: bad sizes");
+  SpdParams p{};
+  p.use_chol = use_cholesky; p.mode = Q_BWD_SCALES; p.x1 = x1; p.m = m; p.ld1 = ld1; p.x2 = x2; p.n = n; p.ld2 = ld2;
+  p.tcoef = tcoef; p.rscale = rscale; p.bscale = bscale; p.Pt = Pt; p.bval = bval; p.bw = bw; p.Pb = Pb;
+  p.G = G; p.ldg = ldg; p.out = g_rscale; p.out2 = g_bscale;
   return spd_launch(p, static_cast<cudaStream_t>(stream));
 }
 

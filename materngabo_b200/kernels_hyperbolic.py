@@ -36,7 +36,7 @@ class HyperbolicRiemannianMillsonGaussianKernel(Kernel):
         dev = x1.device
         ls = self.lengthscale.reshape(()).to(device=dev, dtype=F64)
         # exp(-s^2 / (2 kappa^2)) = exp(-s^2 / (4 t)) with t = kappa^2 / 2   (kernels_hyperbolic.py:58-88)
-        tval = (ls ** 2 / 2).reshape(1).detach()
+        tval = (ls ** 2 / 2).reshape(1)          # differentiable: the device op returns dL/dt
         p = self.nb_points_integral
         s0, ds = 1e-2, (100.0 - 1e-2) / (p - 1)
         if self.dim == 2:

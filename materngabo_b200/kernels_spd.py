@@ -43,7 +43,7 @@ class SpdRiemannianGaussianKernel(Kernel):
     def forward(self, x1, x2, diag=False, **params):
         _check_batch(self)
         dev = x1.device
-        ls = self.lengthscale.reshape(()).to(device=dev, dtype=F64).detach()
+        ls = self.lengthscale.reshape(()).to(device=dev, dtype=F64)
         b, bw = _b_nodes(self.nb_points_integral, dev)
         rscale = (1.0 / (2 * ls ** 2)).reshape(1)
         bscale = (1.0 / ls ** 2).reshape(1)

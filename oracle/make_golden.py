@@ -207,6 +207,16 @@ def main():
     k.sphere_kernel.lengthscale = 0.4
     cases["spd2_product_rs_matern"] = dict(_run(k, c1, c2, gen, grads=False), nu=1.5, ls_euclidean=1.1, ls_manifold=0.4)
 
+    # ---- SPD(2) heat kernel: gradient with respect to the lengthscale only ---------------------------------
+    k = ksp.SpdRiemannianGaussianKernel(2, nb_points_integral=50)
+    k.lengthscale = 1.4
+    k.raw_lengthscale.requires_grad_(True)
+    kk = k.forward(s1, s2)
+    gg = torch.randn(kk.shape, generator=gen)
+    (gl,) = torch.autograd.grad((kk * gg).sum(), [k.raw_lengthscale])
+    cases["spd2_heat_lsgrad"] = dict(x1=s1.numpy(), x2=s2.numpy(), K=kk.detach().numpy(), G=gg.numpy(),
+                                     g_raw_lengthscale=gl.numpy(), lengthscale=1.4, Pb=50)
+
     for name, payload in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **{k_: np.asarray(v) for k_, v in payload.items()})
         print("%-32s K%s max|K|=%.3f" % (name, payload["K"].shape, np.abs(payload["K"]).max()))

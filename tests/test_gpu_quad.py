@@ -46,6 +46,11 @@ def test_hyperbolic_heat(dim):
     k = kh.HyperbolicRiemannianMillsonGaussianKernel(dim=dim, nb_points_integral=int(g["P"]))
     k.lengthscale = float(g["lengthscale"])
     assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
+    # lengthscale gradient: t = kappa^2 / 2 is differentiable, the device returns dL/dt (incl. the normaliser)
+    k.raw_lengthscale.requires_grad_(True)
+    out = k.forward(_t(g["x1"]), _t(g["x2"]))
+    (gl,) = torch.autograd.grad((out * _t(g["G"])).sum(), [k.raw_lengthscale])
+    assert rel_err(gl.reshape(-1), g["g_raw_lengthscale"].reshape(-1)) < 1e-9
 
 
 def test_hyperbolic_unsupported_dim():
@@ -73,6 +78,39 @@ def test_spd2_heat():
     k = ksp.SpdRiemannianGaussianKernel(2, nb_points_integral=int(g["Pb"]))
     k.lengthscale = float(g["lengthscale"])
     assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
+
+
+def test_spd2_heat_lengthscale_gradient():
+    from materngabo_b200 import kernels_spd as ksp
+
+    g = load_golden("spd2_heat_lsgrad")
+    k = ksp.SpdRiemannianGaussianKernel(2, nb_points_integral=int(g["Pb"]))
+    k.lengthscale = float(g["lengthscale"])
+    k.raw_lengthscale.requires_grad_(True)
+    out = k.forward(_t(g["x1"]), _t(g["x2"]))
+    assert rel_err(out, g["K"]) < TOL
+    (gl,) = torch.autograd.grad((out * _t(g["G"])).sum(), [k.raw_lengthscale])
+    assert rel_err(gl.reshape(-1), g["g_raw_lengthscale"].reshape(-1)) < 1e-9
+
+
+def test_spd2_matern_hyper_gradient_matches_oracle_autograd():
+    from materngabo_b200 import kernels_spd as ksp
+    from oracle import restated as R
+
+    g = load_golden("spd2_matern")
+    G = torch.randn(g["K"].shape, generator=torch.Generator().manual_seed(1))
+    k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=None, nb_points_integral_b=32, nb_points_integral_t=32)
+    k.lengthscale = 1.1
+    k.nu = 1.5
+    out = k.forward(_t(g["x1"]), _t(g["x2"]))
+    res = torch.autograd.grad((out * G.to(DEV)).sum(), [k.raw_lengthscale, k.raw_nu])
+    raw_ls = k.raw_lengthscale.detach().clone().requires_grad_(True)
+    raw_nu = k.raw_nu.detach().clone().requires_grad_(True)
+    sp = torch.nn.functional.softplus
+    ref = R.spd2_integrated_matern(torch.tensor(g["x1"]), torch.tensor(g["x2"]), sp(raw_nu), sp(raw_ls), 32, 32)
+    rres = torch.autograd.grad((ref * G).sum(), [raw_ls, raw_nu])
+    assert rel_err(out, ref) < TOL
+    assert rel_err(res[0], rres[0]) < 1e-9 and rel_err(res[1], rres[1]) < 1e-9
 
 
 def test_spd_dim3_raises_like_reference():

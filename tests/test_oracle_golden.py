@@ -89,6 +89,15 @@ def test_torus(dim):
     assert rel_err(k, raw["K"]) < PIN
 
 
+def test_spd2_heat_lengthscale_gradient():
+    raw = load_golden("spd2_heat_lsgrad")
+    raw_ls = _inv_softplus(raw["lengthscale"])
+    k = R.spd2_heat(_t(raw["x1"]), _t(raw["x2"]), _ls(raw_ls), 50)
+    assert rel_err(k, raw["K"]) < PIN
+    (gl,) = torch.autograd.grad((k * _t(raw["G"])).sum(), [raw_ls])
+    assert rel_err(gl.reshape(-1), raw["g_raw_lengthscale"].reshape(-1)) < 1e-11
+
+
 def test_nu_gradient():
     raw = load_golden("sphere_matern_S2_nugrad")
     raw_ls, raw_nu = _inv_softplus(raw["lengthscale"]), _inv_softplus(raw["nu"])
