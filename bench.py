@@ -581,7 +581,7 @@ def main():
         else:
             out = run_gram(args, rank, world, local)
         if rank == 0:
-            if not args.no_cpu_baseline and args.workload == "posterior-s10":
+            if not args.no_cpu_baseline and args.workload == "posterior-s10" and world == 1:   # N = 1 only
                 n = args.n or 5000
                 sample = 2048
                 rate, dt, _ = cpu_posterior_rate(n, sample)
