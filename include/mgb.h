@@ -176,6 +176,8 @@ long long mgb_posterior_tiled_bytes(long long m, long long n);
 int mgb_series_gram_tiled(const mgb_series_desc* desc, const double* x1, long long m, long long ld1,
                           const double* x2, long long n, long long ld2, const double* coef, double* Kb,
                           void* stream);
+/* row-major K (m x n) -> the tiled layout (Gram matrices of the quadrature kernels, which write row-major) */
+int mgb_posterior_retile(const double* K, long long m, long long n, long long ldk, double* Kb, void* stream);
 /* bytes of scratch mgb_posterior_reduce needs for m candidates (0 when one CTA per candidate tile suffices) */
 long long mgb_posterior_reduce_workspace_bytes(long long m, long long n);
 int mgb_posterior_reduce(const double* Kb, long long m, long long n, const double* packed, const double* kss,

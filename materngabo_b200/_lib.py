@@ -50,6 +50,7 @@ PROTOTYPES = {
     "mgb_spd2_gram_bwd_coef": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _I, _P, _P, _I, _P, _LL, _P, _P]),
     "mgb_posterior_pack_bytes": (_LL, [_LL]),
     "mgb_posterior_pack": (_I, [_P, _LL, _LL, _P, _P, _P]),
+    "mgb_posterior_retile": (_I, [_P, _LL, _LL, _LL, _P, _P]),
     "mgb_posterior_reduce_workspace_bytes": (_LL, [_LL, _LL]),
     "mgb_posterior_tiled_bytes": (_LL, [_LL, _LL]),
     "mgb_series_gram_tiled": (_I, [_DESC, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P]),

@@ -282,6 +282,20 @@ __global__ void posterior_pack_kernel(const double* Rinv, long long n, long long
   Rp[((((t * (ldp >> 4) + ch) << 7) + r) << 4) + (((chunk ^ ((r & 3) << 1)) << 1) | (int)(j & 1))] = v;
 }
 
+// Row-major K (m x n, ld = ldk) -> the tile-major swizzled operand layout (for Gram matrices produced by the
+// quadrature kernels, which write row-major).  One thread per 16-byte pair.
+__global__ void posterior_retile_kernel(const double* K, long long m, long long n, long long ldk, double* Kb, long long nch) {
+  const long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pairs_per_row = (n + 1) / 2;
+  if (pair >= m * pairs_per_row) return;
+  const long long row = pair / pairs_per_row, col = 2 * (pair - row * pairs_per_row);
+  const long long ctile = row >> 7, ch = col >> 4;
+  const int r = (int)(row & 127), chunk = (int)(col & 15) >> 1;
+  double* dst = Kb + ((((ctile * nch + ch) << 7) + r) << 4) + ((chunk ^ ((r & 3) << 1)) << 1);
+  dst[0] = K[row * ldk + col];
+  dst[1] = (col + 1 < n) ? K[row * ldk + col + 1] : 0.0;
+}
+
 __global__ void fill_kernel(double* dst, double v, long long count) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) dst[i] = v;
@@ -331,6 +345,16 @@ static int choose_splits(long long m, long long n) {
   if (s < 1) s = 1;
   if (s > n_tiles) s = n_tiles;
   return (int)s;
+}
+
+extern "C" int mgb_posterior_retile(const double* K, long long m, long long n, long long ldk, double* Kb, void* stream) {
+  if (!K || !Kb || m < 0 || n < 1 || ldk < n) return fail(MGB_ERR_ARG, "posterior_retile: bad argument");
+  if (reinterpret_cast<uintptr_t>(Kb) & 15u) return fail(MGB_ERR_ARG, "posterior_retile: Kb must be 16-byte aligned");
+  if (m == 0) return MGB_OK;
+  const long long pairs = m * ((n + 1) / 2);
+  posterior_retile_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      K, m, n, ldk, Kb, round_up(n, PK) / PK);
+  return after_launch("posterior_retile_kernel");
 }
 
 extern "C" long long mgb_posterior_reduce_workspace_bytes(long long m, long long n) {

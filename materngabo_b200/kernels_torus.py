@@ -37,6 +37,18 @@ class _TorusKernel(Kernel):
         if x1c.shape[-1] != 2 * self.dim or x2c.shape[-1] != 2 * self.dim:
             raise RuntimeError("T^%d points must be %d angles or %d circle coordinates" % (self.dim, self.dim, 2 * self.dim))
         spec, coef = _series_on(self, x1c.device)
+        if torch.is_grad_enabled() and (x1c.requires_grad or x2c.requires_grad):
+            # Input gradients (and the Hessian-vector products of the trust-region solver, bo_torus.py:278): evaluate
+            # the product factor by factor - every single-factor op is twice differentiable with respect to its inputs.
+            one = _ops.SeriesSpec(1, 2, spec.basis, spec.scale, spec.shift, spec.lo, spec.hi)
+
+            def fn(a, b):
+                out = None
+                for f in range(self.dim):
+                    kf = _ops.series_gram(one, a[:, 2 * f:2 * f + 2], b[:, 2 * f:2 * f + 2], coef[f:f + 1])
+                    out = kf if out is None else out * kf
+                return out
+            return _ops.pairwise(fn, x1c, x2c, diag=diag)
         return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1c, x2c, diag=diag)
 
 

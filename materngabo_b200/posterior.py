@@ -45,9 +45,12 @@ def _self_kernel_value(spec: _ops.SeriesSpec, coef: torch.Tensor) -> torch.Tenso
 
 
 class ExactGPPosterior:
-    """Constant-mean exact GP over a series kernel (sphere, SO(3), circle, torus).
+    """Constant-mean exact GP over one of the drop-in kernels.
 
-    ``kernel`` is one of the drop-in classes exposing ``series() -> (SeriesSpec, coef)``.
+    Series kernels (sphere, SO(3), circle, torus: anything exposing ``series() -> (SeriesSpec, coef)``) use the
+    fully fused path (Gram chunk written directly in the operand layout).  Any other kernel of this package
+    (hyperbolic, SPD(2), Euclidean, product kernels) goes through ``kernel.forward`` + a re-tiling kernel and the
+    same fused triangular reduction; those kernels are stationary and normalised, so k(x, x) is evaluated once.
     """
 
     def __init__(self, kernel, train_x: torch.Tensor, train_y: torch.Tensor, outputscale: float = 1.0,
@@ -68,19 +71,30 @@ class ExactGPPosterior:
         self.kss_value = None
 
     # ---- one-off N x N work ------------------------------------------------------------------
+    @property
+    def is_series(self):
+        return hasattr(self.kernel, "series")
+
     @torch.no_grad()
     def fit(self):
         x = self._prepared(self.train_x)
         n = x.shape[0]
-        spec, coef = self.kernel.series()
-        coef = (coef.detach().to(self.device, F64) * self._factor_scale(spec)).contiguous()
-        k = _ops.series_gram(spec, x, x, coef)
+        if self.is_series:
+            spec, coef = self.kernel.series()
+            coef = (coef.detach().to(self.device, F64) * self._factor_scale(spec)).contiguous()
+            k = _ops.series_gram(spec, x, x, coef)
+        else:
+            spec, coef = None, None
+            k = self.outputscale * self.kernel.forward(x, x)
         k.diagonal().add_(self.noise)
         L = torch.linalg.cholesky(k)
         self.alpha = torch.cholesky_solve((self.train_y - self.mean_const).unsqueeze(-1), L).squeeze(-1).contiguous()
         self.rinv = torch.linalg.solve_triangular(L, torch.eye(n, dtype=F64, device=self.device), upper=False).contiguous()
         self.spec, self.coef = spec, coef
-        self.kss_value = _self_kernel_value(spec, coef)
+        if self.is_series:
+            self.kss_value = _self_kernel_value(spec, coef)
+        else:
+            self.kss_value = float(self.outputscale * self.kernel.forward(x[:1], x[:1]).reshape(()))
         self.train_prepared = x
         self._pack()
         return self
@@ -135,6 +149,8 @@ class ExactGPPosterior:
             return mean, var
         lib = _lib.load()
         chunk = min(self.chunk, (m + 127) // 128 * 128)
+        if not self.is_series:
+            return self._posterior_generic(x, mean, var, chunk)
         need = lib.mgb_posterior_workspace_bytes(chunk, n)
         if self._ws is None or self._ws.numel() * 8 < need:
             self._ws = torch.empty((need + 7) // 8, dtype=F64, device=self.device)
@@ -148,6 +164,25 @@ class ExactGPPosterior:
         _lib.check(rc, "mgb_series_posterior")
         return mean, var
 
+
+    def _posterior_generic(self, x, mean, var, chunk):
+        """Row-major Gram chunk from ``kernel.forward`` -> re-tile -> fused reduction."""
+        lib = _lib.load()
+        m, n = x.shape[0], self.train_prepared.shape[0]
+        chunk = min(chunk, 8192)                      # quadrature Gram chunks are expensive to hold row-major
+        kb = torch.zeros(lib.mgb_posterior_tiled_bytes(chunk, n) // 8, dtype=F64, device=self.device)
+        part = torch.empty(max(1, lib.mgb_posterior_reduce_workspace_bytes(chunk, n) // 8), dtype=F64, device=self.device)
+        kss = torch.full((chunk,), self.kss_value, dtype=F64, device=self.device)
+        st = _lib.stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            for c0 in range(0, m, chunk):
+                mc = min(chunk, m - c0)
+                k = (self.outputscale * self.kernel.forward(x[c0:c0 + mc], self.train_prepared)).contiguous()
+                _lib.check(lib.mgb_posterior_retile(_lib.ptr(k), mc, n, k.stride(0), _lib.ptr(kb), st), "mgb_posterior_retile")
+                _lib.check(lib.mgb_posterior_reduce(_lib.ptr(kb), mc, n, _lib.ptr(self._packed), _lib.ptr(kss),
+                                                    self.mean_const, _lib.ptr(mean[c0:]), _lib.ptr(var[c0:]),
+                                                    _lib.ptr(part), part.numel() * 8, st), "mgb_posterior_reduce")
+        return mean, var
 
     # ---- differentiable path for the trust-region inner loop -------------------------------------
     def posterior_autograd(self, x: torch.Tensor):
@@ -165,7 +200,10 @@ class ExactGPPosterior:
                 raise NotImplementedError("q > 1 joint posteriors are not provided by the analytic acquisition path")
             x = x.squeeze(-2)
         xp = self._prepared(x)
-        ks = _ops.series_gram(self.spec, xp, self.train_prepared, self.coef)     # already scaled by outputscale
+        if self.is_series:
+            ks = _ops.series_gram(self.spec, xp, self.train_prepared, self.coef)  # already scaled by outputscale
+        else:
+            ks = self.outputscale * self.kernel.forward(xp, self.train_prepared)
         mean = self.mean_const + ks @ self.alpha
         v = ks @ self.rinv.t()                                                    # (L^-1 k*)^T, rinv is lower triangular
         var = self.kss_value - (v * v).sum(-1)

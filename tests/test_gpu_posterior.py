@@ -180,3 +180,51 @@ def test_acquisition_gradient_and_hessian_vector_product():
     assert abs(outs[0][0] - outs[1][0]) < 1e-9
     assert rel_err(outs[0][1], outs[1][1]) < 1e-8
     assert rel_err(outs[0][2], outs[1][2]) < 1e-7
+
+
+def test_generic_posterior_for_quadrature_kernels():
+    """Hyperbolic H^2 Matern through kernel.forward -> re-tile -> the same fused DMMA reduction."""
+    from materngabo_b200 import kernels_hyperbolic as kh
+    from materngabo_b200.posterior import ExactGPPosterior
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(12)
+
+    def lor(cnt):
+        z = torch.randn(cnt, 2, generator=gen)
+        return torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1)
+
+    xt, xc = lor(70), lor(333)
+    y = torch.tanh(xt[:, 1])
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=32)
+    k.lengthscale = 1.0
+    gp = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.5, noise=1e-2, mean_const=0.1).fit()
+    mean, var = gp.posterior(xc.to(DEV))
+    kfn = lambda a, b: R.hyperbolic_integrated_matern(a, b, 2, 2.5, 1.0, 32)  # noqa: E731
+    mean_ref, var_ref = R.gp_posterior(kfn, xt, y, xc, outputscale=1.5, noise=1e-2, mean_const=0.1)
+    assert rel_err(mean, mean_ref) < 1e-9
+    assert float((var.cpu() - var_ref).abs().max()) < 1e-8
+
+
+def test_torus_second_order_input_gradient():
+    from materngabo_b200 import kernels_torus as kt
+    from oracle import restated as R
+
+    torch.manual_seed(13)
+    a1, a2 = torch.rand(5, 3) * 6.28, torch.rand(8, 3) * 6.28
+    G, v = torch.randn(5, 8), torch.randn(5, 6)
+    k = kt.TorusProductOfManifoldsRiemannianMaternKernel(dim=3, nu=2.5)
+    for kk in k.torus_kernel.kernels:
+        kk.lengthscale = 0.5
+    c1, c2 = k._to_circles(a1), k._to_circles(a2)
+
+    def hvp(fn, a, b, g, vec):
+        a = a.clone().requires_grad_(True)
+        (ga,) = torch.autograd.grad((fn(a, b) * g).sum(), [a], create_graph=True)
+        (h,) = torch.autograd.grad((ga * vec).sum(), [a])
+        return ga.detach(), h
+
+    g_ref, h_ref = hvp(lambda a, b: R.torus_matern(a, b, 3, 2.5, 0.5), c1, c2, G, v)
+    g_dev, h_dev = hvp(lambda a, b: k.forward(a, b), c1.to(DEV), c2.to(DEV), G.to(DEV), v.to(DEV))
+    assert rel_err(g_dev, g_ref) < 1e-9
+    assert rel_err(h_dev, h_ref) < 1e-8
