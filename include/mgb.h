@@ -148,6 +148,36 @@ int mgb_spd2_gram_bwd_coef(int use_cholesky, const double* x1, long long m, long
                            double* gtcoef, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Radial profiles of the quadrature kernels and their derivatives in the pair scalar (csrc/quad_profile.cu).
+ *
+ * Input gradients (and Hessian-vector products) of the acquisition function, which the reference obtains by
+ * torch autograd through Kernel.forward (manifold_optimization/manifold_optimize.py:184-217,
+ * pymanopt_addons/tools/autodiff/_pytorch.py:89-116), factor by the chain rule into cheap pair geometry
+ * (distance / log singular values as functions of the inputs) and derivatives of the expensive quadrature with
+ * respect to the pair scalar.  These entry points evaluate the latter for a flat list of pair scalars:
+ *
+ *   mgb_radial_profile:  out[e] = sum_a tcoef[a] * d^order/dz^order heat(z[e], tval[a]),  order in {0, 1, 2}
+ *     kind 0/1/2 = H^1/H^2/H^3 with z = geodesic distance and heat as above (for H^2 the s grid moves with d,
+ *     kernels_hyperbolic.py:299, and the derivative includes it, as autograd does in the reference);
+ *     kind 3 = Euclidean factor, z = |x - y|^2, heat = exp(-z / (4 t)) (kernels_euclidean.py:82-89).
+ *   mgb_radial_profile_bwd_coef:  gtcoef[a] += sum_e G[e] * d^order/dz^order heat(z[e], tval[a])  (caller zeroes)
+ *   mgb_spd2_profile:  out[e] = sum_a tcoef[a] * D h_a(delta[e], r2[e]),  which = 0: D = 1, 1: d/dDelta, 2: d/dr2,
+ *     h_a(Delta, r2) = exp(-r2 rscale[a]) sum_b bw[b] (2 b_b + Delta) exp(-b_b (b_b + Delta) bscale[a])
+ *                                                   / sqrt(sinh b_b sinh(b_b + Delta))   (kernels_spd.py:200-209)
+ *   mgb_spd2_profile_bwd_coef:  gtcoef[a] += sum_e G[e] * D h_a(delta[e], r2[e])  (caller zeroes)
+ * ------------------------------------------------------------------------------------------------ */
+int mgb_radial_profile(int kind, int order, const double* z, long long count, const double* tval,
+                       const double* tcoef, int Pt, double s0, double ds, int Ps, double* out, void* stream);
+int mgb_radial_profile_bwd_coef(int kind, int order, const double* z, long long count, const double* tval, int Pt,
+                                double s0, double ds, int Ps, const double* G, double* gtcoef, void* stream);
+int mgb_spd2_profile(int which, const double* delta, const double* r2, long long count, const double* tcoef,
+                     const double* rscale, const double* bscale, int Pt, const double* bval, const double* bw,
+                     int Pb, double* out, void* stream);
+int mgb_spd2_profile_bwd_coef(int which, const double* delta, const double* r2, long long count,
+                              const double* rscale, const double* bscale, int Pt, const double* bval,
+                              const double* bw, int Pb, const double* G, double* gtcoef, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Exact-GP posterior for a block of candidates (gpytorch ExactGP prediction + botorch call sites:
  * examples/bo_manifolds_benchmark_examples/bo_sphere.py:215-233,265;
  * manifold_optimization/manifold_optimize.py:195,254,337)

@@ -357,6 +357,168 @@ def spd2_gram(use_chol, x1, x2, tcoef, rscale, bscale, bval, bw):
 
 
 # --------------------------------------------------------------------------------------------------
+# differentiable-input path of the quadrature kernels: cheap pair geometry in torch (any derivative order),
+# quadrature profile and its derivatives in the pair scalar on the device (csrc/quad_profile.cu)
+# --------------------------------------------------------------------------------------------------
+KIND_H1, KIND_H2, KIND_H3, KIND_EUCLID = 0, 1, 2, 3
+
+
+def inputs_need_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+
+
+def _radial_profile_raw(kind, order, z, tval, tcoef, s0, ds, ps):
+    lib = _lib.load()
+    z = z.contiguous()
+    out = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        rc = lib.mgb_radial_profile(kind, order, _lib.ptr(z), z.numel(), _lib.ptr(tval), _lib.ptr(tcoef), tval.shape[0],
+                                    s0, ds, ps, _lib.ptr(out), _lib.stream_ptr(z.device))
+    _lib.check(rc, "mgb_radial_profile")
+    return out
+
+
+class RadialProfile(torch.autograd.Function):
+    """P_order(z) = sum_a tcoef[a] d^order/dz^order heat(z, tval[a]) elementwise over ``z``.
+
+    ``backward`` is g * P_{order+1}(z), itself an instance of this Function, so that first- and second-order
+    derivatives with respect to the inputs (gradient and Hessian-vector product of the acquisition function)
+    come from the same device kernel.  Hyper-parameter gradients: tcoef at every order, tval at order 0."""
+
+    @staticmethod
+    def forward(ctx, kind, order, z, tval, tcoef, s0, ds, ps):
+        ctx.args = (kind, order, s0, ds, ps)
+        ctx.save_for_backward(z, tval, tcoef)
+        return _radial_profile_raw(kind, order, z, tval, tcoef, s0, ds, ps)
+
+    @staticmethod
+    def backward(ctx, g):
+        kind, order, s0, ds, ps = ctx.args
+        z, tval, tcoef = ctx.saved_tensors
+        gz = gt = gc = None
+        if ctx.needs_input_grad[2]:
+            if order >= 2:
+                raise NotImplementedError("third-order input derivatives of the quadrature kernels are not provided")
+            gz = g * RadialProfile.apply(kind, order + 1, z, tval, tcoef, s0, ds, ps)
+        if ctx.needs_input_grad[4]:
+            lib = _lib.load()
+            gd = g.detach().contiguous()
+            gc = torch.zeros_like(tcoef)
+            with torch.cuda.device(z.device):
+                rc = lib.mgb_radial_profile_bwd_coef(kind, order, _lib.ptr(z), z.numel(), _lib.ptr(tval), tval.shape[0],
+                                                     s0, ds, ps, _lib.ptr(gd), _lib.ptr(gc), _lib.stream_ptr(z.device))
+            _lib.check(rc, "mgb_radial_profile_bwd_coef")
+        if ctx.needs_input_grad[3]:
+            if order != 0 or kind == KIND_EUCLID:
+                raise NotImplementedError("mixed input / heat-time derivatives of the quadrature kernels are not provided")
+            nodes = _heat_nodes_raw(kind + 1, 1, z.detach().reshape(-1), tval, s0, ds, ps)     # d heat / dt, (E, Pt)
+            gt = (g.detach().reshape(-1, 1) * nodes).sum(0) * tcoef.detach()
+        return None, None, gz, gt, gc, None, None, None
+
+
+def radial_profile(kind, z, tval, tcoef, s0=0.0, ds=0.0, ps=0):
+    _lib.require_cuda_f64(z, tval, tcoef)
+    return RadialProfile.apply(int(kind), 0, z.contiguous(), tval.contiguous(), tcoef.contiguous(), float(s0), float(ds), int(ps))
+
+
+def lorentz_distance(x1, x2):
+    """Geodesic distance matrix on H^n (Lorentz model) in plain torch ops, operation order of
+    Riemannian_utils/hyperbolic_utils_torch.py:29-44,59-60; differentiable to any order.  Used only on the
+    differentiable-input path (the Gram kernels recompute it in registers)."""
+    diff = x1.unsqueeze(-2) - x2.unsqueeze(-3)
+    mink = -diff[..., 0] * diff[..., 0] + torch.sum(diff[..., 1:] * diff[..., 1:], dim=-1)
+    sq = torch.maximum(torch.zeros_like(mink), mink)
+    return 2 * torch.arcsinh(.5 * torch.sqrt(sq + 1e-8))
+
+
+def hyperbolic_gram_autograd(dim, x1, x2, tval, tcoef, s0, ds, ps):
+    return radial_profile(dim - 1, lorentz_distance(x1, x2), tval, tcoef, s0, ds, ps)
+
+
+def euclidean_gram_autograd(x1, x2, tval, tcoef):
+    diff = x1.unsqueeze(-2) - x2.unsqueeze(-3)
+    return radial_profile(KIND_EUCLID, (diff * diff).sum(-1), tval, tcoef)
+
+
+def _spd2_profile_raw(which, delta, r2, tcoef, rscale, bscale, bval, bw):
+    lib = _lib.load()
+    out = torch.empty_like(delta)
+    with torch.cuda.device(delta.device):
+        rc = lib.mgb_spd2_profile(which, _lib.ptr(delta), _lib.ptr(r2), delta.numel(), _lib.ptr(tcoef), _lib.ptr(rscale),
+                                  _lib.ptr(bscale), tcoef.shape[0], _lib.ptr(bval), _lib.ptr(bw), bval.shape[0],
+                                  _lib.ptr(out), _lib.stream_ptr(delta.device))
+    _lib.check(rc, "mgb_spd2_profile")
+    return out
+
+
+class Spd2Profile(torch.autograd.Function):
+    """K(Delta, r2) = sum_a tcoef[a] h_a(Delta, r2) elementwise; first-order derivatives in (Delta, r2) and tcoef
+    (the SPD trust region of the reference uses a finite-difference Hessian: bo_spd.py:383)."""
+
+    @staticmethod
+    def forward(ctx, delta, r2, tcoef, rscale, bscale, bval, bw):
+        ctx.save_for_backward(delta, r2, tcoef, rscale, bscale, bval, bw)
+        return _spd2_profile_raw(0, delta, r2, tcoef, rscale, bscale, bval, bw)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        delta, r2, tcoef, rscale, bscale, bval, bw = ctx.saved_tensors
+        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+            raise NotImplementedError("simultaneous input and heat-lengthscale gradients of the SPD(2) kernel are not "
+                                      "provided (detach one of them)")
+        gd = gr = gc = None
+        if ctx.needs_input_grad[0]:
+            gd = g * _spd2_profile_raw(1, delta, r2, tcoef, rscale, bscale, bval, bw)
+        if ctx.needs_input_grad[1]:
+            gr = g * _spd2_profile_raw(2, delta, r2, tcoef, rscale, bscale, bval, bw)
+        if ctx.needs_input_grad[2]:
+            lib = _lib.load()
+            gg = g.contiguous()
+            gc = torch.zeros_like(tcoef)
+            with torch.cuda.device(delta.device):
+                rc = lib.mgb_spd2_profile_bwd_coef(0, _lib.ptr(delta), _lib.ptr(r2), delta.numel(), _lib.ptr(rscale),
+                                                   _lib.ptr(bscale), rscale.shape[0], _lib.ptr(bval), _lib.ptr(bw),
+                                                   bval.shape[0], _lib.ptr(gg), _lib.ptr(gc), _lib.stream_ptr(delta.device))
+            _lib.check(rc, "mgb_spd2_profile_bwd_coef")
+        return gd, gr, gc, None, None, None, None
+
+
+def _mandel2(v, chol):
+    """Mandel 3-vector -> entries (a, b, c, d) of the 2 x 2 matrix (spd_utils_torch.py:336-371) or of its lower
+    Cholesky factor (kernels_spd.py:90-91)."""
+    s11, s22, s12 = v[..., 0], v[..., 1], v[..., 2] / 2 ** 0.5
+    if not chol:
+        return s11, s12, s12, s22
+    a = torch.sqrt(s11)
+    c = s12 / a
+    return a, torch.zeros_like(a), c, torch.sqrt(s22 - c * c)
+
+
+def spd2_log_singular_values(x1, x2, chol):
+    """H1 >= H2 = log singular values of A_i B_j^-1 (closed form for 2 x 2), differentiable torch ops."""
+    a, b, c, d = (t.unsqueeze(-1) for t in _mandel2(x1, chol))
+    e, f, g, h = (t.unsqueeze(-2) for t in _mandel2(x2, chol))
+    det = e * h - f * g
+    i11, i12, i21, i22 = h / det, -f / det, -g / det, e / det
+    p11, p12 = a * i11 + b * i21, a * i12 + b * i22
+    p21, p22 = c * i11 + d * i21, c * i12 + d * i22
+    q1 = torch.sqrt((p11 + p22) ** 2 + (p12 - p21) ** 2)
+    q2sq = (p11 - p22) ** 2 + (p12 + p21) ** 2
+    q2 = torch.sqrt(torch.where(q2sq > 0, q2sq, torch.ones_like(q2sq))) * (q2sq > 0)   # zero (sub)gradient at q2 = 0
+    s1 = 0.5 * (q1 + q2)
+    s2 = torch.abs(p11 * p22 - p12 * p21) / s1
+    return torch.log(s1), torch.log(s2)
+
+
+def spd2_gram_autograd(use_chol, x1, x2, tcoef, rscale, bscale, bval, bw):
+    _lib.require_cuda_f64(x1, x2, tcoef, rscale, bscale, bval, bw)
+    h1, h2 = spd2_log_singular_values(x1, x2, bool(use_chol))
+    return Spd2Profile.apply((h1 - h2).contiguous(), (h1 * h1 + h2 * h2).contiguous(), tcoef.contiguous(),
+                             rscale.contiguous(), bscale.contiguous(), bval.contiguous(), bw.contiguous())
+
+
+# --------------------------------------------------------------------------------------------------
 # pair-batch plumbing shared by the Kernel.forward overrides
 # --------------------------------------------------------------------------------------------------
 def _is_broadcast_of_2d(t: torch.Tensor) -> bool:

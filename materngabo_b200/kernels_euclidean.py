@@ -23,7 +23,8 @@ class EuclideanHeatKernel(Kernel):
         dim = x1.shape[1]
         tval = torch.as_tensor(t, dtype=F64, device=x1.device).reshape(1)
         tcoef = torch.pow(4 * np.pi * tval, -dim / 2)
-        return _ops.pairwise(lambda a, b: _ops.euclidean_gram(a, b, tval, tcoef), x1, x2, diag=diag)
+        fn = _ops.euclidean_gram_autograd if _ops.inputs_need_grad(x1, x2) else _ops.euclidean_gram
+        return _ops.pairwise(lambda a, b: fn(a, b, tval, tcoef), x1, x2, diag=diag)
 
 
 def unnormalized_heat_kernel(dist_sq, lengthscale):
@@ -55,4 +56,5 @@ class EuclideanIntegratedMaternKernel(_NuMixin, Kernel):
     def forward(self, x1, x2, diag=False, **params):
         _check_batch(self)
         tval, tcoef = self.nodes(x1.device)
-        return _ops.pairwise(lambda a, b: _ops.euclidean_gram(a, b, tval, tcoef), x1, x2, diag=diag)
+        fn = _ops.euclidean_gram_autograd if _ops.inputs_need_grad(x1, x2) else _ops.euclidean_gram
+        return _ops.pairwise(lambda a, b: fn(a, b, tval, tcoef), x1, x2, diag=diag)

@@ -19,6 +19,14 @@ def _check_lorentz(x1, x2, dim):
         raise RuntimeError("H^%d points must have %d Lorentz coordinates" % (dim, dim + 1))
 
 
+def _gram_fn(dim, x1, x2, tval, tcoef, s0, ds, p):
+    """Fused Gram kernel, or - when an input requires grad (acquisition gradient / Hessian-vector product of the
+    trust-region inner loop) - distance in torch + device profile with its d-derivatives (``_ops.RadialProfile``)."""
+    if _ops.inputs_need_grad(x1, x2):
+        return lambda a, b: _ops.hyperbolic_gram_autograd(dim, a, b, tval, tcoef, s0, ds, p)
+    return lambda a, b: _ops.hyperbolic_gram(dim, a, b, tval, tcoef, s0, ds, p)
+
+
 class HyperbolicRiemannianMillsonGaussianKernel(Kernel):
     has_lengthscale = True
 
@@ -44,8 +52,7 @@ class HyperbolicRiemannianMillsonGaussianKernel(Kernel):
         else:
             norm = torch.ones(1, dtype=F64, device=dev)
         tcoef = 1.0 / norm
-        fn = lambda a, b: _ops.hyperbolic_gram(self.dim, a, b, tval, tcoef, s0, ds, p)  # noqa: E731
-        return _ops.pairwise(fn, x1, x2, diag=diag)
+        return _ops.pairwise(_gram_fn(self.dim, x1, x2, tval, tcoef, s0, ds, p), x1, x2, diag=diag)
 
 
 class HyperbolicRiemannianMillsonIntegratedMaternKernel(_NuMixin, Kernel):
@@ -73,5 +80,4 @@ class HyperbolicRiemannianMillsonIntegratedMaternKernel(_NuMixin, Kernel):
             raise NotImplementedError
         _check_lorentz(x1, x2, self.dim)
         tval, tcoef, s0, ds, p = self.nodes(x1.device)
-        fn = lambda a, b: _ops.hyperbolic_gram(self.dim, a, b, tval, tcoef, s0, ds, p)  # noqa: E731
-        return _ops.pairwise(fn, x1, x2, diag=diag)
+        return _ops.pairwise(_gram_fn(self.dim, x1, x2, tval, tcoef, s0, ds, p), x1, x2, diag=diag)

@@ -50,7 +50,8 @@ class SpdRiemannianGaussianKernel(Kernel):
         # normaliser: the b-integral at Delta = 0 (kernels_spd.py:128-134)
         norm = (bw * 2.0 * b * torch.exp(-b * b * bscale) / torch.sinh(b)).sum()
         tcoef = (1.0 / norm).reshape(1)
-        fn = lambda a, c: _ops.spd2_gram(1, a, c, tcoef, rscale, bscale, b, bw)  # noqa: E731
+        op = _ops.spd2_gram_autograd if _ops.inputs_need_grad(x1, x2) else _ops.spd2_gram
+        fn = lambda a, c: op(1, a, c, tcoef, rscale, bscale, b, bw)  # noqa: E731
         return _ops.pairwise(fn, x1, x2, diag=diag)
 
 
@@ -79,7 +80,8 @@ class SpdRiemannianIntegratedMaternKernel(_NuMixin, Kernel):
     def forward(self, x1, x2, diag=False, **params):
         _check_batch(self)
         tcoef, rscale, bscale, b, bw = self.nodes(x1.device)
-        fn = lambda a, c: _ops.spd2_gram(0, a, c, tcoef, rscale, bscale, b, bw)  # noqa: E731
+        op = _ops.spd2_gram_autograd if _ops.inputs_need_grad(x1, x2) else _ops.spd2_gram
+        fn = lambda a, c: op(0, a, c, tcoef, rscale, bscale, b, bw)  # noqa: E731
         return _ops.pairwise(fn, x1, x2, diag=diag)
 
 

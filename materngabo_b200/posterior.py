@@ -15,6 +15,7 @@ product + square-sum, csrc/posterior.cu) and never materialises K(X*, X) beyond 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
 from typing import Callable, Optional
@@ -42,6 +43,18 @@ def _self_kernel_value(spec: _ops.SeriesSpec, coef: torch.Tensor) -> torch.Tenso
             s = sum(float(c[f, k]) * math.cos(k * theta) for k in range(c.shape[1]))
         val *= s
     return val
+
+
+@contextlib.contextmanager
+def _frozen_parameters(module):
+    params = [p for p in module.parameters() if p.requires_grad] if hasattr(module, "parameters") else []
+    for p in params:
+        p.requires_grad_(False)
+    try:
+        yield
+    finally:
+        for p in params:
+            p.requires_grad_(True)
 
 
 class ExactGPPosterior:
@@ -203,7 +216,8 @@ class ExactGPPosterior:
         if self.is_series:
             ks = _ops.series_gram(self.spec, xp, self.train_prepared, self.coef)  # already scaled by outputscale
         else:
-            ks = self.outputscale * self.kernel.forward(xp, self.train_prepared)
+            with _frozen_parameters(self.kernel):     # the fit is fixed here: differentiate with respect to x only
+                ks = self.outputscale * self.kernel.forward(xp, self.train_prepared)
         mean = self.mean_const + ks @ self.alpha
         v = ks @ self.rinv.t()                                                    # (L^-1 k*)^T, rinv is lower triangular
         var = self.kss_value - (v * v).sum(-1)

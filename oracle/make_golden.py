@@ -217,6 +217,38 @@ def main():
     cases["spd2_heat_lsgrad"] = dict(x1=s1.numpy(), x2=s2.numpy(), K=kk.detach().numpy(), G=gg.numpy(),
                                      g_raw_lengthscale=gl.numpy(), lengthscale=1.4, Pb=50)
 
+    # ---- input gradients and Hessian-vector products of the quadrature kernels (what the trust-region inner loop
+    # differentiates: manifold_optimize.py:184-217, pymanopt_addons/tools/autodiff/_pytorch.py:89-116) ---------
+    def _hvp_case(kernel, a, b):
+        a = a.clone().requires_grad_(True)
+        kk_ = kernel.forward(a, b)
+        g_ = torch.randn(kk_.shape, generator=gen)
+        v_ = torch.randn(a.shape, generator=gen)
+        (ga,) = torch.autograd.grad((kk_ * g_).sum(), [a], create_graph=True)
+        (hv,) = torch.autograd.grad((ga * v_).sum(), [a])
+        return dict(x1=a.detach().numpy(), x2=b.numpy(), K=kk_.detach().numpy(), G=g_.numpy(), V=v_.numpy(),
+                    gx1=ga.detach().numpy(), hvp_x1=hv.numpy())
+
+    for dim in (1, 2, 3):
+        h1, h2 = _lorentz(6, dim, gen), _lorentz(11, dim, gen)
+        k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=dim, nu=2.5, nb_points_integral=32)
+        k.lengthscale = 0.9
+        cases["hyperbolic_matern_H%d_hvp" % dim] = dict(_hvp_case(k, h1, h2), dim=dim, nu=2.5, lengthscale=0.9, P=32)
+        k = kh.HyperbolicRiemannianMillsonGaussianKernel(dim=dim, nb_points_integral=200)
+        k.lengthscale = 1.1
+        cases["hyperbolic_heat_H%d_hvp" % dim] = dict(_hvp_case(k, h1, h2), dim=dim, lengthscale=1.1, P=200)
+    s1, s2 = _spd2(7, gen), _spd2(9, gen)
+    k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5, nb_points_integral_b=40, nb_points_integral_t=36)
+    k.lengthscale = 1.2
+    cases["spd2_matern_xgrad"] = dict(_run(k, s1, s2, gen, params=()), nu=2.5, lengthscale=1.2, Pb=40, Pt=36)
+    k = ksp.SpdRiemannianGaussianKernel(2, nb_points_integral=50)
+    k.lengthscale = 1.4
+    cases["spd2_heat_xgrad"] = dict(_run(k, s1, s2, gen, params=()), lengthscale=1.4, Pb=50)
+    e1, e2 = torch.randn(5, 3, generator=gen), torch.randn(8, 3, generator=gen)
+    k = ke.EuclideanIntegratedMaternKernel(3, nu=1.5)
+    k.lengthscale = 0.8
+    cases["euclidean_intmatern_hvp"] = dict(_hvp_case(k, e1, e2), dim=3, nu=1.5, lengthscale=0.8)
+
     for name, payload in cases.items():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **{k_: np.asarray(v) for k_, v in payload.items()})
         print("%-32s K%s max|K|=%.3f" % (name, payload["K"].shape, np.abs(payload["K"]).max()))

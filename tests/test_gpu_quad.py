@@ -181,3 +181,137 @@ def test_spd_product_kernels(name, cls, dim, nu):
     assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
     with pytest.raises(NotImplementedError):
         getattr(ksp, cls)(dim=dim, nu=nu, spd_input=True).forward(_t(g["x1"]), _t(g["x2"]))
+
+
+# ---- input gradients / Hessian-vector products (trust-region inner loop) -------------------
+def _hvp_check(kernel, g, tol_g=1e-9, tol_h=1e-8):
+    a = _t(g["x1"]).requires_grad_(True)
+    k = kernel.forward(a, _t(g["x2"]))
+    assert rel_err(k, g["K"]) < TOL
+    (ga,) = torch.autograd.grad((k * _t(g["G"])).sum(), [a], create_graph=True)
+    assert rel_err(ga, g["gx1"]) < tol_g
+    (hv,) = torch.autograd.grad((ga * _t(g["V"])).sum(), [a])
+    assert rel_err(hv, g["hvp_x1"]) < tol_h
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_hyperbolic_matern_input_gradient_and_hvp(dim):
+    from materngabo_b200 import kernels_hyperbolic as kh
+
+    g = load_golden("hyperbolic_matern_H%d_hvp" % dim)
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=dim, nu=2.5, nb_points_integral=int(g["P"]))
+    k.lengthscale = float(g["lengthscale"])
+    _hvp_check(k, g)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_hyperbolic_heat_input_gradient_and_hvp(dim):
+    from materngabo_b200 import kernels_hyperbolic as kh
+
+    g = load_golden("hyperbolic_heat_H%d_hvp" % dim)
+    k = kh.HyperbolicRiemannianMillsonGaussianKernel(dim=dim, nb_points_integral=int(g["P"]))
+    k.lengthscale = float(g["lengthscale"])
+    for p in k.parameters():
+        p.requires_grad_(False)
+    _hvp_check(k, g)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_hyperbolic_gradients_to_both_inputs_and_lengthscale(dim):
+    """The golden cases of the forward tests also carry dL/dx1, dL/dx2 from the reference's autograd; asking for the
+    input and the lengthscale gradients in one backward exercises the coefficient path of the profile op."""
+    from materngabo_b200 import kernels_hyperbolic as kh
+
+    g = load_golden("hyperbolic_matern_H%d" % dim)
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=dim, nu=2.5, nb_points_integral=int(g["P"]))
+    k.lengthscale = float(g["lengthscale"])
+    a, b = _t(g["x1"]).requires_grad_(True), _t(g["x2"]).requires_grad_(True)
+    out = k.forward(a, b)
+    assert rel_err(out, g["K"]) < TOL
+    ga, gb, gl = torch.autograd.grad((out * _t(g["G"])).sum(), [a, b, k.raw_lengthscale])
+    assert rel_err(ga, g["gx1"]) < 1e-9 and rel_err(gb, g["gx2"]) < 1e-9
+    assert rel_err(gl.reshape(-1), g["g_raw_lengthscale"].reshape(-1)) < 1e-9
+    g = load_golden("hyperbolic_heat_H%d" % dim)
+    k = kh.HyperbolicRiemannianMillsonGaussianKernel(dim=dim, nb_points_integral=int(g["P"]))
+    k.lengthscale = float(g["lengthscale"])
+    a, b = _t(g["x1"]).requires_grad_(True), _t(g["x2"]).requires_grad_(True)
+    out = k.forward(a, b)
+    ga, gb, gl = torch.autograd.grad((out * _t(g["G"])).sum(), [a, b, k.raw_lengthscale])
+    assert rel_err(ga, g["gx1"]) < 1e-9 and rel_err(gb, g["gx2"]) < 1e-9
+    assert rel_err(gl.reshape(-1), g["g_raw_lengthscale"].reshape(-1)) < 1e-9
+
+
+def test_euclidean_input_gradient_and_hvp():
+    from materngabo_b200 import kernels_euclidean as ke
+
+    g = load_golden("euclidean_intmatern_hvp")
+    k = ke.EuclideanIntegratedMaternKernel(3, nu=float(g["nu"]))
+    k.lengthscale = float(g["lengthscale"])
+    _hvp_check(k, g)
+
+
+def test_spd2_input_gradients():
+    from materngabo_b200 import kernels_spd as ksp
+
+    g = load_golden("spd2_matern_xgrad")
+    k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5, nb_points_integral_b=int(g["Pb"]), nb_points_integral_t=int(g["Pt"]))
+    k.lengthscale = float(g["lengthscale"])
+    a, b = _t(g["x1"]).requires_grad_(True), _t(g["x2"]).requires_grad_(True)
+    out = k.forward(a, b)
+    assert rel_err(out, g["K"]) < TOL
+    ga, gb, gl = torch.autograd.grad((out * _t(g["G"])).sum(), [a, b, k.raw_lengthscale])
+    assert rel_err(ga, g["gx1"]) < 1e-9 and rel_err(gb, g["gx2"]) < 1e-9
+    assert torch.isfinite(gl).all()
+    g = load_golden("spd2_heat_xgrad")
+    k = ksp.SpdRiemannianGaussianKernel(2, nb_points_integral=int(g["Pb"]))
+    k.lengthscale = float(g["lengthscale"])
+    k.raw_lengthscale.requires_grad_(False)
+    a, b = _t(g["x1"]).requires_grad_(True), _t(g["x2"]).requires_grad_(True)
+    out = k.forward(a, b)
+    assert rel_err(out, g["K"]) < TOL
+    ga, gb = torch.autograd.grad((out * _t(g["G"])).sum(), [a, b])
+    assert rel_err(ga, g["gx1"]) < 1e-9 and rel_err(gb, g["gx2"]) < 1e-9
+
+
+def test_hyperbolic_acquisition_gradient_and_hvp():
+    """EI value, gradient and Hessian-vector product at single candidates on H^3 (bo_hyperbolic.py uses exact
+    Hessians: approx_hessian=False) against torch autograd through the oracle."""
+    from materngabo_b200 import kernels_hyperbolic as kh
+    from materngabo_b200.posterior import ExactGPPosterior, ExpectedImprovement
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(5)
+
+    def lor(cnt):
+        z = torch.randn(cnt, 3, generator=gen)
+        return torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1)
+
+    xt, xc = lor(40), lor(4)
+    y = torch.tanh(xt[:, 1]) + 0.1 * xt[:, 2]
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=3, nu=2.5, nb_points_integral=32)
+    k.lengthscale = 1.0
+    gp = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.3, noise=1e-2, mean_const=0.05).fit()
+    best = float(y.min())
+    acq = ExpectedImprovement(gp, best_f=best, maximize=False)
+    vec = torch.randn(4, 1, 4, generator=gen)
+    kfn = lambda a, b: R.hyperbolic_integrated_matern(a, b, 3, 2.5, 1.0, 32)  # noqa: E731
+    L, alpha = R.gp_fit(kfn, xt, y, 1.3, 1e-2, 0.05)
+
+    def cost_ref(x):
+        xs = x.squeeze(-2)
+        ks = 1.3 * kfn(xs, xt)
+        mean = 0.05 + ks @ alpha
+        v = torch.linalg.solve_triangular(L, ks.t(), upper=False)
+        var = 1.3 * kfn(xs[:1], xs[:1]).reshape(()).detach() - (v * v).sum(0)
+        return -R.expected_improvement(mean, var, best, maximize=False).sum()
+
+    outs = []
+    for fn, dev in ((lambda x: -acq(x).sum(), DEV), (cost_ref, "cpu")):
+        x = xc.unsqueeze(-2).to(dev).clone().requires_grad_(True)
+        c = fn(x)
+        (g,) = torch.autograd.grad(c, [x], create_graph=True)
+        (h,) = torch.autograd.grad((g * vec.to(dev)).sum(), [x])
+        outs.append((float(c.detach()), g.detach().cpu(), h.cpu()))
+    assert abs(outs[0][0] - outs[1][0]) < 1e-9
+    assert rel_err(outs[0][1], outs[1][1]) < 1e-8
+    assert rel_err(outs[0][2], outs[1][2]) < 1e-7

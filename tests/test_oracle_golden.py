@@ -133,3 +133,42 @@ def test_gp_posterior_identities():
     assert float(var.abs().max()) < 1e-4
     far = R.gp_posterior(kfn, xt[:1], y[:1], -xt[:1], outputscale=2.0, noise=1e-2, mean_const=0.3)
     assert abs(float(far[1]) - 2.0) < 0.2                 # antipodal point: nearly the prior variance
+
+
+HVP_CASES = {
+    "hyperbolic_matern_H1_hvp": lambda a, b: R.hyperbolic_integrated_matern(a, b, 1, 2.5, 0.9, 32),
+    "hyperbolic_matern_H2_hvp": lambda a, b: R.hyperbolic_integrated_matern(a, b, 2, 2.5, 0.9, 32),
+    "hyperbolic_matern_H3_hvp": lambda a, b: R.hyperbolic_integrated_matern(a, b, 3, 2.5, 0.9, 32),
+    "hyperbolic_heat_H1_hvp": lambda a, b: R.hyperbolic_heat(a, b, 1, 1.1, 200),
+    "hyperbolic_heat_H2_hvp": lambda a, b: R.hyperbolic_heat(a, b, 2, 1.1, 200),
+    "hyperbolic_heat_H3_hvp": lambda a, b: R.hyperbolic_heat(a, b, 3, 1.1, 200),
+    "euclidean_intmatern_hvp": lambda a, b: R.euclidean_integrated_matern(a, b, 1.5, 0.8),
+}
+
+
+@pytest.mark.parametrize("name", sorted(HVP_CASES))
+def test_input_gradient_and_hessian_vector_product(name):
+    """What the trust-region inner loop differentiates (manifold_optimize.py:184-217): gradient and Hessian-vector
+    product with respect to the candidate point, through the restated kernels."""
+    raw = load_golden(name)
+    a = _t(raw["x1"], True)
+    k = HVP_CASES[name](a, _t(raw["x2"]))
+    assert rel_err(k, raw["K"]) < PIN
+    (ga,) = torch.autograd.grad((k * _t(raw["G"])).sum(), [a], create_graph=True)
+    assert rel_err(ga, raw["gx1"]) < 1e-11
+    (hv,) = torch.autograd.grad((ga * _t(raw["V"])).sum(), [a])
+    assert rel_err(hv, raw["hvp_x1"]) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["spd2_matern_xgrad", "spd2_heat_xgrad"])
+def test_spd2_input_gradients(name):
+    raw = load_golden(name)
+    a, b = _t(raw["x1"], True), _t(raw["x2"], True)
+    if name == "spd2_matern_xgrad":
+        k = R.spd2_integrated_matern(a, b, 2.5, 1.2, 40, 36)
+    else:
+        k = R.spd2_heat(a, b, 1.4, 50)
+    assert rel_err(k, raw["K"]) < PIN
+    ga, gb = torch.autograd.grad((k * _t(raw["G"])).sum(), [a, b])
+    assert rel_err(ga, raw["gx1"]) < 1e-10
+    assert rel_err(gb, raw["gx2"]) < 1e-10
