@@ -127,6 +127,11 @@ def posterior_problem(n, device, seed=0):
     return gp, k
 
 
+# posterior_reduce_kernel at the default chunk (37888 candidates x 5000 training points): 12.490054 GB read +
+# 11.817472 MB written per launch (ncu --set full, profiles/r01_ncu_posterior_reduce.txt)
+NCU_REDUCE_TRAFFIC_BYTES = 12.490054e9 + 11.817472e6
+
+
 def flops_per_candidate(n):
     """N*78 (kernel row) + 2N (mean) + N^2 (triangular L^-1 k*, N^2/2 FMA) + 2N (norm)."""
     return n * 78.0 + 2.0 * n + float(n) * n + 2.0 * n
@@ -269,7 +274,12 @@ def posterior_roofline(gp, xc, n, lib):
     alg_flops = chunk * (float(n) * n + 4.0 * n)      # triangular product + mean + norm, per launch
     achieved = alg_flops / (red_ms * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": "posterior_reduce_kernel (FP64 DMMA m8n8k4)", "achieved": achieved,
-            "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value, "traffic": None,
+            "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
+            "traffic": NCU_REDUCE_TRAFFIC_BYTES if (chunk, n) == (37888, 5000) else None,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture "
+                              "profiles/r01_ncu_posterior_reduce.txt (chunk 37888, n 5000); algorithmic input bytes per "
+                              "launch = Gram chunk 8*chunk*n = %.2e + packed factor %.2e"
+                              % (8.0 * chunk * n, 8.0 * n * n / 2),
             "peak_source": "FP64 DMMA register-resident micro-benchmark measured in this run "
                            "(MEASURED_PEAKS.json has no FP64 figure; nominal %.1f; DFMA micro-benchmark %.1f)"
                            % (NOMINAL_FP64_TFLOPS, tf_dfma.value),
@@ -528,16 +538,23 @@ def cpu_posterior_rate(n, sample, chunk=512):
     return sample / dt, dt, float(mean[0])
 
 
+def cpu_sample_size(n, seconds, lo=512, hi=65536):
+    """Candidates the oracle port processes in about ``seconds`` on this host (pilot run of 512 candidates)."""
+    rate, _, _ = cpu_posterior_rate(n, 512)
+    return int(min(hi, max(lo, rate * seconds))) // 512 * 512
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return None
     torch.set_default_dtype(F64)
     n = args.n or 5000
-    sample = 1024
     use_all_host_threads()
     cores = torch.get_num_threads()
+    # bounded sample: about 8 s of host work per step so that --steps K --warmup W ends within a few minutes
+    sample = cpu_sample_size(n, 8.0)
     for _ in range(min(args.warmup, 1)):
-        cpu_posterior_rate(n, 256)
+        cpu_posterior_rate(n, 512)
     t0 = time.perf_counter()
     rates = []
     for _ in range(args.steps):
@@ -583,7 +600,7 @@ def main():
         if rank == 0:
             if not args.no_cpu_baseline and args.workload == "posterior-s10" and world == 1:   # N = 1 only
                 n = args.n or 5000
-                sample = 2048
+                sample = cpu_sample_size(n, 12.0)          # about 10-30 s of host work
                 rate, dt, _ = cpu_posterior_rate(n, sample)
                 out["cpu_baseline"] = {"value": rate, "unit": "candidates/s", "cores": torch.get_num_threads(),
                                        "kind": "port",
