@@ -378,7 +378,9 @@ def gram_setup(name, device, m, n):
             kk.lengthscale = 0.5
         x1 = k._to_circles(torch.rand(m, 10, generator=gen, device=device, dtype=F64) * 6.283185307179586)
         x2 = k._to_circles(torch.rand(n, 10, generator=gen, device=device, dtype=F64) * 6.283185307179586)
-        flops = None
+        # 10 factors x (6 + 4 n_eff) flops, n_eff = retained cosine terms per factor
+        n_eff = int(k.series()[1].shape[-1])
+        flops = 10 * (6 + 4 * n_eff)
     elif name == "gram-h2":
         k = kernels_hyperbolic.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=64)
         k.lengthscale = 1.0
@@ -463,7 +465,10 @@ def run_gram(args, rank, world, local):
         ach = (flops or 0) * float(m) * n / (ms_per_step * 1e-3) / 1e12 if flops else None
         roof = {"bound": "fp64", "achieved": ach, "peak": tf.value, "unit": "TFLOP/s",
                 "frac": (ach / tf.value) if ach else None, "traffic": None,
-                "note": "algorithmic convention of SURVEY.md 8d: 32 flops per quadrature node (one exp = 28); the kernel "
+                "algorithmic_flops_per_entry": flops,
+                "note": ("SURVEY.md 8d: 10 x (6 + 4 n_eff) flops per entry, n_eff = %d retained cosine terms per circle "
+                         "factor (of the reference's 201)" % ((flops // 10 - 6) // 4)) if args.workload == "gram-t10" else
+                        "algorithmic convention of SURVEY.md 8d: 32 flops per quadrature node (one exp = 28); the kernel "
                         "executes fewer (factorised exponentials), so frac can exceed what the pipe sustains",
                 "peak_source": "DFMA micro-benchmark in this run"}
     else:

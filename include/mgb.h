@@ -58,6 +58,9 @@ typedef struct {
   int n_terms;      /* T in [1, MGB_MAX_TERMS] */
   int basis;        /* MGB_BASIS_* */
   double scale, shift, lo, hi;
+  int pair_square;  /* 0: u = scale * <x1, x2> + shift;  1: u = scale * <x1, x2>^2 + shift (forward only).
+                       SO(3) through unit quaternions: (tr(R1 R2^T) - 1) / 2 = 2 <q1, q2>^2 - 1, so rows of 4
+                       (mgb_so3_to_quaternion) with scale 2, shift -1 replace rows of 9 with scale 1/2, shift -1/2 */
 } mgb_series_desc;
 
 int mgb_series_gram_fwd(const mgb_series_desc* desc, const double* x1, long long m, long long ld1,
@@ -73,6 +76,13 @@ int mgb_series_gram_bwd(const mgb_series_desc* desc, const double* x1, long long
                         const double* x2, long long n, long long ld2, const double* coef,
                         const double* G, long long ldg_row, long long ldg_col,
                         double* gcoef, double* gx1, double* gx2, void* stream);
+
+/* Rotation matrices (rows of 9, row-major 3 x 3) -> unit quaternions (rows of 4: w, x, y, z) by Shepperd's method, for
+ * the pair_square form of the SO(3) kernels.  *defect (device scalar, caller zeroes) receives the maximum over rows
+ * of max(|R R^T - I|_max, |det R - 1|): the identity above holds only for rotations, so the caller falls back to
+ * the 9-wide form when the inputs are not orthogonal to rounding (kernel_utils/kernels_so.py:323-327 evaluates the
+ * trace formula on whatever matrices it is given). */
+int mgb_so3_to_quaternion(const double* R, long long m, long long ld, double* Q, double* defect, void* stream);
 
 /* Second-order support for trust-region Hessian-vector products (pymanopt_addons/tools/autodiff/
  * _pytorch.py:92-116): same contraction as gx1 of the backward but with the k-th derivative of p_f,
@@ -240,7 +250,8 @@ int mgb_series_posterior_host(const mgb_series_desc* desc, const double* xc, lon
 
 /* ------------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): register-resident FP64 peak micro-benchmarks, result in TFLOP/s.
- * kind 0 = DFMA chains, 1 = DMMA m8n8k4 chains.  Synchronises.
+ * kind 0 = DFMA chains, 1 = DMMA m8n8k4 chains, 2 = both interleaved with equal FMA counts (do the two
+ * instruction kinds share one FP64 data path?).  Synchronises.
  * ------------------------------------------------------------------------------------------------ */
 int mgb_fp64_peak(int kind, int repeats, double* tflops, double* elapsed_ms);
 

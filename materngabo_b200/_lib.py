@@ -22,7 +22,8 @@ MAX_TERMS = 256
 
 class SeriesDesc(C.Structure):
     _fields_ = [("n_factors", C.c_int), ("factor_width", C.c_int), ("n_terms", C.c_int), ("basis", C.c_int),
-                ("scale", C.c_double), ("shift", C.c_double), ("lo", C.c_double), ("hi", C.c_double)]
+                ("scale", C.c_double), ("shift", C.c_double), ("lo", C.c_double), ("hi", C.c_double),
+                ("pair_square", C.c_int)]
 
 
 _P = C.c_void_p
@@ -38,6 +39,7 @@ PROTOTYPES = {
     "mgb_launch_count": (_LL, []),
     "mgb_series_gram_fwd": (_I, [_DESC, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _LL, _P]),
     "mgb_series_gram_bwd": (_I, [_DESC, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _LL, _LL, _P, _P, _P, _P]),
+    "mgb_so3_to_quaternion": (_I, [_P, _LL, _LL, _P, _P, _P]),
     "mgb_series_gram_dx": (_I, [_DESC, _I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _LL, _LL, _P, _P, _P]),
     "mgb_hyperbolic_gram_fwd": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _I, _D, _D, _I, _P, _LL, _P]),
     "mgb_hyperbolic_gram_bwd_coef": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _I, _D, _D, _I, _P, _LL, _P, _P]),

@@ -28,10 +28,11 @@ class SeriesSpec:
     shift: float = 0.0
     lo: float = -1.0
     hi: float = 1.0
+    pair_square: int = 0
 
     def desc(self, n_terms: int) -> _lib.SeriesDesc:
         return _lib.SeriesDesc(self.n_factors, self.factor_width, n_terms, self.basis,
-                               self.scale, self.shift, self.lo, self.hi)
+                               self.scale, self.shift, self.lo, self.hi, self.pair_square)
 
 
 def _c2d(t: torch.Tensor) -> torch.Tensor:
@@ -172,6 +173,28 @@ def series_gram(spec: SeriesSpec, x1: torch.Tensor, x2: torch.Tensor, coef: torc
     """K (m x n) for 2-D inputs."""
     _lib.require_cuda_f64(x1, x2, coef)
     return SeriesGram.apply(spec, _c2d(x1), _c2d(x2), coef.contiguous())
+
+
+def so3_quaternions(*mats, tol: float = 1e-13):
+    """Flattened rotations (m x 9) -> unit quaternions (m x 4) for the pair_square form of the SO(3) kernels.
+    Returns None when any input is not a rotation to ``tol`` (max |R R^T - I|, |det R - 1| measured on the device):
+    the caller then keeps the 9-wide trace form, which is defined for arbitrary matrices as in the reference.
+    Reading the defect synchronises the stream once - this path is meant for large Gram blocks."""
+    lib = _lib.load()
+    dev = mats[0].device
+    defect = torch.zeros(1, dtype=F64, device=dev)
+    outs = []
+    with torch.cuda.device(dev):
+        for x in mats:
+            x = _c2d(x)
+            q = torch.empty((x.shape[0], 4), dtype=F64, device=dev)
+            rc = lib.mgb_so3_to_quaternion(_lib.ptr(x), x.shape[0], x.stride(0), _lib.ptr(q), _lib.ptr(defect),
+                                           _lib.stream_ptr(dev))
+            _lib.check(rc, "mgb_so3_to_quaternion")
+            outs.append(q)
+    if float(defect) > tol:
+        return None
+    return outs
 
 
 # --------------------------------------------------------------------------------------------------

@@ -178,13 +178,16 @@ def sphere_integrated_matern_coef(lengthscale, nu, dim, cst, zero_g, nb_points):
 # circle S^1 / torus  (kernels_sphere.py:443-472, 551-614; kernels_torus.py)
 # --------------------------------------------------------------------------------------------------
 THETA3_TERMS = 200  # hard-wired in the reference (math_utils/jacobi_theta_functions.py:16)
-_TRUNC = 1e-20      # cosine terms below this fraction of the constant term cannot change a float64 result
+_TRUNC = 1e-16      # dropped tail: sum |c_n| below this fraction of sum |c| (|T_n| <= 1, so the kernel value moves by
+                    # less than half an ulp of its own scale - far inside the 1e-10 parity bar and the rounding of the
+                    # reference's own 201-term float64 sum)
 
 
 def _truncate(c: torch.Tensor) -> int:
-    mag = (c.detach().abs() / c.detach().abs()[0]).cpu()
-    keep = torch.nonzero(mag > _TRUNC).max().item() + 1
-    return max(int(keep), 2)
+    mag = c.detach().abs().cpu()
+    tail = torch.flip(torch.cumsum(torch.flip(mag, [0]), 0), [0])     # tail[k] = sum_{n >= k} |c_n|
+    keep = int(torch.nonzero(tail > _TRUNC * tail[0]).max().item()) + 1
+    return max(keep, 2)
 
 
 def circle_gaussian_coef(lengthscale):

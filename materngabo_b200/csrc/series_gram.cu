@@ -39,6 +39,7 @@ struct SeriesParams {
   int row_splits;       // CTAs per column chunk; CTA s walks row panels s, s + row_splits, ...
   int tiled;            // 1: write the tile-major swizzled layout consumed by posterior_reduce_kernel
   long long nch;        // tiled: 16-column chunks per row (n rounded up to 16, / 16)
+  int square;           // u = scale * dot^2 + shift instead of scale * dot + shift (mgb_series_desc::pair_square)
 };
 
 // Address of K[grow][col].  Row-major, or the posterior's operand layout: 128 x 16 blocks stored
@@ -123,13 +124,16 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
   for (int k = 0; k < TREG; ++k) c[k] = (k < p.T) ? __ldg(p.coef + k) : 0.0;
 
   const long long col = cc * kTN + 2 * lane;
+  // square mode: sqrt(scale) is folded into x2 and u = dot * dot + shift
+  const double fold = p.square ? sqrt(p.scale) : p.scale;
+  const double init = p.square ? 0.0 : p.shift;
   double xa[W], xb[W];
   {
     const bool va = col < p.n, vb = col + 1 < p.n;
 #pragma unroll
     for (int k = 0; k < W; ++k) {
-      xa[k] = va ? p.scale * __ldg(p.x2 + col * p.ld2 + k) : 0.0;
-      xb[k] = vb ? p.scale * __ldg(p.x2 + (col + 1) * p.ld2 + k) : 0.0;
+      xa[k] = va ? fold * __ldg(p.x2 + col * p.ld2 + k) : 0.0;
+      xb[k] = vb ? fold * __ldg(p.x2 + (col + 1) * p.ld2 + k) : 0.0;
     }
   }
   if (threadIdx.x == 0) {
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
     if (r >= rows) break;
     double ua[RB], ub[RB];
 #pragma unroll
-    for (int q = 0; q < RB; ++q) ua[q] = ub[q] = p.shift;
+    for (int q = 0; q < RB; ++q) ua[q] = ub[q] = init;
     if constexpr (kRowsInRegs) {
       double v[RB * W];
       const double2* src = reinterpret_cast<const double2*>(x1s + r * W);  // r % RB == 0 -> 16-byte aligned
@@ -200,6 +204,13 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
           ua[q] = fma(v, xa[k], ua[q]);
           ub[q] = fma(v, xb[k], ub[q]);
         }
+      }
+    }
+    if (p.square) {
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        ua[q] = fma(ua[q], ua[q], p.shift);
+        ub[q] = fma(ub[q], ub[q], p.shift);
       }
     }
     unsigned need = 0;
@@ -279,7 +290,10 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_mma(SeriesParams 
   for (int k = 0; k < TREG; ++k) c[k] = (k < p.T) ? __ldg(p.coef + k) : 0.0;
 
   // B fragments: element (k = 4 s + fk, n = frow) of column fragment b is scale * x2[col0 + 8 b + frow][k]
+  // (square mode: sqrt(scale) folded in, u = dot * dot + shift)
   const long long col0 = cc * kTN + 32 * wq;
+  const double fold = p.square ? sqrt(p.scale) : p.scale;
+  const double init = p.square ? 0.0 : p.shift;
   double bf[NB][KS];
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
@@ -287,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_mma(SeriesParams 
 #pragma unroll
     for (int sidx = 0; sidx < KS; ++sidx) {
       const int k = 4 * sidx + fk;
-      bf[b][sidx] = (cj < p.n && k < W) ? p.scale * __ldg(p.x2 + cj * p.ld2 + k) : 0.0;
+      bf[b][sidx] = (cj < p.n && k < W) ? fold * __ldg(p.x2 + cj * p.ld2 + k) : 0.0;
     }
   }
   if (threadIdx.x == 0) {
@@ -334,10 +348,17 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_mma(SeriesParams 
       }
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
-        o0[b] = p.shift;
-        o1[b] = p.shift;
+        o0[b] = init;
+        o1[b] = init;
 #pragma unroll
         for (int sidx = 0; sidx < KS; ++sidx) dmma884(o0[b], o1[b], af[sidx], bf[b][sidx]);
+      }
+      if (p.square) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          o0[b] = fma(o0[b], o0[b], p.shift);
+          o1[b] = fma(o1[b], o1[b], p.shift);
+        }
       }
     };
     inner_products(0, u0[0], u1[0]);
@@ -489,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_general(SeriesPar
         unsigned need = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          u[q] = fma(d[q], p.scale, p.shift);
+          u[q] = fma(p.square ? d[q] * d[q] : d[q], p.scale, p.shift);
           need |= (unsigned)(((unsigned)__double2hiint(u[q]) & 0x7fffffffu) >= p.clamp_word);
         }
         if (need) {
@@ -742,6 +763,55 @@ static int dispatch_fast(const SeriesParams& p, long long tiles, cudaStream_t s,
 
 using namespace mgb;
 
+// Shepperd's method; one thread per rotation.  defect: max(|R R^T - I|_max, |det R - 1|) over all rows (atomicMax on
+// the bit pattern: non-negative doubles order like unsigned integers).
+__global__ void __launch_bounds__(256) so3_quat_kernel(const double* __restrict__ R, long long m, long long ld,
+                                                       double* __restrict__ Q, double* defect) {
+  double worst = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+    const double* r = R + i * ld;
+    const double a = r[0], b = r[1], c = r[2], d = r[3], e = r[4], f = r[5], g = r[6], h = r[7], k = r[8];
+    const double tr = a + e + k;
+    double w, x, y, z;
+    if (tr >= a && tr >= e && tr >= k) {
+      w = 1.0 + tr; x = h - f; y = c - g; z = d - b;
+    } else if (a >= e && a >= k) {
+      w = h - f; x = 1.0 + a - e - k; y = b + d; z = c + g;
+    } else if (e >= k) {
+      w = c - g; x = b + d; y = 1.0 - a + e - k; z = f + h;
+    } else {
+      w = d - b; x = c + g; y = f + h; z = 1.0 - a - e + k;
+    }
+    const double inv = rsqrt(w * w + x * x + y * y + z * z);
+    double* q = Q + i * 4;
+    q[0] = w * inv; q[1] = x * inv; q[2] = y * inv; q[3] = z * inv;
+    double dv = fabs(a * a + b * b + c * c - 1.0);
+    dv = fmax(dv, fabs(d * d + e * e + f * f - 1.0));
+    dv = fmax(dv, fabs(g * g + h * h + k * k - 1.0));
+    dv = fmax(dv, fabs(a * d + b * e + c * f));
+    dv = fmax(dv, fabs(a * g + b * h + c * k));
+    dv = fmax(dv, fabs(d * g + e * h + f * k));
+    const double det = a * (e * k - f * h) - b * (d * k - f * g) + c * (d * h - e * g);
+    dv = fmax(dv, fabs(det - 1.0));
+    if (!(dv == dv)) dv = 1.0;   // NaN input: not a rotation
+    worst = fmax(worst, dv);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+  if ((threadIdx.x & 31) == 0 && worst > 0.0)
+    atomicMax(reinterpret_cast<unsigned long long*>(defect), (unsigned long long)__double_as_longlong(worst));
+}
+
+extern "C" int mgb_so3_to_quaternion(const double* R, long long m, long long ld, double* Q, double* defect,
+                                     void* stream) {
+  if (m < 0 || ld < 9 || !defect || (m > 0 && (!R || !Q))) return fail(MGB_ERR_ARG, "so3_to_quaternion: bad argument");
+  if (m == 0) return MGB_OK;
+  long long blocks = (m + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  so3_quat_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(R, m, ld, Q, defect);
+  return after_launch("so3_quat_kernel");
+}
+
 static int series_sm_count() {
   static int sms = 0;
   if (sms == 0) {
@@ -761,7 +831,9 @@ static int series_fwd_impl(const mgb_series_desc* d, const double* x1, long long
   if (tiled && (reinterpret_cast<uintptr_t>(K) & 15u)) return fail(MGB_ERR_ARG, "series_gram_tiled: K must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SeriesParams p{x1, m, ld1, x2, n, ld2, coef, K, ldk, d->n_factors, d->factor_width, d->n_terms,
-                 d->scale, d->shift, d->lo, d->hi, (n + kTN - 1) / kTN, 0u, 1, tiled, (n + 15) / 16};
+                 d->scale, d->shift, d->lo, d->hi, (n + kTN - 1) / kTN, 0u, 1, tiled, (n + 15) / 16,
+                 d->pair_square ? 1 : 0};
+  if (d->pair_square && !(d->scale > 0.0)) return fail(MGB_ERR_ARG, "series_gram_fwd: pair_square needs scale > 0");
   if (d->lo < 0.0 && d->hi > 0.0) {
     const double bound = fmin(-d->lo, d->hi);
     unsigned long long bits;
@@ -836,6 +908,7 @@ extern "C" int mgb_series_gram_bwd(const mgb_series_desc* d, const double* x1, l
                                    long long ldg_row, long long ldg_col, double* gcoef, double* gx1, double* gx2,
                                    void* stream) {
   MGB_TRY(validate(d, x1, m, ld1, x2, n, ld2, coef));
+  if (d->pair_square) return fail(MGB_ERR_ARG, "series_gram_bwd: pair_square is a forward-only form");
   if (!G) return fail(MGB_ERR_ARG, "series_gram_bwd: null G");
   if (d->factor_width > kBwdMaxW) return fail(MGB_ERR_ARG, "series_gram_bwd: factor width > 32");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -849,6 +922,7 @@ extern "C" int mgb_series_gram_dx(const mgb_series_desc* d, int order, const dou
                                   const double* x2, long long n, long long ld2, const double* coef, const double* G,
                                   long long ldg_row, long long ldg_col, double* out1, double* out2, void* stream) {
   MGB_TRY(validate(d, x1, m, ld1, x2, n, ld2, coef));
+  if (d->pair_square) return fail(MGB_ERR_ARG, "series_gram_dx: pair_square is a forward-only form");
   if (!G) return fail(MGB_ERR_ARG, "series_gram_dx: null G");
   if (order != 1 && order != 2) return fail(MGB_ERR_ARG, "series_gram_dx: order must be 1 or 2");
   if (d->n_factors != 1) return fail(MGB_ERR_ARG, "series_gram_dx: single-factor kernels only");

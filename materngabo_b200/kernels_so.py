@@ -16,6 +16,7 @@ from .gpytorch_compat import Kernel
 from .kernels_sphere import _NuMixin, _check_batch, _series_on
 
 _SO3_CLIP = 1.0 - 1e-8  # kernels_so.py:325
+QUATERNION_MIN_ENTRIES = 1 << 22  # Gram blocks at least this large go through the quaternion form (one stream sync)
 
 
 class _SOSeriesKernel(Kernel):
@@ -36,6 +37,17 @@ class _SOSeriesKernel(Kernel):
         if x1.shape[-1] != 9 or x2.shape[-1] != 9:
             raise RuntimeError("SO(3) points must be flattened 3x3 rotation matrices (9 coordinates)")
         spec, coef = _series_on(self, x1.device)
+        big = (not diag and x1.dim() == 2 and x2.dim() == 2
+               and x1.shape[0] * x2.shape[0] >= QUATERNION_MIN_ENTRIES
+               and not _ops.inputs_need_grad(x1, x2, coef))
+        if big:
+            # (tr(R1 R2^T) - 1) / 2 = 2 <q1, q2>^2 - 1: rows of 4 instead of 9 for the inner products (the FP64 pipe,
+            # not HBM, bounds the 9-wide form).  Only for inputs that are rotations to 1e-13; otherwise the trace form.
+            quats = _ops.so3_quaternions(x1, x2)
+            if quats is not None:
+                spec4 = _ops.SeriesSpec(1, 4, spec.basis, 2.0, -1.0, spec.lo, spec.hi, 1)
+                with torch.no_grad():
+                    return _ops._series_fwd_raw(spec4, quats[0], quats[1], coef.detach().contiguous())
         return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1, x2, diag=diag)
 
 

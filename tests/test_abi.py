@@ -26,7 +26,7 @@ def test_header_symbols_are_exported_and_typed():
 
 def test_loader_and_version():
     lib = _lib.load()
-    assert lib.mgb_version() == 100
+    assert lib.mgb_version() == 101
     assert lib.mgb_launch_count() >= 0
     assert lib.mgb_posterior_pack_bytes(5000) == 5120 * 5008 * 8
     assert lib.mgb_posterior_workspace_bytes(128, 100) == (128 * 112 + 128) * 8 + lib.mgb_posterior_reduce_workspace_bytes(128, 100)
@@ -35,8 +35,9 @@ def test_loader_and_version():
 
 def test_series_desc_layout_matches_header():
     d = _lib.SeriesDesc(1, 3, 10, 0, 1.0, 0.0, -1.0, 1.0)
-    assert ctypes.sizeof(d) == 4 * 4 + 4 * 8
-    assert (d.n_factors, d.factor_width, d.n_terms, d.basis) == (1, 3, 10, 0)
+    assert ctypes.sizeof(d) == 4 * 4 + 4 * 8 + 8             # 4 ints, 4 doubles, pair_square + tail padding
+    assert (d.n_factors, d.factor_width, d.n_terms, d.basis, d.pair_square) == (1, 3, 10, 0, 0)
+    assert _lib.SeriesDesc.pair_square.offset == 48
 
 
 def test_product_has_no_oracle_dependency():

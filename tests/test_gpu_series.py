@@ -259,6 +259,15 @@ def test_config1_full_size_vs_oracle():
     assert torch.linalg.eigvalsh(out + 1e-8 * torch.eye(1000, device=DEV)).min() > 0  # PD (kernels_so.py:365-400 style check)
 
 
+def _forced_trace(kso, k, a, b):
+    saved = kso.QUATERNION_MIN_ENTRIES
+    try:
+        kso.QUATERNION_MIN_ENTRIES = 1 << 62
+        return k.forward(a, b)
+    finally:
+        kso.QUATERNION_MIN_ENTRIES = saved
+
+
 def test_large_gram_properties():
     """Size-independent checks at a size the oracle cannot reach: row blocks of a 200k x 2k SO(3) Gram agree with
     the same rows computed alone, and a sampled set of entries agrees with the oracle."""
@@ -278,7 +287,21 @@ def test_large_gram_properties():
     assert big.shape == (200000, 2000)
     rows = torch.tensor([0, 1, 127, 128, 99999, 199999])
     small = k.forward(xc[rows.to(DEV)], base.to(DEV))
-    assert torch.equal(big[rows.to(DEV)], small)              # tiling does not change values
+    # the large block goes through the quaternion form of the inner product, the 6-row block through the trace form
+    assert rel_err(big[rows.to(DEV)], small) < 1e-13
+    saved = kso.QUATERNION_MIN_ENTRIES
+    try:
+        kso.QUATERNION_MIN_ENTRIES = 1 << 62                  # force the 9-wide trace form
+        big9 = k.forward(xc[:20000], base.to(DEV))
+        assert torch.equal(big9[rows[:4].to(DEV)], small[:4])  # tiling does not change values
+        assert rel_err(big[:20000], big9) < 1e-13
+        kso.QUATERNION_MIN_ENTRIES = saved
+        # inputs that are not rotations (here: drifted by 1e-6) must keep the reference's trace semantics exactly
+        bad = xc[:20000].clone()
+        bad[5] += 1e-6
+        assert torch.equal(k.forward(bad, base.to(DEV)), _forced_trace(kso, k, bad, base.to(DEV)))
+    finally:
+        kso.QUATERNION_MIN_ENTRIES = saved
     ref = R.so3_matern(base[idx[rows]], base[:300], 2.5, 0.5)
     assert rel_err(big[rows.to(DEV)][:, :300], ref) < TOL
     assert torch.isfinite(big).all()
