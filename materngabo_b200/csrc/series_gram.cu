@@ -411,6 +411,178 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_mma(SeriesParams 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-autonomous variant of the tensor-pipe kernel.  Same tiling, fragment mapping and arithmetic order as
+// series_gram_fwd_mma (results are bit-identical), but every warp stages ITS OWN 32-row slice of the x1 panel
+// (32 x W doubles, contiguous in HBM) with its own cp.async.bulk + mbarrier pair, double buffered, and never meets
+// the other warps at a CTA barrier.  Why: DFMA and DMMA share one FP64 data path (tools/probe_peaks.py), and with
+// only 2 CTAs x 8 warps per SM the per-panel __syncthreads of the CTA-staged version keeps the warps of a CTA in
+// phase - they do address arithmetic, loads and stores together and leave the FP64 pipe idle together (ncu: pipe
+// busy 2/3 of the time).  Autonomous warps drift out of phase and fill each other's gaps.
+// ---------------------------------------------------------------------------------------------
+template <int W, int TREG>
+__global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_warp(SeriesParams p) {
+  constexpr int KS = (W + 3) / 4;
+  constexpr int NB = 4;
+  constexpr int NA = 4;
+  constexpr int RBLK = 32;                     // rows per warp per panel
+  constexpr int kWarps = kThreads / 32;
+  extern __shared__ __align__(16) double smem[];   // [warp][2][RBLK * W]
+  __shared__ __align__(8) uint64_t bars[kWarps][2];
+
+  const long long cc = blockIdx.x % p.ncc;
+  const int split = (int)(blockIdx.x / p.ncc);
+  const long long npanels = (p.m + kTM - 1) / kTM;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int frow = lane >> 2, fk = lane & 3;
+  const int wr = warp >> 1;
+  const int wq = warp & 1;
+
+  double c[TREG];
+#pragma unroll
+  for (int k = 0; k < TREG; ++k) c[k] = (k < p.T) ? __ldg(p.coef + k) : 0.0;
+
+  const long long col0 = cc * kTN + 32 * wq;
+  const double fold = p.square ? sqrt(p.scale) : p.scale;
+  const double init = p.square ? 0.0 : p.shift;
+  double bf[NB][KS];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const long long cj = col0 + 8 * b + frow;
+#pragma unroll
+    for (int sidx = 0; sidx < KS; ++sidx) {
+      const int k = 4 * sidx + fk;
+      bf[b][sidx] = (cj < p.n && k < W) ? fold * __ldg(p.x2 + cj * p.ld2 + k) : 0.0;
+    }
+  }
+  if (col0 >= p.n) return;                     // nothing to write for this warp (ragged last column chunk)
+  uint64_t* mybar = bars[warp];
+  if (lane == 0) {
+    mbar_init(&mybar[0], 1);
+    mbar_init(&mybar[1], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  double* wbuf = smem + (size_t)warp * 2 * RBLK * W;
+  const bool can_bulk = (p.ld1 == W) && ((reinterpret_cast<uintptr_t>(p.x1) & 15u) == 0);
+
+  // stage rows [rp*128 + 32 wr, +32) into buffer b; returns true when the copy completes on the mbarrier
+  auto stage = [&](long long rp, int b) -> bool {
+    const long long r0 = rp * kTM + RBLK * wr;
+    const long long left = p.m - r0;
+    double* dst = wbuf + b * (RBLK * W);
+    if (left >= RBLK && can_bulk) {
+      if (lane == 0) {
+        mbar_expect_tx(&mybar[b], RBLK * W * 8u);
+        bulk_g2s(dst, p.x1 + r0 * p.ld1, RBLK * W * 8u, &mybar[b]);
+      }
+      return true;
+    }
+    const int rows = left < 0 ? 0 : (left < RBLK ? (int)left : RBLK);
+    for (int e = lane; e < RBLK * W; e += 32) {
+      const int r = e / W, k = e - r * W;
+      dst[e] = (r < rows) ? p.x1[(r0 + r) * p.ld1 + k] : 0.0;
+    }
+    __syncwarp();
+    return false;
+  };
+
+  const bool aligned = p.tiled || (((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0));
+  const unsigned thr = p.clamp_word;
+
+  long long rp = split;
+  if (rp >= npanels) return;
+  unsigned parity = 0;
+  bool bulk_cur = stage(rp, 0);
+  for (int it = 0; rp < npanels; rp += p.row_splits, ++it) {
+    const int buf = it & 1;
+    const double* x1s = wbuf + buf * (RBLK * W);
+    const long long row0 = rp * kTM + RBLK * wr;
+    const long long left = p.m - row0;
+    const int rows = left < 0 ? 0 : (left < RBLK ? (int)left : RBLK);
+    const long long rp_next = rp + p.row_splits;
+    bool bulk_next = false;
+    if (rp_next < npanels) bulk_next = stage(rp_next, buf ^ 1);   // every lane finished with buf^1 at the __syncwarp below
+    if (bulk_cur) {
+      while (!mbar_try_wait(&mybar[buf], (parity >> buf) & 1u)) {
+      }
+      parity ^= 1u << buf;
+    }
+    if (rows > 0) {
+      double u0[2][NB], u1[2][NB];
+      auto inner_products = [&](int a, double (&o0)[NB], double (&o1)[NB]) {
+        const int r = 8 * a + frow;
+        double af[KS];
+#pragma unroll
+        for (int sidx = 0; sidx < KS; ++sidx) {
+          const int k = 4 * sidx + fk;
+          af[sidx] = (k < W) ? x1s[r * W + k] : 0.0;
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          o0[b] = init;
+          o1[b] = init;
+#pragma unroll
+          for (int sidx = 0; sidx < KS; ++sidx) dmma884(o0[b], o1[b], af[sidx], bf[b][sidx]);
+        }
+        if (p.square) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            o0[b] = fma(o0[b], o0[b], p.shift);
+            o1[b] = fma(o1[b], o1[b], p.shift);
+          }
+        }
+      };
+      inner_products(0, u0[0], u1[0]);
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int cur = a & 1;
+        if (a + 1 < NA) inner_products(a + 1, u0[cur ^ 1], u1[cur ^ 1]);
+        unsigned need = 0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          need |= (unsigned)(((unsigned)__double2hiint(u0[cur][b]) & 0x7fffffffu) >= thr);
+          need |= (unsigned)(((unsigned)__double2hiint(u1[cur][b]) & 0x7fffffffu) >= thr);
+        }
+        if (need) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            u0[cur][b] = clamp_exact(u0[cur][b], p.lo, p.hi);
+            u1[cur][b] = clamp_exact(u1[cur][b], p.lo, p.hi);
+          }
+        }
+        double p0[NB], p1[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) p0[b] = p1[b] = c[TREG - 1];
+#pragma unroll
+        for (int k = TREG - 2; k >= 0; --k) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            p0[b] = fma(p0[b], u0[cur][b], c[k]);
+            p1[b] = fma(p1[b], u1[cur][b], c[k]);
+          }
+        }
+        const int r = 8 * a + frow;
+        if (r < rows) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const long long col = col0 + 8 * b + 2 * fk;
+            double* out = out_ptr(p, row0 + r, col);
+            if (aligned && col + 1 < p.n) {
+              st_keep2(out, p0[b], p1[b], p.tiled);
+            } else {
+              if (col < p.n) st_stream(out, p0[b]);
+              if (col + 1 < p.n) st_stream(out + 1, p1[b]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    bulk_cur = bulk_next;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // General path: F factors of runtime width W, T terms per factor, either basis; coefficients and the
 // transposed x2 panel in shared memory.  Each thread evaluates 2 columns x 2 rows per coefficient read.
 // ---------------------------------------------------------------------------------------------
@@ -721,23 +893,40 @@ static int launch_mma(const SeriesParams& p, long long tiles, cudaStream_t s) {
   return after_launch("series_gram_fwd_mma");
 }
 
-// 0 = DFMA inner products, 1 = DMMA inner products.  Default: DMMA wherever it is instantiated - measured on B200
+template <int W, int TREG>
+static int launch_warp(const SeriesParams& p, long long tiles, cudaStream_t s) {
+  const size_t smem = sizeof(double) * (kThreads / 32) * 2 * 32 * W;
+  series_gram_fwd_warp<W, TREG><<<(unsigned)tiles, kThreads, smem, s>>>(p);
+  return after_launch("series_gram_fwd_warp");
+}
+
+// 0 = DFMA inner products, 1 = DMMA inner products (CTA-staged panels), 2 = DMMA, warp-autonomous staging.  Default: DMMA wherever it is instantiated - measured on B200
 // (1M x 2k): S^2 6.95e11 vs 6.38e11 entries/s, S^10 5.46e11 vs 4.46e11, SO(3) 5.28e11 vs 4.65e11 (profiles/).
-// MGB_SERIES_PATH=dfma|mma overrides (tuning knob).
+// MGB_SERIES_PATH=dfma|mma|warp overrides (tuning knob).
 static int series_path(int W) {
   static int forced = -2;
   if (forced == -2) {
     const char* e = getenv("MGB_SERIES_PATH");
-    forced = (e == nullptr) ? -1 : (strcmp(e, "mma") == 0 ? 1 : (strcmp(e, "dfma") == 0 ? 0 : -1));
+    forced = (e == nullptr) ? -1 : (strcmp(e, "warp") == 0 ? 2 : (strcmp(e, "mma") == 0 ? 1 : (strcmp(e, "dfma") == 0 ? 0 : -1)));
   }
   if (forced >= 0) return forced;
   (void)W;
-  return 1;
+  return 2;   // measured on B200, 1M x 2k: S^2 7.01e11 vs 6.79e11 entries/s, SO(3) (quaternion form) 6.26e11 vs 6.05e11,
+              // S^10 5.58e11 vs 5.56e11 (gpurun_out/series_paths2.log)
 }
 
 template <int TREG>
 static int dispatch_fast(const SeriesParams& p, long long tiles, cudaStream_t s, bool* handled) {
   *handled = true;
+  if (series_path(p.W) == 2) {
+    switch (p.W) {
+      case 3: return launch_warp<3, TREG>(p, tiles, s);
+      case 4: return launch_warp<4, TREG>(p, tiles, s);
+      case 9: return launch_warp<9, TREG>(p, tiles, s);
+      case 11: return launch_warp<11, TREG>(p, tiles, s);
+      default: break;
+    }
+  }
   if (series_path(p.W) == 1) {
     switch (p.W) {
       case 3: return launch_mma<3, TREG>(p, tiles, s);
