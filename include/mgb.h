@@ -146,6 +146,15 @@ int mgb_spd2_gram_fwd(int use_cholesky, const double* x1, long long m, long long
                       long long n, long long ld2, const double* tcoef, const double* rscale,
                       const double* bscale, int Pt, const double* bval, const double* bw, int Pb,
                       double* K, long long ldk, void* stream);
+/* Same result as mgb_spd2_gram_fwd for geometric grids whose log-steps are commensurate:
+ *   bval[b] * bscale[a] = g_min * exp(log_tau * (sb * b + sa * (Pt - 1 - a)))   for all a < Pt, b < Pb
+ * (the reference's grids, kernels_spd.py:262-265: 12 : 7 when Pb == Pt).  The pair-dependent exponential
+ * exp(-Delta bval[b] bscale[a]) is then evaluated once per lattice point instead of once per node.  The caller
+ * verifies the lattice (host side, materngabo_b200/kernels_spd.py); Pt <= 64. */
+int mgb_spd2_gram_fwd_lattice(int use_cholesky, const double* x1, long long m, long long ld1, const double* x2,
+                              long long n, long long ld2, const double* tcoef, const double* rscale,
+                              const double* bscale, int Pt, const double* bval, const double* bw, int Pb,
+                              int sb, int sa, double g_min, double log_tau, double* K, long long ldk, void* stream);
 /* g_rscale[a] += dL/drscale[a], g_bscale[a] += dL/dbscale[a] (caller zeroes): lengthscale gradient of the SPD(2) heat
  * kernel, whose scales 1/(2 kappa^2), 1/kappa^2 are differentiable */
 int mgb_spd2_gram_bwd_scales(int use_cholesky, const double* x1, long long m, long long ld1, const double* x2,

@@ -326,18 +326,30 @@ def euclidean_gram(x1, x2, tval, tcoef):
     return EuclideanGram.apply(_c2d(x1), _c2d(x2), tval.contiguous(), tcoef.contiguous())
 
 
+SPD2_LATTICE_MIN_ENTRIES = 4096   # below this the per-CTA table set-up of the lattice kernel does not pay
+
+
 class Spd2Gram(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, use_chol, x1, x2, tcoef, rscale, bscale, bval, bw):
+    def forward(ctx, use_chol, x1, x2, tcoef, rscale, bscale, bval, bw, lattice=None):
         lib = _lib.load()
         m, n = x1.shape[0], x2.shape[0]
         k = torch.empty((m, n), dtype=F64, device=x1.device)
         with torch.cuda.device(x1.device):
-            rc = lib.mgb_spd2_gram_fwd(use_chol, _lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0),
-                                       _lib.ptr(tcoef), _lib.ptr(rscale), _lib.ptr(bscale), tcoef.shape[0],
-                                       _lib.ptr(bval), _lib.ptr(bw), bval.shape[0], _lib.ptr(k), max(n, 1),
-                                       _lib.stream_ptr(x1.device))
-        _lib.check(rc, "mgb_spd2_gram_fwd")
+            if lattice is not None and m * n >= SPD2_LATTICE_MIN_ENTRIES:
+                sb, sa, g_min, log_tau = lattice
+                rc = lib.mgb_spd2_gram_fwd_lattice(use_chol, _lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0),
+                                                   _lib.ptr(tcoef), _lib.ptr(rscale), _lib.ptr(bscale), tcoef.shape[0],
+                                                   _lib.ptr(bval), _lib.ptr(bw), bval.shape[0], int(sb), int(sa),
+                                                   float(g_min), float(log_tau), _lib.ptr(k), max(n, 1),
+                                                   _lib.stream_ptr(x1.device))
+                _lib.check(rc, "mgb_spd2_gram_fwd_lattice")
+            else:
+                rc = lib.mgb_spd2_gram_fwd(use_chol, _lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0),
+                                           _lib.ptr(tcoef), _lib.ptr(rscale), _lib.ptr(bscale), tcoef.shape[0],
+                                           _lib.ptr(bval), _lib.ptr(bw), bval.shape[0], _lib.ptr(k), max(n, 1),
+                                           _lib.stream_ptr(x1.device))
+                _lib.check(rc, "mgb_spd2_gram_fwd")
         ctx.use_chol = use_chol
         ctx.save_for_backward(x1, x2, tcoef, rscale, bscale, bval, bw)
         return k
@@ -349,7 +361,7 @@ class Spd2Gram(torch.autograd.Function):
             raise NotImplementedError("input gradients of the SPD quadrature kernels are not implemented yet")
         need_c, need_s = ctx.needs_input_grad[3], (ctx.needs_input_grad[4] or ctx.needs_input_grad[5])
         if not (need_c or need_s):
-            return (None,) * 8
+            return (None,) * 9
         lib = _lib.load()
         x1, x2, tcoef, rscale, bscale, bval, bw = ctx.saved_tensors
         g = g.contiguous()
@@ -370,13 +382,13 @@ class Spd2Gram(torch.autograd.Function):
                                                   bval.shape[0], _lib.ptr(g), g.stride(0), _lib.ptr(gr), _lib.ptr(gb),
                                                   _lib.stream_ptr(x1.device))
                 _lib.check(rc, "mgb_spd2_gram_bwd_scales")
-        return None, None, None, gc, gr, gb, None, None
+        return None, None, None, gc, gr, gb, None, None, None
 
 
-def spd2_gram(use_chol, x1, x2, tcoef, rscale, bscale, bval, bw):
+def spd2_gram(use_chol, x1, x2, tcoef, rscale, bscale, bval, bw, lattice=None):
     _lib.require_cuda_f64(x1, x2, tcoef, rscale, bscale, bval, bw)
     return Spd2Gram.apply(int(use_chol), _c2d(x1), _c2d(x2), tcoef.contiguous(), rscale.contiguous(),
-                          bscale.contiguous(), bval.contiguous(), bw.contiguous())
+                          bscale.contiguous(), bval.contiguous(), bw.contiguous(), lattice)
 
 
 # --------------------------------------------------------------------------------------------------

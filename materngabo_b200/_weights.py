@@ -258,7 +258,7 @@ def so3_gaussian_coef(lengthscale, summands):
 # --------------------------------------------------------------------------------------------------
 # quadrature kernels: node grids (detached, as the reference's .item()) and differentiable node weights
 # --------------------------------------------------------------------------------------------------
-def matern_t_nodes(lengthscale, nu, lo_exp, hi_exp, nb_points, power_offset=1.0):
+def matern_t_nodes(lengthscale, nu, lo_exp, hi_exp, nb_points, power_offset=1.0, return_shift=False):
     """t grid logspace(lo+log10 kappa, hi+log10 kappa, P) and the weights
     trapz_w * t^(nu - power_offset) * exp(-2 nu t / kappa^2)
     (kernels_hyperbolic.py:367-375, kernels_spd.py:262-264, kernels_euclidean.py:186-190)."""
@@ -266,4 +266,6 @@ def matern_t_nodes(lengthscale, nu, lo_exp, hi_exp, nb_points, power_offset=1.0)
     shift = torch.log10(ls).item()
     t = _logspace(lo_exp + shift, hi_exp + shift, nb_points, ls.device)
     w = trapz_weights(t) * torch.pow(t, nu - power_offset) * torch.exp(-2.0 * nu / ls ** 2 * t)
+    if return_shift:
+        return t, w, shift
     return t, w

@@ -376,6 +376,129 @@ __global__ void __launch_bounds__(QTHREADS) spd2_gram_kernel(SpdParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// SPD(2), lattice form of the forward kernel.  The reference's grids are both geometric (b = logspace(-5, 1, Pb),
+// t = logspace(.., .., Pt): kernels_spd.py:262-265), so the pair-dependent exponent of node (a, b),
+//     -b_b (b_b + Delta) bscale_a = -b_b^2 bscale_a  -  Delta * (b_b bscale_a),
+// has a pair-INDEPENDENT first part (table E[b][a], shared by the CTA) and a second part whose coefficient
+// b_b bscale_a = g_min tau^k lives on a one-dimensional lattice k = sb*b + sa*(Pt-1-a) whenever the two log-steps are
+// commensurate (12 : 7 for Pb = Pt).  A warp therefore evaluates exp(-Delta g_min tau^k) once per lattice point
+// (1198 exponentials for 64 x 64 nodes instead of 4096) and the node loop becomes two shared-memory reads, one
+// multiplication and one FMA per node.  Same nodes, same weights, same trapezoid sums as spd2_gram_kernel.
+// ------------------------------------------------------------------------------------------------
+struct SpdLatticeParams {
+  int use_chol;
+  const double* x1; long long m, ld1;
+  const double* x2; long long n, ld2;
+  const double* tcoef; const double* rscale; const double* bscale; int Pt;
+  const double* bval; const double* bw; int Pb;
+  int sb, sa, nk;
+  double g_min, log_tau;
+  double* K; long long ldk;
+};
+
+constexpr int LTHREADS = 384;   // 12 warps: per-warp lattice tables (nk + Pb doubles) keep it to one CTA per SM
+constexpr int LWARPS = LTHREADS / 32;
+constexpr int LNQ = 2;   // outer nodes per lane (Pt <= 64)
+
+__global__ void __launch_bounds__(LTHREADS, 1) spd2_lattice_kernel(SpdLatticeParams p) {
+  extern __shared__ __align__(16) double sm[];
+  // layout: E [Pb*Pt] | G [nk] | bv, bw, shb, chb [Pb each] | per warp: X [nk] | qb [Pb]
+  double* Es = sm;
+  double* Gs = Es + (size_t)p.Pb * p.Pt;
+  double* bv = Gs + p.nk;
+  double* bw = bv + p.Pb;
+  double* shb = bw + p.Pb;
+  double* chb = shb + p.Pb;
+  double* wbase = chb + p.Pb;
+  for (int e = threadIdx.x; e < p.Pb * p.Pt; e += blockDim.x) {
+    const int b = e / p.Pt, a = e - b * p.Pt;
+    const double bb = p.bval[b];
+    Es[e] = exp(-bb * bb * p.bscale[a]);
+  }
+  for (int k = threadIdx.x; k < p.nk; k += blockDim.x) Gs[k] = -p.g_min * exp(k * p.log_tau);
+  for (int e = threadIdx.x; e < p.Pb; e += blockDim.x) {
+    const double b = p.bval[e];
+    bv[e] = b;
+    bw[e] = p.bw[e];
+    shb[e] = sinh(b);
+    chb[e] = cosh(b);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* X = wbase + (size_t)warp * (p.nk + p.Pb);
+  double* qb = X + p.nk;
+  double tc[LNQ], rs[LNQ];
+  int koff[LNQ];
+#pragma unroll
+  for (int q = 0; q < LNQ; ++q) {
+    const int a = lane + 32 * q;
+    tc[q] = (a < p.Pt) ? p.tcoef[a] : 0.0;
+    rs[q] = (a < p.Pt) ? p.rscale[a] : 0.0;
+    koff[q] = (a < p.Pt) ? p.sa * (p.Pt - 1 - a) : 0;
+  }
+  const long long total = p.m * p.n;
+  const long long wstride = (long long)gridDim.x * LWARPS;
+  for (long long ebase = (long long)blockIdx.x * LWARPS + warp; ebase < total; ebase += 32 * wstride) {
+   // pair geometry of this warp's next 32 entries, one entry per lane (instead of 32 redundant copies per entry)
+   double g_delta = 0.0, g_r2 = 0.0, g_sh = 0.0, g_ch = 1.0;
+   {
+     const long long el = ebase + lane * wstride;
+     if (el < total) {
+       const long long il = el / p.n, jl = el - il * p.n;
+       double H1, H2;
+       spd2_logsv(p.x1 + il * p.ld1, p.x2 + jl * p.ld2, p.use_chol, H1, H2);
+       g_delta = H1 - H2;
+       g_r2 = H1 * H1 + H2 * H2;
+       g_sh = sinh(g_delta);
+       g_ch = cosh(g_delta);
+     }
+   }
+   for (int sub = 0; sub < 32; ++sub) {
+    const long long e = ebase + sub * wstride;
+    if (e >= total) break;
+    const long long i = e / p.n, j = e - i * p.n;
+    const double delta = __shfl_sync(0xffffffffu, g_delta, sub), r2 = __shfl_sync(0xffffffffu, g_r2, sub);
+    const double shd = __shfl_sync(0xffffffffu, g_sh, sub), chd = __shfl_sync(0xffffffffu, g_ch, sub);
+    __syncwarp();
+    // lattice exponentials, four independent chains per lane
+    int k = lane;
+    for (; k + 96 < p.nk; k += 128) {
+      const double e0 = exp(delta * Gs[k]), e1 = exp(delta * Gs[k + 32]);
+      const double e2 = exp(delta * Gs[k + 64]), e3 = exp(delta * Gs[k + 96]);
+      X[k] = e0; X[k + 32] = e1; X[k + 64] = e2; X[k + 96] = e3;
+    }
+    for (; k < p.nk; k += 32) X[k] = exp(delta * Gs[k]);
+    for (int b = lane; b < p.Pb; b += 32) {
+      const double bb = bv[b];
+      const double sbd = fma(shb[b], chd, chb[b] * shd);  // sinh(b + delta)
+      qb[b] = bw[b] * (2.0 * bb + delta) * rsqrt(shb[b] * sbd);
+    }
+    __syncwarp();
+    double acc[LNQ];
+#pragma unroll
+    for (int q = 0; q < LNQ; ++q) acc[q] = 0.0;
+    for (int b = 0; b < p.Pb; ++b) {
+      const double qv = qb[b];
+      const double* Eb = Es + b * p.Pt;
+      const double* Xb = X + p.sb * b;
+#pragma unroll
+      for (int q = 0; q < LNQ; ++q) {
+        const int a = lane + 32 * q;
+        if (a < p.Pt) acc[q] = fma(qv * Eb[a], Xb[koff[q]], acc[q]);
+      }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < LNQ; ++q) {
+      if (lane + 32 * q < p.Pt) s = fma(tc[q] * exp(-r2 * rs[q]), acc[q], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) st_stream(p.K + i * p.ldk + j, s);
+   }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 static int g_sms = 0;
 static int sm_count() {
   if (g_sms == 0) {
@@ -512,6 +635,35 @@ extern "C" int mgb_spd2_gram_fwd(int use_cholesky, const double* x1, long long m
   p.use_chol = use_cholesky; p.mode = Q_FWD; p.x1 = x1; p.m = m; p.ld1 = ld1; p.x2 = x2; p.n = n; p.ld2 = ld2;
   p.tcoef = tcoef; p.rscale = rscale; p.bscale = bscale; p.Pt = Pt; p.bval = bval; p.bw = bw; p.Pb = Pb; p.K = K; p.ldk = ldk;
   return spd_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mgb_spd2_gram_fwd_lattice(int use_cholesky, const double* x1, long long m, long long ld1,
+                                         const double* x2, long long n, long long ld2, const double* tcoef,
+                                         const double* rscale, const double* bscale, int Pt, const double* bval,
+                                         const double* bw, int Pb, int sb, int sa, double g_min, double log_tau,
+                                         double* K, long long ldk, void* stream) {
+  if (!x1 || !x2 || !tcoef || !rscale || !bscale || !bval || !bw || !K) return fail(MGB_ERR_ARG, "spd2_gram_fwd_lattice: null pointer");
+  if (m < 0 || n < 0 || ld1 < 3 || ld2 < 3 || ldk < n) return fail(MGB_ERR_ARG, "spd2_gram_fwd_lattice: bad sizes");
+  if (Pt < 1 || Pt > 32 * LNQ) return fail(MGB_ERR_ARG, "spd2_gram_fwd_lattice: Pt out of range [1,64]");
+  if (Pb < 2 || Pb > QMAXP) return fail(MGB_ERR_ARG, "spd2_gram_fwd_lattice: Pb out of range [2,1024]");
+  if (sb < 1 || sa < 0 || !(g_min > 0.0) || !(log_tau > 0.0)) return fail(MGB_ERR_ARG, "spd2_gram_fwd_lattice: bad lattice");
+  if (m == 0 || n == 0) return MGB_OK;
+  SpdLatticeParams p{};
+  p.use_chol = use_cholesky; p.x1 = x1; p.m = m; p.ld1 = ld1; p.x2 = x2; p.n = n; p.ld2 = ld2;
+  p.tcoef = tcoef; p.rscale = rscale; p.bscale = bscale; p.Pt = Pt; p.bval = bval; p.bw = bw; p.Pb = Pb;
+  p.sb = sb; p.sa = sa; p.nk = sb * (Pb - 1) + sa * (Pt - 1) + 1; p.g_min = g_min; p.log_tau = log_tau;
+  p.K = K; p.ldk = ldk;
+  const size_t smem = sizeof(double) * ((size_t)Pb * Pt + p.nk + 4 * (size_t)Pb + (size_t)LWARPS * (p.nk + Pb));
+  if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "spd2_gram_fwd_lattice: lattice too large for shared memory");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MGB_TRY(check_cuda(cudaFuncSetAttribute(spd2_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                     "cudaFuncSetAttribute"));
+  const long long total = m * n;
+  long long blocks = (total + LWARPS - 1) / LWARPS;
+  const long long cap = (long long)sm_count();
+  if (blocks > cap) blocks = cap;
+  spd2_lattice_kernel<<<(unsigned)blocks, LTHREADS, smem, s>>>(p);
+  return after_launch("spd2_lattice_kernel");
 }
 
 extern "C" int mgb_spd2_gram_bwd_scales(int use_cholesky, const double* x1, long long m, long long ld1, const double* x2,

@@ -12,6 +12,9 @@ log-Euclidean kernels are out of scope.
 """
 from __future__ import annotations
 
+import math
+from fractions import Fraction
+
 import torch
 
 from . import _ops, _weights
@@ -68,20 +71,41 @@ class SpdRiemannianIntegratedMaternKernel(_NuMixin, Kernel):
         self.nb_points_integral_b = nb_points_integral_b
         self.nb_points_integral_t = nb_points_integral_t
 
-    def nodes(self, device):
+    def nodes(self, device, with_lattice=False):
         ls = self.lengthscale.to(device)
-        t, w = _weights.matern_t_nodes(ls, self.nu.to(device), -2.0, 1.5, self.nb_points_integral_t, power_offset=1.0)
+        t, w, shift = _weights.matern_t_nodes(ls, self.nu.to(device), -2.0, 1.5, self.nb_points_integral_t,
+                                              power_offset=1.0, return_shift=True)
         b, bw = _b_nodes(self.nb_points_integral_b, device)
         rscale, bscale = 1.0 / (4 * t), 1.0 / (2 * t)
         inner0 = (bw * 2.0 * b / torch.sinh(b) * torch.exp(-(b * b).unsqueeze(0) * bscale.unsqueeze(-1))).sum(-1)
         tcoef = w / (w * inner0).sum()                   # kernels_spd.py:277-289
+        if with_lattice:
+            return tcoef, rscale, bscale, b, bw, self._lattice(shift)
         return tcoef, rscale, bscale, b, bw
+
+    def _lattice(self, shift):
+        """Both quadrature grids are geometric (kernels_spd.py:262-265): log b steps by 6 ln10 / (Pb - 1), log(1 / 2t) by
+        -3.5 ln10 / (Pt - 1), so b_b / (2 t_a) = g_min tau^(sb b + sa (Pt - 1 - a)) with sb : sa = 12 (Pt - 1) : 7 (Pb - 1).
+        Returns (sb, sa, g_min, log tau) for mgb_spd2_gram_fwd_lattice, or None when the lattice would be too long."""
+        pb, pt = self.nb_points_integral_b, self.nb_points_integral_t
+        if pt < 2 or pt > 64 or pb < 2:
+            return None
+        fr = Fraction(12 * (pt - 1), 7 * (pb - 1))
+        sb, sa = fr.numerator, fr.denominator
+        nk = sb * (pb - 1) + sa * (pt - 1) + 1
+        if nk > pb * pt // 2 or 8 * (pb * pt + nk + 4 * pb + 12 * (nk + pb)) > 200 * 1024:
+            return None
+        log_tau = 6.0 * math.log(10.0) / (pb - 1) / sb
+        g_min = 1e-5 * 0.5 * 10.0 ** (-(1.5 + shift))     # b_0 / (2 t_max)
+        return sb, sa, g_min, log_tau
 
     def forward(self, x1, x2, diag=False, **params):
         _check_batch(self)
-        tcoef, rscale, bscale, b, bw = self.nodes(x1.device)
-        op = _ops.spd2_gram_autograd if _ops.inputs_need_grad(x1, x2) else _ops.spd2_gram
-        fn = lambda a, c: op(0, a, c, tcoef, rscale, bscale, b, bw)  # noqa: E731
+        tcoef, rscale, bscale, b, bw, lattice = self.nodes(x1.device, with_lattice=True)
+        if _ops.inputs_need_grad(x1, x2):
+            fn = lambda a, c: _ops.spd2_gram_autograd(0, a, c, tcoef, rscale, bscale, b, bw)  # noqa: E731
+        else:
+            fn = lambda a, c: _ops.spd2_gram(0, a, c, tcoef, rscale, bscale, b, bw, lattice)  # noqa: E731
         return _ops.pairwise(fn, x1, x2, diag=diag)
 
 

@@ -315,3 +315,37 @@ def test_hyperbolic_acquisition_gradient_and_hvp():
     assert abs(outs[0][0] - outs[1][0]) < 1e-9
     assert rel_err(outs[0][1], outs[1][1]) < 1e-8
     assert rel_err(outs[0][2], outs[1][2]) < 1e-7
+
+
+def test_spd2_lattice_kernel_matches_direct_kernel_and_golden():
+    """The lattice form (one exponential per lattice point of b_b / 2 t_a) against the node-by-node kernel and the
+    golden vectors of the reference, default 50 x 50 grid and the 64 x 64 grid of BASELINE config 4."""
+    from materngabo_b200 import _ops
+    from materngabo_b200 import kernels_spd as ksp
+
+    saved = _ops.SPD2_LATTICE_MIN_ENTRIES
+    try:
+        g = load_golden("spd2_matern")
+        k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5, nb_points_integral_b=64, nb_points_integral_t=64)
+        k.lengthscale = float(g["lengthscale"])
+        _ops.SPD2_LATTICE_MIN_ENTRIES = 1
+        lat = k.forward(_t(g["x1"]), _t(g["x2"]))
+        _ops.SPD2_LATTICE_MIN_ENTRIES = 1 << 60
+        direct = k.forward(_t(g["x1"]), _t(g["x2"]))
+        assert rel_err(lat, g["K"]) < TOL and rel_err(direct, g["K"]) < TOL
+        assert rel_err(lat, direct) < 1e-12
+        torch.manual_seed(3)
+        a = torch.randn(300, 2, 2)
+        s = a @ a.transpose(-1, -2) + 0.05 * torch.eye(2)        # includes ill-conditioned matrices (large Delta)
+        v = torch.stack([s[:, 0, 0], s[:, 1, 1], s[:, 0, 1] * 2 ** 0.5], -1).to(DEV)
+        for nb, nt, ls in ((50, 50, 0.6), (64, 64, 2.0), (40, 40, 1.0)):
+            k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=1.5, nb_points_integral_b=nb, nb_points_integral_t=nt)
+            k.lengthscale = ls
+            assert k.nodes(DEV, with_lattice=True)[-1] is not None
+            _ops.SPD2_LATTICE_MIN_ENTRIES = 1
+            lat = k.forward(v, v[:77])
+            _ops.SPD2_LATTICE_MIN_ENTRIES = 1 << 60
+            direct = k.forward(v, v[:77])
+            assert rel_err(lat, direct) < 1e-12
+    finally:
+        _ops.SPD2_LATTICE_MIN_ENTRIES = saved
