@@ -8,6 +8,8 @@ one box (strong scaling, one process per GPU, NCCL only for the state broadcast 
   python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA, sm_100a)
   python bench.py --impl reference ...                          the reference's CPU algorithm (oracle port)
   python bench.py --workload gram-so3|gram-s2|gram-s10|gram-t10|gram-h2|gram-spd2   Gram-matrix workloads
+  python bench.py --workload config1-s2      BASELINE configs[0]: S^2 Matern Gram 1000 x 1000 (L2 flushed between steps)
+  python bench.py --workload config2-bo-s3   BASELINE configs[1]: S^3 GaBO call latencies (N = 100)
 
 Rank 0 prints ONE JSON line.  ``value`` = candidates/s with inputs resident in HBM; ``e2e`` = the same through
 the host-buffer C-ABI call (pinned host inputs, H2D + D2H inside the timed region).  The oracle is used only
@@ -355,8 +357,8 @@ def gram_setup(name, device, m, n):
     from materngabo_b200 import kernels_hyperbolic, kernels_so, kernels_spd, kernels_sphere, kernels_torus
 
     gen = torch.Generator(device=device).manual_seed(0)
-    if name in ("gram-s2", "gram-s10"):
-        dim = 2 if name == "gram-s2" else 10
+    if name in ("gram-s2", "gram-s10", "config1-s2"):
+        dim = 10 if name == "gram-s10" else 2
         k = kernels_sphere.SphereRiemannianMaternKernel(dim=dim, nu=2.5)
         k.lengthscale = 0.5
         x1, x2 = unit_rows(m, dim + 1, gen, device), unit_rows(n, dim + 1, gen, device)
@@ -405,7 +407,7 @@ def gram_setup(name, device, m, n):
     return k, x1, x2, flops
 
 
-GRAM_DEFAULTS = {"gram-s2": (1_000_000, 2000), "gram-s10": (1_000_000, 2000), "gram-so3": (1_000_000, 2000),
+GRAM_DEFAULTS = {"config1-s2": (1000, 1000), "gram-s2": (1_000_000, 2000), "gram-s10": (1_000_000, 2000), "gram-so3": (1_000_000, 2000),
                  "gram-t10": (1_000_000, 2000), "gram-h2": (2000, 2000), "gram-spd2": (2000, 2000)}
 
 
@@ -435,15 +437,28 @@ def run_gram(args, rank, world, local):
     barrier()
     sampler = ClockSampler(local).start() if rank == 0 else None
     launches0 = lib.mgb_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    small = 8.0 * m * n < 4 * 126e6            # output would stay L2 resident between steps: flush L2 in between
     out = None
-    for _ in range(args.steps):
-        del out            # the caching allocator hands the same block back: no cudaMalloc inside the timed region
-        out = step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    if small:
+        flush = torch.empty(64 * 1024 * 1024, dtype=F64, device=device)     # 512 MB > 126 MB L2
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in evs:
+            flush.fill_(1.0)               # untimed: evicts x1, x2 and the previous output
+            del out
+            a.record()
+            out = step()
+            b.record()
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            del out        # the caching allocator hands the same block back: no cudaMalloc inside the timed region
+            out = step()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
     launches = lib.mgb_launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms, float(launches)], dtype=F64, device=device)
@@ -489,9 +504,105 @@ def run_gram(args, rank, world, local):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s K(X*, X) %d x %d per GPU" % (args.workload, m, n), "rows": m, "cols": n,
-                       "l2_policy": "output %.2f GB per step >> L2" % (8e-9 * m * n)},
+                       "l2_policy": ("L2 flushed (512 MB fill, untimed) before every timed step; each step timed by its own "
+                                     "CUDA event pair" if small else "output %.2f GB per step >> L2" % (8e-9 * m * n))},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": None,
             "checksum": float(out[:8, :8].sum())}
+
+
+def run_bo_latency(args, local):
+    """BASELINE.json configs[1]: GaBO on S^3 with 100 training points - microseconds per call of what the BO loop
+    calls (SURVEY.md 8d cfg 2: latency-bound, no roofline): one MLL step (Gram + Cholesky + backward to
+    raw_lengthscale), the posterior fit, EI for b = 100 / 500 candidates in botorch's b x 1 x 4 layout, and one
+    trust-region inner step (EI value + gradient at one candidate)."""
+    from materngabo_b200 import _lib, kernels_sphere
+    from materngabo_b200.gpytorch_compat import ScaleKernel
+    from materngabo_b200.posterior import ExactGPPosterior, ExpectedImprovement
+
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(0)
+    x = torch.nn.functional.normalize(torch.randn(100, 4, generator=gen), dim=-1).to(dev)
+    y = torch.sin(3 * x[:, 0])
+    base = kernels_sphere.SphereRiemannianMaternKernel(dim=3, nu=2.5)
+    sk = ScaleKernel(base).to(dev)
+    eye = 1e-2 * torch.eye(100, device=dev)
+
+    def timeit(fn, reps):
+        for _ in range(max(args.warmup, 3) * 5):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e6
+
+    def mll_step():
+        for prm in sk.parameters():
+            prm.grad = None
+        k = sk(x)
+        L = torch.linalg.cholesky(k + eye)
+        a = torch.cholesky_solve(y.unsqueeze(-1), L).squeeze(-1)
+        (0.5 * (y * a).sum() + torch.log(torch.diagonal(L)).sum()).backward()
+
+    reps = 50 * args.steps
+    sampler = ClockSampler(local).start()
+    launches0 = lib.mgb_launch_count()
+    lat = {}
+    base.raw_lengthscale.requires_grad_(True)
+    lat["mll_step_fwd_bwd_us"] = timeit(mll_step, reps)
+    base.raw_lengthscale.requires_grad_(False)
+    with torch.no_grad():
+        lat["gram_100x100_fwd_us"] = timeit(lambda: base.forward(x, x), reps)
+    gp = ExactGPPosterior(base, x, y, outputscale=1.0, noise=1e-2).fit()
+    lat["fit_n100_us"] = timeit(lambda: gp.fit(), reps)
+    acq = ExpectedImprovement(gp, best_f=float(y.min()), maximize=False)
+    for b in (100, 500):
+        xc = torch.nn.functional.normalize(torch.randn(b, 1, 4, generator=gen), dim=-1).to(dev)
+        with torch.no_grad():
+            lat["ei_b%d_us" % b] = timeit(lambda: acq(xc), reps)
+    x1 = torch.nn.functional.normalize(torch.randn(1, 1, 4, generator=gen), dim=-1).to(dev)
+
+    def tr_step():
+        xx = x1.clone().requires_grad_(True)
+        return torch.autograd.grad(-acq(xx).sum(), [xx])[0]
+
+    lat["ei_value_and_grad_b1_us"] = timeit(tr_step, reps)
+    launches = lib.mgb_launch_count() - launches0
+    clocks = sampler.stop()
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import restated as R
+        use_all_host_threads()
+        xc_, yc_ = x.cpu(), y.cpu()
+        raw = torch.zeros(1, 1, requires_grad=True)
+
+        def cpu_mll():
+            raw.grad = None
+            ls = torch.nn.functional.softplus(raw)
+            k = R.sphere_matern(xc_, xc_, 3, 2.5, ls) * 0.6931471805599453
+            L = torch.linalg.cholesky(k + 1e-2 * torch.eye(100))
+            a = torch.cholesky_solve(yc_.unsqueeze(-1), L).squeeze(-1)
+            (0.5 * (yc_ * a).sum() + torch.log(torch.diagonal(L)).sum()).backward()
+
+        for _ in range(3):
+            cpu_mll()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            cpu_mll()
+        cpu = {"value": (time.perf_counter() - t0) / 20 * 1e6, "unit": "us per MLL step", "cores": torch.get_num_threads(),
+               "kind": "port", "sample": "oracle port (reference torch operator sequence): 20 MLL steps, N = 100, S^3"}
+    return {"metric": "mll_step_latency", "value": lat["mll_step_fwd_bwd_us"], "unit": "us", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": lat["mll_step_fwd_bwd_us"] * 1e-3,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[1]: GaBO on S^3 (Matern nu=2.5), 100 training points: MLL step, "
+                                   "fit, EI posterior b=100/500 (b x 1 x 4), trust-region step b=1; host wall clock per call "
+                                   "incl. Python and launch overhead, %d calls each" % reps,
+                       "l2_policy": "latency-bound: working set (80 KB) is cache resident by construction"},
+            "latencies_us": lat, "gpu_launches": launches, "clocks": clocks, "roofline": None, "e2e": None,
+            "cpu_baseline": cpu}
 
 
 def measured_peaks():
@@ -600,6 +711,8 @@ def main():
     try:
         if args.workload == "posterior-s10":
             out = run_posterior(args, rank, world, local)
+        elif args.workload == "config2-bo-s3":
+            out = run_bo_latency(args, local) if rank == 0 else None
         else:
             out = run_gram(args, rank, world, local)
         if rank == 0:
@@ -611,6 +724,20 @@ def main():
                                        "kind": "port",
                                        "sample": "oracle port (reference's torch CPU algorithm): posterior of %d "
                                                  "candidates x %d training points, %.1f s (fit excluded)" % (sample, n, dt)}
+            elif not args.no_cpu_baseline and args.workload == "config1-s2" and world == 1:
+                from oracle import restated as R
+                use_all_host_threads()
+                g = torch.Generator().manual_seed(0)
+                a = torch.nn.functional.normalize(torch.randn(1000, 3, generator=g), dim=-1)
+                R.sphere_matern(a, a, 2, 2.5, 0.5)
+                t0 = time.perf_counter()
+                reps = 20
+                for _ in range(reps):
+                    R.sphere_matern(a, a, 2, 2.5, 0.5)
+                dt = (time.perf_counter() - t0) / reps
+                out["cpu_baseline"] = {"value": 1e6 / dt, "unit": "entries/s", "cores": torch.get_num_threads(), "kind": "port",
+                                       "sample": "oracle port (reference's torch CPU algorithm): S^2 Matern Gram 1000 x 1000, "
+                                                 "%d repetitions, %.3f s each" % (reps, dt)}
             elif "cpu_baseline" not in out:
                 out["cpu_baseline"] = None
             print(json.dumps(out), flush=True)

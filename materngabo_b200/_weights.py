@@ -83,8 +83,29 @@ def chebyshev_to_monomial(terms: int) -> np.ndarray:
     return out
 
 
+_CONST_CACHE = {}
+
+
 def _t(x, like):
-    return torch.as_tensor(x, dtype=F64, device=like.device)
+    """numpy table -> float64 tensor on ``like``'s device; the lru-cached basis-change tables are uploaded once per
+    device (a GP fit calls this hundreds of times with the same table)."""
+    key = (id(x), str(like.device))
+    hit = _CONST_CACHE.get(key)
+    if hit is None or hit[0] is not x:
+        hit = (x, torch.as_tensor(x, dtype=F64, device=like.device))
+        _CONST_CACHE[key] = hit
+    return hit[1]
+
+
+def _const_vec(lst, device):
+    """Python list of 1-element tensors (the reference's cst_nd / zero_gpolynomials) -> one float64 vector on
+    ``device``, cached against the list object (values keep the dtype rounding they were created with)."""
+    key = (id(lst), str(device))
+    hit = _CONST_CACHE.get(key)
+    if hit is None or hit[0] is not lst:
+        hit = (lst, torch.cat([v.reshape(1) for v in lst]).to(device=device, dtype=F64))
+        _CONST_CACHE[key] = hit
+    return hit[1]
 
 
 def choose_basis(terms: int) -> int:
@@ -143,8 +164,7 @@ def sphere_matern_coef(lengthscale, nu, dim, cst, zero_g):
     base = 2 * nu / ls ** 2
     e0 = torch.pow(base, -(nu + dim / 2))
     e = torch.pow(base + n * (n + dim - 1), -(nu + dim / 2)) / e0
-    c = torch.cat([v.reshape(1) for v in cst]).to(device=ls.device, dtype=F64)
-    g = torch.cat([v.reshape(1) for v in zero_g]).to(device=ls.device, dtype=F64)
+    c, g = _const_vec(cst, ls.device), _const_vec(zero_g, ls.device)
     return _sphere_finish(e * c, g, dim)
 
 
@@ -154,8 +174,7 @@ def sphere_gaussian_coef(lengthscale, dim, cst, zero_g):
     terms = len(cst)
     n = torch.arange(terms, dtype=F64, device=ls.device)
     e = torch.exp(-ls ** 2 / 2.0 * n * (n + dim - 1))
-    c = torch.cat([v.reshape(1) for v in cst]).to(device=ls.device, dtype=F64)
-    g = torch.cat([v.reshape(1) for v in zero_g]).to(device=ls.device, dtype=F64)
+    c, g = _const_vec(cst, ls.device), _const_vec(zero_g, ls.device)
     return _sphere_finish(e * c, g, dim)
 
 
@@ -169,8 +188,7 @@ def sphere_integrated_matern_coef(lengthscale, nu, dim, cst, zero_g, nb_points):
     n = torch.arange(terms, dtype=F64, device=ls.device)
     front = wt * torch.pow(t, nu + dim / 2 - 1.0) * torch.exp(-2.0 * nu / ls ** 2 * t)      # (P,)
     heat = torch.exp(-t.unsqueeze(-1) * (n * (n + dim - 1)).unsqueeze(0))                    # (P, T)
-    c = torch.cat([v.reshape(1) for v in cst]).to(device=ls.device, dtype=F64)
-    g = torch.cat([v.reshape(1) for v in zero_g]).to(device=ls.device, dtype=F64)
+    c, g = _const_vec(cst, ls.device), _const_vec(zero_g, ls.device)
     return _sphere_finish((front.unsqueeze(-1) * heat).sum(0) * c, g, dim)
 
 
