@@ -570,6 +570,26 @@ def run_bo_latency(args, local):
         return torch.autograd.grad(-acq(xx).sum(), [xx])[0]
 
     lat["ei_value_and_grad_b1_us"] = timeit(tr_step, reps)
+
+    # the same two launch-bound calls replayed from CUDA graphs (materngabo_b200/graphs.py)
+    from materngabo_b200.graphs import GraphedValueAndGrad, exact_mll
+    base.raw_lengthscale.requires_grad_(True)
+    gm = GraphedValueAndGrad(lambda: exact_mll(sk, x, y, 1e-2, 0.0), inputs=(), wrt=[base.raw_lengthscale, sk.raw_outputscale])
+
+    def mll_graph():
+        value, grads = gm()
+        return float(value)                 # the L-BFGS driver reads the loss back every evaluation
+
+    lat["mll_step_graph_us"] = timeit(mll_graph, reps)
+    base.raw_lengthscale.requires_grad_(False)
+    v1 = torch.randn(1, 1, 4, generator=gen).to(dev)
+    gt = GraphedValueAndGrad(lambda xx, vv: -acq(xx).sum(), inputs=(x1, v1), wrt=[0], hvp_index=1)
+
+    def tr_graph():
+        value, grads, hvp = gt(x1, v1)
+        return float(value)
+
+    lat["ei_value_grad_hvp_b1_graph_us"] = timeit(tr_graph, reps)
     launches = lib.mgb_launch_count() - launches0
     clocks = sampler.stop()
     cpu = None

@@ -1,0 +1,113 @@
+"""CUDA-graph replay of the launch-bound calls of the BO loop.
+
+At the sizes of the reference's BO scripts (5 ... 100 training points: examples/bo_manifolds_benchmark_examples/
+bo_sphere.py:154,351) one marginal-likelihood evaluation or one trust-region step is a chain of ~100 tiny launches
+(hyper-parameter -> series coefficients in torch, the Gram kernel, Cholesky, solves, the backward of all of it), and
+the time goes to Python and launch overhead, not to the GPU.  Both are called hundreds of times with fixed shapes:
+by the L-BFGS fit (``botorch.fit_gpytorch_model``, bo_sphere.py:262) and by the trust-region solver
+(manifold_optimization/manifold_optimize.py:184-236).  ``GraphedValueAndGrad`` captures value + gradient
+(+ optionally a Hessian-vector product) once into a CUDA graph and replays it: one launch per call.
+
+Everything captured must be free of host synchronisation: the libmgb entry points are (they never synchronise or
+allocate), torch ops are, ``torch.linalg.cholesky`` is not (it reads its ``info`` back) - use
+``torch.linalg.cholesky_ex(..., check_errors=False)`` inside captured functions, as ``exact_mll`` does.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+F64 = torch.float64
+
+
+class GraphedValueAndGrad:
+    """``value = fn(*inputs)`` (a scalar) and its gradient with respect to ``wrt``, replayed from a CUDA graph.
+
+    ``inputs``: example tensors fixing shapes / dtypes; per call their values are copied into static buffers.
+    ``wrt``: tensors to differentiate with respect to - module parameters (static by nature: update them in place)
+    and/or integer indices into ``inputs``.  ``hvp_index``: index into ``inputs`` of a direction ``v``; when given the
+    graph also returns d/d wrt[0] <grad[0], v> (Hessian-vector product for the first ``wrt`` entry, what pymanopt's
+    ``ehess`` asks for: pymanopt_addons/tools/autodiff/_pytorch.py:92-116).
+    ``fn`` may return a tuple ``(value, aux...)``: the auxiliary tensors (e.g. the Cholesky ``info`` flag of
+    ``exact_mll``) are kept in ``self.aux`` after every replay.
+    """
+
+    def __init__(self, fn: Callable, inputs: Sequence[torch.Tensor], wrt: Sequence, hvp_index: Optional[int] = None,
+                 warmup: int = 3):
+        dev = _lib.require_cuda_f64(*[t for t in inputs if t.dtype == F64]) if inputs else None
+        if dev is None:
+            tensors = [w for w in wrt if torch.is_tensor(w)]
+            if not tensors or not tensors[0].is_cuda:
+                raise _lib.MgbError("GraphedValueAndGrad needs CUDA tensors (no CPU fallback)")
+            dev = tensors[0].device
+        self.device = dev
+        self.fn = fn
+        self.static_inputs = [t.detach().clone() for t in inputs]
+        self.wrt_spec = list(wrt)
+        for i, w in enumerate(self.wrt_spec):
+            if isinstance(w, int):
+                self.static_inputs[w].requires_grad_(True)
+        self.hvp_index = hvp_index
+        self.graph = torch.cuda.CUDAGraph()
+        self.value = None
+        self.grads = None
+        self.hvp = None
+        self.aux = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):          # allocator warm-up, lazy initialisations, table uploads
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        with torch.cuda.graph(self.graph):
+            self._run()
+
+    def _wrt(self):
+        return [self.static_inputs[w] if isinstance(w, int) else w for w in self.wrt_spec]
+
+    def _run(self):
+        out = self.fn(*self.static_inputs)
+        value, aux = (out[0], out[1:]) if isinstance(out, tuple) else (out, ())
+        wrt = self._wrt()
+        second = self.hvp_index is not None
+        grads = torch.autograd.grad(value, wrt, create_graph=second, allow_unused=True)
+        hvp = None
+        if second:
+            v = self.static_inputs[self.hvp_index]
+            (hvp,) = torch.autograd.grad((grads[0] * v).sum(), [wrt[0]])
+            grads = tuple(g.detach() if g is not None else None for g in grads)
+        self.value, self.grads, self.hvp, self.aux = value.detach(), grads, hvp, aux
+
+    def __call__(self, *inputs):
+        """Copies ``inputs`` into the static buffers, replays, returns (value, grads[, hvp]) - views of static output
+        buffers, valid until the next call."""
+        if len(inputs) != len(self.static_inputs):
+            raise ValueError("expected %d inputs" % len(self.static_inputs))
+        with torch.no_grad():
+            for dst, src in zip(self.static_inputs, inputs):
+                if src is not dst:
+                    dst.copy_(src)
+        self.graph.replay()
+        if self.hvp_index is not None:
+            return self.value, self.grads, self.hvp
+        return self.value, self.grads
+
+
+def exact_mll(kernel, x, y, noise, mean_const=0.0, jitter: float = 0.0):
+    """Negative exact-GP marginal log likelihood divided by N (gpytorch's ExactMarginalLogLikelihood convention) for
+    ``kernel`` (typically ScaleKernel(manifold kernel)) + Gaussian noise + constant mean: the quantity
+    ``botorch.fit_gpytorch_model`` minimises (bo_sphere.py:262).  Capturable: no host synchronisation.
+    Returns (loss, info) - ``info`` is the Cholesky status flag (non-zero: K + noise I not positive definite)."""
+    n = x.shape[-2]
+    k = kernel(x, x) if hasattr(kernel, "forward") else kernel
+    diag = (noise + jitter) if torch.is_tensor(noise) else float(noise) + jitter     # python scalars: no H2D copy
+    kk = k + diag * torch.eye(n, dtype=F64, device=x.device)
+    L, info = torch.linalg.cholesky_ex(kk, check_errors=False)
+    r = (y - mean_const).unsqueeze(-1)
+    alpha = torch.cholesky_solve(r, L)
+    nll = 0.5 * (r * alpha).sum() + torch.log(torch.diagonal(L, dim1=-2, dim2=-1)).sum() + 0.5 * n * math.log(2 * math.pi)
+    return nll / n, info
