@@ -381,8 +381,12 @@ def gram_setup(name, device, m, n):
         x1 = k._to_circles(torch.rand(m, 10, generator=gen, device=device, dtype=F64) * 6.283185307179586)
         x2 = k._to_circles(torch.rand(n, 10, generator=gen, device=device, dtype=F64) * 6.283185307179586)
         # 10 factors x (6 + 4 n_eff) flops, n_eff = retained cosine terms per factor
-        n_eff = int(k.series()[1].shape[-1])
+        spec_, coef_ = k.series()
+        n_eff = int(coef_.shape[-1])
         flops = 10 * (6 + 4 * n_eff)
+        # executed FMA slots: 2-wide inner product + clamp/product bookkeeping (3) + one FMA per term in the monomial
+        # basis (two in the Chebyshev basis), 2 flops each
+        EXECUTED["gram-t10"] = 10 * (2 + 3 + (1 if spec_.basis == 0 else 2) * n_eff) * 2
     elif name == "gram-h2":
         k = kernels_hyperbolic.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=64)
         k.lengthscale = 1.0
@@ -405,6 +409,9 @@ def gram_setup(name, device, m, n):
     else:
         raise SystemExit("unknown workload %s" % name)
     return k, x1, x2, flops
+
+
+EXECUTED = {}
 
 
 GRAM_DEFAULTS = {"config1-s2": (1000, 1000), "gram-s2": (1_000_000, 2000), "gram-s10": (1_000_000, 2000), "gram-so3": (1_000_000, 2000),
@@ -481,6 +488,9 @@ def run_gram(args, rank, world, local):
         roof = {"bound": "fp64", "achieved": ach, "peak": tf.value, "unit": "TFLOP/s",
                 "frac": (ach / tf.value) if ach else None, "traffic": None,
                 "algorithmic_flops_per_entry": flops,
+                "executed_flops_per_entry": EXECUTED.get(args.workload),
+                "executed_frac": (EXECUTED[args.workload] * float(m) * n / (ms_per_step * 1e-3) / 1e12 / tf.value)
+                if args.workload in EXECUTED else None,
                 "note": ("SURVEY.md 8d: 10 x (6 + 4 n_eff) flops per entry, n_eff = %d retained cosine terms per circle "
                          "factor (of the reference's 201)" % ((flops // 10 - 6) // 4)) if args.workload == "gram-t10" else
                         "algorithmic convention of SURVEY.md 8d: 32 flops per quadrature node (one exp = 28); the kernel "

@@ -235,6 +235,28 @@ def circle_integrated_matern_coef(lengthscale, nu, nb_points):
     return c[:_truncate(c)]
 
 
+MONOMIAL_CONDITION_MAX = 100.0   # sum |a_k| / sum |c_n| above which the monomial form would amplify rounding
+
+
+def chebyshev_or_monomial(c: torch.Tensor):
+    """(F, T) Chebyshev coefficients -> (coefficients, basis) for the device.
+
+    Horner in the monomial basis costs one FMA per term, the Chebyshev recurrence two.  The monomial re-expansion
+    a = c @ [T_n]_k is safe exactly when it does not blow up: the rounding error of Horner on [-1, 1] is bounded by
+    2^-53 * sum |a_k|, and for the circle / torus series the coefficients decay so fast (c_n ~ exp(-const n^2)) that
+    sum |a_k| stays O(1) for lengthscales >= ~0.3 (33 terms at kappa = 0.5: sum |a| = 1.0001; 55 terms at kappa = 0.2:
+    1.8e4 - kept in the Chebyshev basis).  Reads the coefficients back once (they live where the hyper-parameters
+    live)."""
+    terms = c.shape[-1]
+    if terms > _lib.MAX_TERMS or terms > 64:
+        return c, _lib.BASIS_CHEBYSHEV
+    a = c @ _t(chebyshev_to_monomial(terms), c)
+    ratio = a.detach().abs().sum(-1) / c.detach().abs().sum(-1).clamp_min(1e-300)
+    if float(ratio.max()) <= MONOMIAL_CONDITION_MAX:
+        return a.contiguous(), _lib.BASIS_MONOMIAL
+    return c, _lib.BASIS_CHEBYSHEV
+
+
 def stack_factor_coefs(coefs):
     """Per-factor Chebyshev coefficient vectors -> zero-padded (F, T) matrix."""
     t = max(int(c.shape[0]) for c in coefs)

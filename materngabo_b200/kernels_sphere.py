@@ -148,8 +148,8 @@ class _CircleSeriesKernel(Kernel):
         raise NotImplementedError
 
     def series(self):
-        coef = self._coef().reshape(1, -1).contiguous()
-        return _ops.SeriesSpec(1, 2, _lib.BASIS_CHEBYSHEV, 1.0, 0.0, -_CLAMP, _CLAMP), coef
+        coef, basis = _weights.chebyshev_or_monomial(self._coef().reshape(1, -1).contiguous())
+        return _ops.SeriesSpec(1, 2, basis, 1.0, 0.0, -_CLAMP, _CLAMP), coef
 
     def forward(self, x1, x2, diag=False, **params):
         _check_batch(self)

@@ -29,7 +29,8 @@ class _TorusKernel(Kernel):
         coef = _weights.stack_factor_coefs([k._coef() for k in self.torus_kernel.kernels])
         if self.dim > _lib.MAX_FACTORS:
             raise NotImplementedError("T^d with d > %d" % _lib.MAX_FACTORS)
-        return _ops.SeriesSpec(self.dim, 2, _lib.BASIS_CHEBYSHEV, 1.0, 0.0, -_CLAMP, _CLAMP), coef
+        coef, basis = _weights.chebyshev_or_monomial(coef)
+        return _ops.SeriesSpec(self.dim, 2, basis, 1.0, 0.0, -_CLAMP, _CLAMP), coef
 
     def forward(self, x1, x2, diag=False, **params):
         _check_batch(self)
