@@ -297,10 +297,7 @@ def posterior_e2e(args, gp, rank, world, local, m_total, m_local, n, xc, dist):
 
     lib = _lib.load()
     device = torch.device("cuda", local)
-    if world > 1 and rank != 0:
-        # every rank needs the fitted state on the host: rank 0 broadcasts, then all move to pinned memory
-        pass
-    state = {}
+    # every rank needs the fitted state on the host: rank 0 broadcasts, then all move it to pinned memory
     if world > 1:
         from materngabo_b200.posterior import ShardedPosterior
         sh = ShardedPosterior(compute=None)

@@ -574,6 +574,7 @@ using namespace mgb;
 extern "C" int mgb_hyperbolic_gram_fwd(int dim, const double* x1, long long m, long long ld1, const double* x2,
                                        long long n, long long ld2, const double* tval, const double* tcoef, int Pt,
                                        double s0, double ds, int Ps, double* K, long long ldk, void* stream) {
+  if (m == 0 || n == 0) return (m < 0 || n < 0) ? fail(MGB_ERR_ARG, "mgb_hyperbolic_gram_fwd: negative size") : MGB_OK;  // empty block
   if (!x1 || !x2 || !tval || !tcoef || !K) return fail(MGB_ERR_ARG, "hyperbolic_gram_fwd: null pointer");
   if (m < 0 || n < 0 || ld1 < dim + 1 || ld2 < dim + 1 || ldk < n) return fail(MGB_ERR_ARG, "hyperbolic_gram_fwd: bad sizes");
   HypParams p{};
@@ -585,6 +586,7 @@ extern "C" int mgb_hyperbolic_gram_fwd(int dim, const double* x1, long long m, l
 extern "C" int mgb_hyperbolic_gram_bwd_coef(int dim, const double* x1, long long m, long long ld1, const double* x2,
                                             long long n, long long ld2, const double* tval, int Pt, double s0, double ds,
                                             int Ps, const double* G, long long ldg, double* gtcoef, void* stream) {
+  if (m == 0 || n == 0) return (m < 0 || n < 0) ? fail(MGB_ERR_ARG, "mgb_hyperbolic_gram_bwd_coef: negative size") : MGB_OK;  // empty block
   if (!x1 || !x2 || !tval || !G || !gtcoef) return fail(MGB_ERR_ARG, "hyperbolic_gram_bwd_coef: null pointer");
   if (m < 0 || n < 0 || ld1 < dim + 1 || ld2 < dim + 1 || ldg < n) return fail(MGB_ERR_ARG, "hyperbolic_gram_bwd_coef: bad sizes");
   HypParams p{};
@@ -597,6 +599,7 @@ extern "C" int mgb_hyperbolic_gram_bwd_tval(int dim, const double* x1, long long
                                             long long n, long long ld2, const double* tval, const double* tcoef, int Pt,
                                             double s0, double ds, int Ps, const double* G, long long ldg, double* gtval,
                                             void* stream) {
+  if (m == 0 || n == 0) return (m < 0 || n < 0) ? fail(MGB_ERR_ARG, "mgb_hyperbolic_gram_bwd_tval: negative size") : MGB_OK;  // empty block
   if (!x1 || !x2 || !tval || !tcoef || !G || !gtval) return fail(MGB_ERR_ARG, "hyperbolic_gram_bwd_tval: null pointer");
   if (m < 0 || n < 0 || ld1 < dim + 1 || ld2 < dim + 1 || ldg < n) return fail(MGB_ERR_ARG, "hyperbolic_gram_bwd_tval: bad sizes");
   HypParams p{};
@@ -618,6 +621,7 @@ extern "C" int mgb_hyperbolic_heat_nodes(int dim, int derivative, const double* 
 extern "C" int mgb_euclidean_gram_fwd(const double* x1, long long m, long long ld1, const double* x2, long long n,
                                       long long ld2, int width, const double* tval, const double* tcoef, int Pt,
                                       double* K, long long ldk, void* stream) {
+  if (m == 0 || n == 0) return (m < 0 || n < 0) ? fail(MGB_ERR_ARG, "mgb_euclidean_gram_fwd: negative size") : MGB_OK;  // empty block
   if (!x1 || !x2 || !tval || !tcoef || !K) return fail(MGB_ERR_ARG, "euclidean_gram_fwd: null pointer");
   if (m < 0 || n < 0 || width < 1 || ld1 < width || ld2 < width || ldk < n) return fail(MGB_ERR_ARG, "euclidean_gram_fwd: bad sizes");
   HypParams p{};
@@ -629,6 +633,7 @@ extern "C" int mgb_euclidean_gram_fwd(const double* x1, long long m, long long l
 extern "C" int mgb_euclidean_gram_bwd_coef(const double* x1, long long m, long long ld1, const double* x2, long long n,
                                            long long ld2, int width, const double* tval, int Pt, const double* G,
                                            long long ldg, double* gtcoef, void* stream) {
+  if (m == 0 || n == 0) return (m < 0 || n < 0) ? fail(MGB_ERR_ARG, "mgb_euclidean_gram_bwd_coef: negative size") : MGB_OK;  // empty block
   if (!x1 || !x2 || !tval || !G || !gtcoef) return fail(MGB_ERR_ARG, "euclidean_gram_bwd_coef: null pointer");
   if (m < 0 || n < 0 || width < 1 || ld1 < width || ld2 < width || ldg < n) return fail(MGB_ERR_ARG, "euclidean_gram_bwd_coef: bad sizes");
   HypParams p{};
@@ -641,6 +646,7 @@ extern "C" int mgb_spd2_gram_fwd(int use_cholesky, const double* x1, long long m
                                  long long n, long long ld2, const double* tcoef, const double* rscale,
                                  const double* bscale, int Pt, const double* bval, const double* bw, int Pb, double* K,
                                  long long ldk, void* stream) {
+  if (m == 0 || n == 0) return (m < 0 || n < 0) ? fail(MGB_ERR_ARG, "mgb_spd2_gram_fwd: negative size") : MGB_OK;  // empty block
   if (!x1 || !x2 || !tcoef || !rscale || !bscale || !bval || !bw || !K) return fail(MGB_ERR_ARG, "spd2_gram_fwd: null pointer");
   if (m < 0 || n < 0 || ld1 < 3 || ld2 < 3 || ldk < n) return fail(MGB_ERR_ARG, "spd2_gram_fwd: bad sizes");
   SpdParams p{};
@@ -654,6 +660,7 @@ extern "C" int mgb_spd2_gram_fwd_lattice(int use_cholesky, const double* x1, lon
                                          const double* rscale, const double* bscale, int Pt, const double* bval,
                                          const double* bw, int Pb, int sb, int sa, double g_min, double log_tau,
                                          double* K, long long ldk, void* stream) {
+  if (m == 0 || n == 0) return (m < 0 || n < 0) ? fail(MGB_ERR_ARG, "mgb_spd2_gram_fwd_lattice: negative size") : MGB_OK;  // empty block
   if (!x1 || !x2 || !tcoef || !rscale || !bscale || !bval || !bw || !K) return fail(MGB_ERR_ARG, "spd2_gram_fwd_lattice: null pointer");
   if (m < 0 || n < 0 || ld1 < 3 || ld2 < 3 || ldk < n) return fail(MGB_ERR_ARG, "spd2_gram_fwd_lattice: bad sizes");
   if (Pt < 1 || Pt > 32 * LNQ) return fail(MGB_ERR_ARG, "spd2_gram_fwd_lattice: Pt out of range [1,64]");
@@ -682,6 +689,7 @@ extern "C" int mgb_spd2_gram_bwd_scales(int use_cholesky, const double* x1, long
                                         long long n, long long ld2, const double* tcoef, const double* rscale,
                                         const double* bscale, int Pt, const double* bval, const double* bw, int Pb,
                                         const double* G, long long ldg, double* g_rscale, double* g_bscale, void* stream) {
+  if (m == 0 || n == 0) return (m < 0 || n < 0) ? fail(MGB_ERR_ARG, "mgb_spd2_gram_bwd_scales: negative size") : MGB_OK;  // empty block
   if (!x1 || !x2 || !tcoef || !rscale || !bscale || !bval || !bw || !G || !g_rscale || !g_bscale)
     return fail(MGB_ERR_ARG, "spd2_gram_bwd_scales: null pointer");
   if (m < 0 || n < 0 || ld1 < 3 || ld2 < 3 || ldg < n) return fail(MGB_ERR_ARG, "spd2_gram_bwd_scales: bad sizes");
@@ -696,6 +704,7 @@ extern "C" int mgb_spd2_gram_bwd_coef(int use_cholesky, const double* x1, long l
                                       long long n, long long ld2, const double* rscale, const double* bscale, int Pt,
                                       const double* bval, const double* bw, int Pb, const double* G, long long ldg,
                                       double* gtcoef, void* stream) {
+  if (m == 0 || n == 0) return (m < 0 || n < 0) ? fail(MGB_ERR_ARG, "mgb_spd2_gram_bwd_coef: negative size") : MGB_OK;  // empty block
   if (!x1 || !x2 || !rscale || !bscale || !bval || !bw || !G || !gtcoef) return fail(MGB_ERR_ARG, "spd2_gram_bwd_coef: null pointer");
   if (m < 0 || n < 0 || ld1 < 3 || ld2 < 3 || ldg < n) return fail(MGB_ERR_ARG, "spd2_gram_bwd_coef: bad sizes");
   SpdParams p{};

@@ -349,3 +349,65 @@ def test_spd2_lattice_kernel_matches_direct_kernel_and_golden():
             assert rel_err(lat, direct) < 1e-12
     finally:
         _ops.SPD2_LATTICE_MIN_ENTRIES = saved
+
+
+@pytest.mark.parametrize("m,n", [(0, 4), (3, 0), (1, 1), (33, 7), (2, 65)])
+def test_quadrature_kernels_ragged_and_empty_sizes(m, n):
+    """Edge shapes through every quadrature Gram kernel, against the oracle (empty blocks return empty matrices)."""
+    from materngabo_b200 import kernels_euclidean as ke
+    from materngabo_b200 import kernels_hyperbolic as kh
+    from materngabo_b200 import kernels_spd as ksp
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(100 + m + n)
+
+    def lor(cnt, dim):
+        z = torch.randn(cnt, dim, generator=gen)
+        return torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1)
+
+    def spd(cnt):
+        a = torch.randn(cnt, 2, 2, generator=gen)
+        s = a @ a.transpose(-1, -2) + 0.5 * torch.eye(2)
+        return torch.stack([s[:, 0, 0], s[:, 1, 1], s[:, 0, 1] * 2 ** 0.5], -1)
+
+    for dim in (1, 2, 3):
+        a, b = lor(m, dim), lor(n, dim)
+        k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=dim, nu=1.5, nb_points_integral=24)
+        k.lengthscale = 0.8
+        out = k.forward(a.to(DEV), b.to(DEV))
+        assert out.shape == (m, n)
+        if m and n:
+            assert rel_err(out, R.hyperbolic_integrated_matern(a, b, dim, 1.5, 0.8, 24)) < TOL
+    a, b = spd(m), spd(n)
+    k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=1.5, nb_points_integral_b=20, nb_points_integral_t=20)
+    k.lengthscale = 1.1
+    out = k.forward(a.to(DEV), b.to(DEV))
+    assert out.shape == (m, n)
+    if m and n:
+        assert rel_err(out, R.spd2_integrated_matern(a, b, 1.5, 1.1, 20, 20)) < TOL
+    a, b = torch.randn(m, 3, generator=gen), torch.randn(n, 3, generator=gen)
+    k = ke.EuclideanIntegratedMaternKernel(3, nu=2.5)
+    k.lengthscale = 0.9
+    out = k.forward(a.to(DEV), b.to(DEV))
+    assert out.shape == (m, n)
+    if m and n:
+        assert rel_err(out, R.euclidean_integrated_matern(a, b, 2.5, 0.9)) < TOL
+
+
+def test_quadrature_kernels_botorch_batch_layout():
+    """b x 1 x D candidates against the expanded training block and diag=True."""
+    from materngabo_b200 import kernels_hyperbolic as kh
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(9)
+    z = torch.randn(30, 2, generator=gen)
+    x = torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1)
+    xc, xt = x[:7], x[7:]
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=32)
+    k.lengthscale = 1.0
+    out = k.forward(xc.unsqueeze(-2).to(DEV), xt.to(DEV).expand(7, *xt.shape))
+    assert out.shape == (7, 1, 23)
+    assert rel_err(out.squeeze(-2), R.hyperbolic_integrated_matern(xc, xt, 2, 2.5, 1.0, 32)) < TOL
+    d = k.forward(x.to(DEV), x.to(DEV), diag=True)
+    full = k.forward(x.to(DEV), x.to(DEV))
+    assert d.shape == (30,) and rel_err(d, torch.diagonal(full)) < 1e-13
