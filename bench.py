@@ -7,7 +7,7 @@ one box (strong scaling, one process per GPU, NCCL only for the state broadcast 
 
   python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA, sm_100a)
   python bench.py --impl reference ...                          the reference's CPU algorithm (oracle port)
-  python bench.py --workload gram-so3|gram-s2|gram-s10|gram-t10|gram-h2|gram-spd2   Gram-matrix workloads
+  python bench.py --workload gram-so3|gram-s2|gram-s10|gram-t10|gram-h2|gram-spd2|gram-spd3   Gram-matrix workloads
   python bench.py --workload config1-s2      BASELINE configs[0]: S^2 Matern Gram 1000 x 1000 (L2 flushed between steps)
   python bench.py --workload config2-bo-s3   BASELINE configs[1]: S^3 GaBO call latencies (N = 100)
 
@@ -403,6 +403,21 @@ def gram_setup(name, device, m, n):
             return torch.stack([s[:, 0, 0], s[:, 1, 1], s[:, 0, 1] * 2 ** 0.5], -1).contiguous()
         x1, x2 = spd(m), spd(n)
         flops = 4096 * 32
+    elif name == "gram-spd3":
+        # The reference has no intrinsic SPD(3) kernel (kernels_spd.py:59-60 raises for dim != 2); SPD(3) goes through
+        # the product kernel R^3 x SO(3) on decomposed inputs (eigenvalues | flattened rotation), SURVEY.md 8d cfg 4.
+        k = kernels_spd.SpdProductOfRSOManifoldsRiemannianMaternKernel(dim=3, nu=2.5, spd_input=False)
+        k.Euclidean_kernel.lengthscale = 1.0
+        k.so_kernel.lengthscale = 0.5
+
+        def dec(cnt):
+            q, r = torch.linalg.qr(torch.randn(cnt, 3, 3, generator=gen, device=device, dtype=F64))
+            q = q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1)).unsqueeze(-2)
+            q[:, :, 0] *= torch.sign(torch.linalg.det(q)).unsqueeze(-1)
+            ev = 0.5 + 2.0 * torch.rand(cnt, 3, generator=gen, device=device, dtype=F64)
+            return torch.cat([ev, q.reshape(cnt, 9)], -1).contiguous()
+        x1, x2 = dec(m), dec(n)
+        flops = 100 * 32 + 62        # 100 t nodes of the Euclidean factor (one exp each) + the SO(3) series
     else:
         raise SystemExit("unknown workload %s" % name)
     return k, x1, x2, flops
@@ -412,7 +427,7 @@ EXECUTED = {}
 
 
 GRAM_DEFAULTS = {"config1-s2": (1000, 1000), "gram-s2": (1_000_000, 2000), "gram-s10": (1_000_000, 2000), "gram-so3": (1_000_000, 2000),
-                 "gram-t10": (1_000_000, 2000), "gram-h2": (2000, 2000), "gram-spd2": (2000, 2000)}
+                 "gram-t10": (1_000_000, 2000), "gram-h2": (2000, 2000), "gram-spd2": (2000, 2000), "gram-spd3": (2000, 2000)}
 
 
 def run_gram(args, rank, world, local):
@@ -477,7 +492,7 @@ def run_gram(args, rank, world, local):
     if rank != 0:
         return None
     peaks = measured_peaks()
-    quad = args.workload in ("gram-h2", "gram-spd2", "gram-t10")
+    quad = args.workload in ("gram-h2", "gram-spd2", "gram-spd3", "gram-t10")
     if quad:
         tf = C.c_double()
         _lib.check(lib.mgb_fp64_peak(0, 3, C.byref(tf), None), "mgb_fp64_peak")

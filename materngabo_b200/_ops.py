@@ -575,7 +575,7 @@ def pairwise(fn2d, x1: torch.Tensor, x2: torch.Tensor, diag: bool = False) -> to
         flat2 = x2.reshape(-1, 1, x2.shape[-1])
         rows = flat1.shape[0]
         out = torch.empty(rows, dtype=F64, device=x1.device)
-        blk = 2048
+        blk = 256                      # block-diagonal sweep: blk x blk entries computed per blk diagonal values
         pieces = []
         for s in range(0, rows, blk):
             k = fn2d(flat1[s:s + blk, 0], flat2[s:s + blk, 0])
