@@ -8,6 +8,7 @@ one box (strong scaling, one process per GPU, NCCL only for the state broadcast 
   python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA, sm_100a)
   python bench.py --impl reference ...                          the reference's CPU algorithm (oracle port)
   python bench.py --workload gram-so3|gram-s2|gram-s10|gram-t10|gram-h2|gram-spd2|gram-spd3   Gram-matrix workloads
+  python bench.py --workload gram-h2-table   opt-in tabulated H^2 profile (not the per-entry quadrature)
   python bench.py --workload config1-s2      BASELINE configs[0]: S^2 Matern Gram 1000 x 1000 (L2 flushed between steps)
   python bench.py --workload config2-bo-s3   BASELINE configs[1]: S^3 GaBO call latencies (N = 100)
 
@@ -403,6 +404,19 @@ def gram_setup(name, device, m, n):
             return torch.stack([s[:, 0, 0], s[:, 1, 1], s[:, 0, 1] * 2 ** 0.5], -1).contiguous()
         x1, x2 = spd(m), spd(n)
         flops = 4096 * 32
+    elif name == "gram-h2-table":
+        # OPT-IN tabulated profile (materngabo_b200/tabulated.py): NOT the per-entry quadrature of config 4 - the
+        # quadrature is evaluated once per table node and each entry interpolates.  Reported under its own name.
+        from materngabo_b200.tabulated import TabulatedRadialKernel
+        base = kernels_hyperbolic.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=64).to(device)
+        base.lengthscale = 1.0
+
+        def lor(cnt):
+            z = torch.randn(cnt, 2, generator=gen, device=device, dtype=F64)
+            return torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1).contiguous()
+        x1, x2 = lor(m), lor(n)
+        k = TabulatedRadialKernel.for_inputs(base, x1, x2)
+        flops = 0
     elif name == "gram-spd3":
         # The reference has no intrinsic SPD(3) kernel (kernels_spd.py:59-60 raises for dim != 2); SPD(3) goes through
         # the product kernel R^3 x SO(3) on decomposed inputs (eigenvalues | flattened rotation), SURVEY.md 8d cfg 4.
@@ -427,7 +441,8 @@ EXECUTED = {}
 
 
 GRAM_DEFAULTS = {"config1-s2": (1000, 1000), "gram-s2": (1_000_000, 2000), "gram-s10": (1_000_000, 2000), "gram-so3": (1_000_000, 2000),
-                 "gram-t10": (1_000_000, 2000), "gram-h2": (2000, 2000), "gram-spd2": (2000, 2000), "gram-spd3": (2000, 2000)}
+                 "gram-t10": (1_000_000, 2000), "gram-h2": (2000, 2000), "gram-spd2": (2000, 2000), "gram-spd3": (2000, 2000),
+                 "gram-h2-table": (1_000_000, 2000)}
 
 
 def run_gram(args, rank, world, local):

@@ -196,6 +196,17 @@ int mgb_spd2_profile_bwd_coef(int which, const double* delta, const double* r2, 
                               const double* rscale, const double* bscale, int Pt, const double* bval,
                               const double* bw, int Pb, const double* G, double* gtcoef, void* stream);
 
+/* Opt-in tabulated form of a radial kernel (hyperbolic H^1..H^3: geom 0, rows dim+1 wide; Euclidean: geom 1):
+ *   K_ij = poly_{I(v_ij)}(s_ij),  v = z + 1,  z = sqrt(max(0, <D,D>_L) + 1e-8) (= 2 sinh(d/2)) or |x1_i - x2_j|,
+ * interval I = (binary exponent of v) * 2^sub_bits + (top sub_bits mantissa bits of v), s in [-1, 1) the position
+ * inside the interval, coef[I][0..degree] monomial coefficients in s.  The table is built on the host side from
+ * mgb_radial_profile (the same quadrature as the per-entry kernels) and validated against it
+ * (materngabo_b200/tabulated.py).  This is NOT how the reference evaluates these kernels (it integrates per entry,
+ * as mgb_hyperbolic_gram_fwd does); it is offered for large candidate sets and reported separately in bench.py. */
+int mgb_radial_table_gram(int geom, int dim, const double* x1, long long m, long long ld1, const double* x2,
+                          long long n, long long ld2, int sub_bits, int n_intervals, int degree, const double* coef,
+                          double* K, long long ldk, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Exact-GP posterior for a block of candidates (gpytorch ExactGP prediction + botorch call sites:
  * examples/bo_manifolds_benchmark_examples/bo_sphere.py:215-233,265;

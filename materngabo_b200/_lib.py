@@ -55,6 +55,7 @@ PROTOTYPES = {
     "mgb_radial_profile_bwd_coef": (_I, [_I, _I, _P, _LL, _P, _I, _D, _D, _I, _P, _P, _P]),
     "mgb_spd2_profile": (_I, [_I, _P, _P, _LL, _P, _P, _P, _I, _P, _P, _I, _P, _P]),
     "mgb_spd2_profile_bwd_coef": (_I, [_I, _P, _P, _LL, _P, _P, _I, _P, _P, _I, _P, _P, _P]),
+    "mgb_radial_table_gram": (_I, [_I, _I, _P, _LL, _LL, _P, _LL, _LL, _I, _I, _I, _P, _P, _LL, _P]),
     "mgb_posterior_pack_bytes": (_LL, [_LL]),
     "mgb_posterior_pack": (_I, [_P, _LL, _LL, _P, _P, _P]),
     "mgb_posterior_retile": (_I, [_P, _LL, _LL, _LL, _P, _P]),

@@ -235,6 +235,109 @@ __global__ void __launch_bounds__(PTHREADS) spd2_profile_kernel(SpdProfParams p)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tabulated radial profile (opt-in, NOT the per-entry quadrature of the reference).
+//
+// For the hyperbolic and Euclidean kernels the Gram entry is a fixed one-dimensional function of the pair scalar,
+// K_ij = P(z_ij): the reference (and hyp_gram_kernel) re-evaluates a 64 x 64 quadrature for every pair although P
+// does not depend on the pair.  Here P is sampled once with the quadrature kernel (mgb_radial_profile) at Chebyshev
+// nodes of a piecewise partition and every entry evaluates a degree-`deg` polynomial instead.  Partition: v = z + 1
+// (z = 2 sinh(d/2) = sqrt(max(0, <D,D>_L) + 1e-8) for H^n, |x - y| for R^d) is split by its binary exponent and
+// the top `sub_bits` mantissa bits, so interval index and local coordinate come from integer operations on the bit
+// pattern - no logarithm, and no asinh per entry.  The host validates the table against the quadrature (error
+// bound reported to the caller); parity tests compare with the oracle at the usual 1e-10.
+// ------------------------------------------------------------------------------------------------
+struct TableParams {
+  int geom, dim;          // geom 0: Lorentz rows (dim + 1 wide); 1: Euclidean rows (dim wide)
+  const double* x1; long long m, ld1;
+  const double* x2; long long n, ld2;
+  int sub_bits, n_int, deg;
+  const double* coef;     // [n_int][deg + 1], monomials in s = 2 t - 1, t = position inside the interval
+  double* K; long long ldk;
+};
+
+constexpr int TB_THREADS = 256;
+constexpr int TB_ROWS = 64;      // rows of K per CTA
+constexpr int TB_MAXW = 4;
+
+__global__ void __launch_bounds__(TB_THREADS) radial_table_gram_kernel(TableParams p) {
+  extern __shared__ __align__(16) double tab[];   // [n_int][deg + 2] (row pitch deg + 2: odd number of 8-byte banks)
+  const int pitch = p.deg + 2;
+  for (int e = threadIdx.x; e < p.n_int * (p.deg + 1); e += blockDim.x) {
+    const int r = e / (p.deg + 1), k = e - r * (p.deg + 1);
+    tab[r * pitch + k] = p.coef[e];
+  }
+  __syncthreads();
+  const int W = (p.geom == 0) ? p.dim + 1 : p.dim;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long col = (long long)blockIdx.x * 64 + 2 * lane;
+  const long long row0 = (long long)blockIdx.y * TB_ROWS;
+  double xa[TB_MAXW], xb[TB_MAXW];
+  const bool va = col < p.n, vb = col + 1 < p.n;
+#pragma unroll
+  for (int k = 0; k < TB_MAXW; ++k) {
+    xa[k] = (va && k < W) ? __ldg(p.x2 + col * p.ld2 + k) : 0.0;
+    xb[k] = (vb && k < W) ? __ldg(p.x2 + (col + 1) * p.ld2 + k) : 0.0;
+  }
+  const bool vec_ok = vb && ((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0);
+  const int shift = 52 - p.sub_bits;
+  const long long sub_mask = (1LL << p.sub_bits) - 1, rem_mask = (1LL << shift) - 1;
+  for (int r = warp; r < TB_ROWS; r += TB_THREADS / 32) {
+    const long long i = row0 + r;
+    if (i >= p.m) break;
+    const double* xr = p.x1 + i * p.ld1;
+    double xrow[TB_MAXW];
+#pragma unroll
+    for (int k = 0; k < TB_MAXW; ++k) xrow[k] = (k < W) ? __ldg(xr + k) : 0.0;
+    double out[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      double z;
+      if (p.geom == 0) {   // reference operation order, no FMA contraction (hyperbolic_utils_torch.py:38-44,59-60)
+        const double d0 = __dsub_rn(xrow[0], h ? xb[0] : xa[0]);
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 1; k < TB_MAXW; ++k) {
+          if (k < W) {
+            const double dk = __dsub_rn(xrow[k], h ? xb[k] : xa[k]);
+            sacc = (k == 1) ? __dmul_rn(dk, dk) : __dadd_rn(sacc, __dmul_rn(dk, dk));
+          }
+        }
+        const double mink = __dadd_rn(-__dmul_rn(d0, d0), sacc);
+        z = sqrt(__dadd_rn(fmax(0.0, mink), 1e-8));
+      } else {
+        z = 0.0;
+#pragma unroll
+        for (int k = 0; k < TB_MAXW; ++k) {
+          if (k < W) {
+            const double df = xrow[k] - (h ? xb[k] : xa[k]);
+            z = fma(df, df, z);
+          }
+        }
+        z = sqrt(z);   // tabulated in the distance: the small-t heat nodes make P sharp in |x - y|^2 near 0
+      }
+      const long long bits = __double_as_longlong(z + 1.0);
+      int idx = (int)((((bits >> 52) - 1023) << p.sub_bits) | ((bits >> shift) & sub_mask));
+      double sloc = 2.0 * __longlong_as_double(((bits & rem_mask) << p.sub_bits) | 0x3ff0000000000000LL) - 3.0;
+      if (idx >= p.n_int) {   // beyond the tabulated range (caller's bound violated): clamp to the last interval's end
+        idx = p.n_int - 1;
+        sloc = 1.0;
+      }
+      const double* c = tab + idx * pitch;
+      double acc = c[p.deg];
+      for (int k = p.deg - 1; k >= 0; --k) acc = fma(acc, sloc, c[k]);
+      out[h] = acc;
+    }
+    double* dst = p.K + i * p.ldk + col;
+    if (vec_ok) {
+      st_stream2(dst, out[0], out[1]);
+    } else {
+      if (va) st_stream(dst, out[0]);
+      if (vb) st_stream(dst + 1, out[1]);
+    }
+  }
+}
+
 static long long profile_blocks(long long count) {
   long long blocks = (count + PWARPS - 1) / PWARPS;
   int dev = 0, sms = 148;
@@ -314,4 +417,38 @@ extern "C" int mgb_spd2_profile_bwd_coef(int which, const double* delta, const d
   p.which = which; p.mode = PM_BWD_COEF; p.delta = delta; p.r2 = r2; p.count = count; p.tcoef = nullptr;
   p.rscale = rscale; p.bscale = bscale; p.Pt = Pt; p.bval = bval; p.bw = bw; p.Pb = Pb; p.G = G; p.out = gtcoef;
   return spd_profile_launch(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mgb_radial_table_gram(int geom, int dim, const double* x1, long long m, long long ld1, const double* x2,
+                                     long long n, long long ld2, int sub_bits, int n_intervals, int degree,
+                                     const double* coef, double* K, long long ldk, void* stream) {
+  if (m == 0 || n == 0) return (m < 0 || n < 0) ? fail(MGB_ERR_ARG, "radial_table_gram: negative size") : MGB_OK;
+  if (!x1 || !x2 || !coef || !K) return fail(MGB_ERR_ARG, "radial_table_gram: null pointer");
+  const int W = (geom == 0) ? dim + 1 : dim;
+  if ((geom != 0 && geom != 1) || dim < 1 || W > TB_MAXW) return fail(MGB_ERR_ARG, "radial_table_gram: geometry must be H^1..H^3 or R^1..R^4");
+  if (m < 0 || n < 0 || ld1 < W || ld2 < W || ldk < n) return fail(MGB_ERR_ARG, "radial_table_gram: bad sizes");
+  if (sub_bits < 0 || sub_bits > 8 || n_intervals < 1 || degree < 1 || degree > 31)
+    return fail(MGB_ERR_ARG, "radial_table_gram: bad table shape");
+  const size_t smem = sizeof(double) * (size_t)n_intervals * (degree + 2);
+  if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "radial_table_gram: table exceeds shared memory");
+  if (smem > 48 * 1024)
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(radial_table_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute"));
+  TableParams p{geom, dim, x1, m, ld1, x2, n, ld2, sub_bits, n_intervals, degree, coef, K, ldk};
+  const long long gy = (m + TB_ROWS - 1) / TB_ROWS;
+  if (gy > 65535) {
+    // split tall problems into row bands of 65535 * 64 rows
+    for (long long r0 = 0; r0 < m; r0 += 65535LL * TB_ROWS) {
+      const long long rows = (m - r0 < 65535LL * TB_ROWS) ? (m - r0) : 65535LL * TB_ROWS;
+      TableParams q = p;
+      q.x1 = x1 + r0 * ld1; q.m = rows; q.K = K + r0 * ldk;
+      dim3 grid((unsigned)((n + 63) / 64), (unsigned)((rows + TB_ROWS - 1) / TB_ROWS));
+      radial_table_gram_kernel<<<grid, TB_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(q);
+      MGB_TRY(after_launch("radial_table_gram_kernel"));
+    }
+    return MGB_OK;
+  }
+  dim3 grid((unsigned)((n + 63) / 64), (unsigned)gy);
+  radial_table_gram_kernel<<<grid, TB_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("radial_table_gram_kernel");
 }

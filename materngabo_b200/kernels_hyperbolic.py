@@ -36,14 +36,10 @@ class HyperbolicRiemannianMillsonGaussianKernel(Kernel):
         self.dim = dim
         self.nb_points_integral = nb_points_integral
 
-    def forward(self, x1, x2, diag=False, **params):
-        _check_batch(self)
-        if self.dim not in (1, 2, 3):
-            raise NotImplementedError("H^n heat kernel for n > 3 is out of scope (nested autograd in the reference)")
-        _check_lorentz(x1, x2, self.dim)
-        dev = x1.device
+    def nodes(self, dev):
+        """(tval, tcoef, s0, ds, Ps): exp(-s^2 / (2 kappa^2)) = exp(-s^2 / (4 t)) with t = kappa^2 / 2 and the
+        normaliser of the H^2 quadrature at d = 0 (kernels_hyperbolic.py:58-88)."""
         ls = self.lengthscale.reshape(()).to(device=dev, dtype=F64)
-        # exp(-s^2 / (2 kappa^2)) = exp(-s^2 / (4 t)) with t = kappa^2 / 2   (kernels_hyperbolic.py:58-88)
         tval = (ls ** 2 / 2).reshape(1)          # differentiable: the device op returns dL/dt
         p = self.nb_points_integral
         s0, ds = 1e-2, (100.0 - 1e-2) / (p - 1)
@@ -51,7 +47,14 @@ class HyperbolicRiemannianMillsonGaussianKernel(Kernel):
             norm = _ops.hyperbolic_heat_nodes(2, torch.zeros(1, dtype=F64, device=dev), tval, s0, ds, p).reshape(1)
         else:
             norm = torch.ones(1, dtype=F64, device=dev)
-        tcoef = 1.0 / norm
+        return tval, 1.0 / norm, s0, ds, p
+
+    def forward(self, x1, x2, diag=False, **params):
+        _check_batch(self)
+        if self.dim not in (1, 2, 3):
+            raise NotImplementedError("H^n heat kernel for n > 3 is out of scope (nested autograd in the reference)")
+        _check_lorentz(x1, x2, self.dim)
+        tval, tcoef, s0, ds, p = self.nodes(x1.device)
         return _ops.pairwise(_gram_fn(self.dim, x1, x2, tval, tcoef, s0, ds, p), x1, x2, diag=diag)
 
 
