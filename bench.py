@@ -130,9 +130,10 @@ def posterior_problem(n, device, seed=0):
     return gp, k
 
 
-# posterior_reduce_kernel at the default chunk (37888 candidates x 5000 training points): 12.490054 GB read +
-# 11.817472 MB written per launch (ncu --set full, profiles/r01_ncu_posterior_reduce.txt)
-NCU_REDUCE_TRAFFIC_BYTES = 12.490054e9 + 11.817472e6
+# posterior_reduce_kernel at the default chunk (37888 candidates x 5000 training points): 12.251238 GB read +
+# 10.569472 MB written per launch (ncu --set full, profiles/r01b_ncu_posterior_reduce.txt).  The kernel is bound by
+# the FP64 tensor pipe (93 % active); this DRAM traffic is 0.44 TB/s = 7 % of the HBM peak.
+NCU_REDUCE_TRAFFIC_BYTES = 12.251238e9 + 10.569472e6
 
 
 def flops_per_candidate(n):
@@ -280,7 +281,7 @@ def posterior_roofline(gp, xc, n, lib):
             "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
             "traffic": NCU_REDUCE_TRAFFIC_BYTES if (chunk, n) == (37888, 5000) else None,
             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture "
-                              "profiles/r01_ncu_posterior_reduce.txt (chunk 37888, n 5000); algorithmic input bytes per "
+                              "profiles/r01b_ncu_posterior_reduce.txt (chunk 37888, n 5000); the kernel is FP64-tensor-pipe bound, this traffic is 7 %% of the HBM peak; algorithmic input bytes per "
                               "launch = Gram chunk 8*chunk*n = %.2e + packed factor %.2e"
                               % (8.0 * chunk * n, 8.0 * n * n / 2),
             "peak_source": "FP64 DMMA register-resident micro-benchmark measured in this run "
