@@ -545,7 +545,8 @@ def run_gram(args, rank, world, local):
                        "l2_policy": ("L2 flushed (512 MB fill, untimed) before every timed step; each step timed by its own "
                                      "CUDA event pair" if small else "output %.2f GB per step >> L2" % (8e-9 * m * n))},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": None,
-            "checksum": float(out[:8, :8].sum())}
+            "checksum": float(out[:8, :8].sum()),
+            "cpu_baseline": None if (args.no_cpu_baseline or world > 1) else cpu_gram_baseline(args.workload, x1, x2)}
 
 
 def run_bo_latency(args, local):
@@ -661,6 +662,37 @@ def run_bo_latency(args, local):
                        "l2_policy": "latency-bound: working set (80 KB) is cache resident by construction"},
             "latencies_us": lat, "gpu_launches": launches, "clocks": clocks, "roofline": None, "e2e": None,
             "cpu_baseline": cpu}
+
+
+def cpu_gram_baseline(workload, x1, x2):
+    """Oracle port (the reference's torch CPU algorithm, all host threads) on a bounded block of the same inputs:
+    entries/s.  Block sizes are chosen so that one evaluation takes seconds (the reference materialises
+    O(P x M x N) temporaries for the quadrature kernels and O(M x N x D) for the distances)."""
+    from oracle import restated as R
+    use_all_host_threads()
+    blocks = {"gram-s2": (4000, 2000), "gram-s10": (4000, 2000), "config1-s2": (1000, 1000), "gram-so3": (800, 500),
+              "gram-t10": (100, 200), "gram-h2": (200, 300), "gram-spd2": (150, 100), "gram-spd3": (600, 400)}
+    if workload not in blocks:
+        return None
+    bm, bn = blocks[workload]
+    a, b = x1[:bm].cpu(), x2[:bn].cpu()
+    fns = {"gram-s2": lambda: R.sphere_matern(a, b, 2, 2.5, 0.5), "config1-s2": lambda: R.sphere_matern(a, b, 2, 2.5, 0.5),
+           "gram-s10": lambda: R.sphere_matern(a, b, 10, 2.5, 0.5), "gram-so3": lambda: R.so3_matern(a, b, 2.5, 0.5),
+           "gram-t10": lambda: R.torus_matern(a, b, 10, 2.5, 0.5), "gram-h2": lambda: R.hyperbolic_integrated_matern(a, b, 2, 2.5, 1.0, 64),
+           "gram-spd2": lambda: R.spd2_integrated_matern(a, b, 2.5, 1.0, 64, 64),
+           "gram-spd3": lambda: R.spd_product_matern(a, b, 3, 2.5, 1.0, 0.5, "so")}
+    fn = fns[workload]
+    with torch.no_grad():
+        fn()                                   # warm-up
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 20 and (time.perf_counter() - t0 < 8.0 or reps < 2):
+            fn()
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+    return {"value": a.shape[0] * b.shape[0] / dt, "unit": "entries/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "oracle port (reference's torch CPU algorithm) on a %d x %d block of the same inputs, %d repetitions, "
+                      "%.3f s each" % (a.shape[0], b.shape[0], reps, dt)}
 
 
 def measured_peaks():
@@ -782,20 +814,6 @@ def main():
                                        "kind": "port",
                                        "sample": "oracle port (reference's torch CPU algorithm): posterior of %d "
                                                  "candidates x %d training points, %.1f s (fit excluded)" % (sample, n, dt)}
-            elif not args.no_cpu_baseline and args.workload == "config1-s2" and world == 1:
-                from oracle import restated as R
-                use_all_host_threads()
-                g = torch.Generator().manual_seed(0)
-                a = torch.nn.functional.normalize(torch.randn(1000, 3, generator=g), dim=-1)
-                R.sphere_matern(a, a, 2, 2.5, 0.5)
-                t0 = time.perf_counter()
-                reps = 20
-                for _ in range(reps):
-                    R.sphere_matern(a, a, 2, 2.5, 0.5)
-                dt = (time.perf_counter() - t0) / reps
-                out["cpu_baseline"] = {"value": 1e6 / dt, "unit": "entries/s", "cores": torch.get_num_threads(), "kind": "port",
-                                       "sample": "oracle port (reference's torch CPU algorithm): S^2 Matern Gram 1000 x 1000, "
-                                                 "%d repetitions, %.3f s each" % (reps, dt)}
             elif "cpu_baseline" not in out:
                 out["cpu_baseline"] = None
             print(json.dumps(out), flush=True)
