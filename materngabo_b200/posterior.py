@@ -67,7 +67,7 @@ class ExactGPPosterior:
     """
 
     def __init__(self, kernel, train_x: torch.Tensor, train_y: torch.Tensor, outputscale: float = 1.0,
-                 noise: float = 1e-2, mean_const: float = 0.0, chunk: int = DEFAULT_CHUNK):
+                 noise: float = 1e-2, mean_const: float = 0.0, chunk: int = DEFAULT_CHUNK, tabulate: bool = False):
         _lib.require_cuda_f64(train_x, train_y)
         self.kernel = kernel
         self.train_x = train_x.contiguous()
@@ -76,6 +76,9 @@ class ExactGPPosterior:
         self.noise = float(noise)
         self.mean_const = float(mean_const)
         self.chunk = int(chunk)
+        # opt-in: candidate rows of the hyperbolic / Euclidean kernels through the tabulated profile
+        # (materngabo_b200/tabulated.py) instead of one quadrature per entry; the fit always uses the quadrature
+        self.tabulate = bool(tabulate)
         self.device = train_x.device
         self._packed = None
         self._ws = None
@@ -187,10 +190,14 @@ class ExactGPPosterior:
         part = torch.empty(max(1, lib.mgb_posterior_reduce_workspace_bytes(chunk, n) // 8), dtype=F64, device=self.device)
         kss = torch.full((chunk,), self.kss_value, dtype=F64, device=self.device)
         st = _lib.stream_ptr(self.device)
+        forward = self.kernel.forward
+        if self.tabulate:
+            from .tabulated import TabulatedRadialKernel
+            forward = TabulatedRadialKernel.for_inputs(self.kernel, x, self.train_prepared).forward
         with torch.cuda.device(self.device):
             for c0 in range(0, m, chunk):
                 mc = min(chunk, m - c0)
-                k = (self.outputscale * self.kernel.forward(x[c0:c0 + mc], self.train_prepared)).contiguous()
+                k = (self.outputscale * forward(x[c0:c0 + mc], self.train_prepared)).contiguous()
                 _lib.check(lib.mgb_posterior_retile(_lib.ptr(k), mc, n, k.stride(0), _lib.ptr(kb), st), "mgb_posterior_retile")
                 _lib.check(lib.mgb_posterior_reduce(_lib.ptr(kb), mc, n, _lib.ptr(self._packed), _lib.ptr(kss),
                                                     self.mean_const, _lib.ptr(mean[c0:]), _lib.ptr(var[c0:]),

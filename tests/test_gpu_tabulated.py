@@ -60,3 +60,25 @@ def test_euclidean_table():
     with torch.no_grad():
         assert rel_err(tab(e1, e2), k.forward(e1, e2)) < 1e-11
     assert tab(e1[:0], e2).shape == (0, 77)
+
+
+def test_posterior_with_tabulated_candidate_rows():
+    """Acquisition scoring of a large candidate set on H^2: tabulated candidate rows against the per-entry quadrature
+    posterior and the oracle."""
+    from materngabo_b200 import kernels_hyperbolic as kh
+    from materngabo_b200.posterior import ExactGPPosterior
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(31)
+    xt, xc = _lor(60, 3, gen), _lor(5000, 3, gen)
+    y = torch.tanh(xt[:, 1]) - 0.2 * xt[:, 3]
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=3, nu=2.5, nb_points_integral=32).to(DEV)
+    k.lengthscale = 1.0
+    direct = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.2, noise=1e-2, mean_const=0.1).fit()
+    tab = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.2, noise=1e-2, mean_const=0.1, tabulate=True).fit()
+    m0, v0 = direct.posterior(xc.to(DEV))
+    m1, v1 = tab.posterior(xc.to(DEV))
+    assert rel_err(m1, m0) < 1e-9 and float((v1 - v0).abs().max()) < 1e-9
+    kfn = lambda a, b: R.hyperbolic_integrated_matern(a, b, 3, 2.5, 1.0, 32)  # noqa: E731
+    mr, vr = R.gp_posterior(kfn, xt, y, xc[:300], outputscale=1.2, noise=1e-2, mean_const=0.1)
+    assert rel_err(m1[:300], mr) < 1e-9 and float((v1[:300].cpu() - vr).abs().max()) < 1e-8
