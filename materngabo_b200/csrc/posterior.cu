@@ -173,7 +173,76 @@ __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParam
     if ((long long)t * PT <= p.n && p.n < (long long)(t + 1) * PT) owns_mean = true;
     int b_hi = 4;                                            // fragments starting beyond row n are all zero
     while (b_hi > 0 && row_base + 32 * (b_hi - 1) > p.n) --b_hi;
-    for (int ch = 0; ch < nch; ++ch) {
+    // Column chunks [0, n_full) need all four fragments of this warp (they lie left of the diagonal block); they run
+    // software-pipelined ACROSS stage boundaries: the fragments of the next stage's first k-step are loaded before the
+    // last 32 DMMAs of the current stage are issued, so the barrier check, address arithmetic and shared-memory
+    // latency of a stage change hide behind tensor work instead of idling the pipe (both warps of an SM sub-partition
+    // change stage at the same time).
+    int n_full = 0;
+    if (b_hi == 4) {
+      // chunk ch is full iff row_base + 7 >= ch * PK  (b_lo == 0)
+      const long long lim = (row_base + 7) / PK + 1;
+      n_full = (int)(lim < nch ? lim : nch);
+    }
+    int ch = 0;
+    if (n_full > 0) {
+      double af[8], bf[4];
+      mbar_spin(full + stage, phase);
+      {
+        const double* at = As + ((size_t)stage * PT + wc * 64 + frow) * PK;
+        const double* bt = Bs + ((size_t)stage * PT + 8 * wi + frow) * PK;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) af[a] = at[(a * 8) * PK + koff[0]];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bf[b] = bt[(b * 32) * PK + koff[0]];
+      }
+      for (; ch < n_full; ++ch) {
+        const double* at = As + ((size_t)stage * PT + wc * 64 + frow) * PK;
+        const double* bt = Bs + ((size_t)stage * PT + 8 * wi + frow) * PK;
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == PSTAGES) {
+          nstage = 0;
+          nphase ^= 1u;
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < PK / 4; ++k4) {
+          double an[8], bn[4];
+          if (k4 + 1 < PK / 4) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) an[a] = at[(a * 8) * PK + koff[(k4 + 1) % (PK / 4)]];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bn[b] = bt[(b * 32) * PK + koff[(k4 + 1) % (PK / 4)]];
+          } else if (ch + 1 < n_full) {
+            mbar_spin(full + nstage, nphase);      // the producer runs several stages ahead: normally already complete
+            const double* atn = As + ((size_t)nstage * PT + wc * 64 + frow) * PK;
+            const double* btn = Bs + ((size_t)nstage * PT + 8 * wi + frow) * PK;
+#pragma unroll
+            for (int a = 0; a < 8; ++a) an[a] = atn[(a * 8) * PK + koff[0]];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bn[b] = btn[(b * 32) * PK + koff[0]];
+          } else {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) an[a] = 0.0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bn[b] = 0.0;
+          }
+#pragma unroll
+          for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dmma(acc0[a][b], acc1[a][b], af[a], bf[b]);
+#pragma unroll
+          for (int a = 0; a < 8; ++a) af[a] = an[a];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) bf[b] = bn[b];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + stage);   // every read of this stage has been consumed by a DMMA
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+    for (; ch < nch; ++ch) {
       // fragment b is needed for this column chunk iff its last row >= first column of the chunk
       const long long j0 = (long long)ch * PK;
       int b_lo = 0;
