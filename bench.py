@@ -613,13 +613,21 @@ def run_bo_latency(args, local):
     # the same two launch-bound calls replayed from CUDA graphs (materngabo_b200/graphs.py)
     from materngabo_b200.graphs import GraphedValueAndGrad, exact_mll
     base.raw_lengthscale.requires_grad_(True)
-    gm = GraphedValueAndGrad(lambda: exact_mll(sk, x, y, 1e-2, 0.0), inputs=(), wrt=[base.raw_lengthscale, sk.raw_outputscale])
+    wrt = [base.raw_lengthscale, sk.raw_outputscale]
 
-    def mll_graph():
-        value, grads = gm()
-        return float(value)                 # the L-BFGS driver reads the loss back every evaluation
+    def mll_fused_eager():
+        loss, _ = exact_mll(sk, x, y, 1e-2, 0.0)          # Gram + Cholesky + solves + gradients in ONE launch (csrc/mll.cu)
+        return torch.autograd.grad(loss, wrt)
 
-    lat["mll_step_graph_us"] = timeit(mll_graph, reps)
+    lat["mll_step_fused_eager_us"] = timeit(mll_fused_eager, reps)
+    for name, fused in (("mll_step_graph_unfused_us", False), ("mll_step_graph_us", True)):
+        gm = GraphedValueAndGrad(lambda: exact_mll(sk, x, y, 1e-2, 0.0, fused=fused), inputs=(), wrt=wrt)
+
+        def mll_graph():
+            value, grads = gm()
+            return float(value)             # the L-BFGS driver reads the loss back every evaluation
+
+        lat[name] = timeit(mll_graph, reps)
     base.raw_lengthscale.requires_grad_(False)
     v1 = torch.randn(1, 1, 4, generator=gen).to(dev)
     gt = GraphedValueAndGrad(lambda xx, vv: -acq(xx).sum(), inputs=(x1, v1), wrt=[0], hvp_index=1)

@@ -257,6 +257,21 @@ int mgb_series_posterior(const mgb_series_desc* desc, const double* xc, long lon
                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused exact-GP marginal likelihood for launch-bound training sizes (csrc/mll.cu): one CTA, everything in
+ * shared memory.  Replaces one evaluation + backward of gpytorch's ExactMarginalLogLikelihood as called by
+ * botorch.fit_gpytorch_model (examples/bo_manifolds_benchmark_examples/bo_sphere.py:228,257-262) for a
+ * single-factor series kernel:
+ *   Kt = hyper[0] * K(X, X) + hyper[1] * I,  r = y - hyper[2]      (outputscale, noise, constant mean: DEVICE scalars)
+ *   out[0] = 1/2 r^T Kt^-1 r + 1/2 log det Kt + n/2 log(2 pi)
+ *   out[1..3] = d out[0] / d (outputscale, noise, mean),  out[4 + k] = d out[0] / d coef[k]
+ *   *status = 0, or j + 1 when the j-th pivot of the Cholesky factorisation was not positive (outputs are NaN).
+ * n <= mgb_series_mll_max_n(factor_width, n_terms) (160 for S^3 with 10 terms).
+ * ------------------------------------------------------------------------------------------------ */
+long long mgb_series_mll_max_n(int factor_width, int n_terms);
+int mgb_series_mll(const mgb_series_desc* desc, const double* x, long long n, long long ld, const double* y,
+                   const double* coef, const double* hyper, double* out, int* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (the reference-facing calls: numpy / CPU tensors in, numpy out).
  * ------------------------------------------------------------------------------------------------ */
 int mgb_series_gram_host(const mgb_series_desc* desc, const double* x1, long long m, const double* x2,

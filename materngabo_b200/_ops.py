@@ -175,6 +175,45 @@ def series_gram(spec: SeriesSpec, x1: torch.Tensor, x2: torch.Tensor, coef: torc
     return SeriesGram.apply(spec, _c2d(x1), _c2d(x2), coef.contiguous())
 
 
+class SeriesMLL(torch.autograd.Function):
+    """Fused negative log marginal likelihood of an exact GP over a single-factor series kernel (csrc/mll.cu):
+    (x, y, coef, hyper = [outputscale, noise, mean]) -> (nll, status).  The gradients with respect to ``coef`` and
+    ``hyper`` come out of the same launch and are replayed in ``backward``."""
+
+    @staticmethod
+    def forward(ctx, spec, x, y, coef, hyper):
+        lib = _lib.load()
+        t = coef.shape[-1]
+        out = torch.empty(4 + t, dtype=F64, device=x.device)
+        status = torch.zeros(1, dtype=torch.int32, device=x.device)
+        d = spec.desc(t)
+        with torch.cuda.device(x.device):
+            rc = lib.mgb_series_mll(C.byref(d), _lib.ptr(x), x.shape[0], x.stride(0), _lib.ptr(y), _lib.ptr(coef),
+                                    _lib.ptr(hyper), _lib.ptr(out), _lib.ptr(status), _lib.stream_ptr(x.device))
+        _lib.check(rc, "mgb_series_mll")
+        ctx.save_for_backward(out)
+        ctx.coef_shape = coef.shape
+        ctx.mark_non_differentiable(status)
+        return out[0].clone(), status
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g, _gs):
+        (out,) = ctx.saved_tensors
+        gcoef = (g * out[4:]).reshape(ctx.coef_shape) if ctx.needs_input_grad[3] else None
+        ghyper = g * out[1:4] if ctx.needs_input_grad[4] else None
+        return None, None, None, gcoef, ghyper
+
+
+def series_mll_max_n(spec: SeriesSpec, n_terms: int) -> int:
+    return int(_lib.load().mgb_series_mll_max_n(spec.factor_width, int(n_terms)))
+
+
+def series_mll(spec: SeriesSpec, x, y, coef, hyper):
+    _lib.require_cuda_f64(x, y, coef, hyper)
+    return SeriesMLL.apply(spec, _c2d(x), y.contiguous().reshape(-1), coef.contiguous(), hyper.contiguous())
+
+
 def so3_quaternions(*mats, tol: float = 1e-13):
     """Flattened rotations (m x 9) -> unit quaternions (m x 4) for the pair_square form of the SO(3) kernels.
     Returns None when any input is not a rotation to ``tol`` (max |R R^T - I|, |det R - 1| measured on the device):

@@ -1,0 +1,272 @@
+// Fused exact-GP marginal likelihood for launch-bound training sizes.
+//
+// What it replaces: one evaluation of gpytorch's ExactMarginalLogLikelihood + its backward, which
+// botorch.fit_gpytorch_model calls ~100 times per BO iteration (examples/bo_manifolds_benchmark_examples/
+// bo_sphere.py:228,257-262).  At the reference's sizes (5 ... 100 training points) that is ~70 tiny launches (Gram
+// kernel, Cholesky, two triangular solves, log-determinant, the Cholesky backward and the Gram backward) whose
+// durations, not their work, add up to ~250 us.  Here ONE CTA does all of it in shared memory:
+//
+//   Kt   = s * K(X, X) + noise * I            series kernel of include/mgb.h, single factor
+//   L    = chol(Kt)                           right-looking rank-1 updates, two CTA barriers per column, no shuffles
+//   U    = L^-T                               rows of U are independent: one thread per row, no communication
+//   z    = L^-1 (y - mean), alpha = U z
+//   nll  = 1/2 (y - mean)^T alpha + sum log L_ii + n/2 log(2 pi)
+//   G    = dnll/dKt = 1/2 (Kt^-1 - alpha alpha^T),  Kt^-1 = U U^T
+//   dnll/dcoef_k = s sum_ij G_ij phi_k(u_ij),  dnll/ds = sum_ij G_ij K_ij,  dnll/dnoise = tr G,  dnll/dmean = -sum alpha
+//
+// Storage: two packed triangles in shared memory (n (n + 1) doubles in total: n <= 160 fits one SM).  The hyper-
+// parameter chain (coef as a function of the lengthscale / smoothness) stays in torch autograd, as everywhere else.
+#include "mgb_common.cuh"
+#include <cmath>
+
+namespace mgb {
+
+constexpr int MLL_THREADS = 512;
+constexpr int MLL_WARPS = MLL_THREADS / 32;
+constexpr int MLL_TCHUNK = 16;
+
+struct MllParams {
+  const double* x; int n; long long ld;
+  const double* y; const double* coef; const double* hyper;
+  double* out; int* status;
+  int W, T, basis;
+  double scale, shift, lo, hi;
+};
+
+__device__ __forceinline__ int low_idx(int i, int j) { return i * (i + 1) / 2 + j; }              // j <= i
+__device__ __forceinline__ int up_off(int j, int n) { return j * n - j * (j - 1) / 2 - j; }       // + k, k >= j
+
+// p(u) and the pair scalar for rows i, j of the staged inputs
+__device__ __forceinline__ double pair_u(const MllParams& p, const double* xs, int i, int j, bool& inside) {
+  double d = 0.0;
+  for (int k = 0; k < p.W; ++k) d = fma(xs[i * p.W + k], xs[j * p.W + k], d);
+  const double raw = fma(d, p.scale, p.shift);
+  inside = (raw >= p.lo) && (raw <= p.hi);
+  return (raw < p.lo) ? p.lo : ((raw > p.hi) ? p.hi : raw);
+}
+
+__device__ __forceinline__ double series_value(const MllParams& p, const double* cf, double u) {
+  if (p.basis == MGB_BASIS_MONOMIAL) {
+    double s = cf[p.T - 1];
+    for (int k = p.T - 2; k >= 0; --k) s = fma(s, u, cf[k]);
+    return s;
+  }
+  double t0 = 1.0, t1 = u, s = cf[0] + ((p.T > 1) ? cf[1] * u : 0.0);
+  for (int k = 2; k < p.T; ++k) {
+    const double t2 = fma(2.0 * u, t1, -t0);
+    s = fma(cf[k], t2, s);
+    t0 = t1;
+    t1 = t2;
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_kernel(MllParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int n = p.n, tri = n * (n + 1) / 2;
+  double* A = sm;                 // packed lower: Kt -> L (strict lower part; diagonal in dg) -> weights
+  double* U = A + tri;            // packed upper: L^-T
+  double* xs = U + tri;           // n * W
+  double* cfs = xs + n * p.W;     // T
+  double* ry = cfs + p.T;         // y - mean
+  double* z = ry + n;             // L^-1 ry
+  double* al = z + n;             // alpha
+  double* dg = al + n;            // diagonal of L
+  double* acc = dg + n;           // 4 + T block accumulators
+  __shared__ int bad;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double s = p.hyper[0], noise = p.hyper[1], mean = p.hyper[2];
+
+  for (int e = tid; e < n * p.W; e += MLL_THREADS) xs[e] = p.x[(long long)(e / p.W) * p.ld + (e % p.W)];
+  for (int e = tid; e < p.T; e += MLL_THREADS) cfs[e] = p.coef[e];
+  for (int e = tid; e < n; e += MLL_THREADS) ry[e] = p.y[e] - mean;
+  for (int e = tid; e < 4 + p.T; e += MLL_THREADS) acc[e] = 0.0;
+  if (tid == 0) bad = 0;
+  __syncthreads();
+
+  // ---- 1. Kt (lower triangle): warp per row, lanes over columns -------------------------------------
+  for (int i = warp; i < n; i += MLL_WARPS) {
+    for (int j = lane; j <= i; j += 32) {
+      bool inside;
+      const double u = pair_u(p, xs, i, j, inside);
+      A[low_idx(i, j)] = s * series_value(p, cfs, u) + ((i == j) ? noise : 0.0);
+    }
+  }
+  __syncthreads();
+
+  // ---- 2. Cholesky, right-looking: scale column j, rank-1 update of the trailing triangle; two barriers per column
+  for (int j = 0; j < n; ++j) {
+    const double dj = A[low_idx(j, j)];           // final after the barrier that ended iteration j - 1
+    const double ljj = sqrt(dj);                  // NaN for a non-positive pivot: flagged, propagates
+    if (tid == 0) {
+      dg[j] = ljj;
+      if (!(dj > 0.0) && bad == 0) bad = j + 1;
+    }
+    const double inv = 1.0 / ljj;
+    for (int i = j + 1 + tid; i < n; i += MLL_THREADS) A[low_idx(i, j)] *= inv;
+    __syncthreads();
+    for (int i = j + 1 + warp; i < n; i += MLL_WARPS) {
+      const double lij = A[low_idx(i, j)];
+      double* rowi = A + low_idx(i, 0);
+      for (int k = j + 1 + lane; k <= i; k += 32) rowi[k] = fma(-lij, A[low_idx(k, j)], rowi[k]);
+    }
+    __syncthreads();
+  }
+
+  // ---- 3. U = L^-T: thread c owns row c of U (= column c of L^-1), forward substitution without any communication
+  if (tid < n) {
+    const int c = tid;
+    double* urow = U + up_off(c, n);               // urow[k], k >= c
+    urow[c] = 1.0 / dg[c];
+    for (int i = c + 1; i < n; ++i) {
+      const double* rowi = A + low_idx(i, 0);
+      double s0 = 0.0, s1 = 0.0;
+      int k = i - 1;
+      for (; k - 1 >= c; k -= 2) {                 // every thread walks k downwards from i - 1: broadcast reads of L
+        s0 = fma(rowi[k], urow[k], s0);
+        s1 = fma(rowi[k - 1], urow[k - 1], s1);
+      }
+      if (k >= c) s0 = fma(rowi[k], urow[k], s0);
+      urow[i] = -(s0 + s1) / dg[i];
+    }
+  }
+  __syncthreads();
+
+  // ---- 4. z = L^-1 ry (column access of U), alpha = U z, log-determinant ------------------------------
+  for (int i = tid; i < n; i += MLL_THREADS) {
+    double a = 0.0;
+    for (int c = 0; c <= i; ++c) a = fma(U[up_off(c, n) + i], ry[c], a);
+    z[i] = a;
+  }
+  __syncthreads();
+  {
+    double quad = 0.0, gmean = 0.0, logdet = 0.0;
+    for (int i = tid; i < n; i += MLL_THREADS) {
+      const double* urow = U + up_off(i, n);
+      double a = 0.0;
+      for (int k = i; k < n; ++k) a = fma(urow[k], z[k], a);
+      al[i] = a;
+      quad = fma(ry[i], a, quad);
+      gmean -= a;
+      logdet += log(dg[i]);
+    }
+    quad = warp_sum(quad);
+    gmean = warp_sum(gmean);
+    logdet = warp_sum(logdet);
+    if (lane == 0) {
+      atomicAdd(acc + 0, 0.5 * quad + logdet);
+      atomicAdd(acc + 3, gmean);
+    }
+  }
+  __syncthreads();
+
+  // ---- 5. weights: A[i][j] <- (i == j ? 1/2 : 1) * (Kt^-1_ij - alpha_i alpha_j), Kt^-1 = U U^T ------
+  for (int i = warp; i < n; i += MLL_WARPS) {
+    const double* ui = U + up_off(i, n);
+    for (int j = lane; j <= i; j += 32) {
+      const double* uj = U + up_off(j, n);
+      double k0 = 0.0, k1 = 0.0;
+      int k = i;
+      for (; k + 1 < n; k += 2) {
+        k0 = fma(ui[k], uj[k], k0);
+        k1 = fma(ui[k + 1], uj[k + 1], k1);
+      }
+      if (k < n) k0 = fma(ui[k], uj[k], k0);
+      A[low_idx(i, j)] = ((i == j) ? 0.5 : 1.0) * ((k0 + k1) - al[i] * al[j]);
+    }
+  }
+  __syncthreads();
+
+  // ---- 6. gradient reductions over the pairs --------------------------------------------------------
+  for (int c0 = 0; c0 < p.T; c0 += MLL_TCHUNK) {
+    double gk[MLL_TCHUNK];
+#pragma unroll
+    for (int q = 0; q < MLL_TCHUNK; ++q) gk[q] = 0.0;
+    double gs = 0.0, gn = 0.0;
+    for (int i = warp; i < n; i += MLL_WARPS) {
+      for (int j = lane; j <= i; j += 32) {
+        const double w = A[low_idx(i, j)];
+        bool inside;
+        const double u = pair_u(p, xs, i, j, inside);
+        if (c0 == 0) {
+          gs = fma(w, series_value(p, cfs, u), gs);
+          if (i == j) gn += w;
+        }
+        // phi_k(u) for k in [c0, c0 + MLL_TCHUNK)
+        if (p.basis == MGB_BASIS_MONOMIAL) {
+          double pw = 1.0;
+          for (int k = 0; k < c0; ++k) pw *= u;
+#pragma unroll
+          for (int q = 0; q < MLL_TCHUNK; ++q) {
+            if (c0 + q < p.T) gk[q] = fma(w, pw, gk[q]);
+            pw *= u;
+          }
+        } else {
+          double t0 = 1.0, t1 = u;
+          for (int k = 0; k < c0; ++k) {
+            const double t2 = fma(2.0 * u, t1, -t0);
+            t0 = t1;
+            t1 = t2;
+          }
+#pragma unroll
+          for (int q = 0; q < MLL_TCHUNK; ++q) {
+            if (c0 + q < p.T) gk[q] = fma(w, t0, gk[q]);
+            const double t2 = fma(2.0 * u, t1, -t0);
+            t0 = t1;
+            t1 = t2;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < MLL_TCHUNK; ++q) {
+      const double v = warp_sum(gk[q]);
+      if (lane == 0 && c0 + q < p.T) atomicAdd(acc + 4 + c0 + q, s * v);
+    }
+    if (c0 == 0) {
+      gs = warp_sum(gs);
+      gn = warp_sum(gn);
+      if (lane == 0) {
+        atomicAdd(acc + 1, gs);
+        atomicAdd(acc + 2, gn);
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 4 + p.T; e += MLL_THREADS)
+    p.out[e] = acc[e] + ((e == 0) ? 0.5 * n * 1.8378770664093453 : 0.0);   // + n/2 log(2 pi)
+  if (tid == 0 && p.status) *p.status = bad;
+}
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" long long mgb_series_mll_max_n(int factor_width, int n_terms) {
+  // two packed triangles + inputs + vectors within 220 KB of shared memory
+  for (long long n = 200; n >= 1; --n) {
+    const long long doubles = n * (n + 1) + n * factor_width + n_terms + 4 * n + 4 + n_terms;
+    if (doubles * 8 <= 220 * 1024) return n;
+  }
+  return 0;
+}
+
+extern "C" int mgb_series_mll(const mgb_series_desc* d, const double* x, long long n, long long ld, const double* y,
+                              const double* coef, const double* hyper, double* out, int* status, void* stream) {
+  if (!d || !x || !y || !coef || !hyper || !out) return fail(MGB_ERR_ARG, "series_mll: null pointer");
+  if (d->n_factors != 1) return fail(MGB_ERR_ARG, "series_mll: single-factor kernels only");
+  if (d->pair_square) return fail(MGB_ERR_ARG, "series_mll: pair_square form not supported");
+  if (d->factor_width < 1 || d->n_terms < 1 || d->n_terms > MGB_MAX_TERMS) return fail(MGB_ERR_ARG, "series_mll: bad descriptor");
+  if (d->basis != MGB_BASIS_MONOMIAL && d->basis != MGB_BASIS_CHEBYSHEV) return fail(MGB_ERR_ARG, "series_mll: bad basis");
+  if (n < 1 || ld < d->factor_width) return fail(MGB_ERR_ARG, "series_mll: bad sizes");
+  if (n > mgb_series_mll_max_n(d->factor_width, d->n_terms))
+    return fail(MGB_ERR_ARG, "series_mll: n exceeds the single-CTA limit (mgb_series_mll_max_n)");
+  MllParams p{x, (int)n, ld, y, coef, hyper, out, status, d->factor_width, d->n_terms, d->basis,
+              d->scale, d->shift, d->lo, d->hi};
+  const size_t smem = sizeof(double) * (size_t)(n * (n + 1) + n * d->factor_width + d->n_terms + 4 * n + 4 + d->n_terms);
+  if (smem > 48 * 1024)
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute"));
+  series_mll_kernel<<<1, MLL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("series_mll_kernel");
+}

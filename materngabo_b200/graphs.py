@@ -97,11 +97,50 @@ class GraphedValueAndGrad:
         return self.value, self.grads
 
 
-def exact_mll(kernel, x, y, noise, mean_const=0.0, jitter: float = 0.0):
+def _scalar(v, like):
+    """Python number or tensor -> 0-dim float64 device tensor without a host-to-device copy (capturable)."""
+    if torch.is_tensor(v):
+        return v.reshape(()).to(device=like.device, dtype=F64)
+    return torch.full((), float(v), dtype=F64, device=like.device)
+
+
+def _fused_mll(kernel, x, y, noise, mean_const, jitter):
+    """(loss, info) through the single-CTA kernel csrc/mll.cu, or None when the problem does not qualify
+    (not a single-factor series kernel, active_dims, batch dimensions, n above the shared-memory limit)."""
+    from . import _ops
+    from .kernels_sphere import _series_on
+
+    base, scale = kernel, 1.0
+    if hasattr(kernel, "base_kernel") and hasattr(kernel, "outputscale"):
+        base, scale = kernel.base_kernel, kernel.outputscale
+        if getattr(kernel, "active_dims", None) is not None:
+            return None
+    if not hasattr(base, "series") or getattr(base, "active_dims", None) is not None or x.dim() != 2:
+        return None
+    if hasattr(base, "_to_circles"):
+        return None
+    spec, coef = _series_on(base, x.device)
+    if spec.n_factors != 1 or x.shape[-1] != spec.factor_width:
+        return None
+    if x.shape[0] > _ops.series_mll_max_n(spec, coef.shape[-1]):
+        return None
+    hyper = torch.stack([_scalar(scale, x), _scalar(noise, x) + jitter, _scalar(mean_const, x)])
+    nll, info = _ops.series_mll(spec, x, y, coef, hyper)
+    return nll / x.shape[0], info
+
+
+def exact_mll(kernel, x, y, noise, mean_const=0.0, jitter: float = 0.0, fused: bool = True):
     """Negative exact-GP marginal log likelihood divided by N (gpytorch's ExactMarginalLogLikelihood convention) for
     ``kernel`` (typically ScaleKernel(manifold kernel)) + Gaussian noise + constant mean: the quantity
     ``botorch.fit_gpytorch_model`` minimises (bo_sphere.py:262).  Capturable: no host synchronisation.
-    Returns (loss, info) - ``info`` is the Cholesky status flag (non-zero: K + noise I not positive definite)."""
+    Single-factor series kernels (sphere, SO(3), circle) with N up to ~160 go through ONE fused launch (csrc/mll.cu:
+    Gram, Cholesky, solves, log-determinant and all gradients in shared memory); everything else through the Gram
+    kernel + torch.linalg.  Returns (loss, info) - ``info`` is the Cholesky status flag (non-zero: K + noise I not
+    positive definite)."""
+    if fused and hasattr(kernel, "forward"):
+        res = _fused_mll(kernel, x, y, noise, mean_const, jitter)
+        if res is not None:
+            return res
     n = x.shape[-2]
     k = kernel(x, x) if hasattr(kernel, "forward") else kernel
     diag = (noise + jitter) if torch.is_tensor(noise) else float(noise) + jitter     # python scalars: no H2D copy

@@ -1,0 +1,93 @@
+"""-m gpu: the fused single-CTA marginal-likelihood kernel (csrc/mll.cu) against the unfused path (Gram kernel +
+torch.linalg + autograd) and against torch autograd through the oracle on the CPU."""
+import pytest
+import torch
+
+from tests.conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+sp = torch.nn.functional.softplus
+
+
+def _grads(loss, params):
+    return torch.autograd.grad(loss, params)
+
+
+def _close(a, b, rtol):
+    """relative to max |b| with an absolute floor (a normalised kernel at a single point has an exactly zero
+    lengthscale gradient: both paths return rounding noise there)"""
+    a, b = a.detach().reshape(-1).cpu(), b.detach().reshape(-1).cpu()
+    return float((a - b).abs().max()) <= rtol * float(b.abs().max()) + 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 2, 37, 100, 160])
+def test_fused_mll_matches_unfused_and_oracle(n):
+    from materngabo_b200 import kernels_sphere
+    from materngabo_b200.gpytorch_compat import ScaleKernel
+    from materngabo_b200.graphs import exact_mll
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(n)
+    x = torch.nn.functional.normalize(torch.randn(n, 4, generator=gen), dim=-1)
+    y = torch.sin(3 * x[:, 0]) + 0.2 * torch.randn(n, generator=gen)
+    base = kernels_sphere.SphereRiemannianMaternKernel(dim=3, nu=None)
+    sk = ScaleKernel(base).to(DEV)
+    with torch.no_grad():
+        base.raw_lengthscale.fill_(-0.3)
+        base.raw_nu.fill_(1.1)
+        sk.raw_outputscale.fill_(0.4)
+    params = [base.raw_lengthscale, base.raw_nu, sk.raw_outputscale]
+    noise = torch.tensor(0.02, device=DEV, requires_grad=True)
+    mean = torch.tensor(0.15, device=DEV, requires_grad=True)
+    xd, yd = x.to(DEV), y.to(DEV)
+    lf, info = exact_mll(sk, xd, yd, noise, mean)
+    assert int(info) == 0
+    gf = _grads(lf, params + [noise, mean])
+    lu, _ = exact_mll(sk, xd, yd, noise, mean, fused=False)
+    gu = _grads(lu, params + [noise, mean])
+    assert abs(float(lf) - float(lu)) < 1e-11 * max(1.0, abs(float(lu)))
+    for a, b in zip(gf, gu):
+        assert _close(a, b, 1e-9)
+    # oracle: torch autograd through the restated reference kernel on the CPU
+    rl = torch.full((1, 1), -0.3, requires_grad=True)
+    rn = torch.full((1, 1), 1.1, requires_grad=True)
+    ro = torch.tensor(0.4, requires_grad=True)
+    nz = torch.tensor(0.02, requires_grad=True)
+    mn = torch.tensor(0.15, requires_grad=True)
+    k = sp(ro) * R.sphere_matern(x, x, 3, sp(rn), sp(rl))
+    lo, _ = exact_mll(k, x, y, nz, mn)
+    go = _grads(lo, [rl, rn, ro, nz, mn])
+    assert abs(float(lf) - float(lo)) < 1e-9 * max(1.0, abs(float(lo)))
+    for a, b in zip(gf, go):
+        assert _close(a, b, 1e-7)
+
+
+def test_fused_mll_so3_and_circle_and_failure_flag():
+    from materngabo_b200 import kernels_so, kernels_sphere
+    from materngabo_b200.graphs import exact_mll
+
+    gen = torch.Generator().manual_seed(3)
+    q, r = torch.linalg.qr(torch.randn(64, 3, 3, generator=gen))
+    q = q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1)).unsqueeze(-2)
+    q[:, :, 0] *= torch.sign(torch.linalg.det(q)).unsqueeze(-1)
+    xr = q.reshape(64, 9).to(DEV)
+    y = torch.randn(64, generator=gen).to(DEV)
+    k = kernels_so.SORiemannianMaternKernel(dim=3, nu=2.5).to(DEV)
+    k.lengthscale = 0.6
+    lf, info = exact_mll(k, xr, y, 0.05, 0.0)
+    lu, _ = exact_mll(k, xr, y, 0.05, 0.0, fused=False)
+    gf, gu = _grads(lf, [k.raw_lengthscale]), _grads(lu, [k.raw_lengthscale])
+    assert int(info) == 0 and abs(float(lf) - float(lu)) < 1e-11 and rel_err(gf[0], gu[0]) < 1e-9
+    for ls in (0.5, 0.15):                               # monomial and Chebyshev (55+ terms) circle series
+        c = kernels_sphere.CircleRiemannianIntegratedMaternKernel(nu=2.5).to(DEV)
+        c.lengthscale = ls
+        xc = torch.nn.functional.normalize(torch.randn(50, 2, generator=gen), dim=-1).to(DEV)
+        yc = torch.randn(50, generator=gen).to(DEV)
+        lf, info = exact_mll(c, xc, yc, 0.05, 0.1)
+        lu, _ = exact_mll(c, xc, yc, 0.05, 0.1, fused=False)
+        gf, gu = _grads(lf, [c.raw_lengthscale]), _grads(lu, [c.raw_lengthscale])
+        assert int(info) == 0 and abs(float(lf) - float(lu)) < 1e-10 and rel_err(gf[0], gu[0]) < 1e-8
+    # not positive definite: negative "noise" larger than the smallest eigenvalue
+    lf, info = exact_mll(k, xr, y, -5.0, 0.0)
+    assert int(info) > 0 and not torch.isfinite(lf)
