@@ -156,14 +156,24 @@ def _sphere_finish(a: torch.Tensor, zero_g: torch.Tensor, dim: int):
     return (w.reshape(1, terms) @ _t(mat, w)).contiguous(), basis
 
 
+def _eigenvalues(terms: int, dim: int, device):
+    """n (n + dim - 1), n < terms: Laplace-Beltrami eigenvalues of S^dim, cached per device."""
+    key = ("lb", terms, dim, str(device))
+    hit = _CONST_CACHE.get(key)
+    if hit is None:
+        n = torch.arange(terms, dtype=F64, device=device)
+        hit = (None, n * (n + dim - 1))
+        _CONST_CACHE[key] = hit
+    return hit[1]
+
+
 def sphere_matern_coef(lengthscale, nu, dim, cst, zero_g):
     """kernels_sphere.py:126-139."""
     ls, nu = lengthscale.reshape(()).to(F64), nu.reshape(()).to(F64)
     terms = len(cst)
-    n = torch.arange(terms, dtype=F64, device=ls.device)
     base = 2 * nu / ls ** 2
-    e0 = torch.pow(base, -(nu + dim / 2))
-    e = torch.pow(base + n * (n + dim - 1), -(nu + dim / 2)) / e0
+    power = -(nu + dim / 2)
+    e = torch.pow(base + _eigenvalues(terms, dim, ls.device), power) / torch.pow(base, power)
     c, g = _const_vec(cst, ls.device), _const_vec(zero_g, ls.device)
     return _sphere_finish(e * c, g, dim)
 
@@ -172,8 +182,7 @@ def sphere_gaussian_coef(lengthscale, dim, cst, zero_g):
     """kernels_sphere.py:212-224."""
     ls = lengthscale.reshape(()).to(F64)
     terms = len(cst)
-    n = torch.arange(terms, dtype=F64, device=ls.device)
-    e = torch.exp(-ls ** 2 / 2.0 * n * (n + dim - 1))
+    e = torch.exp(-ls ** 2 / 2.0 * _eigenvalues(terms, dim, ls.device))
     c, g = _const_vec(cst, ls.device), _const_vec(zero_g, ls.device)
     return _sphere_finish(e * c, g, dim)
 
