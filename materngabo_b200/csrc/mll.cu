@@ -7,8 +7,8 @@
 // durations, not their work, add up to ~250 us.  Here ONE CTA does all of it in shared memory:
 //
 //   Kt   = s * K(X, X) + noise * I            series kernel of include/mgb.h, single factor
-//   L    = chol(Kt)                           right-looking rank-1 updates, two CTA barriers per column, no shuffles
-//   U    = L^-T                               rows of U are independent: one thread per row, no communication
+//   L    = chol(Kt)                           left-looking, 4 columns per round; a group of G lanes per row shares the dots
+//   U    = L^-T                               rows of U are independent: one lane group per row, 4 entries per round
 //   z    = L^-1 (y - mean), alpha = U z
 //   nll  = 1/2 (y - mean)^T alpha + sum log L_ii + n/2 log(2 pi)
 //   G    = dnll/dKt = 1/2 (Kt^-1 - alpha alpha^T),  Kt^-1 = U U^T
@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_kernel(MllParams p)
   double* z = ry + n;             // L^-1 ry
   double* al = z + n;             // alpha
   double* dg = al + n;            // diagonal of L
-  double* acc = dg + n;           // 4 + T block accumulators
+  double* dgi = dg + n;           // its reciprocal
+  double* acc = dgi + n;          // 4 + T block accumulators
   __shared__ int bad;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double s = p.hyper[0], noise = p.hyper[1], mean = p.hyper[2];
@@ -94,40 +95,129 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_kernel(MllParams p)
   }
   __syncthreads();
 
-  // ---- 2. Cholesky, right-looking: scale column j, rank-1 update of the trailing triangle; two barriers per column
-  for (int j = 0; j < n; ++j) {
-    const double dj = A[low_idx(j, j)];           // final after the barrier that ended iteration j - 1
-    const double ljj = sqrt(dj);                  // NaN for a non-positive pivot: flagged, propagates
-    if (tid == 0) {
-      dg[j] = ljj;
-      if (!(dj > 0.0) && bad == 0) bad = j + 1;
+  // Thread groups of G adjacent lanes (G = 2^g <= 32, n * G <= MLL_THREADS) share one dot product: lane q of a group
+  // takes every G-th term and the group combines with g shuffle steps.
+  int G = 1;
+  while (G < 32 && 2 * G * n <= MLL_THREADS) G *= 2;
+  const int grp = tid / G, q = tid % G;
+  auto group_sum = [&](double v) {
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+
+  // ---- 2. Cholesky, left-looking, PB columns per round.  Group r owns row r.  Per round: (a) every active row takes
+  // its PB dot products against the PB panel rows over the columns left of the panel (independent: 4-way ILP);
+  // (b) the PB x PB diagonal block is finished by the groups of the panel rows themselves in PB short steps through
+  // shared memory; (c) after one barrier every row below the panel finishes its PB entries in registers.
+  // One barrier pair per PB columns instead of per column, reciprocal pivots instead of divisions.
+  constexpr int PB = 4;
+  for (int j0 = 0; j0 < n; j0 += PB) {
+    const int pb = (n - j0 < PB) ? (n - j0) : PB;
+    const int r = grp;
+    const bool active = (r < n) && (r >= j0);
+    double v[PB];
+#pragma unroll
+    for (int c = 0; c < PB; ++c) v[c] = 0.0;
+    if (active) {
+      const double* rowr = A + low_idx(r, 0);
+      for (int k = q; k < j0; k += G) {
+        const double a = rowr[k];
+#pragma unroll
+        for (int c = 0; c < PB; ++c)
+          if (c < pb) v[c] = fma(a, A[low_idx(j0 + c, 0) + k], v[c]);
+      }
     }
-    const double inv = 1.0 / ljj;
-    for (int i = j + 1 + tid; i < n; i += MLL_THREADS) A[low_idx(i, j)] *= inv;
-    __syncthreads();
-    for (int i = j + 1 + warp; i < n; i += MLL_WARPS) {
-      const double lij = A[low_idx(i, j)];
-      double* rowi = A + low_idx(i, 0);
-      for (int k = j + 1 + lane; k <= i; k += 32) rowi[k] = fma(-lij, A[low_idx(k, j)], rowi[k]);
+#pragma unroll
+    for (int c = 0; c < PB; ++c) v[c] = group_sum(v[c]);
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < PB; ++c)
+        if (c < pb && j0 + c <= r) v[c] = A[low_idx(r, j0 + c)] - v[c];
+    }
+    // (b) diagonal block: column c of the panel is final once rows j0..j0+c-1 of the block are; pb tiny steps
+    for (int c = 0; c < pb; ++c) {
+      if (active && q == 0 && r < j0 + pb && r >= j0 + c) {
+        // subtract the in-panel part: sum_{k < c} L[r][j0+k] L[j0+c][j0+k]
+        double t = v[c];
+        for (int k = 0; k < c; ++k) t = fma(-A[low_idx(r, j0 + k)], A[low_idx(j0 + c, j0 + k)], t);
+        if (r == j0 + c) {
+          const double rs = rsqrt(t);
+          dg[r] = t * rs;                         // sqrt(t); NaN for a non-positive pivot: flagged, propagates
+          dgi[r] = rs;
+          if (!(t > 0.0) && bad == 0) bad = r + 1;
+        } else {
+          v[c] = t;                               // finished after the barrier below (needs dgi of the pivot row)
+        }
+      }
+      __syncthreads();
+      if (active && q == 0 && r < j0 + pb && r > j0 + c) A[low_idx(r, j0 + c)] = v[c] * dgi[j0 + c];
+      __syncthreads();
+    }
+    // (c) rows below the panel: forward substitution inside the panel, in registers
+    if (active && q == 0 && r >= j0 + pb) {
+#pragma unroll
+      for (int c = 0; c < PB; ++c) {
+        if (c < pb) {
+          double t = v[c];
+#pragma unroll
+          for (int k = 0; k < PB; ++k)
+            if (k < c) t = fma(-v[k], A[low_idx(j0 + c, j0 + k)], t);
+          v[c] = t * dgi[j0 + c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < PB; ++c)
+        if (c < pb) A[low_idx(r, j0 + c)] = v[c];
     }
     __syncthreads();
   }
 
-  // ---- 3. U = L^-T: thread c owns row c of U (= column c of L^-1), forward substitution without any communication
-  if (tid < n) {
-    const int c = tid;
-    double* urow = U + up_off(c, n);               // urow[k], k >= c
-    urow[c] = 1.0 / dg[c];
-    for (int i = c + 1; i < n; ++i) {
-      const double* rowi = A + low_idx(i, 0);
-      double s0 = 0.0, s1 = 0.0;
-      int k = i - 1;
-      for (; k - 1 >= c; k -= 2) {                 // every thread walks k downwards from i - 1: broadcast reads of L
-        s0 = fma(rowi[k], urow[k], s0);
-        s1 = fma(rowi[k - 1], urow[k - 1], s1);
+  // ---- 3. U = L^-T: group c owns row c of U (= column c of L^-1): forward substitution, communication only inside
+  // the group.  PB entries per round: the dot products over k < i0 are independent (ILP), the in-block part is a
+  // short recurrence in registers of lane 0. ----------------------------------------------------------------
+  {
+    const int c = grp;
+    const bool active = c < n;
+    double* urow = U + (active ? up_off(c, n) : 0);  // urow[k], k >= c
+    if (active && q == 0) urow[c] = dgi[c];
+    __syncwarp();
+    for (int i0 = 1; i0 < n; i0 += PB) {            // uniform trip count: the shuffles need every lane
+      double d[PB];
+#pragma unroll
+      for (int e = 0; e < PB; ++e) d[e] = 0.0;
+      if (active && i0 + PB - 1 > c) {
+        const int kend = (i0 > c) ? i0 : c;          // terms k in [c, i0) exist only when i0 > c
+        for (int k = c + q; k < kend; k += G) {
+          const double u = urow[k];
+#pragma unroll
+          for (int e = 0; e < PB; ++e)
+            if (i0 + e < n) d[e] = fma(A[low_idx(i0 + e, 0) + k], u, d[e]);
+        }
       }
-      if (k >= c) s0 = fma(rowi[k], urow[k], s0);
-      urow[i] = -(s0 + s1) / dg[i];
+#pragma unroll
+      for (int e = 0; e < PB; ++e) d[e] = group_sum(d[e]);
+      if (active && q == 0) {
+        double w[PB];
+#pragma unroll
+        for (int e = 0; e < PB; ++e) {
+          const int i = i0 + e;
+          w[e] = 0.0;
+          if (i < n && i > c) {
+            double t = d[e];
+            // in-block terms k in [max(i0, c), i): entries finished earlier in this round (or the diagonal entry)
+#pragma unroll
+            for (int f = 0; f < PB; ++f) {
+              const int k = i0 + f;
+              if (f < e && k >= c) t = fma(A[low_idx(i, k)], (k == c) ? dgi[c] : w[f], t);
+            }
+            w[e] = -t * dgi[i];
+            urow[i] = w[e];
+          } else if (i == c) {
+            w[e] = dgi[c];
+          }
+        }
+      }
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -245,7 +335,7 @@ using namespace mgb;
 extern "C" long long mgb_series_mll_max_n(int factor_width, int n_terms) {
   // two packed triangles + inputs + vectors within 220 KB of shared memory
   for (long long n = 200; n >= 1; --n) {
-    const long long doubles = n * (n + 1) + n * factor_width + n_terms + 4 * n + 4 + n_terms;
+    const long long doubles = n * (n + 1) + n * factor_width + n_terms + 5 * n + 4 + n_terms;
     if (doubles * 8 <= 220 * 1024) return n;
   }
   return 0;
@@ -263,7 +353,7 @@ extern "C" int mgb_series_mll(const mgb_series_desc* d, const double* x, long lo
     return fail(MGB_ERR_ARG, "series_mll: n exceeds the single-CTA limit (mgb_series_mll_max_n)");
   MllParams p{x, (int)n, ld, y, coef, hyper, out, status, d->factor_width, d->n_terms, d->basis,
               d->scale, d->shift, d->lo, d->hi};
-  const size_t smem = sizeof(double) * (size_t)(n * (n + 1) + n * d->factor_width + d->n_terms + 4 * n + 4 + d->n_terms);
+  const size_t smem = sizeof(double) * (size_t)(n * (n + 1) + n * d->factor_width + d->n_terms + 5 * n + 4 + d->n_terms);
   if (smem > 48 * 1024)
     MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                        "cudaFuncSetAttribute"));
