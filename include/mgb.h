@@ -271,6 +271,16 @@ long long mgb_series_mll_max_n(int factor_width, int n_terms);
 int mgb_series_mll(const mgb_series_desc* desc, const double* x, long long n, long long ld, const double* y,
                    const double* coef, const double* hyper, double* out, int* status, void* stream);
 
+/* Series coefficients of the sphere / SO(3) kernels and their Jacobian with respect to (kappa, nu) in one launch
+ * (the hyper-parameter -> coefficient chain of kernels_sphere.py:126-139,212-224 and kernels_so.py:264-273,101, which
+ * torch autograd otherwise spreads over ~60 tiny kernels per marginal-likelihood evaluation):
+ *   a_n = c[n] f(lam[n]),  f = ((b + lam)/b)^-(nu + half_dim), b = 2 nu / kappa^2 (mode 0) or exp(-kappa^2 lam / 2) (mode 1)
+ *   coef = (a / sum_n a_n g[n]) M,  M row-major n_terms x n_out;  jac[0..n_out) = d coef / d kappa, jac[n_out..) = d coef / d nu.
+ * kappa, nu: device scalars (nu may be NULL in mode 1). */
+int mgb_spectral_coef(int mode, int n_terms, int n_out, const double* lam, const double* c, const double* g,
+                      const double* M, double half_dim, const double* kappa, const double* nu, double* coef,
+                      double* jac, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (the reference-facing calls: numpy / CPU tensors in, numpy out).
  * ------------------------------------------------------------------------------------------------ */

@@ -156,6 +156,62 @@ def _sphere_finish(a: torch.Tensor, zero_g: torch.Tensor, dim: int):
     return (w.reshape(1, terms) @ _t(mat, w)).contiguous(), basis
 
 
+class _SpectralCoef(torch.autograd.Function):
+    """coef(kappa, nu) of the sphere / SO(3) series and its Jacobian from ONE device launch (mgb_spectral_coef);
+    the torch formulas below stay the definition (and the CPU path the host tests exercise)."""
+
+    @staticmethod
+    def forward(ctx, mode, lam, c, g, mat, half_dim, kappa, nu):
+        import ctypes as C
+        lib = _lib.load()
+        t, tout = mat.shape
+        coef = torch.empty((1, tout), dtype=F64, device=kappa.device)
+        jac = torch.empty((2, tout), dtype=F64, device=kappa.device)
+        kappa = kappa.detach().contiguous()
+        nu_c = nu.detach().contiguous() if nu is not None else None
+        with torch.cuda.device(kappa.device):
+            rc = lib.mgb_spectral_coef(int(mode), int(t), int(tout), _lib.ptr(lam), _lib.ptr(c), _lib.ptr(g), _lib.ptr(mat),
+                                       float(half_dim), _lib.ptr(kappa), _lib.ptr(nu_c), _lib.ptr(coef), _lib.ptr(jac),
+                                       _lib.stream_ptr(kappa.device))
+        _lib.check(rc, "mgb_spectral_coef")
+        ctx.save_for_backward(jac)
+        ctx.has_nu = nu is not None
+        return coef
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gcoef):
+        (jac,) = ctx.saved_tensors
+        gv = jac @ gcoef.reshape(-1)                       # (2,)
+        gk = gv[0].reshape(()) if ctx.needs_input_grad[6] else None
+        gn = gv[1].reshape(()) if (ctx.has_nu and ctx.needs_input_grad[7]) else None
+        return None, None, None, None, None, None, gk, gn
+
+
+def _so3_matrix(terms: int, basis: int) -> np.ndarray:
+    """lam -> series coefficients as one matrix: v_m = (2 - delta_m0) sum_{l >= m} lam_l, then Chebyshev -> monomial."""
+    key = ("so3mat", terms, basis)
+    hit = _CONST_CACHE.get(key)
+    if hit is None:
+        tail = np.zeros((terms, terms))
+        for l in range(terms):
+            for m in range(l + 1):
+                tail[l, m] = 1.0 if m == 0 else 2.0
+        mat = tail @ chebyshev_to_monomial(terms) if basis == _lib.BASIS_MONOMIAL else tail
+        hit = (None, np.ascontiguousarray(mat))
+        _CONST_CACHE[key] = hit
+    return hit[1]
+
+
+def _device_vec(key, device, make):
+    k = (key, str(device))
+    hit = _CONST_CACHE.get(k)
+    if hit is None:
+        hit = (None, make().to(device=device, dtype=F64).contiguous())
+        _CONST_CACHE[k] = hit
+    return hit[1]
+
+
 def _eigenvalues(terms: int, dim: int, device):
     """n (n + dim - 1), n < terms: Laplace-Beltrami eigenvalues of S^dim, cached per device."""
     key = ("lb", terms, dim, str(device))
@@ -167,10 +223,31 @@ def _eigenvalues(terms: int, dim: int, device):
     return hit[1]
 
 
+def _sphere_device(mode, ls, nu, dim, cst, zero_g):
+    terms = len(cst)
+    basis = choose_basis(terms)
+    mat = gegenbauer_to_monomial(terms, (dim - 1.0) / 2.0) if basis == _lib.BASIS_MONOMIAL else \
+        gegenbauer_to_chebyshev(terms, dim - 1)
+    coef = _SpectralCoef.apply(mode, _eigenvalues(terms, dim, ls.device), _const_vec(cst, ls.device),
+                               _const_vec(zero_g, ls.device), _t(mat, ls), dim / 2.0, ls, nu)
+    return coef, basis
+
+
+def _so3_device(mode, ls, nu, summands):
+    basis = choose_basis(summands)
+    dev = ls.device
+    lam = _device_vec(("so3lam", summands), dev, lambda: torch.arange(summands, dtype=F64) * (torch.arange(summands, dtype=F64) + 1))
+    dims = _device_vec(("so3dim", summands), dev, lambda: 2 * torch.arange(summands, dtype=F64) + 1)
+    coef = _SpectralCoef.apply(mode, lam, dims, dims, _t(_so3_matrix(summands, basis), ls), 1.5, ls, nu)
+    return coef, basis
+
+
 def sphere_matern_coef(lengthscale, nu, dim, cst, zero_g):
     """kernels_sphere.py:126-139."""
     ls, nu = lengthscale.reshape(()).to(F64), nu.reshape(()).to(F64)
     terms = len(cst)
+    if ls.is_cuda:
+        return _sphere_device(0, ls, nu, dim, cst, zero_g)
     base = 2 * nu / ls ** 2
     power = -(nu + dim / 2)
     e = torch.pow(base + _eigenvalues(terms, dim, ls.device), power) / torch.pow(base, power)
@@ -182,6 +259,8 @@ def sphere_gaussian_coef(lengthscale, dim, cst, zero_g):
     """kernels_sphere.py:212-224."""
     ls = lengthscale.reshape(()).to(F64)
     terms = len(cst)
+    if ls.is_cuda:
+        return _sphere_device(1, ls, None, dim, cst, zero_g)
     e = torch.exp(-ls ** 2 / 2.0 * _eigenvalues(terms, dim, ls.device))
     c, g = _const_vec(cst, ls.device), _const_vec(zero_g, ls.device)
     return _sphere_finish(e * c, g, dim)
@@ -293,6 +372,8 @@ def _so3_finish(lam: torch.Tensor):
 def so3_matern_coef(lengthscale, nu, summands):
     """(2 nu/kappa^2 + l(l+1))^(-nu - 3/2) (2l+1); kernels_so.py:264-273 (so_dim = 3)."""
     ls, nu = lengthscale.reshape(()).to(F64), nu.reshape(()).to(F64)
+    if ls.is_cuda:
+        return _so3_device(0, ls, nu, summands)
     l = torch.arange(summands, dtype=F64, device=ls.device)
     return _so3_finish(torch.pow(2 * nu / ls ** 2 + l * (l + 1), -nu - 1.5) * (2 * l + 1))
 
@@ -300,6 +381,8 @@ def so3_matern_coef(lengthscale, nu, summands):
 def so3_gaussian_coef(lengthscale, summands):
     """exp(-l(l+1) kappa^2 / 2) (2l+1); kernels_so.py:101."""
     ls = lengthscale.reshape(()).to(F64)
+    if ls.is_cuda:
+        return _so3_device(1, ls, None, summands)
     l = torch.arange(summands, dtype=F64, device=ls.device)
     return _so3_finish(torch.exp(-l * (l + 1) * ls ** 2 / 2) * (2 * l + 1))
 

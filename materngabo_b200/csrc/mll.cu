@@ -328,9 +328,90 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_kernel(MllParams p)
   if (tid == 0 && p.status) *p.status = bad;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Spectral coefficients of the sphere / SO(3) series kernels and their Jacobian in ONE launch.
+//   a_n   = c_n f(lambda_n; kappa, nu),   f = ((b + lambda) / b)^-(nu + h), b = 2 nu / kappa^2   (Matern, mode 0)
+//                                         f = exp(-kappa^2 lambda / 2)                            (heat, mode 1)
+//   w     = a / sum_n a_n g_n,   coef = w M            (M: T x Tout basis-change matrix)
+//   jac[0] = d coef / d kappa,  jac[1] = d coef / d nu
+// (kernels_sphere.py:126-139,212-224 with c = cst_nd, g = zero_gpolynomials, lambda_n = n (n + d - 1), h = d / 2;
+//  kernels_so.py:264-273,101 with c = g = 2l + 1, lambda_l = l (l + 1), h = 3/2.)  In torch this chain and its
+// backward are ~60 tiny kernels per marginal-likelihood evaluation - half of a graph-replayed step at N = 100.
+// ------------------------------------------------------------------------------------------------
+struct CoefParams {
+  int mode, T, Tout;
+  const double* lam; const double* c; const double* g; const double* M;
+  double half_dim;
+  const double* kappa; const double* nu;
+  double* coef; double* jac;
+};
+
+__global__ void __launch_bounds__(128) spectral_coef_kernel(CoefParams p) {
+  __shared__ double a[MGB_MAX_TERMS], da_k[MGB_MAX_TERMS], da_n[MGB_MAX_TERMS];
+  __shared__ double red[3];
+  const int tid = threadIdx.x;
+  const double kappa = *p.kappa, nu = (p.nu != nullptr) ? *p.nu : 0.0;
+  if (tid < 3) red[tid] = 0.0;
+  __syncthreads();
+  for (int n = tid; n < p.T; n += blockDim.x) {
+    const double lam = p.lam[n], c = p.c[n];
+    double e, dek, den;
+    if (p.mode == 0) {
+      const double b = 2.0 * nu / (kappa * kappa), pw = nu + p.half_dim;
+      const double lr = log1p(lam / b);                     // log((b + lambda) / b)
+      e = exp(-pw * lr);
+      const double deb = -pw * e * (1.0 / (b + lam) - 1.0 / b);
+      dek = deb * (-2.0 * b / kappa);
+      den = deb * (2.0 / (kappa * kappa)) - e * lr;
+    } else {
+      e = exp(-0.5 * kappa * kappa * lam);
+      dek = -kappa * lam * e;
+      den = 0.0;
+    }
+    a[n] = c * e;
+    da_k[n] = c * dek;
+    da_n[n] = c * den;
+  }
+  __syncthreads();
+  if (tid < 3) {   // fixed summation order: deterministic coefficients
+    const double* src = (tid == 0) ? a : ((tid == 1) ? da_k : da_n);
+    double acc = 0.0;
+    for (int n = 0; n < p.T; ++n) acc = fma(src[n], p.g[n], acc);
+    red[tid] = acc;
+  }
+  __syncthreads();
+  const double S = red[0], dSk = red[1], dSn = red[2];
+  for (int o = tid; o < p.Tout; o += blockDim.x) {
+    double v = 0.0, vk = 0.0, vn = 0.0;
+    for (int n = 0; n < p.T; ++n) {
+      const double m = p.M[n * p.Tout + o];
+      const double w = a[n] / S;
+      v = fma(w, m, v);
+      vk = fma((da_k[n] - w * dSk) / S, m, vk);
+      vn = fma((da_n[n] - w * dSn) / S, m, vn);
+    }
+    p.coef[o] = v;
+    p.jac[o] = vk;
+    p.jac[p.Tout + o] = vn;
+  }
+}
+
 }  // namespace mgb
 
 using namespace mgb;
+
+extern "C" int mgb_spectral_coef(int mode, int n_terms, int n_out, const double* lam, const double* c, const double* g,
+                                 const double* M, double half_dim, const double* kappa, const double* nu, double* coef,
+                                 double* jac, void* stream) {
+  if (!lam || !c || !g || !M || !kappa || !coef || !jac) return fail(MGB_ERR_ARG, "spectral_coef: null pointer");
+  if (mode != 0 && mode != 1) return fail(MGB_ERR_ARG, "spectral_coef: mode must be 0 (Matern) or 1 (heat)");
+  if (mode == 0 && !nu) return fail(MGB_ERR_ARG, "spectral_coef: the Matern form needs nu");
+  if (n_terms < 1 || n_terms > MGB_MAX_TERMS || n_out < 1 || n_out > MGB_MAX_TERMS) return fail(MGB_ERR_ARG, "spectral_coef: bad sizes");
+  CoefParams p{mode, n_terms, n_out, lam, c, g, M, half_dim, kappa, nu, coef, jac};
+  spectral_coef_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("spectral_coef_kernel");
+}
+
 
 extern "C" long long mgb_series_mll_max_n(int factor_width, int n_terms) {
   // two packed triangles + inputs + vectors within 220 KB of shared memory

@@ -91,3 +91,35 @@ def test_fused_mll_so3_and_circle_and_failure_flag():
     # not positive definite: negative "noise" larger than the smallest eigenvalue
     lf, info = exact_mll(k, xr, y, -5.0, 0.0)
     assert int(info) > 0 and not torch.isfinite(lf)
+
+
+def test_device_coefficient_op_matches_the_torch_formulas():
+    """mgb_spectral_coef (coefficients + Jacobian in one launch) against the torch definition evaluated on the CPU:
+    values and gradients for the sphere (Matern with learnable nu, heat) and SO(3) kernels."""
+    from materngabo_b200 import kernels_so, kernels_sphere
+
+    def compare(make, raw):
+        dev_k, cpu_k = make().to(DEV), make()
+        outs = []
+        for k in (dev_k, cpu_k):
+            with torch.no_grad():
+                for name, v in raw.items():
+                    getattr(k, name).fill_(v)
+            params = [getattr(k, name) for name in raw]
+            for p in params:
+                p.requires_grad_(True)
+            spec, coef = k.series()
+            w = torch.linspace(0.3, 1.7, coef.numel(), dtype=torch.float64, device=coef.device).reshape(coef.shape)
+            g = torch.autograd.grad((coef * w).sum(), params)
+            outs.append((spec.basis, coef.detach().cpu(), [t.detach().cpu() for t in g]))
+        assert outs[0][0] == outs[1][0]
+        assert rel_err(outs[0][1], outs[1][1]) < 1e-13
+        for a, b in zip(outs[0][2], outs[1][2]):
+            assert _close(a, b, 1e-11)
+
+    compare(lambda: kernels_sphere.SphereRiemannianMaternKernel(dim=3, nu=None), {"raw_lengthscale": -0.4, "raw_nu": 0.9})
+    compare(lambda: kernels_sphere.SphereRiemannianMaternKernel(dim=10, nu=None), {"raw_lengthscale": 0.3, "raw_nu": 2.0})
+    compare(lambda: kernels_sphere.SphereRiemannianMaternKernel(dim=2, nu=None, serie_nb_terms=20), {"raw_lengthscale": 0.1, "raw_nu": 1.0})
+    compare(lambda: kernels_sphere.SphereRiemannianGaussianKernel(dim=3), {"raw_lengthscale": -0.8})
+    compare(lambda: kernels_so.SORiemannianMaternKernel(dim=3, nu=None), {"raw_lengthscale": -0.2, "raw_nu": 1.3})
+    compare(lambda: kernels_so.SORiemannianGaussianKernel(dim=3), {"raw_lengthscale": 0.2})
