@@ -162,7 +162,6 @@ class _SpectralCoef(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mode, lam, c, g, mat, half_dim, kappa, nu):
-        import ctypes as C
         lib = _lib.load()
         t, tout = mat.shape
         coef = torch.empty((1, tout), dtype=F64, device=kappa.device)

@@ -11,7 +11,7 @@ script evaluates that polynomial at permuted / conjugated arguments.  Result (re
          eigen-solver happens to deflate the two conjugate pairs; there is no function of (R1, R2) to be at parity with.
 Usage: python -m oracle.probe_so_n_symmetry 4|5|6
 """
-import time, torch, warnings, itertools, sys
+import torch, warnings, itertools, sys
 warnings.simplefilter("ignore")
 torch.set_default_dtype(torch.float64)
 from oracle import reference_loader as rl
