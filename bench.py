@@ -637,6 +637,21 @@ def run_bo_latency(args, local):
         return float(value)
 
     lat["ei_value_grad_hvp_b1_graph_us"] = timeit(tr_graph, reps)
+
+    # the same three quantities from ONE fused launch (csrc/acquisition.cu), one candidate and all 5 restarts at once
+    def tr_fused():
+        ei, g, h = acq.value_grad_hvp(x1, v1)
+        return float(ei)                     # pymanopt's solver reads the cost back on the host
+
+    lat["ei_value_grad_hvp_b1_fused_us"] = timeit(tr_fused, reps)
+    x5 = torch.nn.functional.normalize(torch.randn(5, 1, 4, generator=gen), dim=-1).to(dev)
+    v5 = torch.randn(5, 1, 4, generator=gen).to(dev)
+
+    def tr_fused5():
+        ei, g, h = acq.value_grad_hvp(x5, v5)
+        return ei.cpu()
+
+    lat["ei_value_grad_hvp_b5_fused_us"] = timeit(tr_fused5, reps)
     launches = lib.mgb_launch_count() - launches0
     clocks = sampler.stop()
     cpu = None

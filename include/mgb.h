@@ -271,6 +271,24 @@ long long mgb_series_mll_max_n(int factor_width, int n_terms);
 int mgb_series_mll(const mgb_series_desc* desc, const double* x, long long n, long long ld, const double* y,
                    const double* coef, const double* hyper, double* out, int* status, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused analytic Expected Improvement with gradient and Hessian-vector product (csrc/acquisition.cu): what the
+ * pymanopt cost / egrad / ehess closures of the reference compute with botorch + torch autograd at one point per call
+ * (manifold_optimization/manifold_optimize.py:184-217; pymanopt_addons/tools/autodiff/_pytorch.py:89-116), for a batch
+ * of b candidates (e.g. all restarts) in one launch.  Single-factor series kernels; coef includes the outputscale.
+ *   rinv = L^-1 (n x n row-major, lower triangle used), rinv_t its transpose (upper triangle used), alpha = Kt^-1 (y - m)
+ *   EI = sigma (phi(u) + u Phi(u)), sigma = sqrt(max(var, 1e-9)), u = +-(mean - best_f) / sigma (+: maximize != 0)
+ *   ei[c];  grad[c*W + k] = d EI / d xc[c][k] (may be NULL);  hvp[c*W + k] = sum_l d2 EI / dx_k dx_l v[c][l]
+ *   (v, hvp may be NULL);  mean, var: optional posterior outputs.  Pairs where the clamp of the pair scalar is
+ *   active contribute zero gradient, as torch.clamp does in the reference.  n <= ~2800 (shared-memory vectors).
+ * ------------------------------------------------------------------------------------------------ */
+int mgb_series_acquisition_ei(const mgb_series_desc* desc, const double* xc, long long b, long long ldc,
+                              const double* v, long long ldv, const double* xtrain, long long n, long long ldt,
+                              const double* coef, const double* rinv, long long ldr, const double* rinv_t,
+                              long long ldrt, const double* alpha, double kss, double mean_const, double best_f,
+                              int maximize, double* ei, double* grad, double* hvp, double* mean, double* var,
+                              void* stream);
+
 /* Series coefficients of the sphere / SO(3) kernels and their Jacobian with respect to (kappa, nu) in one launch
  * (the hyper-parameter -> coefficient chain of kernels_sphere.py:126-139,212-224 and kernels_so.py:264-273,101, which
  * torch autograd otherwise spreads over ~60 tiny kernels per marginal-likelihood evaluation):

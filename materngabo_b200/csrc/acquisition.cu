@@ -1,0 +1,247 @@
+// Fused analytic Expected Improvement with gradient and Hessian-vector product at a batch of candidates
+// (the trust-region inner loop).
+//
+// What it replaces: the pymanopt cost / egrad / ehess closures of the reference
+// (manifold_optimization/manifold_optimize.py:184-217, pymanopt_addons/tools/autodiff/_pytorch.py:89-116), each of
+// which runs botorch's ExpectedImprovement on gpytorch's exact-GP posterior at ONE point and differentiates it with
+// torch autograd (once for egrad, twice for ehess): ~150 tiny launches per call, thousands of calls per BO iteration
+// (num_restarts x trust-region iterations x truncated-CG steps).  Here one CTA per candidate evaluates, for a
+// single-factor series kernel k_j = p(u_j), u_j = clamp(scale <x, x_j> + shift):
+//     mu = m + k.alpha,   w = R k,   var = kss - |w|^2,   beta = R^T w                       (R = L^-1, lower)
+//     grad mu  = sum_j alpha_j k'_j x_j,        grad var = -2 sum_j beta_j k'_j x_j           (k' includes scale and the
+//     Hess mu v  = sum_j alpha_j k''_j (x_j.v) x_j                                             clamp mask, as autograd does)
+//     Hess var v = -2 [ sum_j (R^T R dk)_j k'_j x_j + sum_j beta_j k''_j (x_j.v) x_j ],  dk_j = k'_j (x_j.v)
+// and chains them through EI(mu, var) = sigma (phi(u) + u Phi(u)), sigma = sqrt(max(var, 1e-9)), analytically.
+// The candidates of all restarts go into one launch (grid = number of candidates).
+#include "mgb_common.cuh"
+#include <cmath>
+
+namespace mgb {
+
+constexpr int AQ_THREADS = 256;
+constexpr int AQ_WARPS = AQ_THREADS / 32;
+constexpr int AQ_MAXD = 32;
+
+struct AcqParams {
+  const double* xc; long long b, ldc;
+  const double* v; long long ldv;              // directions for the Hessian-vector product (may be null)
+  const double* xt; int n; long long ldt;
+  const double* coef;
+  const double* R; long long ldr;              // L^-1, row-major lower triangle
+  const double* Rt; long long ldrt;            // its transpose, row-major (upper triangle)
+  const double* alpha;
+  double kss, mean_const, best_f; int maximize;
+  double* ei; double* grad; double* hvp; double* mean; double* var;
+  int W, T, basis;
+  double scale, shift, lo, hi;
+};
+
+// p(u), p'(u), p''(u)
+__device__ __forceinline__ void series_d2(const AcqParams& p, const double* cf, double u, double& f, double& f1, double& f2) {
+  if (p.basis == MGB_BASIS_MONOMIAL) {
+    double b = cf[p.T - 1], d1 = 0.0, d2 = 0.0;
+    for (int k = p.T - 2; k >= 0; --k) {
+      d2 = fma(d2, u, d1);
+      d1 = fma(d1, u, b);
+      b = fma(b, u, cf[k]);
+    }
+    f = b; f1 = d1; f2 = 2.0 * d2;
+    return;
+  }
+  // Chebyshev: T, T', T'' by the differentiated three-term recurrence
+  double t0 = 1.0, t1 = u, a0 = 0.0, a1 = 1.0, c0 = 0.0, c1 = 0.0;
+  f = cf[0] + ((p.T > 1) ? cf[1] * u : 0.0);
+  f1 = (p.T > 1) ? cf[1] : 0.0;
+  f2 = 0.0;
+  for (int k = 2; k < p.T; ++k) {
+    const double t2 = fma(2.0 * u, t1, -t0);
+    const double a2 = fma(2.0 * u, a1, 2.0 * t1 - a0);
+    const double c2 = fma(2.0 * u, c1, 4.0 * a1 - c0);
+    f = fma(cf[k], t2, f);
+    f1 = fma(cf[k], a2, f1);
+    f2 = fma(cf[k], c2, f2);
+    t0 = t1; t1 = t2; a0 = a1; a1 = a2; c0 = c1; c1 = c2;
+  }
+}
+
+// out[i] = sum_j M[i][j] in[j] over j in [jlo(i), jhi(i)): warp per row, lanes over columns (coalesced rows)
+__device__ __forceinline__ void tri_matvec(const double* M, long long ld, const double* in, double* out, int n, bool lower,
+                                           int warp, int lane) {
+  for (int i = warp; i < n; i += AQ_WARPS) {
+    const double* row = M + (long long)i * ld;
+    const int j0 = lower ? 0 : i, j1 = lower ? i + 1 : n;
+    double s = 0.0;
+    for (int j = j0 + lane; j < j1; j += 32) s = fma(__ldg(row + j), in[j], s);
+    s = warp_sum(s);
+    if (lane == 0) out[i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(AQ_THREADS) series_acquisition_kernel(AcqParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int n = p.n;
+  double* k0 = sm;            // k_j
+  double* k1 = k0 + n;        // k'_j (scale and clamp mask included)
+  double* k2 = k1 + n;        // k''_j
+  double* w = k2 + n;         // R k
+  double* be = w + n;         // R^T w
+  double* dk = be + n;        // k'_j (x_j . v)
+  double* w2 = dk + n;        // R dk
+  double* b2 = w2 + n;        // R^T R dk
+  double* xv = b2 + n;        // x_j . v
+  double* cfs = xv + n;       // T
+  double* red = cfs + p.T;    // 2 + 4 * W reduction slots
+  __shared__ double xs[AQ_MAXD], vs[AQ_MAXD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long c = blockIdx.x;
+  const bool want_h = (p.v != nullptr) && (p.hvp != nullptr);
+  const int W = p.W;
+
+  for (int e = tid; e < p.T; e += AQ_THREADS) cfs[e] = p.coef[e];
+  if (tid < W) {
+    xs[tid] = p.xc[c * p.ldc + tid];
+    vs[tid] = want_h ? p.v[c * p.ldv + tid] : 0.0;
+  }
+  for (int e = tid; e < 2 + 4 * W; e += AQ_THREADS) red[e] = 0.0;
+  __syncthreads();
+
+  // ---- kernel row and its derivatives in the pair scalar -------------------------------------------
+  for (int j = tid; j < n; j += AQ_THREADS) {
+    const double* xj = p.xt + (long long)j * p.ldt;
+    double d = 0.0, pv = 0.0;
+    for (int k = 0; k < W; ++k) {
+      const double t = __ldg(xj + k);
+      d = fma(xs[k], t, d);
+      pv = fma(vs[k], t, pv);
+    }
+    const double raw = fma(d, p.scale, p.shift);
+    const bool inside = (raw >= p.lo) && (raw <= p.hi);
+    const double u = (raw < p.lo) ? p.lo : ((raw > p.hi) ? p.hi : raw);
+    double f, f1, f2;
+    series_d2(p, cfs, u, f, f1, f2);
+    k0[j] = f;
+    k1[j] = inside ? f1 * p.scale : 0.0;
+    k2[j] = inside ? f2 * p.scale * p.scale : 0.0;
+    xv[j] = pv;
+    dk[j] = k1[j] * pv;
+  }
+  __syncthreads();
+  tri_matvec(p.R, p.ldr, k0, w, n, true, warp, lane);
+  if (want_h) tri_matvec(p.R, p.ldr, dk, w2, n, true, warp, lane);
+  __syncthreads();
+  tri_matvec(p.Rt, p.ldrt, w, be, n, false, warp, lane);
+  if (want_h) tri_matvec(p.Rt, p.ldrt, w2, b2, n, false, warp, lane);
+  __syncthreads();
+
+  // ---- reductions: mu - m, |w|^2, and the four W-vectors -------------------------------------------
+  // red[0] = k.alpha, red[1] = |w|^2, red[2 + k] = grad mu, [2 + W + k] = -1/2 grad var,
+  // red[2 + 2W + k] = Hess mu v, red[2 + 3W + k] = -1/2 Hess var v
+  {
+    double s_mu = 0.0, s_w = 0.0;
+    for (int j = tid; j < n; j += AQ_THREADS) {
+      s_mu = fma(k0[j], __ldg(p.alpha + j), s_mu);
+      s_w = fma(w[j], w[j], s_w);
+    }
+    s_mu = warp_sum(s_mu);
+    s_w = warp_sum(s_w);
+    if (lane == 0) {
+      atomicAdd(red + 0, s_mu);
+      atomicAdd(red + 1, s_w);
+    }
+  }
+  for (int k = 0; k < W; ++k) {
+    double g_mu = 0.0, g_var = 0.0, h_mu = 0.0, h_var = 0.0;
+    for (int j = tid; j < n; j += AQ_THREADS) {
+      const double xjk = __ldg(p.xt + (long long)j * p.ldt + k);
+      const double a = __ldg(p.alpha + j);
+      g_mu = fma(a * k1[j], xjk, g_mu);
+      g_var = fma(be[j] * k1[j], xjk, g_var);
+      if (want_h) {
+        h_mu = fma(a * k2[j] * xv[j], xjk, h_mu);
+        h_var = fma(fma(b2[j], k1[j], be[j] * k2[j] * xv[j]), xjk, h_var);
+      }
+    }
+    g_mu = warp_sum(g_mu);
+    g_var = warp_sum(g_var);
+    h_mu = warp_sum(h_mu);
+    h_var = warp_sum(h_var);
+    if (lane == 0) {
+      atomicAdd(red + 2 + k, g_mu);
+      atomicAdd(red + 2 + W + k, g_var);
+      atomicAdd(red + 2 + 2 * W + k, h_mu);
+      atomicAdd(red + 2 + 3 * W + k, h_var);
+    }
+  }
+  __syncthreads();
+
+  // ---- EI and its derivatives in (mu, var) ----------------------------------------------------------
+  if (tid < W || tid == 0) {
+    const double mu = p.mean_const + red[0];
+    const double var = p.kss - red[1];
+    const bool clamped = !(var > 1e-9);
+    const double sigma = sqrt(clamped ? 1e-9 : var);
+    const double sg = p.maximize ? 1.0 : -1.0;
+    const double u = sg * (mu - p.best_f) / sigma;
+    const double pdf = exp(-0.5 * u * u) * 0.3989422804014327;
+    const double cdf = 0.5 * erfc(-u * 0.7071067811865476);
+    const double ei = sigma * (pdf + u * cdf);
+    // first derivatives
+    const double e_m = sg * cdf;
+    const double e_v = clamped ? 0.0 : pdf / (2.0 * sigma);
+    // second derivatives
+    const double e_mm = pdf / sigma;
+    const double e_mv = clamped ? 0.0 : -sg * u * pdf / (2.0 * sigma * sigma);
+    const double e_vv = clamped ? 0.0 : pdf * (u * u - 1.0) / (4.0 * sigma * sigma * sigma);
+    if (tid == 0) {
+      p.ei[c] = ei;
+      if (p.mean) p.mean[c] = mu;
+      if (p.var) p.var[c] = var;
+    }
+    if (tid < W) {
+      const double gm = red[2 + tid], gv = -2.0 * red[2 + W + tid];
+      if (p.grad) p.grad[c * W + tid] = e_m * gm + e_v * gv;
+      if (want_h) {
+        // directional derivatives of mu and var along v
+        double dmu = 0.0, dvar = 0.0;
+        for (int k = 0; k < W; ++k) {
+          dmu = fma(red[2 + k], vs[k], dmu);
+          dvar = fma(-2.0 * red[2 + W + k], vs[k], dvar);
+        }
+        const double hm = red[2 + 2 * W + tid], hv = -2.0 * red[2 + 3 * W + tid];
+        p.hvp[c * W + tid] = (e_mm * dmu + e_mv * dvar) * gm + (e_mv * dmu + e_vv * dvar) * gv + e_m * hm + e_v * hv;
+      }
+    }
+  }
+}
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" int mgb_series_acquisition_ei(const mgb_series_desc* d, const double* xc, long long b, long long ldc,
+                                         const double* v, long long ldv, const double* xtrain, long long n,
+                                         long long ldt, const double* coef, const double* rinv, long long ldr,
+                                         const double* rinv_t, long long ldrt, const double* alpha, double kss,
+                                         double mean_const, double best_f, int maximize, double* ei, double* grad,
+                                         double* hvp, double* mean, double* var, void* stream) {
+  if (b == 0) return MGB_OK;
+  if (!d || !xc || !xtrain || !coef || !rinv || !rinv_t || !alpha || !ei) return fail(MGB_ERR_ARG, "series_acquisition_ei: null pointer");
+  if (d->n_factors != 1 || d->pair_square) return fail(MGB_ERR_ARG, "series_acquisition_ei: single-factor kernels in the affine form only");
+  if (d->factor_width < 1 || d->factor_width > AQ_MAXD) return fail(MGB_ERR_ARG, "series_acquisition_ei: factor width out of range [1,32]");
+  if (d->n_terms < 1 || d->n_terms > MGB_MAX_TERMS) return fail(MGB_ERR_ARG, "series_acquisition_ei: bad n_terms");
+  if (d->basis != MGB_BASIS_MONOMIAL && d->basis != MGB_BASIS_CHEBYSHEV) return fail(MGB_ERR_ARG, "series_acquisition_ei: bad basis");
+  const int W = d->factor_width;
+  if (b < 0 || n < 1 || ldc < W || ldt < W || ldr < n || ldrt < n || (v && ldv < W)) return fail(MGB_ERR_ARG, "series_acquisition_ei: bad sizes");
+  if (hvp && !v) return fail(MGB_ERR_ARG, "series_acquisition_ei: hvp requested without directions");
+  if (n > 16000) return fail(MGB_ERR_ARG, "series_acquisition_ei: n too large for the shared-memory vectors");
+  if (b > 0x7fffffffLL) return fail(MGB_ERR_ARG, "series_acquisition_ei: too many candidates for one launch");
+  AcqParams p{xc, b, ldc, v, ldv, xtrain, (int)n, ldt, coef, rinv, ldr, rinv_t, ldrt, alpha, kss, mean_const, best_f,
+              maximize, ei, grad, hvp, mean, var, W, d->n_terms, d->basis, d->scale, d->shift, d->lo, d->hi};
+  const size_t smem = sizeof(double) * (size_t)(9 * n + d->n_terms + 2 + 4 * W);
+  if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "series_acquisition_ei: n too large for the shared-memory vectors");
+  if (smem > 48 * 1024)
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(series_acquisition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute"));
+  series_acquisition_kernel<<<(unsigned)b, AQ_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("series_acquisition_kernel");
+}

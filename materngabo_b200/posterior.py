@@ -106,6 +106,7 @@ class ExactGPPosterior:
         L = torch.linalg.cholesky(k)
         self.alpha = torch.cholesky_solve((self.train_y - self.mean_const).unsqueeze(-1), L).squeeze(-1).contiguous()
         self.rinv = torch.linalg.solve_triangular(L, torch.eye(n, dtype=F64, device=self.device), upper=False).contiguous()
+        self.rinv_t = self.rinv.t().contiguous()          # row access to the columns of L^-1 (fused acquisition kernel)
         self.spec, self.coef = spec, coef
         if self.is_series:
             self.kss_value = _self_kernel_value(spec, coef)
@@ -231,6 +232,46 @@ class ExactGPPosterior:
         return mean, var
 
 
+    # ---- fused EI value + gradient + Hessian-vector product (trust-region inner loop) ----------------------
+    @torch.no_grad()
+    def ei_value_grad_hvp(self, x: torch.Tensor, best_f: float, maximize: bool = True, v: Optional[torch.Tensor] = None):
+        """Analytic EI, dEI/dx and (with directions ``v``) the Hessian-vector product d2EI/dx2 v at every candidate of
+        ``x`` ((b, D) or botorch's (b, 1, D)) in ONE launch (csrc/acquisition.cu) - the three quantities the pymanopt
+        cost / egrad / ehess closures of the reference obtain from botorch + torch autograd
+        (manifold_optimize.py:184-217).  Single-factor series kernels (sphere, SO(3), circle); other kernels go
+        through ``posterior_autograd``.  Returns (ei, grad, hvp or None) shaped like ``x``."""
+        if self._packed is None or getattr(self, "rinv", None) is None:
+            raise RuntimeError("call fit() first")
+        if not self.is_series or self.spec.n_factors != 1 or hasattr(self.kernel, "_to_circles"):
+            raise NotImplementedError("fused acquisition derivatives are provided for single-factor series kernels")
+        _lib.require_cuda_f64(x, v)
+        shape = x.shape
+        xf = x.reshape(-1, shape[-1]).contiguous()
+        if x.dim() == 3 and shape[-2] != 1:
+            raise NotImplementedError("q > 1 joint posteriors are not provided by the analytic acquisition path")
+        vf = v.reshape(-1, shape[-1]).contiguous() if v is not None else None
+        b, w = xf.shape
+        if w != self.spec.factor_width:
+            raise RuntimeError("expected %d coordinates" % self.spec.factor_width)
+        n = self.train_prepared.shape[0]
+        ei = torch.empty(b, dtype=F64, device=self.device)
+        grad = torch.empty((b, w), dtype=F64, device=self.device)
+        hvp = torch.empty((b, w), dtype=F64, device=self.device) if vf is not None else None
+        lib = _lib.load()
+        d = self.spec.desc(self.coef.shape[-1])
+        with torch.cuda.device(self.device):
+            rc = lib.mgb_series_acquisition_ei(C.byref(d), _lib.ptr(xf), b, xf.stride(0), _lib.ptr(vf),
+                                               vf.stride(0) if vf is not None else 0, _lib.ptr(self.train_prepared), n,
+                                               self.train_prepared.stride(0), _lib.ptr(self.coef), _lib.ptr(self.rinv),
+                                               self.rinv.stride(0), _lib.ptr(self.rinv_t), self.rinv_t.stride(0),
+                                               _lib.ptr(self.alpha), float(self.kss_value), self.mean_const, float(best_f),
+                                               1 if maximize else 0, _lib.ptr(ei), _lib.ptr(grad), _lib.ptr(hvp), None, None,
+                                               _lib.stream_ptr(self.device))
+        _lib.check(rc, "mgb_series_acquisition_ei")
+        return ei.reshape(shape[:-1] if x.dim() == 2 else shape[:-2]), grad.reshape(shape), \
+            (hvp.reshape(shape) if hvp is not None else None)
+
+
 class ExpectedImprovement:
     """Analytic EI with botorch's call convention: ``acq(X)`` with ``X`` of shape ``b x 1 x D`` -> ``b``."""
 
@@ -245,6 +286,14 @@ class ExpectedImprovement:
         else:
             mean, var = self.model.posterior(x)              # scoring: fused kernels, no autograd
         return expected_improvement(mean, var, self.best_f, self.maximize)
+
+
+def _ei_value_grad_hvp(self, x, v=None):
+    """(EI, dEI/dx, d2EI/dx2 v) at every candidate in one fused launch; see ExactGPPosterior.ei_value_grad_hvp."""
+    return self.model.ei_value_grad_hvp(x, self.best_f, self.maximize, v)
+
+
+ExpectedImprovement.value_grad_hvp = _ei_value_grad_hvp
 
 
 def expected_improvement(mean, var, best_f, maximize=True):

@@ -230,3 +230,71 @@ def test_torus_second_order_input_gradient():
     g_dev, h_dev = hvp(lambda a, b: k.forward(a, b), c1.to(DEV), c2.to(DEV), G.to(DEV), v.to(DEV))
     assert rel_err(g_dev, g_ref) < 1e-9
     assert rel_err(h_dev, h_ref) < 1e-8
+
+
+@pytest.mark.parametrize("maximize", [False, True])
+def test_fused_acquisition_value_gradient_hvp(maximize):
+    """One launch for EI, its gradient and Hessian-vector product at a batch of candidates (csrc/acquisition.cu)
+    against torch autograd through the differentiable posterior path and through the oracle on the CPU."""
+    from materngabo_b200.posterior import ExpectedImprovement
+    from oracle import restated as R
+
+    gp, xc, _, (xt, y, _) = _setup(3, 60, 8, seed=21, outputscale=1.3, noise=1e-2, mean_const=0.2)
+    best = float(y.min()) if not maximize else float(y.max())
+    acq = ExpectedImprovement(gp, best_f=best, maximize=maximize)
+    gen = torch.Generator().manual_seed(5)
+    x = xc[:7].unsqueeze(-2).to(DEV)
+    v = torch.randn(7, 1, 4, generator=gen).to(DEV)
+    ei, grad, hvp = acq.value_grad_hvp(x, v)
+    assert ei.shape == (7,) and grad.shape == x.shape and hvp.shape == x.shape
+    xa = x.clone().requires_grad_(True)
+    val = acq(xa)
+    (ga,) = torch.autograd.grad(val.sum(), [xa], create_graph=True)
+    (ha,) = torch.autograd.grad((ga * v).sum(), [xa])
+    assert rel_err(ei, val) < 1e-12
+    assert rel_err(grad, ga) < 1e-10
+    assert rel_err(hvp, ha) < 1e-9
+
+    kfn = lambda a, b: R.sphere_matern(a, b, 3, 2.5, 0.5)  # noqa: E731
+    L, alpha = R.gp_fit(kfn, xt, y, 1.3, 1e-2, 0.2)
+    xo = x.cpu().clone().requires_grad_(True)
+    xs = xo.squeeze(-2)
+    ks = 1.3 * kfn(xs, xt)
+    mean = 0.2 + ks @ alpha
+    vv = torch.linalg.solve_triangular(L, ks.t(), upper=False)
+    var = 1.3 * kfn(xs[:1], xs[:1]).reshape(()).detach() - (vv * vv).sum(0)
+    eo = R.expected_improvement(mean, var, best, maximize=maximize)
+    (go,) = torch.autograd.grad(eo.sum(), [xo], create_graph=True)
+    (ho,) = torch.autograd.grad((go * v.cpu()).sum(), [xo])
+    assert rel_err(ei, eo) < 1e-9 and rel_err(grad, go) < 1e-8 and rel_err(hvp, ho) < 1e-7
+    # value + gradient only (no directions)
+    ei2, grad2, none = acq.value_grad_hvp(x.squeeze(-2))
+    assert none is None and torch.equal(ei2, ei) and torch.equal(grad2.reshape(grad.shape), grad)
+
+
+def test_fused_acquisition_so3_and_clamped_pairs():
+    """SO(3) (wide rows, clip at 1 - 1e-8) including candidates equal to training points, where the reference's clamp
+    zeroes the gradient contribution of that pair."""
+    from materngabo_b200 import kernels_so
+    from materngabo_b200.posterior import ExactGPPosterior, ExpectedImprovement
+
+    gen = torch.Generator().manual_seed(2)
+    q, r = torch.linalg.qr(torch.randn(48, 3, 3, generator=gen))
+    q = q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1)).unsqueeze(-2)
+    q[:, :, 0] *= torch.sign(torch.linalg.det(q)).unsqueeze(-1)
+    xr = q.reshape(48, 9)
+    xt, xc = xr[:40].to(DEV), torch.cat([xr[40:], xr[:2]]).to(DEV)     # the last two candidates ARE training points
+    y = torch.sin(xt[:, 0] * 2) + xt[:, 4]
+    k = kernels_so.SORiemannianMaternKernel(dim=3, nu=2.5).to(DEV)
+    k.lengthscale = 0.7
+    for p in k.parameters():
+        p.requires_grad_(False)
+    gp = ExactGPPosterior(k, xt, y, outputscale=1.0, noise=1e-2).fit()
+    acq = ExpectedImprovement(gp, best_f=float(y.min()), maximize=False)
+    v = torch.randn(10, 9, generator=gen).to(DEV)
+    ei, grad, hvp = acq.value_grad_hvp(xc, v)
+    xa = xc.clone().requires_grad_(True)
+    val = acq(xa.unsqueeze(-2))
+    (ga,) = torch.autograd.grad(val.sum(), [xa], create_graph=True)
+    (ha,) = torch.autograd.grad((ga * v).sum(), [xa])
+    assert rel_err(ei, val) < 1e-12 and rel_err(grad, ga) < 1e-10 and rel_err(hvp, ha) < 1e-9
