@@ -298,3 +298,30 @@ def test_fused_acquisition_so3_and_clamped_pairs():
     (ga,) = torch.autograd.grad(val.sum(), [xa], create_graph=True)
     (ha,) = torch.autograd.grad((ga * v).sum(), [xa])
     assert rel_err(ei, val) < 1e-12 and rel_err(grad, ga) < 1e-10 and rel_err(hvp, ha) < 1e-9
+
+
+@pytest.mark.parametrize("ls,n", [(0.5, 33), (0.15, 17), (0.5, 1)])
+def test_fused_acquisition_circle_both_bases_and_tiny_n(ls, n):
+    """Circle kernel: monomial (kappa = 0.5) and Chebyshev (kappa = 0.15, 60+ terms) series through the fused
+    acquisition kernel, and a single training point."""
+    from materngabo_b200 import kernels_sphere
+    from materngabo_b200.posterior import ExactGPPosterior, ExpectedImprovement
+
+    gen = torch.Generator().manual_seed(n)
+    ang = torch.rand(n + 6, generator=gen) * 6.28
+    pts = torch.stack([torch.cos(ang), torch.sin(ang)], -1)
+    xt, xc = pts[:n].to(DEV), pts[n:].to(DEV)
+    y = torch.sin(2 * ang[:n]).to(DEV)
+    k = kernels_sphere.CircleRiemannianIntegratedMaternKernel(nu=2.5).to(DEV)
+    k.lengthscale = ls
+    for p in k.parameters():
+        p.requires_grad_(False)
+    gp = ExactGPPosterior(k, xt, y, outputscale=0.8, noise=1e-2, mean_const=-0.1).fit()
+    acq = ExpectedImprovement(gp, best_f=float(y.max()), maximize=True)
+    v = torch.randn(6, 2, generator=gen).to(DEV)
+    ei, grad, hvp = acq.value_grad_hvp(xc, v)
+    xa = xc.clone().requires_grad_(True)
+    val = acq(xa.unsqueeze(-2))
+    (ga,) = torch.autograd.grad(val.sum(), [xa], create_graph=True)
+    (ha,) = torch.autograd.grad((ga * v).sum(), [xa])
+    assert rel_err(ei, val) < 1e-11 and rel_err(grad, ga) < 1e-9 and rel_err(hvp, ha) < 1e-8
