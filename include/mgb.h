@@ -275,10 +275,11 @@ int mgb_series_mll(const mgb_series_desc* desc, const double* x, long long n, lo
  * Fused analytic Expected Improvement with gradient and Hessian-vector product (csrc/acquisition.cu): what the
  * pymanopt cost / egrad / ehess closures of the reference compute with botorch + torch autograd at one point per call
  * (manifold_optimization/manifold_optimize.py:184-217; pymanopt_addons/tools/autodiff/_pytorch.py:89-116), for a batch
- * of b candidates (e.g. all restarts) in one launch.  Single-factor series kernels; coef includes the outputscale.
+ * of b candidates (e.g. all restarts) in one launch.  Series kernels with rows up to 32 wide (sphere, SO(3), circle;
+ * multi-factor = torus in (cos, sin) coordinates); coef includes the outputscale (on factor 0 for the torus).
  *   rinv = L^-1 (n x n row-major, lower triangle used), rinv_t its transpose (upper triangle used), alpha = Kt^-1 (y - m)
  *   EI = sigma (phi(u) + u Phi(u)), sigma = sqrt(max(var, 1e-9)), u = +-(mean - best_f) / sigma (+: maximize != 0)
- *   ei[c];  grad[c*W + k] = d EI / d xc[c][k] (may be NULL);  hvp[c*W + k] = sum_l d2 EI / dx_k dx_l v[c][l]
+ *   ei[c];  grad[c*D + k] = d EI / d xc[c][k] (may be NULL);  hvp[c*D + k] = sum_l d2 EI / dx_k dx_l v[c][l], D = F*W
  *   (v, hvp may be NULL);  mean, var: optional posterior outputs.  Pairs where the clamp of the pair scalar is
  *   active contribute zero gradient, as torch.clamp does in the reference.  n <= ~2800 (shared-memory vectors).
  * ------------------------------------------------------------------------------------------------ */

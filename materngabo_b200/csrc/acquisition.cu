@@ -214,6 +214,175 @@ __global__ void __launch_bounds__(AQ_THREADS) series_acquisition_kernel(AcqParam
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-factor variant (torus T^d = product of circles, kernel_utils/kernels_torus.py): k_j = prod_f p_f(u_fj) with
+// u_fj from coordinate block f (W wide) of x and x_j.  Per training point and factor:
+//     G_f = (prod_{g != f} p_g) p_f'          coefficient of x_j^f in grad k_j
+//     H_f = d G_f along v = (prod_{g != f} p_g) p_f'' t_f + p_f' sum_{g != f} (prod_{h != f,g} p_h) p_g' t_g,   t_f = x_j^f . v^f
+// (p', p'' include scale and the clamp mask).  Everything else is the single-factor algebra with k'_j x_j replaced by
+// the blocks G_f x_j^f.  Products are formed by loops (no division: a factor may vanish).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AQ_THREADS) series_acquisition_multi_kernel(AcqParams p, int F) {
+  extern __shared__ __align__(16) double sm[];
+  const int n = p.n, W = p.W, D = F * W;
+  double* k0 = sm;                 // k_j
+  double* w = k0 + n;              // R k
+  double* be = w + n;              // R^T w
+  double* dk = be + n;             // grad k_j . v
+  double* w2 = dk + n;             // R dk
+  double* b2 = w2 + n;             // R^T R dk
+  double* P = b2 + n;              // [F][n] p_f
+  double* P1 = P + F * n;          // [F][n] p_f'
+  double* P2 = P1 + F * n;         // [F][n] p_f''
+  double* Tf = P2 + F * n;         // [F][n] t_f
+  double* G = Tf + F * n;          // [F][n]
+  double* H = G + F * n;           // [F][n]
+  double* cfs = H + F * n;         // F * T
+  double* red = cfs + F * p.T;     // 2 + 4 * D
+  __shared__ double xs[AQ_MAXD], vs[AQ_MAXD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long c = blockIdx.x;
+  const bool want_h = (p.v != nullptr) && (p.hvp != nullptr);
+
+  for (int e = tid; e < F * p.T; e += AQ_THREADS) cfs[e] = p.coef[e];
+  if (tid < D) {
+    xs[tid] = p.xc[c * p.ldc + tid];
+    vs[tid] = want_h ? p.v[c * p.ldv + tid] : 0.0;
+  }
+  for (int e = tid; e < 2 + 4 * D; e += AQ_THREADS) red[e] = 0.0;
+  __syncthreads();
+
+  for (int j = tid; j < n; j += AQ_THREADS) {
+    const double* xj = p.xt + (long long)j * p.ldt;
+    double prod = 1.0;
+    for (int f = 0; f < F; ++f) {
+      double d = 0.0, pv = 0.0;
+      for (int k = 0; k < W; ++k) {
+        const double t = __ldg(xj + f * W + k);
+        d = fma(xs[f * W + k], t, d);
+        pv = fma(vs[f * W + k], t, pv);
+      }
+      const double raw = fma(d, p.scale, p.shift);
+      const bool inside = (raw >= p.lo) && (raw <= p.hi);
+      const double u = (raw < p.lo) ? p.lo : ((raw > p.hi) ? p.hi : raw);
+      double f0, f1, f2;
+      series_d2(p, cfs + f * p.T, u, f0, f1, f2);
+      P[f * n + j] = f0;
+      P1[f * n + j] = inside ? f1 * p.scale : 0.0;
+      P2[f * n + j] = inside ? f2 * p.scale * p.scale : 0.0;
+      Tf[f * n + j] = pv;
+      prod *= f0;
+    }
+    k0[j] = prod;
+    double dkj = 0.0;
+    for (int f = 0; f < F; ++f) {
+      double rest = 1.0;
+      for (int g = 0; g < F; ++g)
+        if (g != f) rest *= P[g * n + j];
+      const double gf = rest * P1[f * n + j];
+      G[f * n + j] = gf;
+      dkj = fma(gf, Tf[f * n + j], dkj);
+      double hf = 0.0;
+      if (want_h) {
+        hf = rest * P2[f * n + j] * Tf[f * n + j];
+        double cross = 0.0;
+        for (int g = 0; g < F; ++g) {
+          if (g == f) continue;
+          double r2 = 1.0;
+          for (int h = 0; h < F; ++h)
+            if (h != f && h != g) r2 *= P[h * n + j];
+          cross = fma(r2 * P1[g * n + j], Tf[g * n + j], cross);
+        }
+        hf = fma(P1[f * n + j], cross, hf);
+      }
+      H[f * n + j] = hf;
+    }
+    dk[j] = dkj;
+  }
+  __syncthreads();
+  tri_matvec(p.R, p.ldr, k0, w, n, true, warp, lane);
+  if (want_h) tri_matvec(p.R, p.ldr, dk, w2, n, true, warp, lane);
+  __syncthreads();
+  tri_matvec(p.Rt, p.ldrt, w, be, n, false, warp, lane);
+  if (want_h) tri_matvec(p.Rt, p.ldrt, w2, b2, n, false, warp, lane);
+  __syncthreads();
+
+  {
+    double s_mu = 0.0, s_w = 0.0;
+    for (int j = tid; j < n; j += AQ_THREADS) {
+      s_mu = fma(k0[j], __ldg(p.alpha + j), s_mu);
+      s_w = fma(w[j], w[j], s_w);
+    }
+    s_mu = warp_sum(s_mu);
+    s_w = warp_sum(s_w);
+    if (lane == 0) {
+      atomicAdd(red + 0, s_mu);
+      atomicAdd(red + 1, s_w);
+    }
+  }
+  for (int q = 0; q < D; ++q) {
+    const int f = q / W;
+    double g_mu = 0.0, g_var = 0.0, h_mu = 0.0, h_var = 0.0;
+    for (int j = tid; j < n; j += AQ_THREADS) {
+      const double xjq = __ldg(p.xt + (long long)j * p.ldt + q);
+      const double a = __ldg(p.alpha + j);
+      const double gf = G[f * n + j];
+      g_mu = fma(a * gf, xjq, g_mu);
+      g_var = fma(be[j] * gf, xjq, g_var);
+      if (want_h) {
+        const double hf = H[f * n + j];
+        h_mu = fma(a * hf, xjq, h_mu);
+        h_var = fma(fma(b2[j], gf, be[j] * hf), xjq, h_var);
+      }
+    }
+    g_mu = warp_sum(g_mu);
+    g_var = warp_sum(g_var);
+    h_mu = warp_sum(h_mu);
+    h_var = warp_sum(h_var);
+    if (lane == 0) {
+      atomicAdd(red + 2 + q, g_mu);
+      atomicAdd(red + 2 + D + q, g_var);
+      atomicAdd(red + 2 + 2 * D + q, h_mu);
+      atomicAdd(red + 2 + 3 * D + q, h_var);
+    }
+  }
+  __syncthreads();
+
+  if (tid < D || tid == 0) {
+    const double mu = p.mean_const + red[0];
+    const double var = p.kss - red[1];
+    const bool clamped = !(var > 1e-9);
+    const double sigma = sqrt(clamped ? 1e-9 : var);
+    const double sg = p.maximize ? 1.0 : -1.0;
+    const double u = sg * (mu - p.best_f) / sigma;
+    const double pdf = exp(-0.5 * u * u) * 0.3989422804014327;
+    const double cdf = 0.5 * erfc(-u * 0.7071067811865476);
+    const double e_m = sg * cdf;
+    const double e_v = clamped ? 0.0 : pdf / (2.0 * sigma);
+    const double e_mm = pdf / sigma;
+    const double e_mv = clamped ? 0.0 : -sg * u * pdf / (2.0 * sigma * sigma);
+    const double e_vv = clamped ? 0.0 : pdf * (u * u - 1.0) / (4.0 * sigma * sigma * sigma);
+    if (tid == 0) {
+      p.ei[c] = sigma * (pdf + u * cdf);
+      if (p.mean) p.mean[c] = mu;
+      if (p.var) p.var[c] = var;
+    }
+    if (tid < D) {
+      const double gm = red[2 + tid], gv = -2.0 * red[2 + D + tid];
+      if (p.grad) p.grad[c * D + tid] = e_m * gm + e_v * gv;
+      if (want_h) {
+        double dmu = 0.0, dvar = 0.0;
+        for (int k = 0; k < D; ++k) {
+          dmu = fma(red[2 + k], vs[k], dmu);
+          dvar = fma(-2.0 * red[2 + D + k], vs[k], dvar);
+        }
+        const double hm = red[2 + 2 * D + tid], hv = -2.0 * red[2 + 3 * D + tid];
+        p.hvp[c * D + tid] = (e_mm * dmu + e_mv * dvar) * gm + (e_mv * dmu + e_vv * dvar) * gv + e_m * hm + e_v * hv;
+      }
+    }
+  }
+}
+
 }  // namespace mgb
 
 using namespace mgb;
@@ -226,17 +395,27 @@ extern "C" int mgb_series_acquisition_ei(const mgb_series_desc* d, const double*
                                          double* hvp, double* mean, double* var, void* stream) {
   if (b == 0) return MGB_OK;
   if (!d || !xc || !xtrain || !coef || !rinv || !rinv_t || !alpha || !ei) return fail(MGB_ERR_ARG, "series_acquisition_ei: null pointer");
-  if (d->n_factors != 1 || d->pair_square) return fail(MGB_ERR_ARG, "series_acquisition_ei: single-factor kernels in the affine form only");
-  if (d->factor_width < 1 || d->factor_width > AQ_MAXD) return fail(MGB_ERR_ARG, "series_acquisition_ei: factor width out of range [1,32]");
+  if (d->pair_square) return fail(MGB_ERR_ARG, "series_acquisition_ei: affine pair scalar only");
+  if (d->n_factors < 1 || d->n_factors > MGB_MAX_FACTORS) return fail(MGB_ERR_ARG, "series_acquisition_ei: n_factors out of range");
+  if (d->factor_width < 1 || d->n_factors * d->factor_width > AQ_MAXD) return fail(MGB_ERR_ARG, "series_acquisition_ei: row width out of range [1,32]");
   if (d->n_terms < 1 || d->n_terms > MGB_MAX_TERMS) return fail(MGB_ERR_ARG, "series_acquisition_ei: bad n_terms");
   if (d->basis != MGB_BASIS_MONOMIAL && d->basis != MGB_BASIS_CHEBYSHEV) return fail(MGB_ERR_ARG, "series_acquisition_ei: bad basis");
-  const int W = d->factor_width;
-  if (b < 0 || n < 1 || ldc < W || ldt < W || ldr < n || ldrt < n || (v && ldv < W)) return fail(MGB_ERR_ARG, "series_acquisition_ei: bad sizes");
+  const int W = d->factor_width, F = d->n_factors, D = F * W;
+  if (b < 0 || n < 1 || ldc < D || ldt < D || ldr < n || ldrt < n || (v && ldv < D)) return fail(MGB_ERR_ARG, "series_acquisition_ei: bad sizes");
   if (hvp && !v) return fail(MGB_ERR_ARG, "series_acquisition_ei: hvp requested without directions");
   if (n > 16000) return fail(MGB_ERR_ARG, "series_acquisition_ei: n too large for the shared-memory vectors");
   if (b > 0x7fffffffLL) return fail(MGB_ERR_ARG, "series_acquisition_ei: too many candidates for one launch");
   AcqParams p{xc, b, ldc, v, ldv, xtrain, (int)n, ldt, coef, rinv, ldr, rinv_t, ldrt, alpha, kss, mean_const, best_f,
               maximize, ei, grad, hvp, mean, var, W, d->n_terms, d->basis, d->scale, d->shift, d->lo, d->hi};
+  if (F > 1) {
+    const size_t smem_m = sizeof(double) * (size_t)(6 * n + 6 * (size_t)F * n + (size_t)F * d->n_terms + 2 + 4 * D);
+    if (smem_m > 200 * 1024) return fail(MGB_ERR_ARG, "series_acquisition_ei: n * n_factors too large for the shared-memory vectors");
+    if (smem_m > 48 * 1024)
+      MGB_TRY(check_cuda(cudaFuncSetAttribute(series_acquisition_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem_m), "cudaFuncSetAttribute"));
+    series_acquisition_multi_kernel<<<(unsigned)b, AQ_THREADS, smem_m, static_cast<cudaStream_t>(stream)>>>(p, F);
+    return after_launch("series_acquisition_multi_kernel");
+  }
   const size_t smem = sizeof(double) * (size_t)(9 * n + d->n_terms + 2 + 4 * W);
   if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "series_acquisition_ei: n too large for the shared-memory vectors");
   if (smem > 48 * 1024)

@@ -221,9 +221,9 @@ class ExactGPPosterior:
                 raise NotImplementedError("q > 1 joint posteriors are not provided by the analytic acquisition path")
             x = x.squeeze(-2)
         xp = self._prepared(x)
-        if self.is_series:
+        if self.is_series and self.spec.n_factors == 1:
             ks = _ops.series_gram(self.spec, xp, self.train_prepared, self.coef)  # already scaled by outputscale
-        else:
+        else:   # multi-factor (torus) kernels differentiate factor by factor inside their own forward
             with _frozen_parameters(self.kernel):     # the fit is fixed here: differentiate with respect to x only
                 ks = self.outputscale * self.kernel.forward(xp, self.train_prepared)
         mean = self.mean_const + ks @ self.alpha
@@ -238,12 +238,12 @@ class ExactGPPosterior:
         """Analytic EI, dEI/dx and (with directions ``v``) the Hessian-vector product d2EI/dx2 v at every candidate of
         ``x`` ((b, D) or botorch's (b, 1, D)) in ONE launch (csrc/acquisition.cu) - the three quantities the pymanopt
         cost / egrad / ehess closures of the reference obtain from botorch + torch autograd
-        (manifold_optimize.py:184-217).  Single-factor series kernels (sphere, SO(3), circle); other kernels go
-        through ``posterior_autograd``.  Returns (ei, grad, hvp or None) shaped like ``x``."""
+        (manifold_optimize.py:184-217).  Series kernels (sphere, SO(3), circle, torus in (cos, sin) coordinates); other
+        kernels go through ``posterior_autograd``.  Returns (ei, grad, hvp or None) shaped like ``x``."""
         if self._packed is None or getattr(self, "rinv", None) is None:
             raise RuntimeError("call fit() first")
-        if not self.is_series or self.spec.n_factors != 1 or hasattr(self.kernel, "_to_circles"):
-            raise NotImplementedError("fused acquisition derivatives are provided for single-factor series kernels")
+        if not self.is_series:
+            raise NotImplementedError("fused acquisition derivatives are provided for the series kernels")
         _lib.require_cuda_f64(x, v)
         shape = x.shape
         xf = x.reshape(-1, shape[-1]).contiguous()
@@ -251,8 +251,9 @@ class ExactGPPosterior:
             raise NotImplementedError("q > 1 joint posteriors are not provided by the analytic acquisition path")
         vf = v.reshape(-1, shape[-1]).contiguous() if v is not None else None
         b, w = xf.shape
-        if w != self.spec.factor_width:
-            raise RuntimeError("expected %d coordinates" % self.spec.factor_width)
+        if w != self.spec.factor_width * self.spec.n_factors:
+            raise RuntimeError("expected %d coordinates (torus points as (cos, sin) pairs, not angles)"
+                               % (self.spec.factor_width * self.spec.n_factors))
         n = self.train_prepared.shape[0]
         ei = torch.empty(b, dtype=F64, device=self.device)
         grad = torch.empty((b, w), dtype=F64, device=self.device)

@@ -325,3 +325,30 @@ def test_fused_acquisition_circle_both_bases_and_tiny_n(ls, n):
     (ga,) = torch.autograd.grad(val.sum(), [xa], create_graph=True)
     (ha,) = torch.autograd.grad((ga * v).sum(), [xa])
     assert rel_err(ei, val) < 1e-11 and rel_err(grad, ga) < 1e-9 and rel_err(hvp, ha) < 1e-8
+
+
+def test_fused_acquisition_torus():
+    """T^3 in (cos, sin) coordinates: the multi-factor acquisition kernel against autograd through the factor-by-factor
+    differentiable path (bo_torus.py uses exact Hessian-vector products: approx_hessian=False)."""
+    from materngabo_b200 import kernels_torus as kt
+    from materngabo_b200.posterior import ExactGPPosterior, ExpectedImprovement
+
+    gen = torch.Generator().manual_seed(17)
+    ang = torch.rand(46, 3, generator=gen) * 6.283185307179586
+    pts = torch.stack([torch.cos(ang), torch.sin(ang)], -1).reshape(46, 6)
+    xt, xc = pts[:40].to(DEV), pts[40:].to(DEV)
+    y = (torch.sin(ang[:40, 0]) + torch.cos(2 * ang[:40, 1]) * 0.5).to(DEV)
+    k = kt.TorusProductOfManifoldsRiemannianMaternKernel(dim=3, nu=2.5).to(DEV)
+    for c, kk in enumerate(k.torus_kernel.kernels):
+        kk.lengthscale = 0.4 + 0.1 * c
+    for p in k.parameters():
+        p.requires_grad_(False)
+    gp = ExactGPPosterior(k, xt, y, outputscale=1.7, noise=1e-2, mean_const=0.05).fit()
+    acq = ExpectedImprovement(gp, best_f=float(y.min()), maximize=False)
+    v = torch.randn(6, 6, generator=gen).to(DEV)
+    ei, grad, hvp = acq.value_grad_hvp(xc, v)
+    xa = xc.clone().requires_grad_(True)
+    val = acq(xa.unsqueeze(-2))
+    (ga,) = torch.autograd.grad(val.sum(), [xa], create_graph=True)
+    (ha,) = torch.autograd.grad((ga * v).sum(), [xa])
+    assert rel_err(ei, val) < 1e-11 and rel_err(grad, ga) < 1e-9 and rel_err(hvp, ha) < 1e-8
