@@ -290,6 +290,17 @@ int mgb_series_acquisition_ei(const mgb_series_desc* desc, const double* xc, lon
                               int maximize, double* ei, double* grad, double* hvp, double* mean, double* var,
                               void* stream);
 
+/* The same for the radial quadrature kernels (geom 0: hyperbolic H^1..H^3, rows dim + 1 wide; geom 1: Euclidean):
+ * P0, P1, P2 (b x n each) are the profile and its first two derivatives at the pair scalars (geodesic distance or
+ * |x - y|^2), as returned by mgb_radial_profile; this entry point adds the pair geometry, the triangular mat-vecs and
+ * the chain through EI.  P2, v, hvp may be NULL (value + gradient only). */
+int mgb_radial_acquisition_ei(int geom, int width, const double* xc, long long b, long long ldc, const double* v,
+                              long long ldv, const double* xtrain, long long n, long long ldt, const double* P0,
+                              const double* P1, const double* P2, double outputscale, const double* rinv,
+                              long long ldr, const double* rinv_t, long long ldrt, const double* alpha, double kss,
+                              double mean_const, double best_f, int maximize, double* ei, double* grad, double* hvp,
+                              void* stream);
+
 /* Series coefficients of the sphere / SO(3) kernels and their Jacobian with respect to (kappa, nu) in one launch
  * (the hyper-parameter -> coefficient chain of kernels_sphere.py:126-139,212-224 and kernels_so.py:264-273,101, which
  * torch autograd otherwise spreads over ~60 tiny kernels per marginal-likelihood evaluation):

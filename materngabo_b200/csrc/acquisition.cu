@@ -383,9 +383,212 @@ __global__ void __launch_bounds__(AQ_THREADS) series_acquisition_multi_kernel(Ac
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Radial kernels (hyperbolic H^1..H^3, Euclidean): k_j = s P(z_j) with z_j = d(x, x_j) (geodesic distance, Lorentz
+// model) or |x - x_j|^2.  P, P', P'' at the b x n pair scalars come from mgb_radial_profile (the per-pair quadrature and
+// its derivatives, csrc/quad_profile.cu); this kernel adds the pair geometry
+//     u = max(0, <D,D>_L) + 1e-8,  d = 2 asinh(sqrt(u) / 2),  grad_x d = h'(u) 2 J D,  Hess d v = h''(u) (2JD.v) 2JD + h'(u) 2 J v
+// (zero where the max(0, .) of the reference is active), the four triangular mat-vecs and the chain through EI.
+// ------------------------------------------------------------------------------------------------
+struct RadialAcqParams {
+  int geom, width;               // geom 0: Lorentz rows (width = dim + 1); 1: Euclidean rows (z = squared distance)
+  const double* xc; long long b, ldc;
+  const double* v; long long ldv;
+  const double* xt; int n; long long ldt;
+  const double* P0; const double* P1; const double* P2;   // b x n each (P2 may be null without directions)
+  double outputscale;
+  const double* R; long long ldr; const double* Rt; long long ldrt; const double* alpha;
+  double kss, mean_const, best_f; int maximize;
+  double* ei; double* grad; double* hvp;
+};
+
+constexpr int RA_MAXW = 4;
+
+// e = 2 J D (J = diag(-1, 1, ..) for the Lorentz model, identity otherwise), hp = dz/du-type factors; returns whether the
+// pair contributes a gradient
+__device__ __forceinline__ bool radial_geometry(const RadialAcqParams& p, const double* xs, const double* xj, double* e,
+                                                double& hp, double& hpp) {
+  double mink = 0.0;
+  for (int k = 0; k < p.width; ++k) {
+    const double dlt = xs[k] - __ldg(xj + k);
+    const double sgn = (p.geom == 0 && k == 0) ? -1.0 : 1.0;
+    e[k] = 2.0 * sgn * dlt;
+    mink = fma(sgn * dlt, dlt, mink);
+  }
+  if (p.geom == 1) {
+    hp = 1.0;
+    hpp = 0.0;
+    return true;
+  }
+  if (!(mink >= 0.0)) {                        // max(0, .) of the reference active (or NaN): no gradient
+    hp = hpp = 0.0;
+    return false;
+  }
+  // torch.maximum splits the gradient evenly at a tie: a candidate that coincides with a training point (mink == 0
+  // exactly) passes HALF of it, which matters for the Hessian-vector product (h' 2 J v does not vanish there)
+  const double tie = (mink == 0.0) ? 0.5 : 1.0;
+  const double u = mink + 1e-8;
+  const double q = u * (4.0 + u);
+  const double h1 = rsqrt(q);                  // d/du 2 asinh(sqrt(u)/2) = (u (4 + u))^-1/2
+  hp = tie * h1;
+  hpp = tie * (-0.5 * h1 / q * (4.0 + 2.0 * u));
+  return true;
+}
+
+__global__ void __launch_bounds__(AQ_THREADS) radial_acquisition_kernel(RadialAcqParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int n = p.n, W = p.width;
+  double* k0 = sm;            // s P
+  double* k1 = k0 + n;        // s P'
+  double* k2 = k1 + n;        // s P''
+  double* dd = k2 + n;        // grad d . v
+  double* w = dd + n;
+  double* be = w + n;
+  double* dk = be + n;
+  double* w2 = dk + n;
+  double* b2 = w2 + n;
+  double* red = b2 + n;       // 2 + 4 * W
+  __shared__ double xs[RA_MAXW], vs[RA_MAXW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long c = blockIdx.x;
+  const bool want_h = (p.v != nullptr) && (p.hvp != nullptr) && (p.P2 != nullptr);
+  if (tid < W) {
+    xs[tid] = p.xc[c * p.ldc + tid];
+    vs[tid] = want_h ? p.v[c * p.ldv + tid] : 0.0;
+  }
+  for (int e = tid; e < 2 + 4 * W; e += AQ_THREADS) red[e] = 0.0;
+  __syncthreads();
+  for (int j = tid; j < n; j += AQ_THREADS) {
+    k0[j] = p.outputscale * p.P0[c * n + j];
+    k1[j] = p.outputscale * p.P1[c * n + j];
+    k2[j] = want_h ? p.outputscale * p.P2[c * n + j] : 0.0;
+    double e[RA_MAXW], hp, hpp;
+    const bool act = radial_geometry(p, xs, p.xt + (long long)j * p.ldt, e, hp, hpp);
+    double ev = 0.0;
+    for (int k = 0; k < W; ++k) ev = fma(e[k], vs[k], ev);
+    dd[j] = act ? hp * ev : 0.0;
+    dk[j] = k1[j] * dd[j];
+  }
+  __syncthreads();
+  tri_matvec(p.R, p.ldr, k0, w, n, true, warp, lane);
+  if (want_h) tri_matvec(p.R, p.ldr, dk, w2, n, true, warp, lane);
+  __syncthreads();
+  tri_matvec(p.Rt, p.ldrt, w, be, n, false, warp, lane);
+  if (want_h) tri_matvec(p.Rt, p.ldrt, w2, b2, n, false, warp, lane);
+  __syncthreads();
+  {
+    double s_mu = 0.0, s_w = 0.0;
+    for (int j = tid; j < n; j += AQ_THREADS) {
+      s_mu = fma(k0[j], __ldg(p.alpha + j), s_mu);
+      s_w = fma(w[j], w[j], s_w);
+    }
+    s_mu = warp_sum(s_mu);
+    s_w = warp_sum(s_w);
+    if (lane == 0) {
+      atomicAdd(red + 0, s_mu);
+      atomicAdd(red + 1, s_w);
+    }
+  }
+  {
+    double g_mu[RA_MAXW], g_var[RA_MAXW], h_mu[RA_MAXW], h_var[RA_MAXW];
+#pragma unroll
+    for (int k = 0; k < RA_MAXW; ++k) g_mu[k] = g_var[k] = h_mu[k] = h_var[k] = 0.0;
+    for (int j = tid; j < n; j += AQ_THREADS) {
+      double e[RA_MAXW], hp, hpp;
+      const bool act = radial_geometry(p, xs, p.xt + (long long)j * p.ldt, e, hp, hpp);
+      if (!act) continue;
+      const double a = __ldg(p.alpha + j);
+      double ev = 0.0;
+      for (int k = 0; k < W; ++k) ev = fma(e[k], vs[k], ev);
+#pragma unroll
+      for (int k = 0; k < RA_MAXW; ++k) {
+        if (k < W) {
+          const double gd = hp * e[k];                                           // (grad d)_k
+          const double sgn = (p.geom == 0 && k == 0) ? -1.0 : 1.0;
+          const double hd = hpp * ev * e[k] + hp * 2.0 * sgn * vs[k];            // (Hess d v)_k
+          g_mu[k] = fma(a * k1[j], gd, g_mu[k]);
+          g_var[k] = fma(be[j] * k1[j], gd, g_var[k]);
+          if (want_h) {
+            const double hk = fma(k2[j] * dd[j], gd, k1[j] * hd);               // d/dv of (k' grad d)_k
+            h_mu[k] = fma(a, hk, h_mu[k]);
+            h_var[k] = fma(b2[j] * k1[j], gd, fma(be[j], hk, h_var[k]));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RA_MAXW; ++k) {
+      if (k < W) {
+        const double a0 = warp_sum(g_mu[k]), a1 = warp_sum(g_var[k]), a2 = warp_sum(h_mu[k]), a3 = warp_sum(h_var[k]);
+        if (lane == 0) {
+          atomicAdd(red + 2 + k, a0);
+          atomicAdd(red + 2 + W + k, a1);
+          atomicAdd(red + 2 + 2 * W + k, a2);
+          atomicAdd(red + 2 + 3 * W + k, a3);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < W || tid == 0) {
+    const double mu = p.mean_const + red[0];
+    const double var = p.kss - red[1];
+    const bool clamped = !(var > 1e-9);
+    const double sigma = sqrt(clamped ? 1e-9 : var);
+    const double sg = p.maximize ? 1.0 : -1.0;
+    const double u = sg * (mu - p.best_f) / sigma;
+    const double pdf = exp(-0.5 * u * u) * 0.3989422804014327;
+    const double cdf = 0.5 * erfc(-u * 0.7071067811865476);
+    const double e_m = sg * cdf;
+    const double e_v = clamped ? 0.0 : pdf / (2.0 * sigma);
+    const double e_mm = pdf / sigma;
+    const double e_mv = clamped ? 0.0 : -sg * u * pdf / (2.0 * sigma * sigma);
+    const double e_vv = clamped ? 0.0 : pdf * (u * u - 1.0) / (4.0 * sigma * sigma * sigma);
+    if (tid == 0) p.ei[c] = sigma * (pdf + u * cdf);
+    if (tid < W) {
+      const double gm = red[2 + tid], gv = -2.0 * red[2 + W + tid];
+      if (p.grad) p.grad[c * W + tid] = e_m * gm + e_v * gv;
+      if (want_h) {
+        double dmu = 0.0, dvar = 0.0;
+        for (int k = 0; k < W; ++k) {
+          dmu = fma(red[2 + k], vs[k], dmu);
+          dvar = fma(-2.0 * red[2 + W + k], vs[k], dvar);
+        }
+        const double hm = red[2 + 2 * W + tid], hv = -2.0 * red[2 + 3 * W + tid];
+        p.hvp[c * W + tid] = (e_mm * dmu + e_mv * dvar) * gm + (e_mv * dmu + e_vv * dvar) * gv + e_m * hm + e_v * hv;
+      }
+    }
+  }
+}
+
 }  // namespace mgb
 
 using namespace mgb;
+
+extern "C" int mgb_radial_acquisition_ei(int geom, int width, const double* xc, long long b, long long ldc,
+                                         const double* v, long long ldv, const double* xtrain, long long n, long long ldt,
+                                         const double* P0, const double* P1, const double* P2, double outputscale,
+                                         const double* rinv, long long ldr, const double* rinv_t, long long ldrt,
+                                         const double* alpha, double kss, double mean_const, double best_f, int maximize,
+                                         double* ei, double* grad, double* hvp, void* stream) {
+  if (b == 0) return MGB_OK;
+  if (!xc || !xtrain || !P0 || !P1 || !rinv || !rinv_t || !alpha || !ei) return fail(MGB_ERR_ARG, "radial_acquisition_ei: null pointer");
+  if ((geom != 0 && geom != 1) || width < 1 || width > RA_MAXW) return fail(MGB_ERR_ARG, "radial_acquisition_ei: geometry must be H^1..H^3 or R^1..R^4");
+  if (b < 0 || n < 1 || ldc < width || ldt < width || ldr < n || ldrt < n || (v && ldv < width))
+    return fail(MGB_ERR_ARG, "radial_acquisition_ei: bad sizes");
+  if (hvp && (!v || !P2)) return fail(MGB_ERR_ARG, "radial_acquisition_ei: hvp needs directions and the second profile derivative");
+  if (b > 0x7fffffffLL) return fail(MGB_ERR_ARG, "radial_acquisition_ei: too many candidates for one launch");
+  const size_t smem = sizeof(double) * (size_t)(9 * n + 2 + 4 * width);
+  if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "radial_acquisition_ei: n too large for the shared-memory vectors");
+  if (smem > 48 * 1024)
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(radial_acquisition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute"));
+  RadialAcqParams p{geom, width, xc, b, ldc, v, ldv, xtrain, (int)n, ldt, P0, P1, P2, outputscale, rinv, ldr, rinv_t, ldrt,
+                    alpha, kss, mean_const, best_f, maximize, ei, grad, hvp};
+  radial_acquisition_kernel<<<(unsigned)b, AQ_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("radial_acquisition_kernel");
+}
+
 
 extern "C" int mgb_series_acquisition_ei(const mgb_series_desc* d, const double* xc, long long b, long long ldc,
                                          const double* v, long long ldv, const double* xtrain, long long n,

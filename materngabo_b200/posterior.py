@@ -242,9 +242,9 @@ class ExactGPPosterior:
         kernels go through ``posterior_autograd``.  Returns (ei, grad, hvp or None) shaped like ``x``."""
         if self._packed is None or getattr(self, "rinv", None) is None:
             raise RuntimeError("call fit() first")
-        if not self.is_series:
-            raise NotImplementedError("fused acquisition derivatives are provided for the series kernels")
         _lib.require_cuda_f64(x, v)
+        if not self.is_series:
+            return self._radial_ei_value_grad_hvp(x, best_f, maximize, v)
         shape = x.shape
         xf = x.reshape(-1, shape[-1]).contiguous()
         if x.dim() == 3 and shape[-2] != 1:
@@ -269,6 +269,59 @@ class ExactGPPosterior:
                                                1 if maximize else 0, _lib.ptr(ei), _lib.ptr(grad), _lib.ptr(hvp), None, None,
                                                _lib.stream_ptr(self.device))
         _lib.check(rc, "mgb_series_acquisition_ei")
+        return ei.reshape(shape[:-1] if x.dim() == 2 else shape[:-2]), grad.reshape(shape), \
+            (hvp.reshape(shape) if hvp is not None else None)
+
+
+    def _radial_ei_value_grad_hvp(self, x, best_f, maximize, v):
+        """Hyperbolic (H^1..H^3) and Euclidean kernels: profile and its derivatives at the b x n pair scalars from the
+        device quadrature (mgb_radial_profile), then one launch of the radial acquisition kernel."""
+        nodes = getattr(self.kernel, "nodes", None)
+        if nodes is None:
+            raise NotImplementedError("fused acquisition derivatives: series, hyperbolic and Euclidean kernels")
+        nd = nodes(self.device)
+        shape = x.shape
+        if x.dim() == 3 and shape[-2] != 1:
+            raise NotImplementedError("q > 1 joint posteriors are not provided by the analytic acquisition path")
+        xf = x.reshape(-1, shape[-1]).contiguous()
+        vf = v.reshape(-1, shape[-1]).contiguous() if v is not None else None
+        xt = self.train_prepared
+        if len(nd) == 5:                                   # hyperbolic: (tval, tcoef, s0, ds, Ps)
+            tval, tcoef, s0, ds, ps = nd
+            geom, kind = 0, int(self.kernel.dim) - 1
+            if self.kernel.dim not in (1, 2, 3):
+                raise NotImplementedError
+            z = _ops.lorentz_distance(xf, xt)
+        elif len(nd) == 2:                                 # Euclidean: (tval, tcoef)
+            tval, tcoef = nd
+            s0 = ds = 0.0
+            ps = 0
+            geom, kind = 1, _ops.KIND_EUCLID
+            diff = xf.unsqueeze(-2) - xt.unsqueeze(-3)
+            z = (diff * diff).sum(-1)
+        else:
+            raise NotImplementedError("fused acquisition derivatives: series, hyperbolic and Euclidean kernels")
+        b, w = xf.shape
+        if w > 4 or w != xt.shape[-1]:
+            raise NotImplementedError("radial acquisition kernel: rows up to 4 wide")
+        n = xt.shape[0]
+        zf = z.reshape(-1).contiguous()
+        tval, tcoef = tval.detach().contiguous(), tcoef.detach().contiguous()
+        prof = [_ops._radial_profile_raw(kind, o, zf, tval, tcoef, float(s0), float(ds), int(ps))
+                for o in range(3 if vf is not None else 2)]
+        ei = torch.empty(b, dtype=F64, device=self.device)
+        grad = torch.empty((b, w), dtype=F64, device=self.device)
+        hvp = torch.empty((b, w), dtype=F64, device=self.device) if vf is not None else None
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            rc = lib.mgb_radial_acquisition_ei(geom, w, _lib.ptr(xf), b, xf.stride(0), _lib.ptr(vf),
+                                               vf.stride(0) if vf is not None else 0, _lib.ptr(xt), n, xt.stride(0),
+                                               _lib.ptr(prof[0]), _lib.ptr(prof[1]), _lib.ptr(prof[2]) if vf is not None else None,
+                                               self.outputscale, _lib.ptr(self.rinv), self.rinv.stride(0), _lib.ptr(self.rinv_t),
+                                               self.rinv_t.stride(0), _lib.ptr(self.alpha), float(self.kss_value),
+                                               self.mean_const, float(best_f), 1 if maximize else 0, _lib.ptr(ei),
+                                               _lib.ptr(grad), _lib.ptr(hvp), _lib.stream_ptr(self.device))
+        _lib.check(rc, "mgb_radial_acquisition_ei")
         return ei.reshape(shape[:-1] if x.dim() == 2 else shape[:-2]), grad.reshape(shape), \
             (hvp.reshape(shape) if hvp is not None else None)
 
