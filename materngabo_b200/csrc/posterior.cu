@@ -20,6 +20,7 @@
 // (n+1 rounded up to 128) x (n rounded up to 16), row n holding alpha.
 #include "mgb_common.cuh"
 #include <cmath>
+#include <cstdlib>
 
 namespace mgb {
 
@@ -408,7 +409,12 @@ static int choose_splits(long long m, long long n) {
   const long long ctiles = (m + PT - 1) / PT;
   const int n_tiles = (int)(round_up(n + 1, PT) / PT);
   const double panel_bytes = (double)PT * (double)round_up(n, PK) * 8.0;  // one candidate tile's Gram panel
-  long long s_l2 = (long long)ceil(sms * panel_bytes / (40.0 * 1024 * 1024));
+  static double l2_mb = 0.0;   // MGB_POST_L2MB: tuning knob for the L2 slice the in-flight Gram panels may occupy
+  if (l2_mb == 0.0) {
+    const char* e = getenv("MGB_POST_L2MB");
+    l2_mb = (e != nullptr && atof(e) > 0.0) ? atof(e) : 40.0;
+  }
+  long long s_l2 = (long long)ceil(sms * panel_bytes / (l2_mb * 1024 * 1024));
   long long s_fill = (2LL * sms + ctiles - 1) / ctiles;
   long long s = s_l2 > s_fill ? s_l2 : s_fill;
   if (s < 1) s = 1;
