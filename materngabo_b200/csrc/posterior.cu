@@ -7,10 +7,11 @@
 // FP64-bound, so the design goal is to keep the DMMA (FP64 tensor) pipe busy:
 //   - CTA tile 128 candidates x 128 factor rows, 8 DMMA warps as 2 x 4, warp tile 64 x 32
 //     (8 x 4 m8n8k4 fragments, 64 accumulator doubles per lane) + 1 producer warp;
-//   - the producer streams 128 x 16 double operand panels with cp.async.bulk (TMA engine, one 128-byte row
-//     per copy, completion counted in bytes on a per-stage `full` mbarrier) into a 5-stage ring stored with a
-//     row pitch of 20 doubles, so that every fragment load is bank-conflict free; consumers release stages
-//     through `empty` mbarriers - there is no CTA-wide barrier in the main loop;
+//   - the producer streams 128 x 16 double operand blocks with cp.async.bulk (TMA engine, ONE 16 KB copy per operand
+//     per stage: the blocks are stored tile-major and XOR-swizzled in HBM, completion counted in bytes on a per-stage
+//     `full` mbarrier) into a 6-stage ring, so that every fragment load is bank-conflict free; consumers release
+//     stages through `empty` mbarriers - there is no CTA-wide barrier in the main loop; fragment loads are software
+//     pipelined across stage boundaries;
 //   - a CTA walks a balanced subset of the row tiles of the packed factor for its 128 candidates
 //     (triangular: row tile t only needs columns j < 128 (t+1)); square-sums stay in registers;
 //   - the CTAs that share a candidate tile are adjacent in launch order and share its Gram panel through L2
@@ -79,7 +80,7 @@ __device__ __forceinline__ int tile_of(int j, int r, int S, int n_tiles) {
   return (idx < n_tiles) ? (n_tiles - 1 - idx) : -1;
 }
 
-// Warp-specialised: warp 8 streams 128 x 16 operand panels with cp.async.bulk (TMA engine) into a 5-stage
+// Warp-specialised: warp 8 streams 128 x 16 operand panels with cp.async.bulk (TMA engine) into a 6-stage
 // ring, signalling per-stage `full` mbarriers by transaction bytes; warps 0-7 wait, issue DMMAs and release the
 // stage through `empty` mbarriers.  No CTA-wide barrier in the main loop: warps may drift by up to 4 stages.
 __global__ void __launch_bounds__(PTHREADS, 1) posterior_reduce_kernel(PostParams p) {
