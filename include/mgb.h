@@ -301,6 +301,15 @@ int mgb_radial_acquisition_ei(int geom, int width, const double* xc, long long b
                               double mean_const, double best_f, int maximize, double* ei, double* grad, double* hvp,
                               void* stream);
 
+/* SPD(2) (Mandel 3-vectors): value + gradient (the reference's SPD trust region uses a finite-difference Hessian,
+ * bo_spd.py:383).  P0, Pd, Pr (b x n each): the profile and its derivatives in Delta and r2 at the pairs, from
+ * mgb_spd2_profile (which = 0, 1, 2); use_cholesky as in mgb_spd2_gram_fwd.  grad (b x 3) may be NULL. */
+int mgb_spd2_acquisition_ei(int use_cholesky, const double* xc, long long b, long long ldc, const double* xtrain,
+                            long long n, long long ldt, const double* P0, const double* Pd, const double* Pr,
+                            double outputscale, const double* rinv, long long ldr, const double* rinv_t, long long ldrt,
+                            const double* alpha, double kss, double mean_const, double best_f, int maximize, double* ei,
+                            double* grad, void* stream);
+
 /* Series coefficients of the sphere / SO(3) kernels and their Jacobian with respect to (kappa, nu) in one launch
  * (the hyper-parameter -> coefficient chain of kernels_sphere.py:126-139,212-224 and kernels_so.py:264-273,101, which
  * torch autograd otherwise spreads over ~60 tiny kernels per marginal-likelihood evaluation):

@@ -561,9 +561,178 @@ __global__ void __launch_bounds__(AQ_THREADS) radial_acquisition_kernel(RadialAc
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// SPD(2) (Mandel 3-vectors): k_j = s P(Delta_j, r2_j) with (Delta, r2) from the log singular values H1 >= H2 of
+// A(x) B_j^-1 (kernels_spd.py:230-256; Cholesky factors for the heat kernel, :90-102).  Value + gradient only: the
+// reference's SPD trust region uses a finite-difference Hessian (bo_spd.py:383).  P, dP/dDelta, dP/dr2 at the b x n
+// pairs come from mgb_spd2_profile; this kernel differentiates the closed-form 2 x 2 singular values.
+// ------------------------------------------------------------------------------------------------
+struct SpdAcqParams {
+  int use_chol;
+  const double* xc; long long b, ldc;
+  const double* xt; int n; long long ldt;
+  const double* P0; const double* Pd; const double* Pr;   // b x n each
+  double outputscale;
+  const double* R; long long ldr; const double* Rt; long long ldrt; const double* alpha;
+  double kss, mean_const, best_f; int maximize;
+  double* ei; double* grad;
+};
+
+// Mandel (s11, s22, sqrt2 s12) -> 2 x 2 matrix (optionally its lower Cholesky factor), row-major a b / c d
+__device__ __forceinline__ void spd2_mat(const double* v, int chol, double& a, double& b, double& c, double& d) {
+  const double s11 = v[0], s22 = v[1], s12 = v[2] * 0.7071067811865476;
+  if (!chol) {
+    a = s11; b = s12; c = s12; d = s22;
+  } else {
+    a = sqrt(s11);
+    b = 0.0;
+    c = s12 / a;
+    d = sqrt(s22 - c * c);
+  }
+}
+
+// d Delta / d x and d r2 / d x (3-vectors) for candidate x against training point xj
+__device__ __forceinline__ void spd2_pair_grad(const double* x, const double* xj, int chol, double* gD, double* gR) {
+  double a, b, c, d, e, f, g, h;
+  spd2_mat(x, chol, a, b, c, d);
+  spd2_mat(xj, chol, e, f, g, h);
+  const double detB = e * h - f * g;
+  const double i11 = h / detB, i12 = -f / detB, i21 = -g / detB, i22 = e / detB;
+  const double p11 = a * i11 + b * i21, p12 = a * i12 + b * i22;
+  const double p21 = c * i11 + d * i21, p22 = c * i12 + d * i22;
+  const double t1 = p11 + p22, t2 = p12 - p21, t3 = p11 - p22, t4 = p12 + p21;
+  const double q1 = sqrt(t1 * t1 + t2 * t2), q2sq = t3 * t3 + t4 * t4;
+  const double q2 = sqrt(q2sq);
+  const double det = p11 * p22 - p12 * p21;
+  const double s1 = 0.5 * (q1 + q2);
+  const double H1 = log(s1), H2 = log(fabs(det) / s1);
+  // dH1/dP = (dq1 + dq2) / (q1 + q2); zero sub-gradient of q2 at q2 = 0 (equal singular values)
+  const double w1 = 1.0 / (q1 * (q1 + q2)), w2 = (q2sq > 0.0) ? 1.0 / (q2 * (q1 + q2)) : 0.0;
+  const double h11 = t1 * w1 + t3 * w2, h22 = t1 * w1 - t3 * w2;
+  const double h12 = t2 * w1 + t4 * w2, h21 = -t2 * w1 + t4 * w2;
+  // d log|det| / dP = cof(P) / det
+  const double l11 = p22 / det, l12 = -p21 / det, l21 = -p12 / det, l22 = p11 / det;
+  // Delta = 2 H1 - log|det|,  r2 = H1^2 + H2^2,  H2 = log|det| - H1
+  const double cD1 = 2.0, cDl = -1.0;
+  const double cR1 = 2.0 * H1 - 2.0 * H2, cRl = 2.0 * H2;
+  double GP[2][4];   // [Delta | r2][p11 p12 p21 p22]
+  GP[0][0] = cD1 * h11 + cDl * l11; GP[0][1] = cD1 * h12 + cDl * l12; GP[0][2] = cD1 * h21 + cDl * l21; GP[0][3] = cD1 * h22 + cDl * l22;
+  GP[1][0] = cR1 * h11 + cRl * l11; GP[1][1] = cR1 * h12 + cRl * l12; GP[1][2] = cR1 * h21 + cRl * l21; GP[1][3] = cR1 * h22 + cRl * l22;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    // dF/dA = dF/dP Binv^T
+    const double A11 = GP[q][0] * i11 + GP[q][1] * i12, A12 = GP[q][0] * i21 + GP[q][1] * i22;
+    const double A21 = GP[q][2] * i11 + GP[q][3] * i12, A22 = GP[q][2] * i21 + GP[q][3] * i22;
+    double* out = q ? gR : gD;
+    if (!chol) {
+      out[0] = A11;
+      out[1] = A22;
+      out[2] = (A12 + A21) * 0.7071067811865476;
+    } else {
+      // A = chol(X): a = sqrt(s11), c = s12 / a, d = sqrt(s22 - c^2)  (b = 0: A12 plays no role)
+      const double fs22 = A22 / (2.0 * d);
+      const double fc = A21 - A22 * c / d;
+      const double s12 = x[2] * 0.7071067811865476;
+      const double fs12 = fc / a;
+      const double fa = A11 - fc * s12 / (a * a);
+      out[0] = fa / (2.0 * a);
+      out[1] = fs22;
+      out[2] = fs12 * 0.7071067811865476;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AQ_THREADS) spd2_acquisition_kernel(SpdAcqParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int n = p.n;
+  double* k0 = sm;
+  double* w = k0 + n;
+  double* be = w + n;
+  double* red = be + n;       // 2 + 6
+  __shared__ double xs[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long c = blockIdx.x;
+  if (tid < 3) xs[tid] = p.xc[c * p.ldc + tid];
+  if (tid < 8) red[tid] = 0.0;
+  __syncthreads();
+  for (int j = tid; j < n; j += AQ_THREADS) k0[j] = p.outputscale * p.P0[c * n + j];
+  __syncthreads();
+  tri_matvec(p.R, p.ldr, k0, w, n, true, warp, lane);
+  __syncthreads();
+  tri_matvec(p.Rt, p.ldrt, w, be, n, false, warp, lane);
+  __syncthreads();
+  double s_mu = 0.0, s_w = 0.0, gm[3] = {0.0, 0.0, 0.0}, gv[3] = {0.0, 0.0, 0.0};
+  for (int j = tid; j < n; j += AQ_THREADS) {
+    const double a = __ldg(p.alpha + j);
+    s_mu = fma(k0[j], a, s_mu);
+    s_w = fma(w[j], w[j], s_w);
+    if (p.grad) {
+      double gD[3], gR[3];
+      spd2_pair_grad(xs, p.xt + (long long)j * p.ldt, p.use_chol, gD, gR);
+      const double pd = p.outputscale * p.Pd[c * n + j], pr = p.outputscale * p.Pr[c * n + j];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double gk = fma(pd, gD[k], pr * gR[k]);      // d k_j / d x_k
+        gm[k] = fma(a, gk, gm[k]);
+        gv[k] = fma(be[j], gk, gv[k]);
+      }
+    }
+  }
+  s_mu = warp_sum(s_mu);
+  s_w = warp_sum(s_w);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    gm[k] = warp_sum(gm[k]);
+    gv[k] = warp_sum(gv[k]);
+  }
+  if (lane == 0) {
+    atomicAdd(red + 0, s_mu);
+    atomicAdd(red + 1, s_w);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      atomicAdd(red + 2 + k, gm[k]);
+      atomicAdd(red + 5 + k, gv[k]);
+    }
+  }
+  __syncthreads();
+  if (tid < 3) {
+    const double mu = p.mean_const + red[0];
+    const double var = p.kss - red[1];
+    const bool clamped = !(var > 1e-9);
+    const double sigma = sqrt(clamped ? 1e-9 : var);
+    const double sg = p.maximize ? 1.0 : -1.0;
+    const double u = sg * (mu - p.best_f) / sigma;
+    const double pdf = exp(-0.5 * u * u) * 0.3989422804014327;
+    const double cdf = 0.5 * erfc(-u * 0.7071067811865476);
+    if (tid == 0) p.ei[c] = sigma * (pdf + u * cdf);
+    if (p.grad) p.grad[c * 3 + tid] = sg * cdf * red[2 + tid] + (clamped ? 0.0 : pdf / (2.0 * sigma)) * (-2.0 * red[5 + tid]);
+  }
+}
+
 }  // namespace mgb
 
 using namespace mgb;
+
+extern "C" int mgb_spd2_acquisition_ei(int use_cholesky, const double* xc, long long b, long long ldc, const double* xtrain,
+                                       long long n, long long ldt, const double* P0, const double* Pd, const double* Pr,
+                                       double outputscale, const double* rinv, long long ldr, const double* rinv_t,
+                                       long long ldrt, const double* alpha, double kss, double mean_const, double best_f,
+                                       int maximize, double* ei, double* grad, void* stream) {
+  if (b == 0) return MGB_OK;
+  if (!xc || !xtrain || !P0 || !rinv || !rinv_t || !alpha || !ei) return fail(MGB_ERR_ARG, "spd2_acquisition_ei: null pointer");
+  if (grad && (!Pd || !Pr)) return fail(MGB_ERR_ARG, "spd2_acquisition_ei: the gradient needs both profile derivatives");
+  if (b < 0 || n < 1 || ldc < 3 || ldt < 3 || ldr < n || ldrt < n) return fail(MGB_ERR_ARG, "spd2_acquisition_ei: bad sizes");
+  if (b > 0x7fffffffLL) return fail(MGB_ERR_ARG, "spd2_acquisition_ei: too many candidates for one launch");
+  const size_t smem = sizeof(double) * (size_t)(3 * n + 8);
+  if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "spd2_acquisition_ei: n too large for the shared-memory vectors");
+  if (smem > 48 * 1024)
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(spd2_acquisition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute"));
+  SpdAcqParams p{use_cholesky, xc, b, ldc, xtrain, (int)n, ldt, P0, Pd, Pr, outputscale, rinv, ldr, rinv_t, ldrt, alpha,
+                 kss, mean_const, best_f, maximize, ei, grad};
+  spd2_acquisition_kernel<<<(unsigned)b, AQ_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("spd2_acquisition_kernel");
+}
 
 extern "C" int mgb_radial_acquisition_ei(int geom, int width, const double* xc, long long b, long long ldc,
                                          const double* v, long long ldv, const double* xtrain, long long n, long long ldt,

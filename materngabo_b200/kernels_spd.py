@@ -43,16 +43,21 @@ class SpdRiemannianGaussianKernel(Kernel):
             raise NotImplementedError
         self.nb_points_integral = nb_points_integral
 
-    def forward(self, x1, x2, diag=False, **params):
-        _check_batch(self)
-        dev = x1.device
+    use_cholesky = 1      # singular values of chol(X1) chol(X2)^-1 (kernels_spd.py:90-102)
+
+    def nodes(self, dev):
+        """(tcoef, rscale, bscale, b, bw) of the heat kernel: one outer node with scales 1/(2 kappa^2), 1/kappa^2."""
         ls = self.lengthscale.reshape(()).to(device=dev, dtype=F64)
         b, bw = _b_nodes(self.nb_points_integral, dev)
         rscale = (1.0 / (2 * ls ** 2)).reshape(1)
         bscale = (1.0 / ls ** 2).reshape(1)
         # normaliser: the b-integral at Delta = 0 (kernels_spd.py:128-134)
         norm = (bw * 2.0 * b * torch.exp(-b * b * bscale) / torch.sinh(b)).sum()
-        tcoef = (1.0 / norm).reshape(1)
+        return (1.0 / norm).reshape(1), rscale, bscale, b, bw
+
+    def forward(self, x1, x2, diag=False, **params):
+        _check_batch(self)
+        tcoef, rscale, bscale, b, bw = self.nodes(x1.device)
         op = _ops.spd2_gram_autograd if _ops.inputs_need_grad(x1, x2) else _ops.spd2_gram
         fn = lambda a, c: op(1, a, c, tcoef, rscale, bscale, b, bw)  # noqa: E731
         return _ops.pairwise(fn, x1, x2, diag=diag)
@@ -70,6 +75,8 @@ class SpdRiemannianIntegratedMaternKernel(_NuMixin, Kernel):
             raise NotImplementedError
         self.nb_points_integral_b = nb_points_integral_b
         self.nb_points_integral_t = nb_points_integral_t
+
+    use_cholesky = 0      # singular values of X1 X2^-1 (kernels_spd.py:230-243)
 
     def nodes(self, device, with_lattice=False):
         ls = self.lengthscale.to(device)

@@ -273,12 +273,44 @@ class ExactGPPosterior:
             (hvp.reshape(shape) if hvp is not None else None)
 
 
+    def _spd2_ei_value_grad(self, x, best_f, maximize, v):
+        """SPD(2) kernels: value + gradient (the reference's SPD trust region uses a finite-difference Hessian)."""
+        if v is not None:
+            raise NotImplementedError("SPD(2): Hessian-vector products are not provided (bo_spd.py uses approx_hessian=True)")
+        shape = x.shape
+        if x.dim() == 3 and shape[-2] != 1:
+            raise NotImplementedError("q > 1 joint posteriors are not provided by the analytic acquisition path")
+        xf = x.reshape(-1, shape[-1]).contiguous()
+        xt = self.train_prepared
+        if xf.shape[-1] != 3 or xt.shape[-1] != 3:
+            raise RuntimeError("SPD(2) points are Mandel 3-vectors")
+        chol = int(self.kernel.use_cholesky)
+        tcoef, rscale, bscale, bv, bw = [t.detach().contiguous() for t in self.kernel.nodes(self.device)]
+        h1, h2 = _ops.spd2_log_singular_values(xf, xt, bool(chol))
+        delta, r2 = (h1 - h2).reshape(-1).contiguous(), (h1 * h1 + h2 * h2).reshape(-1).contiguous()
+        prof = [_ops._spd2_profile_raw(wh, delta, r2, tcoef, rscale, bscale, bv, bw) for wh in range(3)]
+        b, n = xf.shape[0], xt.shape[0]
+        ei = torch.empty(b, dtype=F64, device=self.device)
+        grad = torch.empty((b, 3), dtype=F64, device=self.device)
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            rc = lib.mgb_spd2_acquisition_ei(chol, _lib.ptr(xf), b, xf.stride(0), _lib.ptr(xt), n, xt.stride(0),
+                                             _lib.ptr(prof[0]), _lib.ptr(prof[1]), _lib.ptr(prof[2]), self.outputscale,
+                                             _lib.ptr(self.rinv), self.rinv.stride(0), _lib.ptr(self.rinv_t),
+                                             self.rinv_t.stride(0), _lib.ptr(self.alpha), float(self.kss_value), self.mean_const,
+                                             float(best_f), 1 if maximize else 0, _lib.ptr(ei), _lib.ptr(grad),
+                                             _lib.stream_ptr(self.device))
+        _lib.check(rc, "mgb_spd2_acquisition_ei")
+        return ei.reshape(shape[:-1] if x.dim() == 2 else shape[:-2]), grad.reshape(shape), None
+
     def _radial_ei_value_grad_hvp(self, x, best_f, maximize, v):
         """Hyperbolic (H^1..H^3) and Euclidean kernels: profile and its derivatives at the b x n pair scalars from the
         device quadrature (mgb_radial_profile), then one launch of the radial acquisition kernel."""
         nodes = getattr(self.kernel, "nodes", None)
         if nodes is None:
-            raise NotImplementedError("fused acquisition derivatives: series, hyperbolic and Euclidean kernels")
+            raise NotImplementedError("fused acquisition derivatives: series, hyperbolic, Euclidean and SPD(2) kernels")
+        if hasattr(self.kernel, "use_cholesky"):
+            return self._spd2_ei_value_grad(x, best_f, maximize, v)
         nd = nodes(self.device)
         shape = x.shape
         if x.dim() == 3 and shape[-2] != 1:

@@ -472,3 +472,38 @@ def test_fused_radial_acquisition_euclidean():
     (ga,) = torch.autograd.grad(val.sum(), [xa], create_graph=True)
     (ha,) = torch.autograd.grad((ga * v).sum(), [xa])
     assert rel_err(ei, val) < 1e-11 and rel_err(grad, ga) < 1e-9 and rel_err(hvp, ha) < 1e-8
+
+
+@pytest.mark.parametrize("which", ["matern", "heat"])
+def test_fused_spd2_acquisition_value_and_gradient(which):
+    """SPD(2): EI value + gradient from the fused kernel (closed-form derivative of the 2 x 2 log singular values,
+    Cholesky chain for the heat kernel) against torch autograd through the differentiable posterior path."""
+    from materngabo_b200 import kernels_spd as ksp
+    from materngabo_b200.posterior import ExactGPPosterior, ExpectedImprovement
+
+    gen = torch.Generator().manual_seed(55)
+
+    def spd(cnt):
+        a = torch.randn(cnt, 2, 2, generator=gen)
+        s = a @ a.transpose(-1, -2) + 0.5 * torch.eye(2)
+        return torch.stack([s[:, 0, 0], s[:, 1, 1], s[:, 0, 1] * 2 ** 0.5], -1)
+
+    xt, xc = spd(30).to(DEV), spd(6).to(DEV)
+    y = torch.log(xt[:, 0]) - 0.3 * xt[:, 2]
+    if which == "matern":
+        k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5, nb_points_integral_b=32, nb_points_integral_t=32).to(DEV)
+    else:
+        k = ksp.SpdRiemannianGaussianKernel(2, nb_points_integral=50).to(DEV)
+    k.lengthscale = 1.2
+    for p in k.parameters():
+        p.requires_grad_(False)
+    gp = ExactGPPosterior(k, xt, y, outputscale=1.1, noise=5e-2, mean_const=0.1).fit()
+    acq = ExpectedImprovement(gp, best_f=float(y.min()), maximize=False)
+    ei, grad, none = acq.value_grad_hvp(xc)
+    assert none is None
+    xa = xc.clone().requires_grad_(True)
+    val = acq(xa.unsqueeze(-2))
+    (ga,) = torch.autograd.grad(val.sum(), [xa])
+    assert rel_err(ei, val) < 1e-11 and rel_err(grad, ga) < 1e-9
+    with pytest.raises(NotImplementedError):
+        acq.value_grad_hvp(xc, torch.zeros_like(xc))
