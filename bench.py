@@ -11,6 +11,7 @@ one box (strong scaling, one process per GPU, NCCL only for the state broadcast 
   python bench.py --workload gram-h2-table   opt-in tabulated H^2 profile (not the per-entry quadrature)
   python bench.py --workload config1-s2      BASELINE configs[0]: S^2 Matern Gram 1000 x 1000 (L2 flushed between steps)
   python bench.py --workload config2-bo-s3   BASELINE configs[1]: S^3 GaBO call latencies (N = 100)
+  python bench.py --workload tr-step         trust-region inner step on every manifold: fused kernels vs autograd
 
 Rank 0 prints ONE JSON line.  ``value`` = candidates/s with inputs resident in HBM; ``e2e`` = the same through
 the host-buffer C-ABI call (pinned host inputs, H2D + D2H inside the timed region).  The oracle is used only
@@ -719,6 +720,104 @@ def cpu_gram_baseline(workload, x1, x2):
                       "%.3f s each" % (a.shape[0], b.shape[0], reps, dt)}
 
 
+def run_tr_latency(args, local):
+    """Trust-region inner step (EI value + gradient (+ Hessian-vector product)) at ONE candidate, N = 100 training
+    points, on every manifold of the reference's BO scripts: fused acquisition kernel against torch autograd through the
+    differentiable posterior path (what the pymanopt closures of the reference do).  Microseconds per call incl. the
+    host read-back of the cost."""
+    from materngabo_b200 import _lib, kernels_hyperbolic, kernels_so, kernels_spd, kernels_sphere, kernels_torus
+    from materngabo_b200.posterior import ExactGPPosterior, ExpectedImprovement
+
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(0)
+    n = args.n or 100
+
+    def unit(m, d):
+        return torch.nn.functional.normalize(torch.randn(m, d, generator=gen), dim=-1)
+
+    def rot(m):
+        q, r = torch.linalg.qr(torch.randn(m, 3, 3, generator=gen))
+        q = q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1)).unsqueeze(-2)
+        q[:, :, 0] *= torch.sign(torch.linalg.det(q)).unsqueeze(-1)
+        return q.reshape(m, 9)
+
+    def lor(m, d):
+        z = torch.randn(m, d, generator=gen)
+        return torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1)
+
+    def spd(m):
+        a = torch.randn(m, 2, 2, generator=gen)
+        sm = a @ a.transpose(-1, -2) + 0.5 * torch.eye(2)
+        return torch.stack([sm[:, 0, 0], sm[:, 1, 1], sm[:, 0, 1] * 2 ** 0.5], -1)
+
+    def tor(m, d):
+        a = torch.rand(m, d, generator=gen) * 6.283185307179586
+        return torch.stack([torch.cos(a), torch.sin(a)], -1).reshape(m, 2 * d)
+
+    cases = [("sphere S^3", kernels_sphere.SphereRiemannianMaternKernel(dim=3, nu=2.5), unit(n + 1, 4), 0.5, 1e-2, True),
+             ("SO(3)", kernels_so.SORiemannianMaternKernel(dim=3, nu=2.5), rot(n + 1), 0.5, 1e-2, True),
+             ("torus T^3", kernels_torus.TorusProductOfManifoldsRiemannianMaternKernel(dim=3, nu=2.5), tor(n + 1, 3), 0.5, 1e-2, True),
+             ("hyperbolic H^3", kernels_hyperbolic.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=3, nu=2.5), lor(n + 1, 3), 1.0, 1e-2, True),
+             ("SPD(2)", kernels_spd.SpdRiemannianIntegratedMaternKernel(2, nu=2.5), spd(n + 1), 1.0, 5e-2, False)]
+
+    def timeit(fn, reps):
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e6
+
+    reps = 30 * args.steps
+    sampler = ClockSampler(local).start()
+    launches0 = lib.mgb_launch_count()
+    lat = {}
+    for name, k, pts, ls, noise, has_hvp in cases:
+        k = k.to(dev)
+        if hasattr(k, "torus_kernel"):
+            for kk in k.torus_kernel.kernels:
+                kk.lengthscale = ls
+        else:
+            k.lengthscale = ls
+        for prm in k.parameters():
+            prm.requires_grad_(False)
+        xt, xc = pts[:n].to(dev), pts[n:].to(dev)
+        y = torch.sin(2.0 * xt[:, 0]) + 0.3 * xt[:, 1]
+        gp = ExactGPPosterior(k, xt, y, outputscale=1.0, noise=noise).fit()
+        acq = ExpectedImprovement(gp, best_f=float(y.min()), maximize=False)
+        v = torch.randn(1, xc.shape[-1], generator=gen).to(dev)
+
+        def fused():
+            ei, g, h = acq.value_grad_hvp(xc, v if has_hvp else None)
+            return float(ei)
+
+        def autograd():
+            xa = xc.clone().requires_grad_(True)
+            val = -acq(xa.unsqueeze(-2)).sum()
+            (g,) = torch.autograd.grad(val, [xa], create_graph=has_hvp)
+            if has_hvp:
+                torch.autograd.grad((g * v).sum(), [xa])
+            return float(val)
+
+        lat[name] = {"fused_us": timeit(fused, reps), "autograd_us": timeit(autograd, max(10, reps // 3)),
+                     "quantities": "value + gradient + Hessian-vector product" if has_hvp else "value + gradient"}
+    launches = lib.mgb_launch_count() - launches0
+    clocks = sampler.stop()
+    return {"metric": "trust_region_step_latency", "value": lat["sphere S^3"]["fused_us"], "unit": "us", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": lat["sphere S^3"]["fused_us"] * 1e-3,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "trust-region inner step at one candidate, %d training points, Matern nu=2.5 on every manifold "
+                                   "of the reference's BO scripts; fused acquisition kernels vs torch autograd through the "
+                                   "differentiable posterior (value = S^3 fused); host wall clock per call" % n,
+                       "l2_policy": "latency-bound: working set is cache resident by construction"},
+            "latencies_us": lat, "gpu_launches": launches, "clocks": clocks, "roofline": None, "e2e": None,
+            "cpu_baseline": None}
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -827,6 +926,8 @@ def main():
             out = run_posterior(args, rank, world, local)
         elif args.workload == "config2-bo-s3":
             out = run_bo_latency(args, local) if rank == 0 else None
+        elif args.workload == "tr-step":
+            out = run_tr_latency(args, local) if rank == 0 else None
         else:
             out = run_gram(args, rank, world, local)
         if rank == 0:

@@ -290,6 +290,13 @@ int mgb_series_acquisition_ei(const mgb_series_desc* desc, const double* xc, lon
                               int maximize, double* ei, double* grad, double* hvp, double* mean, double* var,
                               void* stream);
 
+/* Pair scalars of the quadrature kernels for a candidate block (m rows) against the training set (n rows), row-major
+ * m x n: kind 0 Lorentz distance (rows `width` = dim + 1 wide), 1 squared Euclidean distance, 2 / 3 SPD(2) (Delta -> out0,
+ * r2 -> out1) from the matrices / from their Cholesky factors (the geometry of mgb_hyperbolic_gram_fwd,
+ * mgb_euclidean_gram_fwd, mgb_spd2_gram_fwd as a stand-alone step for the acquisition path). */
+int mgb_pair_scalars(int kind, int width, const double* x1, long long m, long long ld1, const double* x2, long long n,
+                     long long ld2, double* out0, double* out1, void* stream);
+
 /* The same for the radial quadrature kernels (geom 0: hyperbolic H^1..H^3, rows dim + 1 wide; geom 1: Euclidean):
  * P0, P1, P2 (b x n each) are the profile and its first two derivatives at the pair scalars (geodesic distance or
  * |x - y|^2), as returned by mgb_radial_profile; this entry point adds the pair geometry, the triangular mat-vecs and

@@ -567,9 +567,52 @@ static int spd_launch(SpdParams p, cudaStream_t s) {
   return after_launch("spd2_gram_kernel");
 }
 
+// Pair scalars of the quadrature kernels for a candidate block against the training set (acquisition path: the
+// profile kernels take them as flat lists).  kind 0: Lorentz distance (rows width wide); 1: squared Euclidean
+// distance; 2 / 3: SPD(2) (Delta, r2) from the matrices / from their Cholesky factors.
+__global__ void __launch_bounds__(256) pair_scalars_kernel(int kind, int width, const double* x1, long long m, long long ld1,
+                                                           const double* x2, long long n, long long ld2, double* out0,
+                                                           double* out1) {
+  const long long total = m * n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / n, j = e - i * n;
+    const double* a = x1 + i * ld1;
+    const double* b = x2 + j * ld2;
+    if (kind == 0) {
+      out0[e] = lorentz_dist(a, b, width - 1);
+    } else if (kind == 1) {
+      double d = 0.0;
+      for (int k = 0; k < width; ++k) {
+        const double df = a[k] - b[k];
+        d = fma(df, df, d);
+      }
+      out0[e] = d;
+    } else {
+      double H1, H2;
+      spd2_logsv(a, b, kind == 3, H1, H2);
+      out0[e] = H1 - H2;
+      out1[e] = H1 * H1 + H2 * H2;
+    }
+  }
+}
+
 }  // namespace mgb
 
 using namespace mgb;
+
+extern "C" int mgb_pair_scalars(int kind, int width, const double* x1, long long m, long long ld1, const double* x2,
+                                long long n, long long ld2, double* out0, double* out1, void* stream) {
+  if (m == 0 || n == 0) return (m < 0 || n < 0) ? fail(MGB_ERR_ARG, "pair_scalars: negative size") : MGB_OK;
+  if (!x1 || !x2 || !out0 || (kind >= 2 && !out1)) return fail(MGB_ERR_ARG, "pair_scalars: null pointer");
+  if (kind < 0 || kind > 3) return fail(MGB_ERR_ARG, "pair_scalars: kind must be 0..3");
+  if (kind >= 2) width = 3;
+  if (width < 1 || (kind == 0 && (width < 2 || width > 4)) || ld1 < width || ld2 < width) return fail(MGB_ERR_ARG, "pair_scalars: bad widths");
+  long long blocks = (m * n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pair_scalars_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(kind, width, x1, m, ld1, x2, n, ld2, out0, out1);
+  return after_launch("pair_scalars_kernel");
+}
+
 
 extern "C" int mgb_hyperbolic_gram_fwd(int dim, const double* x1, long long m, long long ld1, const double* x2,
                                        long long n, long long ld2, const double* tval, const double* tcoef, int Pt,

@@ -113,6 +113,10 @@ class ExactGPPosterior:
         else:
             self.kss_value = float(self.outputscale * self.kernel.forward(x[:1], x[:1]).reshape(()))
         self.train_prepared = x
+        # quadrature node weights of the non-series kernels: fixed once the hyper-parameters are (acquisition path)
+        nodes = getattr(self.kernel, "nodes", None)
+        self._nodes = tuple(t.detach().contiguous() if torch.is_tensor(t) else t for t in nodes(self.device)) \
+            if (nodes is not None and not self.is_series) else None
         self._pack()
         return self
 
@@ -273,6 +277,18 @@ class ExactGPPosterior:
             (hvp.reshape(shape) if hvp is not None else None)
 
 
+    def _pair_scalars(self, kind, xf, xt):
+        """Flat (b * n) pair scalars from one launch (mgb_pair_scalars)."""
+        lib = _lib.load()
+        b, n = xf.shape[0], xt.shape[0]
+        out0 = torch.empty(b * n, dtype=F64, device=self.device)
+        out1 = torch.empty(b * n, dtype=F64, device=self.device) if kind >= 2 else None
+        with torch.cuda.device(self.device):
+            rc = lib.mgb_pair_scalars(kind, xf.shape[-1], _lib.ptr(xf), b, xf.stride(0), _lib.ptr(xt), n, xt.stride(0),
+                                      _lib.ptr(out0), _lib.ptr(out1), _lib.stream_ptr(self.device))
+        _lib.check(rc, "mgb_pair_scalars")
+        return out0, out1
+
     def _spd2_ei_value_grad(self, x, best_f, maximize, v):
         """SPD(2) kernels: value + gradient (the reference's SPD trust region uses a finite-difference Hessian)."""
         if v is not None:
@@ -285,9 +301,8 @@ class ExactGPPosterior:
         if xf.shape[-1] != 3 or xt.shape[-1] != 3:
             raise RuntimeError("SPD(2) points are Mandel 3-vectors")
         chol = int(self.kernel.use_cholesky)
-        tcoef, rscale, bscale, bv, bw = [t.detach().contiguous() for t in self.kernel.nodes(self.device)]
-        h1, h2 = _ops.spd2_log_singular_values(xf, xt, bool(chol))
-        delta, r2 = (h1 - h2).reshape(-1).contiguous(), (h1 * h1 + h2 * h2).reshape(-1).contiguous()
+        tcoef, rscale, bscale, bv, bw = self._nodes
+        delta, r2 = self._pair_scalars(2 + chol, xf, xt)
         prof = [_ops._spd2_profile_raw(wh, delta, r2, tcoef, rscale, bscale, bv, bw) for wh in range(3)]
         b, n = xf.shape[0], xt.shape[0]
         ei = torch.empty(b, dtype=F64, device=self.device)
@@ -311,7 +326,7 @@ class ExactGPPosterior:
             raise NotImplementedError("fused acquisition derivatives: series, hyperbolic, Euclidean and SPD(2) kernels")
         if hasattr(self.kernel, "use_cholesky"):
             return self._spd2_ei_value_grad(x, best_f, maximize, v)
-        nd = nodes(self.device)
+        nd = self._nodes
         shape = x.shape
         if x.dim() == 3 and shape[-2] != 1:
             raise NotImplementedError("q > 1 joint posteriors are not provided by the analytic acquisition path")
@@ -323,14 +338,13 @@ class ExactGPPosterior:
             geom, kind = 0, int(self.kernel.dim) - 1
             if self.kernel.dim not in (1, 2, 3):
                 raise NotImplementedError
-            z = _ops.lorentz_distance(xf, xt)
+            z, _ = self._pair_scalars(0, xf, xt)
         elif len(nd) == 2:                                 # Euclidean: (tval, tcoef)
             tval, tcoef = nd
             s0 = ds = 0.0
             ps = 0
             geom, kind = 1, _ops.KIND_EUCLID
-            diff = xf.unsqueeze(-2) - xt.unsqueeze(-3)
-            z = (diff * diff).sum(-1)
+            z, _ = self._pair_scalars(1, xf, xt)
         else:
             raise NotImplementedError("fused acquisition derivatives: series, hyperbolic and Euclidean kernels")
         b, w = xf.shape
@@ -338,7 +352,6 @@ class ExactGPPosterior:
             raise NotImplementedError("radial acquisition kernel: rows up to 4 wide")
         n = xt.shape[0]
         zf = z.reshape(-1).contiguous()
-        tval, tcoef = tval.detach().contiguous(), tcoef.detach().contiguous()
         prof = [_ops._radial_profile_raw(kind, o, zf, tval, tcoef, float(s0), float(ds), int(ps))
                 for o in range(3 if vf is not None else 2)]
         ei = torch.empty(b, dtype=F64, device=self.device)
