@@ -586,23 +586,23 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_warp(SeriesParams
 // General path: F factors of runtime width W, T terms per factor, either basis; coefficients and the
 // transposed x2 panel in shared memory.  Each thread evaluates 2 columns x 2 rows per coefficient read.
 // ---------------------------------------------------------------------------------------------
-template <int BASIS>
-__device__ __forceinline__ void eval4(const double* __restrict__ cf, int T, const double (&u)[4], double (&s)[4]) {
+template <int BASIS, int NE>
+__device__ __forceinline__ void eval_n(const double* __restrict__ cf, int T, const double (&u)[NE], double (&s)[NE]) {
   if (BASIS == MGB_BASIS_MONOMIAL) {
     double c = cf[T - 1];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) s[q] = c;
+    for (int q = 0; q < NE; ++q) s[q] = c;
     for (int k = T - 2; k >= 0; --k) {
       c = cf[k];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) s[q] = fma(s[q], u[q], c);
+      for (int q = 0; q < NE; ++q) s[q] = fma(s[q], u[q], c);
     }
   } else {
     // forward Chebyshev recurrence T_k = 2u T_{k-1} - T_{k-2}, accumulated on the fly
-    double t0[4], t1[4], u2[4];
+    double t0[NE], t1[NE], u2[NE];
     const double c0 = cf[0], c1 = (T > 1) ? cf[1] : 0.0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NE; ++q) {
       t0[q] = 1.0;
       t1[q] = u[q];
       u2[q] = 2.0 * u[q];
@@ -611,7 +611,7 @@ __device__ __forceinline__ void eval4(const double* __restrict__ cf, int T, cons
     for (int k = 2; k < T; ++k) {
       const double c = cf[k];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < NE; ++q) {
         const double t2 = fma(u2[q], t1[q], -t0[q]);
         s[q] = fma(c, t2, s[q]);
         t0[q] = t1[q];
@@ -621,8 +621,12 @@ __device__ __forceinline__ void eval4(const double* __restrict__ cf, int T, cons
   }
 }
 
+// RPT rows x 2 columns per thread and coefficient read: 8 independent chains for the monomial basis (one FMA per term:
+// the chain latency, not the pipe, limited the 4-chain version), 4 for the Chebyshev basis (three live values per chain).
 template <int BASIS>
 __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_general(SeriesParams p) {
+  constexpr int RPT = (BASIS == MGB_BASIS_MONOMIAL) ? 4 : 2;
+  constexpr int NE = 2 * RPT;
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t bar;
   const int D = p.F * p.W;
@@ -662,40 +666,47 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_general(SeriesPar
     } else {
       __syncthreads();
     }
-    for (int rr = 0; rr < kRowsPerWarp; rr += 2) {
+    for (int rr = 0; rr < kRowsPerWarp; rr += RPT) {
       const int r0 = r_begin + rr;
       if (r0 >= rows) break;
-      const int r1 = min(r0 + 1, rows - 1);
-      double prod[4] = {1.0, 1.0, 1.0, 1.0};
+      int rix[RPT];
+#pragma unroll
+      for (int h = 0; h < RPT; ++h) rix[h] = min(r0 + h, rows - 1);
+      double prod[NE];
+#pragma unroll
+      for (int q = 0; q < NE; ++q) prod[q] = 1.0;
       for (int f = 0; f < p.F; ++f) {
-        double d[4] = {0.0, 0.0, 0.0, 0.0};
+        double d[NE];
+#pragma unroll
+        for (int q = 0; q < NE; ++q) d[q] = 0.0;
         for (int k = 0; k < p.W; ++k) {
           const int kk = f * p.W + k;
           const double2 xc = *reinterpret_cast<const double2*>(x2t + kk * kTN + 2 * lane);
-          const double v0 = x1s[r0 * D + kk], v1 = x1s[r1 * D + kk];
-          d[0] = fma(v0, xc.x, d[0]);
-          d[1] = fma(v0, xc.y, d[1]);
-          d[2] = fma(v1, xc.x, d[2]);
-          d[3] = fma(v1, xc.y, d[3]);
+#pragma unroll
+          for (int h = 0; h < RPT; ++h) {
+            const double v = x1s[rix[h] * D + kk];
+            d[2 * h] = fma(v, xc.x, d[2 * h]);
+            d[2 * h + 1] = fma(v, xc.y, d[2 * h + 1]);
+          }
         }
-        double u[4], s[4];
+        double u[NE], s[NE];
         unsigned need = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < NE; ++q) {
           u[q] = fma(p.square ? d[q] * d[q] : d[q], p.scale, p.shift);
           need |= (unsigned)(((unsigned)__double2hiint(u[q]) & 0x7fffffffu) >= p.clamp_word);
         }
         if (need) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) u[q] = clamp_exact(u[q], p.lo, p.hi);
+          for (int q = 0; q < NE; ++q) u[q] = clamp_exact(u[q], p.lo, p.hi);
         }
-        eval4<BASIS>(cfs + f * p.T, p.T, u, s);
+        eval_n<BASIS, NE>(cfs + f * p.T, p.T, u, s);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) prod[q] *= s[q];
+        for (int q = 0; q < NE; ++q) prod[q] *= s[q];
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int r = (h == 0) ? r0 : r0 + 1;
+      for (int h = 0; h < RPT; ++h) {
+        const int r = r0 + h;
         if (r >= rows) break;
         double* out = out_ptr(p, row0 + r, col);
         if (vec_ok) {
