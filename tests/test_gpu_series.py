@@ -359,3 +359,29 @@ def test_gradient_through_scaled_sum_of_kernels():
     ref = torch.autograd.grad(nll(kref, y), [raw_ls, raw_os])
     assert abs(float(loss) - float(nll(kref, y))) < 1e-9
     assert rel_err(grads[0], ref[0]) < 1e-8 and rel_err(grads[1].reshape(-1), ref[1].reshape(-1)) < 1e-8
+
+
+def test_float32_construction_regime_on_the_device():
+    """The reference's BO scripts build the kernels under a float32 default dtype and then cast the model to the
+    float64 training data ("BO-loop dtype regime"): the constants stay float32-rounded inside
+    float64 arithmetic.  The device path (incl. the one-launch coefficient op) must reproduce exactly that regime."""
+    from materngabo_b200 import kernels_sphere as ks
+    from oracle import restated as R
+
+    torch.set_default_dtype(torch.float32)
+    try:
+        k = ks.SphereRiemannianMaternKernel(dim=2, nu=2.5)
+        k.lengthscale = 0.5
+    finally:
+        torch.set_default_dtype(torch.float64)
+    k = k.to(device=DEV, dtype=torch.float64)            # what SingleTaskGP does with the model (self.to(train_X))
+    gen = torch.Generator().manual_seed(6)
+    x1 = torch.nn.functional.normalize(torch.randn(50, 3, generator=gen), dim=-1)
+    x2 = torch.nn.functional.normalize(torch.randn(40, 3, generator=gen), dim=-1)
+    out = k.forward(x1.to(DEV), x2.to(DEV))
+    # lengthscale and nu were set through float32 raw parameters: 0.5 and 2.5 only to float32 accuracy
+    ls, nu = float(k.lengthscale.detach()), float(k.nu.detach())
+    ref32 = R.sphere_matern(x1, x2, 2, nu, ls, const_dtype=torch.float32)
+    ref64 = R.sphere_matern(x1, x2, 2, nu, ls)
+    assert rel_err(out, ref32) < TOL
+    assert rel_err(ref32, ref64) > 1e-9                   # the two regimes really differ
