@@ -352,3 +352,32 @@ def test_fused_acquisition_torus():
     (ga,) = torch.autograd.grad(val.sum(), [xa], create_graph=True)
     (ha,) = torch.autograd.grad((ga * v).sum(), [xa])
     assert rel_err(ei, val) < 1e-11 and rel_err(grad, ga) < 1e-9 and rel_err(hvp, ha) < 1e-8
+
+
+def test_baseline_train_size_chunk_consistency():
+    """BASELINE configs[4] geometry (S^10, 5000 training points) beyond what the oracle finishes in seconds:
+    size-independent properties - rows taken from different 37888-candidate chunks agree with the same rows evaluated
+    alone, training inputs reproduce the noise-level variance bound, and a sample of rows agrees with the oracle."""
+    from materngabo_b200 import kernels_sphere
+    from materngabo_b200.posterior import ExactGPPosterior
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(99)
+    n, m = 5000, 80000
+    xt = torch.nn.functional.normalize(torch.randn(n, 11, generator=gen), dim=-1)
+    xc = torch.nn.functional.normalize(torch.randn(m, 11, generator=gen), dim=-1)
+    y = torch.sin(3.0 * xt[:, 0]) + 0.5 * xt[:, 1] * xt[:, 2]
+    k = kernels_sphere.SphereRiemannianMaternKernel(dim=10, nu=2.5)
+    k.lengthscale = 0.5
+    gp = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.0, noise=1e-2).fit()
+    mean, var = gp.posterior(xc.to(DEV))
+    rows = torch.tensor([0, 127, 128, 37887, 37888, 75775, 75776, m - 1])
+    ms, vs = gp.posterior(xc[rows].to(DEV))
+    assert rel_err(mean[rows.to(DEV)], ms) < 1e-12 and float((var[rows.to(DEV)] - vs).abs().max()) < 1e-11
+    mt, vt = gp.posterior(xt[:300].to(DEV))
+    assert (vt >= -1e-9).all() and (vt <= 1e-2 + 1e-9).all()
+    kfn = lambda a, b: R.sphere_matern(a, b, 10, 2.5, 0.5)  # noqa: E731
+    L, alpha = R.gp_fit(kfn, xt, y, 1.0, 1e-2, 0.0)
+    mr, vr = R.gp_predict(kfn, xt, L, alpha, xc[rows], outputscale=1.0, mean_const=0.0)
+    assert rel_err(ms, mr) < 1e-9 and float((vs.cpu() - vr).abs().max()) < 1e-8
+    assert torch.isfinite(mean).all() and (var > -1e-9).all() and (var <= 1.0 + 1e-9).all()
