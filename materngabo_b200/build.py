@@ -5,6 +5,8 @@ materngabo_b200.build`` or ``__graft_entry__.build()``.
 """
 from __future__ import annotations
 
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -26,18 +28,45 @@ def _nvcc():
     return exe
 
 
+STAMP = os.path.join(LIBDIR, "libmgb.stamp")
+
+
+def _source_digest() -> str:
+    """Content hash of every source, the header and the compiler flags: a tree copied to another machine (gpurun
+    snapshot: fresh mtimes) must not rebuild a library that matches its sources."""
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "mgb.h")]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "mgb.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as fh:
+        return fh.read().strip() != _source_digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
+    # one builder at a time (several ranks of a torchrun launch may import the package at once)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -52,8 +81,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB)                         # atomic: a concurrent loader sees the old or the new library
+    with open(STAMP, "w") as fh:
+        fh.write(_source_digest() + "\n")
     return LIB
 
 
