@@ -290,6 +290,13 @@ int mgb_series_acquisition_ei(const mgb_series_desc* desc, const double* xc, lon
                               int maximize, double* ei, double* grad, double* hvp, double* mean, double* var,
                               void* stream);
 
+/* Posterior fit for launch-bound training sizes with the same single-CTA kernel: rinv = L^-1 (n x n row-major, lower
+ * triangle, zeros above), rinv_t = its transpose, alpha = Kt^-1 (y - mean), *nll as out[0] of mgb_series_mll.  Replaces
+ * the Gram + Cholesky + solves of ExactGPPosterior.fit (gpytorch's prediction-strategy caches) at n <= mgb_series_mll_max_n. */
+int mgb_series_fit(const mgb_series_desc* desc, const double* x, long long n, long long ld, const double* y,
+                   const double* coef, const double* hyper, double* rinv, double* rinv_t, long long ldo, double* alpha,
+                   double* nll, int* status, void* stream);
+
 /* Pair scalars of the quadrature kernels for a candidate block (m rows) against the training set (n rows), row-major
  * m x n: kind 0 Lorentz distance (rows `width` = dim + 1 wide), 1 squared Euclidean distance, 2 / 3 SPD(2) (Delta -> out0,
  * r2 -> out1) from the matrices / from their Cholesky factors (the geometry of mgb_hyperbolic_gram_fwd,

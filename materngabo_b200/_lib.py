@@ -74,6 +74,7 @@ PROTOTYPES = {
     "mgb_pair_scalars": (_I, [_I, _I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P]),
     "mgb_spectral_coef": (_I, [_I, _I, _I, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
     "mgb_series_mll_max_n": (_LL, [_I, _I]),
+    "mgb_series_fit": (_I, [_DESC, _P, _LL, _LL, _P, _P, _P, _P, _P, _LL, _P, _P, _P, _P]),
     "mgb_series_mll": (_I, [_DESC, _P, _LL, _LL, _P, _P, _P, _P, _P, _P]),
     "mgb_series_gram_host": (_I, [_DESC, _P, _LL, _P, _LL, _P, _P, _I]),
     "mgb_series_posterior_host": (_I, [_DESC, _P, _LL, _P, _LL, _P, _P, _P, _D, _D, _P, _P, _LL, _I]),

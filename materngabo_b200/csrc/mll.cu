@@ -31,6 +31,8 @@ struct MllParams {
   double* out; int* status;
   int W, T, basis;
   double scale, shift, lo, hi;
+  // fit mode (rinv != nullptr): write L^-1 (row-major, lower), its transpose and alpha instead of the gradients
+  double* rinv; double* rinv_t; double* alpha_out; long long ldo;
 };
 
 __device__ __forceinline__ int low_idx(int i, int j) { return i * (i + 1) / 2 + j; }              // j <= i
@@ -250,6 +252,21 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_kernel(MllParams p)
   }
   __syncthreads();
 
+  if (p.rinv != nullptr) {
+    // ---- fit mode: L^-1 = U^T, alpha; out[0] = nll ------------------------------------------------------
+    for (int e = tid; e < n * n; e += MLL_THREADS) {
+      const int i = e / n, j = e - i * n;                        // rinv[i][j] = L^-1_ij = U[j][i] (j <= i)
+      p.rinv[(long long)i * p.ldo + j] = (j <= i) ? U[up_off(j, n) + i] : 0.0;
+      p.rinv_t[(long long)i * p.ldo + j] = (j >= i) ? U[up_off(i, n) + j] : 0.0;
+    }
+    for (int e = tid; e < n; e += MLL_THREADS) p.alpha_out[e] = al[e];
+    if (tid == 0) {
+      p.out[0] = acc[0] + 0.5 * n * 1.8378770664093453;
+      if (p.status) *p.status = bad;
+    }
+    return;
+  }
+
   // ---- 5. weights: A[i][j] <- (i == j ? 1/2 : 1) * (Kt^-1_ij - alpha_i alpha_j), Kt^-1 = U U^T ------
   for (int i = warp; i < n; i += MLL_WARPS) {
     const double* ui = U + up_off(i, n);
@@ -400,6 +417,26 @@ __global__ void __launch_bounds__(128) spectral_coef_kernel(CoefParams p) {
 
 using namespace mgb;
 
+extern "C" int mgb_series_fit(const mgb_series_desc* d, const double* x, long long n, long long ld, const double* y,
+                              const double* coef, const double* hyper, double* rinv, double* rinv_t, long long ldo,
+                              double* alpha, double* nll, int* status, void* stream) {
+  if (!d || !x || !y || !coef || !hyper || !rinv || !rinv_t || !alpha || !nll) return fail(MGB_ERR_ARG, "series_fit: null pointer");
+  if (d->n_factors != 1 || d->pair_square) return fail(MGB_ERR_ARG, "series_fit: single-factor kernels in the affine form only");
+  if (d->factor_width < 1 || d->n_terms < 1 || d->n_terms > MGB_MAX_TERMS) return fail(MGB_ERR_ARG, "series_fit: bad descriptor");
+  if (d->basis != MGB_BASIS_MONOMIAL && d->basis != MGB_BASIS_CHEBYSHEV) return fail(MGB_ERR_ARG, "series_fit: bad basis");
+  if (n < 1 || ld < d->factor_width || ldo < n) return fail(MGB_ERR_ARG, "series_fit: bad sizes");
+  if (n > mgb_series_mll_max_n(d->factor_width, d->n_terms))
+    return fail(MGB_ERR_ARG, "series_fit: n exceeds the single-CTA limit (mgb_series_mll_max_n)");
+  MllParams p{x, (int)n, ld, y, coef, hyper, nll, status, d->factor_width, d->n_terms, d->basis,
+              d->scale, d->shift, d->lo, d->hi, rinv, rinv_t, alpha, ldo};
+  const size_t smem = sizeof(double) * (size_t)(n * (n + 1) + n * d->factor_width + d->n_terms + 5 * n + 4 + d->n_terms);
+  if (smem > 48 * 1024)
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute"));
+  series_mll_kernel<<<1, MLL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("series_mll_kernel (fit)");
+}
+
 extern "C" int mgb_spectral_coef(int mode, int n_terms, int n_out, const double* lam, const double* c, const double* g,
                                  const double* M, double half_dim, const double* kappa, const double* nu, double* coef,
                                  double* jac, void* stream) {
@@ -433,7 +470,7 @@ extern "C" int mgb_series_mll(const mgb_series_desc* d, const double* x, long lo
   if (n > mgb_series_mll_max_n(d->factor_width, d->n_terms))
     return fail(MGB_ERR_ARG, "series_mll: n exceeds the single-CTA limit (mgb_series_mll_max_n)");
   MllParams p{x, (int)n, ld, y, coef, hyper, out, status, d->factor_width, d->n_terms, d->basis,
-              d->scale, d->shift, d->lo, d->hi};
+              d->scale, d->shift, d->lo, d->hi, nullptr, nullptr, nullptr, 0};
   const size_t smem = sizeof(double) * (size_t)(n * (n + 1) + n * d->factor_width + d->n_terms + 5 * n + 4 + d->n_terms);
   if (smem > 48 * 1024)
     MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),

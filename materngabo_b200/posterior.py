@@ -98,6 +98,8 @@ class ExactGPPosterior:
         if self.is_series:
             spec, coef = self.kernel.series()
             coef = (coef.detach().to(self.device, F64) * self._factor_scale(spec)).contiguous()
+            if self._fused_fit(spec, coef, x):
+                return self
             k = _ops.series_gram(spec, x, x, coef)
         else:
             spec, coef = None, None
@@ -119,6 +121,35 @@ class ExactGPPosterior:
             if (nodes is not None and not self.is_series) else None
         self._pack()
         return self
+
+    def _fused_fit(self, spec, coef, x) -> bool:
+        """Launch-bound sizes (single-factor series kernel, n <= ~160): Gram, Cholesky, L^-1 and alpha from ONE launch of
+        the single-CTA kernel (csrc/mll.cu) instead of the Gram kernel + four torch.linalg calls."""
+        n = x.shape[0]
+        if spec.n_factors != 1 or spec.pair_square or n > _ops.series_mll_max_n(spec, coef.shape[-1]):
+            return False
+        lib = _lib.load()
+        self.rinv = torch.empty((n, n), dtype=F64, device=self.device)
+        self.rinv_t = torch.empty((n, n), dtype=F64, device=self.device)
+        self.alpha = torch.empty(n, dtype=F64, device=self.device)
+        nll = torch.empty(1, dtype=F64, device=self.device)
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # coef already carries the outputscale: hyper = (1, noise, mean)
+        hyper = torch.tensor([1.0, self.noise, self.mean_const], dtype=F64).to(self.device)
+        d = spec.desc(coef.shape[-1])
+        with torch.cuda.device(self.device):
+            rc = lib.mgb_series_fit(C.byref(d), _lib.ptr(x), n, x.stride(0), _lib.ptr(self.train_y), _lib.ptr(coef),
+                                    _lib.ptr(hyper), _lib.ptr(self.rinv), _lib.ptr(self.rinv_t), n, _lib.ptr(self.alpha),
+                                    _lib.ptr(nll), _lib.ptr(status), _lib.stream_ptr(self.device))
+        _lib.check(rc, "mgb_series_fit")
+        if int(status) != 0:
+            raise torch.linalg.LinAlgError("ExactGPPosterior.fit: s K + noise I is not positive definite (pivot %d)" % int(status))
+        self.spec, self.coef = spec, coef
+        self.kss_value = _self_kernel_value(spec, coef)
+        self.train_prepared = x
+        self._nodes = None
+        self._pack()
+        return True
 
     def _factor_scale(self, spec):
         # outputscale multiplies the product of factors once: put it on factor 0 only
