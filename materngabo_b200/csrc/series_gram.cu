@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_mma(SeriesParams 
 // phase - they do address arithmetic, loads and stores together and leave the FP64 pipe idle together (ncu: pipe
 // busy 2/3 of the time).  Autonomous warps drift out of phase and fill each other's gaps.
 // ---------------------------------------------------------------------------------------------
-template <int W, int TREG>
+template <int W, int TREG, bool TILED>
 __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_warp(SeriesParams p) {
   constexpr int KS = (W + 3) / 4;
   constexpr int NB = 4;
@@ -486,8 +486,22 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_warp(SeriesParams
     return false;
   };
 
-  const bool aligned = p.tiled || (((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0));
+  const bool aligned = TILED || (((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0));
+  const bool full_cols = aligned && (col0 + 32 <= p.n);   // warp-uniform: all 32 columns of this warp exist
   const unsigned thr = p.clamp_word;
+  // Full tiles (the common case) store through one base pointer per fragment row with compile-time offsets: layout
+  // (row-major or the posterior's tile-major swizzle) is a template parameter, alignment / bounds tests are hoisted.
+  long long lane_off, a_step;
+  int sw0 = 0, sw1 = 0;
+  if constexpr (TILED) {
+    sw0 = ((fk ^ ((frow & 3) << 1)) << 1);
+    sw1 = (((4 + fk) ^ ((frow & 3) << 1)) << 1);
+    lane_off = (((col0 >> 4) << 7) + 32 * wr + frow) << 4;   // + (row panel) * nch * 2048
+    a_step = 8 * 16;
+  } else {
+    lane_off = (long long)frow * p.ldk + col0 + 2 * fk;
+    a_step = 8 * p.ldk;
+  }
 
   long long rp = split;
   if (rp >= npanels) return;
@@ -508,6 +522,13 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_warp(SeriesParams
       parity ^= 1u << buf;
     }
     if (rows > 0) {
+      // Measured on B200 (1M x 2k): hoisted addressing helps the wide rows and the tiled layout (S^10 5.59e11 ->
+      // 5.89e11 entries/s, posterior Gram chunk 0.40 -> 0.33 ms) but costs the narrow row-major ones (S^2 7.09e11 ->
+      // 6.2e11): those keep the generic store path.
+      constexpr bool kHoist = TILED || (W > 4);
+      const bool fast = kHoist && full_cols && rows == RBLK;
+      // row0 = rp * 128 + 32 * wr: tile-major layout addresses the 128-row panel rp, row-major the row itself
+      double* outp = p.K + lane_off + (TILED ? rp * p.nch * 2048 : row0 * p.ldk);
       double u0[2][NB], u1[2][NB];
       auto inner_products = [&](int a, double (&o0)[NB], double (&o1)[NB]) {
         const int r = 8 * a + frow;
@@ -561,17 +582,29 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_warp(SeriesParams
             p1[b] = fma(p1[b], u1[cur][b], c[k]);
           }
         }
-        const int r = 8 * a + frow;
-        if (r < rows) {
+        if (fast) {
+          double* o = outp + a * a_step;
 #pragma unroll
           for (int b = 0; b < NB; ++b) {
-            const long long col = col0 + 8 * b + 2 * fk;
-            double* out = out_ptr(p, row0 + r, col);
-            if (aligned && col + 1 < p.n) {
-              st_keep2(out, p0[b], p1[b], p.tiled);
+            if constexpr (TILED) {
+              *reinterpret_cast<double2*>(o + (b >> 1) * 2048 + ((b & 1) ? sw1 : sw0)) = make_double2(p0[b], p1[b]);
             } else {
-              if (col < p.n) st_stream(out, p0[b]);
-              if (col + 1 < p.n) st_stream(out + 1, p1[b]);
+              st_stream2(o + 8 * b, p0[b], p1[b]);
+            }
+          }
+        } else {
+          const int r = 8 * a + frow;
+          if (r < rows) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+              const long long col = col0 + 8 * b + 2 * fk;
+              double* out = out_ptr(p, row0 + r, col);
+              if (aligned && col + 1 < p.n) {
+                st_keep2(out, p0[b], p1[b], TILED);
+              } else {
+                if (col < p.n) st_stream(out, p0[b]);
+                if (col + 1 < p.n) st_stream(out + 1, p1[b]);
+              }
             }
           }
         }
@@ -907,7 +940,8 @@ static int launch_mma(const SeriesParams& p, long long tiles, cudaStream_t s) {
 template <int W, int TREG>
 static int launch_warp(const SeriesParams& p, long long tiles, cudaStream_t s) {
   const size_t smem = sizeof(double) * (kThreads / 32) * 2 * 32 * W;
-  series_gram_fwd_warp<W, TREG><<<(unsigned)tiles, kThreads, smem, s>>>(p);
+  if (p.tiled) series_gram_fwd_warp<W, TREG, true><<<(unsigned)tiles, kThreads, smem, s>>>(p);
+  else series_gram_fwd_warp<W, TREG, false><<<(unsigned)tiles, kThreads, smem, s>>>(p);
   return after_launch("series_gram_fwd_warp");
 }
 
