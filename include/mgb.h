@@ -304,6 +304,11 @@ int mgb_series_fit(const mgb_series_desc* desc, const double* x, long long n, lo
 int mgb_pair_scalars(int kind, int width, const double* x1, long long m, long long ld1, const double* x2, long long n,
                      long long ld2, double* out0, double* out1, void* stream);
 
+/* Analytic EI from posterior means / variances (botorch ExpectedImprovement: sigma = sqrt(max(var, 1e-9)),
+ * u = +-(mean - best_f) / sigma, EI = sigma (phi(u) + u Phi(u))), elementwise over m candidates. */
+int mgb_expected_improvement(const double* mean, const double* var, long long m, double best_f, int maximize,
+                             double* ei, void* stream);
+
 /* The same for the radial quadrature kernels (geom 0: hyperbolic H^1..H^3, rows dim + 1 wide; geom 1: Euclidean):
  * P0, P1, P2 (b x n each) are the profile and its first two derivatives at the pair scalars (geodesic distance or
  * |x - y|^2), as returned by mgb_radial_profile; this entry point adds the pair geometry, the triangular mat-vecs and

@@ -734,6 +734,31 @@ extern "C" int mgb_spd2_acquisition_ei(int use_cholesky, const double* xc, long 
   return after_launch("spd2_acquisition_kernel");
 }
 
+namespace mgb {
+// EI = sigma (phi(u) + u Phi(u)), sigma = sqrt(max(var, 1e-9)), u = +-(mean - best_f) / sigma: botorch's analytic
+// ExpectedImprovement on posterior means / variances, one launch instead of a dozen elementwise torch kernels.
+__global__ void expected_improvement_kernel(const double* mean, const double* var, long long m, double best_f, int maximize,
+                                            double* out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m) return;
+  const double sigma = sqrt(fmax(var[c], 1e-9));
+  double u = (mean[c] - best_f) / sigma;
+  if (!maximize) u = -u;
+  const double pdf = exp(-0.5 * u * u) * 0.3989422804014327;
+  const double cdf = 0.5 * erfc(-u * 0.7071067811865476);
+  out[c] = sigma * (pdf + u * cdf);
+}
+}  // namespace mgb
+
+extern "C" int mgb_expected_improvement(const double* mean, const double* var, long long m, double best_f, int maximize,
+                                        double* ei, void* stream) {
+  if (m == 0) return MGB_OK;
+  if (!mean || !var || !ei || m < 0) return fail(MGB_ERR_ARG, "expected_improvement: bad argument");
+  expected_improvement_kernel<<<(unsigned)((m + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(mean, var, m, best_f,
+                                                                                                           maximize, ei);
+  return after_launch("expected_improvement_kernel");
+}
+
 extern "C" int mgb_radial_acquisition_ei(int geom, int width, const double* xc, long long b, long long ldc,
                                          const double* v, long long ldv, const double* xtrain, long long n, long long ldt,
                                          const double* P0, const double* P1, const double* P2, double outputscale,

@@ -415,6 +415,13 @@ class ExpectedImprovement:
             mean, var = self.model.posterior_autograd(x)     # trust-region inner loop: value + gradient (+ HVP)
         else:
             mean, var = self.model.posterior(x)              # scoring: fused kernels, no autograd
+            ei = torch.empty_like(mean)
+            lib = _lib.load()
+            with torch.cuda.device(mean.device):
+                rc = lib.mgb_expected_improvement(_lib.ptr(mean), _lib.ptr(var), mean.numel(), self.best_f,
+                                                  1 if self.maximize else 0, _lib.ptr(ei), _lib.stream_ptr(mean.device))
+            _lib.check(rc, "mgb_expected_improvement")
+            return ei
         return expected_improvement(mean, var, self.best_f, self.maximize)
 
 
