@@ -43,3 +43,26 @@ def test_our_arm_needs_a_gpu():
         return
     r = _run(["--steps", "1", "--warmup", "1"])
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_our_arm_json_line_on_the_gpu():
+    """Small instance of the default workload through bench.py: one JSON line with value, roofline, e2e (host buffers,
+    copies counted), launches of our own kernels and clocks."""
+    r = _run(["--steps", "1", "--warmup", "3", "--cands", "300000", "--train", "1000"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["metric"] == "posterior_cands_per_sec" and d["n_gpus"] == 1 and d["value"] > 0 and d["dtype"] == "f64"
+    assert d["gpu_launches"] > 0 and d["scaling"] in ("weak", "strong") and d["vs_baseline"] is None
+    roof = d["roofline"]
+    assert roof["bound"] == "tensor" and 0 < roof["frac"] <= 1.05 and roof["achieved"] > 0 and roof["peak"] > 0
+    e2e = d["e2e"]
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] > 8 * 300000 * 11 and e2e["d2h_bytes_per_step"] == 16 * 300000
+    assert abs(e2e["value"] - d["value"]) > 0              # a separate measurement, not a copy of the device number
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert "sm_mhz" in d["clocks"] and "workload" in d["config"] and "l2_policy" in d["config"]
