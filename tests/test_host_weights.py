@@ -138,3 +138,51 @@ def test_reference_error_conventions():
     x = torch.nn.functional.normalize(torch.randn(4, 3), dim=-1)
     with pytest.raises(MgbError):                                # CPU tensors: loud failure, no fallback
         k.forward(x, x)
+
+
+def test_circle_series_truncation_and_basis_choice():
+    """Tail-sum truncation of the theta_3 series and the conditioning rule for the monomial re-expansion."""
+    import math
+
+    full = _weights.THETA3_TERMS + 1
+    for ls, expect_basis in ((0.5, _lib.BASIS_MONOMIAL), (1.0, _lib.BASIS_MONOMIAL), (0.15, _lib.BASIS_CHEBYSHEV)):
+        c = _weights.circle_integrated_matern_coef(torch.tensor(ls), torch.tensor(2.5), 50)
+        assert 2 <= c.numel() < full
+        # what was dropped is below 1e-16 of the sum: recompute the untruncated series
+        saved = _weights._TRUNC
+        try:
+            _weights._TRUNC = 0.0
+            c_all = _weights.circle_integrated_matern_coef(torch.tensor(ls), torch.tensor(2.5), 50)
+        finally:
+            _weights._TRUNC = saved
+        assert float(c_all[c.numel():].abs().sum()) <= 1e-16 * float(c_all.abs().sum())
+        coef, basis = _weights.chebyshev_or_monomial(c.reshape(1, -1))
+        assert basis == expect_basis
+        u = torch.cos(torch.linspace(0, math.pi, 301))
+        cheb = sum(c[k] * torch.cos(k * torch.acos(u.clamp(-1, 1))) for k in range(c.numel()))
+        if basis == _lib.BASIS_MONOMIAL:
+            mono = torch.zeros_like(u)
+            for k in range(coef.shape[-1] - 1, -1, -1):
+                mono = mono * u + coef[0, k]
+            assert float((mono - cheb).abs().max()) < 1e-14
+        else:
+            assert torch.equal(coef.reshape(-1), c)
+
+
+def test_spd2_lattice_matches_the_actual_grids():
+    """b_b / (2 t_a) = g_min tau^(sb b + sa (Pt - 1 - a)) for the reference's logspace grids (kernels_spd.py:262-265)."""
+    from materngabo_b200 import kernels_spd as ksp
+
+    for pb, pt, ls in ((64, 64, 1.0), (50, 50, 0.7), (40, 40, 2.0)):
+        k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5, nb_points_integral_b=pb, nb_points_integral_t=pt)
+        k.lengthscale = ls
+        tcoef, rscale, bscale, b, bw, lattice = k.nodes("cpu", with_lattice=True)
+        assert lattice is not None
+        sb, sa, g_min, log_tau = lattice
+        bi = torch.arange(pb, dtype=torch.float64).unsqueeze(1)
+        ai = torch.arange(pt, dtype=torch.float64).unsqueeze(0)
+        model = g_min * torch.exp((sb * bi + sa * (pt - 1 - ai)) * log_tau)
+        true = b.unsqueeze(1) * bscale.unsqueeze(0)
+        assert float(((model - true) / true).abs().max()) < 1e-13
+    k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5, nb_points_integral_b=64, nb_points_integral_t=32)
+    assert k.nodes("cpu", with_lattice=True)[-1] is None          # incommensurate enough: falls back to the node-by-node kernel
