@@ -52,22 +52,44 @@ struct HypParams {
   double* out;                                 // Q_BWD_COEF: gtcoef[Pt]; Q_NODES: out[count*Pt]
 };
 
-template <int NQ>
+// PAD: the table E is stored lane-major and zero-padded to 32 * NQ columns (for even NQ as double2 = the two t nodes
+// a lane owns in a node pair), and the two entries' inner weights are interleaved as double2: the Horner loop is then
+// two 16-byte shared loads + 4 NQ FP64 instructions per inner node with compile-time strides and no predicates.
+// (NQ odd > 1 is launched as NQ + 1.)  Without PAD (large Ps, e.g. the heat kernel's Ps = 1000, Pt = 1) E is Ps x Pt.
+template <int NQ, bool PAD>
 __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
+  static_assert(!PAD || NQ == 1 || NQ % 2 == 0, "padded table: one or an even number of t nodes per lane");
   extern __shared__ __align__(16) double sm[];
-  // layout: E [Ps*Pt] | cm1 [Ps] | sh [Ps] | wq [Ps] | per-warp qw [2 * QWARPS][Ps] (two entries in flight)
+  // layout: E | per-warp qw [2 * QWARPS][Ps] (two entries in flight) | cm1 [Ps] | sh [Ps] | wq [Ps]
   double* Es = sm;
-  const int nE = (p.dim == 2) ? p.Ps * p.Pt : 0;
+  const int nE = (p.dim == 2) ? (PAD ? p.Ps * 32 * NQ : p.Ps * p.Pt + ((p.Ps * p.Pt) & 1)) : 0;
   const int nP = (p.dim == 2) ? p.Ps : 0;
-  double* cm1 = Es + nE;
+  double* qw_all = Es + nE;
+  double* cm1 = qw_all + 2 * QWARPS * nP;
   double* sh = cm1 + nP;
   double* wq = sh + nP;
-  double* qw_all = wq + nP;
   // pair-independent tables, rebuilt per CTA (Ps*Pt exponentials: negligible next to the entry loop)
-  for (int e = threadIdx.x; e < nE; e += blockDim.x) {
-    const int k = e / p.Pt, a = e - k * p.Pt;
-    const double b = p.s0 + k * p.ds;
-    Es[e] = exp(-(b * b) / (4.0 * p.tval[a]));  // E[k][a] = exp(-b_k^2 / (4 t_a))
+  if (PAD) {
+    for (int e = threadIdx.x; e < nE; e += blockDim.x) {
+      int k, a;
+      if (NQ == 1) {
+        k = e >> 5;
+        a = e & 31;
+      } else {
+        const int d2 = e >> 1, comp = e & 1, ln = d2 & 31, t = d2 >> 5;
+        const int qp = t % (NQ / 2);
+        k = t / (NQ / 2);
+        a = ln + 32 * (2 * qp + comp);
+      }
+      const double b = p.s0 + k * p.ds;
+      Es[e] = (a < p.Pt) ? exp(-(b * b) / (4.0 * p.tval[a])) : 0.0;
+    }
+  } else {
+    for (int e = threadIdx.x; e < p.Ps * p.Pt && p.dim == 2; e += blockDim.x) {
+      const int k = e / p.Pt, a = e - k * p.Pt;
+      const double b = p.s0 + k * p.ds;
+      Es[e] = exp(-(b * b) / (4.0 * p.tval[a]));  // E[k][a] = exp(-b_k^2 / (4 t_a))
+    }
   }
   for (int e = threadIdx.x; e < nP; e += blockDim.x) {
     const double b = p.s0 + e * p.ds;
@@ -98,6 +120,7 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
   // and broadcast by shuffles, instead of 32 redundant copies per entry.
   double* qw0 = qw;
   double* qw1 = qw_all + (QWARPS + warp) * nP;
+  double2* qw01 = reinterpret_cast<double2*>(qw_all + 2 * warp * nP);   // PAD: {entry 0, entry 1} per inner node
   for (long long ebase = (long long)blockIdx.x * QWARPS + warp; ebase < total; ebase += 64 * wstride) {
     double l_dd[2] = {0.0, 0.0}, l_dsq[2] = {0.0, 0.0}, l_ch[2] = {1.0, 1.0}, l_sh[2] = {0.0, 0.0};
 #pragma unroll
@@ -149,15 +172,32 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
     double h[2][NQ];
     if (p.dim == 2 && p.geom != 1) {
       __syncwarp();
-#pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        const double chd = chd2[s2], shd = shd2[s2];
-        double* dst = s2 ? qw1 : qw0;
+      if (PAD) {
         for (int k = lane; k < p.Ps; k += 32) {
           const double bk = p.s0 + k * p.ds;
-          const double den = fma(chd, cm1[k], shd * sh[k]);
-          const double sk = bk + dd[s2];
-          dst[k] = wq[k] * sk * rsqrt(den) * (p.deriv ? sk * sk : 1.0);   // d/dt brings down s^2 / (4 t^2)
+          const double c = cm1[k], sn = sh[k], wk = wq[k];
+          double2 w2;
+          {
+            const double sk = bk + dd[0];
+            w2.x = wk * sk * rsqrt(fma(chd2[0], c, shd2[0] * sn)) * (p.deriv ? sk * sk : 1.0);
+          }
+          {
+            const double sk = bk + dd[1];
+            w2.y = wk * sk * rsqrt(fma(chd2[1], c, shd2[1] * sn)) * (p.deriv ? sk * sk : 1.0);
+          }
+          qw01[k] = w2;
+        }
+      } else {
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const double chd = chd2[s2], shd = shd2[s2];
+          double* dst = s2 ? qw1 : qw0;
+          for (int k = lane; k < p.Ps; k += 32) {
+            const double bk = p.s0 + k * p.ds;
+            const double den = fma(chd, cm1[k], shd * sh[k]);
+            const double sk = bk + dd[s2];
+            dst[k] = wq[k] * sk * rsqrt(den) * (p.deriv ? sk * sk : 1.0);   // d/dt brings down s^2 / (4 t^2)
+          }
         }
       }
       __syncwarp();
@@ -174,14 +214,46 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
           acc[s2][q] = 0.0;
         }
       }
-      for (int k = p.Ps - 1; k >= 0; --k) {
-        const double w0 = qw0[k], w1 = qw1[k];
+      if (PAD) {
+        if (NQ == 1) {
+          const double* ep = Es + lane + (p.Ps - 1) * 32;
+          const double2* wp = qw01 + (p.Ps - 1);
+#pragma unroll 4
+          for (int k = p.Ps - 1; k >= 0; --k, ep -= 32, --wp) {
+            const double2 w = *wp;
+            const double ev = *ep;
+            acc[0][0] = fma(acc[0][0], r[0][0], w.x * ev);
+            acc[1][0] = fma(acc[1][0], r[1][0], w.y * ev);
+          }
+        } else {
+          constexpr int H = (NQ > 1) ? NQ / 2 : 1;
+          const double2* ep = reinterpret_cast<const double2*>(Es) + lane + (p.Ps - 1) * (32 * H);
+          const double2* wp = qw01 + (p.Ps - 1);
+#pragma unroll 4
+          for (int k = p.Ps - 1; k >= 0; --k, ep -= 32 * H, --wp) {
+            const double2 w = *wp;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          const int a = lane + 32 * q;
-          const double ev = (a < p.Pt) ? Es[k * p.Pt + a] : 0.0;
-          acc[0][q] = fma(acc[0][q], r[0][q], w0 * ev);
-          acc[1][q] = fma(acc[1][q], r[1][q], w1 * ev);
+            for (int qp = 0; qp < H; ++qp) {
+              const double2 ev = ep[32 * qp];
+              acc[0][2 * qp] = fma(acc[0][2 * qp], r[0][2 * qp], w.x * ev.x);
+              acc[1][2 * qp] = fma(acc[1][2 * qp], r[1][2 * qp], w.y * ev.x);
+              if (2 * qp + 1 < NQ) {
+                acc[0][2 * qp + 1] = fma(acc[0][2 * qp + 1], r[0][2 * qp + 1], w.x * ev.y);
+                acc[1][2 * qp + 1] = fma(acc[1][2 * qp + 1], r[1][2 * qp + 1], w.y * ev.y);
+              }
+            }
+          }
+        }
+      } else {
+        for (int k = p.Ps - 1; k >= 0; --k) {
+          const double w0 = qw0[k], w1 = qw1[k];
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const int a = lane + 32 * q;
+            const double ev = (a < p.Pt) ? Es[k * p.Pt + a] : 0.0;
+            acc[0][q] = fma(acc[0][q], r[0][q], w0 * ev);
+            acc[1][q] = fma(acc[1][q], r[1][q], w1 * ev);
+          }
         }
       }
 #pragma unroll
@@ -528,26 +600,38 @@ static int hyp_launch(HypParams p, cudaStream_t s) {
   const long long total = (p.mode == Q_NODES) ? p.count : p.m * p.n;
   if (total == 0) return MGB_OK;
   size_t smem = 0;
+  const int nq = (p.Pt + 31) / 32;
+  bool pad = false;
   if (p.dim == 2) {
+    const size_t rest = 3 * (size_t)p.Ps + (size_t)2 * QWARPS * p.Ps;
+    const int nqp = (nq == 3) ? 4 : nq;
+    const size_t padded = sizeof(double) * ((size_t)p.Ps * 32 * nqp + rest);
+    // padded lane-major table while two CTAs per SM still fit (the register file allows no more)
+    pad = p.geom != 1 && padded <= 100 * 1024;
     const size_t nE = (size_t)p.Ps * p.Pt;
-    smem = sizeof(double) * (nE + 3 * (size_t)p.Ps + (size_t)2 * QWARPS * p.Ps);
+    smem = pad ? padded : sizeof(double) * (nE + (nE & 1) + rest);
     if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "hyperbolic: Ps*Pt table exceeds shared memory");
   }
   long long blocks = (total + QWARPS - 1) / QWARPS;
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  const int nq = (p.Pt + 31) / 32;
-#define MGB_HYP_LAUNCH(NQV)                                                                                             \
+#define MGB_HYP_LAUNCH(NQV, PADV)                                                                                       \
   do {                                                                                                                  \
     if (smem > 48 * 1024)                                                                                               \
-      MGB_TRY(check_cuda(cudaFuncSetAttribute(hyp_gram_kernel<NQV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+      MGB_TRY(check_cuda(cudaFuncSetAttribute(hyp_gram_kernel<NQV, PADV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                               (int)smem), "cudaFuncSetAttribute"));                                     \
-    hyp_gram_kernel<NQV><<<(unsigned)blocks, QTHREADS, smem, s>>>(p);                                                   \
+    hyp_gram_kernel<NQV, PADV><<<(unsigned)blocks, QTHREADS, smem, s>>>(p);                                             \
   } while (0)
-  if (nq == 1) MGB_HYP_LAUNCH(1);
-  else if (nq == 2) MGB_HYP_LAUNCH(2);
-  else if (nq == 3) MGB_HYP_LAUNCH(3);
-  else MGB_HYP_LAUNCH(4);
+  if (pad) {
+    if (nq == 1) MGB_HYP_LAUNCH(1, true);
+    else if (nq == 2) MGB_HYP_LAUNCH(2, true);
+    else MGB_HYP_LAUNCH(4, true);
+  } else {
+    if (nq == 1) MGB_HYP_LAUNCH(1, false);
+    else if (nq == 2) MGB_HYP_LAUNCH(2, false);
+    else if (nq == 3) MGB_HYP_LAUNCH(3, false);
+    else MGB_HYP_LAUNCH(4, false);
+  }
 #undef MGB_HYP_LAUNCH
   return after_launch("hyp_gram_kernel");
 }

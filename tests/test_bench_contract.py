@@ -66,3 +66,18 @@ def test_our_arm_json_line_on_the_gpu():
     assert abs(e2e["value"] - d["value"]) > 0              # a separate measurement, not a copy of the device number
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert "sm_mhz" in d["clocks"] and "workload" in d["config"] and "l2_policy" in d["config"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("workload,rows,cols", [("config1-s2", 500, 500), ("gram-so3", 4096, 512), ("gram-t10", 4096, 256),
+                                                ("gram-h2", 256, 256), ("gram-spd2", 256, 256), ("gram-spd3", 256, 256),
+                                                ("gram-h2-table", 4096, 512)])
+def test_gram_workloads_run_small(workload, rows, cols):
+    """Every Gram workload of bench.py on a small block (also the L2-flushed / graph-replayed timing branch)."""
+    r = _run(["--workload", workload, "--cands", str(rows), "--train", str(cols), "--steps", "2", "--warmup", "3", "--no-cpu-baseline"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["metric"] == "kernel_entries_per_sec" and d["value"] > 0 and d["gpu_launches"] > 0
+    assert d["config"]["rows"] == rows and d["config"]["cols"] == cols and "l2_policy" in d["config"]
