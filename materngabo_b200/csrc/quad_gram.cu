@@ -14,6 +14,8 @@
 // cosh(b_k + d) - cosh(d) is formed as cosh(d)(cosh b_k - 1) + sinh(d) sinh(b_k): all terms positive, no
 // cancellation.
 #include "mgb_common.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace mgb {
 
@@ -314,6 +316,184 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// H^2 forward Gram, four entries per warp iteration.  Same nodes, tables and Horner recurrence as hyp_gram_kernel
+// (PAD form); what changes is the reuse of the shared-memory traffic: with two entries in flight the node loop
+// needs 5 shared-memory wavefronts (4 for the lane-major table row, 1 for the weights) per 8 FP64 instructions
+// = 4 SM cycles of the FP64 pipe, i.e. the kernel is shared-memory bound (ncu: 65 % LSU wavefronts, 56 % FP64 pipe);
+// with four entries it is 6 wavefronts per 16 FP64 instructions.  The pair geometry (distance, cosh, sinh, output
+// offset) of the warp's next 128 entries is computed one entry per lane and parked in shared memory, and the four
+// t-sums are reduced by a split butterfly (12 shuffles instead of 40).
+// ------------------------------------------------------------------------------------------------
+constexpr int H4E = 4;              // entries per warp iteration
+constexpr int H4ROUND = 128;        // entries per geometry round (4 per lane)
+
+template <int NQ>
+__global__ void __launch_bounds__(QTHREADS, 2) h2_gram_fwd4_kernel(HypParams p) {
+  static_assert(NQ == 1 || NQ == 2, "one or two t nodes per lane");
+  extern __shared__ __align__(16) double sm[];
+  // layout: E [Ps][32 NQ] | qw [QWARPS][Ps][4] | geo [QWARPS][4][128] | cm1 [Ps] | sh [Ps] | wq [Ps]
+  double* Es = sm;
+  const int nE = p.Ps * 32 * NQ;
+  double* qw_all = Es + nE;
+  double* geo_all = qw_all + QWARPS * H4E * p.Ps;
+  double* cm1 = geo_all + QWARPS * 4 * H4ROUND;
+  double* sh = cm1 + p.Ps;
+  double* wq = sh + p.Ps;
+  for (int e = threadIdx.x; e < nE; e += blockDim.x) {
+    int k, a;
+    if (NQ == 1) {
+      k = e >> 5;
+      a = e & 31;
+    } else {
+      const int d2 = e >> 1;
+      k = d2 >> 5;
+      a = (d2 & 31) + 32 * (e & 1);
+    }
+    const double b = p.s0 + k * p.ds;
+    Es[e] = (a < p.Pt) ? exp(-(b * b) / (4.0 * p.tval[a])) : 0.0;
+  }
+  for (int e = threadIdx.x; e < p.Ps; e += blockDim.x) {
+    const double b = p.s0 + e * p.ds;
+    const double hs = sinh(0.5 * b);
+    cm1[e] = 2.0 * hs * hs;
+    sh[e] = sinh(b);
+    wq[e] = (e == 0 || e == p.Ps - 1) ? 0.5 * p.ds : p.ds;
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double2* qw = reinterpret_cast<double2*>(qw_all + warp * H4E * p.Ps);     // [k][2] double2 = 4 entries
+  double* geo = geo_all + warp * 4 * H4ROUND;
+  double* g_dd = geo;
+  double* g_ch = geo + H4ROUND;
+  double* g_sh = geo + 2 * H4ROUND;
+  long long* g_off = reinterpret_cast<long long*>(geo + 3 * H4ROUND);
+  const long long total = p.m * p.n;
+  const long long wstride = (long long)gridDim.x * QWARPS;
+
+  double i2t[NQ], tc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int a = lane + 32 * q;
+    i2t[q] = 0.5 / ((a < p.Pt) ? p.tval[a] : 1.0);
+    tc[q] = (a < p.Pt) ? p.tcoef[a] : 0.0;
+  }
+
+  for (long long ebase = (long long)blockIdx.x * QWARPS + warp; ebase < total; ebase += H4ROUND * wstride) {
+    __syncwarp();
+#pragma unroll 1
+    for (int mth = 0; mth < H4ROUND / 32; ++mth) {
+      const int t = lane + 32 * mth;
+      const long long el = ebase + t * wstride;
+      double d = 0.0, c = 1.0, sn = 0.0;
+      long long off = -1;
+      if (el < total) {
+        const long long il = el / p.n, jl = el - il * p.n;
+        d = lorentz_dist(p.x1 + il * p.ld1, p.x2 + jl * p.ld2, 2);
+        c = cosh(d);
+        sn = sinh(d);
+        off = il * p.ldk + jl;
+      }
+      g_dd[t] = d;
+      g_ch[t] = c;
+      g_sh[t] = sn;
+      g_off[t] = off;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int sub = 0; sub < H4ROUND / H4E; ++sub) {
+      if (ebase + (long long)(H4E * sub) * wstride >= total) break;
+      double dd[H4E];
+      {
+        const double2 a01 = reinterpret_cast<const double2*>(g_dd)[2 * sub], a23 = reinterpret_cast<const double2*>(g_dd)[2 * sub + 1];
+        dd[0] = a01.x; dd[1] = a01.y; dd[2] = a23.x; dd[3] = a23.y;
+      }
+      __syncwarp();          // the previous iteration's node loop has finished reading qw
+      {
+        const double2 c01 = reinterpret_cast<const double2*>(g_ch)[2 * sub], c23 = reinterpret_cast<const double2*>(g_ch)[2 * sub + 1];
+        const double2 s01 = reinterpret_cast<const double2*>(g_sh)[2 * sub], s23 = reinterpret_cast<const double2*>(g_sh)[2 * sub + 1];
+        for (int k = lane; k < p.Ps; k += 32) {
+          const double bk = p.s0 + k * p.ds;
+          const double c = cm1[k], sn = sh[k], wk = wq[k];
+          double2 w01, w23;
+          w01.x = wk * (bk + dd[0]) * rsqrt(fma(c01.x, c, s01.x * sn));
+          w01.y = wk * (bk + dd[1]) * rsqrt(fma(c01.y, c, s01.y * sn));
+          w23.x = wk * (bk + dd[2]) * rsqrt(fma(c23.x, c, s23.x * sn));
+          w23.y = wk * (bk + dd[3]) * rsqrt(fma(c23.y, c, s23.y * sn));
+          qw[2 * k] = w01;
+          qw[2 * k + 1] = w23;
+        }
+      }
+      __syncwarp();
+      double r[H4E][NQ], acc[H4E][NQ];
+#pragma unroll
+      for (int j = 0; j < H4E; ++j)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          r[j][q] = exp(-p.ds * dd[j] * i2t[q]);
+          acc[j][q] = 0.0;
+        }
+      {
+        const double2* wp = qw + 2 * (p.Ps - 1);
+        if (NQ == 1) {
+          const double* ep = Es + lane + (p.Ps - 1) * 32;
+#pragma unroll 4
+          for (int k = p.Ps - 1; k >= 0; --k, ep -= 32, wp -= 2) {
+            const double2 w01 = wp[0], w23 = wp[1];
+            const double ev = *ep;
+            acc[0][0] = fma(acc[0][0], r[0][0], w01.x * ev);
+            acc[1][0] = fma(acc[1][0], r[1][0], w01.y * ev);
+            acc[2][0] = fma(acc[2][0], r[2][0], w23.x * ev);
+            acc[3][0] = fma(acc[3][0], r[3][0], w23.y * ev);
+          }
+        } else {
+          const double2* ep = reinterpret_cast<const double2*>(Es) + lane + (p.Ps - 1) * 32;
+#pragma unroll 4
+          for (int k = p.Ps - 1; k >= 0; --k, ep -= 32, wp -= 2) {
+            const double2 w01 = wp[0], w23 = wp[1];
+            const double2 ev = *ep;
+            acc[0][0] = fma(acc[0][0], r[0][0], w01.x * ev.x);
+            acc[1][0] = fma(acc[1][0], r[1][0], w01.y * ev.x);
+            acc[2][0] = fma(acc[2][0], r[2][0], w23.x * ev.x);
+            acc[3][0] = fma(acc[3][0], r[3][0], w23.y * ev.x);
+            acc[0][NQ - 1] = fma(acc[0][NQ - 1], r[0][NQ - 1], w01.x * ev.y);
+            acc[1][NQ - 1] = fma(acc[1][NQ - 1], r[1][NQ - 1], w01.y * ev.y);
+            acc[2][NQ - 1] = fma(acc[2][NQ - 1], r[2][NQ - 1], w23.x * ev.y);
+            acc[3][NQ - 1] = fma(acc[3][NQ - 1], r[3][NQ - 1], w23.y * ev.y);
+          }
+        }
+      }
+      double sum[H4E];
+#pragma unroll
+      for (int j = 0; j < H4E; ++j) {
+        sum[j] = 0.0;
+        const double cexp = -(dd[j] * dd[j] + 2.0 * p.s0 * dd[j]) * 0.5;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) sum[j] = fma(tc[q], exp(cexp * i2t[q]) * acc[j][q], sum[j]);
+      }
+      // split butterfly: after the xor-16 and xor-8 stages each group of 8 lanes owns one entry
+      {
+        const bool hi = lane & 16;
+        const double keep0 = hi ? sum[2] : sum[0], keep1 = hi ? sum[3] : sum[1];
+        const double send0 = hi ? sum[0] : sum[2], send1 = hi ? sum[1] : sum[3];
+        const double a0 = keep0 + __shfl_xor_sync(0xffffffffu, send0, 16);
+        const double a1 = keep1 + __shfl_xor_sync(0xffffffffu, send1, 16);
+        const bool mid = lane & 8;
+        const double keep = mid ? a1 : a0, send = mid ? a0 : a1;
+        double v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if ((lane & 7) == 0) {
+          const long long off = g_off[H4E * sub + (lane >> 3)];
+          if (off >= 0) st_stream(p.K + off, v);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // SPD(2)
 // ------------------------------------------------------------------------------------------------
 struct SpdParams {
@@ -593,6 +773,12 @@ static int sm_count() {
   return g_sms;
 }
 
+// MGB_H2_PATH=generic keeps the two-entries-per-iteration kernel for the forward Gram as well (A/B measurements, tests)
+static bool hyp_force_generic() {
+  const char* e = getenv("MGB_H2_PATH");
+  return e != nullptr && strcmp(e, "generic") == 0;
+}
+
 static int hyp_launch(HypParams p, cudaStream_t s) {
   if (p.dim < 1 || p.dim > 3) return fail(MGB_ERR_ARG, "hyperbolic: dim must be 1, 2 or 3 (NotImplementedError in the reference)");
   if (p.Pt < 1 || p.Pt > QMAXT) return fail(MGB_ERR_ARG, "hyperbolic: Pt out of range [1,128]");
@@ -611,6 +797,24 @@ static int hyp_launch(HypParams p, cudaStream_t s) {
     const size_t nE = (size_t)p.Ps * p.Pt;
     smem = pad ? padded : sizeof(double) * (nE + (nE & 1) + rest);
     if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "hyperbolic: Ps*Pt table exceeds shared memory");
+  }
+  if (p.dim == 2 && p.geom != 1 && p.mode == Q_FWD && !p.deriv && nq <= 2 && total >= 4096 && !hyp_force_generic()) {
+    const size_t smem4 = sizeof(double) * ((size_t)p.Ps * 32 * nq + (size_t)QWARPS * H4E * p.Ps + (size_t)QWARPS * 4 * H4ROUND +
+                                           3 * (size_t)p.Ps);
+    if (smem4 <= 110 * 1024) {
+      long long blocks4 = (total + QWARPS * H4E - 1) / (QWARPS * H4E);
+      if (blocks4 > 2LL * sm_count()) blocks4 = 2LL * sm_count();
+      if (nq == 1) {
+        MGB_TRY(check_cuda(cudaFuncSetAttribute(h2_gram_fwd4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4),
+                           "cudaFuncSetAttribute"));
+        h2_gram_fwd4_kernel<1><<<(unsigned)blocks4, QTHREADS, smem4, s>>>(p);
+      } else {
+        MGB_TRY(check_cuda(cudaFuncSetAttribute(h2_gram_fwd4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4),
+                           "cudaFuncSetAttribute"));
+        h2_gram_fwd4_kernel<2><<<(unsigned)blocks4, QTHREADS, smem4, s>>>(p);
+      }
+      return after_launch("h2_gram_fwd4_kernel");
+    }
   }
   long long blocks = (total + QWARPS - 1) / QWARPS;
   const long long cap = (long long)sm_count() * 8;

@@ -507,3 +507,32 @@ def test_fused_spd2_acquisition_value_and_gradient(which):
     assert rel_err(ei, val) < 1e-11 and rel_err(grad, ga) < 1e-9
     with pytest.raises(NotImplementedError):
         acq.value_grad_hvp(xc, torch.zeros_like(xc))
+
+
+@pytest.mark.parametrize("m,n,P", [(67, 71, 64), (130, 129, 50), (96, 80, 20), (257, 31, 33), (1024, 517, 64)])
+def test_h2_four_entry_forward_kernel_matches_generic_kernel_and_oracle(m, n, P):
+    """The forward Gram of H^2 blocks with >= 4096 entries runs the four-entries-per-warp kernel (h2_gram_fwd4_kernel);
+    MGB_H2_PATH=generic keeps the two-entry kernel: same nodes, same tables - the values agree to rounding, for ragged
+    sizes (partial last rounds / partial groups of four) and for one and two t nodes per lane."""
+    import os
+    from materngabo_b200 import kernels_hyperbolic as kh
+    from oracle import restated as R
+
+    torch.manual_seed(m + n)
+    z1, z2 = 0.8 * torch.randn(m, 2), 0.8 * torch.randn(n, 2)
+    x1 = torch.cat([torch.sqrt(1 + (z1 ** 2).sum(-1, keepdim=True)), z1], -1)
+    x2 = torch.cat([torch.sqrt(1 + (z2 ** 2).sum(-1, keepdim=True)), z2], -1)
+    x2[: min(m, n) // 3] = x1[: min(m, n) // 3]                  # repeated points: d = 2 asinh(5e-5)
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=P)
+    k.lengthscale = 0.9
+    with torch.no_grad():
+        fast = k.forward(x1.to(DEV), x2.to(DEV))
+        os.environ["MGB_H2_PATH"] = "generic"
+        try:
+            slow = k.forward(x1.to(DEV), x2.to(DEV))
+        finally:
+            del os.environ["MGB_H2_PATH"]
+    assert torch.isfinite(fast).all()
+    assert rel_err(fast, slow) < 1e-13
+    ref = R.hyperbolic_integrated_matern(x1[:40], x2[:36], 2, 2.5, 0.9, P)
+    assert rel_err(fast[:40, :36], ref) < TOL
