@@ -40,6 +40,37 @@ __device__ __forceinline__ double lorentz_dist(const double* a, const double* b,
   return 2.0 * asinh(0.5 * nrm);
 }
 
+// Branch-free exp for the quadrature inner phases (arguments <= 0 up to rounding; any |x| < 1e9 is handled).
+// Same scheme as the CUDA library's fast path - round x log2(e) with the 1.5 * 2^52 trick, two-constant reduction,
+// degree-11 polynomial (Chebyshev-node interpolant on |r| <= ln2 / 2, approximation error 1.5e-17) - but the scaling
+// by 2^n is done without the library's out-of-range branch: the exponent is added in two pieces (n1 >= -1000 into the
+// exponent field, the rest as a power-of-two factor that reaches 0 for results below the denormal range).  Without the
+// branch the compiler interleaves the independent exponentials of an unrolled loop, which is what hides the FP64
+// latency at 8-16 warps per SM.
+__device__ __forceinline__ double exp_bf(double x) {
+  double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+  const int n = __double2loint(t);
+  t -= 6755399441055744.0;
+  double r = fma(t, -6.9314718055994529e-1, x);
+  r = fma(t, -2.3190468138462996e-17, r);
+  double q = 2.5110095611886237e-08;
+  q = fma(q, r, 2.7632715071632255e-07);
+  q = fma(q, r, 2.7557240761739257e-06);
+  q = fma(q, r, 2.4801485278370062e-05);
+  q = fma(q, r, 0.00019841269890193705);
+  q = fma(q, r, 0.0013888888952505406);
+  q = fma(q, r, 0.008333333333319546);
+  q = fma(q, r, 0.04166666666648738);
+  q = fma(q, r, 0.1666666666666668);
+  q = fma(q, r, 0.5000000000000019);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  const int n1 = max(n, -1000);
+  const int n2 = max(n - n1, -1023);
+  const double v = __hiloint2double(__double2hiint(q) + (n1 << 20), __double2loint(q));
+  return v * __hiloint2double((n2 + 1023) << 20, 0);
+}
+
 struct HypParams {
   int dim, mode;
   int geom, width;   // geom 1: Euclidean rows of `width` doubles, heat(d, t) = exp(-|x1 - x2|^2 / (4 t))
@@ -430,7 +461,7 @@ __global__ void __launch_bounds__(QTHREADS, 2) h2_gram_fwd4_kernel(HypParams p) 
       for (int j = 0; j < H4E; ++j)
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-          r[j][q] = exp(-p.ds * dd[j] * i2t[q]);
+          r[j][q] = exp_bf(-p.ds * dd[j] * i2t[q]);
           acc[j][q] = 0.0;
         }
       {
@@ -469,7 +500,7 @@ __global__ void __launch_bounds__(QTHREADS, 2) h2_gram_fwd4_kernel(HypParams p) 
         sum[j] = 0.0;
         const double cexp = -(dd[j] * dd[j] + 2.0 * p.s0 * dd[j]) * 0.5;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) sum[j] = fma(tc[q], exp(cexp * i2t[q]) * acc[j][q], sum[j]);
+        for (int q = 0; q < NQ; ++q) sum[j] = fma(tc[q], exp_bf(cexp * i2t[q]) * acc[j][q], sum[j]);
       }
       // split butterfly: after the xor-16 and xor-8 stages each group of 8 lanes owns one entry
       {
@@ -762,6 +793,151 @@ __global__ void __launch_bounds__(LTHREADS, 1) spd2_lattice_kernel(SpdLatticePar
   }
 }
 
+// Two entries per warp iteration.  spd2_lattice_kernel is bound by shared-memory wavefronts (ncu: 69 % LSU, 43 % FP64
+// pipe): per inner node b it reads 1 (weight) + 4 (table row E[b][.]) + 4 (lattice gather) wavefronts for 4 FP64
+// instructions.  Here the table row and the weight pair serve two entries (13 wavefronts per 8 FP64 instructions), the
+// table is stored lane-major as double2 = the two t nodes of a lane (zero padded, no predicates), the two entries'
+// lattice exponentials are interleaved ({X0[k], X1[k]}: one 16-byte gather per t node) and so are the weights.
+constexpr int L2THREADS = 256;
+constexpr int L2WARPS = L2THREADS / 32;
+
+__global__ void __launch_bounds__(L2THREADS, 1) spd2_lattice2_kernel(SpdLatticeParams p) {
+  extern __shared__ __align__(16) double sm[];
+  // layout: E2 [Pb][32] double2 | G [nk (+1)] | bv, bw, shb, chb [Pb each (+pad)] | per warp: X01 [nk] double2 | qb01 [Pb] double2
+  double2* E2 = reinterpret_cast<double2*>(sm);
+  double* Gs = sm + (size_t)p.Pb * 64;
+  const int nkp = p.nk + (p.nk & 1), Pbp = p.Pb + (p.Pb & 1);
+  double* bv = Gs + nkp;
+  double* bw = bv + Pbp;
+  double* shb = bw + Pbp;
+  double* chb = shb + Pbp;
+  double2* wbase = reinterpret_cast<double2*>(chb + Pbp);
+  for (int e = threadIdx.x; e < p.Pb * 64; e += blockDim.x) {
+    const int d2 = e >> 1, b = d2 >> 5, a = (d2 & 31) + 32 * (e & 1);
+    const double bb = p.bval[b];
+    sm[e] = (a < p.Pt) ? exp(-bb * bb * p.bscale[a]) : 0.0;
+  }
+  for (int k = threadIdx.x; k < p.nk; k += blockDim.x) Gs[k] = -p.g_min * exp(k * p.log_tau);
+  for (int e = threadIdx.x; e < p.Pb; e += blockDim.x) {
+    const double b = p.bval[e];
+    bv[e] = b;
+    bw[e] = p.bw[e];
+    shb[e] = sinh(b);
+    chb[e] = cosh(b);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double2* X = wbase + (size_t)warp * (p.nk + p.Pb);
+  double2* qb = X + p.nk;
+  double tc[LNQ], rs[LNQ];
+  int koff[LNQ];
+#pragma unroll
+  for (int q = 0; q < LNQ; ++q) {
+    const int a = lane + 32 * q;
+    tc[q] = (a < p.Pt) ? p.tcoef[a] : 0.0;
+    rs[q] = (a < p.Pt) ? p.rscale[a] : 0.0;
+    koff[q] = (a < p.Pt) ? p.sa * (p.Pt - 1 - a) : 0;
+  }
+  const long long total = p.m * p.n;
+  const long long wstride = (long long)gridDim.x * L2WARPS;
+  for (long long ebase = (long long)blockIdx.x * L2WARPS + warp; ebase < total; ebase += 32 * wstride) {
+    // pair geometry of this warp's next 32 entries, one entry per lane
+    double g_delta = 0.0, g_r2 = 0.0, g_sh = 0.0, g_ch = 1.0;
+    long long g_off = -1;
+    {
+      const long long el = ebase + lane * wstride;
+      if (el < total) {
+        const long long il = el / p.n, jl = el - il * p.n;
+        double H1, H2;
+        spd2_logsv(p.x1 + il * p.ld1, p.x2 + jl * p.ld2, p.use_chol, H1, H2);
+        g_delta = H1 - H2;
+        g_r2 = H1 * H1 + H2 * H2;
+        g_sh = sinh(g_delta);
+        g_ch = cosh(g_delta);
+        g_off = il * p.ldk + jl;
+      }
+    }
+#pragma unroll 1
+    for (int sub = 0; sub < 16; ++sub) {
+      if (ebase + (long long)(2 * sub) * wstride >= total) break;
+      const double d0 = __shfl_sync(0xffffffffu, g_delta, 2 * sub), d1 = __shfl_sync(0xffffffffu, g_delta, 2 * sub + 1);
+      __syncwarp();          // the previous iteration's node loop has finished reading X and qb
+      {
+        int k = lane;
+        for (; k + 32 < p.nk; k += 64) {
+          const double ga = Gs[k], gb = Gs[k + 32];
+          double2 xa, xb;
+          xa.x = exp_bf(d0 * ga); xa.y = exp_bf(d1 * ga);
+          xb.x = exp_bf(d0 * gb); xb.y = exp_bf(d1 * gb);
+          X[k] = xa;
+          X[k + 32] = xb;
+        }
+        for (; k < p.nk; k += 32) {
+          const double ga = Gs[k];
+          double2 xa;
+          xa.x = exp_bf(d0 * ga); xa.y = exp_bf(d1 * ga);
+          X[k] = xa;
+        }
+      }
+      {
+        const double sh0 = __shfl_sync(0xffffffffu, g_sh, 2 * sub), sh1 = __shfl_sync(0xffffffffu, g_sh, 2 * sub + 1);
+        const double ch0 = __shfl_sync(0xffffffffu, g_ch, 2 * sub), ch1 = __shfl_sync(0xffffffffu, g_ch, 2 * sub + 1);
+        for (int b = lane; b < p.Pb; b += 32) {
+          const double bb = bv[b], sb_ = shb[b], cb_ = chb[b], wb = bw[b];
+          double2 qv;
+          qv.x = wb * (2.0 * bb + d0) * rsqrt(sb_ * fma(sb_, ch0, cb_ * sh0));   // sinh(b + delta) = sinh b cosh delta + cosh b sinh delta
+          qv.y = wb * (2.0 * bb + d1) * rsqrt(sb_ * fma(sb_, ch1, cb_ * sh1));
+          qb[b] = qv;
+        }
+      }
+      __syncwarp();
+      double acc[2][LNQ];
+#pragma unroll
+      for (int q = 0; q < LNQ; ++q) acc[0][q] = acc[1][q] = 0.0;
+      {
+        const double2* Ep = E2 + lane;
+        const double2* X0 = X + koff[0];
+        const double2* X1 = X + koff[1];
+        const int sb = p.sb;
+#pragma unroll 4
+        for (int b = 0; b < p.Pb; ++b, Ep += 32, X0 += sb, X1 += sb) {
+          const double2 qv = qb[b];
+          const double2 ev = *Ep;
+          const double2 xa = *X0, xb = *X1;
+          acc[0][0] = fma(qv.x * ev.x, xa.x, acc[0][0]);
+          acc[1][0] = fma(qv.y * ev.x, xa.y, acc[1][0]);
+          acc[0][1] = fma(qv.x * ev.y, xb.x, acc[0][1]);
+          acc[1][1] = fma(qv.y * ev.y, xb.y, acc[1][1]);
+        }
+      }
+      const double r20 = __shfl_sync(0xffffffffu, g_r2, 2 * sub), r21 = __shfl_sync(0xffffffffu, g_r2, 2 * sub + 1);
+      const long long off0 = __shfl_sync(0xffffffffu, g_off, 2 * sub), off1 = __shfl_sync(0xffffffffu, g_off, 2 * sub + 1);
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < LNQ; ++q) {
+        s0 = fma(tc[q] * exp_bf(-r20 * rs[q]), acc[0][q], s0);
+        s1 = fma(tc[q] * exp_bf(-r21 * rs[q]), acc[1][q], s1);
+      }
+      // split butterfly: lanes 0-15 end up with entry 0, lanes 16-31 with entry 1
+      const bool hi = lane & 16;
+      double v = (hi ? s1 : s0) + __shfl_xor_sync(0xffffffffu, hi ? s0 : s1, 16);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      if ((lane & 15) == 0) {
+        const long long off = hi ? off1 : off0;
+        if (off >= 0) st_stream(p.K + off, v);
+      }
+    }
+  }
+}
+
+static size_t spd2_lattice2_smem(int Pb, int nk) {
+  const int nkp = nk + (nk & 1), Pbp = Pb + (Pb & 1);
+  return sizeof(double) * ((size_t)Pb * 64 + nkp + 4 * (size_t)Pbp + (size_t)L2WARPS * 2 * (nk + Pb));
+}
+
 // ------------------------------------------------------------------------------------------------
 static int g_sms = 0;
 static int sm_count() {
@@ -1003,9 +1179,22 @@ extern "C" int mgb_spd2_gram_fwd_lattice(int use_cholesky, const double* x1, lon
   p.tcoef = tcoef; p.rscale = rscale; p.bscale = bscale; p.Pt = Pt; p.bval = bval; p.bw = bw; p.Pb = Pb;
   p.sb = sb; p.sa = sa; p.nk = sb * (Pb - 1) + sa * (Pt - 1) + 1; p.g_min = g_min; p.log_tau = log_tau;
   p.K = K; p.ldk = ldk;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    const char* force = getenv("MGB_SPD2_PATH");       // "lattice1": the one-entry-per-iteration kernel (A/B measurements, tests)
+    const size_t smem2 = spd2_lattice2_smem(Pb, p.nk);
+    if (smem2 <= 227 * 1024 && !(force != nullptr && strcmp(force, "lattice1") == 0)) {
+      MGB_TRY(check_cuda(cudaFuncSetAttribute(spd2_lattice2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2),
+                         "cudaFuncSetAttribute"));
+      const long long total2 = m * n;
+      long long blocks2 = (total2 + 2 * L2WARPS - 1) / (2 * L2WARPS);
+      if (blocks2 > (long long)sm_count()) blocks2 = sm_count();
+      spd2_lattice2_kernel<<<(unsigned)blocks2, L2THREADS, smem2, s>>>(p);
+      return after_launch("spd2_lattice2_kernel");
+    }
+  }
   const size_t smem = sizeof(double) * ((size_t)Pb * Pt + p.nk + 4 * (size_t)Pb + (size_t)LWARPS * (p.nk + Pb));
   if (smem > 200 * 1024) return fail(MGB_ERR_ARG, "spd2_gram_fwd_lattice: lattice too large for shared memory");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   MGB_TRY(check_cuda(cudaFuncSetAttribute(spd2_lattice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                      "cudaFuncSetAttribute"));
   const long long total = m * n;

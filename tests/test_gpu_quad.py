@@ -536,3 +536,36 @@ def test_h2_four_entry_forward_kernel_matches_generic_kernel_and_oracle(m, n, P)
     assert rel_err(fast, slow) < 1e-13
     ref = R.hyperbolic_integrated_matern(x1[:40], x2[:36], 2, 2.5, 0.9, P)
     assert rel_err(fast[:40, :36], ref) < TOL
+
+
+@pytest.mark.parametrize("m,n,nb,nt", [(67, 71, 64, 64), (33, 1, 50, 50), (130, 129, 40, 40), (1, 3, 64, 64), (200, 77, 64, 64)])
+def test_spd2_two_entry_lattice_kernel_matches_one_entry_kernel(m, n, nb, nt):
+    """spd2_lattice2_kernel (two entries per warp iteration, the default) against spd2_lattice_kernel
+    (MGB_SPD2_PATH=lattice1): same lattice, same nodes; odd entry counts leave the second slot of the last pair empty."""
+    import os
+    from materngabo_b200 import _ops
+    from materngabo_b200 import kernels_spd as ksp
+
+    torch.manual_seed(m * 7 + n)
+    a = torch.randn(max(m, n), 2, 2)
+    s = a @ a.transpose(-1, -2) + 0.05 * torch.eye(2)
+    v = torch.stack([s[:, 0, 0], s[:, 1, 1], s[:, 0, 1] * 2 ** 0.5], -1).to(DEV)
+    k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5, nb_points_integral_b=nb, nb_points_integral_t=nt)
+    k.lengthscale = 1.3
+    saved = _ops.SPD2_LATTICE_MIN_ENTRIES
+    try:
+        _ops.SPD2_LATTICE_MIN_ENTRIES = 1
+        with torch.no_grad():
+            two = k.forward(v[:m], v[:n])
+            os.environ["MGB_SPD2_PATH"] = "lattice1"
+            try:
+                one = k.forward(v[:m], v[:n])
+            finally:
+                del os.environ["MGB_SPD2_PATH"]
+            _ops.SPD2_LATTICE_MIN_ENTRIES = 1 << 60
+            direct = k.forward(v[:m], v[:n])
+    finally:
+        _ops.SPD2_LATTICE_MIN_ENTRIES = saved
+    assert torch.isfinite(two).all()
+    assert rel_err(two, one) < 1e-13
+    assert rel_err(two, direct) < 1e-12
