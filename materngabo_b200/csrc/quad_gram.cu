@@ -864,6 +864,18 @@ __global__ void __launch_bounds__(L2THREADS, 1) spd2_lattice2_kernel(SpdLatticeP
       __syncwarp();          // the previous iteration's node loop has finished reading X and qb
       {
         int k = lane;
+        for (; k + 96 < p.nk; k += 128) {
+          const double ga = Gs[k], gb = Gs[k + 32], gc = Gs[k + 64], gd = Gs[k + 96];
+          double2 xa, xb, xc, xd;
+          xa.x = exp_bf(d0 * ga); xa.y = exp_bf(d1 * ga);
+          xb.x = exp_bf(d0 * gb); xb.y = exp_bf(d1 * gb);
+          xc.x = exp_bf(d0 * gc); xc.y = exp_bf(d1 * gc);
+          xd.x = exp_bf(d0 * gd); xd.y = exp_bf(d1 * gd);
+          X[k] = xa;
+          X[k + 32] = xb;
+          X[k + 64] = xc;
+          X[k + 96] = xd;
+        }
         for (; k + 32 < p.nk; k += 64) {
           const double ga = Gs[k], gb = Gs[k + 32];
           double2 xa, xb;
