@@ -139,13 +139,14 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
   const long long wstride = (long long)gridDim.x * QWARPS;
 
   // per-lane outer nodes a = lane + 32 q
-  double tv[NQ], tc[NQ], gacc[NQ];
+  double tv[NQ], tc[NQ], gacc[NQ], i4t[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const int a = lane + 32 * q;
     tv[q] = (a < p.Pt) ? p.tval[a] : 1.0;
     tc[q] = (a < p.Pt && p.tcoef != nullptr) ? p.tcoef[a] : 0.0;
     gacc[q] = 0.0;
+    i4t[q] = 0.25 / tv[q];
   }
 
   // Two entries per warp iteration: the pair-independent table values E[k][a] are fetched once and used for both.
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
   double2* qw01 = reinterpret_cast<double2*>(qw_all + 2 * warp * nP);   // PAD: {entry 0, entry 1} per inner node
   for (long long ebase = (long long)blockIdx.x * QWARPS + warp; ebase < total; ebase += 64 * wstride) {
     double l_dd[2] = {0.0, 0.0}, l_dsq[2] = {0.0, 0.0}, l_ch[2] = {1.0, 1.0}, l_sh[2] = {0.0, 0.0};
+    long long l_off[2] = {0, 0};   // output (Q_FWD) / upstream-gradient (backward modes) offset of the lane's entries
 #pragma unroll
     for (int s2 = 0; s2 < 2; ++s2) {
       const long long el = ebase + (2 * lane + s2) * wstride;
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
           l_dd[s2] = p.dist[el];
         } else {
           const long long il = el / p.n, jl = el - il * p.n;
+          l_off[s2] = il * (p.mode == Q_FWD ? p.ldk : p.ldg) + jl;
           if (p.geom == 1) {
             const double* xa = p.x1 + il * p.ld1;
             const double* xb = p.x2 + jl * p.ld2;
@@ -179,6 +182,8 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
         if (p.dim == 2 && p.geom != 1) {
           l_ch[s2] = cosh(l_dd[s2]);
           l_sh[s2] = sinh(l_dd[s2]);
+        } else if (p.dim == 3 && p.geom != 1) {
+          l_ch[s2] = (l_dd[s2] + 1e-8) / sinh(l_dd[s2] + 1e-8);   // heat kernel of H^3: exp(-d^2 / 4t) d / sinh d
         }
       }
     }
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
     const long long e1 = e0 + wstride;
     const bool has1 = e1 < total;
     long long ei[2] = {e0, has1 ? e1 : e0};
-    long long ii[2] = {0, 0}, jj[2] = {0, 0};
+    long long off[2];
     double dd[2], dsq[2], chd2[2], shd2[2];
 #pragma unroll
     for (int s2 = 0; s2 < 2; ++s2) {
@@ -196,10 +201,7 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
       dsq[s2] = __shfl_sync(0xffffffffu, l_dsq[s2], sub);
       chd2[s2] = __shfl_sync(0xffffffffu, l_ch[s2], sub);
       shd2[s2] = __shfl_sync(0xffffffffu, l_sh[s2], sub);
-      if (p.mode != Q_NODES) {
-        ii[s2] = ei[s2] / p.n;
-        jj[s2] = ei[s2] - ii[s2] * p.n;
-      }
+      off[s2] = __shfl_sync(0xffffffffu, l_off[s2], sub);
     }
     if (!has1) { dd[1] = dd[0]; dsq[1] = dsq[0]; chd2[1] = chd2[0]; shd2[1] = shd2[0]; }
     double h[2][NQ];
@@ -302,9 +304,9 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
           const int a = lane + 32 * q;
           h[s2][q] = 0.0;
           if (a < p.Pt) {
-            double v = exp(-dsq[s2] / (4.0 * tv[q]));
-            if (p.dim == 3 && p.geom != 1) v = v * (dd[s2] + 1e-8) / sinh(dd[s2] + 1e-8);
-            if (p.deriv) v = v * dsq[s2] / (4.0 * tv[q] * tv[q]);
+            double v = exp_bf(-dsq[s2] * i4t[q]);
+            if (p.dim == 3 && p.geom != 1) v = v * chd2[s2];
+            if (p.deriv) v = v * dsq[s2] * (4.0 * i4t[q] * i4t[q]);
             h[s2][q] = v;
           }
         }
@@ -318,13 +320,13 @@ __global__ void __launch_bounds__(QTHREADS) hyp_gram_kernel(HypParams p) {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) sum = fma(tc[q], h[s2][q], sum);
         sum = warp_sum(sum);
-        if (lane == 0) st_stream(p.K + ii[s2] * p.ldk + jj[s2], sum);
+        if (lane == 0) st_stream(p.K + off[s2], sum);
       } else if (p.mode == Q_BWD_COEF) {
-        const double gg = p.G[ii[s2] * p.ldg + jj[s2]];
+        const double gg = p.G[off[s2]];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) gacc[q] = fma(gg, h[s2][q], gacc[q]);
       } else if (p.mode == Q_BWD_TVAL) {
-        const double gg = p.G[ii[s2] * p.ldg + jj[s2]];
+        const double gg = p.G[off[s2]];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) gacc[q] = fma(gg * tc[q], h[s2][q], gacc[q]);
       } else {
