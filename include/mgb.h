@@ -179,10 +179,12 @@ int mgb_spd2_gram_bwd_coef(int use_cholesky, const double* x1, long long m, long
  *     kind 0/1/2 = H^1/H^2/H^3 with z = geodesic distance and heat as above (for H^2 the s grid moves with d,
  *     kernels_hyperbolic.py:299, and the derivative includes it, as autograd does in the reference);
  *     kind 3 = Euclidean factor, z = |x - y|^2, heat = exp(-z / (4 t)) (kernels_euclidean.py:82-89).
+ *     order 3 = all three orders from one launch, out[o * count + e] (the exponentials are shared);
  *   mgb_radial_profile_bwd_coef:  gtcoef[a] += sum_e G[e] * d^order/dz^order heat(z[e], tval[a])  (caller zeroes)
  *   mgb_spd2_profile:  out[e] = sum_a tcoef[a] * D h_a(delta[e], r2[e]),  which = 0: D = 1, 1: d/dDelta, 2: d/dr2,
  *     h_a(Delta, r2) = exp(-r2 rscale[a]) sum_b bw[b] (2 b_b + Delta) exp(-b_b (b_b + Delta) bscale[a])
  *                                                   / sqrt(sinh b_b sinh(b_b + Delta))   (kernels_spd.py:200-209)
+ *     which 3 = all three from one launch, out[which * count + e];
  *   mgb_spd2_profile_bwd_coef:  gtcoef[a] += sum_e G[e] * D h_a(delta[e], r2[e])  (caller zeroes)
  * ------------------------------------------------------------------------------------------------ */
 int mgb_radial_profile(int kind, int order, const double* z, long long count, const double* tval,
@@ -328,6 +330,27 @@ int mgb_spd2_acquisition_ei(int use_cholesky, const double* xc, long long b, lon
                             double outputscale, const double* rinv, long long ldr, const double* rinv_t, long long ldrt,
                             const double* alpha, double kss, double mean_const, double best_f, int maximize, double* ei,
                             double* grad, void* stream);
+
+/* The whole trust-region step of the quadrature kernels in ONE call: pair scalars (mgb_pair_scalars) -> profile and
+ * its derivatives (mgb_radial_profile / mgb_spd2_profile) -> acquisition kernel, enqueued back to back on `stream`
+ * with the b x n intermediates in caller-owned scratch `work` (work_doubles >= 4 * b * n for the radial kernels,
+ * >= 5 * b * n for SPD(2)).  Same results as the three-step sequence; what it removes is the host time between the
+ * launches (five binding calls and allocations per step at the reference's b = 1 ... 5 restarts, n <= a few hundred).
+ * kind: 0/1/2 = H^1/H^2/H^3 (rows kind + 2 wide), 3 = Euclidean (rows `width` wide). */
+int mgb_radial_acquisition_ei_step(int kind, int width, const double* xc, long long b, long long ldc, const double* v,
+                                   long long ldv, const double* xtrain, long long n, long long ldt, const double* tval,
+                                   const double* tcoef, int Pt, double s0, double ds, int Ps, double outputscale,
+                                   const double* rinv, long long ldr, const double* rinv_t, long long ldrt,
+                                   const double* alpha, double kss, double mean_const, double best_f, int maximize,
+                                   double* work, long long work_doubles, double* ei, double* grad, double* hvp,
+                                   void* stream);
+int mgb_spd2_acquisition_ei_step(int use_cholesky, const double* xc, long long b, long long ldc, const double* xtrain,
+                                 long long n, long long ldt, const double* tcoef, const double* rscale,
+                                 const double* bscale, int Pt, const double* bval, const double* bw, int Pb,
+                                 double outputscale, const double* rinv, long long ldr, const double* rinv_t,
+                                 long long ldrt, const double* alpha, double kss, double mean_const, double best_f,
+                                 int maximize, double* work, long long work_doubles, double* ei, double* grad,
+                                 void* stream);
 
 /* Series coefficients of the sphere / SO(3) kernels and their Jacobian with respect to (kappa, nu) in one launch
  * (the hyper-parameter -> coefficient chain of kernels_sphere.py:126-139,212-224 and kernels_so.py:264-273,101, which

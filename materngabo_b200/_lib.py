@@ -71,6 +71,10 @@ PROTOTYPES = {
                                        _D, _D, _D, _I, _P, _P, _P, _P]),
     "mgb_spd2_acquisition_ei": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P, _D, _P, _LL, _P, _LL, _P, _D, _D, _D, _I,
                                      _P, _P, _P]),
+    "mgb_radial_acquisition_ei_step": (_I, [_I, _I, _P, _LL, _LL, _P, _LL, _P, _LL, _LL, _P, _P, _I, _D, _D, _I, _D, _P, _LL,
+                                            _P, _LL, _P, _D, _D, _D, _I, _P, _LL, _P, _P, _P, _P]),
+    "mgb_spd2_acquisition_ei_step": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P, _I, _P, _P, _I, _D, _P, _LL, _P, _LL,
+                                          _P, _D, _D, _D, _I, _P, _LL, _P, _P, _P]),
     "mgb_expected_improvement": (_I, [_P, _P, _LL, _D, _I, _P, _P]),
     "mgb_pair_scalars": (_I, [_I, _I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P]),
     "mgb_spectral_coef": (_I, [_I, _I, _I, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),

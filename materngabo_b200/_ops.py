@@ -444,7 +444,7 @@ def inputs_need_grad(*tensors) -> bool:
 def _radial_profile_raw(kind, order, z, tval, tcoef, s0, ds, ps):
     lib = _lib.load()
     z = z.contiguous()
-    out = torch.empty_like(z)
+    out = torch.empty_like(z) if order != 3 else torch.empty((3,) + tuple(z.shape), dtype=z.dtype, device=z.device)
     with torch.cuda.device(z.device):
         rc = lib.mgb_radial_profile(kind, order, _lib.ptr(z), z.numel(), _lib.ptr(tval), _lib.ptr(tcoef), tval.shape[0],
                                     s0, ds, ps, _lib.ptr(out), _lib.stream_ptr(z.device))
@@ -516,7 +516,7 @@ def euclidean_gram_autograd(x1, x2, tval, tcoef):
 
 def _spd2_profile_raw(which, delta, r2, tcoef, rscale, bscale, bval, bw):
     lib = _lib.load()
-    out = torch.empty_like(delta)
+    out = torch.empty_like(delta) if which != 3 else torch.empty((3,) + tuple(delta.shape), dtype=delta.dtype, device=delta.device)
     with torch.cuda.device(delta.device):
         rc = lib.mgb_spd2_profile(which, _lib.ptr(delta), _lib.ptr(r2), delta.numel(), _lib.ptr(tcoef), _lib.ptr(rscale),
                                   _lib.ptr(bscale), tcoef.shape[0], _lib.ptr(bval), _lib.ptr(bw), bval.shape[0],

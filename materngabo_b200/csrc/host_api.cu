@@ -152,3 +152,50 @@ extern "C" int mgb_series_posterior_host(const mgb_series_desc* desc, const doub
   MGB_TRY(check_cuda(cudaStreamSynchronize(st.compute), "cudaStreamSynchronize"));
   return check_cuda(cudaStreamSynchronize(st.copy), "cudaStreamSynchronize");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Trust-region step of the quadrature kernels as one call (mgb.h): the existing entry points enqueued back to back.
+// ------------------------------------------------------------------------------------------------
+extern "C" int mgb_radial_acquisition_ei_step(int kind, int width, const double* xc, long long b, long long ldc,
+                                              const double* v, long long ldv, const double* xtrain, long long n,
+                                              long long ldt, const double* tval, const double* tcoef, int Pt, double s0,
+                                              double ds, int Ps, double outputscale, const double* rinv, long long ldr,
+                                              const double* rinv_t, long long ldrt, const double* alpha, double kss,
+                                              double mean_const, double best_f, int maximize, double* work,
+                                              long long work_doubles, double* ei, double* grad, double* hvp,
+                                              void* stream) {
+  if (kind < 0 || kind > 3) return mgb::fail(MGB_ERR_ARG, "radial_acquisition_ei_step: kind must be 0..3");
+  if (b < 0 || n < 1) return mgb::fail(MGB_ERR_ARG, "radial_acquisition_ei_step: bad sizes");
+  if (b == 0) return MGB_OK;
+  const long long bn = b * n;
+  if (!work || work_doubles < 4 * bn) return mgb::fail(MGB_ERR_ARG, "radial_acquisition_ei_step: scratch too small");
+  if (hvp && !v) return mgb::fail(MGB_ERR_ARG, "radial_acquisition_ei_step: hvp requested without directions");
+  const int geom = (kind == 3) ? 1 : 0;
+  const int w = (kind == 3) ? width : kind + 2;
+  double* z = work;
+  double* P[3] = {work + bn, work + 2 * bn, work + 3 * bn};
+  MGB_TRY(mgb_pair_scalars(geom, w, xc, b, ldc, xtrain, n, ldt, z, nullptr, stream));
+  MGB_TRY(mgb_radial_profile(kind, 3, z, bn, tval, tcoef, Pt, s0, ds, Ps, P[0], stream));    // all three orders, one launch
+  return mgb_radial_acquisition_ei(geom, w, xc, b, ldc, v, ldv, xtrain, n, ldt, P[0], P[1], hvp ? P[2] : nullptr, outputscale, rinv, ldr,
+                                   rinv_t, ldrt, alpha, kss, mean_const, best_f, maximize, ei, grad, hvp, stream);
+}
+
+extern "C" int mgb_spd2_acquisition_ei_step(int use_cholesky, const double* xc, long long b, long long ldc,
+                                            const double* xtrain, long long n, long long ldt, const double* tcoef,
+                                            const double* rscale, const double* bscale, int Pt, const double* bval,
+                                            const double* bw, int Pb, double outputscale, const double* rinv,
+                                            long long ldr, const double* rinv_t, long long ldrt, const double* alpha,
+                                            double kss, double mean_const, double best_f, int maximize, double* work,
+                                            long long work_doubles, double* ei, double* grad, void* stream) {
+  if (b < 0 || n < 1) return mgb::fail(MGB_ERR_ARG, "spd2_acquisition_ei_step: bad sizes");
+  if (b == 0) return MGB_OK;
+  const long long bn = b * n;
+  if (!work || work_doubles < 5 * bn) return mgb::fail(MGB_ERR_ARG, "spd2_acquisition_ei_step: scratch too small");
+  double* delta = work;
+  double* r2 = work + bn;
+  double* P[3] = {work + 2 * bn, work + 3 * bn, work + 4 * bn};
+  MGB_TRY(mgb_pair_scalars(2 + (use_cholesky ? 1 : 0), 3, xc, b, ldc, xtrain, n, ldt, delta, r2, stream));
+  MGB_TRY(mgb_spd2_profile(3, delta, r2, bn, tcoef, rscale, bscale, Pt, bval, bw, Pb, P[0], stream));   // value, d/dDelta, d/dr2
+  return mgb_spd2_acquisition_ei(use_cholesky, xc, b, ldc, xtrain, n, ldt, P[0], P[1], P[2], outputscale, rinv, ldr, rinv_t,
+                                 ldrt, alpha, kss, mean_const, best_f, maximize, ei, grad, stream);
+}

@@ -40,37 +40,6 @@ __device__ __forceinline__ double lorentz_dist(const double* a, const double* b,
   return 2.0 * asinh(0.5 * nrm);
 }
 
-// Branch-free exp for the quadrature inner phases (arguments <= 0 up to rounding; any |x| < 1e9 is handled).
-// Same scheme as the CUDA library's fast path - round x log2(e) with the 1.5 * 2^52 trick, two-constant reduction,
-// degree-11 polynomial (Chebyshev-node interpolant on |r| <= ln2 / 2, approximation error 1.5e-17) - but the scaling
-// by 2^n is done without the library's out-of-range branch: the exponent is added in two pieces (n1 >= -1000 into the
-// exponent field, the rest as a power-of-two factor that reaches 0 for results below the denormal range).  Without the
-// branch the compiler interleaves the independent exponentials of an unrolled loop, which is what hides the FP64
-// latency at 8-16 warps per SM.
-__device__ __forceinline__ double exp_bf(double x) {
-  double t = fma(x, 1.4426950408889634, 6755399441055744.0);
-  const int n = __double2loint(t);
-  t -= 6755399441055744.0;
-  double r = fma(t, -6.9314718055994529e-1, x);
-  r = fma(t, -2.3190468138462996e-17, r);
-  double q = 2.5110095611886237e-08;
-  q = fma(q, r, 2.7632715071632255e-07);
-  q = fma(q, r, 2.7557240761739257e-06);
-  q = fma(q, r, 2.4801485278370062e-05);
-  q = fma(q, r, 0.00019841269890193705);
-  q = fma(q, r, 0.0013888888952505406);
-  q = fma(q, r, 0.008333333333319546);
-  q = fma(q, r, 0.04166666666648738);
-  q = fma(q, r, 0.1666666666666668);
-  q = fma(q, r, 0.5000000000000019);
-  q = fma(q, r, 1.0);
-  q = fma(q, r, 1.0);
-  const int n1 = max(n, -1000);
-  const int n2 = max(n - n1, -1023);
-  const double v = __hiloint2double(__double2hiint(q) + (n1 << 20), __double2loint(q));
-  return v * __hiloint2double((n2 + 1023) << 20, 0);
-}
-
 struct HypParams {
   int dim, mode;
   int geom, width;   // geom 1: Euclidean rows of `width` doubles, heat(d, t) = exp(-|x1 - x2|^2 / (4 t))

@@ -236,6 +236,159 @@ __global__ void __launch_bounds__(PTHREADS) spd2_profile_kernel(SpdProfParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
+// All derivative orders in one launch (order = 3 / which = 3 of the C ABI): what the trust-region step asks for
+// (mgb_*_acquisition_ei_step).  Same tables and sums as the single-order kernels above; the exponentials - the
+// cost of these kernels - are shared by the three results.  out is order-major: out[o * count + e].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PTHREADS) hyp_profile_all_kernel(ProfParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* tab = sm + (size_t)warp * 7 * p.Ps;   // [s^2 | a0 | b0 b1 | c0 c1 c2] (H^2 only)
+  double i2t[PNQ], tc[PNQ];
+#pragma unroll
+  for (int q = 0; q < PNQ; ++q) {
+    const int a = lane + 32 * q;
+    i2t[q] = (a < p.Pt) ? 0.5 / p.tval[a] : 0.0;
+    tc[q] = (a < p.Pt) ? p.tcoef[a] : 0.0;
+  }
+  const long long wstride = (long long)gridDim.x * PWARPS;
+  for (long long e = (long long)blockIdx.x * PWARPS + warp; e < p.count; e += wstride) {
+    const double z = p.in[e];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    if (p.kind == PK_H2) {
+      const double chd = cosh(z), shd = sinh(z);
+      __syncwarp();
+      for (int k = lane; k < p.Ps; k += 32) {
+        const double b = p.s0 + k * p.ds;
+        const double s = b + z;
+        const double hs = sinh(0.5 * b);
+        const double cm1 = 2.0 * hs * hs, shb = sinh(b);
+        const double D = fma(chd, cm1, shd * shb);
+        const double N1 = fma(shd, cm1, chd * shb);
+        const double w = (k == 0 || k == p.Ps - 1) ? 0.5 * p.ds : p.ds;
+        const double F = rsqrt(D);
+        const double F1 = -0.5 * F * F * F * N1;
+        const double F2 = 0.75 * F * F * F * F * F * N1 * N1 - 0.5 * F;
+        tab[k] = s * s;
+        tab[p.Ps + k] = w * s * F;
+        tab[2 * p.Ps + k] = w * (F + s * F1);
+        tab[3 * p.Ps + k] = -w * s * s * F;
+        tab[4 * p.Ps + k] = w * (2.0 * F1 + s * F2);
+        tab[5 * p.Ps + k] = w * (-3.0 * s * F - 2.0 * s * s * F1);
+        tab[6 * p.Ps + k] = w * s * s * s * F;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < PNQ; ++q) {
+        if (lane + 32 * q < p.Pt) {
+          const double h = i2t[q], mh = -0.5 * h;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll 2
+          for (int k = 0; k < p.Ps; ++k) {
+            const double ex = exp_bf(mh * tab[k]);   // exp(-s^2 / 4t)
+            a0 = fma(ex, tab[p.Ps + k], a0);
+            a1 = fma(ex, fma(h, tab[3 * p.Ps + k], tab[2 * p.Ps + k]), a1);
+            a2 = fma(ex, fma(h, fma(h, tab[6 * p.Ps + k], tab[5 * p.Ps + k]), tab[4 * p.Ps + k]), a2);
+          }
+          s0 = fma(tc[q], a0, s0);
+          s1 = fma(tc[q], a1, s1);
+          s2 = fma(tc[q], a2, s2);
+        }
+      }
+    } else {
+      double qq = 1.0, q1 = 0.0, q2 = 0.0;
+      if (p.kind == PK_H3) z_over_sinh(z + 1e-8, qq, q1, q2);
+#pragma unroll
+      for (int q = 0; q < PNQ; ++q) {
+        if (lane + 32 * q < p.Pt) {
+          const double h = i2t[q];
+          double v0, v1, v2;
+          if (p.kind == PK_EUCLID) {
+            const double E = exp_bf(-0.5 * h * z);
+            v0 = E; v1 = -0.5 * h * E; v2 = 0.25 * h * h * E;
+          } else {
+            const double E = exp_bf(-0.5 * h * z * z);
+            const double E1 = -z * h, E2 = -h + z * z * h * h;
+            if (p.kind == PK_H1) {
+              v0 = E; v1 = E1 * E; v2 = E2 * E;
+            } else {
+              v0 = E * qq; v1 = E * (E1 * qq + q1); v2 = E * (E2 * qq + 2.0 * E1 * q1 + q2);
+            }
+          }
+          s0 = fma(tc[q], v0, s0);
+          s1 = fma(tc[q], v1, s1);
+          s2 = fma(tc[q], v2, s2);
+        }
+      }
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      p.out[e] = s0;
+      p.out[p.count + e] = s1;
+      p.out[2 * p.count + e] = s2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PTHREADS) spd2_profile_all_kernel(SpdProfParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* tab = sm + (size_t)warp * 4 * p.Pb;   // [c_b | base lin | d/dDelta constant part | d/dDelta bscale part]
+  double tc[PNQ], rs[PNQ], bs[PNQ];
+#pragma unroll
+  for (int q = 0; q < PNQ; ++q) {
+    const int a = lane + 32 * q;
+    tc[q] = (a < p.Pt) ? p.tcoef[a] : 0.0;
+    rs[q] = (a < p.Pt) ? p.rscale[a] : 0.0;
+    bs[q] = (a < p.Pt) ? p.bscale[a] : 0.0;
+  }
+  const long long wstride = (long long)gridDim.x * PWARPS;
+  for (long long e = (long long)blockIdx.x * PWARPS + warp; e < p.count; e += wstride) {
+    const double delta = p.delta[e], r2 = p.r2[e];
+    __syncwarp();
+    for (int k = lane; k < p.Pb; k += 32) {
+      const double b = p.bval[k];
+      const double sb = sinh(b), sbd = sinh(b + delta);
+      const double base = p.bw[k] * rsqrt(sb * sbd);
+      const double lin = 2.0 * b + delta;
+      tab[k] = b * (b + delta);
+      tab[p.Pb + k] = base * lin;
+      tab[2 * p.Pb + k] = base * (1.0 - 0.5 * lin * cosh(b + delta) / sbd);
+      tab[3 * p.Pb + k] = -base * lin * b;
+    }
+    __syncwarp();
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < PNQ; ++q) {
+      if (lane + 32 * q < p.Pt) {
+        double a0 = 0.0, a1 = 0.0;
+        const double mb = -bs[q];
+#pragma unroll 4
+        for (int k = 0; k < p.Pb; ++k) {
+          const double ex = exp_bf(mb * tab[k]);
+          a0 = fma(ex, tab[p.Pb + k], a0);
+          a1 = fma(ex, fma(bs[q], tab[3 * p.Pb + k], tab[2 * p.Pb + k]), a1);
+        }
+        const double er = tc[q] * exp_bf(-r2 * rs[q]);
+        s0 = fma(er, a0, s0);
+        s1 = fma(er, a1, s1);
+        s2 = fma(-rs[q] * er, a0, s2);
+      }
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      p.out[e] = s0;
+      p.out[p.count + e] = s1;
+      p.out[2 * p.count + e] = s2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Tabulated radial profile (opt-in, NOT the per-entry quadrature of the reference).
 //
 // For the hyperbolic and Euclidean kernels the Gram entry is a fixed one-dimensional function of the pair scalar,
@@ -348,10 +501,28 @@ static long long profile_blocks(long long count) {
 
 static int hyp_profile_launch(ProfParams p, cudaStream_t s) {
   if (p.kind < PK_H1 || p.kind > PK_EUCLID) return fail(MGB_ERR_ARG, "profile: kind must be 0 (H^1), 1 (H^2), 2 (H^3) or 3 (Euclidean)");
-  if (p.order < 0 || p.order > 2) return fail(MGB_ERR_ARG, "profile: derivative order must be 0, 1 or 2");
+  const bool all = (p.order == 3 && p.mode == PM_SUM);
+  if (!all && (p.order < 0 || p.order > 2)) return fail(MGB_ERR_ARG, "profile: derivative order must be 0, 1, 2 (or 3 = all three, forward only)");
   if (p.Pt < 1 || p.Pt > PMAXT) return fail(MGB_ERR_ARG, "profile: Pt out of range [1,128]");
   if (p.kind == PK_H2 && (p.Ps < 2 || p.Ps > PMAXP)) return fail(MGB_ERR_ARG, "profile: Ps out of range [2,1024]");
   if (p.count == 0) return MGB_OK;
+  if (all) {
+    const size_t smem_all = (p.kind == PK_H2) ? sizeof(double) * (size_t)PWARPS * 7 * p.Ps : 0;
+    if (smem_all > 200 * 1024) {                       // very long s grids: three single-order launches
+      for (int o = 0; o < 3; ++o) {
+        ProfParams q = p;
+        q.order = o;
+        q.out = p.out + o * p.count;
+        MGB_TRY(hyp_profile_launch(q, s));
+      }
+      return MGB_OK;
+    }
+    if (smem_all > 48 * 1024)
+      MGB_TRY(check_cuda(cudaFuncSetAttribute(hyp_profile_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem_all), "cudaFuncSetAttribute"));
+    hyp_profile_all_kernel<<<(unsigned)profile_blocks(p.count), PTHREADS, smem_all, s>>>(p);
+    return after_launch("hyp_profile_all_kernel");
+  }
   const size_t smem = (p.kind == PK_H2) ? sizeof(double) * (size_t)PWARPS * 4 * p.Ps : 0;
   if (smem > 48 * 1024)
     MGB_TRY(check_cuda(cudaFuncSetAttribute(hyp_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -361,10 +532,20 @@ static int hyp_profile_launch(ProfParams p, cudaStream_t s) {
 }
 
 static int spd_profile_launch(SpdProfParams p, cudaStream_t s) {
-  if (p.which < 0 || p.which > 2) return fail(MGB_ERR_ARG, "spd2 profile: which must be 0 (value), 1 (d/dDelta) or 2 (d/dr2)");
+  const bool all = (p.which == 3 && p.mode == PM_SUM);
+  if (!all && (p.which < 0 || p.which > 2))
+    return fail(MGB_ERR_ARG, "spd2 profile: which must be 0 (value), 1 (d/dDelta), 2 (d/dr2) (or 3 = all three, forward only)");
   if (p.Pt < 1 || p.Pt > PMAXT) return fail(MGB_ERR_ARG, "spd2 profile: Pt out of range [1,128]");
   if (p.Pb < 2 || p.Pb > PMAXP) return fail(MGB_ERR_ARG, "spd2 profile: Pb out of range [2,1024]");
   if (p.count == 0) return MGB_OK;
+  if (all) {
+    const size_t smem_all = sizeof(double) * (size_t)PWARPS * 4 * p.Pb;
+    if (smem_all > 48 * 1024)
+      MGB_TRY(check_cuda(cudaFuncSetAttribute(spd2_profile_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem_all), "cudaFuncSetAttribute"));
+    spd2_profile_all_kernel<<<(unsigned)profile_blocks(p.count), PTHREADS, smem_all, s>>>(p);
+    return after_launch("spd2_profile_all_kernel");
+  }
   const size_t smem = sizeof(double) * (size_t)PWARPS * 3 * p.Pb;
   if (smem > 48 * 1024)
     MGB_TRY(check_cuda(cudaFuncSetAttribute(spd2_profile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),

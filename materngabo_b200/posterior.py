@@ -308,6 +308,14 @@ class ExactGPPosterior:
             (hvp.reshape(shape) if hvp is not None else None)
 
 
+    def _scratch(self, doubles):
+        """Cached device scratch for the b x n intermediates of the fused acquisition step (grows, never shrinks)."""
+        buf = getattr(self, "_scratch_buf", None)
+        if buf is None or buf.numel() < doubles or buf.device != self.device:
+            buf = torch.empty(max(int(doubles), 1), dtype=F64, device=self.device)
+            self._scratch_buf = buf
+        return buf
+
     def _pair_scalars(self, kind, xf, xt):
         """Flat (b * n) pair scalars from one launch (mgb_pair_scalars)."""
         lib = _lib.load()
@@ -333,20 +341,20 @@ class ExactGPPosterior:
             raise RuntimeError("SPD(2) points are Mandel 3-vectors")
         chol = int(self.kernel.use_cholesky)
         tcoef, rscale, bscale, bv, bw = self._nodes
-        delta, r2 = self._pair_scalars(2 + chol, xf, xt)
-        prof = [_ops._spd2_profile_raw(wh, delta, r2, tcoef, rscale, bscale, bv, bw) for wh in range(3)]
         b, n = xf.shape[0], xt.shape[0]
         ei = torch.empty(b, dtype=F64, device=self.device)
         grad = torch.empty((b, 3), dtype=F64, device=self.device)
+        work = self._scratch(5 * b * n)
         lib = _lib.load()
         with torch.cuda.device(self.device):
-            rc = lib.mgb_spd2_acquisition_ei(chol, _lib.ptr(xf), b, xf.stride(0), _lib.ptr(xt), n, xt.stride(0),
-                                             _lib.ptr(prof[0]), _lib.ptr(prof[1]), _lib.ptr(prof[2]), self.outputscale,
-                                             _lib.ptr(self.rinv), self.rinv.stride(0), _lib.ptr(self.rinv_t),
-                                             self.rinv_t.stride(0), _lib.ptr(self.alpha), float(self.kss_value), self.mean_const,
-                                             float(best_f), 1 if maximize else 0, _lib.ptr(ei), _lib.ptr(grad),
-                                             _lib.stream_ptr(self.device))
-        _lib.check(rc, "mgb_spd2_acquisition_ei")
+            rc = lib.mgb_spd2_acquisition_ei_step(chol, _lib.ptr(xf), b, xf.stride(0), _lib.ptr(xt), n, xt.stride(0),
+                                                  _lib.ptr(tcoef), _lib.ptr(rscale), _lib.ptr(bscale), tcoef.numel(),
+                                                  _lib.ptr(bv), _lib.ptr(bw), bv.numel(), self.outputscale,
+                                                  _lib.ptr(self.rinv), self.rinv.stride(0), _lib.ptr(self.rinv_t),
+                                                  self.rinv_t.stride(0), _lib.ptr(self.alpha), float(self.kss_value),
+                                                  self.mean_const, float(best_f), 1 if maximize else 0, _lib.ptr(work),
+                                                  work.numel(), _lib.ptr(ei), _lib.ptr(grad), _lib.stream_ptr(self.device))
+        _lib.check(rc, "mgb_spd2_acquisition_ei_step")
         return ei.reshape(shape[:-1] if x.dim() == 2 else shape[:-2]), grad.reshape(shape), None
 
     def _radial_ei_value_grad_hvp(self, x, best_f, maximize, v):
@@ -366,38 +374,35 @@ class ExactGPPosterior:
         xt = self.train_prepared
         if len(nd) == 5:                                   # hyperbolic: (tval, tcoef, s0, ds, Ps)
             tval, tcoef, s0, ds, ps = nd
-            geom, kind = 0, int(self.kernel.dim) - 1
+            kind = int(self.kernel.dim) - 1
             if self.kernel.dim not in (1, 2, 3):
                 raise NotImplementedError
-            z, _ = self._pair_scalars(0, xf, xt)
         elif len(nd) == 2:                                 # Euclidean: (tval, tcoef)
             tval, tcoef = nd
             s0 = ds = 0.0
             ps = 0
-            geom, kind = 1, _ops.KIND_EUCLID
-            z, _ = self._pair_scalars(1, xf, xt)
+            kind = _ops.KIND_EUCLID
         else:
             raise NotImplementedError("fused acquisition derivatives: series, hyperbolic and Euclidean kernels")
         b, w = xf.shape
         if w > 4 or w != xt.shape[-1]:
             raise NotImplementedError("radial acquisition kernel: rows up to 4 wide")
         n = xt.shape[0]
-        zf = z.reshape(-1).contiguous()
-        prof = [_ops._radial_profile_raw(kind, o, zf, tval, tcoef, float(s0), float(ds), int(ps))
-                for o in range(3 if vf is not None else 2)]
         ei = torch.empty(b, dtype=F64, device=self.device)
         grad = torch.empty((b, w), dtype=F64, device=self.device)
         hvp = torch.empty((b, w), dtype=F64, device=self.device) if vf is not None else None
+        work = self._scratch(4 * b * n)
         lib = _lib.load()
         with torch.cuda.device(self.device):
-            rc = lib.mgb_radial_acquisition_ei(geom, w, _lib.ptr(xf), b, xf.stride(0), _lib.ptr(vf),
-                                               vf.stride(0) if vf is not None else 0, _lib.ptr(xt), n, xt.stride(0),
-                                               _lib.ptr(prof[0]), _lib.ptr(prof[1]), _lib.ptr(prof[2]) if vf is not None else None,
-                                               self.outputscale, _lib.ptr(self.rinv), self.rinv.stride(0), _lib.ptr(self.rinv_t),
-                                               self.rinv_t.stride(0), _lib.ptr(self.alpha), float(self.kss_value),
-                                               self.mean_const, float(best_f), 1 if maximize else 0, _lib.ptr(ei),
-                                               _lib.ptr(grad), _lib.ptr(hvp), _lib.stream_ptr(self.device))
-        _lib.check(rc, "mgb_radial_acquisition_ei")
+            rc = lib.mgb_radial_acquisition_ei_step(kind, w, _lib.ptr(xf), b, xf.stride(0), _lib.ptr(vf),
+                                                    vf.stride(0) if vf is not None else 0, _lib.ptr(xt), n, xt.stride(0),
+                                                    _lib.ptr(tval), _lib.ptr(tcoef), tval.numel(), float(s0), float(ds), int(ps),
+                                                    self.outputscale, _lib.ptr(self.rinv), self.rinv.stride(0),
+                                                    _lib.ptr(self.rinv_t), self.rinv_t.stride(0), _lib.ptr(self.alpha),
+                                                    float(self.kss_value), self.mean_const, float(best_f),
+                                                    1 if maximize else 0, _lib.ptr(work), work.numel(), _lib.ptr(ei),
+                                                    _lib.ptr(grad), _lib.ptr(hvp), _lib.stream_ptr(self.device))
+        _lib.check(rc, "mgb_radial_acquisition_ei_step")
         return ei.reshape(shape[:-1] if x.dim() == 2 else shape[:-2]), grad.reshape(shape), \
             (hvp.reshape(shape) if hvp is not None else None)
 

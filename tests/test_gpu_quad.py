@@ -569,3 +569,36 @@ def test_spd2_two_entry_lattice_kernel_matches_one_entry_kernel(m, n, nb, nt):
     assert torch.isfinite(two).all()
     assert rel_err(two, one) < 1e-13
     assert rel_err(two, direct) < 1e-12
+
+
+def test_all_orders_profile_launch_matches_single_order_launches():
+    """order = 3 / which = 3 of mgb_radial_profile / mgb_spd2_profile (one launch for the three quantities of the
+    trust-region step) against the three single-order launches."""
+    from materngabo_b200 import _ops
+    from materngabo_b200 import kernels_hyperbolic as kh
+    from materngabo_b200 import kernels_spd as ksp
+
+    torch.manual_seed(5)
+    z = (3.0 * torch.rand(257, dtype=torch.float64)).to(DEV)
+    z[0] = 2e-4
+    for dim in (1, 2, 3):
+        for cls in (kh.HyperbolicRiemannianMillsonIntegratedMaternKernel, kh.HyperbolicRiemannianMillsonGaussianKernel):
+            k = cls(dim=dim, nu=2.5) if "Matern" in cls.__name__ else cls(dim=dim)
+            k.lengthscale = 0.8
+            k = k.to(DEV)
+            with torch.no_grad():
+                tval, tcoef, s0, ds, ps = k.nodes(DEV)
+            allp = _ops._radial_profile_raw(dim - 1, 3, z, tval, tcoef, float(s0), float(ds), int(ps))
+            for o in range(3):
+                one = _ops._radial_profile_raw(dim - 1, o, z, tval, tcoef, float(s0), float(ds), int(ps))
+                assert rel_err(allp[o], one) < 1e-13, (dim, cls.__name__, o)
+    delta = (4.0 * torch.rand(130, dtype=torch.float64)).to(DEV)
+    r2 = (delta * delta * (0.5 + torch.rand(130, dtype=torch.float64).to(DEV)))
+    k = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5).to(DEV)
+    k.lengthscale = 1.1
+    with torch.no_grad():
+        tcoef, rscale, bscale, bv, bw = k.nodes(DEV)
+    allp = _ops._spd2_profile_raw(3, delta, r2, tcoef, rscale, bscale, bv, bw)
+    for wh in range(3):
+        one = _ops._spd2_profile_raw(wh, delta, r2, tcoef, rscale, bscale, bv, bw)
+        assert rel_err(allp[wh], one) < 1e-13, wh
