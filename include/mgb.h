@@ -292,6 +292,14 @@ int mgb_series_acquisition_ei(const mgb_series_desc* desc, const double* xc, lon
                               int maximize, double* ei, double* grad, double* hvp, double* mean, double* var,
                               void* stream);
 
+/* The same single-CTA evaluation for a Gram matrix ANY kernel produced (quadrature kernels, torus, products):
+ *   Kt = hyper[0] * K + hyper[1] * I,  out[0] = nll as above, out[1] = dnll/ds, out[2] = dnll/dnoise, out[3] = dnll/dmean,
+ *   G (n x n, symmetric) = dnll/dK = s/2 (Kt^-1 - alpha alpha^T): the upstream gradient for the kernel's own backward.
+ * Replaces the Cholesky / solve / log-determinant ops of gpytorch's ExactMarginalLogLikelihood and their autograd
+ * backward (~60 launches) by one launch; n <= mgb_series_mll_max_n(0, 0). */
+int mgb_dense_mll(const double* K, long long n, long long ldk, const double* y, const double* hyper, double* out,
+                  double* G, long long ldg, int* status, void* stream);
+
 /* Posterior fit for launch-bound training sizes with the same single-CTA kernel: rinv = L^-1 (n x n row-major, lower
  * triangle, zeros above), rinv_t = its transpose, alpha = Kt^-1 (y - mean), *nll as out[0] of mgb_series_mll.  Replaces
  * the Gram + Cholesky + solves of ExactGPPosterior.fit (gpytorch's prediction-strategy caches) at n <= mgb_series_mll_max_n. */

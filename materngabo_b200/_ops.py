@@ -214,6 +214,46 @@ def series_mll(spec: SeriesSpec, x, y, coef, hyper):
     return SeriesMLL.apply(spec, _c2d(x), y.contiguous().reshape(-1), coef.contiguous(), hyper.contiguous())
 
 
+class DenseMLL(torch.autograd.Function):
+    """Fused negative log marginal likelihood for a Gram matrix any kernel produced (csrc/mll.cu, dense mode):
+    (K, y, hyper = [outputscale, noise, mean]) -> (nll, status) with Kt = outputscale * K + noise I.  dnll/dK and
+    dnll/dhyper come out of the same launch; ``backward`` hands dnll/dK to the kernel's own backward."""
+
+    @staticmethod
+    def forward(ctx, k, y, hyper):
+        lib = _lib.load()
+        n = k.shape[0]
+        out = torch.empty(4, dtype=F64, device=k.device)
+        g = torch.empty((n, n), dtype=F64, device=k.device)
+        status = torch.zeros(1, dtype=torch.int32, device=k.device)
+        with torch.cuda.device(k.device):
+            rc = lib.mgb_dense_mll(_lib.ptr(k), n, k.stride(0), _lib.ptr(y), _lib.ptr(hyper), _lib.ptr(out), _lib.ptr(g), n,
+                                   _lib.ptr(status), _lib.stream_ptr(k.device))
+        _lib.check(rc, "mgb_dense_mll")
+        ctx.save_for_backward(out, g)
+        ctx.mark_non_differentiable(status)
+        return out[0].clone(), status
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad, _gs):
+        out, g = ctx.saved_tensors
+        gk = grad * g if ctx.needs_input_grad[0] else None
+        ghyper = grad * out[1:4] if ctx.needs_input_grad[2] else None
+        return gk, None, ghyper
+
+
+def dense_mll_max_n() -> int:
+    return int(_lib.load().mgb_series_mll_max_n(0, 0))
+
+
+def dense_mll(k, y, hyper):
+    _lib.require_cuda_f64(k, y, hyper)
+    if k.dim() != 2 or k.shape[0] != k.shape[1]:
+        raise RuntimeError("dense_mll: square Gram matrix expected")
+    return DenseMLL.apply(k.contiguous(), y.contiguous().reshape(-1), hyper.contiguous())
+
+
 def so3_quaternions(*mats, tol: float = 1e-13):
     """Flattened rotations (m x 9) -> unit quaternions (m x 4) for the pair_square form of the SO(3) kernels.
     Returns None when any input is not a rotation to ``tol`` (max |R R^T - I|, |det R - 1| measured on the device):

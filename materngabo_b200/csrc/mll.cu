@@ -33,6 +33,8 @@ struct MllParams {
   double scale, shift, lo, hi;
   // fit mode (rinv != nullptr): write L^-1 (row-major, lower), its transpose and alpha instead of the gradients
   double* rinv; double* rinv_t; double* alpha_out; long long ldo;
+  // dense mode (Kin != nullptr): Kt = s * Kin + noise I from a Gram matrix any kernel produced; writes G = dnll/dKin
+  const double* Kin; long long ldk; double* Gout; long long ldg;
 };
 
 __device__ __forceinline__ int low_idx(int i, int j) { return i * (i + 1) / 2 + j; }              // j <= i
@@ -90,9 +92,15 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_kernel(MllParams p)
   // ---- 1. Kt (lower triangle): warp per row, lanes over columns -------------------------------------
   for (int i = warp; i < n; i += MLL_WARPS) {
     for (int j = lane; j <= i; j += 32) {
-      bool inside;
-      const double u = pair_u(p, xs, i, j, inside);
-      A[low_idx(i, j)] = s * series_value(p, cfs, u) + ((i == j) ? noise : 0.0);
+      double kij;
+      if (p.Kin != nullptr) {
+        kij = p.Kin[(long long)i * p.ldk + j];
+      } else {
+        bool inside;
+        const double u = pair_u(p, xs, i, j, inside);
+        kij = series_value(p, cfs, u);
+      }
+      A[low_idx(i, j)] = s * kij + ((i == j) ? noise : 0.0);
     }
   }
   __syncthreads();
@@ -283,6 +291,31 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_kernel(MllParams p)
     }
   }
   __syncthreads();
+
+  if (p.Kin != nullptr) {
+    // ---- 6 (dense mode). G = dnll/dKin = s/2 (Kt^-1 - alpha alpha^T) as a full symmetric matrix; dnll/ds, dnll/dnoise
+    double gs = 0.0, gn = 0.0;
+    for (int i = warp; i < n; i += MLL_WARPS) {
+      for (int j = lane; j <= i; j += 32) {
+        const double w = A[low_idx(i, j)];
+        gs = fma(w, p.Kin[(long long)i * p.ldk + j], gs);
+        if (i == j) gn += w;
+        const double g = s * ((i == j) ? w : 0.5 * w);
+        p.Gout[(long long)i * p.ldg + j] = g;
+        p.Gout[(long long)j * p.ldg + i] = g;
+      }
+    }
+    gs = warp_sum(gs);
+    gn = warp_sum(gn);
+    if (lane == 0) {
+      atomicAdd(acc + 1, gs);
+      atomicAdd(acc + 2, gn);
+    }
+    __syncthreads();
+    for (int e = tid; e < 4; e += MLL_THREADS) p.out[e] = acc[e] + ((e == 0) ? 0.5 * n * 1.8378770664093453 : 0.0);
+    if (tid == 0 && p.status) *p.status = bad;
+    return;
+  }
 
   // ---- 6. gradient reductions over the pairs --------------------------------------------------------
   for (int c0 = 0; c0 < p.T; c0 += MLL_TCHUNK) {
@@ -477,4 +510,20 @@ extern "C" int mgb_series_mll(const mgb_series_desc* d, const double* x, long lo
                        "cudaFuncSetAttribute"));
   series_mll_kernel<<<1, MLL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
   return after_launch("series_mll_kernel");
+}
+
+extern "C" int mgb_dense_mll(const double* K, long long n, long long ldk, const double* y, const double* hyper, double* out,
+                             double* G, long long ldg, int* status, void* stream) {
+  if (!K || !y || !hyper || !out || !G) return fail(MGB_ERR_ARG, "dense_mll: null pointer");
+  if (n < 1 || ldk < n || ldg < n) return fail(MGB_ERR_ARG, "dense_mll: bad sizes");
+  if (n > mgb_series_mll_max_n(0, 0)) return fail(MGB_ERR_ARG, "dense_mll: n exceeds the single-CTA limit (mgb_series_mll_max_n(0, 0))");
+  MllParams p{};
+  p.n = (int)n; p.y = y; p.hyper = hyper; p.out = out; p.status = status;
+  p.Kin = K; p.ldk = ldk; p.Gout = G; p.ldg = ldg;
+  const size_t smem = sizeof(double) * (size_t)(n * (n + 1) + 5 * n + 4);
+  if (smem > 48 * 1024)
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute"));
+  series_mll_kernel<<<1, MLL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("series_mll_kernel (dense)");
 }

@@ -129,16 +129,37 @@ def _fused_mll(kernel, x, y, noise, mean_const, jitter):
     return nll / x.shape[0], info
 
 
+def _dense_mll(kernel, x, y, noise, mean_const, jitter):
+    """(loss, info) for any kernel: its own Gram kernel (with its own backward), then ONE launch for Cholesky, solves,
+    log-determinant and dnll/dK (csrc/mll.cu, dense mode).  None when n exceeds the single-CTA limit or for batches."""
+    from . import _ops
+
+    if x.dim() != 2 or x.shape[0] > _ops.dense_mll_max_n():
+        return None
+    base, scale = kernel, 1.0
+    if hasattr(kernel, "base_kernel") and hasattr(kernel, "outputscale") and getattr(kernel, "active_dims", None) is None:
+        base, scale = kernel.base_kernel, kernel.outputscale
+    k = base(x, x)
+    if not torch.is_tensor(k):          # gpytorch lazy tensors
+        k = k.to_dense() if hasattr(k, "to_dense") else k.evaluate()
+    hyper = torch.stack([_scalar(scale, x), _scalar(noise, x) + jitter, _scalar(mean_const, x)])
+    nll, info = _ops.dense_mll(k, y, hyper)
+    return nll / x.shape[0], info
+
+
 def exact_mll(kernel, x, y, noise, mean_const=0.0, jitter: float = 0.0, fused: bool = True):
     """Negative exact-GP marginal log likelihood divided by N (gpytorch's ExactMarginalLogLikelihood convention) for
     ``kernel`` (typically ScaleKernel(manifold kernel)) + Gaussian noise + constant mean: the quantity
     ``botorch.fit_gpytorch_model`` minimises (bo_sphere.py:262).  Capturable: no host synchronisation.
     Single-factor series kernels (sphere, SO(3), circle) with N up to ~160 go through ONE fused launch (csrc/mll.cu:
-    Gram, Cholesky, solves, log-determinant and all gradients in shared memory); everything else through the Gram
-    kernel + torch.linalg.  Returns (loss, info) - ``info`` is the Cholesky status flag (non-zero: K + noise I not
+    Gram, Cholesky, solves, log-determinant and all gradients in shared memory); every other kernel at those sizes
+    through its own Gram kernel + one launch of the same CTA kernel in dense mode (dnll/dK handed to the kernel's
+    backward); larger N through the Gram kernel + torch.linalg.  Returns (loss, info) - ``info`` is the Cholesky status flag (non-zero: K + noise I not
     positive definite)."""
     if fused and hasattr(kernel, "forward"):
         res = _fused_mll(kernel, x, y, noise, mean_const, jitter)
+        if res is None:
+            res = _dense_mll(kernel, x, y, noise, mean_const, jitter)
         if res is not None:
             return res
     n = x.shape[-2]

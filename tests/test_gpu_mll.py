@@ -46,7 +46,7 @@ def test_fused_mll_matches_unfused_and_oracle(n):
     gf = _grads(lf, params + [noise, mean])
     lu, _ = exact_mll(sk, xd, yd, noise, mean, fused=False)
     gu = _grads(lu, params + [noise, mean])
-    assert abs(float(lf) - float(lu)) < 1e-11 * max(1.0, abs(float(lu)))
+    assert abs(float(lf.detach()) - float(lu.detach())) < 1e-11 * max(1.0, abs(float(lu.detach())))
     for a, b in zip(gf, gu):
         assert _close(a, b, 1e-9)
     # oracle: torch autograd through the restated reference kernel on the CPU
@@ -58,7 +58,7 @@ def test_fused_mll_matches_unfused_and_oracle(n):
     k = sp(ro) * R.sphere_matern(x, x, 3, sp(rn), sp(rl))
     lo, _ = exact_mll(k, x, y, nz, mn)
     go = _grads(lo, [rl, rn, ro, nz, mn])
-    assert abs(float(lf) - float(lo)) < 1e-9 * max(1.0, abs(float(lo)))
+    assert abs(float(lf.detach()) - float(lo.detach())) < 1e-9 * max(1.0, abs(float(lo.detach())))
     for a, b in zip(gf, go):
         assert _close(a, b, 1e-7)
 
@@ -123,3 +123,64 @@ def test_device_coefficient_op_matches_the_torch_formulas():
     compare(lambda: kernels_sphere.SphereRiemannianGaussianKernel(dim=3), {"raw_lengthscale": -0.8})
     compare(lambda: kernels_so.SORiemannianMaternKernel(dim=3, nu=None), {"raw_lengthscale": -0.2, "raw_nu": 1.3})
     compare(lambda: kernels_so.SORiemannianGaussianKernel(dim=3), {"raw_lengthscale": 0.2})
+
+
+def _hyp_points(n, dim, gen):
+    z = 0.7 * torch.randn(n, dim, generator=gen)
+    return torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1)
+
+
+def _spd_points(n, gen):
+    a = torch.randn(n, 2, 2, generator=gen)
+    s = a @ a.transpose(-1, -2) + 0.5 * torch.eye(2)
+    return torch.stack([s[:, 0, 0], s[:, 1, 1], s[:, 0, 1] * 2 ** 0.5], -1)
+
+
+@pytest.mark.parametrize("which,n", [("torus", 60), ("h2", 100), ("h3", 37), ("spd2", 100), ("spd2", 1), ("h2", 164)])
+def test_dense_mll_matches_unfused_path_on_every_other_manifold(which, n):
+    """Kernels without the single-factor series form go through their own Gram kernel + ONE launch of the CTA kernel
+    in dense mode (mgb_dense_mll): value and gradients to every raw hyper-parameter, the noise and the mean against
+    the Gram kernel + torch.linalg + autograd path."""
+    from materngabo_b200 import kernels_hyperbolic as kh, kernels_spd as ksp, kernels_torus as kt
+    from materngabo_b200 import _ops
+    from materngabo_b200.gpytorch_compat import ScaleKernel
+    from materngabo_b200.graphs import exact_mll
+
+    gen = torch.Generator().manual_seed(n + len(which))
+    if which == "torus":
+        base, x = kt.TorusProductOfManifoldsRiemannianMaternKernel(dim=3, nu=2.5), torch.rand(n, 3, generator=gen) * 6.28
+    elif which == "h2":
+        base, x = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5), _hyp_points(n, 2, gen)
+    elif which == "h3":
+        base, x = kh.HyperbolicRiemannianMillsonGaussianKernel(dim=3), _hyp_points(n, 3, gen)
+    else:
+        base, x = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5), _spd_points(n, gen)
+    assert n <= _ops.dense_mll_max_n()
+    y = torch.sin(2 * x[:, 0]) + 0.1 * torch.randn(n, generator=gen)
+    sk = ScaleKernel(base).to(DEV)
+    with torch.no_grad():
+        sk.raw_outputscale.fill_(0.3)
+    params = [p for p in sk.parameters() if p.requires_grad]
+    # the reference's H^2 quadrature kernel is not positive definite at its default node counts: larger noise there
+    noise = torch.tensor(1.5 if which == "h2" else 0.05, device=DEV, requires_grad=True)
+    mean = torch.tensor(-0.1, device=DEV, requires_grad=True)
+    xd, yd = x.to(DEV), y.to(DEV)
+    lf, info = exact_mll(sk, xd, yd, noise, mean)
+    assert int(info) == 0
+    gf = torch.autograd.grad(lf, params + [noise, mean], allow_unused=True)
+    lu, _ = exact_mll(sk, xd, yd, noise, mean, fused=False)
+    gu = torch.autograd.grad(lu, params + [noise, mean], allow_unused=True)
+    assert abs(float(lf.detach()) - float(lu.detach())) < 1e-11 * max(1.0, abs(float(lu.detach())))
+    for a, b in zip(gf, gu):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert _close(a, b, 1e-8)
+
+
+def test_dense_mll_reports_a_non_positive_definite_matrix():
+    from materngabo_b200 import _ops
+
+    k = torch.tensor([[1.0, 2.0], [2.0, 1.0]], device=DEV)
+    hyper = torch.tensor([1.0, 0.0, 0.0], device=DEV)
+    _, info = _ops.dense_mll(k, torch.zeros(2, device=DEV), hyper)
+    assert int(info) != 0
