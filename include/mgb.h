@@ -292,6 +292,17 @@ int mgb_series_acquisition_ei(const mgb_series_desc* desc, const double* xc, lon
                               int maximize, double* ei, double* grad, double* hvp, double* mean, double* var,
                               void* stream);
 
+/* Chebyshev coefficients (in cos(phi)) of the circle kernels - the torus factors - and their Jacobian in one launch:
+ *   mode 0, integrated Matern (kernels_sphere.py:551-614): a_n = (2 - delta_n0) sum_a tw[a] t[a]^(nu - 1/2)
+ *           exp(-2 nu t[a] / kappa^2) exp(-4 pi^2 t[a] n^2), t = the reference's logspace grid (P nodes, built by the
+ *           caller from the detached lengthscale), tw = its trapezoid weights;
+ *   mode 1, heat (kernels_sphere.py:443-472, math_utils/jacobi_theta_functions.py:16-20): a_0 = 1, a_n = 2 q^(n^2),
+ *           q = exp(-2 pi^2 kappa^2) (t, tw, nu unused);
+ *   coef[n] = a_n / sum_m a_m, n < n_terms (<= 256; the reference sums 201),  jac[0][n] = d coef_n / d kappa,
+ *   jac[1][n] = d coef_n / d nu.  kappa, nu: device scalars. */
+int mgb_circle_coef(int mode, int n_terms, const double* t, const double* tw, int P, const double* kappa,
+                    const double* nu, double* coef, double* jac, void* stream);
+
 /* The same single-CTA evaluation for a Gram matrix ANY kernel produced (quadrature kernels, torus, products):
  *   Kt = hyper[0] * K + hyper[1] * I,  out[0] = nll as above, out[1] = dnll/ds, out[2] = dnll/dnoise, out[3] = dnll/dmean,
  *   G (n x n, symmetric) = dnll/dK = s/2 (Kt^-1 - alpha alpha^T): the upstream gradient for the kernel's own backward.

@@ -295,10 +295,60 @@ def _truncate(c: torch.Tensor) -> int:
     return max(keep, 2)
 
 
+class _CircleCoef(torch.autograd.Function):
+    """coef(kappa, nu) of a circle kernel (201 Chebyshev coefficients, normalised at phi = 0) and its Jacobian from ONE
+    device launch (mgb_circle_coef); the torch formulas below stay the definition and the CPU path."""
+
+    @staticmethod
+    def forward(ctx, mode, grid, kappa, nu):
+        lib = _lib.load()
+        terms = THETA3_TERMS + 1
+        coef = torch.empty(terms, dtype=F64, device=kappa.device)
+        jac = torch.empty((2, terms), dtype=F64, device=kappa.device)
+        kappa = kappa.detach().contiguous()
+        nu_c = nu.detach().contiguous() if nu is not None else None
+        with torch.cuda.device(kappa.device):
+            rc = lib.mgb_circle_coef(int(mode), terms, _lib.ptr(grid[0]) if grid is not None else None,
+                                     _lib.ptr(grid[1]) if grid is not None else None,
+                                     int(grid.shape[1]) if grid is not None else 0, _lib.ptr(kappa), _lib.ptr(nu_c),
+                                     _lib.ptr(coef), _lib.ptr(jac), _lib.stream_ptr(kappa.device))
+        _lib.check(rc, "mgb_circle_coef")
+        ctx.save_for_backward(jac)
+        ctx.has_nu = nu is not None
+        return coef
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gcoef):
+        (jac,) = ctx.saved_tensors
+        gv = jac @ gcoef.reshape(-1)
+        gk = gv[0].reshape(()) if ctx.needs_input_grad[2] else None
+        gn = gv[1].reshape(()) if (ctx.has_nu and ctx.needs_input_grad[3]) else None
+        return None, None, gk, gn
+
+
+def _circle_grid(shift: float, nb_points: int, device):
+    """(2, P) device tensor [t; trapezoid weights] of the reference's logspace grid for one lengthscale, built on the
+    host exactly as the torch path does and cached (the acquisition phase evaluates the kernel hundreds of times with
+    the hyper-parameters fixed)."""
+    key = ("circle_grid", float(shift), int(nb_points), str(device), str(torch.get_default_dtype()))
+    hit = _CONST_CACHE.get(key)
+    if hit is None:
+        t = torch.logspace(-3 + shift, 1 + shift, nb_points).to(F64)
+        if len(_CONST_CACHE) > 4096:
+            _CONST_CACHE.clear()
+        hit = (None, torch.stack([t, trapz_weights(t)]).to(device).contiguous())
+        _CONST_CACHE[key] = hit
+    return hit[1]
+
+
 def circle_gaussian_coef(lengthscale):
     """theta_3(phi/2, q) / theta_3(0, q), q = exp(-2 pi^2 kappa^2)  ->  Chebyshev series in cos(phi):
     c_0 = 1, c_n = 2 q^(n^2)."""
     ls = lengthscale.reshape(()).to(F64)
+    if ls.is_cuda:
+        c = _CircleCoef.apply(1, None, ls, None)
+        return c[:_truncate(c)]
     q = torch.exp(-2 * math.pi ** 2 * ls ** 2)
     n = torch.arange(0, THETA3_TERMS + 1, dtype=F64, device=ls.device)
     c = 2.0 * torch.pow(q, n ** 2)
@@ -311,6 +361,9 @@ def circle_integrated_matern_coef(lengthscale, nu, nb_points):
     """trapz_t t^(nu-1/2) exp(-2 nu t/kappa^2) theta_3(phi/2, exp(-4 pi^2 t)), normalised at phi = 0."""
     ls, nu = lengthscale.reshape(()).to(F64), nu.reshape(()).to(F64)
     shift = torch.log10(ls).item()
+    if ls.is_cuda:
+        c = _CircleCoef.apply(0, _circle_grid(shift, nb_points, ls.device), ls, nu)
+        return c[:_truncate(c)]
     t = _logspace(-3 + shift, 1 + shift, nb_points, ls.device)
     wt = trapz_weights(t)
     front = wt * torch.pow(t, nu + 0.5 - 1.0) * torch.exp(-2.0 * nu / ls ** 2 * t)          # (P,)

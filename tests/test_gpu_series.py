@@ -385,3 +385,25 @@ def test_float32_construction_regime_on_the_device():
     ref64 = R.sphere_matern(x1, x2, 2, nu, ls)
     assert rel_err(out, ref32) < TOL
     assert rel_err(ref32, ref64) > 1e-9                   # the two regimes really differ
+
+
+@pytest.mark.parametrize("ls,nu", [(0.5, 2.5), (0.15, 1.5), (1.3, 0.5)])
+def test_circle_coefficients_on_the_device_match_the_torch_formulas(ls, nu):
+    """mgb_circle_coef (one launch: 201 Chebyshev coefficients of a torus factor + Jacobian) against the torch
+    formulas of _weights.py on the CPU: values, truncation length and the gradients to the lengthscale and nu."""
+    from materngabo_b200 import _weights as w
+
+    for heat in (False, True):
+        outs = []
+        for dev in ("cpu", DEV):
+            l = torch.tensor(ls, dtype=torch.float64, device=dev, requires_grad=True)
+            n = torch.tensor(nu, dtype=torch.float64, device=dev, requires_grad=True)
+            c = w.circle_gaussian_coef(l) if heat else w.circle_integrated_matern_coef(l, n, 50)
+            probe = torch.cos(0.37 * torch.arange(c.numel(), dtype=torch.float64, device=dev))
+            g = torch.autograd.grad((c * probe).sum(), [l] if heat else [l, n])
+            outs.append((c.detach().cpu(), [x.cpu() for x in g]))
+        (c0, g0), (c1, g1) = outs
+        assert c0.numel() == c1.numel()
+        assert float((c0 - c1).abs().max()) < 1e-14 * float(c0.abs().max())
+        for a, b in zip(g0, g1):
+            assert abs(float(a) - float(b)) < 1e-11 * max(1.0, abs(float(a)))
