@@ -303,6 +303,14 @@ int mgb_series_acquisition_ei(const mgb_series_desc* desc, const double* xc, lon
 int mgb_circle_coef(int mode, int n_terms, const double* t, const double* tw, int P, const double* kappa,
                     const double* nu, double* coef, double* jac, void* stream);
 
+/* Normalised t-node weights of the integrated-Matern quadrature kernels (hyperbolic, SPD(2), Euclidean) and their
+ * Jacobian in one launch: w_a = tw[a] t[a]^(nu - power_offset) exp(-2 nu t[a] / kappa^2),
+ * tcoef[a] = w_a / sum_b w_b h0[b] (h0 = the inner integral at zero distance on the same grid, NULL = 1;
+ * kernels_hyperbolic.py:367-383, kernels_spd.py:262-289, kernels_euclidean.py:186-207),
+ * jac[0][a] = d tcoef_a / d kappa, jac[1][a] = d tcoef_a / d nu.  P <= 1024; kappa, nu: device scalars. */
+int mgb_matern_t_weights(const double* t, const double* tw, const double* h0, int P, double power_offset,
+                         const double* kappa, const double* nu, double* tcoef, double* jac, void* stream);
+
 /* The same single-CTA evaluation for a Gram matrix ANY kernel produced (quadrature kernels, torus, products):
  *   Kt = hyper[0] * K + hyper[1] * I,  out[0] = nll as above, out[1] = dnll/ds, out[2] = dnll/dnoise, out[3] = dnll/dmean,
  *   G (n x n, symmetric) = dnll/dK = s/2 (Kt^-1 - alpha alpha^T): the upstream gradient for the kernel's own backward.

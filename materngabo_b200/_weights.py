@@ -442,6 +442,59 @@ def so3_gaussian_coef(lengthscale, summands):
 # --------------------------------------------------------------------------------------------------
 # quadrature kernels: node grids (detached, as the reference's .item()) and differentiable node weights
 # --------------------------------------------------------------------------------------------------
+class _MaternTWeights(torch.autograd.Function):
+    """Normalised t-node weights tcoef(kappa, nu) on a fixed grid and their Jacobian from ONE device launch
+    (mgb_matern_t_weights); the torch formulas of ``matern_t_nodes`` + the kernels' ``nodes`` stay the definition."""
+
+    @staticmethod
+    def forward(ctx, grid, has_h0, power_offset, kappa, nu):
+        lib = _lib.load()
+        p = grid.shape[1]
+        tcoef = torch.empty(p, dtype=F64, device=kappa.device)
+        jac = torch.empty((2, p), dtype=F64, device=kappa.device)
+        kappa, nu = kappa.detach().contiguous(), nu.detach().contiguous()
+        with torch.cuda.device(kappa.device):
+            rc = lib.mgb_matern_t_weights(_lib.ptr(grid[0]), _lib.ptr(grid[1]), _lib.ptr(grid[2]) if has_h0 else None, int(p),
+                                          float(power_offset), _lib.ptr(kappa), _lib.ptr(nu), _lib.ptr(tcoef), _lib.ptr(jac),
+                                          _lib.stream_ptr(kappa.device))
+        _lib.check(rc, "mgb_matern_t_weights")
+        ctx.save_for_backward(jac)
+        return tcoef
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (jac,) = ctx.saved_tensors
+        gv = jac @ g.reshape(-1)
+        return None, None, None, (gv[0].reshape(()) if ctx.needs_input_grad[3] else None), \
+            (gv[1].reshape(()) if ctx.needs_input_grad[4] else None)
+
+
+def matern_t_coef(lengthscale, nu, lo_exp, hi_exp, nb_points, power_offset, h0_key, h0_fn):
+    """Device path of ``matern_t_nodes`` + normalisation: (t, tcoef, shift) with tcoef = w / sum(w h0).
+    ``h0_fn(t)`` evaluates the inner integral at zero distance on the grid (None: 1); the grid, its trapezoid weights
+    and h0 depend on the lengthscale only through the detached shift and are cached per (shift, ...)."""
+    ls, nu = lengthscale.reshape(()).to(F64), nu.reshape(()).to(F64)
+    shift = torch.log10(ls).item()
+    key = ("t_grid", float(shift), float(lo_exp), float(hi_exp), int(nb_points), h0_key, str(ls.device),
+           str(torch.get_default_dtype()))
+    hit = _CONST_CACHE.get(key)
+    if hit is None:
+        if len(_CONST_CACHE) > 4096:
+            _CONST_CACHE.clear()
+        t = torch.logspace(lo_exp + shift, hi_exp + shift, nb_points).to(F64)
+        tw = trapz_weights(t)
+        t_dev = t.to(ls.device)
+        with torch.no_grad():
+            h0 = h0_fn(t_dev).reshape(-1).to(F64) if h0_fn is not None else torch.ones_like(t_dev)
+        grid = torch.stack([t_dev, tw.to(ls.device), h0]).contiguous()
+        hit = (None, grid)
+        _CONST_CACHE[key] = hit
+    grid = hit[1]
+    tcoef = _MaternTWeights.apply(grid, h0_fn is not None, power_offset, ls, nu)
+    return grid[0], tcoef, shift
+
+
 def matern_t_nodes(lengthscale, nu, lo_exp, hi_exp, nb_points, power_offset=1.0, return_shift=False):
     """t grid logspace(lo+log10 kappa, hi+log10 kappa, P) and the weights
     trapz_w * t^(nu - power_offset) * exp(-2 nu t / kappa^2)

@@ -520,6 +520,49 @@ __global__ void __launch_bounds__(CC_THREADS) circle_coef_kernel(CircleCoefParam
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Normalised t-node weights of the integrated-Matern quadrature kernels and their Jacobian in ONE launch:
+//   w_a = tw_a t_a^(nu - power_offset) exp(-2 nu t_a / kappa^2),  tcoef_a = w_a / sum_b w_b h0_b
+// (kernels_hyperbolic.py:367-383, kernels_spd.py:262-289, kernels_euclidean.py:186-207; h0 = the inner integral at
+// zero distance on the same grid, NULL = 1).  The grid t is the caller's (detached, as the reference's .item()).
+// ------------------------------------------------------------------------------------------------
+struct TWeightParams {
+  int P;
+  const double* t; const double* tw; const double* h0;
+  double power_offset;
+  const double* kappa; const double* nu;
+  double* tcoef; double* jac;
+};
+
+__global__ void __launch_bounds__(CC_THREADS) matern_t_weights_kernel(TWeightParams p) {
+  __shared__ double w[CC_MAXP], wk[CC_MAXP], wn[CC_MAXP];
+  __shared__ double red[3];
+  const int tid = threadIdx.x;
+  const double kappa = *p.kappa, nu = *p.nu;
+  for (int e = tid; e < p.P; e += CC_THREADS) {
+    const double t = p.t[e], lt = log(t);
+    const double v = p.tw[e] * exp((nu - p.power_offset) * lt - 2.0 * nu * t / (kappa * kappa));
+    w[e] = v;
+    wk[e] = v * (4.0 * nu * t / (kappa * kappa * kappa));
+    wn[e] = v * (lt - 2.0 * t / (kappa * kappa));
+  }
+  __syncthreads();
+  if (tid < 3) {   // fixed summation order
+    const double* src = (tid == 0) ? w : ((tid == 1) ? wk : wn);
+    double acc = 0.0;
+    for (int e = 0; e < p.P; ++e) acc = fma(src[e], (p.h0 != nullptr) ? p.h0[e] : 1.0, acc);
+    red[tid] = acc;
+  }
+  __syncthreads();
+  const double S = red[0];
+  for (int e = tid; e < p.P; e += CC_THREADS) {
+    const double c = w[e] / S;
+    p.tcoef[e] = c;
+    p.jac[e] = (wk[e] - c * red[1]) / S;
+    p.jac[p.P + e] = (wn[e] - c * red[2]) / S;
+  }
+}
+
 }  // namespace mgb
 
 using namespace mgb;
@@ -611,4 +654,13 @@ extern "C" int mgb_circle_coef(int mode, int n_terms, const double* t, const dou
   CircleCoefParams p{mode, n_terms, P, t, tw, kappa, nu, coef, jac};
   circle_coef_kernel<<<1, CC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return after_launch("circle_coef_kernel");
+}
+
+extern "C" int mgb_matern_t_weights(const double* t, const double* tw, const double* h0, int P, double power_offset,
+                                    const double* kappa, const double* nu, double* tcoef, double* jac, void* stream) {
+  if (!t || !tw || !kappa || !nu || !tcoef || !jac) return fail(MGB_ERR_ARG, "matern_t_weights: null pointer");
+  if (P < 1 || P > CC_MAXP) return fail(MGB_ERR_ARG, "matern_t_weights: P out of range [1,1024]");
+  TWeightParams p{P, t, tw, h0, power_offset, kappa, nu, tcoef, jac};
+  matern_t_weights_kernel<<<1, CC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("matern_t_weights_kernel");
 }

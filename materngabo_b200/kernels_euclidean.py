@@ -49,8 +49,11 @@ class EuclideanIntegratedMaternKernel(_NuMixin, Kernel):
 
     def nodes(self, device):
         """t grid logspace(-3 + log10 l, 3 + log10 l, P) and the normalised trapezoid weights (:186-207)."""
-        t, w = _weights.matern_t_nodes(self.lengthscale.to(device), self.nu.to(device), -3.0, 3.0,
-                                       self.nb_points_integral, power_offset=1.0)
+        ls = self.lengthscale.to(device)
+        if ls.is_cuda:
+            t, tcoef, _ = _weights.matern_t_coef(ls, self.nu.to(device), -3.0, 3.0, self.nb_points_integral, 1.0, "euclid", None)
+            return t, tcoef
+        t, w = _weights.matern_t_nodes(ls, self.nu.to(device), -3.0, 3.0, self.nb_points_integral, power_offset=1.0)
         return t, w / w.sum()
 
     def forward(self, x1, x2, diag=False, **params):

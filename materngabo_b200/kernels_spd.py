@@ -28,8 +28,14 @@ F64 = torch.float64
 
 
 def _b_nodes(nb, device):
-    b = _weights._logspace(-5.0, 1.0, nb, device)      # kernels_spd.py:118,265
-    return b, _weights.trapz_weights(b)
+    """b grid logspace(-5, 1, nb) (kernels_spd.py:118,265) and its trapezoid weights, cached per device."""
+    key = ("spd_b_nodes", int(nb), str(device), str(torch.get_default_dtype()))
+    hit = _weights._CONST_CACHE.get(key)
+    if hit is None:
+        b = _weights._logspace(-5.0, 1.0, nb, device)
+        hit = (None, (b, _weights.trapz_weights(b)))
+        _weights._CONST_CACHE[key] = hit
+    return hit[1]
 
 
 class SpdRiemannianGaussianKernel(Kernel):
@@ -80,9 +86,22 @@ class SpdRiemannianIntegratedMaternKernel(_NuMixin, Kernel):
 
     def nodes(self, device, with_lattice=False):
         ls = self.lengthscale.to(device)
+        b, bw = _b_nodes(self.nb_points_integral_b, device)
+        if ls.is_cuda:      # one launch for the normalised weights + Jacobian; grid and zero-distance integral cached
+            inner = lambda t: (bw * 2.0 * b / torch.sinh(b) * torch.exp(-(b * b).unsqueeze(0) / (2 * t).unsqueeze(-1))).sum(-1)  # noqa: E731
+            t, tcoef, shift = _weights.matern_t_coef(ls, self.nu.to(device), -2.0, 1.5, self.nb_points_integral_t, 1.0,
+                                                     ("spd2", self.nb_points_integral_b), inner)
+            key = ("spd2_scales", id(t))
+            hit = _weights._CONST_CACHE.get(key)
+            if hit is None or hit[0] is not t:
+                hit = (t, (1.0 / (4 * t), 1.0 / (2 * t)))
+                _weights._CONST_CACHE[key] = hit
+            rscale, bscale = hit[1]
+            if with_lattice:
+                return tcoef, rscale, bscale, b, bw, self._lattice(shift)
+            return tcoef, rscale, bscale, b, bw
         t, w, shift = _weights.matern_t_nodes(ls, self.nu.to(device), -2.0, 1.5, self.nb_points_integral_t,
                                               power_offset=1.0, return_shift=True)
-        b, bw = _b_nodes(self.nb_points_integral_b, device)
         rscale, bscale = 1.0 / (4 * t), 1.0 / (2 * t)
         inner0 = (bw * 2.0 * b / torch.sinh(b) * torch.exp(-(b * b).unsqueeze(0) * bscale.unsqueeze(-1))).sum(-1)
         tcoef = w / (w * inner0).sum()                   # kernels_spd.py:277-289
