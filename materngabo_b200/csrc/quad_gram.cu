@@ -916,6 +916,147 @@ __global__ void __launch_bounds__(L2THREADS, 1) spd2_lattice2_kernel(SpdLatticeP
   }
 }
 
+// The same two-entry scheme with PAIRS of warps: spd2_lattice2_kernel is latency-bound at 8 warps per SM (the per-warp
+// lattice tables fill the shared memory; ncu: issue slots 50 %, FP64 pipe 48 %, top stall "wait").  Here two warps
+// share one pair of lattice tables: each computes half of the lattice exponentials and half of the inner weights,
+// then owns one t node per lane (warp 0 of the pair a < 32, warp 1 a >= 32) in the node loop.  Same tables per SM,
+// twice the warps; the two warps meet at a 64-thread named barrier twice per entry pair.
+constexpr int LPTHREADS = 512;
+constexpr int LPPAIRS = LPTHREADS / 64;
+
+__device__ __forceinline__ void pair_barrier(int pair) {
+  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+}
+
+__global__ void __launch_bounds__(LPTHREADS, 1) spd2_lattice2p_kernel(SpdLatticeParams p) {
+  extern __shared__ __align__(16) double sm[];
+  // layout: E [Pb][64] | G [nk (+1)] | bv, bw, shb, chb [Pb each (+pad)] | per pair: X01 [nk] double2 | qb01 [Pb] double2 | part [2]
+  double* Es = sm;
+  double* Gs = sm + (size_t)p.Pb * 64;
+  const int nkp = p.nk + (p.nk & 1), Pbp = p.Pb + (p.Pb & 1);
+  double* bv = Gs + nkp;
+  double* bw = bv + Pbp;
+  double* shb = bw + Pbp;
+  double* chb = shb + Pbp;
+  double2* wbase = reinterpret_cast<double2*>(chb + Pbp);
+  for (int e = threadIdx.x; e < p.Pb * 64; e += blockDim.x) {
+    const int b = e >> 6, a = e & 63;
+    const double bb = p.bval[b];
+    Es[e] = (a < p.Pt) ? exp(-bb * bb * p.bscale[a]) : 0.0;
+  }
+  for (int k = threadIdx.x; k < p.nk; k += blockDim.x) Gs[k] = -p.g_min * exp(k * p.log_tau);
+  for (int e = threadIdx.x; e < p.Pb; e += blockDim.x) {
+    const double b = p.bval[e];
+    bv[e] = b;
+    bw[e] = p.bw[e];
+    shb[e] = sinh(b);
+    chb[e] = cosh(b);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pair = warp >> 1, half = warp & 1;
+  double2* X = wbase + (size_t)pair * (p.nk + p.Pb + 1);
+  double2* qb = X + p.nk;
+  double* part = reinterpret_cast<double*>(qb + p.Pb);
+  const int a = lane + 32 * half;
+  const double tc = (a < p.Pt) ? p.tcoef[a] : 0.0;
+  const double rs = (a < p.Pt) ? p.rscale[a] : 0.0;
+  const int koff = (a < p.Pt) ? p.sa * (p.Pt - 1 - a) : 0;
+  const long long total = p.m * p.n;
+  const long long wstride = (long long)gridDim.x * LPPAIRS;
+  for (long long ebase = (long long)blockIdx.x * LPPAIRS + pair; ebase < total; ebase += 32 * wstride) {
+    // pair geometry of the next 32 entries, one per lane (both warps of the pair hold a copy)
+    double g_delta = 0.0, g_r2 = 0.0, g_sh = 0.0, g_ch = 1.0;
+    long long g_off = -1;
+    {
+      const long long el = ebase + lane * wstride;
+      if (el < total) {
+        const long long il = el / p.n, jl = el - il * p.n;
+        double H1, H2;
+        spd2_logsv(p.x1 + il * p.ld1, p.x2 + jl * p.ld2, p.use_chol, H1, H2);
+        g_delta = H1 - H2;
+        g_r2 = H1 * H1 + H2 * H2;
+        g_sh = sinh(g_delta);
+        g_ch = cosh(g_delta);
+        g_off = il * p.ldk + jl;
+      }
+    }
+#pragma unroll 1
+    for (int sub = 0; sub < 16; ++sub) {
+      if (ebase + (long long)(2 * sub) * wstride >= total) break;      // uniform over the pair: same ebase, same total
+      const double d0 = __shfl_sync(0xffffffffu, g_delta, 2 * sub), d1 = __shfl_sync(0xffffffffu, g_delta, 2 * sub + 1);
+      {
+        // this warp's half of the lattice: k = lane + 32 (2 i + half)
+        int k = lane + 32 * half;
+        for (; k + 192 < p.nk; k += 256) {
+          const double ga = Gs[k], gb = Gs[k + 64], gc = Gs[k + 128], gd = Gs[k + 192];
+          double2 xa, xb, xc, xd;
+          xa.x = exp_bf(d0 * ga); xa.y = exp_bf(d1 * ga);
+          xb.x = exp_bf(d0 * gb); xb.y = exp_bf(d1 * gb);
+          xc.x = exp_bf(d0 * gc); xc.y = exp_bf(d1 * gc);
+          xd.x = exp_bf(d0 * gd); xd.y = exp_bf(d1 * gd);
+          X[k] = xa;
+          X[k + 64] = xb;
+          X[k + 128] = xc;
+          X[k + 192] = xd;
+        }
+        for (; k < p.nk; k += 64) {
+          const double ga = Gs[k];
+          double2 xa;
+          xa.x = exp_bf(d0 * ga); xa.y = exp_bf(d1 * ga);
+          X[k] = xa;
+        }
+      }
+      {
+        const double sh0 = __shfl_sync(0xffffffffu, g_sh, 2 * sub), sh1 = __shfl_sync(0xffffffffu, g_sh, 2 * sub + 1);
+        const double ch0 = __shfl_sync(0xffffffffu, g_ch, 2 * sub), ch1 = __shfl_sync(0xffffffffu, g_ch, 2 * sub + 1);
+        for (int b = lane + 32 * half; b < p.Pb; b += 64) {
+          const double bb = bv[b], sb_ = shb[b], cb_ = chb[b], wb = bw[b];
+          double2 qv;
+          qv.x = wb * (2.0 * bb + d0) * rsqrt(sb_ * fma(sb_, ch0, cb_ * sh0));
+          qv.y = wb * (2.0 * bb + d1) * rsqrt(sb_ * fma(sb_, ch1, cb_ * sh1));
+          qb[b] = qv;
+        }
+      }
+      pair_barrier(pair);      // (B) tables complete
+      double acc0 = 0.0, acc1 = 0.0;
+      {
+        const double* Ep = Es + a;
+        const double2* Xp = X + koff;
+        const int sb = p.sb;
+#pragma unroll 4
+        for (int b = 0; b < p.Pb; ++b, Ep += 64, Xp += sb) {
+          const double2 qv = qb[b];
+          const double ev = *Ep;
+          const double2 xv = *Xp;
+          acc0 = fma(qv.x * ev, xv.x, acc0);
+          acc1 = fma(qv.y * ev, xv.y, acc1);
+        }
+      }
+      const double r20 = __shfl_sync(0xffffffffu, g_r2, 2 * sub), r21 = __shfl_sync(0xffffffffu, g_r2, 2 * sub + 1);
+      const double s0 = tc * exp_bf(-r20 * rs) * acc0, s1 = tc * exp_bf(-r21 * rs) * acc1;
+      // split butterfly: lanes 0-15 end up with entry 0, lanes 16-31 with entry 1
+      const bool hi = lane & 16;
+      double v = (hi ? s1 : s0) + __shfl_xor_sync(0xffffffffu, hi ? s0 : s1, 16);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      const long long off0 = __shfl_sync(0xffffffffu, g_off, 2 * sub), off1 = __shfl_sync(0xffffffffu, g_off, 2 * sub + 1);
+      if (half == 1 && (lane & 15) == 0) part[lane >> 4] = v;
+      pair_barrier(pair);      // (A) node loop finished on both warps (tables may be rewritten), partial sums visible
+      if (half == 0 && (lane & 15) == 0) {
+        const long long off = hi ? off1 : off0;
+        if (off >= 0) st_stream(p.K + off, v + part[lane >> 4]);
+      }
+    }
+  }
+}
+
+static size_t spd2_lattice2p_smem(int Pb, int nk) {
+  const int nkp = nk + (nk & 1), Pbp = Pb + (Pb & 1);
+  return sizeof(double) * ((size_t)Pb * 64 + nkp + 4 * (size_t)Pbp + (size_t)LPPAIRS * 2 * (nk + Pb + 1));
+}
+
 static size_t spd2_lattice2_smem(int Pb, int nk) {
   const int nkp = nk + (nk & 1), Pbp = Pb + (Pb & 1);
   return sizeof(double) * ((size_t)Pb * 64 + nkp + 4 * (size_t)Pbp + (size_t)L2WARPS * 2 * (nk + Pb));
@@ -1164,7 +1305,17 @@ extern "C" int mgb_spd2_gram_fwd_lattice(int use_cholesky, const double* x1, lon
   p.K = K; p.ldk = ldk;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   {
-    const char* force = getenv("MGB_SPD2_PATH");       // "lattice1": the one-entry-per-iteration kernel (A/B measurements, tests)
+    const char* force = getenv("MGB_SPD2_PATH");       // "lattice1" / "lattice2" / "pairs": pick a kernel (A/B measurements, tests)
+    const size_t smem2p = spd2_lattice2p_smem(Pb, p.nk);
+    if (smem2p <= 227 * 1024 && (force == nullptr || strcmp(force, "pairs") == 0)) {
+      MGB_TRY(check_cuda(cudaFuncSetAttribute(spd2_lattice2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2p),
+                         "cudaFuncSetAttribute"));
+      const long long totalp = m * n;
+      long long blocksp = (totalp + 2 * LPPAIRS - 1) / (2 * LPPAIRS);
+      if (blocksp > (long long)sm_count()) blocksp = sm_count();
+      spd2_lattice2p_kernel<<<(unsigned)blocksp, LPTHREADS, smem2p, s>>>(p);
+      return after_launch("spd2_lattice2p_kernel");
+    }
     const size_t smem2 = spd2_lattice2_smem(Pb, p.nk);
     if (smem2 <= 227 * 1024 && !(force != nullptr && strcmp(force, "lattice1") == 0)) {
       MGB_TRY(check_cuda(cudaFuncSetAttribute(spd2_lattice2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2),

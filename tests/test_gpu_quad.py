@@ -540,8 +540,9 @@ def test_h2_four_entry_forward_kernel_matches_generic_kernel_and_oracle(m, n, P)
 
 @pytest.mark.parametrize("m,n,nb,nt", [(67, 71, 64, 64), (33, 1, 50, 50), (130, 129, 40, 40), (1, 3, 64, 64), (200, 77, 64, 64)])
 def test_spd2_two_entry_lattice_kernel_matches_one_entry_kernel(m, n, nb, nt):
-    """spd2_lattice2_kernel (two entries per warp iteration, the default) against spd2_lattice_kernel
-    (MGB_SPD2_PATH=lattice1): same lattice, same nodes; odd entry counts leave the second slot of the last pair empty."""
+    """spd2_lattice2p_kernel (two entries per iteration of a warp pair, the default) against spd2_lattice2_kernel (one
+    warp per entry pair, MGB_SPD2_PATH=lattice2) and spd2_lattice_kernel (MGB_SPD2_PATH=lattice1): same lattice, same
+    nodes; odd entry counts leave the second slot of the last pair empty."""
     import os
     from materngabo_b200 import _ops
     from materngabo_b200 import kernels_spd as ksp
@@ -557,17 +558,20 @@ def test_spd2_two_entry_lattice_kernel_matches_one_entry_kernel(m, n, nb, nt):
         _ops.SPD2_LATTICE_MIN_ENTRIES = 1
         with torch.no_grad():
             two = k.forward(v[:m], v[:n])
-            os.environ["MGB_SPD2_PATH"] = "lattice1"
-            try:
-                one = k.forward(v[:m], v[:n])
-            finally:
-                del os.environ["MGB_SPD2_PATH"]
+            others = []
+            for path in ("lattice1", "lattice2"):
+                os.environ["MGB_SPD2_PATH"] = path
+                try:
+                    others.append(k.forward(v[:m], v[:n]))
+                finally:
+                    del os.environ["MGB_SPD2_PATH"]
+            one, two_single_warp = others
             _ops.SPD2_LATTICE_MIN_ENTRIES = 1 << 60
             direct = k.forward(v[:m], v[:n])
     finally:
         _ops.SPD2_LATTICE_MIN_ENTRIES = saved
     assert torch.isfinite(two).all()
-    assert rel_err(two, one) < 1e-13
+    assert rel_err(two, one) < 1e-13 and rel_err(two, two_single_warp) < 1e-13
     assert rel_err(two, direct) < 1e-12
 
 
