@@ -326,6 +326,10 @@ int mgb_series_fit(const mgb_series_desc* desc, const double* x, long long n, lo
                    const double* coef, const double* hyper, double* rinv, double* rinv_t, long long ldo, double* alpha,
                    double* nll, int* status, void* stream);
 
+/* mgb_series_fit for a Gram matrix any kernel produced: Kt = hyper[0] * K + hyper[1] * I (n <= mgb_series_mll_max_n(0, 0)). */
+int mgb_dense_fit(const double* K, long long n, long long ldk, const double* y, const double* hyper, double* rinv,
+                  double* rinv_t, long long ldo, double* alpha, double* nll, int* status, void* stream);
+
 /* Pair scalars of the quadrature kernels for a candidate block (m rows) against the training set (n rows), row-major
  * m x n: kind 0 Lorentz distance (rows `width` = dim + 1 wide), 1 squared Euclidean distance, 2 / 3 SPD(2) (Delta -> out0,
  * r2 -> out1) from the matrices / from their Cholesky factors (the geometry of mgb_hyperbolic_gram_fwd,

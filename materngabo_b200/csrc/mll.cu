@@ -664,3 +664,20 @@ extern "C" int mgb_matern_t_weights(const double* t, const double* tw, const dou
   matern_t_weights_kernel<<<1, CC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return after_launch("matern_t_weights_kernel");
 }
+
+extern "C" int mgb_dense_fit(const double* K, long long n, long long ldk, const double* y, const double* hyper, double* rinv,
+                             double* rinv_t, long long ldo, double* alpha, double* nll, int* status, void* stream) {
+  if (!K || !y || !hyper || !rinv || !rinv_t || !alpha || !nll) return fail(MGB_ERR_ARG, "dense_fit: null pointer");
+  if (n < 1 || ldk < n || ldo < n) return fail(MGB_ERR_ARG, "dense_fit: bad sizes");
+  if (n > mgb_series_mll_max_n(0, 0)) return fail(MGB_ERR_ARG, "dense_fit: n exceeds the single-CTA limit (mgb_series_mll_max_n(0, 0))");
+  MllParams p{};
+  p.n = (int)n; p.y = y; p.hyper = hyper; p.out = nll; p.status = status;
+  p.rinv = rinv; p.rinv_t = rinv_t; p.alpha_out = alpha; p.ldo = ldo;
+  p.Kin = K; p.ldk = ldk;
+  const size_t smem = sizeof(double) * (size_t)(n * (n + 1) + 5 * n + 4);
+  if (smem > 48 * 1024)
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute"));
+  series_mll_kernel<<<1, MLL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("series_mll_kernel (dense fit)");
+}

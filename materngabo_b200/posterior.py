@@ -104,11 +104,13 @@ class ExactGPPosterior:
         else:
             spec, coef = None, None
             k = self.outputscale * self.kernel.forward(x, x)
-        k.diagonal().add_(self.noise)
-        L = torch.linalg.cholesky(k)
-        self.alpha = torch.cholesky_solve((self.train_y - self.mean_const).unsqueeze(-1), L).squeeze(-1).contiguous()
-        self.rinv = torch.linalg.solve_triangular(L, torch.eye(n, dtype=F64, device=self.device), upper=False).contiguous()
-        self.rinv_t = self.rinv.t().contiguous()          # row access to the columns of L^-1 (fused acquisition kernel)
+        if not self._dense_fit(k.detach()):
+            k = k.detach().clone()
+            k.diagonal().add_(self.noise)
+            L = torch.linalg.cholesky(k)
+            self.alpha = torch.cholesky_solve((self.train_y - self.mean_const).unsqueeze(-1), L).squeeze(-1).contiguous()
+            self.rinv = torch.linalg.solve_triangular(L, torch.eye(n, dtype=F64, device=self.device), upper=False).contiguous()
+            self.rinv_t = self.rinv.t().contiguous()      # row access to the columns of L^-1 (fused acquisition kernel)
         self.spec, self.coef = spec, coef
         if self.is_series:
             self.kss_value = _self_kernel_value(spec, coef)
@@ -149,6 +151,29 @@ class ExactGPPosterior:
         self.train_prepared = x
         self._nodes = None
         self._pack()
+        return True
+
+    def _dense_fit(self, k) -> bool:
+        """Launch-bound sizes, any kernel: Cholesky, L^-1 and alpha of k + noise I from ONE launch of the single-CTA kernel
+        in dense mode (mgb_dense_fit) instead of four torch.linalg calls."""
+        n = k.shape[0]
+        if k.dim() != 2 or n > _ops.dense_mll_max_n():
+            return False
+        k = k.contiguous()
+        lib = _lib.load()
+        self.rinv = torch.empty((n, n), dtype=F64, device=self.device)
+        self.rinv_t = torch.empty((n, n), dtype=F64, device=self.device)
+        self.alpha = torch.empty(n, dtype=F64, device=self.device)
+        nll = torch.empty(1, dtype=F64, device=self.device)
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        hyper = torch.tensor([1.0, self.noise, self.mean_const], dtype=F64).to(self.device)      # k carries the outputscale
+        with torch.cuda.device(self.device):
+            rc = lib.mgb_dense_fit(_lib.ptr(k), n, k.stride(0), _lib.ptr(self.train_y), _lib.ptr(hyper), _lib.ptr(self.rinv),
+                                   _lib.ptr(self.rinv_t), n, _lib.ptr(self.alpha), _lib.ptr(nll), _lib.ptr(status),
+                                   _lib.stream_ptr(self.device))
+        _lib.check(rc, "mgb_dense_fit")
+        if int(status) != 0:
+            raise torch.linalg.LinAlgError("ExactGPPosterior.fit: s K + noise I is not positive definite (pivot %d)" % int(status))
         return True
 
     def _factor_scale(self, spec):
