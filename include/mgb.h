@@ -337,6 +337,24 @@ int mgb_dense_fit(const double* K, long long n, long long ldk, const double* y, 
 int mgb_pair_scalars(int kind, int width, const double* x1, long long m, long long ld1, const double* x2, long long n,
                      long long ld2, double* out0, double* out1, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Opt-in INT8 tensor-core path for the posterior's N^2 contraction (csrc/int8_posterior.cu): every row of K* and of
+ * L^-1 is scaled by a power of two and cut into seven signed 7-bit slices; the 28 slice products with p + q <= 6 are
+ * seven int8 GEMMs (exact int32 accumulation), recombined in float64.  Same quantities as mgb_posterior_reduce, to
+ * ~1e-11 of max var at n = 5000 (the FP64 kernel: ~1e-14).  The GEMM is a library kernel (CUTLASS headers at build
+ * time); mgb_int8_available() == 0 when the library was built without them.
+ *   pack:    rinv (n x n, lower triangular L^-1, row-major, ld) -> packed (mgb_posterior_int8_pack_bytes(n) bytes)
+ *   reduce:  kstar (m x n float64 kernel rows, row-major, ldk), packed, alpha -> mean[m], var[m];
+ *            workspace of mgb_posterior_int8_workspace_bytes(m, n) bytes (caller-owned).
+ * ------------------------------------------------------------------------------------------------ */
+int mgb_int8_available(void);
+long long mgb_posterior_int8_pack_bytes(long long n);
+int mgb_posterior_int8_pack(const double* rinv, long long n, long long ld, void* packed, void* stream);
+long long mgb_posterior_int8_workspace_bytes(long long m, long long n);
+int mgb_posterior_int8_reduce(const double* kstar, long long m, long long n, long long ldk, const void* packed,
+                              const double* alpha, double kss, double mean_const, double* mean, double* var,
+                              void* workspace, long long workspace_bytes, void* stream);
+
 /* Analytic EI from posterior means / variances (botorch ExpectedImprovement: sigma = sqrt(max(var, 1e-9)),
  * u = +-(mean - best_f) / sigma, EI = sigma (phi(u) + u Phi(u))), elementwise over m candidates. */
 int mgb_expected_improvement(const double* mean, const double* var, long long m, double best_f, int maximize,

@@ -75,6 +75,11 @@ PROTOTYPES = {
                                             _P, _LL, _P, _D, _D, _D, _I, _P, _LL, _P, _P, _P, _P]),
     "mgb_spd2_acquisition_ei_step": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P, _I, _P, _P, _I, _D, _P, _LL, _P, _LL,
                                           _P, _D, _D, _D, _I, _P, _LL, _P, _P, _P]),
+    "mgb_int8_available": (_I, []),
+    "mgb_posterior_int8_pack_bytes": (_LL, [_LL]),
+    "mgb_posterior_int8_pack": (_I, [_P, _LL, _LL, _P, _P]),
+    "mgb_posterior_int8_workspace_bytes": (_LL, [_LL, _LL]),
+    "mgb_posterior_int8_reduce": (_I, [_P, _LL, _LL, _LL, _P, _P, _D, _D, _P, _P, _P, _LL, _P]),
     "mgb_expected_improvement": (_I, [_P, _P, _LL, _D, _I, _P, _P]),
     "mgb_pair_scalars": (_I, [_I, _I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P]),
     "mgb_spectral_coef": (_I, [_I, _I, _I, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),

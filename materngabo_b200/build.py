@@ -16,9 +16,24 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmgb.so")
-SOURCES = ["runtime.cu", "series_gram.cu", "quad_gram.cu", "quad_profile.cu", "posterior.cu", "mll.cu", "acquisition.cu", "host_api.cu"]
+SOURCES = ["runtime.cu", "series_gram.cu", "quad_gram.cu", "quad_profile.cu", "posterior.cu", "mll.cu", "acquisition.cu", "host_api.cu",
+           "int8_posterior.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def _cutlass_flags():
+    """Include flags for the CUTLASS / CuTe header tree vendored in the image (flashinfer wheel), used by
+    int8_posterior.cu only (a library int8 GEMM for the opt-in INT8 path).  Without the headers that file builds its
+    stub: mgb_int8_available() == 0 and the FP64 tensor-core path stays the only one."""
+    roots = []
+    for base in sys.path:
+        roots.append(os.path.join(base, "flashinfer", "data", "cutlass"))
+    roots.append(os.environ.get("MGB_CUTLASS_DIR", ""))
+    for root in roots:
+        if root and os.path.exists(os.path.join(root, "include", "cutlass", "gemm", "collective", "builders", "sm100_umma_builder.inl")):
+            return ["-I" + os.path.join(root, "include"), "-DMGB_HAVE_CUTLASS=1", "-diag-suppress", "20012", "--expt-extended-lambda"]
+    return []
 
 
 def _nvcc():
@@ -72,7 +87,8 @@ def _build_locked(verbose: bool) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        extra = _cutlass_flags() if src == "int8_posterior.cu" else []
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, pr in procs:

@@ -15,6 +15,8 @@ product + square-sum, csrc/posterior.cu) and never materialises K(X*, X) beyond 
 """
 from __future__ import annotations
 
+import os
+
 import contextlib
 import ctypes as C
 import math
@@ -67,7 +69,8 @@ class ExactGPPosterior:
     """
 
     def __init__(self, kernel, train_x: torch.Tensor, train_y: torch.Tensor, outputscale: float = 1.0,
-                 noise: float = 1e-2, mean_const: float = 0.0, chunk: int = DEFAULT_CHUNK, tabulate: bool = False):
+                 noise: float = 1e-2, mean_const: float = 0.0, chunk: int = DEFAULT_CHUNK, tabulate: bool = False,
+                 int8: Optional[bool] = None):
         _lib.require_cuda_f64(train_x, train_y)
         self.kernel = kernel
         self.train_x = train_x.contiguous()
@@ -80,8 +83,13 @@ class ExactGPPosterior:
         # (materngabo_b200/tabulated.py) instead of one quadrature per entry; the fit always uses the quadrature
         self.tabulate = bool(tabulate)
         self.device = train_x.device
+        # opt-in: the N^2 contraction on the INT8 tensor cores by error-free slicing (csrc/int8_posterior.cu; ~1e-11 of
+        # max var instead of ~1e-14).  Default: the FP64 tensor-core kernel.  MGB_POSTERIOR_PATH=int8 turns it on globally.
+        self.int8 = bool(int8) if int8 is not None else os.environ.get("MGB_POSTERIOR_PATH", "") == "int8"
         self._packed = None
+        self._packed_i8 = None
         self._ws = None
+        self._ws_i8 = None
         self.spec = None
         self.coef = None
         self.kss_value = None
@@ -197,6 +205,7 @@ class ExactGPPosterior:
             rc = lib.mgb_posterior_pack(_lib.ptr(self.rinv), n, self.rinv.stride(0), _lib.ptr(self.alpha),
                                         _lib.ptr(self._packed), _lib.stream_ptr(self.device))
         _lib.check(rc, "mgb_posterior_pack")
+        self._packed_i8 = None                     # sliced lazily by the first INT8 evaluation after a (re)fit
 
     # ---- state exchange for the sharded path ---------------------------------------------------
     def state(self):
@@ -226,6 +235,8 @@ class ExactGPPosterior:
             return mean, var
         lib = _lib.load()
         chunk = min(self.chunk, (m + 127) // 128 * 128)
+        if self.int8:
+            return self._posterior_int8(x, mean, var, chunk)
         if not self.is_series:
             return self._posterior_generic(x, mean, var, chunk)
         need = lib.mgb_posterior_workspace_bytes(chunk, n)
@@ -241,6 +252,43 @@ class ExactGPPosterior:
         _lib.check(rc, "mgb_series_posterior")
         return mean, var
 
+
+    def _posterior_int8(self, x, mean, var, chunk):
+        """Opt-in INT8 tensor-core path (csrc/int8_posterior.cu): row-major float64 kernel rows from the Gram kernel,
+        sliced into int8, seven int8 GEMMs against the sliced L^-1, recombined in float64.  ~1e-11 of max var."""
+        lib = _lib.load()
+        if not lib.mgb_int8_available():
+            raise _lib.MgbError("libmgb was built without the CUTLASS headers: the INT8 path is not available")
+        m, n = x.shape[0], self.train_prepared.shape[0]
+        st = _lib.stream_ptr(self.device)
+        if getattr(self, "rinv", None) is None or getattr(self, "alpha", None) is None:
+            raise RuntimeError("the INT8 path needs L^-1 and alpha of a local fit() (not a state loaded from a peer)")
+        if self._packed_i8 is None:
+            self._packed_i8 = torch.empty(lib.mgb_posterior_int8_pack_bytes(n), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(lib.mgb_posterior_int8_pack(_lib.ptr(self.rinv), n, self.rinv.stride(0), _lib.ptr(self._packed_i8), st),
+                           "mgb_posterior_int8_pack")
+        chunk = min(chunk, 16384)
+        need = lib.mgb_posterior_int8_workspace_bytes(chunk, n)
+        if self._ws_i8 is None or self._ws_i8.numel() < need:
+            self._ws_i8 = torch.empty(need, dtype=torch.uint8, device=self.device)
+        forward = None
+        if not self.is_series:
+            forward = self.kernel.forward
+        with torch.cuda.device(self.device):
+            for c0 in range(0, m, chunk):
+                mc = min(chunk, m - c0)
+                if forward is None:
+                    k = _ops.series_gram(self.spec, x[c0:c0 + mc], self.train_prepared, self.coef)   # carries the outputscale
+                else:
+                    k = (self.outputscale * forward(x[c0:c0 + mc], self.train_prepared)).contiguous()
+                rc = lib.mgb_posterior_int8_reduce(_lib.ptr(k), mc, n, k.stride(0), _lib.ptr(self._packed_i8),
+                                                   _lib.ptr(self.alpha), float(self.kss_value), self.mean_const,
+                                                   _lib.ptr(mean[c0:]), _lib.ptr(var[c0:]), _lib.ptr(self._ws_i8),
+                                                   self._ws_i8.numel(), st)
+                _lib.check(rc, "mgb_posterior_int8_reduce")
+                del k
+        return mean, var
 
     def _posterior_generic(self, x, mean, var, chunk):
         """Row-major Gram chunk from ``kernel.forward`` -> re-tile -> fused reduction."""

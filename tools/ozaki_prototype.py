@@ -21,15 +21,18 @@ torch.set_default_dtype(torch.float64)
 from oracle import restated as R  # noqa: E402
 
 
+ROUND = True      # round-to-nearest slices (|q| <= 2^(bits-1), zero-mean remainders) instead of truncation
+
+
 def slices(a, s, bits):
     """a (rows x k) -> list of s integer-valued float64 matrices and the per-row scale 2^e with
     a = 2^e * sum_p slices[p] * 2^(-bits (p + 1)) + O(2^(e - bits s))."""
-    e = np.ceil(np.log2(np.abs(a).max(axis=1, keepdims=True) + 1e-300))
-    r = a / np.exp2(e)                       # in [-1, 1]
+    e = np.floor(np.log2(np.abs(a).max(axis=1, keepdims=True) + 1e-300)) + (2.0 if ROUND else 1.0)
+    r = a / np.exp2(e)                       # |r| < 1 (truncation) or <= 1/2 (rounding)
     out = []
     for _ in range(s):
         r = r * (1 << bits)
-        q = np.trunc(r)                      # |q| <= 2^bits - 1 after the first step: fits a signed (bits + 1)-bit integer
+        q = np.rint(r) if ROUND else np.trunc(r)
         out.append(q)
         r = r - q
     return out, np.exp2(e)
@@ -71,11 +74,14 @@ def main(n=1000, m=512):
     print("n = %d training points, m = %d candidates (a quarter of them 1e-3 from a training point); min var %.3e"
           % (n, m, var_ref.min()))
     print("float64 BLAS:                      max |var - ref| / max|var| = %.2e" % (np.abs(var64 - var_ref).max() / scale))
-    for bits in (6, 7):
-        for s in (5, 6, 7, 8, 9):
+    global ROUND
+    for ROUND in (False, True):
+      print("round-to-nearest slices" if ROUND else "truncated slices")
+      for bits in (7,):
+        for s in (6, 7, 8):
             v, gemms, peak = sliced_product(ks, rinv, s, bits)
             var = 1.0 - (v * v).sum(1)
-            print("bits %d, %d slices: %2d integer GEMMs, max |accumulator| 2^%.1f, max |var - ref| / max|var| = %.2e"
+            print("  " +"bits %d, %d slices: %2d integer GEMMs, max |accumulator| 2^%.1f, max |var - ref| / max|var| = %.2e"
                   % (bits, s, gemms, np.log2(max(peak, 1.0)), np.abs(var - var_ref).max() / scale))
 
 
