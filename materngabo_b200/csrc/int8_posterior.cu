@@ -10,6 +10,9 @@
 // with C_d an INTEGER matrix product (exact in int32: 7 * 5000 * 64^2 < 2^31).  The slices are stored side by side,
 // A as [A_0 | ... | A_6] and B REVERSED as [B_6 | ... | B_0]: anti-diagonal d is then ONE int8 GEMM with
 // K' = (d + 1) Kpad over a prefix of A and a suffix of B - 7 GEMMs (28 slice products) per candidate block.
+// L^-1 is lower triangular: its rows are split into NB column blocks of the product (rows j in [J nb, (J + 1) nb) only
+// meet k < (J + 1) nb), and each block gets its own compacted copy of the operands ([A_0[:, :kJ] | ... | A_6[:, :kJ]],
+// kJ = (J + 1) nb), so that the prefix / suffix trick works per block: 7 NB GEMMs with 62.5 % of the dense work at NB = 4.
 // Dropped pairs (p + q >= 7) and slice remainders leave 8.5e-12 of max var at n = 5000 (tools/ozaki_prototype.py),
 // inside the 1e-10 parity bar.
 //
@@ -36,17 +39,40 @@ constexpr int I8_PAD = 256;
 
 __host__ __device__ inline long long i8_round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
+// Column blocks of the triangular operand: NB = 4 from 2048 training points on, Npad a multiple of 256 NB.
+struct I8Geom {
+  int NB;
+  long long np, nb;                       // padded n, block width
+  __host__ __device__ long long kJ(int J) const { return (J + 1) * nb; }
+  // byte offset of block J's operand copy in a buffer of `rows`-row copies: sum_{I < J} rows * S * kI
+  __host__ __device__ long long a_off(int J, long long rows) const { return rows * I8_SLICES * nb * ((long long)J * (J + 1) / 2); }
+  __host__ __device__ long long a_bytes(long long rows) const { return a_off(NB, rows); }
+  // B copies hold only the nb rows of their block
+  __host__ __device__ long long b_off(int J) const { return nb * I8_SLICES * nb * ((long long)J * (J + 1) / 2); }
+  __host__ __device__ long long b_bytes() const { return b_off(NB); }
+};
+
+__host__ __device__ inline I8Geom i8_geom(long long n) {
+  I8Geom g;
+  g.NB = (n >= 2048) ? 4 : 1;
+  g.np = i8_round_up(n, (long long)I8_PAD * g.NB);
+  g.nb = g.np / g.NB;
+  return g;
+}
+
 // One warp per row: e = floor(log2 max|row|) + 2 (so |row| 2^-e <= 1/2), then S round-to-nearest slices of 7 bits.
-// dst row = [slice 0 | slice 1 | ... ] (reversed = 0) or [slice S-1 | ... | slice 0] (reversed = 1), each Kpad wide,
-// zero beyond `cols`.
-__global__ void __launch_bounds__(256) i8_slice_rows_kernel(const double* src, long long ld, long long rows, int cols,
-                                                            int Kpad, int reversed, signed char* dst, int* exps) {
+// A operand (is_b = 0): the row goes into EVERY block copy J >= column block, at [row][p kJ + c].
+// B operand (is_b = 1, L^-1): row j belongs to block J = j / nb only, slices reversed: [j - J nb][(S - 1 - p) kJ + c];
+// entries right of the diagonal are zero by construction and are written as zeros.
+__global__ void __launch_bounds__(256) i8_slice_rows_kernel(const double* src, long long ld, long long rows, int cols, I8Geom g,
+                                                            int is_b, signed char* dst, int* exps) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const double* s = src + row * ld;
+  const int used = is_b ? (int)min((long long)cols, row + 1) : cols;      // lower triangle of L^-1
   double mx = 0.0;
-  for (int c = lane; c < cols; c += 32) mx = fmax(mx, fabs(s[c]));
+  for (int c = lane; c < used; c += 32) mx = fmax(mx, fabs(s[c]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   int e = 0;
@@ -55,11 +81,13 @@ __global__ void __launch_bounds__(256) i8_slice_rows_kernel(const double* src, l
     e += 1;                   // |row| 2^-e < 1/2
   }
   if (lane == 0) exps[row] = e;
-  signed char* d = dst + row * (long long)(I8_SLICES * Kpad);
-  for (int c0 = 4 * lane; c0 < Kpad; c0 += 128) {      // four columns per lane: one 32-bit store per slice
+  const int Jrow = is_b ? (int)(row / g.nb) : 0;
+  const long long kmax = is_b ? g.kJ(Jrow) : g.np;
+  for (long long c0 = 4 * lane; c0 < kmax; c0 += 128) {      // four columns per lane: one 32-bit store per slice and copy
     double r[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) r[t] = (c0 + t < cols) ? ldexp(s[c0 + t], -e) : 0.0;
+    for (int t = 0; t < 4; ++t) r[t] = (c0 + t < used) ? ldexp(s[c0 + t], -e) : 0.0;
+    const int kb = (int)(c0 / g.nb);
 #pragma unroll
     for (int p = 0; p < I8_SLICES; ++p) {
       char4 q;
@@ -71,8 +99,15 @@ __global__ void __launch_bounds__(256) i8_slice_rows_kernel(const double* src, l
         qq[t] = (signed char)(int)qi;
         r[t] = x - qi;
       }
-      const int slot = reversed ? (I8_SLICES - 1 - p) : p;
-      *reinterpret_cast<char4*>(d + (long long)slot * Kpad + c0) = q;
+      if (is_b) {
+        const long long k = g.kJ(Jrow);
+        *reinterpret_cast<char4*>(dst + g.b_off(Jrow) + (row - Jrow * g.nb) * (I8_SLICES * k) + (long long)(I8_SLICES - 1 - p) * k + c0) = q;
+      } else {
+        for (int J = kb; J < g.NB; ++J) {
+          const long long k = g.kJ(J);
+          *reinterpret_cast<char4*>(dst + g.a_off(J, rows) + row * (I8_SLICES * k) + (long long)p * k + c0) = q;
+        }
+      }
     }
   }
 }
@@ -172,27 +207,26 @@ extern "C" int mgb_int8_available(void) {
 
 extern "C" long long mgb_posterior_int8_pack_bytes(long long n) {
   if (n < 1) return 0;
-  const long long np = i8_round_up(n, I8_PAD);
-  return 4 * np + np * (long long)I8_SLICES * np;
+  const I8Geom g = i8_geom(n);
+  return 4 * g.np + g.b_bytes();
 }
 
 extern "C" int mgb_posterior_int8_pack(const double* rinv, long long n, long long ld, void* packed, void* stream) {
   if (!rinv || !packed || n < 1 || ld < n) return fail(MGB_ERR_ARG, "posterior_int8_pack: bad argument");
   if (n > 32768) return fail(MGB_ERR_ARG, "posterior_int8_pack: n too large for exact int32 accumulation");
-  const long long np = i8_round_up(n, I8_PAD);
+  const I8Geom g = i8_geom(n);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int* eb = static_cast<int*>(packed);
-  signed char* B = static_cast<signed char*>(packed) + 4 * np;
+  signed char* B = static_cast<signed char*>(packed) + 4 * g.np;
   MGB_TRY(check_cuda(cudaMemsetAsync(packed, 0, (size_t)mgb_posterior_int8_pack_bytes(n), s), "cudaMemsetAsync"));
-  i8_slice_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(rinv, ld, n, (int)n, (int)np, 1, B, eb);
+  i8_slice_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(rinv, ld, n, (int)n, g, 1, B, eb);
   return after_launch("i8_slice_rows_kernel (pack)");
 }
 
 extern "C" long long mgb_posterior_int8_workspace_bytes(long long m, long long n) {
   if (m < 1 || n < 1) return 0;
-  const long long np = i8_round_up(n, I8_PAD);
-  return i8_round_up(4 * m, 256) + i8_round_up(m * (long long)I8_SLICES * np, 256) + (long long)I8_SLICES * m * np * 4 +
-         (long long)I8_GEMM_WS;
+  const I8Geom g = i8_geom(n);
+  return i8_round_up(4 * m, 256) + i8_round_up(g.a_bytes(m), 256) + (long long)I8_SLICES * m * g.np * 4 + (long long)I8_GEMM_WS;
 }
 
 extern "C" int mgb_posterior_int8_reduce(const double* kstar, long long m, long long n, long long ldk, const void* packed,
@@ -208,27 +242,31 @@ extern "C" int mgb_posterior_int8_reduce(const double* kstar, long long m, long 
     return fail(MGB_ERR_ARG, "posterior_int8_reduce: bad argument");
   if (m > 0x7fffffffLL / 8 || n > 32768) return fail(MGB_ERR_ARG, "posterior_int8_reduce: block too large");
   if (workspace_bytes < mgb_posterior_int8_workspace_bytes(m, n)) return fail(MGB_ERR_ARG, "posterior_int8_reduce: workspace too small");
-  const long long np = i8_round_up(n, I8_PAD);
+  const I8Geom g = i8_geom(n);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   char* w = static_cast<char*>(workspace);
   int* ea = reinterpret_cast<int*>(w);
   w += i8_round_up(4 * m, 256);
   signed char* A = reinterpret_cast<signed char*>(w);
-  w += i8_round_up(m * (long long)I8_SLICES * np, 256);
+  w += i8_round_up(g.a_bytes(m), 256);
   int* C = reinterpret_cast<int*>(w);
-  w += (long long)I8_SLICES * m * np * 4;
+  w += (long long)I8_SLICES * m * g.np * 4;
   void* gws = w;
   const int* eb = static_cast<const int*>(packed);
-  const signed char* B = static_cast<const signed char*>(packed) + 4 * np;
-  i8_slice_rows_kernel<<<(unsigned)((m + 7) / 8), 256, 0, s>>>(kstar, ldk, m, (int)n, (int)np, 0, A, ea);
+  const signed char* B = static_cast<const signed char*>(packed) + 4 * g.np;
+  i8_slice_rows_kernel<<<(unsigned)((m + 7) / 8), 256, 0, s>>>(kstar, ldk, m, (int)n, g, 0, A, ea);
   MGB_TRY(after_launch("i8_slice_rows_kernel"));
-  const long long lda = (long long)I8_SLICES * np;
-  for (int d = 0; d < I8_SLICES; ++d) {
-    // pairs (p, d - p), p = 0..d: A slices 0..d against B slices d..0 = columns [(S-1-d) np, S np) of the reversed B
-    MGB_TRY(i8_gemm(A, lda, B + (long long)(I8_SLICES - 1 - d) * np, lda, C + (long long)d * m * np, np, (int)m, (int)np,
-                    (int)((d + 1) * np), gws, I8_GEMM_WS, s));
+  for (int J = 0; J < g.NB; ++J) {
+    const long long k = g.kJ(J), ldab = (long long)I8_SLICES * k;
+    const signed char* AJ = A + g.a_off(J, m);
+    const signed char* BJ = B + g.b_off(J);
+    for (int d = 0; d < I8_SLICES; ++d) {
+      // pairs (p, d - p), p = 0..d: A slices 0..d against B slices d..0 = columns [(S-1-d) kJ, S kJ) of the reversed B
+      MGB_TRY(i8_gemm(AJ, ldab, BJ + (long long)(I8_SLICES - 1 - d) * k, ldab, C + (long long)d * m * g.np + J * g.nb, g.np,
+                      (int)m, (int)g.nb, (int)((d + 1) * k), gws, I8_GEMM_WS, s));
+    }
   }
-  i8_combine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, s>>>(C, m, (int)n, (int)np, ea, eb, kstar, ldk, alpha, kss, mean_const,
+  i8_combine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, s>>>(C, m, (int)n, (int)g.np, ea, eb, kstar, ldk, alpha, kss, mean_const,
                                                            mean, var);
   return after_launch("i8_combine_kernel");
 #endif

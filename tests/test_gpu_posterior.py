@@ -383,7 +383,7 @@ def test_baseline_train_size_chunk_consistency():
     assert torch.isfinite(mean).all() and (var > -1e-9).all() and (var <= 1.0 + 1e-9).all()
 
 
-@pytest.mark.parametrize("n,m", [(300, 1000), (1000, 20000)])
+@pytest.mark.parametrize("n,m", [(300, 1000), (1000, 20000), (2100, 3001)])
 def test_int8_tensor_core_posterior_matches_the_fp64_path(n, m):
     """Opt-in INT8 path (error-free 7-bit slicing, seven int8 GEMMs, float64 recombination) against the FP64
     tensor-core kernel: variance to 1e-10 of max var (measured ~1e-11), mean to 1e-12 - including candidates 1e-3
