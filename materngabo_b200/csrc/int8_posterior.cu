@@ -125,15 +125,31 @@ __global__ void __launch_bounds__(256) i8_combine_kernel(const int* C, long long
   const int* c = C + row * (long long)Npad;
   const double* kr = kstar + row * ldk;
   const int ei = ea[row];
-  double ss = 0.0, mu = 0.0;
-  for (int j = lane; j < n; j += 32) {
-    double acc = 0.0;
+  double wgt[I8_SLICES];
 #pragma unroll
-    for (int d = I8_SLICES - 1; d >= 0; --d)      // smallest weights first
-      acc = fma((double)c[d * plane + j], exp2((double)(-I8_BITS * (d + 2))), acc);
-    const double v = ldexp(acc, ei + eb[j]);
-    ss = fma(v, v, ss);
-    mu = fma(kr[j], alpha[j], mu);
+  for (int d = 0; d < I8_SLICES; ++d) wgt[d] = exp2((double)(-I8_BITS * (d + 2)));
+  double ss = 0.0, mu = 0.0;
+  // four columns per lane and iteration: 16-byte loads from each of the seven accumulator planes (Npad % 4 == 0)
+  for (int j0 = 4 * lane; j0 < n; j0 += 128) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = I8_SLICES - 1; d >= 0; --d) {      // smallest weights first
+      const int4 q = *reinterpret_cast<const int4*>(c + d * plane + j0);
+      acc[0] = fma((double)q.x, wgt[d], acc[0]);
+      acc[1] = fma((double)q.y, wgt[d], acc[1]);
+      acc[2] = fma((double)q.z, wgt[d], acc[2]);
+      acc[3] = fma((double)q.w, wgt[d], acc[3]);
+    }
+    const int4 e4 = *reinterpret_cast<const int4*>(eb + j0);
+    const int ee[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (j0 + t < n) {
+        const double v = ldexp(acc[t], ei + ee[t]);
+        ss = fma(v, v, ss);
+        mu = fma(kr[j0 + t], alpha[j0 + t], mu);
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

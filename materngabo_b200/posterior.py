@@ -59,6 +59,9 @@ def _frozen_parameters(module):
             p.requires_grad_(True)
 
 
+INT8_CHUNK = 32768      # candidates per block of the INT8 path: 640 GEMM tiles per launch = 9 waves of 2-SM tile pairs
+
+
 class ExactGPPosterior:
     """Constant-mean exact GP over one of the drop-in kernels.
 
@@ -268,7 +271,7 @@ class ExactGPPosterior:
             with torch.cuda.device(self.device):
                 _lib.check(lib.mgb_posterior_int8_pack(_lib.ptr(self.rinv), n, self.rinv.stride(0), _lib.ptr(self._packed_i8), st),
                            "mgb_posterior_int8_pack")
-        chunk = min(chunk, 16384)
+        chunk = min(INT8_CHUNK, (m + 255) // 256 * 256)
         need = lib.mgb_posterior_int8_workspace_bytes(chunk, n)
         if self._ws_i8 is None or self._ws_i8.numel() < need:
             self._ws_i8 = torch.empty(need, dtype=torch.uint8, device=self.device)
