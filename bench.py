@@ -216,6 +216,11 @@ def run_posterior(args, rank, world, local):
     if rank == 0:
         roof = posterior_roofline(gp, xc, n, lib)
 
+    # ---- opt-in INT8 tensor-core path on a bounded sample (rank 0, one GPU), with its parity against `value`'s path ---
+    int8 = None
+    if rank == 0 and world == 1 and lib.mgb_int8_available() and m_local >= 65536:
+        int8 = posterior_int8_sample(gp, xc[: min(m_local, 2 * 1024 * 1024)], value)
+
     # ---- end to end through the host-buffer C-ABI call -------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -235,9 +240,37 @@ def run_posterior(args, rank, world, local):
                                     "(chunk buffer %.2f GB > 126 MB L2)" % (8e-9 * m_total * n / world,
                                                                             8e-9 * gp.chunk * n)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e,
-            "checksum": checksum,
+            "checksum": checksum, "int8_path": int8,
         }
     return out
+
+
+def posterior_int8_sample(gp, xs, fp64_value):
+    """The opt-in INT8 path (materngabo_b200/csrc/int8_posterior.cu) on a sample of the same candidates: candidates/s
+    and the difference to the FP64 path's results on that sample.  Reported beside the headline, not as the headline:
+    its GEMM is a library kernel (CUTLASS int8, tcgen05 kind::i8); slicing and recombination are this repo's kernels."""
+    mean0, var0 = gp.posterior(xs)
+    gp.int8 = True
+    try:
+        gp.posterior(xs[:65536])                                   # slices L^-1, allocates the workspace
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mean1, var1 = gp.posterior(xs)
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        gp.int8 = False
+        gp._ws_i8 = None
+    ms = e0.elapsed_time(e1)
+    v = xs.shape[0] / (ms * 1e-3)
+    return {"value": v, "unit": "candidates/s", "sample_candidates": int(xs.shape[0]), "ms": ms,
+            "ratio_to_fp64_path": v / fp64_value,
+            "max_var_diff_rel_to_max_var": float((var1 - var0).abs().max() / var0.abs().max()),
+            "max_mean_diff_rel_to_max_mean": float((mean1 - mean0).abs().max() / mean0.abs().max()),
+            "note": "opt-in (ExactGPPosterior(int8=True) / MGB_POSTERIOR_PATH=int8): error-free 7-bit slicing of K* and "
+                    "L^-1, 28 slice products as 7 x 4 int8 GEMMs (library kernel: CUTLASS collective builder, tcgen05 "
+                    "kind::i8) over column blocks of the triangular factor, float64 recombination; parity bar 1e-10"}
 
 
 def posterior_roofline(gp, xc, n, lib):

@@ -66,6 +66,8 @@ def test_our_arm_json_line_on_the_gpu():
     assert abs(e2e["value"] - d["value"]) > 0              # a separate measurement, not a copy of the device number
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert "sm_mhz" in d["clocks"] and "workload" in d["config"] and "l2_policy" in d["config"]
+    i8 = d["int8_path"]
+    assert i8 is None or (i8["value"] > 0 and i8["max_var_diff_rel_to_max_var"] < 1e-10)
 
 
 @pytest.mark.gpu
