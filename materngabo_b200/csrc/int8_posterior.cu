@@ -83,17 +83,19 @@ __global__ void __launch_bounds__(256) i8_slice_rows_kernel(const double* src, l
   if (lane == 0) exps[row] = e;
   const int Jrow = is_b ? (int)(row / g.nb) : 0;
   const long long kmax = is_b ? g.kJ(Jrow) : g.np;
-  for (long long c0 = 4 * lane; c0 < kmax; c0 += 128) {      // four columns per lane: one 32-bit store per slice and copy
-    double r[4];
+  // sixteen columns per lane and iteration: one 16-byte store per slice and operand copy (nb is a multiple of 256, so the
+  // sixteen columns lie in one column block)
+  for (long long c0 = 16 * lane; c0 < kmax; c0 += 512) {
+    double r[16];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) r[t] = (c0 + t < used) ? ldexp(s[c0 + t], -e) : 0.0;
+    for (int t = 0; t < 16; ++t) r[t] = (c0 + t < used) ? ldexp(s[c0 + t], -e) : 0.0;
     const int kb = (int)(c0 / g.nb);
-#pragma unroll
+#pragma unroll 1
     for (int p = 0; p < I8_SLICES; ++p) {
-      char4 q;
+      uint4 q;
       signed char* qq = reinterpret_cast<signed char*>(&q);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < 16; ++t) {
         const double x = r[t] * (double)(1 << I8_BITS);
         const double qi = rint(x);
         qq[t] = (signed char)(int)qi;
@@ -101,11 +103,11 @@ __global__ void __launch_bounds__(256) i8_slice_rows_kernel(const double* src, l
       }
       if (is_b) {
         const long long k = g.kJ(Jrow);
-        *reinterpret_cast<char4*>(dst + g.b_off(Jrow) + (row - Jrow * g.nb) * (I8_SLICES * k) + (long long)(I8_SLICES - 1 - p) * k + c0) = q;
+        *reinterpret_cast<uint4*>(dst + g.b_off(Jrow) + (row - Jrow * g.nb) * (I8_SLICES * k) + (long long)(I8_SLICES - 1 - p) * k + c0) = q;
       } else {
         for (int J = kb; J < g.NB; ++J) {
           const long long k = g.kJ(J);
-          *reinterpret_cast<char4*>(dst + g.a_off(J, rows) + row * (I8_SLICES * k) + (long long)p * k + c0) = q;
+          *reinterpret_cast<uint4*>(dst + g.a_off(J, rows) + row * (I8_SLICES * k) + (long long)p * k + c0) = q;
         }
       }
     }

@@ -409,3 +409,30 @@ def test_int8_tensor_core_posterior_matches_the_fp64_path(n, m):
     assert float((v1 - v0).abs().max() / v0.abs().max()) < 1e-10
     assert float((m1 - m0).abs().max() / m0.abs().max()) < 1e-12
     assert float(v0.min()) < 0.1 * float(v0.max())          # the near-training candidates are in the sample
+
+
+def test_int8_posterior_path_serves_the_quadrature_kernels_too():
+    """The INT8 contraction only needs the float64 kernel rows: a hyperbolic H^3 kernel through its own Gram kernel."""
+    from materngabo_b200 import _lib, kernels_hyperbolic as kh
+    from materngabo_b200.posterior import ExactGPPosterior
+
+    if not _lib.load().mgb_int8_available():
+        pytest.skip("libmgb built without the CUTLASS headers")
+    gen = torch.Generator().manual_seed(7)
+
+    def pts(k):
+        z = 0.7 * torch.randn(k, 3, generator=gen)
+        return torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1).to(DEV)
+
+    xt, xc = pts(200), pts(777)
+    y = torch.sin(2 * xt[:, 1])
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=3, nu=2.5).to(DEV)
+    ref = ExactGPPosterior(k, xt, y, outputscale=0.8, noise=1e-2).fit()
+    fast = ExactGPPosterior(k, xt, y, outputscale=0.8, noise=1e-2, int8=True).fit()
+    m0, v0 = ref.posterior(xc)
+    m1, v1 = fast.posterior(xc)
+    assert float((v1 - v0).abs().max() / v0.abs().max()) < 1e-10
+    assert float((m1 - m0).abs().max() / m0.abs().max()) < 1e-12
+    # empty block
+    me, ve = fast.posterior(xc[:0])
+    assert me.numel() == 0 and ve.numel() == 0
