@@ -33,8 +33,14 @@ using OpClass = cutlass::arch::OpClassTensorOp;
 #define TILE_N _128
 #define CL_M _1
 #endif
-using TileShape = Shape<TILE_M, TILE_N, _128>;
-using ClusterShape = Shape<CL_M, _1, _1>;
+#ifndef TILE_K
+#define TILE_K _128
+#endif
+#ifndef CL_N
+#define CL_N _1
+#endif
+using TileShape = Shape<TILE_M, TILE_N, TILE_K>;
+using ClusterShape = Shape<CL_M, CL_N, _1>;
 
 using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
     ArchTag, OpClass, TileShape, ClusterShape, cutlass::epilogue::collective::EpilogueTileAuto, ElementAcc, ElementAcc,
