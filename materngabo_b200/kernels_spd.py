@@ -91,10 +91,10 @@ class SpdRiemannianIntegratedMaternKernel(_NuMixin, Kernel):
             inner = lambda t: (bw * 2.0 * b / torch.sinh(b) * torch.exp(-(b * b).unsqueeze(0) / (2 * t).unsqueeze(-1))).sum(-1)  # noqa: E731
             t, tcoef, shift = _weights.matern_t_coef(ls, self.nu.to(device), -2.0, 1.5, self.nb_points_integral_t, 1.0,
                                                      ("spd2", self.nb_points_integral_b), inner)
-            key = ("spd2_scales", id(t))
+            key = ("spd2_scales", float(shift), self.nb_points_integral_t, str(ls.device), str(torch.get_default_dtype()))
             hit = _weights._CONST_CACHE.get(key)
-            if hit is None or hit[0] is not t:
-                hit = (t, (1.0 / (4 * t), 1.0 / (2 * t)))
+            if hit is None:
+                hit = (None, (1.0 / (4 * t), 1.0 / (2 * t)))
                 _weights._CONST_CACHE[key] = hit
             rscale, bscale = hit[1]
             if with_lattice:
