@@ -269,7 +269,7 @@ def posterior_int8_sample(gp, xs, fp64_value):
             "max_var_diff_rel_to_max_var": float((var1 - var0).abs().max() / var0.abs().max()),
             "max_mean_diff_rel_to_max_mean": float((mean1 - mean0).abs().max() / mean0.abs().max()),
             "note": "opt-in (ExactGPPosterior(int8=True) / MGB_POSTERIOR_PATH=int8): error-free 7-bit slicing of K* and "
-                    "L^-1, 28 slice products as 7 x 4 int8 GEMMs (library kernel: CUTLASS collective builder, tcgen05 "
+                    "L^-1, 28 slice products as 7 x 5 int8 GEMMs (library kernel: CUTLASS collective builder, tcgen05 "
                     "kind::i8) over column blocks of the triangular factor, float64 recombination; parity bar 1e-10"}
 
 

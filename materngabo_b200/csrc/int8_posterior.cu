@@ -12,7 +12,7 @@
 // K' = (d + 1) Kpad over a prefix of A and a suffix of B - 7 GEMMs (28 slice products) per candidate block.
 // L^-1 is lower triangular: its rows are split into NB column blocks of the product (rows j in [J nb, (J + 1) nb) only
 // meet k < (J + 1) nb), and each block gets its own compacted copy of the operands ([A_0[:, :kJ] | ... | A_6[:, :kJ]],
-// kJ = (J + 1) nb), so that the prefix / suffix trick works per block: 7 NB GEMMs with 62.5 % of the dense work at NB = 4.
+// kJ = (J + 1) nb), so that the prefix / suffix trick works per block: 7 NB GEMMs with 60 % of the dense work at NB = 5.
 // Dropped pairs (p + q >= 7) and slice remainders leave 8.5e-12 of max var at n = 5000 (tools/ozaki_prototype.py),
 // inside the 1e-10 parity bar.
 //
@@ -39,7 +39,7 @@ constexpr int I8_PAD = 256;
 
 __host__ __device__ inline long long i8_round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
-// Column blocks of the triangular operand: NB = 4 from 2048 training points on, Npad a multiple of 256 NB.
+// Column blocks of the triangular operand: NB = 5 from 2048 training points on, Npad a multiple of 256 NB.
 struct I8Geom {
   int NB;
   long long np, nb;                       // padded n, block width
@@ -54,7 +54,7 @@ struct I8Geom {
 
 __host__ __device__ inline I8Geom i8_geom(long long n) {
   I8Geom g;
-  g.NB = (n >= 2048) ? 4 : 1;
+  g.NB = (n >= 2048) ? 5 : 1;      // 5 blocks: 60 % of the dense work, block width 1024 = 4 GEMM tiles at n = 5000
   g.np = i8_round_up(n, (long long)I8_PAD * g.NB);
   g.nb = g.np / g.NB;
   return g;
@@ -64,15 +64,28 @@ __host__ __device__ inline I8Geom i8_geom(long long n) {
 // A operand (is_b = 0): the row goes into EVERY block copy J >= column block, at [row][p kJ + c].
 // B operand (is_b = 1, L^-1): row j belongs to block J = j / nb only, slices reversed: [j - J nb][(S - 1 - p) kJ + c];
 // entries right of the diagonal are zero by construction and are written as zeros.
+// For the A operand the same pass over the row also forms mean_i = mean_const + sum_j K*_ij alpha_j (alpha != nullptr).
 __global__ void __launch_bounds__(256) i8_slice_rows_kernel(const double* src, long long ld, long long rows, int cols, I8Geom g,
-                                                            int is_b, signed char* dst, int* exps) {
+                                                            int is_b, signed char* dst, int* exps, const double* alpha,
+                                                            double mean_const, double* mean) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const double* s = src + row * ld;
   const int used = is_b ? (int)min((long long)cols, row + 1) : cols;      // lower triangle of L^-1
-  double mx = 0.0;
-  for (int c = lane; c < used; c += 32) mx = fmax(mx, fabs(s[c]));
+  double mx = 0.0, mu = 0.0;
+  if (alpha != nullptr) {
+    for (int c = lane; c < used; c += 32) {
+      const double v = s[c];
+      mx = fmax(mx, fabs(v));
+      mu = fma(v, alpha[c], mu);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mu += __shfl_xor_sync(0xffffffffu, mu, o);
+    if (lane == 0) mean[row] = mean_const + mu;
+  } else {
+    for (int c = lane; c < used; c += 32) mx = fmax(mx, fabs(s[c]));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   int e = 0;
@@ -114,23 +127,19 @@ __global__ void __launch_bounds__(256) i8_slice_rows_kernel(const double* src, l
   }
 }
 
-// One warp per candidate: v_ij = 2^(ea_i + eb_j) sum_d 2^(-7 (d + 2)) C_d[i][j], var_i = kss - sum_j v_ij^2,
-// mean_i = mean_const + sum_j K*_ij alpha_j.
+// One warp per candidate: v_ij = 2^(ea_i + eb_j) sum_d 2^(-7 (d + 2)) C_d[i][j], var_i = kss - sum_j v_ij^2.
 __global__ void __launch_bounds__(256) i8_combine_kernel(const int* C, long long m, int n, int Npad, const int* ea,
-                                                         const int* eb, const double* kstar, long long ldk,
-                                                         const double* alpha, double kss, double mean_const, double* mean,
-                                                         double* var) {
+                                                         const int* eb, double kss, double* var) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= m) return;
   const long long plane = m * (long long)Npad;
   const int* c = C + row * (long long)Npad;
-  const double* kr = kstar + row * ldk;
   const int ei = ea[row];
   double wgt[I8_SLICES];
 #pragma unroll
   for (int d = 0; d < I8_SLICES; ++d) wgt[d] = exp2((double)(-I8_BITS * (d + 2)));
-  double ss = 0.0, mu = 0.0;
+  double ss = 0.0;
   // four columns per lane and iteration: 16-byte loads from each of the seven accumulator planes (Npad % 4 == 0)
   for (int j0 = 4 * lane; j0 < n; j0 += 128) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -149,19 +158,12 @@ __global__ void __launch_bounds__(256) i8_combine_kernel(const int* C, long long
       if (j0 + t < n) {
         const double v = ldexp(acc[t], ei + ee[t]);
         ss = fma(v, v, ss);
-        mu = fma(kr[j0 + t], alpha[j0 + t], mu);
       }
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    mu += __shfl_xor_sync(0xffffffffu, mu, o);
-  }
-  if (lane == 0) {
-    var[row] = kss - ss;
-    mean[row] = mean_const + mu;
-  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) var[row] = kss - ss;
 }
 
 #ifdef MGB_HAVE_CUTLASS
@@ -237,7 +239,7 @@ extern "C" int mgb_posterior_int8_pack(const double* rinv, long long n, long lon
   int* eb = static_cast<int*>(packed);
   signed char* B = static_cast<signed char*>(packed) + 4 * g.np;
   MGB_TRY(check_cuda(cudaMemsetAsync(packed, 0, (size_t)mgb_posterior_int8_pack_bytes(n), s), "cudaMemsetAsync"));
-  i8_slice_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(rinv, ld, n, (int)n, g, 1, B, eb);
+  i8_slice_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(rinv, ld, n, (int)n, g, 1, B, eb, nullptr, 0.0, nullptr);
   return after_launch("i8_slice_rows_kernel (pack)");
 }
 
@@ -272,7 +274,7 @@ extern "C" int mgb_posterior_int8_reduce(const double* kstar, long long m, long 
   void* gws = w;
   const int* eb = static_cast<const int*>(packed);
   const signed char* B = static_cast<const signed char*>(packed) + 4 * g.np;
-  i8_slice_rows_kernel<<<(unsigned)((m + 7) / 8), 256, 0, s>>>(kstar, ldk, m, (int)n, g, 0, A, ea);
+  i8_slice_rows_kernel<<<(unsigned)((m + 7) / 8), 256, 0, s>>>(kstar, ldk, m, (int)n, g, 0, A, ea, alpha, mean_const, mean);
   MGB_TRY(after_launch("i8_slice_rows_kernel"));
   for (int J = 0; J < g.NB; ++J) {
     const long long k = g.kJ(J), ldab = (long long)I8_SLICES * k;
@@ -284,8 +286,7 @@ extern "C" int mgb_posterior_int8_reduce(const double* kstar, long long m, long 
                       (int)m, (int)g.nb, (int)((d + 1) * k), gws, I8_GEMM_WS, s));
     }
   }
-  i8_combine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, s>>>(C, m, (int)n, (int)g.np, ea, eb, kstar, ldk, alpha, kss, mean_const,
-                                                           mean, var);
+  i8_combine_kernel<<<(unsigned)((m + 7) / 8), 256, 0, s>>>(C, m, (int)n, (int)g.np, ea, eb, kss, var);
   return after_launch("i8_combine_kernel");
 #endif
 }

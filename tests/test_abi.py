@@ -50,18 +50,18 @@ def test_product_has_no_oracle_dependency():
 
 
 def test_int8_path_size_queries_need_no_gpu():
-    """Host-side size arithmetic of the opt-in INT8 posterior path (csrc/int8_posterior.cu): four column blocks from
-    2048 training points on, operands padded to 256 * blocks, compacted copies of (J + 1) / 4 of the columns."""
+    """Host-side size arithmetic of the opt-in INT8 posterior path (csrc/int8_posterior.cu): five column blocks from
+    2048 training points on, operands padded to 256 * blocks, compacted copies of (J + 1) / 5 of the columns."""
     from materngabo_b200 import _lib
 
     lib = _lib.load()
     assert lib.mgb_int8_available() in (0, 1)
     assert lib.mgb_posterior_int8_pack_bytes(0) == 0
-    # n = 5000 -> padded 5120, four blocks of 1280 rows; block J holds 1280 rows x 7 slices x (J + 1) * 1280 columns
-    assert lib.mgb_posterior_int8_pack_bytes(5000) == 4 * 5120 + 7 * 1280 * 1280 * (1 + 2 + 3 + 4)
+    # n = 5000 -> padded 5120, five blocks of 1024 rows; block J holds 1024 rows x 7 slices x (J + 1) * 1024 columns
+    assert lib.mgb_posterior_int8_pack_bytes(5000) == 4 * 5120 + 7 * 1024 * 1024 * (1 + 2 + 3 + 4 + 5)
     # n = 1000 -> one block, padded 1024
     assert lib.mgb_posterior_int8_pack_bytes(1000) == 4 * 1024 + 7 * 1024 * 1024
     m = 32768
     ws = lib.mgb_posterior_int8_workspace_bytes(m, 5000)
-    assert ws == 4 * m + m * 7 * 1280 * 10 + 7 * m * 5120 * 4 + (1 << 20)
+    assert ws == 4 * m + m * 7 * 1024 * 15 + 7 * m * 5120 * 4 + (1 << 20)
     assert lib.mgb_posterior_int8_workspace_bytes(0, 5000) == 0
