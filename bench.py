@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--workload", default="posterior-s10")
     ap.add_argument("--cands", dest="m", type=int, default=None, help="override candidate / row count")
     ap.add_argument("--train", dest="n", type=int, default=None, help="override training / column count")
+    ap.add_argument("--posterior-path", default="fp64", choices=["fp64", "int8"],
+                    help="default workload: fp64 = hand-written DMMA kernel (default); int8 = opt-in INT8 tensor-core path")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -157,6 +159,10 @@ def run_posterior(args, rank, world, local):
 
     # rank 0 owns the fit; the other ranks receive the state every step (as after a refit in the BO loop)
     gp, kernel = posterior_problem(n, device)
+    use_int8 = args.posterior_path == "int8"
+    if use_int8 and not lib.mgb_int8_available():
+        raise SystemExit("--posterior-path int8: libmgb was built without the CUTLASS headers")
+    gp.int8 = use_int8
     if rank == 0:
         gp.fit()
     sh = ShardedPosterior(compute=None) if world > 1 else None
@@ -169,7 +175,7 @@ def run_posterior(args, rank, world, local):
             state = sh.broadcast_state(gp.state() if rank == 0 else {"like": xc[:0]}, src=0)
             if rank != 0:
                 gp.load_state(spec, state["train"], state["packed"], state["coef"],
-                              _self_k(spec, state["coef"]))
+                              _self_k(spec, state["coef"]), state.get("packed_i8"), state.get("alpha"))
         mean, var = gp.posterior(xc)
         if world > 1:
             sizes = [shard_bounds(m_total, world, r)[1] - shard_bounds(m_total, world, r)[0] for r in range(world)]
@@ -215,10 +221,18 @@ def run_posterior(args, rank, world, local):
     roof = None
     if rank == 0:
         roof = posterior_roofline(gp, xc, n, lib)
+        if use_int8:
+            roof = {"bound": "tensor", "kernel": "CUTLASS int8 GEMM (tcgen05 kind::i8), 35 launches per block of 32768 candidates",
+                    "achieved": value / world * 28 * 0.6 * 2.0 * n * n / 1e12, "unit": "TOP/s (int8, executed slice products over the "
+                    "whole step time of one GPU: slicing, recombination and the Gram kernel included)",
+                    "peak": 2.0 * float(measured_peaks().get("bf16_tflops_sustained") or 1371.4),
+                    "peak_source": "2 x the sustained bf16 rate of MEASURED_PEAKS.json (int8 dense = 2 x bf16 dense)",
+                    "traffic": None, "fp64_kernel": roof}
+            roof["frac"] = roof["achieved"] / roof["peak"]
 
     # ---- opt-in INT8 tensor-core path on a bounded sample (rank 0, one GPU), with its parity against `value`'s path ---
     int8 = None
-    if rank == 0 and world == 1 and lib.mgb_int8_available() and m_local >= 65536:
+    if rank == 0 and world == 1 and lib.mgb_int8_available() and m_local >= 65536 and not use_int8:
         int8 = posterior_int8_sample(gp, xc[: min(m_local, 2 * 1024 * 1024)], value)
 
     # ---- end to end through the host-buffer C-ABI call -------------------------------------------
@@ -232,6 +246,7 @@ def run_posterior(args, rank, world, local):
             "metric": "posterior_cands_per_sec", "value": value, "unit": "candidates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "posterior_path": args.posterior_path,
             "config": {"workload": "S^10 Riemannian Matern nu=2.5 kappa=0.5 T=10 exact-GP posterior mean/var, "
                                    "%d candidates x %d training points, candidate rows sharded over %d GPU(s); "
                                    "BASELINE.json configs[4]" % (m_total, n, world),
@@ -333,6 +348,8 @@ def posterior_e2e(args, gp, rank, world, local, m_total, m_local, n, xc, dist):
 
     lib = _lib.load()
     device = torch.device("cuda", local)
+    if gp.int8:
+        return posterior_e2e_int8(args, gp, rank, world, local, m_total, m_local, n, xc, dist)
     # every rank needs the fitted state on the host: rank 0 broadcasts, then all move it to pinned memory
     if world > 1:
         from materngabo_b200.posterior import ShardedPosterior
@@ -381,6 +398,33 @@ def posterior_e2e(args, gp, rank, world, local, m_total, m_local, n, xc, dist):
             "d2h_bytes_per_step": d2h, "steps": steps,
             "api": "mgb_series_posterior_host (C-ABI, pinned host buffers, per rank)",
             "sample_mean0": float(mean_h[0]), "timer": "host wall clock around the synchronous C-ABI call, max over ranks"}
+
+
+def posterior_e2e_int8(args, gp, rank, world, local, m_total, m_local, n, xc, dist):
+    """Same metric through ExactGPPosterior.posterior_host on the INT8 path: pinned HOST candidates in, HOST mean / var
+    out; the fitted state (sliced factor, alpha, training points) is already on every rank's device after step()."""
+    device = torch.device("cuda", local)
+    xc_h = xc.cpu().pin_memory()
+    mean_h = torch.empty(m_local, dtype=F64).pin_memory()
+    var_h = torch.empty(m_local, dtype=F64).pin_memory()
+    steps = max(1, min(args.steps, 2))
+    gp.posterior_host(xc_h[: min(m_local, 1 << 20)])          # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        gp.posterior_host(xc_h, mean_h, var_h)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=F64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t[0])
+    return {"value": m_total / (dt / steps), "unit": "candidates/s", "h2d_bytes_per_step": 8 * m_local * 11,
+            "d2h_bytes_per_step": 8 * 2 * m_local, "steps": steps,
+            "api": "ExactGPPosterior.posterior_host (INT8 path, pinned host buffers, per rank; fitted state resident on the device)",
+            "sample_mean0": float(mean_h[0]), "timer": "host wall clock around the synchronous call, max over ranks"}
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -213,10 +213,17 @@ class ExactGPPosterior:
     # ---- state exchange for the sharded path ---------------------------------------------------
     def state(self):
         """Tensors a peer rank needs to evaluate the posterior (what NCCL broadcasts after a fit)."""
-        return {"train": self.train_prepared, "packed": self._packed, "coef": self.coef}
+        st = {"train": self.train_prepared, "packed": self._packed, "coef": self.coef}
+        if self.int8:
+            self._ensure_packed_i8()
+            st["packed_i8"] = self._packed_i8
+            st["alpha"] = self.alpha
+        return st
 
-    def load_state(self, spec, train, packed, coef, kss_value):
+    def load_state(self, spec, train, packed, coef, kss_value, packed_i8=None, alpha=None):
         self.spec, self.train_prepared, self._packed, self.coef, self.kss_value = spec, train, packed, coef, kss_value
+        if packed_i8 is not None:
+            self._packed_i8, self.alpha = packed_i8, alpha
         return self
 
     # ---- candidates ----------------------------------------------------------------------------
@@ -256,6 +263,42 @@ class ExactGPPosterior:
         return mean, var
 
 
+    @torch.no_grad()
+    def posterior_host(self, x_host: torch.Tensor, mean_host: Optional[torch.Tensor] = None,
+                       var_host: Optional[torch.Tensor] = None, rows_per_copy: int = 1 << 20):
+        """``posterior`` for candidates in (pinned) HOST memory with the results returned to the host: rows are uploaded
+        in pieces on the current stream, evaluated by whichever path is selected (FP64 or INT8) and read back
+        asynchronously; one synchronisation at the end.  The C-ABI twin for the FP64 path is mgb_series_posterior_host."""
+        if x_host.is_cuda or x_host.dtype != F64 or x_host.dim() != 2:
+            raise RuntimeError("posterior_host expects a 2-D float64 host tensor")
+        m = x_host.shape[0]
+        mean_host = mean_host if mean_host is not None else torch.empty(m, dtype=F64).pin_memory()
+        var_host = var_host if var_host is not None else torch.empty(m, dtype=F64).pin_memory()
+        for c0 in range(0, m, rows_per_copy):
+            c1 = min(m, c0 + rows_per_copy)
+            xd = x_host[c0:c1].to(self.device, non_blocking=True)
+            mean, var = self.posterior(xd)
+            mean_host[c0:c1].copy_(mean, non_blocking=True)
+            var_host[c0:c1].copy_(var, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return mean_host, var_host
+
+    def _ensure_packed_i8(self):
+        """Sliced L^-1 of the INT8 path: cut from ``rinv`` on the rank that did the fit, received through ``load_state``
+        on its peers."""
+        if getattr(self, "alpha", None) is None:
+            raise RuntimeError("the INT8 path needs alpha (fit() locally, or load_state(..., packed_i8=, alpha=))")
+        if self._packed_i8 is not None:
+            return
+        if getattr(self, "rinv", None) is None:
+            raise RuntimeError("the INT8 path needs L^-1 of a local fit() or the sliced factor of a peer (load_state)")
+        lib = _lib.load()
+        n = self.rinv.shape[0]
+        self._packed_i8 = torch.empty(lib.mgb_posterior_int8_pack_bytes(n), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.mgb_posterior_int8_pack(_lib.ptr(self.rinv), n, self.rinv.stride(0), _lib.ptr(self._packed_i8),
+                                                   _lib.stream_ptr(self.device)), "mgb_posterior_int8_pack")
+
     def _posterior_int8(self, x, mean, var, chunk):
         """Opt-in INT8 tensor-core path (csrc/int8_posterior.cu): row-major float64 kernel rows from the Gram kernel,
         sliced into int8, seven int8 GEMMs against the sliced L^-1, recombined in float64.  ~1e-11 of max var."""
@@ -264,13 +307,7 @@ class ExactGPPosterior:
             raise _lib.MgbError("libmgb was built without the CUTLASS headers: the INT8 path is not available")
         m, n = x.shape[0], self.train_prepared.shape[0]
         st = _lib.stream_ptr(self.device)
-        if getattr(self, "rinv", None) is None or getattr(self, "alpha", None) is None:
-            raise RuntimeError("the INT8 path needs L^-1 and alpha of a local fit() (not a state loaded from a peer)")
-        if self._packed_i8 is None:
-            self._packed_i8 = torch.empty(lib.mgb_posterior_int8_pack_bytes(n), dtype=torch.uint8, device=self.device)
-            with torch.cuda.device(self.device):
-                _lib.check(lib.mgb_posterior_int8_pack(_lib.ptr(self.rinv), n, self.rinv.stride(0), _lib.ptr(self._packed_i8), st),
-                           "mgb_posterior_int8_pack")
+        self._ensure_packed_i8()
         chunk = min(INT8_CHUNK, (m + 255) // 256 * 256)
         need = lib.mgb_posterior_int8_workspace_bytes(chunk, n)
         if self._ws_i8 is None or self._ws_i8.numel() < need:

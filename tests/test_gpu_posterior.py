@@ -436,3 +436,23 @@ def test_int8_posterior_path_serves_the_quadrature_kernels_too():
     # empty block
     me, ve = fast.posterior(xc[:0])
     assert me.numel() == 0 and ve.numel() == 0
+
+
+@pytest.mark.parametrize("int8", [False, True])
+def test_posterior_host_matches_device_posterior(int8):
+    """Host-buffer call of the Python API (pinned candidates in, pinned mean / var out), both contraction paths."""
+    from materngabo_b200 import _lib, kernels_sphere
+    from materngabo_b200.posterior import ExactGPPosterior
+
+    if int8 and not _lib.load().mgb_int8_available():
+        pytest.skip("libmgb built without the CUTLASS headers")
+    gen = torch.Generator().manual_seed(3)
+    xt = torch.nn.functional.normalize(torch.randn(400, 4, generator=gen), dim=-1)
+    xc = torch.nn.functional.normalize(torch.randn(5000, 4, generator=gen), dim=-1)
+    y = torch.cos(2 * xt[:, 1])
+    k = kernels_sphere.SphereRiemannianMaternKernel(dim=3, nu=2.5).to(DEV)
+    gp = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), noise=1e-2, int8=int8).fit()
+    m0, v0 = gp.posterior(xc.to(DEV))
+    mh, vh = gp.posterior_host(xc.pin_memory(), rows_per_copy=1536)
+    assert not mh.is_cuda and mh.is_pinned()
+    assert torch.equal(mh, m0.cpu()) and torch.equal(vh, v0.cpu())
