@@ -7,7 +7,7 @@ magnitude) and cut into `s` signed slices of `bits` magnitude bits; the slice pr
 below 2^53), recombined in float64.  Only slice pairs with p + q <= s + 1 are formed (the rest is below the truncation
 error of the slicing itself).
 
-usage: python tools/ozaki_prototype.py [n_train] [n_cand]     (CPU only; imports the oracle - test infrastructure)
+usage: python tools/ozaki_prototype.py [n_train] [n_cand] [noise]     (CPU only; imports the oracle - test infrastructure)
 """
 import os
 import sys
@@ -56,14 +56,14 @@ def sliced_product(a, b, s, bits):
     return acc * ea * eb.T, gemms, peak
 
 
-def main(n=1000, m=512):
+def main(n=1000, m=512, noise=1e-2):
     gen = torch.Generator().manual_seed(0)
     xt = torch.nn.functional.normalize(torch.randn(n, 11, generator=gen), dim=-1)
     xc = torch.nn.functional.normalize(torch.randn(m, 11, generator=gen), dim=-1)
     xc[: m // 4] = torch.nn.functional.normalize(xt[: m // 4] + 1e-3 * torch.randn(m // 4, 11, generator=gen), dim=-1)
     k = R.sphere_matern(xt, xt, 10, 2.5, 0.5).numpy()
     ks = R.sphere_matern(xc, xt, 10, 2.5, 0.5).numpy()
-    L = np.linalg.cholesky(k + 1e-2 * np.eye(n))
+    L = np.linalg.cholesky(k + noise * np.eye(n))
     rinv = np.linalg.solve(L, np.eye(n))     # lower triangular
     # reference in extended precision
     v_ref = ks.astype(np.longdouble) @ rinv.T.astype(np.longdouble)
@@ -71,8 +71,8 @@ def main(n=1000, m=512):
     v64 = ks @ rinv.T
     var64 = 1.0 - (v64 * v64).sum(1)
     scale = np.abs(var_ref).max()
-    print("n = %d training points, m = %d candidates (a quarter of them 1e-3 from a training point); min var %.3e"
-          % (n, m, var_ref.min()))
+    print("n = %d training points, m = %d candidates (a quarter of them 1e-3 from a training point), noise %.1e; min var %.3e, max |L^-1| %.2e"
+          % (n, m, noise, var_ref.min(), np.abs(rinv).max()))
     print("float64 BLAS:                      max |var - ref| / max|var| = %.2e" % (np.abs(var64 - var_ref).max() / scale))
     global ROUND
     for ROUND in (False, True):
@@ -86,4 +86,4 @@ def main(n=1000, m=512):
 
 
 if __name__ == "__main__":
-    main(*(int(a) for a in sys.argv[1:3]))
+    main(*(int(a) for a in sys.argv[1:3]), *(float(a) for a in sys.argv[3:4]))
