@@ -240,7 +240,8 @@ int mgb_series_gram_tiled(const mgb_series_desc* desc, const double* x1, long lo
                           void* stream);
 /* row-major K (m x n) -> the tiled layout (Gram matrices of the quadrature kernels, which write row-major) */
 int mgb_posterior_retile(const double* K, long long m, long long n, long long ldk, double* Kb, void* stream);
-/* bytes of scratch mgb_posterior_reduce needs for m candidates (0 when one CTA per candidate tile suffices) */
+/* bytes of scratch that suffice for mgb_posterior_reduce on ANY block of at most m candidates (a chunked caller sizes it
+ * once for its chunk and reuses it for the shorter tail block, which needs more splits per candidate tile) */
 long long mgb_posterior_reduce_workspace_bytes(long long m, long long n);
 int mgb_posterior_reduce(const double* Kb, long long m, long long n, const double* packed, const double* kss,
                          double mean_const, double* mean, double* var, void* workspace,

@@ -14,6 +14,7 @@ import torch
 from . import build as _build
 
 MGB_OK = 0
+MGB_VERSION = 200      # must equal mgb_version() (csrc/runtime.cu): bumped whenever a signature changes
 BASIS_MONOMIAL = 0
 BASIS_CHEBYSHEV = 1
 MAX_FACTORS = 16
@@ -111,14 +112,14 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not os.path.exists(path):
-        path = _build.build()
+    path = _build.build()       # no-op when the content digest of sources + flags matches the stamp
     lib = C.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
+    if lib.mgb_version() != MGB_VERSION:
+        raise MgbError("libmgb.so reports version %d, the Python binding expects %d (stale build?)" % (lib.mgb_version(), MGB_VERSION))
     _lib = lib
     return lib
 

@@ -61,8 +61,9 @@ def _series_bwd_raw(spec, x1, x2, coef, g, want_coef, want_x1, want_x2):
     m, n = x1.shape[0], x2.shape[0]
     dwidth = spec.n_factors * spec.factor_width
     gcoef = torch.zeros_like(coef) if want_coef else None
-    gx1 = torch.empty((m, dwidth), dtype=F64, device=x1.device) if want_x1 else None
-    gx2 = torch.empty((n, dwidth), dtype=F64, device=x1.device) if want_x2 else None
+    # zeros, not empty: the library returns early for an empty opposite block without writing the outputs
+    gx1 = torch.zeros((m, dwidth), dtype=F64, device=x1.device) if want_x1 else None
+    gx2 = torch.zeros((n, dwidth), dtype=F64, device=x1.device) if want_x2 else None
     d = spec.desc(coef.shape[-1])
     with torch.cuda.device(x1.device):
         rc = lib.mgb_series_gram_bwd(C.byref(d), _lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0),
@@ -76,8 +77,8 @@ def _series_dx_raw(spec, order, x1, x2, coef, g, want1, want2):
     lib = _lib.load()
     m, n = x1.shape[0], x2.shape[0]
     dwidth = spec.n_factors * spec.factor_width
-    o1 = torch.empty((m, dwidth), dtype=F64, device=x1.device) if want1 else None
-    o2 = torch.empty((n, dwidth), dtype=F64, device=x1.device) if want2 else None
+    o1 = torch.zeros((m, dwidth), dtype=F64, device=x1.device) if want1 else None
+    o2 = torch.zeros((n, dwidth), dtype=F64, device=x1.device) if want2 else None
     d = spec.desc(coef.shape[-1])
     with torch.cuda.device(x1.device):
         rc = lib.mgb_series_gram_dx(C.byref(d), order, _lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0),
@@ -108,6 +109,10 @@ class SeriesGramGradX(torch.autograd.Function):
         x1, x2, coef, g = ctx.saved_tensors
         if spec.n_factors != 1:
             raise NotImplementedError("second-order input gradients are implemented for single-factor kernels")
+        if ctx.needs_input_grad[2]:
+            # silently returning None here would drop terms of a Hessian-vector product (e.g. k(x, x) with x1 aliasing x2)
+            raise NotImplementedError("second-order gradients are provided with respect to x1 and G only "
+                                      "(x2 = the training points, constants of the acquisition path); detach x2")
         if v1 is None or v1.dim() != 2:
             return (None,) * 8
         v1 = v1.contiguous()

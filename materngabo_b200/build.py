@@ -55,7 +55,7 @@ def _source_digest() -> str:
         h.update(os.path.basename(d).encode())
         with open(d, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    h.update(" ".join(NVCC_FLAGS + SOURCES + _cutlass_flags()).encode())
     return h.hexdigest()
 
 

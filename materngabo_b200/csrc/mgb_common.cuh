@@ -27,6 +27,19 @@ inline int after_launch(const char* what) {
   return check_cuda(cudaGetLastError(), what);
 }
 
+// SM count of the CURRENT device, cached per device (a process may drive several GPUs through the _host entry points)
+inline int device_sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 #define MGB_TRY(expr)                 \
   do {                                \
     int _rc = (expr);                 \

@@ -391,31 +391,26 @@ extern "C" int mgb_posterior_pack(const double* Rinv, long long n, long long ldr
   return after_launch("posterior_pack_kernel");
 }
 
-static int g_post_sms = 0;
-static int post_sm_count() {
-  if (g_post_sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_post_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      g_post_sms = 148;
-  }
-  return g_post_sms;
-}
+static int post_sm_count() { return device_sm_count(); }
 
 // How many CTAs share one 128-candidate tile.  (a) Few candidates: split so that the grid fills the SMs.
 // (b) Many: the 128 x n Gram panel of a candidate tile is re-read once per row tile; CTAs working on the SAME
 // panel at the same time share it through L2, so enough splits are used that the panels of all concurrently
 // resident CTAs fit in a ~40 MB slice of the 126 MB L2 (the factor streams through the rest).
+static double post_l2_mb() {   // MGB_POST_L2MB: tuning knob for the L2 slice the in-flight Gram panels may occupy
+  static double l2_mb = 0.0;
+  if (l2_mb == 0.0) {
+    const char* e = getenv("MGB_POST_L2MB");
+    l2_mb = (e != nullptr && atof(e) > 0.0) ? atof(e) : 40.0;
+  }
+  return l2_mb;
+}
 static int choose_splits(long long m, long long n) {
   const int sms = post_sm_count();
   const long long ctiles = (m + PT - 1) / PT;
   const int n_tiles = (int)(round_up(n + 1, PT) / PT);
   const double panel_bytes = (double)PT * (double)round_up(n, PK) * 8.0;  // one candidate tile's Gram panel
-  static double l2_mb = 0.0;   // MGB_POST_L2MB: tuning knob for the L2 slice the in-flight Gram panels may occupy
-  if (l2_mb == 0.0) {
-    const char* e = getenv("MGB_POST_L2MB");
-    l2_mb = (e != nullptr && atof(e) > 0.0) ? atof(e) : 40.0;
-  }
-  long long s_l2 = (long long)ceil(sms * panel_bytes / (l2_mb * 1024 * 1024));
+  long long s_l2 = (long long)ceil(sms * panel_bytes / (post_l2_mb() * 1024 * 1024));
   long long s_fill = (2LL * sms + ctiles - 1) / ctiles;
   long long s = s_l2 > s_fill ? s_l2 : s_fill;
   if (s < 1) s = 1;
@@ -433,10 +428,18 @@ extern "C" int mgb_posterior_retile(const double* K, long long m, long long n, l
   return after_launch("posterior_retile_kernel");
 }
 
+// Upper bound of splits(mc, n) * mc over every block size mc <= m: a workspace sized for `m` candidates also serves the
+// shorter tail block of a chunked evaluation (fewer candidate tiles -> MORE splits per tile).  splits = max(s_l2,
+// s_fill(mc)) clipped to n_tiles; s_l2 does not depend on mc and s_fill(mc) * mc <= (2 sms + ctiles(mc)) * 128.
 extern "C" long long mgb_posterior_reduce_workspace_bytes(long long m, long long n) {
   if (m <= 0 || n <= 0) return 0;
-  const int s = choose_splits(m, n);
-  return s > 1 ? (long long)s * m * (long long)sizeof(double) : 0;
+  const long long m_pad = round_up(m, PT), ctiles = m_pad / PT;
+  const long long n_tiles = round_up(n + 1, PT) / PT;
+  const double panel_bytes = (double)PT * (double)round_up(n, PK) * 8.0;
+  const long long s_l2 = (long long)ceil(post_sm_count() * panel_bytes / (post_l2_mb() * 1024 * 1024));
+  long long doubles = (s_l2 > 1 ? s_l2 : 1) * m_pad + (2LL * post_sm_count() + ctiles) * PT;
+  if (doubles > n_tiles * m_pad) doubles = n_tiles * m_pad;
+  return doubles * (long long)sizeof(double);
 }
 
 extern "C" int mgb_posterior_reduce(const double* Kb, long long m, long long n, const double* packed,
@@ -447,12 +450,9 @@ extern "C" int mgb_posterior_reduce(const double* Kb, long long m, long long n, 
   if (reinterpret_cast<uintptr_t>(Kb) & 15u) return fail(MGB_ERR_ARG, "posterior_reduce: Kb must be 16-byte aligned");
   if (m == 0) return MGB_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MGB_TRY(check_cuda(cudaFuncSetAttribute(posterior_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)kPostSmem), "cudaFuncSetAttribute"));
-    attr_set = true;
-  }
+  // per device, not per process: set on every call (cheap, legal during stream capture)
+  MGB_TRY(check_cuda(cudaFuncSetAttribute(posterior_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kPostSmem), "cudaFuncSetAttribute"));
   PostParams p;
   p.Kb = Kb; p.m = m; p.n = n;
   p.Rp = packed; p.rows_p = round_up(n + 1, PT); p.ldp = round_up(n, PK);

@@ -1063,15 +1063,7 @@ static size_t spd2_lattice2_smem(int Pb, int nk) {
 }
 
 // ------------------------------------------------------------------------------------------------
-static int g_sms = 0;
-static int sm_count() {
-  if (g_sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_sms = 148;
-  }
-  return g_sms;
-}
+static int sm_count() { return device_sm_count(); }
 
 // MGB_H2_PATH=generic keeps the two-entries-per-iteration kernel for the forward Gram as well (A/B measurements, tests)
 static bool hyp_force_generic() {

@@ -1046,15 +1046,7 @@ extern "C" int mgb_so3_to_quaternion(const double* R, long long m, long long ld,
   return after_launch("so3_quat_kernel");
 }
 
-static int series_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      sms = 148;
-  }
-  return sms;
-}
+static int series_sm_count() { return device_sm_count(); }
 
 static int series_fwd_impl(const mgb_series_desc* d, const double* x1, long long m, long long ld1, const double* x2,
                            long long n, long long ld2, const double* coef, double* K, long long ldk, int tiled,

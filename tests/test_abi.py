@@ -26,7 +26,7 @@ def test_header_symbols_are_exported_and_typed():
 
 def test_loader_and_version():
     lib = _lib.load()
-    assert lib.mgb_version() == 116
+    assert lib.mgb_version() == _lib.MGB_VERSION
     assert lib.mgb_launch_count() >= 0
     assert lib.mgb_posterior_pack_bytes(5000) == 5120 * 5008 * 8
     assert lib.mgb_posterior_workspace_bytes(128, 100) == (128 * 112 + 128) * 8 + lib.mgb_posterior_reduce_workspace_bytes(128, 100)
