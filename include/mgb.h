@@ -425,6 +425,37 @@ int mgb_series_posterior_host(const mgb_series_desc* desc, const double* xc, lon
                               double* var, long long chunk, int device);
 
 /* ------------------------------------------------------------------------------------------------
+ * Persistent posterior handle.  The reference fits once per BO iteration and then calls acq(X) hundreds of times
+ * (manifold_optimization/manifold_optimize.py:229-236 trust-region restarts, :329-339 initial-condition scoring;
+ * gpytorch keeps the Cholesky / root-inverse caches of its prediction strategy between those calls).  The handle is
+ * that cache: the fitted state is uploaded and packed ONCE, and every evaluation reuses the handle's device buffers,
+ * workspace, pinned staging block, streams and events - no allocation and no factor upload per call.
+ *   mgb_posterior_create             host pointers (Rinv: n x n row-major, lower triangle used; alpha: n); synchronises
+ *   mgb_posterior_create_from_device device pointers that the CALLER keeps alive (e.g. the packed factor received
+ *                                    over NCCL / NVLink from the rank that did the fit: no PCIe upload per rank);
+ *                                    packed = output of mgb_posterior_pack
+ *   mgb_posterior_eval_host          host candidates (m x D, row-major, dense) -> host mean / var; synchronous.
+ *                                    m <= 8192: one pinned staging block, one stream, one synchronisation (latency);
+ *                                    larger: blocks of mgb_posterior_chunk(h) rows, uploads / kernels / downloads on
+ *                                    three streams (throughput; pinned user buffers make the copies asynchronous)
+ *   mgb_posterior_eval_device        device candidates -> device mean / var on `stream`; never allocates / synchronises
+ *   mgb_posterior_destroy            releases everything the handle owns (NULL is allowed)
+ * max_chunk <= 0: default 37888 candidates per block.  A handle is bound to `device` and is not thread-safe.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct mgb_posterior mgb_posterior;
+int mgb_posterior_create(const mgb_series_desc* desc, const double* xtrain, long long n, const double* coef,
+                         const double* Rinv, const double* alpha, double kss_value, double mean_const,
+                         long long max_chunk, int device, mgb_posterior** out);
+int mgb_posterior_create_from_device(const mgb_series_desc* desc, const double* xtrain_dev, long long n, long long ldt,
+                                     const double* coef_dev, const double* packed_dev, double kss_value,
+                                     double mean_const, long long max_chunk, int device, mgb_posterior** out);
+long long mgb_posterior_chunk(const mgb_posterior* h);
+int mgb_posterior_eval_host(mgb_posterior* h, const double* xc, long long m, double* mean, double* var);
+int mgb_posterior_eval_device(mgb_posterior* h, const double* xc_dev, long long m, long long ldc, double* mean_dev,
+                              double* var_dev, void* stream);
+int mgb_posterior_destroy(mgb_posterior* h);
+
+/* ------------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): register-resident FP64 peak micro-benchmarks, result in TFLOP/s.
  * kind 0 = DFMA chains, 1 = DMMA m8n8k4 chains, 2 = both interleaved with equal FMA counts (do the two
  * instruction kinds share one FP64 data path?).  Synchronises.

@@ -93,6 +93,12 @@ PROTOTYPES = {
     "mgb_matern_t_weights": (_I, [_P, _P, _P, _I, _D, _P, _P, _P, _P, _P]),
     "mgb_series_gram_host": (_I, [_DESC, _P, _LL, _P, _LL, _P, _P, _I]),
     "mgb_series_posterior_host": (_I, [_DESC, _P, _LL, _P, _LL, _P, _P, _P, _D, _D, _P, _P, _LL, _I]),
+    "mgb_posterior_create": (_I, [_DESC, _P, _LL, _P, _P, _P, _D, _D, _LL, _I, C.POINTER(_P)]),
+    "mgb_posterior_create_from_device": (_I, [_DESC, _P, _LL, _LL, _P, _P, _D, _D, _LL, _I, C.POINTER(_P)]),
+    "mgb_posterior_chunk": (_LL, [_P]),
+    "mgb_posterior_eval_host": (_I, [_P, _P, _LL, _P, _P]),
+    "mgb_posterior_eval_device": (_I, [_P, _P, _LL, _LL, _P, _P, _P]),
+    "mgb_posterior_destroy": (_I, [_P]),
     "mgb_fp64_peak": (_I, [_I, _I, C.POINTER(_D), C.POINTER(_D)]),
 }
 

@@ -3,6 +3,8 @@
 // device entry points as the torch-side bindings.  Candidate rows are double-buffered: the copy stream
 // uploads block b+1 and downloads results of block b-1 while the compute stream works on block b.
 #include "mgb_common.cuh"
+#include <cstring>
+#include <new>
 #include <vector>
 
 namespace mgb {
@@ -151,6 +153,223 @@ extern "C" int mgb_series_posterior_host(const mgb_series_desc* desc, const doub
   }
   MGB_TRY(check_cuda(cudaStreamSynchronize(st.compute), "cudaStreamSynchronize"));
   return check_cuda(cudaStreamSynchronize(st.copy), "cudaStreamSynchronize");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent posterior handle (mgb.h): the fitted state (training points, coefficients, packed factor) is uploaded and
+// packed ONCE; every evaluation reuses the device buffers, workspace, streams and events of the handle.  This is the
+// call pattern of the reference: one fit per BO iteration, then hundreds of acq(X) calls (manifold_optimize.py:229-236,
+// 329-339).
+// ------------------------------------------------------------------------------------------------
+struct mgb_posterior {
+  int device = 0;
+  mgb_series_desc desc{};
+  long long n = 0, D = 0, T = 0, chunk = 0;
+  double kss = 0.0, mean_const = 0.0;
+  bool owns_state = false;
+  double *d_xt = nullptr, *d_coef = nullptr, *d_pack = nullptr;   // owned (create) or borrowed (create_from_device)
+  long long ldt = 0;
+  double* d_xc[2] = {nullptr, nullptr};
+  double* d_out[2] = {nullptr, nullptr};    // [mean chunk | var chunk]
+  void* d_ws = nullptr;
+  long long ws_bytes = 0;
+  double* h_stage = nullptr;                // pinned: small blocks from pageable user memory go through it
+  long long stage_rows = 0;
+  cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
+  cudaEvent_t up[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, down[2] = {nullptr, nullptr};
+};
+
+namespace mgb {
+static void posterior_release(mgb_posterior* h) {
+  if (!h) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(h->device);
+  if (h->compute) cudaStreamSynchronize(h->compute);
+  if (h->h2d) cudaStreamSynchronize(h->h2d);
+  if (h->d2h) cudaStreamSynchronize(h->d2h);
+  if (h->owns_state) {
+    cudaFree(h->d_xt);
+    cudaFree(h->d_coef);
+    cudaFree(h->d_pack);
+  }
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(h->d_xc[b]);
+    cudaFree(h->d_out[b]);
+    if (h->up[b]) cudaEventDestroy(h->up[b]);
+    if (h->done[b]) cudaEventDestroy(h->done[b]);
+    if (h->down[b]) cudaEventDestroy(h->down[b]);
+  }
+  cudaFree(h->d_ws);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->compute) cudaStreamDestroy(h->compute);
+  if (h->h2d) cudaStreamDestroy(h->h2d);
+  if (h->d2h) cudaStreamDestroy(h->d2h);
+  cudaSetDevice(prev);
+  delete h;
+}
+
+static int dev_alloc(double** p, size_t doubles) {
+  return check_cuda(cudaMalloc(reinterpret_cast<void**>(p), sizeof(double) * (doubles ? doubles : 2)), "cudaMalloc");
+}
+
+// buffers every handle needs, whatever the origin of its state
+static int posterior_common_init(mgb_posterior* h, long long max_chunk) {
+  long long chunk = max_chunk > 0 ? max_chunk : 37888;     // 2 waves of 128-candidate tiles on 148 SMs
+  chunk = (chunk + 127) / 128 * 128;
+  h->chunk = chunk;
+  for (int b = 0; b < 2; ++b) {
+    MGB_TRY(dev_alloc(&h->d_xc[b], (size_t)(chunk * h->D)));
+    MGB_TRY(dev_alloc(&h->d_out[b], (size_t)(2 * chunk)));
+    MGB_TRY(check_cuda(cudaEventCreateWithFlags(&h->up[b], cudaEventDisableTiming), "cudaEventCreate"));
+    MGB_TRY(check_cuda(cudaEventCreateWithFlags(&h->done[b], cudaEventDisableTiming), "cudaEventCreate"));
+    MGB_TRY(check_cuda(cudaEventCreateWithFlags(&h->down[b], cudaEventDisableTiming), "cudaEventCreate"));
+  }
+  h->ws_bytes = mgb_posterior_workspace_bytes(chunk, h->n);
+  MGB_TRY(check_cuda(cudaMalloc(&h->d_ws, (size_t)h->ws_bytes), "cudaMalloc"));
+  h->stage_rows = chunk < 8192 ? chunk : 8192;
+  MGB_TRY(check_cuda(cudaHostAlloc(reinterpret_cast<void**>(&h->h_stage), sizeof(double) * (size_t)(h->stage_rows * (h->D + 2)),
+                                   cudaHostAllocDefault), "cudaHostAlloc"));
+  MGB_TRY(check_cuda(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking), "cudaStreamCreate"));
+  MGB_TRY(check_cuda(cudaStreamCreateWithFlags(&h->h2d, cudaStreamNonBlocking), "cudaStreamCreate"));
+  return check_cuda(cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking), "cudaStreamCreate");
+}
+}  // namespace mgb
+
+extern "C" int mgb_posterior_create(const mgb_series_desc* desc, const double* xtrain, long long n, const double* coef,
+                                    const double* Rinv, const double* alpha, double kss_value, double mean_const,
+                                    long long max_chunk, int device, mgb_posterior** out) {
+  if (!desc || !xtrain || !coef || !Rinv || !alpha || !out || n < 1) return fail(MGB_ERR_ARG, "posterior_create: bad argument");
+  *out = nullptr;
+  MGB_TRY(select_device(device));
+  mgb_posterior* h = new (std::nothrow) mgb_posterior();
+  if (!h) return fail(MGB_ERR_ARG, "posterior_create: out of host memory");
+  h->device = device; h->desc = *desc; h->n = n;
+  h->D = (long long)desc->n_factors * desc->factor_width;
+  h->T = (long long)desc->n_factors * desc->n_terms;
+  h->ldt = h->D; h->kss = kss_value; h->mean_const = mean_const; h->owns_state = true;
+  int rc = MGB_OK;
+  double* d_R = nullptr;
+  double* d_alpha = nullptr;
+  do {
+    if ((rc = posterior_common_init(h, max_chunk)) != MGB_OK) break;
+    if ((rc = dev_alloc(&h->d_xt, (size_t)(n * h->D))) != MGB_OK) break;
+    if ((rc = dev_alloc(&h->d_coef, (size_t)h->T)) != MGB_OK) break;
+    if ((rc = check_cuda(cudaMalloc(reinterpret_cast<void**>(&h->d_pack), (size_t)mgb_posterior_pack_bytes(n)), "cudaMalloc")) != MGB_OK) break;
+    if ((rc = dev_alloc(&d_R, (size_t)(n * n))) != MGB_OK) break;
+    if ((rc = dev_alloc(&d_alpha, (size_t)n)) != MGB_OK) break;
+    cudaStream_t s = h->compute;
+    if ((rc = check_cuda(cudaMemcpyAsync(h->d_xt, xtrain, sizeof(double) * n * h->D, cudaMemcpyHostToDevice, s), "H2D xtrain")) != MGB_OK) break;
+    if ((rc = check_cuda(cudaMemcpyAsync(h->d_coef, coef, sizeof(double) * h->T, cudaMemcpyHostToDevice, s), "H2D coef")) != MGB_OK) break;
+    if ((rc = check_cuda(cudaMemcpyAsync(d_R, Rinv, sizeof(double) * n * n, cudaMemcpyHostToDevice, s), "H2D Rinv")) != MGB_OK) break;
+    if ((rc = check_cuda(cudaMemcpyAsync(d_alpha, alpha, sizeof(double) * n, cudaMemcpyHostToDevice, s), "H2D alpha")) != MGB_OK) break;
+    if ((rc = mgb_posterior_pack(d_R, n, n, d_alpha, h->d_pack, s)) != MGB_OK) break;
+    rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  } while (0);
+  cudaFree(d_R);
+  cudaFree(d_alpha);
+  if (rc != MGB_OK) {
+    posterior_release(h);
+    return rc;
+  }
+  *out = h;
+  return MGB_OK;
+}
+
+extern "C" int mgb_posterior_create_from_device(const mgb_series_desc* desc, const double* xtrain_dev, long long n,
+                                                long long ldt, const double* coef_dev, const double* packed_dev,
+                                                double kss_value, double mean_const, long long max_chunk, int device,
+                                                mgb_posterior** out) {
+  if (!desc || !xtrain_dev || !coef_dev || !packed_dev || !out || n < 1) return fail(MGB_ERR_ARG, "posterior_create_from_device: bad argument");
+  *out = nullptr;
+  MGB_TRY(select_device(device));
+  mgb_posterior* h = new (std::nothrow) mgb_posterior();
+  if (!h) return fail(MGB_ERR_ARG, "posterior_create_from_device: out of host memory");
+  h->device = device; h->desc = *desc; h->n = n;
+  h->D = (long long)desc->n_factors * desc->factor_width;
+  h->T = (long long)desc->n_factors * desc->n_terms;
+  if (ldt < h->D) { delete h; return fail(MGB_ERR_ARG, "posterior_create_from_device: ldt smaller than the row width"); }
+  h->ldt = ldt; h->kss = kss_value; h->mean_const = mean_const; h->owns_state = false;
+  h->d_xt = const_cast<double*>(xtrain_dev);
+  h->d_coef = const_cast<double*>(coef_dev);
+  h->d_pack = const_cast<double*>(packed_dev);
+  const int rc = posterior_common_init(h, max_chunk);
+  if (rc != MGB_OK) {
+    posterior_release(h);
+    return rc;
+  }
+  *out = h;
+  return MGB_OK;
+}
+
+extern "C" int mgb_posterior_destroy(mgb_posterior* h) {
+  posterior_release(h);
+  return MGB_OK;
+}
+
+extern "C" long long mgb_posterior_chunk(const mgb_posterior* h) { return h ? h->chunk : 0; }
+
+extern "C" int mgb_posterior_eval_device(mgb_posterior* h, const double* xc_dev, long long m, long long ldc,
+                                         double* mean_dev, double* var_dev, void* stream) {
+  if (!h || !xc_dev || !mean_dev || !var_dev || m < 0 || ldc < h->D) return fail(MGB_ERR_ARG, "posterior_eval_device: bad argument");
+  if (m == 0) return MGB_OK;
+  const long long chunk = m < h->chunk ? (m + 127) / 128 * 128 : h->chunk;
+  return mgb_series_posterior(&h->desc, xc_dev, m, ldc, h->d_xt, h->n, h->ldt, h->d_coef, h->d_pack, h->kss, h->mean_const,
+                              mean_dev, var_dev, h->d_ws, h->ws_bytes, chunk, stream);
+}
+
+extern "C" int mgb_posterior_eval_host(mgb_posterior* h, const double* xc, long long m, double* mean, double* var) {
+  if (!h || !xc || !mean || !var || m < 0) return fail(MGB_ERR_ARG, "posterior_eval_host: bad argument");
+  if (m == 0) return MGB_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  MGB_TRY(check_cuda(cudaSetDevice(h->device), "cudaSetDevice"));
+  struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
+  const long long D = h->D;
+  if (m <= h->stage_rows) {
+    // latency path (the reference's acq(X) calls: b = 1 ... a few hundred): one pinned staging block, one stream,
+    // one synchronisation; pageable user memory never meets the DMA engine
+    double* st_x = h->h_stage;
+    double* st_out = h->h_stage + h->stage_rows * D;
+    memcpy(st_x, xc, sizeof(double) * (size_t)(m * D));
+    cudaStream_t s = h->compute;
+    MGB_TRY(check_cuda(cudaMemcpyAsync(h->d_xc[0], st_x, sizeof(double) * m * D, cudaMemcpyHostToDevice, s), "H2D xc"));
+    MGB_TRY(mgb_posterior_eval_device(h, h->d_xc[0], m, D, h->d_out[0], h->d_out[0] + m, s));
+    MGB_TRY(check_cuda(cudaMemcpyAsync(st_out, h->d_out[0], sizeof(double) * 2 * m, cudaMemcpyDeviceToHost, s), "D2H mean/var"));
+    MGB_TRY(check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize"));
+    memcpy(mean, st_out, sizeof(double) * (size_t)m);
+    memcpy(var, st_out + m, sizeof(double) * (size_t)m);
+    return MGB_OK;
+  }
+  // throughput path: blocks of `chunk` rows, uploads / kernels / downloads on three streams, two buffers in flight
+  const long long chunk = h->chunk;
+  const long long nblk = (m + chunk - 1) / chunk;
+  auto rows_of = [&](long long blk) { const long long c0 = blk * chunk; return (m - c0 < chunk) ? (m - c0) : chunk; };
+  auto upload = [&](long long blk) -> int {
+    const int buf = (int)(blk & 1);
+    if (blk >= 2) MGB_TRY(check_cuda(cudaStreamWaitEvent(h->h2d, h->done[buf], 0), "cudaStreamWaitEvent"));  // kernels of blk-2 read it
+    MGB_TRY(check_cuda(cudaMemcpyAsync(h->d_xc[buf], xc + blk * chunk * D, sizeof(double) * rows_of(blk) * D,
+                                       cudaMemcpyHostToDevice, h->h2d), "H2D xc"));
+    return check_cuda(cudaEventRecord(h->up[buf], h->h2d), "cudaEventRecord");
+  };
+  MGB_TRY(upload(0));
+  for (long long blk = 0; blk < nblk; ++blk) {
+    const long long c0 = blk * chunk, rows = rows_of(blk);
+    const int buf = (int)(blk & 1);
+    MGB_TRY(check_cuda(cudaStreamWaitEvent(h->compute, h->up[buf], 0), "cudaStreamWaitEvent"));
+    if (blk >= 2) MGB_TRY(check_cuda(cudaStreamWaitEvent(h->compute, h->down[buf], 0), "cudaStreamWaitEvent"));  // results of blk-2 left
+    MGB_TRY(mgb_series_posterior(&h->desc, h->d_xc[buf], rows, D, h->d_xt, h->n, h->ldt, h->d_coef, h->d_pack, h->kss,
+                                 h->mean_const, h->d_out[buf], h->d_out[buf] + chunk, h->d_ws, h->ws_bytes, chunk, h->compute));
+    MGB_TRY(check_cuda(cudaEventRecord(h->done[buf], h->compute), "cudaEventRecord"));
+    if (blk + 1 < nblk) MGB_TRY(upload(blk + 1));
+    MGB_TRY(check_cuda(cudaStreamWaitEvent(h->d2h, h->done[buf], 0), "cudaStreamWaitEvent"));
+    MGB_TRY(check_cuda(cudaMemcpyAsync(mean + c0, h->d_out[buf], sizeof(double) * rows, cudaMemcpyDeviceToHost, h->d2h), "D2H mean"));
+    MGB_TRY(check_cuda(cudaMemcpyAsync(var + c0, h->d_out[buf] + chunk, sizeof(double) * rows, cudaMemcpyDeviceToHost, h->d2h), "D2H var"));
+    MGB_TRY(check_cuda(cudaEventRecord(h->down[buf], h->d2h), "cudaEventRecord"));
+  }
+  MGB_TRY(check_cuda(cudaStreamSynchronize(h->compute), "cudaStreamSynchronize"));
+  MGB_TRY(check_cuda(cudaStreamSynchronize(h->h2d), "cudaStreamSynchronize"));
+  return check_cuda(cudaStreamSynchronize(h->d2h), "cudaStreamSynchronize");
 }
 
 // ------------------------------------------------------------------------------------------------

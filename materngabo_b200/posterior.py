@@ -283,6 +283,19 @@ class ExactGPPosterior:
         torch.cuda.current_stream(self.device).synchronize()
         return mean_host, var_host
 
+    def handle(self, max_chunk: int = 0) -> "PosteriorHandle":
+        """Persistent C-ABI handle over the fitted state (no upload, no allocation per evaluation)."""
+        return PosteriorHandle(self, max_chunk)
+
+    @classmethod
+    def from_model(cls, model, **kwargs):
+        """Fitted SingleTaskGP-like model (covar_module[.base_kernel, .outputscale], likelihood.noise,
+        mean_module.constant, train_inputs, train_targets; bo_sphere.py:211-233) -> fitted ExactGPPosterior."""
+        from .botorch_adapter import FusedExactGP
+
+        kernel, x, y, s, noise, mean_const = FusedExactGP.read_model(model)
+        return cls(kernel, x, y, outputscale=s, noise=noise, mean_const=mean_const, **kwargs).fit()
+
     def _ensure_packed_i8(self):
         """Sliced L^-1 of the INT8 path: cut from ``rinv`` on the rank that did the fit, received through ``load_state``
         on its peers."""
@@ -518,6 +531,81 @@ class ExactGPPosterior:
         _lib.check(rc, "mgb_radial_acquisition_ei_step")
         return ei.reshape(shape[:-1] if x.dim() == 2 else shape[:-2]), grad.reshape(shape), \
             (hvp.reshape(shape) if hvp is not None else None)
+
+
+class PosteriorHandle:
+    """Persistent C-ABI handle (include/mgb.h: mgb_posterior_create* / _eval_host / _eval_device / _destroy) over a
+    fitted series-kernel posterior.  The handle borrows the device tensors of the ExactGPPosterior it was made from
+    (kept alive here); evaluations reuse its device buffers, workspace, pinned staging block and streams."""
+
+    def __init__(self, gp: "ExactGPPosterior", max_chunk: int = 0):
+        if not gp.is_series or gp._packed is None:
+            raise RuntimeError("PosteriorHandle: fit() a series-kernel posterior first")
+        lib = _lib.load()
+        self._lib = lib
+        self._keep = (gp.train_prepared, gp.coef, gp._packed)
+        self.device = gp.device
+        self.n = gp.train_prepared.shape[0]
+        self.width = gp.train_prepared.shape[1]
+        d = gp.spec.desc(gp.coef.shape[-1])
+        h = C.c_void_p()
+        index = gp.device.index if gp.device.index is not None else torch.cuda.current_device()
+        torch.cuda.current_stream(gp.device).synchronize()      # the state was produced on torch's stream
+        rc = lib.mgb_posterior_create_from_device(C.byref(d), _lib.ptr(gp.train_prepared), self.n, gp.train_prepared.stride(0),
+                                                  _lib.ptr(gp.coef), _lib.ptr(gp._packed), float(gp.kss_value),
+                                                  float(gp.mean_const), int(max_chunk), int(index), C.byref(h))
+        _lib.check(rc, "mgb_posterior_create_from_device")
+        self._h = h
+
+    @property
+    def chunk(self) -> int:
+        return int(self._lib.mgb_posterior_chunk(self._h))
+
+    def eval_host(self, x_host, mean_host=None, var_host=None):
+        """x_host: (m, D) float64 CPU tensor or numpy array (pinned memory makes the large-m copies asynchronous)."""
+        if self._h is None:
+            raise RuntimeError("handle destroyed")
+        x = torch.as_tensor(x_host)
+        if x.is_cuda or x.dtype != F64 or x.dim() != 2 or x.shape[1] != self.width or not x.is_contiguous():
+            raise ValueError("eval_host expects a contiguous (m, %d) float64 host array" % self.width)
+        m = x.shape[0]
+        mean = mean_host if mean_host is not None else torch.empty(m, dtype=F64)
+        var = var_host if var_host is not None else torch.empty(m, dtype=F64)
+        rc = self._lib.mgb_posterior_eval_host(self._h, C.c_void_p(x.data_ptr()), m, C.c_void_p(mean.data_ptr()),
+                                               C.c_void_p(var.data_ptr()))
+        _lib.check(rc, "mgb_posterior_eval_host")
+        return mean, var
+
+    def eval_device(self, x: torch.Tensor):
+        if self._h is None:
+            raise RuntimeError("handle destroyed")
+        _lib.require_cuda_f64(x)
+        m = x.shape[0]
+        mean = torch.empty(m, dtype=F64, device=x.device)
+        var = torch.empty(m, dtype=F64, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = self._lib.mgb_posterior_eval_device(self._h, _lib.ptr(x), m, x.stride(0), _lib.ptr(mean), _lib.ptr(var),
+                                                     _lib.stream_ptr(x.device))
+        _lib.check(rc, "mgb_posterior_eval_device")
+        return mean, var
+
+    def destroy(self):
+        if getattr(self, "_h", None) is not None:
+            self._lib.mgb_posterior_destroy(self._h)
+            self._h = None
+            self._keep = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.destroy()
 
 
 class ExpectedImprovement:
