@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--posterior-path", default="fp64", choices=["fp64", "int8"],
                     help="default workload: fp64 = hand-written DMMA kernel (default); int8 = opt-in INT8 tensor-core path")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gram", action="store_true", help="default workload: skip the Gram-matrix leg (configs[0], [2], [3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -169,10 +170,15 @@ def run_posterior(args, rank, world, local):
     gen = torch.Generator(device=device).manual_seed(1234 + rank)
     xc = unit_rows(m_local, 11, gen, device)                      # this rank's candidate rows, HBM resident
     spec, coef0 = kernel.series()
+    # shapes of the fitted state, known on every rank from n and the kernel: the broadcast is one flat NCCL transfer
+    state_meta = None
+    if not use_int8:
+        state_meta = {"train": ((n, 11), F64), "coef": (tuple(coef0.shape), F64),
+                      "packed": ((lib.mgb_posterior_pack_bytes(n) // 8,), F64)}
 
     def step():
         if world > 1:
-            state = sh.broadcast_state(gp.state() if rank == 0 else {"like": xc[:0]}, src=0)
+            state = sh.broadcast_state(gp.state() if rank == 0 else {"like": xc[:0]}, src=0, meta=state_meta)
             if rank != 0:
                 gp.load_state(spec, state["train"], state["packed"], state["coef"],
                               _self_k(spec, state["coef"]), state.get("packed_i8"), state.get("alpha"))
@@ -240,6 +246,14 @@ def run_posterior(args, rank, world, local):
     if not args.no_e2e:
         e2e = posterior_e2e(args, gp, rank, world, local, m_total, m_local, n, xc, dist)
 
+    # ---- Gram-matrix half of the metric (rank 0, one GPU): configs[0], [2], [3] with sustained timing --------------
+    gram = None
+    if rank == 0 and world == 1 and not args.no_gram and args.m is None and args.n is None:
+        del xc
+        gp._ws = None
+        torch.cuda.empty_cache()
+        gram = gram_leg(args, rank, world, local)
+
     out = None
     if rank == 0:
         out = {
@@ -255,7 +269,7 @@ def run_posterior(args, rank, world, local):
                                     "(chunk buffer %.2f GB > 126 MB L2)" % (8e-9 * m_total * n / world,
                                                                             8e-9 * gp.chunk * n)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e,
-            "checksum": checksum, "int8_path": int8,
+            "checksum": checksum, "int8_path": int8, "gram": gram,
         }
     return out
 
@@ -343,60 +357,36 @@ def posterior_roofline(gp, xc, n, lib):
 
 
 def posterior_e2e(args, gp, rank, world, local, m_total, m_local, n, xc, dist):
-    """Same metric through mgb_series_posterior_host: pinned HOST candidates / factor in, HOST mean/var out."""
-    from materngabo_b200 import _lib
-
-    lib = _lib.load()
+    """Same metric through the persistent C-ABI handle (include/mgb.h: mgb_posterior_create_from_device /
+    mgb_posterior_eval_host): pinned HOST candidates in, HOST mean / var out, H2D + D2H inside the timed region.  The
+    fitted state is the model - it is resident on every rank's device after the NCCL broadcast of step(), exactly as
+    gpytorch keeps its prediction caches on the device between acq(X) calls - so each call moves candidates and results
+    only."""
     device = torch.device("cuda", local)
     if gp.int8:
         return posterior_e2e_int8(args, gp, rank, world, local, m_total, m_local, n, xc, dist)
-    # every rank needs the fitted state on the host: rank 0 broadcasts, then all move it to pinned memory
-    if world > 1:
-        from materngabo_b200.posterior import ShardedPosterior
-        sh = ShardedPosterior(compute=None)
-        full = sh.broadcast_state({"train": gp.train_prepared, "coef": gp.coef, "rinv": gp.rinv, "alpha": gp.alpha}
-                                  if rank == 0 else {"like": xc[:0]}, src=0)
-        state = full
-    else:
-        state = {"train": gp.train_prepared, "coef": gp.coef, "rinv": gp.rinv, "alpha": gp.alpha}
     xc_h = xc.cpu().pin_memory()
-    xt_h = state["train"].cpu().pin_memory()
-    coef_h = state["coef"].cpu().contiguous()
-    rinv_h = state["rinv"].cpu().pin_memory()
-    alpha_h = state["alpha"].cpu().pin_memory()
     mean_h = torch.empty(m_local, dtype=F64).pin_memory()
     var_h = torch.empty(m_local, dtype=F64).pin_memory()
-    spec = gp.spec
-    if spec is None:
-        spec, _ = gp.kernel.series()
-    from materngabo_b200.posterior import _self_kernel_value
-    kss = _self_kernel_value(spec, coef_h)
-    d = spec.desc(coef_h.shape[-1])
-
-    def call():
-        _lib.check(lib.mgb_series_posterior_host(C.byref(d), _lib.ptr(xc_h), m_local, _lib.ptr(xt_h), n, _lib.ptr(coef_h),
-                                                 _lib.ptr(rinv_h), _lib.ptr(alpha_h), kss, gp.mean_const,
-                                                 _lib.ptr(mean_h), _lib.ptr(var_h), gp.chunk, local), "posterior_host")
-
+    handle = gp.handle(gp.chunk)
     steps = max(1, min(args.steps, 2))
-    call()  # warm-up (allocations, page faults)
+    handle.eval_host(xc_h[: min(m_local, 4 * gp.chunk)].contiguous())       # warm-up
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        call()
-    torch.cuda.synchronize()
+        handle.eval_host(xc_h, mean_h, var_h)
     dt = time.perf_counter() - t0
+    handle.destroy()
     t = torch.tensor([dt], dtype=F64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t[0])
-    h2d = 8 * (m_local * 11 + n * 11 + n * n + n + coef_h.numel())
-    d2h = 8 * 2 * m_local
-    return {"value": m_total / (dt / steps), "unit": "candidates/s", "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "steps": steps,
-            "api": "mgb_series_posterior_host (C-ABI, pinned host buffers, per rank)",
+    return {"value": m_total / (dt / steps), "unit": "candidates/s", "h2d_bytes_per_step": 8 * m_local * 11,
+            "d2h_bytes_per_step": 8 * 2 * m_local, "steps": steps,
+            "api": "mgb_posterior_eval_host on a persistent handle (C-ABI, pinned host buffers, per rank; fitted state "
+                   "resident on the device)",
             "sample_mean0": float(mean_h[0]), "timer": "host wall clock around the synchronous C-ABI call, max over ranks"}
 
 
@@ -524,7 +514,22 @@ GRAM_DEFAULTS = {"config1-s2": (1000, 1000), "gram-s2": (1_000_000, 2000), "gram
                  "gram-h2-table": (1_000_000, 2000)}
 
 
-def run_gram(args, rank, world, local):
+# FP64 instructions (DFMA + DMUL + DADD, thread level) the quadrature Gram kernels EXECUTE per entry at 64 x 64 nodes,
+# from the per-opcode warp-instruction counts of the committed ncu captures (x 32 lanes / entries of the profiled
+# launch).  SURVEY.md 8d's "32 flops per node" is a convention the factorised kernels undercut, so the honest
+# utilisation figure is executed instructions / s against the FP64 pipe's issue rate (measured DFMA TFLOP/s / 2).
+EXECUTED_FP64_INSTR = {
+    "gram-h2": (11440.0, "profiles/r01d_ncu_gram_h2_fwd4.txt: (200.43 M DFMA + 148.55 M DMUL + 8.54 M DADD) warp-instructions x 32 / 1.0e6 entries"),
+    "gram-spd2": (31450.0, "profiles/r01d_ncu_gram_spd2_pairs.txt: (708.05 M DFMA + 226.96 M DMUL + 47.80 M DADD) warp-instructions x 32 / 1.0e6 entries"),
+}
+
+
+class _GramArgs:
+    def __init__(self, workload, m, n, steps, warmup, no_cpu_baseline):
+        self.workload, self.m, self.n, self.steps, self.warmup, self.no_cpu_baseline = workload, m, n, steps, warmup, no_cpu_baseline
+
+
+def run_gram(args, rank, world, local, min_seconds=0.0, cpu_seconds=8.0):
     import torch.distributed as dist
     from materngabo_b200 import _lib
 
@@ -548,6 +553,21 @@ def run_gram(args, rank, world, local):
         out = step()
         del out
     barrier()
+    steps = args.steps
+    if min_seconds > 0:
+        # sustained timing: enough steps for >= min_seconds of timed work (>= 10 clock samples at 200 ms), so that the
+        # board reaches its load power / clocks instead of a 15 ms burst from idle
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(3):
+            out = step()
+            del out
+        p1.record()
+        torch.cuda.synchronize()
+        est = max(p0.elapsed_time(p1) / 3.0, 1e-3)
+        steps = max(args.steps, int(min_seconds * 1e3 / est) + 1)
+        if 8.0 * m * n < 4 * 126e6:
+            steps = min(steps, 20000)          # small problems: the untimed L2 flush dominates the wall clock
     sampler = ClockSampler(local).start() if rank == 0 else None
     launches0 = lib.mgb_launch_count()
     small = 8.0 * m * n < 4 * 126e6            # output would stay L2 resident between steps: flush L2 in between
@@ -555,7 +575,7 @@ def run_gram(args, rank, world, local):
     graphable = args.workload in ("config1-s2", "gram-s2", "gram-s10", "gram-so3")   # quadrature kernels read their node
     if small and not graphable:                                                       # grids back on the host: eager
         flush = torch.empty(64 * 1024 * 1024, dtype=F64, device=device)     # 512 MB > 126 MB L2
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for a, b in evs:
             del out
             flush.fill_(1.0)               # untimed: evicts x1, x2 and the previous output
@@ -576,7 +596,7 @@ def run_gram(args, rank, world, local):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             out = step()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for a, b in evs:
             flush.fill_(1.0)               # untimed: evicts x1, x2 and the previous output
             a.record()
@@ -584,11 +604,11 @@ def run_gram(args, rank, world, local):
             b.record()
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in evs)
-        launches0 -= args.steps            # replays do not pass through the library's launch counter
+        launches0 -= steps            # replays do not pass through the library's launch counter
     else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             del out        # the caching allocator hands the same block back: no cudaMalloc inside the timed region
             out = step()
         e1.record()
@@ -602,7 +622,7 @@ def run_gram(args, rank, world, local):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, launches = float(tmax[0]), int(tsum[1])
-    ms_per_step = ms / args.steps
+    ms_per_step = ms / steps
     entries = float(m) * n * world
     value = entries / (ms_per_step * 1e-3)
     if rank != 0:
@@ -612,17 +632,28 @@ def run_gram(args, rank, world, local):
     if quad:
         tf = C.c_double()
         _lib.check(lib.mgb_fp64_peak(0, 3, C.byref(tf), None), "mgb_fp64_peak")
-        ach = (flops or 0) * float(m) * n / (ms_per_step * 1e-3) / 1e12 if flops else None
+        rate = float(m) * n / (ms_per_step * 1e-3)                          # entries/s of one GPU
+        ach = (flops or 0) * rate / 1e12 if flops else None
+        executed = EXECUTED.get(args.workload)                              # flops (FMA = 2) where the mix is all-FMA
+        executed_frac = executed * rate / 1e12 / tf.value if executed else None
+        executed_src = "FMA slots of the kernel's inner loops x 2 (see gram_setup)" if executed else None
+        if args.workload in EXECUTED_FP64_INSTR and (m, n) == GRAM_DEFAULTS[args.workload]:
+            instr, executed_src = EXECUTED_FP64_INSTR[args.workload]
+            executed = instr                                                 # FP64 instructions per entry
+            executed_frac = instr * rate / (tf.value * 1e12 / 2.0)          # against the pipe's instruction issue rate
         roof = {"bound": "fp64", "achieved": ach, "peak": tf.value, "unit": "TFLOP/s",
-                "frac": (ach / tf.value) if ach else None, "traffic": None,
+                "frac": executed_frac if executed_frac is not None else ((ach / tf.value) if ach else None),
+                "frac_definition": "executed FP64 operations / s over the measured DFMA peak" if executed_frac is not None
+                else "SURVEY.md 8d algorithmic flops / s over the measured DFMA peak",
+                "frac_survey_convention": (ach / tf.value) if ach else None, "traffic": None,
                 "algorithmic_flops_per_entry": flops,
-                "executed_flops_per_entry": EXECUTED.get(args.workload),
-                "executed_frac": (EXECUTED[args.workload] * float(m) * n / (ms_per_step * 1e-3) / 1e12 / tf.value)
-                if args.workload in EXECUTED else None,
+                "executed_per_entry": executed, "executed_unit": "FP64 instructions" if args.workload in EXECUTED_FP64_INSTR else "flops (FMA = 2)",
+                "executed_source": executed_src, "executed_frac": executed_frac,
                 "note": ("SURVEY.md 8d: 10 x (6 + 4 n_eff) flops per entry, n_eff = %d retained cosine terms per circle "
                          "factor (of the reference's 201)" % ((flops // 10 - 6) // 4)) if args.workload == "gram-t10" else
-                        "algorithmic convention of SURVEY.md 8d: 32 flops per quadrature node (one exp = 28); the kernel "
-                        "executes fewer (factorised exponentials), so frac can exceed what the pipe sustains",
+                        "frac = executed FP64 instructions / s over the pipe's issue rate; frac_survey_convention uses "
+                        "SURVEY.md 8d's 32 flops per quadrature node (one exp = 28), which the factorised kernels undercut "
+                        "(it can exceed 1 and is kept only for comparison with the survey's roof)",
                 "peak_source": "DFMA micro-benchmark in this run"}
     else:
         ach = 8.0 * m * n / (ms_per_step * 1e-3) / 1e9
@@ -632,14 +663,23 @@ def run_gram(args, rank, world, local):
         hbm_roof = hbm * 1e9 / 8.0                                  # entries/s at 8 B per entry
         fp64_roof = tf.value * 1e12 / flops if flops else None      # SURVEY.md 8d algorithmic flops per entry
         lower = min(hbm_roof, fp64_roof) if fp64_roof else hbm_roof
+        w = int(x1.shape[1])
+        slots = 4 * ((w + 3) // 4) + (int(kernel.series()[1].shape[-1]) - 1 if hasattr(kernel, "series") else 9)
+        if args.workload == "gram-so3" and 8.0 * m * n >= 4e6 * 8:
+            slots = 4 + 1 + 9                       # quaternion form: 4-wide inner product, square, 10-term Horner
+        exec_roof = tf.value * 1e12 / (2.0 * slots)
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "bytes_per_entry": 8,
+                "fp64_executed": {"fma_slots_per_entry": slots, "roof_entries_per_s": exec_roof, "frac": value / world / exec_roof,
+                                  "note": "executed FMA slots on the shared FP64 data path: DMMA inner product padded to a "
+                                          "multiple of 4 + one DFMA per Horner term (DESIGN.md section 4)"},
                 "survey_8d": {"algorithmic_flops_per_entry": flops, "hbm_roof_entries_per_s": hbm_roof,
                               "fp64_roof_entries_per_s": fp64_roof, "fp64_peak_tflops_measured": tf.value,
                               "frac_of_lower_roof": value / lower}}
     return {"metric": "kernel_entries_per_sec", "value": value, "unit": "entries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "timed_seconds": ms * 1e-3,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s K(X*, X) %d x %d per GPU" % (args.workload, m, n), "rows": m, "cols": n,
                        "l2_policy": (("L2 flushed (512 MB fill, untimed) before every timed step; each step is "
@@ -648,7 +688,28 @@ def run_gram(args, rank, world, local):
                                      else "output %.2f GB per step >> L2" % (8e-9 * m * n))},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": None,
             "checksum": float(out[:8, :8].sum()),
-            "cpu_baseline": None if (args.no_cpu_baseline or world > 1) else cpu_gram_baseline(args.workload, x1, x2)}
+            "cpu_baseline": None if (args.no_cpu_baseline or world > 1) else cpu_gram_baseline(args.workload, x1, x2, cpu_seconds)}
+
+
+GRAM_LEG = ("config1-s2", "gram-s2", "gram-s10", "gram-so3", "gram-t10", "gram-h2", "gram-spd2")
+
+
+def gram_leg(args, rank, world, local):
+    """The "kernel entries/sec (fp64)" half of BASELINE.json's metric inside the default (driver-run) line: every Gram
+    workload of configs[0], [2], [3] (+ S^2 / S^10 at the 1 M x 2 k shape), each timed for >= 2 s with its own clock
+    record, roofline (HBM-write and FP64, executed-operation fractions) and oracle-port CPU baseline."""
+    out = {}
+    for wl in GRAM_LEG:
+        ga = _GramArgs(wl, None, None, 5, 3, args.no_cpu_baseline)
+        try:
+            r = run_gram(ga, rank, world, local, min_seconds=2.0, cpu_seconds=2.0)
+        except Exception as exc:                      # one failing workload must not take the headline line with it
+            out[wl] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            continue
+        out[wl] = {k: r[k] for k in ("value", "unit", "steps", "ms_per_step", "timed_seconds", "config", "clocks", "roofline",
+                                     "cpu_baseline", "gpu_launches", "checksum")}
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_bo_latency(args, local):
@@ -790,7 +851,7 @@ def run_bo_latency(args, local):
             "cpu_baseline": cpu}
 
 
-def cpu_gram_baseline(workload, x1, x2):
+def cpu_gram_baseline(workload, x1, x2, seconds=8.0):
     """Oracle port (the reference's torch CPU algorithm, all host threads) on a bounded block of the same inputs:
     entries/s.  Block sizes are chosen so that one evaluation takes seconds (the reference materialises
     O(P x M x N) temporaries for the quadrature kernels and O(M x N x D) for the distances)."""
@@ -812,7 +873,7 @@ def cpu_gram_baseline(workload, x1, x2):
         fn()                                   # warm-up
         t0 = time.perf_counter()
         reps = 0
-        while reps < 20 and (time.perf_counter() - t0 < 8.0 or reps < 2):
+        while reps < 20 and (time.perf_counter() - t0 < seconds or reps < 2):
             fn()
             reps += 1
         dt = (time.perf_counter() - t0) / reps

@@ -67,6 +67,18 @@ int mgb_series_gram_fwd(const mgb_series_desc* desc, const double* x1, long long
                         const double* x2, long long n, long long ld2, const double* coef,
                         double* K, long long ldk, void* stream);
 
+/* gpytorch batch dimensions (b x m x D against b x n x D, e.g. a materialised expansion of the training inputs in the
+ * posterior call): `batch` Gram matrices from ONE launch (gridDim.z = batch); stride1 / stride2 / stridek
+ * = elements between consecutive batch members (0 = shared operand). */
+int mgb_series_gram_fwd_batched(const mgb_series_desc* desc, const double* x1, long long m, long long ld1,
+                                long long stride1, const double* x2, long long n, long long ld2, long long stride2,
+                                const double* coef, double* K, long long ldk, long long stridek, long long batch,
+                                void* stream);
+/* diag=True of Kernel.forward: out[i] = k(x1[i], x2[i]) for two equally long point lists, one thread per row
+ * (the reference computes a full bmm on expanded pairs: Riemannian_utils/sphere_utils_torch.py:50-53). */
+int mgb_series_gram_diag(const mgb_series_desc* desc, const double* x1, long long ld1, const double* x2, long long ld2,
+                         long long rows, const double* coef, double* out, void* stream);
+
 /* Backward of the above for L = sum(K * G):
  *   gcoef[f*T + k] += dL/dcoef (accumulated with atomics: caller zeroes it),
  *   gx1 (m x F*W, ld = F*W) = dL/dx1 (overwritten; may be NULL), gx2 likewise (may be NULL).

@@ -39,6 +39,8 @@ PROTOTYPES = {
     "mgb_version": (_I, []),
     "mgb_launch_count": (_LL, []),
     "mgb_series_gram_fwd": (_I, [_DESC, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _LL, _P]),
+    "mgb_series_gram_fwd_batched": (_I, [_DESC, _P, _LL, _LL, _LL, _P, _LL, _LL, _LL, _P, _P, _LL, _LL, _LL, _P]),
+    "mgb_series_gram_diag": (_I, [_DESC, _P, _LL, _P, _LL, _LL, _P, _P, _P]),
     "mgb_series_gram_bwd": (_I, [_DESC, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _LL, _LL, _P, _P, _P, _P]),
     "mgb_so3_to_quaternion": (_I, [_P, _LL, _LL, _P, _P, _P]),
     "mgb_series_gram_dx": (_I, [_DESC, _I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _LL, _LL, _P, _P, _P]),

@@ -644,27 +644,58 @@ def _is_broadcast_of_2d(t: torch.Tensor) -> bool:
     return t.dim() > 2 and all(s == 0 or sz == 1 for s, sz in zip(t.stride()[:-2], t.shape[:-2]))
 
 
-def pairwise(fn2d, x1: torch.Tensor, x2: torch.Tensor, diag: bool = False) -> torch.Tensor:
+def _series_diag_raw(spec, x1, x2, coef):
+    lib = _lib.load()
+    rows = x1.shape[0]
+    out = torch.empty(rows, dtype=F64, device=x1.device)
+    d = spec.desc(coef.shape[-1])
+    with torch.cuda.device(x1.device):
+        rc = lib.mgb_series_gram_diag(C.byref(d), _lib.ptr(x1), x1.stride(0), _lib.ptr(x2), x2.stride(0), rows,
+                                      _lib.ptr(coef), _lib.ptr(out), _lib.stream_ptr(x1.device))
+    _lib.check(rc, "mgb_series_gram_diag")
+    return out
+
+
+def _series_batched_raw(spec, f1, f2, coef):
+    """(B, m, D) x (B, n, D) -> (B, m, n) from one launch (gridDim.z = B)."""
+    lib = _lib.load()
+    bsz, m, n = f1.shape[0], f1.shape[1], f2.shape[1]
+    k = torch.empty((bsz, m, n), dtype=F64, device=f1.device)
+    if bsz == 0 or m == 0 or n == 0:
+        return k
+    d = spec.desc(coef.shape[-1])
+    with torch.cuda.device(f1.device):
+        rc = lib.mgb_series_gram_fwd_batched(C.byref(d), _lib.ptr(f1), m, f1.stride(1), f1.stride(0), _lib.ptr(f2), n,
+                                             f2.stride(1), f2.stride(0), _lib.ptr(coef), _lib.ptr(k), n, m * n, bsz,
+                                             _lib.stream_ptr(f1.device))
+    _lib.check(rc, "mgb_series_gram_fwd_batched")
+    return k
+
+
+def pairwise(fn2d, x1: torch.Tensor, x2: torch.Tensor, diag: bool = False, series=None, rowwise=None) -> torch.Tensor:
     """Apply a 2-D Gram function over gpytorch-style batch dimensions.
 
     * no batch dims: one launch;
     * x2 a broadcast of one N x D block (botorch's posterior layout b x q x D against the expanded training
-      inputs, SURVEY.md 3.2): one launch on (b*q) x D against N x D;
-    * otherwise one launch per batch element.
-    ``diag=True`` returns the per-row kernel k(x1_i, x2_i) (shape ... x N)."""
+      inputs, SURVEY.md 3.2) - by strides, or materialised with identical members: one launch on (b*q) x D against N x D;
+    * otherwise one batched launch (``series=(spec, coef)``, no autograd needed) or one launch per batch element.
+    ``diag=True`` returns the per-row kernel k(x1_i, x2_i) (shape ... x N): one thread per row for the series kernels,
+    ``rowwise`` (the kernel's profile path on (rows, 1, D) batches) for the quadrature kernels."""
+    plain_series = series is not None and not inputs_need_grad(x1, x2, series[1])
     if diag:
         if x1.shape != x2.shape:
             raise RuntimeError("diag=True requires x1 and x2 of the same shape")
-        flat1 = x1.reshape(-1, 1, x1.shape[-1])
-        flat2 = x2.reshape(-1, 1, x2.shape[-1])
+        flat1 = x1.reshape(-1, x1.shape[-1]).contiguous()
+        flat2 = x2.reshape(-1, x2.shape[-1]).contiguous()
         rows = flat1.shape[0]
-        out = torch.empty(rows, dtype=F64, device=x1.device)
-        blk = 256                      # block-diagonal sweep: blk x blk entries computed per blk diagonal values
-        pieces = []
-        for s in range(0, rows, blk):
-            k = fn2d(flat1[s:s + blk, 0], flat2[s:s + blk, 0])
-            pieces.append(torch.diagonal(k))
-        out = torch.cat(pieces) if pieces else out
+        if plain_series:
+            _lib.require_cuda_f64(flat1, flat2)
+            return _series_diag_raw(series[0], flat1, flat2, series[1].contiguous()).reshape(x1.shape[:-1])
+        if rowwise is not None and rows > 0:
+            return rowwise(flat1.unsqueeze(-2), flat2.unsqueeze(-2)).reshape(x1.shape[:-1])
+        blk = 32                       # block-diagonal sweep (differentiable series path): blk x blk entries per blk values
+        pieces = [torch.diagonal(fn2d(flat1[s:s + blk], flat2[s:s + blk])) for s in range(0, rows, blk)]
+        out = torch.cat(pieces) if pieces else torch.empty(0, dtype=F64, device=x1.device)
         return out.reshape(x1.shape[:-1])
     if x1.dim() == 2 and x2.dim() == 2:
         return fn2d(x1, x2)
@@ -676,16 +707,25 @@ def pairwise(fn2d, x1: torch.Tensor, x2: torch.Tensor, diag: bool = False) -> to
     x1 = x1.expand(*batch, *x1.shape[-2:])
     x2 = x2.expand(*batch, *x2.shape[-2:])
     m, n = x1.shape[-2], x2.shape[-2]
-    if _is_broadcast_of_2d(x2):
-        base = x2[(0,) * len(batch)]
-        k = fn2d(x1.reshape(-1, x1.shape[-1]), base)
+    first = (0,) * len(batch)
+
+    def _same_members(t):
+        """A materialised expansion (gpytorch may hand train_inputs.expand(...).contiguous()): identical batch members."""
+        return t.numel() > 0 and not t.requires_grad and bool((t == t[first]).all())
+
+    if _is_broadcast_of_2d(x2) or (not _is_broadcast_of_2d(x1) and _same_members(x2)):
+        k = fn2d(x1.reshape(-1, x1.shape[-1]), x2[first])
         return k.reshape(*batch, m, n)
     if _is_broadcast_of_2d(x1):
-        base = x1[(0,) * len(batch)]
-        k = fn2d(base, x2.reshape(-1, x2.shape[-1]))          # m x (B*n)
+        k = fn2d(x1[first], x2.reshape(-1, x2.shape[-1]))          # m x (B*n)
         return k.reshape(m, *batch, n).movedim(0, -2)
     f1 = x1.reshape(-1, m, x1.shape[-1])
     f2 = x2.reshape(-1, n, x2.shape[-1])
+    if plain_series:
+        _lib.require_cuda_f64(f1, f2)
+        f1 = f1 if f1.stride(-1) == 1 else f1.contiguous()
+        f2 = f2 if f2.stride(-1) == 1 else f2.contiguous()
+        return _series_batched_raw(series[0], f1, f2, series[1].contiguous()).reshape(*batch, m, n)
     out = torch.stack([fn2d(f1[b], f2[b]) for b in range(f1.shape[0])]) if f1.shape[0] else \
         torch.empty((0, m, n), dtype=F64, device=x1.device)
     return out.reshape(*batch, m, n)

@@ -40,7 +40,17 @@ struct SeriesParams {
   int tiled;            // 1: write the tile-major swizzled layout consumed by posterior_reduce_kernel
   long long nch;        // tiled: 16-column chunks per row (n rounded up to 16, / 16)
   int square;           // u = scale * dot^2 + shift instead of scale * dot + shift (mgb_series_desc::pair_square)
+  long long bs1, bs2, bsk;  // batched launch (gridDim.z = batch): element strides between the batch members' x1 / x2 / K
+  int batch;
 };
+
+// gridDim.z = batch members (gpytorch batch dimensions b x m x D against b x n x D): same tile code, shifted bases
+__device__ __forceinline__ void batch_offset(SeriesParams& p) {
+  const long long b = blockIdx.z;
+  p.x1 += b * p.bs1;
+  p.x2 += b * p.bs2;
+  p.K += b * p.bsk;
+}
 
 // Address of K[grow][col].  Row-major, or the posterior's operand layout: 128 x 16 blocks stored
 // [candidate tile][column chunk][row][16], each row's eight 16-byte chunks XOR-swizzled by 2*(row & 3) so that the
@@ -108,6 +118,7 @@ __device__ __forceinline__ double clamp_exact(double u, double lo, double hi) {
 
 template <int W, int TREG>
 __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams p) {
+  batch_offset(p);
   constexpr int RB = 4;                       // rows per iteration: 8 independent chains per thread
   constexpr bool kRowsInRegs = (W <= 6);      // small rows are fetched with 16-byte broadcasts up front
   extern __shared__ __align__(16) double smem[];
@@ -256,6 +267,117 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_fast(SeriesParams
 }
 
 // ---------------------------------------------------------------------------------------------
+// Small problems (m * n below ~4 M entries: BASELINE configs[0], the 1000 x 1000 S^2 Gram; GP-fit sizes): the
+// persistent-panel kernels above launch ~128 CTAs whose prologue (mbarrier set-up, bulk copy, two dependent DRAM
+// round trips) is most of the 10 us they take.  Here nothing is staged and nothing is synchronised: a warp owns
+// 8 (W <= 4) or 4 rows x 64 columns, a lane keeps its two x2 rows and the coefficients in registers, x1 rows arrive as warp-wide
+// broadcast loads, and every load of the prologue is issued before the first use.  32-row x 64-column CTAs of 4
+// warps: 512 CTAs for 1000 x 1000 - one wave over the 148 SMs with ~14 warps each to hide the FP64 latency.
+// Same arithmetic as series_gram_fwd_fast (DFMA inner product with scale folded into x2, integer-pipe clamp test,
+// Horner), so the results agree bit for bit with that kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmallThreads = 128;
+__host__ __device__ constexpr int small_rows_per_warp(int W) { return W <= 4 ? 8 : 4; }   // wide rows: registers
+
+template <int W, int TREG>
+__global__ void __launch_bounds__(kSmallThreads) series_gram_fwd_small(SeriesParams p) {
+  batch_offset(p);
+  constexpr int RB = 4;
+  constexpr int kSmallRowsPerWarp = small_rows_per_warp(W);
+  constexpr int kSmallRows = (kSmallThreads / 32) * kSmallRowsPerWarp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long col = (long long)blockIdx.x * kTN + 2 * lane;
+  const long long row_w = (long long)blockIdx.y * kSmallRows + warp * kSmallRowsPerWarp;
+  if (row_w >= p.m) return;
+  const bool va = col < p.n, vb = col + 1 < p.n;
+  // every global load of the prologue is in flight before the first one is needed
+  double xa[W], xb[W], c[TREG], v[kSmallRowsPerWarp][W];
+  {
+    const double* pa = p.x2 + (va ? col : 0) * p.ld2;
+    const double* pb = p.x2 + (vb ? col + 1 : 0) * p.ld2;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      xa[k] = __ldg(pa + k);
+      xb[k] = __ldg(pb + k);
+    }
+#pragma unroll
+    for (int q = 0; q < kSmallRowsPerWarp; ++q) {
+      const long long r = (row_w + q < p.m) ? row_w + q : p.m - 1;
+#pragma unroll
+      for (int k = 0; k < W; ++k) v[q][k] = __ldg(p.x1 + r * p.ld1 + k);      // warp-wide broadcast
+    }
+#pragma unroll
+    for (int k = 0; k < TREG; ++k) c[k] = (k < p.T) ? __ldg(p.coef + k) : 0.0;
+  }
+  const double fold = p.square ? sqrt(p.scale) : p.scale;
+  const double init = p.square ? 0.0 : p.shift;
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    xa[k] = va ? fold * xa[k] : 0.0;
+    xb[k] = vb ? fold * xb[k] : 0.0;
+  }
+  const bool vec_ok = vb && ((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0);
+  const unsigned thr = p.clamp_word;
+#pragma unroll
+  for (int r0 = 0; r0 < kSmallRowsPerWarp; r0 += RB) {
+    double ua[RB], ub[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) ua[q] = ub[q] = init;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        ua[q] = fma(v[r0 + q][k], xa[k], ua[q]);
+        ub[q] = fma(v[r0 + q][k], xb[k], ub[q]);
+      }
+    }
+    if (p.square) {
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        ua[q] = fma(ua[q], ua[q], p.shift);
+        ub[q] = fma(ub[q], ub[q], p.shift);
+      }
+    }
+    unsigned need = 0;
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      need |= (unsigned)(((unsigned)__double2hiint(ua[q]) & 0x7fffffffu) >= thr);
+      need |= (unsigned)(((unsigned)__double2hiint(ub[q]) & 0x7fffffffu) >= thr);
+    }
+    if (need) {
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        ua[q] = clamp_exact(ua[q], p.lo, p.hi);
+        ub[q] = clamp_exact(ub[q], p.lo, p.hi);
+      }
+    }
+    double pa[RB], pb[RB];
+#pragma unroll
+    for (int q = 0; q < RB; ++q) pa[q] = pb[q] = c[TREG - 1];
+#pragma unroll
+    for (int k = TREG - 2; k >= 0; --k) {
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        pa[q] = fma(pa[q], ua[q], c[k]);
+        pb[q] = fma(pb[q], ub[q], c[k]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      const long long r = row_w + r0 + q;
+      if (r < p.m) {
+        double* out = p.K + r * p.ldk + col;
+        if (vec_ok) st_stream2(out, pa[q], pb[q]);
+        else {
+          if (va) st_stream(out, pa[q]);
+          if (vb) st_stream(out + 1, pb[q]);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tensor-pipe variant of the fast path: the W-wide inner products run as FP64 DMMA m8n8k4 fragments (x2 columns
 // resident in registers as B fragments, x1 rows fetched from the shared-memory panel as A fragments, k padded
 // with zeros to a multiple of 4), which moves W of the W + T + 1 FMAs per entry off the FP64 DFMA pipe: DMMA
@@ -271,6 +393,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 template <int W, int TREG>
 __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_mma(SeriesParams p) {
+  batch_offset(p);
   constexpr int KS = (W + 3) / 4;
   constexpr int NB = 4;   // 8-column fragments per warp (32 columns)
   constexpr int NA = 4;   // 8-row fragments per warp (32 rows)
@@ -421,6 +544,7 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_mma(SeriesParams 
 // ---------------------------------------------------------------------------------------------
 template <int W, int TREG, bool TILED>
 __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_warp(SeriesParams p) {
+  batch_offset(p);
   constexpr int KS = (W + 3) / 4;
   constexpr int NB = 4;
   constexpr int NA = 4;
@@ -658,6 +782,7 @@ __device__ __forceinline__ void eval_n(const double* __restrict__ cf, int T, con
 // the chain latency, not the pipe, limited the 4-chain version), 4 for the Chebyshev basis (three live values per chain).
 template <int BASIS>
 __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_general(SeriesParams p) {
+  batch_offset(p);
   constexpr int RPT = (BASIS == MGB_BASIS_MONOMIAL) ? 4 : 2;
   constexpr int NE = 2 * RPT;
   extern __shared__ __align__(16) double smem[];
@@ -926,22 +1051,22 @@ static int validate(const mgb_series_desc* d, const void* x1, long long m, long 
 template <int W, int TREG>
 static int launch_fast(const SeriesParams& p, long long tiles, cudaStream_t s) {
   const size_t smem = sizeof(double) * 2 * kTM * W;
-  series_gram_fwd_fast<W, TREG><<<(unsigned)tiles, kThreads, smem, s>>>(p);
+  series_gram_fwd_fast<W, TREG><<<dim3((unsigned)tiles, 1, (unsigned)p.batch), kThreads, smem, s>>>(p);
   return after_launch("series_gram_fwd_fast");
 }
 
 template <int W, int TREG>
 static int launch_mma(const SeriesParams& p, long long tiles, cudaStream_t s) {
   const size_t smem = sizeof(double) * 2 * kTM * W;
-  series_gram_fwd_mma<W, TREG><<<(unsigned)tiles, kThreads, smem, s>>>(p);
+  series_gram_fwd_mma<W, TREG><<<dim3((unsigned)tiles, 1, (unsigned)p.batch), kThreads, smem, s>>>(p);
   return after_launch("series_gram_fwd_mma");
 }
 
 template <int W, int TREG>
 static int launch_warp(const SeriesParams& p, long long tiles, cudaStream_t s) {
   const size_t smem = sizeof(double) * (kThreads / 32) * 2 * 32 * W;
-  if (p.tiled) series_gram_fwd_warp<W, TREG, true><<<(unsigned)tiles, kThreads, smem, s>>>(p);
-  else series_gram_fwd_warp<W, TREG, false><<<(unsigned)tiles, kThreads, smem, s>>>(p);
+  if (p.tiled) series_gram_fwd_warp<W, TREG, true><<<dim3((unsigned)tiles, 1, (unsigned)p.batch), kThreads, smem, s>>>(p);
+  else series_gram_fwd_warp<W, TREG, false><<<dim3((unsigned)tiles, 1, (unsigned)p.batch), kThreads, smem, s>>>(p);
   return after_launch("series_gram_fwd_warp");
 }
 
@@ -958,6 +1083,37 @@ static int series_path(int W) {
   (void)W;
   return 2;   // measured on B200, 1M x 2k: S^2 7.01e11 vs 6.79e11 entries/s, SO(3) (quaternion form) 6.26e11 vs 6.05e11,
               // S^10 5.58e11 vs 5.56e11 (gpurun_out/series_paths2.log)
+}
+
+template <int W, int TREG>
+static int launch_small(const SeriesParams& p, cudaStream_t s) {
+  constexpr int kSmallRows = (kSmallThreads / 32) * small_rows_per_warp(W);
+  dim3 grid((unsigned)p.ncc, (unsigned)((p.m + kSmallRows - 1) / kSmallRows), (unsigned)p.batch);
+  series_gram_fwd_small<W, TREG><<<grid, kSmallThreads, 0, s>>>(p);
+  return after_launch("series_gram_fwd_small");
+}
+
+// MGB_SERIES_SMALL=0 disables the small-problem kernel (tuning / comparison knob)
+static bool series_small_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MGB_SERIES_SMALL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
+template <int TREG>
+static int dispatch_small(const SeriesParams& p, cudaStream_t s, bool* handled) {
+  *handled = true;
+  switch (p.W) {
+    case 2: return launch_small<2, TREG>(p, s);
+    case 3: return launch_small<3, TREG>(p, s);
+    case 4: return launch_small<4, TREG>(p, s);
+    case 9: return launch_small<9, TREG>(p, s);
+    case 11: return launch_small<11, TREG>(p, s);
+    default: *handled = false; return MGB_OK;
+  }
 }
 
 template <int TREG>
@@ -1050,7 +1206,7 @@ static int series_sm_count() { return device_sm_count(); }
 
 static int series_fwd_impl(const mgb_series_desc* d, const double* x1, long long m, long long ld1, const double* x2,
                            long long n, long long ld2, const double* coef, double* K, long long ldk, int tiled,
-                           void* stream) {
+                           void* stream, long long batch = 1, long long bs1 = 0, long long bs2 = 0, long long bsk = 0) {
   MGB_TRY(validate(d, x1, m, ld1, x2, n, ld2, coef));
   if (m == 0 || n == 0) return MGB_OK;
   if (!K || (!tiled && ldk < n)) return fail(MGB_ERR_ARG, "series_gram_fwd: bad K / ldk");
@@ -1058,7 +1214,8 @@ static int series_fwd_impl(const mgb_series_desc* d, const double* x1, long long
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SeriesParams p{x1, m, ld1, x2, n, ld2, coef, K, ldk, d->n_factors, d->factor_width, d->n_terms,
                  d->scale, d->shift, d->lo, d->hi, (n + kTN - 1) / kTN, 0u, 1, tiled, (n + 15) / 16,
-                 d->pair_square ? 1 : 0};
+                 d->pair_square ? 1 : 0, bs1, bs2, bsk, (int)batch};
+  if (batch < 1 || batch > 65535) return fail(MGB_ERR_ARG, "series_gram_fwd: batch must be in [1, 65535] per launch");
   if (d->pair_square && !(d->scale > 0.0)) return fail(MGB_ERR_ARG, "series_gram_fwd: pair_square needs scale > 0");
   if (d->lo < 0.0 && d->hi > 0.0) {
     const double bound = fmin(-d->lo, d->hi);
@@ -1069,12 +1226,18 @@ static int series_fwd_impl(const mgb_series_desc* d, const double* x1, long long
   // persistent over row panels: about 8 CTAs per SM in total, each walking a strided set of 128-row panels of
   // its 64-column chunk with the x2 rows / coefficients resident in registers
   const long long npanels = (m + kTM - 1) / kTM;
-  long long splits = (8LL * series_sm_count() + p.ncc - 1) / p.ncc;
+  long long splits = (8LL * series_sm_count() + p.ncc * batch - 1) / (p.ncc * batch);
   if (splits > npanels) splits = npanels;
   if (splits < 1) splits = 1;
   p.row_splits = (int)splits;
   const long long tiles = p.ncc * splits;
   if (tiles > 0x7fffffffLL) return fail(MGB_ERR_ARG, "series_gram_fwd: too many tiles for one launch");
+  if (d->n_factors == 1 && d->basis == MGB_BASIS_MONOMIAL && d->n_terms <= 12 && !tiled && series_small_enabled() &&
+      m * n * batch < (4LL << 20) && m <= 16 * 65535) {
+    bool handled = false;
+    int rc = (d->n_terms <= 10) ? dispatch_small<10>(p, s, &handled) : dispatch_small<12>(p, s, &handled);
+    if (handled) return rc;
+  }
   if (d->n_factors == 1 && d->basis == MGB_BASIS_MONOMIAL && d->n_terms <= 12) {
     bool handled = false;
     int rc = (d->n_terms <= 10) ? dispatch_fast<10>(p, tiles, s, &handled) : dispatch_fast<12>(p, tiles, s, &handled);
@@ -1086,11 +1249,11 @@ static int series_fwd_impl(const mgb_series_desc* d, const double* x1, long long
   if (d->basis == MGB_BASIS_MONOMIAL) {
     MGB_TRY(check_cuda(cudaFuncSetAttribute(series_gram_fwd_general<MGB_BASIS_MONOMIAL>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
-    series_gram_fwd_general<MGB_BASIS_MONOMIAL><<<(unsigned)tiles, kThreads, smem, s>>>(p);
+    series_gram_fwd_general<MGB_BASIS_MONOMIAL><<<dim3((unsigned)tiles, 1, (unsigned)p.batch), kThreads, smem, s>>>(p);
   } else {
     MGB_TRY(check_cuda(cudaFuncSetAttribute(series_gram_fwd_general<MGB_BASIS_CHEBYSHEV>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
-    series_gram_fwd_general<MGB_BASIS_CHEBYSHEV><<<(unsigned)tiles, kThreads, smem, s>>>(p);
+    series_gram_fwd_general<MGB_BASIS_CHEBYSHEV><<<dim3((unsigned)tiles, 1, (unsigned)p.batch), kThreads, smem, s>>>(p);
   }
   return after_launch("series_gram_fwd_general");
 }
@@ -1099,6 +1262,55 @@ extern "C" int mgb_series_gram_fwd(const mgb_series_desc* d, const double* x1, l
                                    const double* x2, long long n, long long ld2, const double* coef, double* K,
                                    long long ldk, void* stream) {
   return series_fwd_impl(d, x1, m, ld1, x2, n, ld2, coef, K, ldk, 0, stream);
+}
+
+extern "C" int mgb_series_gram_fwd_batched(const mgb_series_desc* d, const double* x1, long long m, long long ld1,
+                                           long long stride1, const double* x2, long long n, long long ld2,
+                                           long long stride2, const double* coef, double* K, long long ldk,
+                                           long long stridek, long long batch, void* stream) {
+  if (batch < 0 || stride1 < 0 || stride2 < 0 || stridek < 0) return fail(MGB_ERR_ARG, "series_gram_fwd_batched: bad batch / strides");
+  for (long long b0 = 0; b0 < batch; b0 += 65535) {     // gridDim.z limit
+    const long long nb = (batch - b0 < 65535) ? (batch - b0) : 65535;
+    MGB_TRY(series_fwd_impl(d, x1 + b0 * stride1, m, ld1, x2 + b0 * stride2, n, ld2, coef, K + b0 * stridek, ldk, 0, stream, nb,
+                            stride1, stride2, stridek));
+  }
+  return MGB_OK;
+}
+
+namespace mgb {
+// out[i] = prod_f p_f(clamp(scale <x1_i[f], x2_i[f]> + shift)): the diagonal of the Gram matrix of two equally long
+// point lists, one thread per row (gpytorch's diag=True: the test x test block of the posterior variance).
+template <int BASIS>
+__global__ void __launch_bounds__(256) series_gram_diag_kernel(SeriesParams p, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.m) return;
+  const double* a = p.x1 + i * p.ld1;
+  const double* b = p.x2 + i * p.ld2;
+  double prod = 1.0;
+  for (int f = 0; f < p.F; ++f) {
+    double dsum = 0.0;
+    for (int k = 0; k < p.W; ++k) dsum = fma(a[f * p.W + k], b[f * p.W + k], dsum);
+    double u[1], sv[1];
+    u[0] = clamp_exact(fma(p.square ? dsum * dsum : dsum, p.scale, p.shift), p.lo, p.hi);
+    eval_n<BASIS, 1>(p.coef + f * p.T, p.T, u, sv);
+    prod *= sv[0];
+  }
+  out[i] = prod;
+}
+}  // namespace mgb
+
+extern "C" int mgb_series_gram_diag(const mgb_series_desc* d, const double* x1, long long ld1, const double* x2,
+                                    long long ld2, long long rows, const double* coef, double* out, void* stream) {
+  MGB_TRY(validate(d, x1, rows, ld1, x2, rows, ld2, coef));
+  if (rows == 0) return MGB_OK;
+  if (!out) return fail(MGB_ERR_ARG, "series_gram_diag: null output");
+  SeriesParams p{x1, rows, ld1, x2, rows, ld2, coef, nullptr, 0, d->n_factors, d->factor_width, d->n_terms,
+                 d->scale, d->shift, d->lo, d->hi, 0, 0u, 1, 0, 0, d->pair_square ? 1 : 0, 0, 0, 0, 1};
+  const unsigned blocks = (unsigned)((rows + 255) / 256);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (d->basis == MGB_BASIS_MONOMIAL) series_gram_diag_kernel<MGB_BASIS_MONOMIAL><<<blocks, 256, 0, s>>>(p, out);
+  else series_gram_diag_kernel<MGB_BASIS_CHEBYSHEV><<<blocks, 256, 0, s>>>(p, out);
+  return after_launch("series_gram_diag_kernel");
 }
 
 extern "C" long long mgb_posterior_tiled_bytes(long long m, long long n) {

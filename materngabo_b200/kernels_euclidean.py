@@ -24,7 +24,8 @@ class EuclideanHeatKernel(Kernel):
         tval = torch.as_tensor(t, dtype=F64, device=x1.device).reshape(1)
         tcoef = torch.pow(4 * np.pi * tval, -dim / 2)
         fn = _ops.euclidean_gram_autograd if _ops.inputs_need_grad(x1, x2) else _ops.euclidean_gram
-        return _ops.pairwise(lambda a, b: fn(a, b, tval, tcoef), x1, x2, diag=diag)
+        return _ops.pairwise(lambda a, b: fn(a, b, tval, tcoef), x1, x2, diag=diag,
+                             rowwise=lambda a, b: _ops.euclidean_gram_autograd(a, b, tval, tcoef))
 
 
 def unnormalized_heat_kernel(dist_sq, lengthscale):
@@ -60,4 +61,5 @@ class EuclideanIntegratedMaternKernel(_NuMixin, Kernel):
         _check_batch(self)
         tval, tcoef = self.nodes(x1.device)
         fn = _ops.euclidean_gram_autograd if _ops.inputs_need_grad(x1, x2) else _ops.euclidean_gram
-        return _ops.pairwise(lambda a, b: fn(a, b, tval, tcoef), x1, x2, diag=diag)
+        return _ops.pairwise(lambda a, b: fn(a, b, tval, tcoef), x1, x2, diag=diag,
+                             rowwise=lambda a, b: _ops.euclidean_gram_autograd(a, b, tval, tcoef))

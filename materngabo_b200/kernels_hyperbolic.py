@@ -55,7 +55,8 @@ class HyperbolicRiemannianMillsonGaussianKernel(Kernel):
             raise NotImplementedError("H^n heat kernel for n > 3 is out of scope (nested autograd in the reference)")
         _check_lorentz(x1, x2, self.dim)
         tval, tcoef, s0, ds, p = self.nodes(x1.device)
-        return _ops.pairwise(_gram_fn(self.dim, x1, x2, tval, tcoef, s0, ds, p), x1, x2, diag=diag)
+        return _ops.pairwise(_gram_fn(self.dim, x1, x2, tval, tcoef, s0, ds, p), x1, x2, diag=diag,
+                             rowwise=lambda a, b: _ops.hyperbolic_gram_autograd(self.dim, a, b, tval, tcoef, s0, ds, p))
 
 
 class HyperbolicRiemannianMillsonIntegratedMaternKernel(_NuMixin, Kernel):
@@ -87,4 +88,5 @@ class HyperbolicRiemannianMillsonIntegratedMaternKernel(_NuMixin, Kernel):
             raise NotImplementedError
         _check_lorentz(x1, x2, self.dim)
         tval, tcoef, s0, ds, p = self.nodes(x1.device)
-        return _ops.pairwise(_gram_fn(self.dim, x1, x2, tval, tcoef, s0, ds, p), x1, x2, diag=diag)
+        return _ops.pairwise(_gram_fn(self.dim, x1, x2, tval, tcoef, s0, ds, p), x1, x2, diag=diag,
+                             rowwise=lambda a, b: _ops.hyperbolic_gram_autograd(self.dim, a, b, tval, tcoef, s0, ds, p))

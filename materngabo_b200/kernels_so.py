@@ -48,7 +48,7 @@ class _SOSeriesKernel(Kernel):
                 spec4 = _ops.SeriesSpec(1, 4, spec.basis, 2.0, -1.0, spec.lo, spec.hi, 1)
                 with torch.no_grad():
                     return _ops._series_fwd_raw(spec4, quats[0], quats[1], coef.detach().contiguous())
-        return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1, x2, diag=diag)
+        return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1, x2, diag=diag, series=(spec, coef))
 
 
 class SORiemannianGaussianKernel(_SOSeriesKernel):

@@ -66,7 +66,8 @@ class SpdRiemannianGaussianKernel(Kernel):
         tcoef, rscale, bscale, b, bw = self.nodes(x1.device)
         op = _ops.spd2_gram_autograd if _ops.inputs_need_grad(x1, x2) else _ops.spd2_gram
         fn = lambda a, c: op(1, a, c, tcoef, rscale, bscale, b, bw)  # noqa: E731
-        return _ops.pairwise(fn, x1, x2, diag=diag)
+        return _ops.pairwise(fn, x1, x2, diag=diag,
+                             rowwise=lambda a, c: _ops.spd2_gram_autograd(1, a, c, tcoef, rscale, bscale, b, bw))
 
 
 class SpdRiemannianIntegratedMaternKernel(_NuMixin, Kernel):
@@ -132,7 +133,8 @@ class SpdRiemannianIntegratedMaternKernel(_NuMixin, Kernel):
             fn = lambda a, c: _ops.spd2_gram_autograd(0, a, c, tcoef, rscale, bscale, b, bw)  # noqa: E731
         else:
             fn = lambda a, c: _ops.spd2_gram(0, a, c, tcoef, rscale, bscale, b, bw, lattice)  # noqa: E731
-        return _ops.pairwise(fn, x1, x2, diag=diag)
+        return _ops.pairwise(fn, x1, x2, diag=diag,
+                             rowwise=lambda a, c: _ops.spd2_gram_autograd(0, a, c, tcoef, rscale, bscale, b, bw))
 
 
 class _SpdProductKernel(Kernel):

@@ -97,7 +97,7 @@ class _SphereSeriesKernel(Kernel):
         if x1.shape[-1] != self.dim + 1 or x2.shape[-1] != self.dim + 1:
             raise RuntimeError("S^%d points must have %d coordinates" % (self.dim, self.dim + 1))
         spec, coef = _series_on(self, x1.device)
-        return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1, x2, diag=diag)
+        return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1, x2, diag=diag, series=(spec, coef))
 
 
 class SphereRiemannianMaternKernel(_NuMixin, _SphereSeriesKernel):
@@ -156,7 +156,7 @@ class _CircleSeriesKernel(Kernel):
         if x1.shape[-1] != 2 or x2.shape[-1] != 2:
             raise RuntimeError("S^1 points must have 2 coordinates")
         spec, coef = _series_on(self, x1.device)
-        return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1, x2, diag=diag)
+        return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1, x2, diag=diag, series=(spec, coef))
 
 
 class CircleRiemannianGaussianKernel(_CircleSeriesKernel):
@@ -187,7 +187,7 @@ def _sphere_distance(x1, x2, diag=False):
     d = x1.shape[-1]
     spec = _ops.SeriesSpec(1, d, _lib.BASIS_MONOMIAL, 1.0, 0.0, -_CLAMP, _CLAMP)
     coef = torch.tensor([[0.0, 1.0]], dtype=torch.float64, device=x1.device)
-    u = _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1, x2, diag=diag)
+    u = _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1, x2, diag=diag, series=(spec, coef))
     return torch.acos(u)
 
 

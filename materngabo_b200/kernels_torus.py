@@ -50,7 +50,7 @@ class _TorusKernel(Kernel):
                     out = kf if out is None else out * kf
                 return out
             return _ops.pairwise(fn, x1c, x2c, diag=diag)
-        return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1c, x2c, diag=diag)
+        return _ops.pairwise(lambda a, b: _ops.series_gram(spec, a, b, coef), x1c, x2c, diag=diag, series=(spec, coef))
 
 
 class TorusProductOfManifoldsRiemannianGaussianKernel(_TorusKernel):

@@ -676,11 +676,18 @@ class ShardedPosterior:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.compute = compute
 
-    def broadcast_state(self, tensors: dict, src: int = 0):
-        """Broadcast a dict of same-shaped-on-every-rank tensors from ``src`` (shapes are exchanged first)."""
+    def broadcast_state(self, tensors: dict, src: int = 0, meta=None):
+        """Broadcast a dict of tensors from ``src``.
+
+        ``meta`` = {name: (shape, dtype)} known on EVERY rank (e.g. derived from n and the kernel): the state then
+        travels as ONE flat buffer per dtype - one NCCL broadcast over NVLink, no pickled shape exchange, no host
+        synchronisation, receive buffers cached across calls (a refit re-broadcasts into the same memory).  Without
+        ``meta`` the shapes are exchanged first (``broadcast_object_list``) and each tensor is broadcast on its own."""
         dist = self.dist
         if self.world == 1:
             return tensors
+        if meta is not None:
+            return self._broadcast_flat(tensors, src, meta)
         names = sorted(tensors.keys()) if self.rank == src else None
         meta = [names, {k: (tuple(tensors[k].shape), str(tensors[k].dtype)) for k in names}] if self.rank == src else [None, None]
         dist.broadcast_object_list(meta, src=src, group=self.group)
@@ -698,6 +705,36 @@ class ShardedPosterior:
             out[k] = t
         return out
 
+    def _broadcast_flat(self, tensors, src, meta):
+        dist = self.dist
+        like = next(iter(tensors.values())) if tensors else None
+        dev = like.device if like is not None else self._default_device()
+        out = {}
+        by_dtype = {}
+        for name in sorted(meta):
+            shape, dtype = meta[name]
+            by_dtype.setdefault(dtype, []).append((name, tuple(shape)))
+        cache = self.__dict__.setdefault("_flat_cache", {})
+        for dtype, items in by_dtype.items():
+            sizes = [int(math.prod(shape)) for _, shape in items]
+            total = sum(sizes)
+            key = (str(dtype), total, str(dev))
+            flat = cache.get(key)
+            if flat is None:
+                flat = torch.empty(total, dtype=dtype, device=dev)
+                cache[key] = flat
+            if self.rank == src:
+                off = 0
+                for (name, shape), sz in zip(items, sizes):
+                    flat[off:off + sz].copy_(tensors[name].reshape(-1))
+                    off += sz
+            dist.broadcast(flat, src=src, group=self.group)
+            off = 0
+            for (name, shape), sz in zip(items, sizes):
+                out[name] = tensors[name] if self.rank == src else flat[off:off + sz].view(shape)
+                off += sz
+        return out
+
     def _default_device(self):
         return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
 
@@ -712,12 +749,24 @@ class ShardedPosterior:
             allc = [torch.zeros_like(cnt) for _ in range(self.world)]
             dist.all_gather(allc, cnt, group=self.group)
             sizes = [int(c.item()) for c in allc]
-        packed = torch.stack([mean, var])                       # one collective for both
         pad = max(sizes)
-        buf = torch.zeros((2, pad), dtype=packed.dtype, device=packed.device)
-        buf[:, :packed.shape[1]] = packed
-        parts = [torch.empty_like(buf) for _ in range(self.world)]
-        dist.all_gather(parts, buf, group=self.group)
-        mean_all = torch.cat([p[0, :s] for p, s in zip(parts, sizes)])
-        var_all = torch.cat([p[1, :s] for p, s in zip(parts, sizes)])
-        return mean_all, var_all
+        cache = self.__dict__.setdefault("_gather_cache", {})
+        key = (pad, self.world, str(mean.device), mean.dtype)
+        bufs = cache.get(key)
+        if bufs is None:
+            bufs = (torch.empty((self.world, pad), dtype=mean.dtype, device=mean.device),
+                    torch.empty((self.world, pad), dtype=mean.dtype, device=mean.device))
+            cache[key] = bufs
+        outs = []
+        for src_t, buf in ((mean, bufs[0]), (var, bufs[1])):
+            if src_t.shape[0] == pad:
+                piece = src_t.contiguous()
+            else:
+                piece = torch.zeros(pad, dtype=src_t.dtype, device=src_t.device)
+                piece[:src_t.shape[0]] = src_t
+            dist.all_gather_into_tensor(buf.view(-1), piece, group=self.group)
+            if all(sz == pad for sz in sizes):
+                outs.append(buf.view(-1))                        # equal shards: the gathered buffer IS the result
+            else:
+                outs.append(torch.cat([buf[r, :sz] for r, sz in enumerate(sizes)]))
+        return outs[0], outs[1]

@@ -410,7 +410,29 @@ def test_quadrature_kernels_botorch_batch_layout():
     assert rel_err(out.squeeze(-2), R.hyperbolic_integrated_matern(xc, xt, 2, 2.5, 1.0, 32)) < TOL
     d = k.forward(x.to(DEV), x.to(DEV), diag=True)
     full = k.forward(x.to(DEV), x.to(DEV))
-    assert d.shape == (30,) and rel_err(d, torch.diagonal(full)) < 1e-13
+    assert d.shape == (30,) and rel_err(d, torch.diagonal(full)) < 1e-11     # per-row profile kernel vs fused Gram kernel
+    x2 = x.roll(3, 0)
+    d2 = k.forward(x.to(DEV), x2.to(DEV), diag=True)                          # genuinely different rows
+    assert rel_err(d2, torch.diagonal(k.forward(x.to(DEV), x2.to(DEV)))) < 1e-11
+    assert rel_err(d2, torch.diagonal(R.hyperbolic_integrated_matern(x, x2, 2, 2.5, 1.0, 32))) < TOL
+
+
+def test_spd2_and_euclidean_diag_rows():
+    from materngabo_b200 import kernels_euclidean as ke, kernels_spd as kspd
+
+    gen = torch.Generator().manual_seed(10)
+    a = torch.randn(40, 2, 2, generator=gen)
+    sm = a @ a.transpose(-1, -2) + 0.5 * torch.eye(2)
+    x = torch.stack([sm[:, 0, 0], sm[:, 1, 1], sm[:, 0, 1] * 2 ** 0.5], -1).to(DEV)
+    for k in (kspd.SpdRiemannianIntegratedMaternKernel(2, nu=2.5), kspd.SpdRiemannianGaussianKernel(2)):
+        k.lengthscale = 1.0
+        d = k.forward(x, x.roll(1, 0), diag=True)
+        assert d.shape == (40,) and rel_err(d, torch.diagonal(k.forward(x, x.roll(1, 0)))) < 1e-10
+    e = ke.EuclideanIntegratedMaternKernel(dim=3, nu=2.5)
+    e.lengthscale = 0.8
+    y = torch.randn(50, 3, generator=gen).to(DEV)
+    d = e.forward(y, y.roll(2, 0), diag=True)
+    assert rel_err(d, torch.diagonal(e.forward(y, y.roll(2, 0)))) < 1e-11
 
 
 @pytest.mark.parametrize("dim", [1, 2, 3])

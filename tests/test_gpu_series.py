@@ -187,6 +187,82 @@ def test_batch_layouts_and_diag():
     assert d.shape == (23,) and rel_err(d, R.sphere_matern(xt, xt, 3, 2.5, 0.5, diag=True).reshape(-1)) < TOL
     kk = k(xt.to(DEV))                                             # Kernel.__call__ with x2 = None
     assert rel_err(kk, R.sphere_matern(xt, xt, 3, 2.5, 0.5)) < TOL
+    # a MATERIALISED expansion of the training block (no stride-0 batch dimension): still one 2-D launch
+    out2 = k.forward(xb.to(DEV), xt.to(DEV).expand(17, 23, 4).contiguous())
+    assert out2.shape == (17, 1, 23) and torch.equal(out2, out)
+    # diag of two different point lists (one thread per row)
+    xs = xt.roll(5, 0)
+    d2 = k.forward(xt.to(DEV), xs.to(DEV), diag=True)
+    assert rel_err(d2, torch.diagonal(R.sphere_matern(xt, xs, 3, 2.5, 0.5))) < TOL
+
+
+def test_batched_launch_and_diag_on_every_series_family():
+    """gridDim.z batches (sphere small kernel, torus general kernel, SO(3)) and the per-row diag kernel (monomial and
+    Chebyshev bases, multi-factor) against the oracle; a batch larger than one wave and ragged member sizes."""
+    from materngabo_b200 import kernels_so as kso, kernels_sphere as ks, kernels_torus as kt
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(5)
+    k = ks.SphereRiemannianMaternKernel(dim=10, nu=2.5)
+    k.lengthscale = 0.5
+    x3 = torch.nn.functional.normalize(torch.randn(40, 33, 11, generator=gen), dim=-1)
+    y3 = torch.nn.functional.normalize(torch.randn(40, 70, 11, generator=gen), dim=-1)
+    out = k.forward(x3.to(DEV), y3.to(DEV))
+    assert out.shape == (40, 33, 70) and rel_err(out, R.sphere_matern(x3, y3, 10, 2.5, 0.5)) < TOL
+    # two batch dimensions, non-contiguous members
+    x4 = x3.reshape(5, 8, 33, 11).transpose(0, 1)
+    y4 = y3.reshape(5, 8, 70, 11).transpose(0, 1)
+    out4 = k.forward(x4.to(DEV), y4.to(DEV))
+    assert out4.shape == (8, 5, 33, 70) and rel_err(out4, out.reshape(5, 8, 33, 70).transpose(0, 1)) < 1e-15
+    # torus: multi-factor series (general kernel) batched + diag
+    t = kt.TorusProductOfManifoldsRiemannianMaternKernel(dim=3, nu=2.5)
+    for kk in t.torus_kernel.kernels:
+        kk.lengthscale = 0.5
+    a = torch.rand(4, 9, 3, generator=gen) * 6.283185307179586
+    b = torch.rand(4, 12, 3, generator=gen) * 6.283185307179586
+    outt = t.forward(a.to(DEV), b.to(DEV))
+    reft = torch.stack([R.torus_matern(R._to_circles(a[i], 3), R._to_circles(b[i], 3), 3, 2.5, [0.5] * 3) for i in range(4)])
+    assert outt.shape == (4, 9, 12) and rel_err(outt, reft) < TOL
+    dt = t.forward(a[0].to(DEV), b[0][:9].to(DEV), diag=True)
+    assert rel_err(dt, torch.diagonal(reft[0][:, :9])) < TOL
+    # SO(3)
+    q, r = torch.linalg.qr(torch.randn(3, 20, 3, 3, generator=gen))
+    q = q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1)).unsqueeze(-2)
+    q[..., 0] *= torch.sign(torch.linalg.det(q)).unsqueeze(-1)
+    rot = q.reshape(3, 20, 9)
+    so = kso.SORiemannianMaternKernel(dim=3, nu=2.5)
+    so.lengthscale = 0.5
+    outs = so.forward(rot[:, :8].to(DEV), rot[:, 8:].to(DEV))
+    refs = torch.stack([R.so3_matern(rot[i, :8], rot[i, 8:], 2.5, 0.5) for i in range(3)])
+    assert rel_err(outs, refs) < TOL
+    ds = so.forward(rot[0, :8].to(DEV), rot[1, :8].to(DEV), diag=True)
+    assert rel_err(ds, torch.diagonal(R.so3_matern(rot[0, :8], rot[1, :8], 2.5, 0.5))) < TOL
+
+
+def test_small_problem_kernel_matches_the_panel_kernels():
+    """config1-sized problems take series_gram_fwd_small; MGB_SERIES_SMALL=0 is read once per process, so compare with
+    the oracle and with a > 4 M-entry call (panel kernel) on the same rows."""
+    from materngabo_b200 import kernels_so as kso, kernels_sphere as ks
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(8)
+    for dim in (2, 3, 10):
+        k = ks.SphereRiemannianMaternKernel(dim=dim, nu=2.5)
+        k.lengthscale = 0.5
+        x = torch.nn.functional.normalize(torch.randn(1000, dim + 1, generator=gen), dim=-1)
+        x[5] = x[3]                                       # clamp active
+        small = k.forward(x.to(DEV), x.to(DEV))           # 1 M entries: small kernel
+        assert rel_err(small, R.sphere_matern(x, x, dim, 2.5, 0.5)) < TOL
+        big = torch.nn.functional.normalize(torch.randn(5000, dim + 1, generator=gen), dim=-1)
+        big[:1000] = x
+        panel = k.forward(big.to(DEV), x.to(DEV))         # 5 M entries: persistent panel kernel
+        assert float((panel[:1000] - small).abs().max()) < 1e-14
+    for m, n in ((1, 1), (3, 130), (77, 65), (1001, 999)):
+        k = ks.SphereRiemannianGaussianKernel(dim=3)
+        k.lengthscale = 0.4
+        a = torch.nn.functional.normalize(torch.randn(m, 4, generator=gen), dim=-1)
+        b = torch.nn.functional.normalize(torch.randn(n, 4, generator=gen), dim=-1)
+        assert rel_err(k.forward(a.to(DEV), b.to(DEV)), R.sphere_gaussian(a, b, 3, 0.4)) < TOL
 
 
 @pytest.mark.parametrize("m,n", [(0, 5), (5, 0), (1, 1), (129, 65), (257, 3), (64, 127), (1, 1001)])

@@ -51,6 +51,11 @@ def _worker(rank, world, port, m, out_dir):
         else:
             state = {"like": torch.zeros(0)}
         state = sh.broadcast_state(state, src=0)
+        # the flat path: shapes known on every rank, ONE broadcast per dtype, receive buffer reused by the next call
+        meta = {"train": ((40, 4), torch.float64), "L": ((40, 40), torch.float64), "alpha": ((40,), torch.float64)}
+        for _ in range(2):
+            flat_state = sh.broadcast_state(state if rank == 0 else {"like": torch.zeros(0)}, src=0, meta=meta)
+            assert all(torch.equal(flat_state[k], state[k]) for k in meta)
         sh.compute = lambda x: R.gp_predict(kfn, state["train"], state["L"], state["alpha"], x, 1.0, 0.0)
         lo, hi = shard_bounds(m, world, rank)
         mean, var = sh.evaluate(xc[lo:hi], gather=True)
@@ -70,3 +75,48 @@ def test_world_size_2_gloo(tmp_path):
     a = torch.load(os.path.join(str(tmp_path), "mean_0.pt"))
     b = torch.load(os.path.join(str(tmp_path), "mean_1.pt"))
     assert torch.equal(a, b)   # every rank ends with the same gathered vector
+
+
+def _gram_worker(rank, world, port, m):
+    """Row-sharded Gram with the backward all-reduce of dL/dcoef: every rank ends up with the FULL
+    hyper-parameter gradient although it only saw its own rows of dL/dK."""
+    import torch.distributed as dist
+
+    from materngabo_b200.sharded_gram import sharded_series_gram
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_default_dtype(torch.float64)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gen = torch.Generator().manual_seed(1)
+        x1 = torch.nn.functional.normalize(torch.randn(m, 4, generator=gen), dim=-1)
+        x2 = torch.nn.functional.normalize(torch.randn(9, 4, generator=gen), dim=-1)
+        g_up = torch.randn(m, 9, generator=gen)
+        coef0 = torch.randn(6, generator=gen)
+
+        def gram(a, b, c):          # injected per-rank compute: a polynomial series of the inner product (plain torch)
+            u = (a @ b.t()).clamp(-1 + 1e-15, 1 - 1e-15)
+            return sum(c[k] * u ** k for k in range(c.shape[0]))
+
+        coef = coef0.clone().requires_grad_(True)
+        x2r = x2.clone().requires_grad_(True)
+        lo, hi = shard_bounds(m, world, rank)
+        x1l = x1[lo:hi].clone().requires_grad_(True)
+        k_local = sharded_series_gram(None, x1l, x2r, coef, gram_fn=gram)
+        (k_local * g_up[lo:hi]).sum().backward()
+        # single-process reference on all rows
+        cf = coef0.clone().requires_grad_(True)
+        x2f = x2.clone().requires_grad_(True)
+        x1f = x1.clone().requires_grad_(True)
+        (gram(x1f, x2f, cf) * g_up).sum().backward()
+        assert torch.allclose(coef.grad, cf.grad, rtol=0, atol=1e-12)        # completed by the all-reduce
+        assert torch.allclose(x2r.grad, x2f.grad, rtol=0, atol=1e-12)
+        assert torch.allclose(x1l.grad, x1f.grad[lo:hi], rtol=0, atol=1e-12)  # local, no collective
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_gram_backward_allreduce_world_size_2():
+    mp.spawn(_gram_worker, args=(2, _free_port(), 37), nprocs=2, join=True)
