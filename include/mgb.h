@@ -106,6 +106,25 @@ int mgb_series_gram_dx(const mgb_series_desc* desc, int order, const double* x1,
                        double* out1, double* out2, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * SO(n) character sums for n != 3 (n = 2, 4, 5, 6, 7; rank r = n / 2), rows of n*n (row-major rotation matrices).
+ *
+ * Replaces the dim != 3 branch of kernel_utils/kernels_so.py:329-362 (Matern) / :149-177 (heat): bmm -> torch.linalg.
+ * eigvals -> Python loop pairing conjugate eigenvalues -> sympy-lambdified character polynomial.  The polynomial is the
+ * reference's (host side: materngabo_b200/_so_characters.py rebuilds it exactly); its argument is the vector of
+ * eigen-angles of R1 R2^T in (0, pi) in DESCENDING order, obtained in registers from tr R, tr R^2, tr R^3 (closed form
+ * for r <= 2, trigonometric cubic for r = 3).  The reference feeds the angles in the order LAPACK lists the conjugate
+ * pairs, which makes its value order dependent; the two agree where that order is descending.
+ *   grids: [patterns][(J+1)^r] normalised coefficients G_s[a] of prod_i (cos | sin)(a_i theta_i); patterns = sign
+ *          patterns with an even number of sines in lexicographic order: r = 1: (c); r = 2: (c,c), (s,s);
+ *          r = 3: (c,c,c), (c,s,s), (s,c,s), (s,s,c).  J <= 12.
+ *   mode 0: out = K (m x n, ld = ldo).   mode 1: out[(i*n + j)*B + b] = the b-th basis product, B = mgb_son_basis_size
+ *          (hyper-parameter gradients: K = basis . grids in torch; grids unused).
+ * ------------------------------------------------------------------------------------------------ */
+long long mgb_son_basis_size(int dim, int J);
+int mgb_son_gram(int dim, int mode, const double* x1, long long m, long long ld1, const double* x2, long long n,
+                 long long ld2, const double* grids, int J, double* out, long long ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Quadrature Gram matrices.
  *
  * Hyperbolic space H^dim in Lorentz coordinates (rows dim+1 wide), dim in {1,2,3}:

@@ -44,6 +44,8 @@ PROTOTYPES = {
     "mgb_series_gram_bwd": (_I, [_DESC, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _LL, _LL, _P, _P, _P, _P]),
     "mgb_so3_to_quaternion": (_I, [_P, _LL, _LL, _P, _P, _P]),
     "mgb_series_gram_dx": (_I, [_DESC, _I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _LL, _LL, _P, _P, _P]),
+    "mgb_son_basis_size": (_LL, [_I, _I]),
+    "mgb_son_gram": (_I, [_I, _I, _P, _LL, _LL, _P, _LL, _LL, _P, _I, _P, _LL, _P]),
     "mgb_hyperbolic_gram_fwd": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _I, _D, _D, _I, _P, _LL, _P]),
     "mgb_hyperbolic_gram_bwd_coef": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _I, _D, _D, _I, _P, _LL, _P, _P]),
     "mgb_hyperbolic_gram_bwd_tval": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _I, _D, _D, _I, _P, _LL, _P, _P]),

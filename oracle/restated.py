@@ -254,6 +254,174 @@ def so3_gaussian(x1, x2, lengthscale, summands=10):
 
 
 # ----------------------------------------------------------------------------------------------
+# SO(n), n != 3: eigenvalues of R1 R2^T, conjugate pairing in LAPACK order, Weyl character sum
+# ----------------------------------------------------------------------------------------------
+def _son_root_data(n):
+    """Root-system data the reference builds with sympy (kernels_so.py:204-227, math_utils/so_root_systems.py), here in
+    exact rational arithmetic: Gram matrix B of the simple roots (integer scaled), fundamental weights in the root
+    basis, delta, the Weyl group as (matrix, determinant) pairs and the positive roots."""
+    from fractions import Fraction as Fr
+    from math import lcm
+
+    rk = n // 2
+    if n in (2, 3):
+        cm = [[Fr(2)]]
+    else:
+        cm = [[Fr(2) if i == j else (Fr(-1) if abs(i - j) == 1 else Fr(0)) for j in range(rk)] for i in range(rk)]
+        if n % 2:
+            cm[rk - 2][rk - 1] = Fr(-2)                                  # B_k (so_root_systems.py:14-17)
+        elif rk > 2:
+            for (i, j), v in {(0, 1): -1, (0, 2): -1, (1, 0): -1, (1, 2): 0, (2, 0): -1, (2, 1): 0}.items():
+                cm[rk - 3 + i][rk - 3 + j] = Fr(v)                       # D_k tail (:20-24)
+    sq = [None] * rk                                                     # squared root lengths (symmetrize, :39-60)
+    sq[0] = Fr(1)
+    changed = True
+    while changed:
+        changed = False
+        for x in range(rk):
+            for y in range(rk):
+                if sq[x] is not None and sq[y] is None and cm[x][y] != 0:
+                    sq[y] = sq[x] * cm[y][x] / cm[x][y]
+                    changed = True
+    bm = [[cm[x][y] * sq[y] / 2 for y in range(rk)] for x in range(rk)]
+    scale = 1
+    for row in bm:
+        for v in row:
+            scale = lcm(scale, v.denominator)
+    bm = [[v * scale for v in row] for row in bm]
+    # fundamental weights: columns of (cm^-1)^T, by solving cm^T w = e_i with Gaussian elimination
+    aug = [[cm[j][i] for j in range(rk)] + [Fr(int(i == c)) for c in range(rk)] for i in range(rk)]   # rows of cm^T | I
+    for c in range(rk):
+        piv = next(r for r in range(c, rk) if aug[r][c] != 0)
+        aug[c], aug[piv] = aug[piv], aug[c]
+        aug[c] = [v / aug[c][c] for v in aug[c]]
+        for r in range(rk):
+            if r != c and aug[r][c] != 0:
+                f = aug[r][c]
+                aug[r] = [a - f * b for a, b in zip(aug[r], aug[c])]
+    inv_t = [row[rk:] for row in aug]                                     # (cm^T)^-1
+    fw = inv_t                                                            # fw[i][j]: i-th root coordinate of weight j
+    delta = [sum(fw[i][j] for j in range(rk)) for i in range(rk)]
+
+    def bil(u, v):
+        return sum(u[i] * bm[i][j] * v[j] for i in range(rk) for j in range(rk))
+
+    unit = [[Fr(int(i == j)) for i in range(rk)] for j in range(rk)]
+
+    def reflect(i, v):
+        f = 2 * bil(v, unit[i]) / bil(unit[i], unit[i])
+        return tuple(a - f * b for a, b in zip(v, unit[i]))
+
+    # Weyl group through its action on the basis vectors (columns), closure under the simple reflections
+    ident = tuple(tuple(u) for u in unit)
+    group = {ident: 1}
+    frontier = [ident]
+    while frontier:
+        nxt = []
+        for g in frontier:
+            for i in range(rk):
+                h = tuple(reflect(i, col) for col in g)
+                if h not in group:
+                    group[h] = -group[g]
+                    nxt.append(h)
+        frontier = nxt
+    roots = set()
+    for g in group:
+        for col in g:
+            if all(c >= 0 for c in col):
+                roots.add(col)
+    return rk, bm, fw, delta, group, sorted(roots), bil
+
+
+def _son_summands(n, bound):
+    """Highest weights by height until >= bound summands (kernels_so.py:247-282): (shifted weight pi + delta,
+    Laplace-Beltrami eigenvalue, dimension by Weyl's dimension formula)."""
+    import itertools
+    from fractions import Fraction as Fr
+
+    rk, bm, fw, delta, group, roots, bil = _son_root_data(n)
+    out = []
+    for height in itertools.count(0):
+        for pi in itertools.product(range(height + 1), repeat=rk):
+            if sum(pi) != height:
+                continue
+            vec = [sum(fw[i][j] * pi[j] for j in range(rk)) for i in range(rk)]
+            if any(sum(bm[i][j] * vec[j] for j in range(rk)).denominator != 1 for i in range(rk)):
+                continue
+            sh = [a + b for a, b in zip(vec, delta)]
+            dim = Fr(1)
+            for r in roots:
+                dim *= bil(sh, r) / bil(delta, r)
+            out.append((sh, float(bil(sh, sh) - bil(delta, delta)), float(dim)))
+        if len(out) >= bound:
+            break
+    return rk, bm, delta, group, out
+
+
+def son_reference_angles(x1, x2, n):
+    """Arguments of the character polynomial as the reference picks them (kernels_so.py:329-346): eigvals of R1 R2^T,
+    first member of each complex-conjugate pair in the order LAPACK lists them.  (m, k, n // 2) angles."""
+    m, k = x1.shape[0], x2.shape[0]
+    a = x1.reshape(m, 1, n, n).expand(m, k, n, n).reshape(-1, n, n)
+    b = x2.reshape(1, k, n, n).expand(m, k, n, n).reshape(-1, n, n)
+    ev = torch.linalg.eigvals(torch.bmm(a, b.transpose(-1, -2)))
+    ang = torch.zeros(m * k, n // 2, dtype=F64)
+    for p in range(ev.shape[0]):
+        lst = list(ev[p])
+        q = 0
+        while lst:
+            e = lst.pop(0)
+            for i, other in enumerate(lst):
+                if torch.abs(torch.conj(e) - other) < 1e-10:
+                    ang[p, q] = torch.angle(e)
+                    q += 1
+                    del lst[i]
+                    break
+    return ang.reshape(m, k, n // 2)
+
+
+def son_kernel_from_angles(angles, n, lengthscale, nu=None, summands=10):
+    """sum_pi lambda_pi Re chi_pi / sum_pi lambda_pi dim_pi with chi_pi by Weyl's character formula evaluated
+    NUMERICALLY as a ratio of alternating sums (kernels_so.py:234-239,269 build the same ratio symbolically and cancel
+    it); x_i = exp(i angle_i) in the reference's simple-root coordinates.  nu = None: heat kernel coefficients (:101),
+    else Matern (:273).  Valid away from the zeros of the Weyl denominator (generic pairs)."""
+    rk, bm, delta, group, summ = _son_summands(n, summands)
+    so_dim = 2 * rk * rk + rk if n % 2 else 2 * rk * rk - rk
+    ls = _as_param(lengthscale).reshape(())
+    th = angles.to(torch.complex128)
+
+    def alt(weight):
+        tot = 0
+        for g, sign in group.items():
+            w = [sum(g[j][i] * weight[j] for j in range(rk)) for i in range(rk)]          # g applied to the weight
+            e = [float(sum(w[i] * bm[i][j] for i in range(rk))) for j in range(rk)]
+            tot = tot + sign * torch.exp(1j * sum(e[j] * th[..., j] for j in range(rk)))
+        return tot
+
+    den = alt(delta)
+    num_total, norm = 0, 0
+    for sh, ev, dim in summ:
+        lam = torch.exp(-ev * ls ** 2 / 2) * dim if nu is None else \
+            torch.pow(2 * _as_param(nu).reshape(()) / ls ** 2 + ev, -_as_param(nu).reshape(()) - so_dim / 2) * dim
+        num_total = num_total + lam * (alt(sh) / den).real
+        norm = norm + lam * dim
+    return num_total / norm
+
+
+def son_matern(x1, x2, n, nu, lengthscale, summands=10, angles=None):
+    """kernels_so.py:305-362, dim != 3.  ``angles`` overrides the LAPACK-order arguments (golden vectors record the ones
+    the reference used; passing angles sorted descending gives the order-independent function the CUDA path evaluates)."""
+    ang = son_reference_angles(x1, x2, n) if angles is None else angles
+    return son_kernel_from_angles(ang, n, lengthscale, nu, summands)
+
+
+def son_gaussian(x1, x2, n, lengthscale, summands=10, angles=None):
+    """kernels_so.py:121-177, dim != 3."""
+    ang = son_reference_angles(x1, x2, n) if angles is None else angles
+    return son_kernel_from_angles(ang, n, lengthscale, None, summands)
+
+
+# ----------------------------------------------------------------------------------------------
 # hyperbolic (Lorentz model)
 # ----------------------------------------------------------------------------------------------
 def lorentz_distance(x1, x2, diag=False):

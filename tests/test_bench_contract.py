@@ -62,7 +62,7 @@ def test_our_arm_json_line_on_the_gpu():
     roof = d["roofline"]
     assert roof["bound"] == "tensor" and 0 < roof["frac"] <= 1.05 and roof["achieved"] > 0 and roof["peak"] > 0
     e2e = d["e2e"]
-    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] > 8 * 300000 * 11 and e2e["d2h_bytes_per_step"] == 16 * 300000
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] >= 8 * 300000 * 11 and e2e["d2h_bytes_per_step"] == 16 * 300000
     assert abs(e2e["value"] - d["value"]) > 0              # a separate measurement, not a copy of the device number
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert "sm_mhz" in d["clocks"] and "workload" in d["config"] and "l2_policy" in d["config"]

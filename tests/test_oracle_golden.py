@@ -172,3 +172,22 @@ def test_spd2_input_gradients(name):
     ga, gb = torch.autograd.grad((k * _t(raw["G"])).sum(), [a, b])
     assert rel_err(ga, raw["gx1"]) < 1e-10
     assert rel_err(gb, raw["gx2"]) < 1e-10
+
+
+@pytest.mark.parametrize("n", [2, 4, 5, 6])
+@pytest.mark.parametrize("kind", ["matern", "gaussian"])
+def test_son_oracle_against_reference_goldens(n, kind):
+    """SO(n), n != 3 (oracle/make_golden_son.py): the restatement evaluates Weyl's character formula numerically at the
+    arguments the reference used (recorded per pair: they depend on LAPACK's eigenvalue order) - value on ALL pairs and
+    the raw_lengthscale gradient of the masked sum."""
+    raw = load_golden("son_%s_SO%d" % (kind, n))
+    ang = _t(raw["angles"])
+    raw_ls = _inv_softplus(raw["lengthscale"])
+    x1, x2 = _t(raw["x1"]), _t(raw["x2"])
+    fn = (lambda ls: R.son_matern(x1, x2, n, 2.5, ls, angles=ang)) if kind == "matern" else \
+        (lambda ls: R.son_gaussian(x1, x2, n, ls, angles=ang))
+    k = fn(_ls(raw_ls))
+    assert rel_err(k, raw["K"]) < 1e-12
+    (gl,) = torch.autograd.grad((k * _t(raw["G"])).sum(), [raw_ls])
+    assert rel_err(gl.reshape(-1), raw["g_raw_lengthscale"].reshape(-1)) < 1e-10
+    assert raw["canonical"].sum() >= 0.3 * raw["canonical"].size       # a usable share of pairs is in canonical order
