@@ -572,6 +572,7 @@ def run_gram(args, rank, world, local, min_seconds=0.0, cpu_seconds=8.0):
     launches0 = lib.mgb_launch_count()
     small = 8.0 * m * n < 4 * 126e6            # output would stay L2 resident between steps: flush L2 in between
     out = None
+    protocol = None
     graphable = args.workload in ("config1-s2", "gram-s2", "gram-s10", "gram-so3")   # quadrature kernels read their node
     if small and not graphable:                                                       # grids back on the host: eager
         flush = torch.empty(64 * 1024 * 1024, dtype=F64, device=device)     # 512 MB > 126 MB L2
@@ -605,6 +606,31 @@ def run_gram(args, rank, world, local, min_seconds=0.0, cpu_seconds=8.0):
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in evs)
         launches0 -= steps            # replays do not pass through the library's launch counter
+        # What the protocol itself costs: the same flush / event / graph-replay / event sequence around a ONE-ELEMENT
+        # kernel.  On B200 that floor is ~6 us (gpurun_out/r2_config1_probe.log), i.e. most of a 10 us reading is the
+        # replay launch path between the two events, not the Gram kernel.
+        tiny = torch.zeros(32, dtype=F64, device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            tiny.add_(1.0)
+        torch.cuda.current_stream(device).wait_stream(side)
+        fgraph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(fgraph):
+            tiny.add_(1.0)
+        fevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(steps, 400))]
+        for a, b in fevs:
+            flush.fill_(1.0)
+            a.record()
+            fgraph.replay()
+            b.record()
+        barrier()
+        floor_us = statistics.median(a.elapsed_time(b) for a, b in fevs) * 1e3
+        median_us = statistics.median(a.elapsed_time(b) for a, b in evs) * 1e3
+        protocol = {"event_to_event_us_median": median_us, "floor_us_one_element_kernel": floor_us,
+                    "above_floor_us": median_us - floor_us,
+                    "entries_per_s_above_floor": float(m) * n / max((median_us - floor_us) * 1e-6, 1e-9),
+                    "note": "value / ms_per_step are the plain event-to-event figures; the floor is the same flush + event + "
+                            "CUDA-graph replay + event sequence around a one-element kernel"}
     else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -687,7 +713,7 @@ def run_gram(args, rank, world, local, min_seconds=0.0, cpu_seconds=8.0):
                                       + " timed by its own CUDA event pair") if small
                                      else "output %.2f GB per step >> L2" % (8e-9 * m * n))},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": None,
-            "checksum": float(out[:8, :8].sum()),
+            "checksum": float(out[:8, :8].sum()), "timing_protocol": protocol,
             "cpu_baseline": None if (args.no_cpu_baseline or world > 1) else cpu_gram_baseline(args.workload, x1, x2, cpu_seconds)}
 
 
@@ -707,7 +733,7 @@ def gram_leg(args, rank, world, local):
             out[wl] = {"error": "%s: %s" % (type(exc).__name__, exc)}
             continue
         out[wl] = {k: r[k] for k in ("value", "unit", "steps", "ms_per_step", "timed_seconds", "config", "clocks", "roofline",
-                                     "cpu_baseline", "gpu_launches", "checksum")}
+                                     "cpu_baseline", "gpu_launches", "checksum", "timing_protocol")}
         torch.cuda.empty_cache()
     return out
 

@@ -197,6 +197,17 @@ int mgb_spd2_gram_bwd_coef(int use_cholesky, const double* x1, long long m, long
                            const double* bval, const double* bw, int Pb, const double* G, long long ldg,
                            double* gtcoef, void* stream);
 
+/* Eigen-decomposition front-end of the SPD product kernels (spd_input=True; Riemannian_utils/spd_utils_torch.py:293-333
+ * called from kernel_utils/kernels_spd.py:520-533,746-757; the reference uses torch.symeig, removed from torch >= 1.13):
+ * rows of x are Mandel vectors of SPD(dim) matrices, dim in {2, 3} (3 / 6 wide).  Per row, one thread: cyclic Jacobi in
+ * registers -> eigenvalues ascending, eigenvectors as columns, sign of each eigenvector fixed by "largest-magnitude
+ * component positive", then Q = det(V) V as in the reference.
+ *   target 0: out row = [eigenvalues (dim) | Q row-major (dim^2)]                  (R^d x SO(d) kernels)
+ *   target 1: out row = [eigenvalues (dim) | first row of Q (dim 2) or quaternion (dim 3, Corke's algorithm as in
+ *             Riemannian_utils/sphere_utils_torch.py:127-190)]                        (R^d x S kernels) */
+int mgb_spd_decompose(int dim, int target, const double* x, long long m, long long ld, double* out, long long ldo,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Radial profiles of the quadrature kernels and their derivatives in the pair scalar (csrc/quad_profile.cu).
  *

@@ -56,6 +56,7 @@ PROTOTYPES = {
     "mgb_spd2_gram_fwd_lattice": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P, _I, _P, _P, _I, _I, _I, _D, _D, _P, _LL, _P]),
     "mgb_spd2_gram_bwd_scales": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P, _I, _P, _P, _I, _P, _LL, _P, _P, _P]),
     "mgb_spd2_gram_bwd_coef": (_I, [_I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _I, _P, _P, _I, _P, _LL, _P, _P]),
+    "mgb_spd_decompose": (_I, [_I, _I, _P, _LL, _LL, _P, _LL, _P]),
     "mgb_radial_profile": (_I, [_I, _I, _P, _LL, _P, _P, _I, _D, _D, _I, _P, _P]),
     "mgb_radial_profile_bwd_coef": (_I, [_I, _I, _P, _LL, _P, _I, _D, _D, _I, _P, _P, _P]),
     "mgb_spd2_profile": (_I, [_I, _P, _P, _LL, _P, _P, _P, _I, _P, _P, _I, _P, _P]),

@@ -637,6 +637,26 @@ def spd2_gram_autograd(use_chol, x1, x2, tcoef, rscale, bscale, bval, bw):
                              rscale.contiguous(), bscale.contiguous(), bval.contiguous(), bw.contiguous())
 
 
+def spd_decompose(x: torch.Tensor, dim: int, target: int) -> torch.Tensor:
+    """Mandel vectors (..., d(d+1)/2) of SPD(dim) matrices -> (..., dim + dim^2) [eigenvalues | vec(Q)] (target 0) or
+    (..., dim + 2 | 4) [eigenvalues | sphere point] (target 1) on the device (csrc/spd_eigh.cu; conventions in mgb.h)."""
+    _lib.require_cuda_f64(x)
+    if inputs_need_grad(x):
+        raise NotImplementedError("spd_input=True: input gradients through the eigen-decomposition are not provided")
+    width = dim * (dim + 1) // 2
+    if x.shape[-1] != width:
+        raise RuntimeError("SPD(%d) points must be Mandel vectors with %d coordinates" % (dim, width))
+    flat = x.detach().reshape(-1, width).contiguous()
+    wout = dim + (dim * dim if target == 0 else (2 if dim == 2 else 4))
+    out = torch.empty((flat.shape[0], wout), dtype=F64, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        rc = lib.mgb_spd_decompose(dim, target, _lib.ptr(flat), flat.shape[0], width, _lib.ptr(out), wout,
+                                   _lib.stream_ptr(x.device))
+    _lib.check(rc, "mgb_spd_decompose")
+    return out.reshape(*x.shape[:-1], wout)
+
+
 # --------------------------------------------------------------------------------------------------
 # pair-batch plumbing shared by the Kernel.forward overrides
 # --------------------------------------------------------------------------------------------------

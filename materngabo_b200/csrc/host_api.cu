@@ -311,16 +311,18 @@ extern "C" long long mgb_posterior_chunk(const mgb_posterior* h) { return h ? h-
 
 extern "C" int mgb_posterior_eval_device(mgb_posterior* h, const double* xc_dev, long long m, long long ldc,
                                          double* mean_dev, double* var_dev, void* stream) {
-  if (!h || !xc_dev || !mean_dev || !var_dev || m < 0 || ldc < h->D) return fail(MGB_ERR_ARG, "posterior_eval_device: bad argument");
+  if (!h || m < 0) return fail(MGB_ERR_ARG, "posterior_eval_device: bad argument");
   if (m == 0) return MGB_OK;
+  if (!xc_dev || !mean_dev || !var_dev || ldc < h->D) return fail(MGB_ERR_ARG, "posterior_eval_device: null pointer / bad ldc");
   const long long chunk = m < h->chunk ? (m + 127) / 128 * 128 : h->chunk;
   return mgb_series_posterior(&h->desc, xc_dev, m, ldc, h->d_xt, h->n, h->ldt, h->d_coef, h->d_pack, h->kss, h->mean_const,
                               mean_dev, var_dev, h->d_ws, h->ws_bytes, chunk, stream);
 }
 
 extern "C" int mgb_posterior_eval_host(mgb_posterior* h, const double* xc, long long m, double* mean, double* var) {
-  if (!h || !xc || !mean || !var || m < 0) return fail(MGB_ERR_ARG, "posterior_eval_host: bad argument");
+  if (!h || m < 0) return fail(MGB_ERR_ARG, "posterior_eval_host: bad argument");
   if (m == 0) return MGB_OK;
+  if (!xc || !mean || !var) return fail(MGB_ERR_ARG, "posterior_eval_host: null pointer");
   int prev = 0;
   cudaGetDevice(&prev);
   MGB_TRY(check_cuda(cudaSetDevice(h->device), "cudaSetDevice"));

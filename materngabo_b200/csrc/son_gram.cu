@@ -10,16 +10,17 @@
 // random pairs for r = 2, tests/golden/son_*.npz record which).
 //
 // Per pair, in registers (no eigen-solver):
-//   1. R = R1 R2^T (n x n), t_k = tr R^k for k = 1..r;
-//   2. power sums of c_i = cos theta_i:  tr R^k = (n mod 2) + 2 sum_i cos(k theta_i)  ->  p_1, p_2, p_3 ->
-//      elementary symmetric functions -> c_i as roots of a quadratic (r = 2, closed form) or of a cubic with three
-//      real roots (r = 3, trigonometric form), sorted ascending (= angles descending); s_i = +sqrt(1 - c_i^2);
+//   1. R = R1 R2^T (n x n) and its symmetric part S = (R + R^T) / 2, whose eigenvalues are cos theta_i, each twice
+//      (plus 1 for odd n);
+//   2. eigenvalues of S by cyclic Jacobi rotations in registers (absolute accuracy ~1e-16 also for coinciding angles -
+//      a closed form through tr R^k / symmetric functions loses half the digits there, e.g. on the diagonal of a Gram
+//      matrix where R = I), sorted ascending, paired (the largest dropped for odd n): c_1 <= c_2 <= ... = angles
+//      descending; s_i = +sqrt(1 - c_i^2);
 //   3. cos(a theta_i) = T_a(c_i), sin(a theta_i) = s_i U_{a-1}(c_i) by three-term recurrences, a <= J;
 //   4. K = sum over sign patterns and exponent grids G_s[a] prod_i (cos | sin)(a_i theta_i): the host
 //      (materngabo_b200/_so_characters.py) folds hyper-parameters, multiplicities and the normalisation into G.
 // mode 1 writes the products themselves (the basis, for hyper-parameter gradients through torch).
-// Accuracy: c_i come from symmetric functions, so two nearly equal angles (|c_1 - c_2| = e) lose digits like
-// 1e-16 / e; generic pairs are at 1e-14.
+// Accuracy: 1e-14 for generic pairs; sin theta_i = sqrt(1 - c_i^2) carries 1e-16 / theta_i for tiny angles.
 #include "mgb_common.cuh"
 #include <cmath>
 
@@ -46,44 +47,53 @@ struct SonPatterns<2> { static constexpr int count = 2; };   // (c,c), (s,s)
 template <>
 struct SonPatterns<3> { static constexpr int count = 4; };   // (c,c,c), (c,s,s), (s,c,s), (s,s,c)
 
-// cosines of the eigen-angles, ascending, from power sums
-template <int R>
-__device__ __forceinline__ void son_cosines(const double (&p)[3], double (&c)[R]) {
-  if constexpr (R == 1) {
-    c[0] = p[0];
-  } else if constexpr (R == 2) {
-    // c1 + c2 = p1, c1^2 + c2^2 = p2: (c1 - c2)^2 = 2 p2 - p1^2
-    const double disc = fmax(2.0 * p[1] - p[0] * p[0], 0.0);
-    const double rt = sqrt(disc);
-    c[0] = 0.5 * (p[0] - rt);
-    c[1] = 0.5 * (p[0] + rt);
-  } else {
-    // t^3 - e1 t^2 + e2 t - e3 = 0 with three real roots: t = e1/3 + 2 sqrt(-P/3) cos(phi - 2 pi k / 3)
-    const double e1 = p[0];
-    const double e2 = 0.5 * (p[0] * p[0] - p[1]);
-    const double e3 = (p[0] * p[0] * p[0] - 3.0 * p[0] * p[1] + 2.0 * p[2]) / 6.0;
-    const double sh = e1 / 3.0;
-    const double P = e2 - e1 * e1 / 3.0;                            // depressed: u^3 + P u + Q
-    const double Q = -2.0 * e1 * e1 * e1 / 27.0 + e1 * e2 / 3.0 - e3;
-    const double mag = sqrt(fmax(-P / 3.0, 0.0));
-    double arg = (mag > 0.0) ? (3.0 * Q / (2.0 * P * mag)) : 0.0;   // = cos(3 phi)
-    arg = fmin(1.0, fmax(-1.0, arg));
-    const double phi = acos(arg) / 3.0;
-    const double r0 = sh + 2.0 * mag * cos(phi);                            // largest
-    const double r1 = sh + 2.0 * mag * cos(phi - 2.0943951023931953);       // middle (phi in [0, pi/3])
-    const double r2 = sh + 2.0 * mag * cos(phi + 2.0943951023931953);       // smallest
-    c[0] = r2;
-    c[1] = r1;
-    c[2] = r0;
-    // one Newton step on each root polishes the trigonometric evaluation
+// eigenvalues of the symmetric D x D matrix a (destroyed) by cyclic Jacobi rotations, ascending in ev
+template <int D>
+__device__ __forceinline__ void sym_eigenvalues(double (&a)[D][D], double (&ev)[D]) {
+  if constexpr (D > 1) {
+    for (int sweep = 0; sweep < 15; ++sweep) {
+      double off = 0.0, dg = 0.0;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const double t = c[i];
-      const double f = ((t - e1) * t + e2) * t - e3;
-      const double df = (3.0 * t - 2.0 * e1) * t + e2;
-      if (fabs(df) > 1e-8) c[i] = t - f / df;
+      for (int p = 0; p < D; ++p) {
+        dg = fma(a[p][p], a[p][p], dg);
+#pragma unroll
+        for (int q = p + 1; q < D; ++q) off = fma(a[p][q], a[p][q], off);
+      }
+      if (off <= 1e-33 * dg) break;
+#pragma unroll
+      for (int p = 0; p < D - 1; ++p)
+#pragma unroll
+        for (int q = p + 1; q < D; ++q) {
+          const double apq = a[p][q];
+          if (apq != 0.0) {
+            const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+            const double c = rsqrt(fma(t, t, 1.0)), sn = t * c;
+            a[p][p] = fma(-t, apq, a[p][p]);
+            a[q][q] = fma(t, apq, a[q][q]);
+            a[p][q] = a[q][p] = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+              if (k != p && k != q) {
+                const double akp = a[k][p], akq = a[k][q];
+                a[k][p] = a[p][k] = c * akp - sn * akq;
+                a[k][q] = a[q][k] = sn * akp + c * akq;
+              }
+            }
+          }
+        }
     }
   }
+#pragma unroll
+  for (int k = 0; k < D; ++k) ev[k] = a[k][k];
+#pragma unroll
+  for (int pass = 0; pass < D - 1; ++pass)
+#pragma unroll
+    for (int k = 0; k < D - 1 - pass; ++k) {
+      const double lo = fmin(ev[k], ev[k + 1]), hi = fmax(ev[k], ev[k + 1]);
+      ev[k] = lo;
+      ev[k + 1] = hi;
+    }
 }
 
 template <int DIM>
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(kSonTile * kSonTile) son_gram_kernel(SonParams
   const double* A = a_s + threadIdx.y * D2;
   const double* B = b_s + threadIdx.x * D2;
 
-  // ---- R = A B^T and traces of its powers -------------------------------------------------------
+  // ---- R = A B^T ------------------------------------------------------------------------------------
   double Rm[DIM][DIM];
 #pragma unroll
   for (int a = 0; a < DIM; ++a)
@@ -125,35 +135,18 @@ __global__ void __launch_bounds__(kSonTile * kSonTile) son_gram_kernel(SonParams
       for (int k = 0; k < DIM; ++k) s = fma(A[a * DIM + k], B[b * DIM + k], s);
       Rm[a][b] = s;
     }
-  double tr[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-  for (int a = 0; a < DIM; ++a) tr[0] += Rm[a][a];
-  if constexpr (R >= 2) {
-#pragma unroll
-    for (int a = 0; a < DIM; ++a) {
-      double row2[DIM];                       // row a of R^2
-#pragma unroll
-      for (int b = 0; b < DIM; ++b) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < DIM; ++k) s = fma(Rm[a][k], Rm[k][b], s);
-        row2[b] = s;
-      }
-      tr[1] += row2[a];
-      if constexpr (R >= 3) {
-#pragma unroll
-        for (int b = 0; b < DIM; ++b) tr[2] = fma(row2[b], Rm[b][a], tr[2]);
-      }
-    }
-  }
-  // tr R^k = odd + 2 sum_i cos(k theta_i);  cos 2t = 2 c^2 - 1, cos 3t = 4 c^3 - 3 c
-  constexpr double odd = (DIM & 1) ? 1.0 : 0.0;
-  double pw[3];
-  pw[0] = 0.5 * (tr[0] - odd);
-  pw[1] = 0.5 * (0.5 * (tr[1] - odd) + R);
-  pw[2] = 0.25 * (0.5 * (tr[2] - odd) + 3.0 * pw[0]);
   double c[R], s[R];
-  son_cosines<R>(pw, c);
+  {
+    double S[DIM][DIM], ev[DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)
+#pragma unroll
+      for (int b = 0; b < DIM; ++b) S[a][b] = 0.5 * (Rm[a][b] + Rm[b][a]);
+    sym_eigenvalues<DIM>(S, ev);
+    // cos theta_i twice each (the single eigenvalue 1 of odd n is the largest and is dropped)
+#pragma unroll
+    for (int q = 0; q < R; ++q) c[q] = 0.5 * (ev[2 * q] + ev[2 * q + 1]);
+  }
   // ascending cosines = descending angles: (c[0], theta_1 largest) is the first argument of the polynomial
 #pragma unroll
   for (int q = 0; q < R; ++q) {

@@ -140,10 +140,14 @@ class SpdRiemannianIntegratedMaternKernel(_NuMixin, Kernel):
 class _SpdProductKernel(Kernel):
     has_lengthscale = True
 
+    decompose_target = 1      # 1: [eigenvalues | sphere point] (R x S kernels); 0: [eigenvalues | rotation] (R x SO)
+
     def forward(self, x1, x2, diag=False, **params):
         if self.spd_input:
-            raise NotImplementedError("spd_input=True needs the SPD eigen-decomposition front-end (torch.symeig in the "
-                                      "reference); pass eigenvalues + sphere/rotation coordinates (spd_input=False)")
+            # Mandel vectors -> eigenvalues + rotation / sphere coordinates on the device (kernels_spd.py:520-533,746-757;
+            # the reference's torch.symeig is gone, the solver and its sign convention are csrc/spd_eigh.cu's)
+            x1 = _ops.spd_decompose(x1, self.dim, self.decompose_target)
+            x2 = _ops.spd_decompose(x2, self.dim, self.decompose_target)
         return self.spd_kernel.forward(x1, x2, diag=diag)
 
 
@@ -195,6 +199,8 @@ class SpdProductOfRSManifoldsRiemannianMaternKernel(_SpdProductKernel):
 
 
 class SpdProductOfRSOManifoldsRiemannianGaussianKernel(_SpdProductKernel):
+    decompose_target = 0
+
     def __init__(self, dim, spd_input=False, **kwargs):
         self.has_lengthscale = True
         super().__init__(has_lengthscale=True, ard_num_dims=None, **kwargs)
@@ -209,6 +215,8 @@ class SpdProductOfRSOManifoldsRiemannianGaussianKernel(_SpdProductKernel):
 
 
 class SpdProductOfRSOManifoldsRiemannianMaternKernel(_SpdProductKernel):
+    decompose_target = 0
+
     def __init__(self, dim, nu=None, nu_so=None, nu_prior_so=None, nu_euclidean=None, nu_prior_euclidean=None,
                  spd_input=False, **kwargs):
         self.has_lengthscale = True

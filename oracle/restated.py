@@ -600,6 +600,53 @@ def spd_product_matern(x1, x2, dim, nu, ls_euclidean, ls_manifold, manifold):
     return ke * km
 
 
+def rotation_to_quaternion(rot):
+    """Riemannian_utils/sphere_utils_torch.py:127-190 (Corke's algorithm), rot: (..., 3, 3) -> (..., 4)."""
+    shape = rot.shape[:-2]
+    r = rot.reshape(-1, 3, 3)
+    out = torch.zeros(r.shape[0], 4, dtype=rot.dtype)
+    for i in range(r.shape[0]):
+        m = r[i]
+        qs = min(float(torch.sqrt(m[0, 0] + m[1, 1] + m[2, 2] + 1) / 2.0), 1.0)
+        kx, ky, kz = m[2, 1] - m[1, 2], m[0, 2] - m[2, 0], m[1, 0] - m[0, 1]
+        if m[0, 0] >= m[1, 1] and m[0, 0] >= m[2, 2]:
+            k1 = (m[0, 0] - m[1, 1] - m[2, 2] + 1, m[1, 0] + m[0, 1], m[2, 0] + m[0, 2])
+            add = kx >= 0
+        elif m[1, 1] >= m[2, 2]:
+            k1 = (m[1, 0] + m[0, 1], m[1, 1] - m[0, 0] - m[2, 2] + 1, m[2, 1] + m[1, 2])
+            add = ky >= 0
+        else:
+            k1 = (m[2, 0] + m[0, 2], m[2, 1] + m[1, 2], m[2, 2] - m[0, 0] - m[1, 1] + 1)
+            add = kz >= 0
+        sg = 1.0 if add else -1.0
+        kv = torch.stack([kx + sg * k1[0], ky + sg * k1[1], kz + sg * k1[2]])
+        nm = kv.norm()
+        out[i, 0] = qs
+        if nm != 0:
+            out[i, 1:] = (1 - qs ** 2) ** 0.5 / nm * kv
+    return out.reshape(*shape, 4)
+
+
+def spd_decompose(x, dim, target):
+    """spd_to_so_and_euclidean_torch / spd_to_sphere_and_euclidean_torch (Riemannian_utils/spd_utils_torch.py:293-333)
+    with torch.linalg.eigh in place of the removed torch.symeig and the sign convention the CUDA front-end states
+    (largest-magnitude component of every eigenvector positive), then Q = det(V) V (:309-311).
+    target 0 -> [eigenvalues | vec(Q)], target 1 -> [eigenvalues | first row of Q (dim 2) or quaternion (dim 3)]."""
+    mat = mandel_to_sym(x)
+    ev, vec = torch.linalg.eigh(mat)
+    big = vec.abs().argmax(dim=-2, keepdim=True)
+    sign = torch.sign(torch.gather(vec, -2, big))
+    vec = vec * sign
+    q = torch.linalg.det(vec).unsqueeze(-1).unsqueeze(-1) * vec
+    if target == 0:
+        tail = q.reshape(*q.shape[:-2], dim * dim)
+    elif dim == 2:
+        tail = q[..., 0, :]
+    else:
+        tail = rotation_to_quaternion(q)
+    return torch.cat([ev, tail], dim=-1)
+
+
 # ----------------------------------------------------------------------------------------------
 # exact GP posterior + analytic EI (gpytorch / botorch arithmetic; unvendored - see SURVEY 8c)
 # ----------------------------------------------------------------------------------------------

@@ -179,8 +179,78 @@ def test_spd_product_kernels(name, cls, dim, nu):
     manifold_kernel = k.so_kernel if "RSO" in cls else k.sphere_kernel
     manifold_kernel.lengthscale = float(g["ls_manifold"])
     assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
+
+
+def _random_spd_mandel(cnt, dim, gen, spread=1.0):
+    a = torch.randn(cnt, dim, dim, generator=gen)
+    sm = a @ a.transpose(-1, -2) * spread + 0.3 * torch.eye(dim)
+    if dim == 2:
+        return torch.stack([sm[:, 0, 0], sm[:, 1, 1], sm[:, 0, 1] * 2 ** 0.5], -1)
+    return torch.stack([sm[:, 0, 0], sm[:, 1, 1], sm[:, 2, 2], sm[:, 0, 1] * 2 ** 0.5, sm[:, 1, 2] * 2 ** 0.5,
+                        sm[:, 0, 2] * 2 ** 0.5], -1)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_spd_eigen_front_end_conventions_and_reconstruction(dim):
+    """csrc/spd_eigh.cu: Q diag(ev) Q^T reconstructs S to 1e-13, Q is orthogonal, eigenvalues
+    ascending, every eigenvector's largest component positive before the reference's Q = det(V) V, and the result
+    agrees with the oracle's torch.linalg.eigh under the same convention - incl. nearly isotropic matrices, a diagonal
+    matrix and widely spread eigenvalues."""
+    from materngabo_b200 import _ops
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(40 + dim)
+    x = _random_spd_mandel(500, dim, gen)
+    x[0] = 0.0
+    x[0, :dim] = torch.arange(1, dim + 1, dtype=torch.float64)            # already diagonal
+    x[1] = x[0] + 1e-9 * torch.randn(x.shape[1], generator=gen)           # tiny off-diagonal part
+    x[2:20] = _random_spd_mandel(18, dim, gen, spread=1e6)                # condition ~1e6
+    out = _ops.spd_decompose(x.to(DEV), dim, 0).cpu()
+    ev, q = out[:, :dim], out[:, dim:].reshape(-1, dim, dim)
+    sm = R.mandel_to_sym(x)
+    rec = q @ torch.diag_embed(ev) @ q.transpose(-1, -2)
+    scale = sm.abs().amax(dim=(-1, -2), keepdim=True)
+    assert float(((rec - sm).abs() / scale).max()) < 1e-13
+    assert float((q.transpose(-1, -2) @ q - torch.eye(dim)).abs().max()) < 1e-14
+    assert bool((ev[:, 1:] >= ev[:, :-1]).all())
+    assert float((ev - torch.linalg.eigvalsh(sm)).abs().max() / float(scale.max())) < 1e-14
+    if dim == 3:
+        assert float((torch.linalg.det(q) - 1.0).abs().max()) < 1e-13     # det(V) V lands in SO(3)
+    ref = R.spd_decompose(x, dim, 0)
+    generic = slice(20, None)                                              # well separated eigenvalues
+    assert float((out[generic] - ref[generic]).abs().max()) < 1e-10
+    sph = _ops.spd_decompose(x.to(DEV), dim, 1).cpu()
+    assert sph.shape == (500, dim + (2 if dim == 2 else 4))
+    assert float((sph[generic] - R.spd_decompose(x, dim, 1)[generic]).abs().max()) < 1e-10
+    assert float((sph[:, dim:].norm(dim=-1) - 1.0).abs().max()) < 1e-13
+    assert _ops.spd_decompose(x[:0].to(DEV), dim, 0).shape == (0, dim + dim * dim)
+
+
+@pytest.mark.parametrize("cls,dim,manifold", [("SpdProductOfRSOManifoldsRiemannianMaternKernel", 3, "so"),
+                                              ("SpdProductOfRSManifoldsRiemannianMaternKernel", 3, "s"),
+                                              ("SpdProductOfRSManifoldsRiemannianMaternKernel", 2, "s")])
+def test_spd_product_kernels_with_spd_input(cls, dim, manifold):
+    """spd_input=True end to end: Mandel vectors -> device eigen-decomposition -> product kernel, against the oracle's
+    product kernel fed the SAME decomposition (the reference's own, torch.symeig, no longer exists)."""
+    from materngabo_b200 import _ops, kernels_spd as ksp
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(50 + dim)
+    x1, x2 = _random_spd_mandel(23, dim, gen), _random_spd_mandel(17, dim, gen)
+    k = getattr(ksp, cls)(dim=dim, nu=2.5, spd_input=True)
+    k.Euclidean_kernel.lengthscale = 1.1
+    (k.so_kernel if manifold == "so" else k.sphere_kernel).lengthscale = 0.6
+    out = k.forward(x1.to(DEV), x2.to(DEV))
+    target = 0 if manifold == "so" else 1
+    d1, d2 = _ops.spd_decompose(x1.to(DEV), dim, target).cpu(), _ops.spd_decompose(x2.to(DEV), dim, target).cpu()
+    ref = R.spd_product_matern(d1, d2, dim, 2.5, 1.1, 0.6, manifold)
+    assert out.shape == (23, 17) and rel_err(out, ref) < TOL
+    pre = getattr(ksp, cls)(dim=dim, nu=2.5, spd_input=False)
+    pre.Euclidean_kernel.lengthscale = 1.1
+    (pre.so_kernel if manifold == "so" else pre.sphere_kernel).lengthscale = 0.6
+    assert rel_err(pre.forward(d1.to(DEV), d2.to(DEV)), out) < 1e-14
     with pytest.raises(NotImplementedError):
-        getattr(ksp, cls)(dim=dim, nu=nu, spd_input=True).forward(_t(g["x1"]), _t(g["x2"]))
+        k.forward(x1.to(DEV).requires_grad_(True), x2.to(DEV))
 
 
 # ---- input gradients / Hessian-vector products (trust-region inner loop, SURVEY.md 8f rank 1) -------------------

@@ -152,12 +152,16 @@ def test_so3(name, cls):
         assert rel_err(k.forward(_t(g["x1"]), _t(g["x2"])), g["K"]) < TOL
 
 
-def test_so_other_dims_raise():
+def test_so_unsupported_dims_raise():
+    """n = 2, 4 ... 7 run on csrc/son_gram.cu (tests/test_gpu_son.py); rank > 3 is refused loudly."""
     from materngabo_b200 import kernels_so as kso
 
-    k = kso.SORiemannianMaternKernel(dim=4, nu=2.5)
+    k = kso.SORiemannianMaternKernel(dim=8, nu=2.5)
     with pytest.raises(NotImplementedError):
-        k.forward(torch.zeros(2, 16, device=DEV), torch.zeros(2, 16, device=DEV))
+        k.forward(torch.zeros(2, 64, device=DEV), torch.zeros(2, 64, device=DEV))
+    k4 = kso.SORiemannianMaternKernel(dim=4, nu=2.5)
+    with pytest.raises(RuntimeError):
+        k4.forward(torch.zeros(2, 9, device=DEV), torch.zeros(2, 9, device=DEV))      # wrong row width
 
 
 def test_circle_dimension_raises_like_reference():

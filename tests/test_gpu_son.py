@@ -47,8 +47,10 @@ def test_parity_with_the_reference_on_canonical_pairs(n, kind):
     ang = torch.from_numpy(g["angles"]).abs().sort(dim=-1, descending=True).values
     full = R.son_matern(x1, x2, n, 2.5, 0.5, angles=ang) if kind == "matern" else R.son_gaussian(x1, x2, n, 0.5, angles=ang)
     assert rel_err(out, full) < TOL
-    if n > 2:      # and the reference really is order dependent: the non-canonical pairs differ
+    if n in (5, 6):      # the reference really is order dependent there: the non-canonical pairs differ
         assert float((full - ref)[~mask].abs().max()) > 1e-6
+    else:                # n = 2 (one angle) and n = 4 (the A_2 polynomial is symmetric in its two arguments): every pair
+        assert float((out - ref).abs().max()) < TOL * float(ref.abs().max())
 
 
 @pytest.mark.parametrize("n", [4, 5])
