@@ -310,9 +310,33 @@ int mgb_series_posterior(const mgb_series_desc* desc, const double* xc, long lon
  *   out[0] = 1/2 r^T Kt^-1 r + 1/2 log det Kt + n/2 log(2 pi)
  *   out[1..3] = d out[0] / d (outputscale, noise, mean),  out[4 + k] = d out[0] / d coef[k]
  *   *status = 0, or j + 1 when the j-th pivot of the Cholesky factorisation was not positive (outputs are NaN).
- * n <= mgb_series_mll_max_n(factor_width, n_terms) (160 for S^3 with 10 terms).
+ * n <= mgb_series_mll_single_cta_max_n(factor_width, n_terms) (160 for S^3 with 10 terms): ONE launch, everything in
+ * shared memory (mgb_series_mll / mgb_dense_mll / mgb_series_fit / mgb_dense_fit).  Up to mgb_series_mll_max_n (16384):
+ * the multi-CTA path below (mgb_series_mll_large / mgb_dense_mll_large / mgb_dense_fit_large, caller-owned workspace).
  * ------------------------------------------------------------------------------------------------ */
 long long mgb_series_mll_max_n(int factor_width, int n_terms);
+long long mgb_series_mll_single_cta_max_n(int factor_width, int n_terms);
+
+/* Multi-CTA dense SPD path (csrc/dense_spd.cu) for 160 < n <= mgb_dense_max_n(): replaces torch.linalg.cholesky /
+ * cholesky_solve / solve_triangular (cuSOLVER, cuBLAS) in the marginal-likelihood step and in the posterior fit.
+ *   Cholesky: one COOPERATIVE launch for the whole factorisation (32-column panels; diagonal block in one warp by
+ *   shuffles; grid barriers instead of launches);  L^-1: recursive doubling, two batched GEMMs per level;
+ *   Kt^-1 = L^-T L^-1: one GEMM with the k-range clipped to the triangles.
+ * Same outputs as the single-CTA entry points.  hyper = DEVICE scalars (outputscale, noise, mean).  Workspaces are
+ * caller-owned, 16-byte aligned, mgb_dense_{fit,mll}_workspace_bytes(n) bytes.  mgb_dense_fit_large: rinv (and rinv_t,
+ * may be NULL) are n x ldo with ldo = n rounded up to an even number; zeros above the diagonal.  *status = 0 or the
+ * failing pivot + 1. */
+long long mgb_dense_max_n(void);
+long long mgb_dense_fit_workspace_bytes(long long n);
+long long mgb_dense_mll_workspace_bytes(long long n);
+int mgb_dense_fit_large(const double* K, long long n, long long ldk, const double* y, const double* hyper, double* rinv,
+                        double* rinv_t, long long ldo, double* alpha, double* nll, int* status, void* workspace,
+                        long long workspace_bytes, void* stream);
+int mgb_dense_mll_large(const double* K, long long n, long long ldk, const double* y, const double* hyper, double* out,
+                        double* G, long long ldg, int* status, void* workspace, long long workspace_bytes, void* stream);
+int mgb_series_mll_large(const mgb_series_desc* desc, const double* x, long long n, long long ld, const double* y,
+                         const double* coef, const double* hyper, double* out, int* status, void* workspace,
+                         long long workspace_bytes, void* stream);
 int mgb_series_mll(const mgb_series_desc* desc, const double* x, long long n, long long ld, const double* y,
                    const double* coef, const double* hyper, double* out, int* status, void* stream);
 

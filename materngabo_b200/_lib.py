@@ -90,6 +90,13 @@ PROTOTYPES = {
     "mgb_pair_scalars": (_I, [_I, _I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P]),
     "mgb_spectral_coef": (_I, [_I, _I, _I, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),
     "mgb_series_mll_max_n": (_LL, [_I, _I]),
+    "mgb_series_mll_single_cta_max_n": (_LL, [_I, _I]),
+    "mgb_dense_max_n": (_LL, []),
+    "mgb_dense_fit_workspace_bytes": (_LL, [_LL]),
+    "mgb_dense_mll_workspace_bytes": (_LL, [_LL]),
+    "mgb_dense_fit_large": (_I, [_P, _LL, _LL, _P, _P, _P, _P, _LL, _P, _P, _P, _P, _LL, _P]),
+    "mgb_dense_mll_large": (_I, [_P, _LL, _LL, _P, _P, _P, _P, _LL, _P, _P, _LL, _P]),
+    "mgb_series_mll_large": (_I, [_DESC, _P, _LL, _LL, _P, _P, _P, _P, _P, _P, _LL, _P]),
     "mgb_series_fit": (_I, [_DESC, _P, _LL, _LL, _P, _P, _P, _P, _P, _LL, _P, _P, _P, _P]),
     "mgb_series_mll": (_I, [_DESC, _P, _LL, _LL, _P, _P, _P, _P, _P, _P]),
     "mgb_dense_mll": (_I, [_P, _LL, _LL, _P, _P, _P, _P, _LL, _P, _P]),

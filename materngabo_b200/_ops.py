@@ -180,6 +180,19 @@ def series_gram(spec: SeriesSpec, x1: torch.Tensor, x2: torch.Tensor, coef: torc
     return SeriesGram.apply(spec, _c2d(x1), _c2d(x2), coef.contiguous())
 
 
+_DENSE_WS = {}
+
+
+def _dense_workspace(device, nbytes: int) -> torch.Tensor:
+    """Cached scratch for the multi-CTA dense path (csrc/dense_spd.cu), one buffer per device, grows, never shrinks."""
+    key = str(device)
+    buf = _DENSE_WS.get(key)
+    if buf is None or buf.numel() * 8 < nbytes:
+        buf = torch.empty((nbytes + 7) // 8, dtype=F64, device=device)
+        _DENSE_WS[key] = buf
+    return buf
+
+
 class SeriesMLL(torch.autograd.Function):
     """Fused negative log marginal likelihood of an exact GP over a single-factor series kernel (csrc/mll.cu):
     (x, y, coef, hyper = [outputscale, noise, mean]) -> (nll, status).  The gradients with respect to ``coef`` and
@@ -192,9 +205,16 @@ class SeriesMLL(torch.autograd.Function):
         out = torch.empty(4 + t, dtype=F64, device=x.device)
         status = torch.zeros(1, dtype=torch.int32, device=x.device)
         d = spec.desc(t)
+        n = x.shape[0]
         with torch.cuda.device(x.device):
-            rc = lib.mgb_series_mll(C.byref(d), _lib.ptr(x), x.shape[0], x.stride(0), _lib.ptr(y), _lib.ptr(coef),
-                                    _lib.ptr(hyper), _lib.ptr(out), _lib.ptr(status), _lib.stream_ptr(x.device))
+            if n <= lib.mgb_series_mll_single_cta_max_n(spec.factor_width, int(t)):
+                rc = lib.mgb_series_mll(C.byref(d), _lib.ptr(x), n, x.stride(0), _lib.ptr(y), _lib.ptr(coef),
+                                        _lib.ptr(hyper), _lib.ptr(out), _lib.ptr(status), _lib.stream_ptr(x.device))
+            else:       # multi-CTA path: Gram kernel + cooperative Cholesky + triangular inverse + gradient contraction
+                ws = _dense_workspace(x.device, lib.mgb_dense_mll_workspace_bytes(n))
+                rc = lib.mgb_series_mll_large(C.byref(d), _lib.ptr(x), n, x.stride(0), _lib.ptr(y), _lib.ptr(coef),
+                                              _lib.ptr(hyper), _lib.ptr(out), _lib.ptr(status), _lib.ptr(ws),
+                                              ws.numel() * 8, _lib.stream_ptr(x.device))
         _lib.check(rc, "mgb_series_mll")
         ctx.save_for_backward(out)
         ctx.coef_shape = coef.shape
@@ -211,7 +231,13 @@ class SeriesMLL(torch.autograd.Function):
 
 
 def series_mll_max_n(spec: SeriesSpec, n_terms: int) -> int:
-    return int(_lib.load().mgb_series_mll_max_n(spec.factor_width, int(n_terms)))
+    """Largest n of the SINGLE-CTA fused kernel (everything in shared memory)."""
+    return int(_lib.load().mgb_series_mll_single_cta_max_n(spec.factor_width, int(n_terms)))
+
+
+def dense_large_max_n() -> int:
+    """Largest n of the multi-CTA dense path (csrc/dense_spd.cu)."""
+    return int(_lib.load().mgb_dense_max_n())
 
 
 def series_mll(spec: SeriesSpec, x, y, coef, hyper):
@@ -232,8 +258,14 @@ class DenseMLL(torch.autograd.Function):
         g = torch.empty((n, n), dtype=F64, device=k.device)
         status = torch.zeros(1, dtype=torch.int32, device=k.device)
         with torch.cuda.device(k.device):
-            rc = lib.mgb_dense_mll(_lib.ptr(k), n, k.stride(0), _lib.ptr(y), _lib.ptr(hyper), _lib.ptr(out), _lib.ptr(g), n,
-                                   _lib.ptr(status), _lib.stream_ptr(k.device))
+            if n <= lib.mgb_series_mll_single_cta_max_n(0, 0):
+                rc = lib.mgb_dense_mll(_lib.ptr(k), n, k.stride(0), _lib.ptr(y), _lib.ptr(hyper), _lib.ptr(out), _lib.ptr(g), n,
+                                       _lib.ptr(status), _lib.stream_ptr(k.device))
+            else:
+                ws = _dense_workspace(k.device, lib.mgb_dense_mll_workspace_bytes(n))
+                rc = lib.mgb_dense_mll_large(_lib.ptr(k), n, k.stride(0), _lib.ptr(y), _lib.ptr(hyper), _lib.ptr(out),
+                                             _lib.ptr(g), n, _lib.ptr(status), _lib.ptr(ws), ws.numel() * 8,
+                                             _lib.stream_ptr(k.device))
         _lib.check(rc, "mgb_dense_mll")
         ctx.save_for_backward(out, g)
         ctx.mark_non_differentiable(status)
@@ -249,7 +281,8 @@ class DenseMLL(torch.autograd.Function):
 
 
 def dense_mll_max_n() -> int:
-    return int(_lib.load().mgb_series_mll_max_n(0, 0))
+    """Largest n of the single-CTA kernel in dense mode."""
+    return int(_lib.load().mgb_series_mll_single_cta_max_n(0, 0))
 
 
 def dense_mll(k, y, hyper):

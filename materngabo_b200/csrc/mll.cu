@@ -575,8 +575,8 @@ extern "C" int mgb_series_fit(const mgb_series_desc* d, const double* x, long lo
   if (d->factor_width < 1 || d->n_terms < 1 || d->n_terms > MGB_MAX_TERMS) return fail(MGB_ERR_ARG, "series_fit: bad descriptor");
   if (d->basis != MGB_BASIS_MONOMIAL && d->basis != MGB_BASIS_CHEBYSHEV) return fail(MGB_ERR_ARG, "series_fit: bad basis");
   if (n < 1 || ld < d->factor_width || ldo < n) return fail(MGB_ERR_ARG, "series_fit: bad sizes");
-  if (n > mgb_series_mll_max_n(d->factor_width, d->n_terms))
-    return fail(MGB_ERR_ARG, "series_fit: n exceeds the single-CTA limit (mgb_series_mll_max_n)");
+  if (n > mgb_series_mll_single_cta_max_n(d->factor_width, d->n_terms))
+    return fail(MGB_ERR_ARG, "series_fit: n exceeds the single-CTA limit: use mgb_dense_fit_large");
   MllParams p{x, (int)n, ld, y, coef, hyper, nll, status, d->factor_width, d->n_terms, d->basis,
               d->scale, d->shift, d->lo, d->hi, rinv, rinv_t, alpha, ldo};
   const size_t smem = sizeof(double) * (size_t)(n * (n + 1) + n * d->factor_width + d->n_terms + 5 * n + 4 + d->n_terms);
@@ -601,6 +601,11 @@ extern "C" int mgb_spectral_coef(int mode, int n_terms, int n_out, const double*
 
 
 extern "C" long long mgb_series_mll_max_n(int factor_width, int n_terms) {
+  (void)factor_width; (void)n_terms;
+  return mgb_dense_max_n();     // beyond the single-CTA limit: the multi-CTA path (csrc/dense_spd.cu, *_large entry points)
+}
+
+extern "C" long long mgb_series_mll_single_cta_max_n(int factor_width, int n_terms) {
   // two packed triangles + inputs + vectors within 220 KB of shared memory
   for (long long n = 200; n >= 1; --n) {
     const long long doubles = n * (n + 1) + n * factor_width + n_terms + 5 * n + 4 + n_terms;
@@ -617,8 +622,8 @@ extern "C" int mgb_series_mll(const mgb_series_desc* d, const double* x, long lo
   if (d->factor_width < 1 || d->n_terms < 1 || d->n_terms > MGB_MAX_TERMS) return fail(MGB_ERR_ARG, "series_mll: bad descriptor");
   if (d->basis != MGB_BASIS_MONOMIAL && d->basis != MGB_BASIS_CHEBYSHEV) return fail(MGB_ERR_ARG, "series_mll: bad basis");
   if (n < 1 || ld < d->factor_width) return fail(MGB_ERR_ARG, "series_mll: bad sizes");
-  if (n > mgb_series_mll_max_n(d->factor_width, d->n_terms))
-    return fail(MGB_ERR_ARG, "series_mll: n exceeds the single-CTA limit (mgb_series_mll_max_n)");
+  if (n > mgb_series_mll_single_cta_max_n(d->factor_width, d->n_terms))
+    return fail(MGB_ERR_ARG, "series_mll: n exceeds the single-CTA limit: use mgb_series_mll_large");
   MllParams p{x, (int)n, ld, y, coef, hyper, out, status, d->factor_width, d->n_terms, d->basis,
               d->scale, d->shift, d->lo, d->hi, nullptr, nullptr, nullptr, 0};
   const size_t smem = sizeof(double) * (size_t)(n * (n + 1) + n * d->factor_width + d->n_terms + 5 * n + 4 + d->n_terms);
@@ -633,7 +638,7 @@ extern "C" int mgb_dense_mll(const double* K, long long n, long long ldk, const 
                              double* G, long long ldg, int* status, void* stream) {
   if (!K || !y || !hyper || !out || !G) return fail(MGB_ERR_ARG, "dense_mll: null pointer");
   if (n < 1 || ldk < n || ldg < n) return fail(MGB_ERR_ARG, "dense_mll: bad sizes");
-  if (n > mgb_series_mll_max_n(0, 0)) return fail(MGB_ERR_ARG, "dense_mll: n exceeds the single-CTA limit (mgb_series_mll_max_n(0, 0))");
+  if (n > mgb_series_mll_single_cta_max_n(0, 0)) return fail(MGB_ERR_ARG, "dense_mll: n exceeds the single-CTA limit: use mgb_dense_mll_large");
   MllParams p{};
   p.n = (int)n; p.y = y; p.hyper = hyper; p.out = out; p.status = status;
   p.Kin = K; p.ldk = ldk; p.Gout = G; p.ldg = ldg;
@@ -669,7 +674,7 @@ extern "C" int mgb_dense_fit(const double* K, long long n, long long ldk, const 
                              double* rinv_t, long long ldo, double* alpha, double* nll, int* status, void* stream) {
   if (!K || !y || !hyper || !rinv || !rinv_t || !alpha || !nll) return fail(MGB_ERR_ARG, "dense_fit: null pointer");
   if (n < 1 || ldk < n || ldo < n) return fail(MGB_ERR_ARG, "dense_fit: bad sizes");
-  if (n > mgb_series_mll_max_n(0, 0)) return fail(MGB_ERR_ARG, "dense_fit: n exceeds the single-CTA limit (mgb_series_mll_max_n(0, 0))");
+  if (n > mgb_series_mll_single_cta_max_n(0, 0)) return fail(MGB_ERR_ARG, "dense_fit: n exceeds the single-CTA limit: use mgb_dense_fit_large");
   MllParams p{};
   p.n = (int)n; p.y = y; p.hyper = hyper; p.out = nll; p.status = status;
   p.rinv = rinv; p.rinv_t = rinv_t; p.alpha_out = alpha; p.ldo = ldo;

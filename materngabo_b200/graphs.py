@@ -122,7 +122,7 @@ def _fused_mll(kernel, x, y, noise, mean_const, jitter):
     spec, coef = _series_on(base, x.device)
     if spec.n_factors != 1 or x.shape[-1] != spec.factor_width:
         return None
-    if x.shape[0] > _ops.series_mll_max_n(spec, coef.shape[-1]):
+    if x.shape[0] > _ops.dense_large_max_n():
         return None
     hyper = torch.stack([_scalar(scale, x), _scalar(noise, x) + jitter, _scalar(mean_const, x)])
     nll, info = _ops.series_mll(spec, x, y, coef, hyper)
@@ -134,7 +134,7 @@ def _dense_mll(kernel, x, y, noise, mean_const, jitter):
     log-determinant and dnll/dK (csrc/mll.cu, dense mode).  None when n exceeds the single-CTA limit or for batches."""
     from . import _ops
 
-    if x.dim() != 2 or x.shape[0] > _ops.dense_mll_max_n():
+    if x.dim() != 2 or x.shape[0] > _ops.dense_large_max_n():
         return None
     base, scale = kernel, 1.0
     if hasattr(kernel, "base_kernel") and hasattr(kernel, "outputscale") and getattr(kernel, "active_dims", None) is None:
@@ -154,7 +154,8 @@ def exact_mll(kernel, x, y, noise, mean_const=0.0, jitter: float = 0.0, fused: b
     Single-factor series kernels (sphere, SO(3), circle) with N up to ~160 go through ONE fused launch (csrc/mll.cu:
     Gram, Cholesky, solves, log-determinant and all gradients in shared memory); every other kernel at those sizes
     through its own Gram kernel + one launch of the same CTA kernel in dense mode (dnll/dK handed to the kernel's
-    backward); larger N through the Gram kernel + torch.linalg.  Returns (loss, info) - ``info`` is the Cholesky status flag (non-zero: K + noise I not
+    backward); 160 < N <= 16384 through the multi-CTA path (csrc/dense_spd.cu: cooperative blocked Cholesky, triangular
+    inverse by recursive doubling, gradient contraction); torch.linalg only beyond that or with fused=False.  Returns (loss, info) - ``info`` is the Cholesky status flag (non-zero: K + noise I not
     positive definite)."""
     if fused and hasattr(kernel, "forward"):
         res = _fused_mll(kernel, x, y, noise, mean_const, jitter)

@@ -115,8 +115,8 @@ class ExactGPPosterior:
         else:
             spec, coef = None, None
             k = self.outputscale * self.kernel.forward(x, x)
-        if not self._dense_fit(k.detach()):
-            k = k.detach().clone()
+        if not self._dense_fit(k.detach()) and not self._dense_fit_large(k.detach()):
+            k = k.detach().clone()                        # n beyond mgb_dense_max_n(): torch.linalg (cuSOLVER)
             k.diagonal().add_(self.noise)
             L = torch.linalg.cholesky(k)
             self.alpha = torch.cholesky_solve((self.train_y - self.mean_const).unsqueeze(-1), L).squeeze(-1).contiguous()
@@ -185,6 +185,35 @@ class ExactGPPosterior:
         _lib.check(rc, "mgb_dense_fit")
         if int(status) != 0:
             raise torch.linalg.LinAlgError("ExactGPPosterior.fit: s K + noise I is not positive definite (pivot %d)" % int(status))
+        return True
+
+    def _dense_fit_large(self, k) -> bool:
+        """160 < n <= mgb_dense_max_n(): Cholesky, L^-1 and alpha from this library's multi-CTA path (csrc/dense_spd.cu:
+        one cooperative launch for the factorisation, recursive-doubling triangular inverse) instead of torch.linalg."""
+        lib = _lib.load()
+        n = k.shape[0]
+        if k.dim() != 2 or n > lib.mgb_dense_max_n() or os.environ.get("MGB_FIT_PATH", "") == "torch":
+            return False
+        k = k.contiguous()
+        ld = (n + 1) // 2 * 2
+        rinv = torch.empty((n, ld), dtype=F64, device=self.device)
+        self.alpha = torch.empty(n, dtype=F64, device=self.device)
+        nll = torch.empty(1, dtype=F64, device=self.device)
+        status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        hyper = torch.tensor([1.0, self.noise, self.mean_const], dtype=F64).to(self.device)      # k carries the outputscale
+        ws = _ops._dense_workspace(self.device, lib.mgb_dense_fit_workspace_bytes(n))
+        want_t = n <= 4096                               # the transposed copy only serves the fused acquisition kernel
+        rinv_t = torch.empty((n, ld), dtype=F64, device=self.device) if want_t else None
+        with torch.cuda.device(self.device):
+            rc = lib.mgb_dense_fit_large(_lib.ptr(k), n, k.stride(0), _lib.ptr(self.train_y), _lib.ptr(hyper), _lib.ptr(rinv),
+                                         _lib.ptr(rinv_t), ld, _lib.ptr(self.alpha), _lib.ptr(nll), _lib.ptr(status),
+                                         _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr(self.device))
+        _lib.check(rc, "mgb_dense_fit_large")
+        if int(status) != 0:
+            raise torch.linalg.LinAlgError("ExactGPPosterior.fit: s K + noise I is not positive definite (pivot %d)" % int(status))
+        self.rinv = rinv[:, :n]
+        self.rinv_t = rinv_t[:, :n] if rinv_t is not None else None
+        self.fit_nll = nll
         return True
 
     def _factor_scale(self, spec):

@@ -184,3 +184,105 @@ def test_dense_mll_reports_a_non_positive_definite_matrix():
     hyper = torch.tensor([1.0, 0.0, 0.0], device=DEV)
     _, info = _ops.dense_mll(k, torch.zeros(2, device=DEV), hyper)
     assert int(info) != 0
+
+
+# ---- multi-CTA dense path (csrc/dense_spd.cu): 160 < n <= 16384 ---------------------------------------------------------
+@pytest.mark.parametrize("n", [161, 500, 1000, 1057])
+def test_large_mll_matches_unfused_and_oracle(n):
+    """SURVEY.md 8f rank 4 beyond the single-CTA limit: Gram kernel -> cooperative blocked Cholesky -> triangular inverse
+    by recursive doubling -> K^-1 = X^T X -> gradient contraction, against (a) the torch.linalg + autograd path on the
+    same device and (b) torch autograd through the oracle kernel on the CPU (sizes the oracle finishes in seconds)."""
+    from materngabo_b200 import _lib, kernels_sphere
+    from materngabo_b200.gpytorch_compat import ScaleKernel
+    from materngabo_b200.graphs import exact_mll
+    from oracle import restated as R
+
+    assert _lib.load().mgb_series_mll_max_n(4, 10) >= 1000
+    gen = torch.Generator().manual_seed(n)
+    x = torch.nn.functional.normalize(torch.randn(n, 4, generator=gen), dim=-1)
+    y = torch.sin(3 * x[:, 0]) + 0.2 * torch.randn(n, generator=gen)
+    base = kernels_sphere.SphereRiemannianMaternKernel(dim=3, nu=None)
+    sk = ScaleKernel(base).to(DEV)
+    with torch.no_grad():
+        base.raw_lengthscale.fill_(-0.3)
+        base.raw_nu.fill_(1.1)
+        sk.raw_outputscale.fill_(0.4)
+    params = [base.raw_lengthscale, base.raw_nu, sk.raw_outputscale]
+    noise = torch.tensor(0.02, device=DEV, requires_grad=True)
+    mean = torch.tensor(0.15, device=DEV, requires_grad=True)
+    xd, yd = x.to(DEV), y.to(DEV)
+    lf, info = exact_mll(sk, xd, yd, noise, mean)
+    assert int(info) == 0
+    gf = _grads(lf, params + [noise, mean])
+    lu, _ = exact_mll(sk, xd, yd, noise, mean, fused=False)
+    gu = _grads(lu, params + [noise, mean])
+    assert abs(float(lf.detach()) - float(lu.detach())) < 1e-11 * max(1.0, abs(float(lu.detach())))
+    for a, b in zip(gf, gu):
+        assert _close(a, b, 1e-8)
+    if n <= 500:
+        rl = torch.full((1, 1), -0.3, requires_grad=True)
+        rn = torch.full((1, 1), 1.1, requires_grad=True)
+        ro = torch.tensor(0.4, requires_grad=True)
+        nz = torch.tensor(0.02, requires_grad=True)
+        mn = torch.tensor(0.15, requires_grad=True)
+        k = sp(ro) * R.sphere_matern(x, x, 3, sp(rn), sp(rl))
+        lo, _ = exact_mll(k, x, y, nz, mn)
+        go = _grads(lo, [rl, rn, ro, nz, mn])
+        assert abs(float(lf.detach()) - float(lo.detach())) < 1e-9 * max(1.0, abs(float(lo.detach())))
+        for a, b in zip(gf, go):
+            assert _close(a, b, 1e-7)
+
+
+def test_large_dense_mll_for_a_quadrature_kernel_and_failure_flag():
+    from materngabo_b200 import kernels_hyperbolic as kh
+    from materngabo_b200.graphs import exact_mll
+
+    gen = torch.Generator().manual_seed(12)
+    z = 0.8 * torch.randn(300, 2, generator=gen)
+    x = torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1).to(DEV)
+    y = torch.sin(2 * x[:, 1]).to(DEV)
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=24).to(DEV)
+    k.lengthscale = 0.9
+    lf, info = exact_mll(k, x, y, 0.05, 0.1)
+    lu, _ = exact_mll(k, x, y, 0.05, 0.1, fused=False)
+    assert int(info) == 0 and abs(float(lf.detach()) - float(lu.detach())) < 1e-10 * max(1.0, abs(float(lu.detach())))
+    gf, gu = _grads(lf, [k.raw_lengthscale]), _grads(lu, [k.raw_lengthscale])
+    assert _close(gf[0], gu[0], 1e-8)
+    # not positive definite (negative "noise" larger than the smallest eigenvalue): the flag names a pivot, no exception
+    lbad, ibad = exact_mll(k, x, y, -0.5, 0.0)
+    assert int(ibad) > 0
+
+
+@pytest.mark.parametrize("n", [161, 700, 2049])
+def test_large_fit_matches_torch_linalg(n):
+    """ExactGPPosterior.fit beyond 160 training points: this library's Cholesky + L^-1 (MGB_FIT_PATH=torch selects the
+    cuSOLVER route) - L^-1 rows, alpha and the posterior agree; L^-1 L L^-T ... = identity residual at 1e-12."""
+    import os
+
+    from materngabo_b200 import kernels_sphere
+    from materngabo_b200.posterior import ExactGPPosterior
+
+    gen = torch.Generator().manual_seed(n)
+    xt = torch.nn.functional.normalize(torch.randn(n, 11, generator=gen), dim=-1).to(DEV)
+    xc = torch.nn.functional.normalize(torch.randn(513, 11, generator=gen), dim=-1).to(DEV)
+    y = (torch.sin(3 * xt[:, 0]) + 0.3 * xt[:, 1]).to(DEV)
+    k = kernels_sphere.SphereRiemannianMaternKernel(dim=10, nu=2.5)
+    k.lengthscale = 0.5
+    own = ExactGPPosterior(k, xt, y, outputscale=1.2, noise=1e-2, mean_const=0.1).fit()
+    os.environ["MGB_FIT_PATH"] = "torch"
+    try:
+        ref = ExactGPPosterior(k, xt, y, outputscale=1.2, noise=1e-2, mean_const=0.1).fit()
+    finally:
+        del os.environ["MGB_FIT_PATH"]
+    assert float((own.rinv - ref.rinv).abs().max()) < 1e-10 * float(ref.rinv.abs().max())
+    assert float((own.rinv.triu(1)).abs().max()) == 0.0
+    assert float((own.alpha - ref.alpha).abs().max()) < 1e-9 * float(ref.alpha.abs().max())
+    m0, v0 = own.posterior(xc)
+    m1, v1 = ref.posterior(xc)
+    assert float((m0 - m1).abs().max()) < 1e-10 * float(m1.abs().max())
+    assert float((v0 - v1).abs().max()) < 1e-10 * float(v1.abs().max())
+    if own.rinv_t is not None:
+        assert torch.equal(own.rinv_t, own.rinv.t())
+    kt = 1.2 * k.forward(xt, xt).detach() + 1e-2 * torch.eye(n, device=DEV)
+    resid = own.rinv @ kt @ own.rinv.t() - torch.eye(n, device=DEV)
+    assert float(resid.abs().max()) < 1e-10
