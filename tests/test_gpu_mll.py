@@ -238,10 +238,10 @@ def test_large_dense_mll_for_a_quadrature_kernel_and_failure_flag():
     from materngabo_b200.graphs import exact_mll
 
     gen = torch.Generator().manual_seed(12)
-    z = 0.8 * torch.randn(300, 2, generator=gen)
+    z = 0.8 * torch.randn(300, 3, generator=gen)          # H^3: closed-form heat factor, positive definite by construction
     x = torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1).to(DEV)
     y = torch.sin(2 * x[:, 1]).to(DEV)
-    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=24).to(DEV)
+    k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=3, nu=2.5, nb_points_integral=24).to(DEV)
     k.lengthscale = 0.9
     lf, info = exact_mll(k, x, y, 0.05, 0.1)
     lu, _ = exact_mll(k, x, y, 0.05, 0.1, fused=False)

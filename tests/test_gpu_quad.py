@@ -698,3 +698,32 @@ def test_all_orders_profile_launch_matches_single_order_launches():
     for wh in range(3):
         one = _ops._spd2_profile_raw(wh, delta, r2, tcoef, rscale, bscale, bv, bw)
         assert rel_err(allp[wh], one) < 1e-13, wh
+
+
+@pytest.mark.parametrize("dim", [4, 5, 6, 7])
+def test_hyperbolic_heat_high_dimension(dim):
+    """H^n heat kernel, n > 3 (kernels_hyperbolic.py:118-180): -((1 / sinh d) d/dd)^m of the H^2 / H^3 kernel.  The
+    reference normalises by the same expression at d = 1e-6 through nested autograd, which is numerical noise for
+    n = 4, 6, 7 (normalisers of 6.6e5, -6.6e17, -4.2e9 at kappa = 1.3: repeated division by sinh(1e-6)); the CUDA path
+    reproduces that number with the same torch operations on the host and evaluates the numerator - which IS well
+    conditioned - from the d-derivatives of the device profile kernels.  Oracle = the reference's algorithm restated
+    (oracle/restated.py), run on this machine's CPU."""
+    from materngabo_b200 import kernels_hyperbolic as kh
+    from oracle import restated as R
+
+    gen = torch.Generator().manual_seed(60 + dim)
+    z = 0.6 * torch.randn(23, dim, generator=gen)
+    x = torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1)
+    k = kh.HyperbolicRiemannianMillsonGaussianKernel(dim=dim, nb_points_integral=400)
+    k.lengthscale = 1.3
+    k = k.to(DEV)
+    out = k.forward(x[:10].to(DEV), x[10:].to(DEV)).cpu()
+    num, nrm = R.hyperbolic_heat_high_dim(x[:10], x[10:], dim, 1.3, 400, return_parts=True)
+    ref = num / nrm
+    assert out.shape == (10, 13)
+    assert float((out * nrm - num).abs().max()) < 1e-9 * float(num.abs().max())          # the well-conditioned part
+    assert float((out - ref).abs().max()) < 1e-9 * float(ref.abs().max())
+    d = k.forward(x[:10].to(DEV), x[10:20].to(DEV), diag=True).cpu()
+    assert float((d - torch.diagonal(ref[:, :10])).abs().max()) < 1e-9 * float(ref.abs().max())
+    with pytest.raises(NotImplementedError):
+        kh.HyperbolicRiemannianMillsonGaussianKernel(dim=8).to(DEV).forward(torch.zeros(2, 9, device=DEV), torch.zeros(2, 9, device=DEV))
