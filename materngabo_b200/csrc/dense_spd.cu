@@ -16,7 +16,7 @@
 //                      X = L^-1 by recursive doubling: invert the 32 x 32 diagonal blocks (warp per block), then per
 //                      level s = 32, 64, ...: X21 = -X22 (L21 X11) for all aligned block pairs at once (two batched
 //                      GEMMs per level, k-ranges clipped to the triangles) - log2(n / 32) levels, all GEMM-shaped.
-//   dense_gemm_kernel  64 x 64 x 16 shared-memory tiles, 4 x 4 per thread, generic strides (N / T operands), batched over
+//   dense_gemm_kernel  64 x 64 x 16 tiles on the FP64 tensor cores (DMMA m8n8k4), generic strides (N / T operands), batched over
 //                      gridDim.z, k-range clipped by the triangular structure of the operands; also K^-1 = X^T X.
 //   glue               r = y - mean, z = X r, alpha = X^T z, G = s/2 (K^-1 - alpha alpha^T), reductions for dnll/ds,
 //                      dnll/dnoise, dnll/dmean; dnll/dcoef through mgb_series_gram_bwd on G.
@@ -216,11 +216,21 @@ struct GemmParams {
   int k_eq_m;         // K_b = M_b
 };
 
-constexpr int GT = 64, GK = 16, GPAD = 66;
+constexpr int GT = 64, GK = 16;
+constexpr int GEMM_THREADS = 128;
 
-__global__ void __launch_bounds__(256) dense_gemm_kernel(GemmParams p) {
-  __shared__ __align__(16) double As[GK][GPAD];
-  __shared__ __align__(16) double Bs[GK][GPAD];
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// 64 x 64 CTA tile, 4 warps as 2 x 2, warp tile 32 x 32 = 4 x 4 FP64 tensor-core fragments (mma.m8n8k4: lane holds
+// A[lane / 4][lane % 4], B[lane % 4][lane / 4], C[lane / 4][2 (lane % 4) + {0, 1}]).  Operand tiles are stored
+// [k / 4][row or column][k % 4]: a fragment load touches 32 consecutive doubles - bank-conflict free.
+__global__ void __launch_bounds__(GEMM_THREADS, 4) dense_gemm_kernel(GemmParams p) {
+  __shared__ __align__(16) double As[GK / 4][GT][4];
+  __shared__ __align__(16) double Bs[GK / 4][GT][4];
   const int b = blockIdx.z;
   int M = p.M;
   if (p.m_clip_step > 0) {
@@ -239,48 +249,56 @@ __global__ void __launch_bounds__(256) dense_gemm_kernel(GemmParams p) {
   else if (p.klo_mode == 2) klo = (i0 > j0) ? i0 : j0;
   if (p.khi_mode == 1) khi = (i0 + GT < K) ? i0 + GT : K;
   klo = klo / GK * GK;
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  double acc[4][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = warp >> 1, wc = warp & 1;
+  const int frow = lane >> 2, fk = lane & 3;
+  double acc0[4][4], acc1[4][4];
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+    for (int v = 0; v < 4; ++v) acc0[u][v] = acc1[u][v] = 0.0;
   const bool a_kfast = (p.a_cs == 1), b_kfast = (p.b_rs == 1);
   for (int k0 = klo; k0 < khi; k0 += GK) {
     __syncthreads();
 #pragma unroll
-    for (int rep = 0; rep < (GT * GK) / 256; ++rep) {
-      const int e = tid + rep * 256;
+    for (int rep = 0; rep < (GT * GK) / GEMM_THREADS; ++rep) {
+      const int e = tid + rep * GEMM_THREADS;
       int ai, ak, bj, bk;
       if (a_kfast) { ai = e / GK; ak = e % GK; } else { ak = e / GT; ai = e % GT; }
       if (b_kfast) { bj = e / GK; bk = e % GK; } else { bk = e / GT; bj = e % GT; }
       const int gi = i0 + ai, gka = k0 + ak, gj = j0 + bj, gkb = k0 + bk;
-      As[ak][ai] = (gi < M && gka < khi) ? A[(long long)gi * p.a_rs + (long long)gka * p.a_cs] : 0.0;
-      Bs[bk][bj] = (gj < p.N && gkb < khi) ? B[(long long)gkb * p.b_rs + (long long)gj * p.b_cs] : 0.0;
+      As[ak >> 2][ai][ak & 3] = (gi < M && gka < khi) ? A[(long long)gi * p.a_rs + (long long)gka * p.a_cs] : 0.0;
+      Bs[bk >> 2][bj][bk & 3] = (gj < p.N && gkb < khi) ? B[(long long)gkb * p.b_rs + (long long)gj * p.b_cs] : 0.0;
     }
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < GK; ++kk) {
-      const double2 a01 = *reinterpret_cast<const double2*>(&As[kk][ty * 4]);
-      const double2 a23 = *reinterpret_cast<const double2*>(&As[kk][ty * 4 + 2]);
-      const double2 b01 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4]);
-      const double2 b23 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4 + 2]);
-      const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-      const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+    for (int q = 0; q < GK / 4; ++q) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) af[u] = As[q][wr * 32 + u * 8 + frow][fk];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) bf[v] = Bs[q][wc * 32 + v * 8 + frow][fk];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+        for (int v = 0; v < 4; ++v) dmma_884(acc0[u][v], acc1[u][v], af[u], bf[v]);
     }
   }
+  const bool vec = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    const int gi = i0 + ty * 4 + u;
+    const int gi = i0 + wr * 32 + u * 8 + frow;
     if (gi >= M) continue;
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-      const int gj = j0 + tx * 4 + v;
-      if (gj < p.N) C[(long long)gi * p.ldc + gj] = p.alpha * acc[u][v];
+      const int gj = j0 + wc * 32 + v * 8 + 2 * fk;
+      double* dst = C + (long long)gi * p.ldc + gj;
+      if (vec && gj + 1 < p.N) {
+        *reinterpret_cast<double2*>(dst) = make_double2(p.alpha * acc0[u][v], p.alpha * acc1[u][v]);
+      } else {
+        if (gj < p.N) dst[0] = p.alpha * acc0[u][v];
+        if (gj + 1 < p.N) dst[1] = p.alpha * acc1[u][v];
+      }
     }
   }
 }
@@ -398,7 +416,7 @@ static int launch_gemm(const GemmParams& p, int batch, cudaStream_t s) {
   if (p.M <= 0 || p.N <= 0 || batch <= 0) return MGB_OK;
   dim3 grid((unsigned)((p.N + GT - 1) / GT), (unsigned)((p.M + GT - 1) / GT), (unsigned)batch);
   if (grid.y > 65535 || grid.z > 65535) return fail(MGB_ERR_ARG, "dense_gemm: matrix too large");
-  dense_gemm_kernel<<<grid, 256, 0, s>>>(p);
+  dense_gemm_kernel<<<grid, GEMM_THREADS, 0, s>>>(p);
   return after_launch("dense_gemm_kernel");
 }
 

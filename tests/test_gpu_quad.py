@@ -717,6 +717,9 @@ def test_hyperbolic_heat_high_dimension(dim):
     k = kh.HyperbolicRiemannianMillsonGaussianKernel(dim=dim, nb_points_integral=400)
     k.lengthscale = 1.3
     k = k.to(DEV)
+    with pytest.raises(NotImplementedError):        # forward only: a silent zero lengthscale gradient would mislead a fit
+        k.forward(x[:10].to(DEV), x[10:].to(DEV))
+    k.raw_lengthscale.requires_grad_(False)
     out = k.forward(x[:10].to(DEV), x[10:].to(DEV)).cpu()
     num, nrm = R.hyperbolic_heat_high_dim(x[:10], x[10:], dim, 1.3, 400, return_parts=True)
     ref = num / nrm
