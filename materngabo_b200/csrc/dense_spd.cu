@@ -7,11 +7,13 @@
 // 257-265) at the sizes SURVEY.md section 8f rank 4 names.
 //
 //   chol_coop_kernel   right-looking, 32-column panels, ONE cooperative launch for the whole factorisation: per panel
-//                      (1) every CTA factorises the 32 x 32 diagonal block redundantly in ONE WARP (lane = row, the block
-//                      lives in registers, pivots and multipliers travel by shuffles: no barrier in the 32 dependent
-//                      steps), then solves its share of the rows below (one thread per row, L11 broadcast from shared
-//                      memory); grid barrier; (2) rank-32 update of the trailing lower triangle in 64 x 64 tiles; grid
-//                      barrier.  2 barriers per 32 columns instead of a launch (or a CTA barrier) per column.
+//                      (1) every CTA factorises the 32 x 32 diagonal block redundantly in shared memory (elimination
+//                      without pivot-column scaling: one CTA barrier per column; a first version kept the block in the
+//                      registers of ONE warp and moved pivots by shuffles - latency bound at ~40 us per panel, ncu:
+//                      profiles/r02_ncu_chol_v1.txt), then solves its share of the rows below (one thread per row, L11
+//                      broadcast from shared memory); grid barrier; (2) rank-32 update of the trailing lower triangle
+//                      in 64 x 64 tiles on the FP64 tensor cores; grid barrier.  2 grid barriers per 32 columns
+//                      instead of a launch per column.
 //   tri_inv_diag_kernel + dense_gemm_kernel
 //                      X = L^-1 by recursive doubling: invert the 32 x 32 diagonal blocks (warp per block), then per
 //                      level s = 32, 64, ...: X21 = -X22 (L21 X11) for all aligned block pairs at once (two batched
@@ -32,57 +34,66 @@ namespace mgb {
 constexpr int CB = 32;          // Cholesky panel width = warp width
 constexpr int CHOL_THREADS = 256;
 constexpr int UT = 64;          // trailing-update tile edge
-constexpr int UPAD = 66;        // padded row length of the transposed panel tiles (16-byte aligned rows)
 
 // ---------------------------------------------------------------------------------------------------------------
 // Cholesky
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_chol(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
 __global__ void __launch_bounds__(CHOL_THREADS) chol_coop_kernel(double* __restrict__ A, int n, long long ld, int* status,
                                                                  double* sum_log_diag) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double Ls[CB][CB + 1];
   __shared__ double inv_s[CB];
-  __shared__ __align__(16) double Pi[CB][UPAD];
-  __shared__ __align__(16) double Pj[CB][UPAD];
+  __shared__ double dg_s[CB];
+  __shared__ __align__(16) double Pi[CB / 4][UT][4];      // [k / 4][row][k % 4]: DMMA fragment loads are 32 consecutive doubles
+  __shared__ __align__(16) double Pj[CB / 4][UT][4];
+  __shared__ int bad_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double logsum = 0.0;      // CTA 0, warp 0: lane j accumulates log L_jj of its panel column
-  int bad = 0;
+  double logsum = 0.0;      // thread j < 32 accumulates log L_jj of its panel column (CTA 0 reports)
+  if (tid == 0) bad_s = 0x7fffffff;
 
   for (int k0 = 0; k0 < n; k0 += CB) {
     const int nb = (n - k0 < CB) ? (n - k0) : CB;
     const int k1 = k0 + nb;
-    // ---- (1a) diagonal block in one warp: lane i holds row i (identity padding beyond nb) ----------------------
-    if (warp == 0) {
-      double a[CB];
-#pragma unroll
-      for (int c = 0; c < CB; ++c) {
-        double v = (c == lane) ? 1.0 : 0.0;
-        if (lane < nb && c < nb && c <= lane) v = A[(long long)(k0 + lane) * ld + k0 + c];
-        a[c] = v;
-      }
-#pragma unroll
-      for (int j = 0; j < CB; ++j) {
-        const double piv = __shfl_sync(0xffffffffu, a[j], j);
-        const double d = sqrt(piv);                    // NaN for a negative pivot: flagged, propagates
-        const double inv = 1.0 / d;
-        if (!(piv > 0.0) && bad == 0) bad = k0 + j + 1;
-        if (lane == j) {
-          a[j] = d;
-          if (j < nb) logsum += log(d);
-        } else if (lane > j) {
-          a[j] *= inv;
-        }
-#pragma unroll
-        for (int c = j + 1; c < CB; ++c) {
-          const double lcj = __shfl_sync(0xffffffffu, a[j], c);
-          if (lane >= c) a[c] = fma(-a[j], lcj, a[c]);
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < CB; ++c) Ls[lane][c] = (c <= lane) ? a[c] : 0.0;
+    // ---- (1a) diagonal block, whole CTA, in shared memory (identity padding beyond nb).  Right-looking elimination
+    // WITHOUT scaling the pivot column (a_ic -= a_ij a_cj / a_jj), so that one barrier per column suffices; the
+    // columns are scaled by 1 / sqrt(a_jj) at the end.  Every CTA does this redundantly: no broadcast, no extra barrier.
+    for (int e = tid; e < CB * CB; e += CHOL_THREADS) {
+      const int i = e / CB, c = e - i * CB;
+      double v = (i == c) ? 1.0 : 0.0;
+      if (i < nb && c < nb && c <= i) v = A[(long long)(k0 + i) * ld + k0 + c];
+      Ls[i][c] = v;
     }
     __syncthreads();
-    if (tid < CB) inv_s[tid] = 1.0 / Ls[tid][tid];
+    for (int j = 0; j < CB - 1; ++j) {
+      const double rj = 1.0 / Ls[j][j];
+      const int cnt = CB - 1 - j;                       // rows / columns j+1 .. 31
+      for (int e = tid; e < cnt * cnt; e += CHOL_THREADS) {
+        const int i = j + 1 + e / cnt, c = j + 1 + e % cnt;
+        if (c <= i) Ls[i][c] = fma(-Ls[i][j] * rj, Ls[c][j], Ls[i][c]);
+      }
+      __syncthreads();
+    }
+    if (tid < CB) {
+      const double piv = Ls[tid][tid];
+      if (!(piv > 0.0) && tid < nb) atomicMin(&bad_s, k0 + tid + 1);      // first non-positive pivot (NaNs propagate)
+      const double d = sqrt(piv);
+      dg_s[tid] = d;
+      inv_s[tid] = 1.0 / d;
+      if (tid < nb) logsum += log(d);
+    }
+    __syncthreads();
+    for (int e = tid; e < CB * CB; e += CHOL_THREADS) {
+      const int i = e / CB, c = e - i * CB;
+      if (c < i) Ls[i][c] *= inv_s[c];
+      else if (c == i) Ls[i][c] = dg_s[c];
+      else Ls[i][c] = 0.0;
+    }
     __syncthreads();
     // ---- (1b) rows below the panel: x L11^T = a_r, one thread per row ----------------------------------------
     for (long long r = (long long)k1 + (long long)blockIdx.x * CHOL_THREADS + tid; r < n; r += (long long)gridDim.x * CHOL_THREADS) {
@@ -108,11 +119,13 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_coop_kernel(double* __restr
         const int i = e / nb, c = e - i * nb;
         if (c <= i) A[(long long)(k0 + i) * ld + k0 + c] = Ls[i][c];
       }
-    // ---- (2) trailing update A22 -= L21 L21^T (lower triangle), 64 x 64 tiles ----------------------------------
+    // ---- (2) trailing update A22 -= L21 L21^T (lower triangle): 64 x 64 tiles on the FP64 tensor cores, 8 warps as
+    // 2 x 4, warp tile 32 x 16 = 4 x 2 m8n8k4 fragments, k = 32 ------------------------------------------------
     const int rem = n - k1;
     const int T = (rem + UT - 1) / UT;
     const int ntiles = T * (T + 1) / 2;
-    const int ty = tid >> 4, tx = tid & 15;
+    const int wr = warp >> 2, wc = warp & 3;
+    const int frow = lane >> 2, fk = lane & 3;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
       while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
@@ -123,51 +136,56 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_coop_kernel(double* __restr
       for (int e = tid; e < UT * CB; e += CHOL_THREADS) {
         const int rr = e / CB, pc = e - rr * CB;
         const int gi = i0 + rr, gj = j0 + rr;
-        Pi[pc][rr] = (gi < n && pc < nb) ? A[(long long)gi * ld + k0 + pc] : 0.0;
-        Pj[pc][rr] = (gj < n && pc < nb) ? A[(long long)gj * ld + k0 + pc] : 0.0;
+        Pi[pc >> 2][rr][pc & 3] = (gi < n && pc < nb) ? A[(long long)gi * ld + k0 + pc] : 0.0;
+        Pj[pc >> 2][rr][pc & 3] = (gj < n && pc < nb) ? A[(long long)gj * ld + k0 + pc] : 0.0;
       }
       __syncthreads();
-      double acc[4][4];
+      double acc0[4][2], acc1[4][2];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-#pragma unroll 8
-      for (int pc = 0; pc < CB; ++pc) {
-        const double2 a01 = *reinterpret_cast<const double2*>(&Pi[pc][ty * 4]);
-        const double2 a23 = *reinterpret_cast<const double2*>(&Pi[pc][ty * 4 + 2]);
-        const double2 b01 = *reinterpret_cast<const double2*>(&Pj[pc][tx * 4]);
-        const double2 b23 = *reinterpret_cast<const double2*>(&Pj[pc][tx * 4 + 2]);
-        const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-        const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+        for (int v = 0; v < 2; ++v) acc0[u][v] = acc1[u][v] = 0.0;
+#pragma unroll
+      for (int q = 0; q < CB / 4; ++q) {
+        double af[4], bf[2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) af[u] = Pi[q][wr * 32 + u * 8 + frow][fk];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) bf[v] = Pj[q][wc * 16 + v * 8 + frow][fk];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+          for (int v = 0; v < 2; ++v) dmma_chol(acc0[u][v], acc1[u][v], af[u], bf[v]);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int gi = i0 + ty * 4 + u;
+        const int gi = i0 + wr * 32 + u * 8 + frow;
         if (gi >= n) continue;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const int gj = j0 + tx * 4 + v;
-          if (gj <= gi) A[(long long)gi * ld + gj] -= acc[u][v];
+        for (int v = 0; v < 2; ++v) {
+          const int gj = j0 + wc * 16 + v * 8 + 2 * fk;
+          double* dst = A + (long long)gi * ld + gj;
+          if (gj + 1 <= gi) {
+            double2 cur = *reinterpret_cast<double2*>(dst);      // ld even, gj even, base 16-byte aligned
+            cur.x -= acc0[u][v];
+            cur.y -= acc1[u][v];
+            *reinterpret_cast<double2*>(dst) = cur;
+          } else if (gj <= gi) {
+            dst[0] -= acc0[u][v];
+          }
         }
       }
     }
     grid.sync();
   }
-  if (blockIdx.x == 0 && warp == 0) {
-    logsum = warp_sum(logsum);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const int other = __shfl_xor_sync(0xffffffffu, bad, o);
-      bad = (bad == 0) ? other : ((other == 0) ? bad : min(bad, other));
-    }
-    if (lane == 0) {
-      if (sum_log_diag) *sum_log_diag = logsum;
-      if (status) *status = bad;
+  if (blockIdx.x == 0) {
+    __syncthreads();
+    if (warp == 0) {
+      logsum = warp_sum(logsum);
+      if (lane == 0) {
+        if (sum_log_diag) *sum_log_diag = logsum;
+        if (status) *status = (bad_s == 0x7fffffff) ? 0 : bad_s;
+      }
     }
   }
 }
