@@ -133,6 +133,19 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_coop_kernel(double* __restr
       const int tj = t - ti * (ti + 1) / 2;
       const int i0 = k1 + ti * UT, j0 = k1 + tj * UT;
       __syncthreads();     // the previous tile's reads of Pi / Pj are done
+      // the C tile is requested first: its global-memory latency overlaps the panel loads and the tensor-core work
+      double2 cur[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int gi = i0 + wr * 32 + u * 8 + frow;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int gj = j0 + wc * 16 + v * 8 + 2 * fk;
+          cur[u][v] = make_double2(0.0, 0.0);
+          if (gi < n && gj + 1 <= gi) cur[u][v] = *reinterpret_cast<const double2*>(A + (long long)gi * ld + gj);
+          else if (gi < n && gj <= gi) cur[u][v].x = A[(long long)gi * ld + gj];
+        }
+      }
       for (int e = tid; e < UT * CB; e += CHOL_THREADS) {
         const int rr = e / CB, pc = e - rr * CB;
         const int gi = i0 + rr, gj = j0 + rr;
@@ -165,13 +178,10 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_coop_kernel(double* __restr
         for (int v = 0; v < 2; ++v) {
           const int gj = j0 + wc * 16 + v * 8 + 2 * fk;
           double* dst = A + (long long)gi * ld + gj;
-          if (gj + 1 <= gi) {
-            double2 cur = *reinterpret_cast<double2*>(dst);      // ld even, gj even, base 16-byte aligned
-            cur.x -= acc0[u][v];
-            cur.y -= acc1[u][v];
-            *reinterpret_cast<double2*>(dst) = cur;
+          if (gj + 1 <= gi) {                                    // ld even, gj even, base 16-byte aligned
+            *reinterpret_cast<double2*>(dst) = make_double2(cur[u][v].x - acc0[u][v], cur[u][v].y - acc1[u][v]);
           } else if (gj <= gi) {
-            dst[0] -= acc0[u][v];
+            dst[0] = cur[u][v].x - acc0[u][v];
           }
         }
       }
@@ -349,19 +359,29 @@ __global__ void __launch_bounds__(256) tri_matvec_kernel(const double* __restric
   if (lane == 0) z[row] = s;
 }
 
-// alpha = X^T z: thread per column, coalesced across columns
-__global__ void __launch_bounds__(128) tri_matvec_t_kernel(const double* __restrict__ X, int n, long long ldx,
+// alpha = X^T z: CTA per 32 columns (lane = column, coalesced 256-byte row segments), the 8 warps stride over the rows
+__global__ void __launch_bounds__(256) tri_matvec_t_kernel(const double* __restrict__ X, int n, long long ldx,
                                                            const double* __restrict__ z, double* __restrict__ alpha) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+  __shared__ double red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j0 = blockIdx.x * 32, j = j0 + lane;
   double s0 = 0.0, s1 = 0.0;
-  int i = j;
-  for (; i + 1 < n; i += 2) {
-    s0 = fma(X[(long long)i * ldx + j], z[i], s0);
-    s1 = fma(X[(long long)(i + 1) * ldx + j], z[i + 1], s1);
+  if (j < n) {
+    int i = j0 + warp;
+    for (; i + 8 < n; i += 16) {
+      if (i >= j) s0 = fma(X[(long long)i * ldx + j], z[i], s0);
+      s1 = fma((i + 8 >= j) ? X[(long long)(i + 8) * ldx + j] : 0.0, z[i + 8], s1);
+    }
+    if (i < n && i >= j) s0 = fma(X[(long long)i * ldx + j], z[i], s0);
   }
-  if (i < n) s0 = fma(X[(long long)i * ldx + j], z[i], s0);
-  alpha[j] = s0 + s1;
+  red[warp][lane] = s0 + s1;
+  __syncthreads();
+  if (warp == 0 && j < n) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    alpha[j] = t;
+  }
 }
 
 // G = s/2 (C - alpha alpha^T) (full symmetric); out[1] += sum_ij 1/2 (C - aa^T)_ij K_ij, out[2] += tr 1/2 (C - aa^T)
@@ -535,7 +555,7 @@ extern "C" int mgb_dense_fit_large(const double* K, long long n, long long ldk, 
   MGB_TRY(after_launch("residual_kernel"));
   tri_matvec_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(rinv, ni, ld, r, z);
   MGB_TRY(after_launch("tri_matvec_kernel"));
-  tri_matvec_t_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(rinv, ni, ld, z, alpha);
+  tri_matvec_t_kernel<<<(unsigned)((n + 31) / 32), 256, 0, s>>>(rinv, ni, ld, z, alpha);
   MGB_TRY(after_launch("tri_matvec_t_kernel"));
   if (nll) {
     mll_scalars_kernel<<<1, 256, 0, s>>>(r, alpha, ni, logd, nll, 0);
@@ -581,7 +601,7 @@ extern "C" int mgb_dense_mll_large(const double* K, long long n, long long ldk, 
   MGB_TRY(after_launch("residual_kernel"));
   tri_matvec_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(X, ni, ld, r, z);
   MGB_TRY(after_launch("tri_matvec_kernel"));
-  tri_matvec_t_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(X, ni, ld, z, al);
+  tri_matvec_t_kernel<<<(unsigned)((n + 31) / 32), 256, 0, s>>>(X, ni, ld, z, al);
   MGB_TRY(after_launch("tri_matvec_t_kernel"));
   // Kt^-1 = X^T X
   GemmParams g{};
