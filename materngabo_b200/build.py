@@ -7,10 +7,12 @@ from __future__ import annotations
 
 import fcntl
 import hashlib
+import json
 import os
 import shutil
 import subprocess
 import sys
+import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -44,6 +46,8 @@ def _nvcc():
 
 
 STAMP = os.path.join(LIBDIR, "libmgb.stamp")
+INFO = os.path.join(LIBDIR, "build_info.json")     # how the library on disk came to be (compiled here / reused)
+LAST_MODE = None                                   # "compiled" or "reused": what the last build() call in this process did
 
 
 def _source_digest() -> str:
@@ -66,8 +70,21 @@ def needs_build() -> bool:
         return fh.read().strip() != _source_digest()
 
 
+def build_info() -> dict:
+    """{"compiled_at", "seconds", "nvcc", "digest", "sources", "int8_cutlass"} of the library on disk + "last_call"."""
+    try:
+        with open(INFO) as fh:
+            info = json.load(fh)
+    except Exception:
+        info = {}
+    info["last_call"] = LAST_MODE
+    return info
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    global LAST_MODE
     if not force and not needs_build():
+        LAST_MODE = "reused"
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     # one builder at a time (several ranks of a torchrun launch may import the package at once)
@@ -75,7 +92,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         fcntl.flock(lock, fcntl.LOCK_EX)
         try:
             if not force and not needs_build():
+                LAST_MODE = "reused"
                 return LIB
+            LAST_MODE = "compiled"
             return _build_locked(verbose)
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)
@@ -83,6 +102,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
+    t0 = time.time()
     objs = []
     procs = []
     for src in SOURCES:
@@ -103,8 +123,17 @@ def _build_locked(verbose: bool) -> str:
     os.replace(tmp, LIB)                         # atomic: a concurrent loader sees the old or the new library
     with open(STAMP, "w") as fh:
         fh.write(_source_digest() + "\n")
+    try:
+        version = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-1]
+    except Exception:
+        version = "unknown"
+    with open(INFO, "w") as fh:
+        json.dump({"compiled_at": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "seconds": round(time.time() - t0, 1),
+                   "nvcc": version, "flags": NVCC_FLAGS, "digest": _source_digest(), "sources": SOURCES,
+                   "int8_cutlass": bool(_cutlass_flags())}, fh)
     return LIB
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(json.dumps(build_info()))

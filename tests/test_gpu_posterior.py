@@ -530,3 +530,37 @@ def test_ragged_tail_block_generic_kernel_path():
     assert rel_err(mean[rows.to(DEV)], mr) < 1e-9
     assert float((var[rows.to(DEV)].cpu() - vr).abs().max()) < 1e-9
     assert torch.isfinite(mean).all() and torch.isfinite(var).all()
+
+
+@pytest.mark.parametrize("noise", [1e-2, 1e-4, 1e-6])
+def test_int8_path_against_the_oracle_and_truth_at_the_headline_size(noise):
+    """The opt-in INT8 tensor-core contraction (library GEMM; slicing and recombination are this repo's kernels) against
+    the ORACLE and the long-double truth leg - not against the repo's own FP64 kernel - at n = 5000, incl. the
+    cancellation rows: 1e-10 of max|mean| / max var (measured ~2e-11 for the variance)."""
+    from materngabo_b200 import _lib, kernels_sphere
+    from materngabo_b200.posterior import ExactGPPosterior
+    from oracle import restated as R, truth
+
+    if not _lib.load().mgb_int8_available():
+        pytest.skip("libmgb built without the CUTLASS headers")
+    n, m, mt = 5000, 2048, 256
+    gen = torch.Generator().manual_seed(6)
+    xt = torch.nn.functional.normalize(torch.randn(n, 11, generator=gen), dim=-1)
+    xc = torch.nn.functional.normalize(torch.randn(m, 11, generator=gen), dim=-1)
+    xc[:128] = torch.nn.functional.normalize(xt[:128] + 1e-3 * torch.randn(128, 11, generator=gen), dim=-1)
+    xc[128:192] = xt[128:192]
+    y = torch.sin(3.0 * xt[:, 0]) + 0.5 * xt[:, 1] * xt[:, 2]
+    k = kernels_sphere.SphereRiemannianMaternKernel(dim=10, nu=2.5)
+    k.lengthscale = 0.5
+    gp = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.0, noise=noise, int8=True).fit()
+    mg, vg = (t.cpu().numpy() for t in gp.posterior(xc.to(DEV)))
+    kfn = lambda a, b: R.sphere_matern(a, b, 10, 2.5, 0.5)  # noqa: E731
+    L, alpha = R.gp_fit(kfn, xt, y, 1.0, noise, 0.0)
+    mo, vo = (t.numpy() for t in R.gp_predict(kfn, xt, L, alpha, xc, outputscale=1.0, mean_const=0.0, chunk=1024))
+    sel = np.arange(mt)
+    mtr, vtr = truth.sphere_matern_posterior(xt.numpy(), y.numpy(), xc[:mt].numpy(), 10, 2.5, 0.5, 1.0, noise)
+    mscale, vscale = float(np.abs(mo).max()), float(vo.max())
+    assert np.abs(mg - mo).max() <= 1e-10 * mscale
+    assert np.abs(vg - vo).max() <= 1e-10 * vscale
+    assert np.abs(mg[sel] - mtr).max() <= 1e-10 * mscale
+    assert np.abs(vg[sel] - vtr).max() <= 1e-10 * vscale

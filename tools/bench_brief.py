@@ -2,7 +2,7 @@
 import json
 import sys
 
-d = json.load(open(sys.argv[1]))
+d = [json.loads(ln) for ln in open(sys.argv[1]) if ln.startswith("{")][-1]
 print("value", d["value"], "e2e", (d.get("e2e") or {}).get("value"), "roofline.frac", (d.get("roofline") or {}).get("frac"))
 for k, v in (d.get("gram") or {}).items():
     if "error" in v:
