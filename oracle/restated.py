@@ -9,6 +9,10 @@ torch operator sequence as the reference (pair expansion + batched product, Pyth
 terms and quadrature nodes), which also makes it the honest CPU baseline.  Every function cites the
 reference lines it follows (paths relative to /root/reference/BoManifolds).
 
+Pinning of the posterior / EI arithmetic (gpytorch / botorch: unvendored, not installable here): PARITY UNPINNED
+against gpytorch itself; pinned against scikit-learn's GaussianProcessRegressor and scipy's normal distribution
+(tests/test_oracle_posterior_sklearn.py) and against an extended-precision restatement (oracle/truth_ld.c).
+
 Pinning: the reference ships no tests or golden vectors.  This file is pinned
 against the UNMODIFIED reference imported in the dev container (``oracle/reference_loader.py``) by
 ``tests/test_oracle_vs_reference.py`` (runs only where /root/reference exists) and by the committed
