@@ -375,6 +375,11 @@ int mgb_circle_coef(int mode, int n_terms, const double* t, const double* tw, in
  * tcoef[a] = w_a / sum_b w_b h0[b] (h0 = the inner integral at zero distance on the same grid, NULL = 1;
  * kernels_hyperbolic.py:367-383, kernels_spd.py:262-289, kernels_euclidean.py:186-207),
  * jac[0][a] = d tcoef_a / d kappa, jac[1][a] = d tcoef_a / d nu.  P <= 1024; kappa, nu: device scalars. */
+/* The t grid itself from a DEVICE lengthscale: t = logspace(lo_exp + log10 kappa, hi_exp + log10 kappa, P) with
+ * torch.logspace's float64 formula, tw = its trapezoid weights (kernels_hyperbolic.py:367-369, kernels_spd.py:262-265,
+ * kernels_euclidean.py:186-188 build it on the host from lengthscale.item()).  With this the whole hyper-parameter ->
+ * node-weight chain of the quadrature kernels runs without a host synchronisation (CUDA-graph capturable). */
+int mgb_matern_t_grid(const double* kappa, double lo_exp, double hi_exp, int P, double* t, double* tw, void* stream);
 int mgb_matern_t_weights(const double* t, const double* tw, const double* h0, int P, double power_offset,
                          const double* kappa, const double* nu, double* tcoef, double* jac, void* stream);
 

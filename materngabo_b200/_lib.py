@@ -102,6 +102,7 @@ PROTOTYPES = {
     "mgb_dense_mll": (_I, [_P, _LL, _LL, _P, _P, _P, _P, _LL, _P, _P]),
     "mgb_dense_fit": (_I, [_P, _LL, _LL, _P, _P, _P, _P, _LL, _P, _P, _P, _P]),
     "mgb_circle_coef": (_I, [_I, _I, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "mgb_matern_t_grid": (_I, [_P, _D, _D, _I, _P, _P, _P]),
     "mgb_matern_t_weights": (_I, [_P, _P, _P, _I, _D, _P, _P, _P, _P, _P]),
     "mgb_series_gram_host": (_I, [_DESC, _P, _LL, _P, _LL, _P, _P, _I]),
     "mgb_series_posterior_host": (_I, [_DESC, _P, _LL, _P, _LL, _P, _P, _P, _D, _D, _P, _P, _LL, _I]),

@@ -10,6 +10,7 @@ including its ``.item()`` detachments of the quadrature grids and the dtype of i
 from __future__ import annotations
 
 import math
+import os
 from fractions import Fraction
 from functools import lru_cache
 
@@ -468,6 +469,32 @@ class _MaternTWeights(torch.autograd.Function):
         gv = jac @ g.reshape(-1)
         return None, None, None, (gv[0].reshape(()) if ctx.needs_input_grad[3] else None), \
             (gv[1].reshape(()) if ctx.needs_input_grad[4] else None)
+
+
+def device_grids_enabled() -> bool:
+    """Sync-free (CUDA-graph capturable) node grids: only in the float64 regime - in the reference's float32-default
+    regime torch.logspace rounds the grid to float32 on the host, which a device kernel cannot reproduce bit for bit."""
+    return torch.get_default_dtype() == F64 and os.environ.get("MGB_DEVICE_GRIDS", "1") != "0"
+
+
+def matern_t_coef_device(lengthscale, nu, lo_exp, hi_exp, nb_points, power_offset, h0_fn):
+    """``matern_t_coef`` without the host read of the lengthscale: grid and trapezoid weights from ``mgb_matern_t_grid``
+    (device kappa), zero-distance inner integral recomputed on the device, weights + Jacobian from
+    ``mgb_matern_t_weights``.  No cache, no synchronisation.  Returns (t, tcoef)."""
+    ls, nu = lengthscale.reshape(()).to(F64), nu.reshape(()).to(F64)
+    lib = _lib.load()
+    p = int(nb_points)
+    grid = torch.empty((3, p), dtype=F64, device=ls.device)
+    kd = ls.detach().contiguous()
+    with torch.cuda.device(ls.device):
+        rc = lib.mgb_matern_t_grid(_lib.ptr(kd), float(lo_exp), float(hi_exp), p, _lib.ptr(grid[0]), _lib.ptr(grid[1]),
+                                   _lib.stream_ptr(ls.device))
+    _lib.check(rc, "mgb_matern_t_grid")
+    if h0_fn is not None:
+        with torch.no_grad():
+            grid[2].copy_(h0_fn(grid[0]).reshape(-1))
+    tcoef = _MaternTWeights.apply(grid, h0_fn is not None, power_offset, ls, nu)
+    return grid[0], tcoef
 
 
 def matern_t_coef(lengthscale, nu, lo_exp, hi_exp, nb_points, power_offset, h0_key, h0_fn):

@@ -563,9 +563,40 @@ __global__ void __launch_bounds__(CC_THREADS) matern_t_weights_kernel(TWeightPar
   }
 }
 
+// t[i] = 10^(lo + log10(kappa) + i step) with torch.logspace's float64 formula (first half from the start, second half
+// from the end), trapezoid weights tw; one CTA.
+__global__ void __launch_bounds__(CC_THREADS) matern_t_grid_kernel(const double* kappa, double lo, double hi, int P, double* t,
+                                                                  double* tw) {
+  __shared__ double ts[CC_MAXP];
+  const double shift = log10(*kappa);
+  const double start = lo + shift, end = hi + shift;
+  const double step = (P > 1) ? (end - start) / (double)(P - 1) : 0.0;
+  const int halfway = P / 2;
+  for (int i = threadIdx.x; i < P; i += CC_THREADS) {
+    const double v = (i < halfway) ? pow(10.0, start + step * i) : pow(10.0, end - step * (P - i - 1));
+    ts[i] = v;
+    t[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += CC_THREADS) {
+    double w = 0.0;
+    if (i + 1 < P) w += 0.5 * (ts[i + 1] - ts[i]);
+    if (i > 0) w += 0.5 * (ts[i] - ts[i - 1]);
+    tw[i] = w;
+  }
+}
+
 }  // namespace mgb
 
 using namespace mgb;
+
+extern "C" int mgb_matern_t_grid(const double* kappa, double lo_exp, double hi_exp, int P, double* t, double* tw,
+                                 void* stream) {
+  if (!kappa || !t || !tw) return fail(MGB_ERR_ARG, "matern_t_grid: null pointer");
+  if (P < 2 || P > CC_MAXP) return fail(MGB_ERR_ARG, "matern_t_grid: P out of range [2,1024]");
+  matern_t_grid_kernel<<<1, CC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(kappa, lo_exp, hi_exp, P, t, tw);
+  return after_launch("matern_t_grid_kernel");
+}
 
 extern "C" int mgb_series_fit(const mgb_series_desc* d, const double* x, long long n, long long ld, const double* y,
                               const double* coef, const double* hyper, double* rinv, double* rinv_t, long long ldo,

@@ -52,6 +52,8 @@ class EuclideanIntegratedMaternKernel(_NuMixin, Kernel):
         """t grid logspace(-3 + log10 l, 3 + log10 l, P) and the normalised trapezoid weights (:186-207)."""
         ls = self.lengthscale.to(device)
         if ls.is_cuda:
+            if _weights.device_grids_enabled():       # no host read of the lengthscale: CUDA-graph capturable
+                return _weights.matern_t_coef_device(ls, self.nu.to(device), -3.0, 3.0, self.nb_points_integral, 1.0, None)
             t, tcoef, _ = _weights.matern_t_coef(ls, self.nu.to(device), -3.0, 3.0, self.nb_points_integral, 1.0, "euclid", None)
             return t, tcoef
         t, w = _weights.matern_t_nodes(ls, self.nu.to(device), -3.0, 3.0, self.nb_points_integral, power_offset=1.0)

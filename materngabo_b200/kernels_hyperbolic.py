@@ -139,8 +139,11 @@ class HyperbolicRiemannianMillsonIntegratedMaternKernel(_NuMixin, Kernel):
         p = self.nb_points_integral
         s0, ds = 1.5e-1, (100.0 - 1.5e-1) / (p - 1)
         ls = self.lengthscale.to(device)
-        if ls.is_cuda:      # one launch for the normalised weights + Jacobian; grid and zero-distance integral cached
+        if ls.is_cuda:      # one launch for the normalised weights + Jacobian
             h0 = lambda t: _ops.hyperbolic_heat_nodes(self.dim, torch.zeros(1, dtype=F64, device=t.device), t, s0, ds, p)[0]  # noqa: E731
+            if _weights.device_grids_enabled():       # no host read of the lengthscale: CUDA-graph capturable
+                tval, tcoef = _weights.matern_t_coef_device(ls, self.nu.to(device), -2.5, 1.5, p, 1.0, h0)
+                return tval, tcoef, s0, ds, p
             tval, tcoef, _ = _weights.matern_t_coef(ls, self.nu.to(device), -2.5, 1.5, p, 1.0, ("hyp", int(self.dim), p), h0)
             return tval, tcoef, s0, ds, p
         tval, w = _weights.matern_t_nodes(ls, self.nu.to(device), -2.5, 1.5, p, power_offset=1.0)

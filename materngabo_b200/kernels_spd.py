@@ -38,6 +38,9 @@ def _b_nodes(nb, device):
     return hit[1]
 
 
+SYNC_FREE_MAX_ENTRIES = 1 << 16      # Gram blocks below this size take the sync-free node chain (direct forward kernel)
+
+
 class SpdRiemannianGaussianKernel(Kernel):
     has_lengthscale = True
 
@@ -85,9 +88,16 @@ class SpdRiemannianIntegratedMaternKernel(_NuMixin, Kernel):
 
     use_cholesky = 0      # singular values of X1 X2^-1 (kernels_spd.py:230-243)
 
-    def nodes(self, device, with_lattice=False):
+    def nodes(self, device, with_lattice=False, sync_free=False):
         ls = self.lengthscale.to(device)
         b, bw = _b_nodes(self.nb_points_integral_b, device)
+        if ls.is_cuda and sync_free and _weights.device_grids_enabled():
+            # launch-bound sizes (GP fit): no host read of the lengthscale - CUDA-graph capturable; the lattice form of
+            # the forward kernel needs g_min(kappa) on the host and is left to the large blocks
+            inner = lambda t: (bw * 2.0 * b / torch.sinh(b) * torch.exp(-(b * b).unsqueeze(0) / (2 * t).unsqueeze(-1))).sum(-1)  # noqa: E731
+            t, tcoef = _weights.matern_t_coef_device(ls, self.nu.to(device), -2.0, 1.5, self.nb_points_integral_t, 1.0, inner)
+            out = (tcoef, 1.0 / (4 * t), 1.0 / (2 * t), b, bw)
+            return out + (None,) if with_lattice else out
         if ls.is_cuda:      # one launch for the normalised weights + Jacobian; grid and zero-distance integral cached
             inner = lambda t: (bw * 2.0 * b / torch.sinh(b) * torch.exp(-(b * b).unsqueeze(0) / (2 * t).unsqueeze(-1))).sum(-1)  # noqa: E731
             t, tcoef, shift = _weights.matern_t_coef(ls, self.nu.to(device), -2.0, 1.5, self.nb_points_integral_t, 1.0,
@@ -128,7 +138,8 @@ class SpdRiemannianIntegratedMaternKernel(_NuMixin, Kernel):
 
     def forward(self, x1, x2, diag=False, **params):
         _check_batch(self)
-        tcoef, rscale, bscale, b, bw, lattice = self.nodes(x1.device, with_lattice=True)
+        small = x1.shape[-2] * x2.shape[-2] < SYNC_FREE_MAX_ENTRIES
+        tcoef, rscale, bscale, b, bw, lattice = self.nodes(x1.device, with_lattice=True, sync_free=small)
         if _ops.inputs_need_grad(x1, x2):
             fn = lambda a, c: _ops.spd2_gram_autograd(0, a, c, tcoef, rscale, bscale, b, bw)  # noqa: E731
         else:

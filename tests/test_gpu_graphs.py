@@ -78,3 +78,50 @@ def test_graphed_trust_region_step_matches_eager():
         assert abs(float(value) - float(c)) < 1e-12
         assert rel_err(grads[0], ge) < 1e-11
         assert rel_err(hvp, he) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["H2", "H3", "SPD2", "Euclid"])
+def test_graphed_mll_step_on_the_quadrature_kernels(name):
+    """The hyper-parameter -> node-weight chain of the quadrature kernels runs without a host read of the lengthscale
+    (mgb_matern_t_grid, float64 regime), so the whole marginal-likelihood step is CUDA-graph capturable: replays track
+    parameter updates and equal the eager path with the host-built grids (MGB_DEVICE_GRIDS=0 semantics)."""
+    import os
+
+    from materngabo_b200 import kernels_euclidean as ke, kernels_hyperbolic as kh, kernels_spd as ksp
+    from materngabo_b200.gpytorch_compat import ScaleKernel
+    from materngabo_b200.graphs import GraphedValueAndGrad, exact_mll
+
+    gen = torch.Generator().manual_seed(17)
+    n = 100
+    if name in ("H2", "H3"):
+        dim = int(name[1])
+        z = 0.7 * torch.randn(n, dim, generator=gen)
+        x = torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1)
+        base = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=dim, nu=2.5)
+    elif name == "SPD2":
+        a = torch.randn(n, 2, 2, generator=gen)
+        sm = a @ a.transpose(-1, -2) + 0.5 * torch.eye(2)
+        x = torch.stack([sm[:, 0, 0], sm[:, 1, 1], sm[:, 0, 1] * 2 ** 0.5], -1)
+        base = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5)
+    else:
+        x = torch.randn(n, 3, generator=gen)
+        base = ke.EuclideanIntegratedMaternKernel(3, nu=2.5)
+    x = x.to(DEV)
+    y = torch.sin(2 * x[:, 1])
+    sk = ScaleKernel(base).to(DEV)
+    params = [base.raw_lengthscale, sk.raw_outputscale]
+    g = GraphedValueAndGrad(lambda: exact_mll(sk, x, y, 5e-2, 0.1), inputs=(), wrt=params)
+    for raw_ls, raw_os in ((0.3, 0.0), (0.9, 0.5), (-0.2, -0.4)):
+        with torch.no_grad():
+            base.raw_lengthscale.fill_(raw_ls)
+            sk.raw_outputscale.fill_(raw_os)
+        value, grads = g()
+        assert int(g.aux[0]) == 0
+        os.environ["MGB_DEVICE_GRIDS"] = "0"                 # host-built grids (lengthscale.item()), eager
+        try:
+            loss, _ = exact_mll(sk, x, y, 5e-2, 0.1)
+            ref = torch.autograd.grad(loss, params)
+        finally:
+            del os.environ["MGB_DEVICE_GRIDS"]
+        assert abs(float(value) - float(loss.detach())) < 1e-11 * max(1.0, abs(float(loss.detach())))
+        assert rel_err(grads[0], ref[0]) < 1e-9 and rel_err(grads[1], ref[1]) < 1e-9

@@ -60,7 +60,27 @@ for name, base, x in cases:
         torch.cuda.synchronize()
     evs = [e for e in p.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     tot = sum(getattr(e, "device_time", 0) for e in evs)
-    print("%-14s %8.1f us per MLL step eager; %3d device launches, %7.1f us of device time" % (name, us, len(evs), tot))
+    graph_us = float("nan")
+    try:
+        from materngabo_b200.graphs import GraphedValueAndGrad
+        gm = GraphedValueAndGrad(lambda: exact_mll(sk, x, y, 1e-2, 0.0), inputs=(), wrt=params)
+
+        def gstep():
+            value, grads = gm()
+            return float(value)              # the L-BFGS driver reads the loss back every evaluation
+
+        for _ in range(5):
+            gstep()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            gstep()
+        torch.cuda.synchronize()
+        graph_us = (time.perf_counter() - t0) / 50 * 1e6
+    except Exception as exc:                 # not capturable (host synchronisation inside the step)
+        print("      graph capture failed: %s: %s" % (type(exc).__name__, str(exc)[:120]))
+    print("%-14s %8.1f us per MLL step eager, %8.1f us under CUDA-graph replay; %3d device launches, %7.1f us of device time"
+          % (name, us, graph_us, len(evs), tot))
     c = collections.Counter()
     for e in evs:
         c[e.name[:70]] += getattr(e, "device_time", 0)
