@@ -343,6 +343,24 @@ def _circle_grid(shift: float, nb_points: int, device):
     return hit[1]
 
 
+def circle_coef_sync_free(mode, lengthscale, nu, nb_points):
+    """All 201 Chebyshev coefficients of a circle kernel (mode 0: integrated Matern, 1: heat) WITHOUT any host read:
+    the t grid comes from mgb_matern_t_grid (device lengthscale), nothing is truncated and no basis decision is taken
+    (both need the values on the host).  For launch-bound problems (GP fit on a torus: CUDA-graph capturable); large
+    Gram matrices use the truncated / monomial form of ``circle_*_coef``."""
+    ls = lengthscale.reshape(()).to(F64)
+    grid = None
+    if mode == 0:
+        lib = _lib.load()
+        grid = torch.empty((2, int(nb_points)), dtype=F64, device=ls.device)
+        kd = ls.detach().contiguous()
+        with torch.cuda.device(ls.device):
+            rc = lib.mgb_matern_t_grid(_lib.ptr(kd), -3.0, 1.0, int(nb_points), _lib.ptr(grid[0]), _lib.ptr(grid[1]),
+                                       _lib.stream_ptr(ls.device))
+        _lib.check(rc, "mgb_matern_t_grid")
+    return _CircleCoef.apply(int(mode), grid, ls, nu.reshape(()).to(F64) if nu is not None else None)
+
+
 def circle_gaussian_coef(lengthscale):
     """theta_3(phi/2, q) / theta_3(0, q), q = exp(-2 pi^2 kappa^2)  ->  Chebyshev series in cos(phi):
     c_0 = 1, c_n = 2 q^(n^2)."""

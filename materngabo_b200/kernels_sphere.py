@@ -165,6 +165,8 @@ class CircleRiemannianGaussianKernel(_CircleSeriesKernel):
         super().__init__(has_lengthscale=True, ard_num_dims=None, **kwargs)
         self.serie_nb_terms = serie_nb_terms  # unused, as in the reference (theta_3 always sums 200 terms)
 
+    _coef_mode = 1        # mgb_circle_coef mode: heat
+
     def _coef(self):
         return _weights.circle_gaussian_coef(self.lengthscale)
 
@@ -177,6 +179,8 @@ class CircleRiemannianIntegratedMaternKernel(_NuMixin, _CircleSeriesKernel):
         self._register_nu(nu, nu_prior)
         self.nb_points_integral = nb_points_integral
         self.serie_nb_terms = serie_nb_terms
+
+    _coef_mode = 0        # mgb_circle_coef mode: integrated Matern
 
     def _coef(self):
         return _weights.circle_integrated_matern_coef(self.lengthscale, self.nu, self.nb_points_integral)

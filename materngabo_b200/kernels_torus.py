@@ -16,6 +16,9 @@ from .kernels_sphere import (CircleRiemannianGaussianKernel, CircleRiemannianInt
                              _check_batch, _series_on)
 
 
+SYNC_FREE_MAX_ENTRIES = 1 << 16      # Gram blocks below this size (GP fit) take the sync-free coefficient chain
+
+
 class _TorusKernel(Kernel):
     has_lengthscale = True
 
@@ -25,10 +28,17 @@ class _TorusKernel(Kernel):
             return torch.stack([torch.cos(x), torch.sin(x)], dim=-1).reshape(*x.shape[:-1], 2 * self.dim)
         return x
 
-    def series(self):
-        coef = _weights.stack_factor_coefs([k._coef() for k in self.torus_kernel.kernels])
+    def series(self, sync_free=False):
         if self.dim > _lib.MAX_FACTORS:
             raise NotImplementedError("T^d with d > %d" % _lib.MAX_FACTORS)
+        kernels = list(self.torus_kernel.kernels)
+        if sync_free and _weights.device_grids_enabled() and all(k.lengthscale.is_cuda for k in kernels):
+            # GP-fit sizes: every factor's 201 Chebyshev coefficients straight from the device (no truncation, no basis
+            # decision, no lengthscale.item()): the marginal-likelihood step is then CUDA-graph capturable
+            rows = [_weights.circle_coef_sync_free(k._coef_mode, k.lengthscale, getattr(k, "nu", None) if k._coef_mode == 0 else None,
+                                                   getattr(k, "nb_points_integral", 0)) for k in kernels]
+            return _ops.SeriesSpec(self.dim, 2, _lib.BASIS_CHEBYSHEV, 1.0, 0.0, -_CLAMP, _CLAMP), torch.stack(rows).contiguous()
+        coef = _weights.stack_factor_coefs([k._coef() for k in kernels])
         coef, basis = _weights.chebyshev_or_monomial(coef)
         return _ops.SeriesSpec(self.dim, 2, basis, 1.0, 0.0, -_CLAMP, _CLAMP), coef
 
@@ -37,7 +47,13 @@ class _TorusKernel(Kernel):
         x1c, x2c = self._to_circles(x1), self._to_circles(x2)
         if x1c.shape[-1] != 2 * self.dim or x2c.shape[-1] != 2 * self.dim:
             raise RuntimeError("T^%d points must be %d angles or %d circle coordinates" % (self.dim, self.dim, 2 * self.dim))
-        spec, coef = _series_on(self, x1c.device)
+        fit_sized = (x1c.dim() == 2 and x2c.dim() == 2 and x1c.shape[0] * x2c.shape[0] < SYNC_FREE_MAX_ENTRIES
+                     and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+                     and not (x1c.requires_grad or x2c.requires_grad))
+        if fit_sized:
+            spec, coef = self.series(sync_free=True)
+        else:
+            spec, coef = _series_on(self, x1c.device)
         if torch.is_grad_enabled() and (x1c.requires_grad or x2c.requires_grad):
             # Input gradients (and the Hessian-vector products of the trust-region solver, bo_torus.py:278): evaluate
             # the product factor by factor - every single-factor op is twice differentiable with respect to its inputs.

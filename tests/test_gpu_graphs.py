@@ -80,14 +80,14 @@ def test_graphed_trust_region_step_matches_eager():
         assert rel_err(hvp, he) < 1e-10
 
 
-@pytest.mark.parametrize("name", ["H2", "H3", "SPD2", "Euclid"])
+@pytest.mark.parametrize("name", ["H2", "H3", "SPD2", "Euclid", "T3"])
 def test_graphed_mll_step_on_the_quadrature_kernels(name):
     """The hyper-parameter -> node-weight chain of the quadrature kernels runs without a host read of the lengthscale
     (mgb_matern_t_grid, float64 regime), so the whole marginal-likelihood step is CUDA-graph capturable: replays track
     parameter updates and equal the eager path with the host-built grids (MGB_DEVICE_GRIDS=0 semantics)."""
     import os
 
-    from materngabo_b200 import kernels_euclidean as ke, kernels_hyperbolic as kh, kernels_spd as ksp
+    from materngabo_b200 import kernels_euclidean as ke, kernels_hyperbolic as kh, kernels_spd as ksp, kernels_torus as kt
     from materngabo_b200.gpytorch_compat import ScaleKernel
     from materngabo_b200.graphs import GraphedValueAndGrad, exact_mll
 
@@ -97,23 +97,29 @@ def test_graphed_mll_step_on_the_quadrature_kernels(name):
         dim = int(name[1])
         z = 0.7 * torch.randn(n, dim, generator=gen)
         x = torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1)
-        base = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=dim, nu=2.5)
+        # (the reference's default of 50 nodes does not give a positive definite H^2 Gram matrix at these points:
+        #  smallest eigenvalue -0.7 in the oracle; 128 nodes do)
+        base = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=dim, nu=2.5, nb_points_integral=128)
     elif name == "SPD2":
         a = torch.randn(n, 2, 2, generator=gen)
         sm = a @ a.transpose(-1, -2) + 0.5 * torch.eye(2)
         x = torch.stack([sm[:, 0, 0], sm[:, 1, 1], sm[:, 0, 1] * 2 ** 0.5], -1)
         base = ksp.SpdRiemannianIntegratedMaternKernel(2, nu=2.5)
+    elif name == "T3":
+        x = torch.rand(n, 3, generator=gen) * 6.283185307179586
+        base = kt.TorusProductOfManifoldsRiemannianMaternKernel(dim=3, nu=2.5)
     else:
         x = torch.randn(n, 3, generator=gen)
         base = ke.EuclideanIntegratedMaternKernel(3, nu=2.5)
     x = x.to(DEV)
     y = torch.sin(2 * x[:, 1])
     sk = ScaleKernel(base).to(DEV)
-    params = [base.raw_lengthscale, sk.raw_outputscale]
+    first = base.torus_kernel.kernels[0] if name == "T3" else base        # the torus carries one lengthscale per circle
+    params = [first.raw_lengthscale, sk.raw_outputscale]
     g = GraphedValueAndGrad(lambda: exact_mll(sk, x, y, 5e-2, 0.1), inputs=(), wrt=params)
     for raw_ls, raw_os in ((0.3, 0.0), (0.9, 0.5), (-0.2, -0.4)):
         with torch.no_grad():
-            base.raw_lengthscale.fill_(raw_ls)
+            first.raw_lengthscale.fill_(raw_ls)
             sk.raw_outputscale.fill_(raw_os)
         value, grads = g()
         assert int(g.aux[0]) == 0
