@@ -52,6 +52,7 @@ class _TorusKernel(Kernel):
                      and not (x1c.requires_grad or x2c.requires_grad))
         if fit_sized:
             spec, coef = self.series(sync_free=True)
+            coef = coef.to(x1c.device)
         else:
             spec, coef = _series_on(self, x1c.device)
         if torch.is_grad_enabled() and (x1c.requires_grad or x2c.requires_grad):
