@@ -15,7 +15,11 @@ dev = "cuda:0"
 gen = torch.Generator().manual_seed(0)
 
 
+REPS = int(os.environ.get("REPS", "0"))
+
+
 def timed(name, fn, reps=5):
+    reps = REPS or reps
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
