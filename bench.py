@@ -7,7 +7,7 @@ one box (strong scaling, one process per GPU, NCCL only for the state broadcast 
 
   python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA, sm_100a)
   python bench.py --impl reference ...                          the reference's CPU algorithm (oracle port)
-  python bench.py --workload gram-so3|gram-s2|gram-s10|gram-t10|gram-h2|gram-spd2|gram-spd3   Gram-matrix workloads
+  python bench.py --workload gram-so3|gram-so5|gram-s2|gram-s10|gram-t10|gram-h2|gram-spd2|gram-spd3   Gram-matrix workloads
   python bench.py --workload gram-h2-table   opt-in tabulated H^2 profile (not the per-entry quadrature)
   python bench.py --workload config1-s2      BASELINE configs[0]: S^2 Matern Gram 1000 x 1000 (L2 flushed between steps)
   python bench.py --workload config2-bo-s3   BASELINE configs[1]: S^3 GaBO call latencies (N = 100)
@@ -441,6 +441,19 @@ def gram_setup(name, device, m, n):
             return q.reshape(cnt, 9).contiguous()
         x1, x2 = rot(m), rot(n)
         flops = 62
+    elif name == "gram-so5":
+        # SO(5) character sum at the canonical eigen-angles (csrc/son_gram.cu): latency / FP64 bound,
+        # no roofline convention in the survey - reported as entries/s with the oracle-port CPU baseline beside it
+        k = kernels_so.SORiemannianMaternKernel(dim=5, nu=2.5)
+        k.lengthscale = 0.5
+
+        def rot5(cnt):
+            q, r = torch.linalg.qr(torch.randn(cnt, 5, 5, generator=gen, device=device, dtype=F64))
+            q = q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1)).unsqueeze(-2)
+            q[:, :, 0] = q[:, :, 0] * torch.sign(torch.linalg.det(q)).unsqueeze(-1)
+            return q.reshape(cnt, 25).contiguous()
+        x1, x2 = rot5(m), rot5(n)
+        flops = 0
     elif name == "gram-t10":
         k = kernels_torus.TorusProductOfManifoldsRiemannianMaternKernel(dim=10, nu=2.5)
         for kk in k.torus_kernel.kernels:
@@ -511,7 +524,7 @@ EXECUTED = {}
 
 GRAM_DEFAULTS = {"config1-s2": (1000, 1000), "gram-s2": (1_000_000, 2000), "gram-s10": (1_000_000, 2000), "gram-so3": (1_000_000, 2000),
                  "gram-t10": (1_000_000, 2000), "gram-h2": (2000, 2000), "gram-spd2": (2000, 2000), "gram-spd3": (2000, 2000),
-                 "gram-h2-table": (1_000_000, 2000)}
+                 "gram-h2-table": (1_000_000, 2000), "gram-so5": (65536, 2048)}
 
 
 # FP64 instructions (DFMA + DMUL + DADD, thread level) the quadrature Gram kernels EXECUTE per entry at 64 x 64 nodes,
@@ -654,7 +667,7 @@ def run_gram(args, rank, world, local, min_seconds=0.0, cpu_seconds=8.0):
     if rank != 0:
         return None
     peaks = measured_peaks()
-    quad = args.workload in ("gram-h2", "gram-spd2", "gram-spd3", "gram-t10")
+    quad = args.workload in ("gram-h2", "gram-spd2", "gram-spd3", "gram-t10", "gram-so5")
     if quad:
         tf = C.c_double()
         _lib.check(lib.mgb_fp64_peak(0, 3, C.byref(tf), None), "mgb_fp64_peak")
@@ -841,6 +854,37 @@ def run_bo_latency(args, local):
         return ei.cpu()
 
     lat["ei_value_grad_hvp_b5_fused_us"] = timeit(tr_fused5, reps)
+    # the same marginal-likelihood step on the other manifolds of the reference's BO scripts, N = 100, CUDA-graph replay
+    # (sync-free hyper-parameter chains: mgb_matern_t_grid / circle_coef_sync_free)
+    from materngabo_b200 import kernels_hyperbolic, kernels_spd, kernels_torus
+
+    def _hyp(dim):
+        z = 0.7 * torch.randn(100, dim, generator=gen)
+        return torch.cat([torch.sqrt(1 + (z ** 2).sum(-1, keepdim=True)), z], -1)
+
+    def _spd():
+        a = torch.randn(100, 2, 2, generator=gen)
+        sm = a @ a.transpose(-1, -2) + 0.5 * torch.eye(2)
+        return torch.stack([sm[:, 0, 0], sm[:, 1, 1], sm[:, 0, 1] * 2 ** 0.5], -1)
+
+    for tag, kern, pts in (("torus_T3", kernels_torus.TorusProductOfManifoldsRiemannianMaternKernel(dim=3, nu=2.5), torch.rand(100, 3, generator=gen) * 6.283185307179586),
+                           ("hyperbolic_H2", kernels_hyperbolic.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=2, nu=2.5, nb_points_integral=128), _hyp(2)),
+                           ("hyperbolic_H3", kernels_hyperbolic.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=3, nu=2.5), _hyp(3)),
+                           ("spd2", kernels_spd.SpdRiemannianIntegratedMaternKernel(2, nu=2.5), _spd())):
+        try:
+            skm = ScaleKernel(kern).to(dev)
+            xm = pts.to(dev)
+            ym = torch.sin(3 * xm[:, 0])
+            prm = [p_ for p_ in skm.parameters() if p_.requires_grad]
+            gmm = GraphedValueAndGrad(lambda: exact_mll(skm, xm, ym, 5e-2, 0.0), inputs=(), wrt=prm)
+
+            def _step():
+                value, grads = gmm()
+                return float(value)
+
+            lat["mll_step_graph_%s_us" % tag] = timeit(_step, reps)
+        except Exception as exc:
+            lat["mll_step_graph_%s_us" % tag] = "failed: %s" % type(exc).__name__
     launches = lib.mgb_launch_count() - launches0
     clocks = sampler.stop()
     cpu = None
@@ -883,7 +927,7 @@ def cpu_gram_baseline(workload, x1, x2, seconds=8.0):
     O(P x M x N) temporaries for the quadrature kernels and O(M x N x D) for the distances)."""
     from oracle import restated as R
     use_all_host_threads()
-    blocks = {"gram-s2": (4000, 2000), "gram-s10": (4000, 2000), "config1-s2": (1000, 1000), "gram-so3": (800, 500),
+    blocks = {"gram-s2": (4000, 2000), "gram-s10": (4000, 2000), "config1-s2": (1000, 1000), "gram-so3": (800, 500), "gram-so5": (24, 24),
               "gram-t10": (100, 200), "gram-h2": (200, 300), "gram-spd2": (150, 100), "gram-spd3": (600, 400)}
     if workload not in blocks:
         return None
@@ -891,6 +935,7 @@ def cpu_gram_baseline(workload, x1, x2, seconds=8.0):
     a, b = x1[:bm].cpu(), x2[:bn].cpu()
     fns = {"gram-s2": lambda: R.sphere_matern(a, b, 2, 2.5, 0.5), "config1-s2": lambda: R.sphere_matern(a, b, 2, 2.5, 0.5),
            "gram-s10": lambda: R.sphere_matern(a, b, 10, 2.5, 0.5), "gram-so3": lambda: R.so3_matern(a, b, 2.5, 0.5),
+           "gram-so5": lambda: R.son_matern(a, b, 5, 2.5, 0.5),
            "gram-t10": lambda: R.torus_matern(a, b, 10, 2.5, 0.5), "gram-h2": lambda: R.hyperbolic_integrated_matern(a, b, 2, 2.5, 1.0, 64),
            "gram-spd2": lambda: R.spd2_integrated_matern(a, b, 2.5, 1.0, 64, 64),
            "gram-spd3": lambda: R.spd_product_matern(a, b, 3, 2.5, 1.0, 0.5, "so")}

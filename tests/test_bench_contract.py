@@ -73,7 +73,7 @@ def test_our_arm_json_line_on_the_gpu():
 @pytest.mark.gpu
 @pytest.mark.parametrize("workload,rows,cols", [("config1-s2", 500, 500), ("gram-so3", 4096, 512), ("gram-t10", 4096, 256),
                                                 ("gram-h2", 256, 256), ("gram-spd2", 256, 256), ("gram-spd3", 256, 256),
-                                                ("gram-h2-table", 4096, 512)])
+                                                ("gram-h2-table", 4096, 512), ("gram-so5", 512, 256)])
 def test_gram_workloads_run_small(workload, rows, cols):
     """Every Gram workload of bench.py on a small block (also the L2-flushed / graph-replayed timing branch)."""
     r = _run(["--workload", workload, "--cands", str(rows), "--train", str(cols), "--steps", "2", "--warmup", "3", "--no-cpu-baseline"])
