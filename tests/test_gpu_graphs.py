@@ -131,3 +131,25 @@ def test_graphed_mll_step_on_the_quadrature_kernels(name):
             del os.environ["MGB_DEVICE_GRIDS"]
         assert abs(float(value) - float(loss.detach())) < 1e-11 * max(1.0, abs(float(loss.detach())))
         assert rel_err(grads[0], ref[0]) < 1e-9 and rel_err(grads[1], ref[1]) < 1e-9
+
+
+def test_graphed_mll_step_on_the_multi_cta_dense_path():
+    """n = 300: Gram kernel + cooperative Cholesky + triangular inverse + gradient contraction (csrc/dense_spd.cu) captured
+    into a CUDA graph (cooperative launches are capturable) - replays track the parameters and equal eager execution."""
+    from materngabo_b200.graphs import GraphedValueAndGrad, exact_mll
+
+    x, y, base, sk, _ = _problem(300, seed=5)
+    params = [base.raw_lengthscale, sk.raw_outputscale]
+    for p in params:
+        p.requires_grad_(True)
+    g = GraphedValueAndGrad(lambda: exact_mll(sk, x, y, 1e-2, 0.1), inputs=(), wrt=params)
+    for raw_ls, raw_os in ((0.0, 0.0), (-0.5, 0.6)):
+        with torch.no_grad():
+            base.raw_lengthscale.fill_(raw_ls)
+            sk.raw_outputscale.fill_(raw_os)
+        value, grads = g()
+        assert int(g.aux[0]) == 0
+        loss, _ = exact_mll(sk, x, y, 1e-2, 0.1, fused=False)
+        ref = torch.autograd.grad(loss, params)
+        assert abs(float(value) - float(loss.detach())) < 1e-11 * max(1.0, abs(float(loss.detach())))
+        assert rel_err(grads[0], ref[0]) < 1e-9 and rel_err(grads[1], ref[1]) < 1e-9
