@@ -764,7 +764,9 @@ def pairwise(fn2d, x1: torch.Tensor, x2: torch.Tensor, diag: bool = False, serie
 
     def _same_members(t):
         """A materialised expansion (gpytorch may hand train_inputs.expand(...).contiguous()): identical batch members."""
-        return t.numel() > 0 and not t.requires_grad and bool((t == t[first]).all())
+        if t.numel() == 0 or t.requires_grad or (t.is_cuda and torch.cuda.is_current_stream_capturing()):
+            return False                    # the comparison reads a flag back: not during CUDA-graph capture
+        return bool((t == t[first]).all())
 
     if _is_broadcast_of_2d(x2) or (not _is_broadcast_of_2d(x1) and _same_members(x2)):
         k = fn2d(x1.reshape(-1, x1.shape[-1]), x2[first])
