@@ -427,6 +427,23 @@ int mgb_posterior_int8_reduce(const double* kstar, long long m, long long n, lon
                               const double* alpha, double kss, double mean_const, double* mean, double* var,
                               void* workspace, long long workspace_bytes, void* stream);
 
+/* The same contraction in ONE hand-written tcgen05 kernel (csrc/int8_fused.cu): tcgen05.mma kind::i8 on 128-candidate x
+ * 64-column tiles with the seven int32 planes in tensor memory, operands pre-tiled in the tensor core's shared-memory
+ * image and staged with cp.async.bulk, exact triangular k range, float64 recombination and the sum of squares in the
+ * epilogue (no int32 plane reaches HBM).  Same semantics and error as the mgb_posterior_int8_* calls; needs no CUTLASS.
+ * The _debug form additionally dumps the raw accumulators, planes[row block][column tile][7][128][64] int32
+ * (mgb_posterior_i8f_planes_bytes(m, n) bytes), for the tests. */
+long long mgb_posterior_i8f_pack_bytes(long long n);
+int mgb_posterior_i8f_pack(const double* rinv, long long n, long long ld, void* packed, void* stream);
+long long mgb_posterior_i8f_workspace_bytes(long long m, long long n);
+int mgb_posterior_i8f_reduce(const double* kstar, long long m, long long n, long long ldk, const void* packed,
+                             const double* alpha, double kss, double mean_const, double* mean, double* var,
+                             void* workspace, long long workspace_bytes, void* stream);
+long long mgb_posterior_i8f_planes_bytes(long long m, long long n);
+int mgb_posterior_i8f_reduce_debug(const double* kstar, long long m, long long n, long long ldk, const void* packed,
+                                   const double* alpha, double kss, double mean_const, double* mean, double* var,
+                                   void* workspace, long long workspace_bytes, int* planes, void* stream);
+
 /* Analytic EI from posterior means / variances (botorch ExpectedImprovement: sigma = sqrt(max(var, 1e-9)),
  * u = +-(mean - best_f) / sigma, EI = sigma (phi(u) + u Phi(u))), elementwise over m candidates. */
 int mgb_expected_improvement(const double* mean, const double* var, long long m, double best_f, int maximize,

@@ -14,7 +14,7 @@ import torch
 from . import build as _build
 
 MGB_OK = 0
-MGB_VERSION = 200      # must equal mgb_version() (csrc/runtime.cu): bumped whenever a signature changes
+MGB_VERSION = 201      # must equal mgb_version() (csrc/runtime.cu): bumped whenever a signature changes
 BASIS_MONOMIAL = 0
 BASIS_CHEBYSHEV = 1
 MAX_FACTORS = 16
@@ -86,6 +86,12 @@ PROTOTYPES = {
     "mgb_posterior_int8_pack": (_I, [_P, _LL, _LL, _P, _P]),
     "mgb_posterior_int8_workspace_bytes": (_LL, [_LL, _LL]),
     "mgb_posterior_int8_reduce": (_I, [_P, _LL, _LL, _LL, _P, _P, _D, _D, _P, _P, _P, _LL, _P]),
+    "mgb_posterior_i8f_pack_bytes": (_LL, [_LL]),
+    "mgb_posterior_i8f_pack": (_I, [_P, _LL, _LL, _P, _P]),
+    "mgb_posterior_i8f_workspace_bytes": (_LL, [_LL, _LL]),
+    "mgb_posterior_i8f_reduce": (_I, [_P, _LL, _LL, _LL, _P, _P, _D, _D, _P, _P, _P, _LL, _P]),
+    "mgb_posterior_i8f_planes_bytes": (_LL, [_LL, _LL]),
+    "mgb_posterior_i8f_reduce_debug": (_I, [_P, _LL, _LL, _LL, _P, _P, _D, _D, _P, _P, _P, _LL, _P, _P]),
     "mgb_expected_improvement": (_I, [_P, _P, _LL, _D, _I, _P, _P]),
     "mgb_pair_scalars": (_I, [_I, _I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P]),
     "mgb_spectral_coef": (_I, [_I, _I, _I, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),

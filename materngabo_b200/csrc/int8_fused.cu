@@ -1,0 +1,472 @@
+// Posterior variance on the INT8 tensor cores, hand-written: tcgen05.mma kind::i8 with the accumulators in tensor
+// memory, operands staged by the bulk-copy engine, float64 recombination in the epilogue (opt-in path).
+//
+//   V = K* L^-T  (m x n),   var_i = kss - sum_j V_ij^2          (reference: gpytorch's exact prediction strategy behind
+//                                                                 model.posterior(X), manifold_optimize.py:195,254,337)
+//
+// Error-free slicing as in int8_posterior.cu: every row of K* and of L^-1 is scaled by a power of two and cut into
+// S = 7 signed 7-bit slices, a_ik = 2^ea_i sum_p A_p[i][k] 2^(-7 (p + 1)) (likewise b_jk), so that
+//      V_ij = 2^(ea_i + eb_j) sum_{d < 7} 2^(-7 (d + 2)) C_d[i][j],     C_d = sum_{p + q = d} A_p B_q^T   (int32, exact).
+// What differs from int8_posterior.cu (library GEMMs + a recombination pass over 7 int32 planes in HBM):
+//   * ONE kernel per candidate block.  A CTA owns a 128-candidate x 64-column tile of V; the seven planes C_0..C_6 of
+//     that tile live in tensor memory (7 x 64 = 448 of the 512 columns) for the whole k loop, the 28 slice products of a
+//     k-block are 112 tcgen05.mma (M 128, N 64, K 32) issued by one thread, and the epilogue warps read the planes back
+//     with tcgen05.ld, recombine in float64 and reduce to sum_j V_ij^2 - no int32 plane ever reaches HBM;
+//   * the k loop of a column tile stops at the diagonal of L^-1 (rows j only meet k <= j): the exact triangle instead
+//     of five column blocks (50 % of the dense work instead of 60 %), with no compacted operand copies;
+//   * the slicing kernels write the operands directly in the tensor core's shared-memory image (K-major, 128-byte
+//     swizzle, one contiguous 16 KB / 8 KB tile per slice and k-block), so a tile arrives with ONE cp.async.bulk and no
+//     tensor map.
+// Pipeline per CTA (192 threads): warp 0 = producer (bulk copies: the seven B tiles of a k-block as one 56 KB copy into
+// a 2-deep ring, the A tiles one by one into a 6-deep ring), warp 1 = MMA issuer (lane 0), warps 2-5 = epilogue (one
+// TMEM lane quarter each).  mbarriers: a_full / a_empty, b_full / b_empty (tcgen05.commit releases a slot when the
+// MMAs reading it have retired), tmem_full / tmem_empty between the issuer and the epilogue.
+// Work items (row block, column tile) are laid out so that 16 row blocks (their A slices: 73 MB at n = 5000) stay in
+// L2 while the column tiles sweep over them, longest k loops first, and dealt round-robin to the persistent CTAs.
+#include "mgb_common.cuh"
+
+namespace mgb {
+
+constexpr int F8_S = 7;                   // slices
+constexpr int F8_BITS = 7;                // bits per slice
+constexpr int F8_BM = 128;                // candidates per tile = UMMA M = TMEM lanes
+constexpr int F8_BN = 64;                 // columns per tile = UMMA N
+constexpr int F8_BK = 128;                // int8 per k-block = one swizzle row
+constexpr int F8_A_TILE = F8_BM * F8_BK;  // 16 KB
+constexpr int F8_B_TILE = F8_BN * F8_BK;  // 8 KB
+constexpr int F8_A_STAGES = 6;
+constexpr int F8_B_STAGES = 2;
+constexpr int F8_THREADS = 192;
+constexpr int F8_GROUP = 16;              // row blocks per L2 group
+constexpr int F8_TMEM_COLS = 512;
+constexpr size_t F8_SMEM = 1024 + (size_t)F8_B_STAGES * F8_S * F8_B_TILE + (size_t)F8_A_STAGES * F8_A_TILE + 256;
+
+__host__ __device__ inline long long f8_round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+struct F8Geom {
+  long long np;     // n rounded up to 128
+  int KB, CT;       // k-blocks of 128, column tiles of 64 that hold columns < n
+  __host__ __device__ long long b_tile(int ct, int kb, int q) const { return (((long long)ct * KB + kb) * F8_S + q) * F8_B_TILE; }
+  __host__ __device__ long long a_tile(long long rb, int kb, int p) const { return ((rb * KB + kb) * F8_S + p) * (long long)F8_A_TILE; }
+  __host__ __device__ long long b_bytes() const { return b_tile((int)(np / F8_BN), 0, 0); }
+  __host__ __device__ long long a_bytes(long long m) const { return a_tile(f8_round_up(m, F8_BM) / F8_BM, 0, 0); }
+  __host__ __device__ static int nkb(int ct) { return ct / 2 + 1; }      // k-blocks up to the diagonal of column tile ct
+};
+
+__host__ __device__ inline F8Geom f8_geom(long long n) {
+  F8Geom g;
+  g.np = f8_round_up(n, F8_BK);
+  g.KB = (int)(g.np / F8_BK);
+  g.CT = (int)((n + F8_BN - 1) / F8_BN);
+  return g;
+}
+
+// Byte offset of (row r, 16-byte chunk c) inside a K-major tile with the 128-byte swizzle: rows are 128 bytes, groups of
+// eight rows are 1024 bytes, and the chunk index is XORed with the row index inside the group.
+__device__ __forceinline__ int f8_swizzled(int r, int c16) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4); }
+
+// One warp per row: e = exponent with |row| 2^-e < 1/2, then S round-to-nearest slices of 7 bits, written into the
+// tiled operand image.  is_b = 0: K* rows (128-row tiles; also mean_i = mean_const + sum_j K*_ij alpha_j);
+// is_b = 1: rows of L^-1 (64-row tiles, lower triangle only, k-blocks beyond the tile's diagonal are never read).
+// Rows in [rows, rows_pad) are written as zeros.
+__global__ void __launch_bounds__(256) f8_slice_kernel(const double* src, long long ld, long long rows, long long rows_pad, int cols,
+                                                       F8Geom g, int is_b, signed char* dst, int* exps, double* scales,
+                                                       const double* alpha, double mean_const, double* mean) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows_pad) return;
+  const bool valid = row < rows;
+  const double* s = src + (valid ? row : 0) * ld;
+  const int used = !valid ? 0 : (is_b ? (int)min((long long)cols, row + 1) : cols);
+  double mx = 0.0, mu = 0.0;
+  if (alpha != nullptr) {
+    for (int c = lane; c < used; c += 32) {
+      const double v = s[c];
+      mx = fmax(mx, fabs(v));
+      mu = fma(v, alpha[c], mu);
+    }
+    mu = warp_sum(mu);
+    if (lane == 0 && valid) mean[row] = mean_const + mu;
+  } else {
+    for (int c = lane; c < used; c += 32) mx = fmax(mx, fabs(s[c]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  int e = 0;
+  if (mx > 0.0) {
+    (void)frexp(mx, &e);
+    e += 1;
+  }
+  if (lane == 0) {
+    if (exps != nullptr) exps[row] = e;
+    if (scales != nullptr) scales[row] = ldexp(1.0, e);
+  }
+  const int tile_rows = is_b ? F8_BN : F8_BM;
+  const long long tile_bytes = (long long)tile_rows * F8_BK;
+  const long long rt = row / tile_rows;
+  const int rr = (int)(row % tile_rows);
+  const int kb_end = is_b ? min(g.KB, F8Geom::nkb((int)rt)) : g.KB;
+  signed char* base = dst + rt * g.KB * F8_S * tile_bytes;
+  for (long long c0 = 16 * lane; c0 < (long long)kb_end * F8_BK; c0 += 512) {
+    double r[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) r[t] = (c0 + t < used) ? ldexp(s[c0 + t], -e) : 0.0;
+    const int kb = (int)(c0 / F8_BK);
+    signed char* tile = base + (long long)kb * F8_S * tile_bytes + f8_swizzled(rr, (int)(c0 % F8_BK) >> 4);
+#pragma unroll 1
+    for (int p = 0; p < F8_S; ++p) {
+      uint4 q;
+      signed char* qq = reinterpret_cast<signed char*>(&q);
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const double x = r[t] * (double)(1 << F8_BITS);
+        const double qi = rint(x);
+        qq[t] = (signed char)(int)qi;
+        r[t] = x - qi;
+      }
+      *reinterpret_cast<uint4*>(tile + p * tile_bytes) = q;
+    }
+  }
+}
+
+// ---- tcgen05 / tensor memory ---------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle: start address >> 4 in [0, 14), leading byte offset
+// (unused for swizzled K-major, 1) in [16, 30), stride byte offset (eight rows = 1024 bytes) >> 4 in [32, 46),
+// descriptor version 1 in [46, 48), layout type 2 (128-byte swizzle) in [61, 64).
+__device__ __forceinline__ uint64_t f8_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor, kind::i8: D int32 (2 in [4, 6)), A and B signed 8-bit (1 in [7, 10) and [10, 13)), both
+// K-major (0 in bits 15, 16), N >> 3 in [17, 23), M >> 4 in [24, 29).
+constexpr uint32_t F8_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(F8_BN >> 3) << 17) | ((uint32_t)(F8_BM >> 4) << 24);
+
+__device__ __forceinline__ void f8_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(F8_IDESC), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once every tcgen05 operation issued so far by this thread has completed
+__device__ __forceinline__ void f8_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void f8_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void f8_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// 16 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void f8_tmem_ld16(uint32_t taddr, int (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void f8_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ bool f8_mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol error traps (launch failure reported to the host) instead of hanging the device.
+__device__ __forceinline__ void f8_mbar_spin(uint64_t* bar, uint32_t parity) {
+  for (unsigned spins = 0; !f8_mbar_test(bar, parity); ++spins) {
+    if (spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void f8_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct F8Params {
+  const signed char* A;      // tiled K* slices  [row block][k-block][slice][128 x 128 swizzled]
+  const signed char* B;      // tiled L^-1 slices [column tile][k-block][slice][64 x 128 swizzled]
+  const int* ea;             // exponent per candidate
+  const double* sb;          // 2^eb per column
+  double* partial;           // [column tile][m_pad] sums of squares
+  int* planes;               // debug: [row block][column tile][7][128][64] raw accumulators, or nullptr
+  long long m, m_pad;
+  long long n_rb;            // row blocks
+  long long items;           // work items incl. the padding of the last group
+  F8Geom g;
+};
+
+struct F8Item {
+  long long rb;
+  int ct;
+  bool live;
+};
+__device__ __forceinline__ F8Item f8_item(const F8Params& P, long long it) {
+  const long long per_group = (long long)F8_GROUP * P.g.CT;
+  const long long grp = it / per_group;
+  const int r = (int)(it % per_group);
+  F8Item w;
+  w.ct = P.g.CT - 1 - r / F8_GROUP;              // longest k loops first
+  w.rb = grp * F8_GROUP + r % F8_GROUP;
+  w.live = w.rb < P.n_rb;
+  return w;
+}
+
+__global__ void __launch_bounds__(F8_THREADS, 1) f8_posterior_kernel(const F8Params P) {
+  extern __shared__ unsigned char f8_smem_raw[];
+  const uint32_t raw = smem_u32(f8_smem_raw);
+  unsigned char* smem = f8_smem_raw + (((raw + 1023u) & ~1023u) - raw);      // the swizzle pattern is on absolute address bits
+  unsigned char* Bs = smem;
+  unsigned char* As = smem + (size_t)F8_B_STAGES * F8_S * F8_B_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(As + (size_t)F8_A_STAGES * F8_A_TILE);
+  uint64_t* a_full = bars;                          // [F8_A_STAGES]
+  uint64_t* a_empty = a_full + F8_A_STAGES;         // [F8_A_STAGES]
+  uint64_t* b_full = a_empty + F8_A_STAGES;         // [F8_B_STAGES]
+  uint64_t* b_empty = b_full + F8_B_STAGES;         // [F8_B_STAGES]
+  uint64_t* tmem_full = b_empty + F8_B_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < F8_A_STAGES; ++s) {
+      mbar_init(a_full + s, 1);
+      mbar_init(a_empty + s, 1);
+    }
+    for (int s = 0; s < F8_B_STAGES; ++s) {
+      mbar_init(b_full + s, 1);
+      mbar_init(b_empty + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(F8_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  f8_fence_before();
+  __syncthreads();
+  f8_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0;
+      for (long long it = blockIdx.x; it < P.items; it += gridDim.x) {
+        const F8Item w = f8_item(P, it);
+        if (!w.live) continue;
+        const int nkb = F8Geom::nkb(w.ct);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t bs = b_it % F8_B_STAGES, bph = (b_it / F8_B_STAGES) & 1u;
+          f8_mbar_spin(b_empty + bs, bph ^ 1u);
+          mbar_expect_tx(b_full + bs, F8_S * F8_B_TILE);
+          bulk_g2s(Bs + (size_t)bs * F8_S * F8_B_TILE, P.B + P.g.b_tile(w.ct, kb, 0), F8_S * F8_B_TILE, b_full + bs);
+          ++b_it;
+          for (int p = 0; p < F8_S; ++p) {
+            const uint32_t as = a_it % F8_A_STAGES, aph = (a_it / F8_A_STAGES) & 1u;
+            f8_mbar_spin(a_empty + as, aph ^ 1u);
+            mbar_expect_tx(a_full + as, F8_A_TILE);
+            bulk_g2s(As + (size_t)as * F8_A_TILE, P.A + P.g.a_tile(w.rb, kb, p), F8_A_TILE, a_full + as);
+            ++a_it;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    uint32_t a_it = 0, b_it = 0, n_item = 0;
+    for (long long it = blockIdx.x; it < P.items; it += gridDim.x) {
+      const F8Item w = f8_item(P, it);
+      if (!w.live) continue;
+      const int nkb = F8Geom::nkb(w.ct);
+      f8_mbar_spin(tmem_empty, (n_item & 1u) ^ 1u);       // the epilogue has drained the previous tile
+      f8_fence_after();
+      for (int kb = 0; kb < nkb; ++kb) {
+        const uint32_t bs = b_it % F8_B_STAGES, bph = (b_it / F8_B_STAGES) & 1u;
+        f8_mbar_spin(b_full + bs, bph);
+        const uint32_t b_addr = smem_u32(Bs + (size_t)bs * F8_S * F8_B_TILE);
+        for (int p = 0; p < F8_S; ++p) {
+          const uint32_t as = a_it % F8_A_STAGES, aph = (a_it / F8_A_STAGES) & 1u;
+          f8_mbar_spin(a_full + as, aph);
+          f8_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(As + (size_t)as * F8_A_TILE);
+            for (int q = 0; q < F8_S - p; ++q) {
+#pragma unroll
+              for (int ks = 0; ks < F8_BK / 32; ++ks) {
+                f8_mma(tmem_base + (uint32_t)((p + q) * F8_BN), f8_smem_desc(a_addr + ks * 32),
+                       f8_smem_desc(b_addr + q * F8_B_TILE + ks * 32), (kb | p | ks) != 0 ? 1u : 0u);
+              }
+            }
+            f8_commit(a_empty + as);                      // slot free once these MMAs have read it
+          }
+          __syncwarp();
+          ++a_it;
+        }
+        if (lane == 0) f8_commit(b_empty + bs);
+        __syncwarp();
+        ++b_it;
+      }
+      if (lane == 0) f8_commit(tmem_full);                // all seven planes of the tile are final
+      __syncwarp();
+      ++n_item;
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    double wgt[F8_S];
+#pragma unroll
+    for (int d = 0; d < F8_S; ++d) wgt[d] = exp2((double)(-F8_BITS * (d + 2)));
+    uint32_t n_item = 0;
+    for (long long it = blockIdx.x; it < P.items; it += gridDim.x) {
+      const F8Item w = f8_item(P, it);
+      if (!w.live) continue;
+      const long long row = w.rb * F8_BM + quarter * 32 + lane;
+      f8_mbar_spin(tmem_full, n_item & 1u);
+      f8_fence_after();
+      double ss = 0.0;
+#pragma unroll 1
+      for (int c = 0; c < F8_BN / 16; ++c) {
+        double acc[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc[t] = 0.0;
+#pragma unroll
+        for (int d = F8_S - 1; d >= 0; --d) {             // smallest weights first
+          int v[16];
+          f8_tmem_ld16(lane_addr + (uint32_t)(d * F8_BN + c * 16), v);
+          f8_tmem_ld_wait();
+          if (P.planes != nullptr) {
+            int* dbg = P.planes + (((w.rb * P.g.CT + w.ct) * F8_S + d) * F8_BM + (quarter * 32 + lane)) * F8_BN + c * 16;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) dbg[t] = v[t];
+          }
+#pragma unroll
+          for (int t = 0; t < 16; ++t) acc[t] = fma((double)v[t], wgt[d], acc[t]);
+        }
+        const double* sb = P.sb + (long long)w.ct * F8_BN + c * 16;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const double x = acc[t] * __ldg(sb + t);
+          ss = fma(x, x, ss);
+        }
+      }
+      f8_fence_before();
+      __syncwarp();
+      if (lane == 0) f8_mbar_arrive(tmem_empty);
+      if (row < P.m) P.partial[(long long)w.ct * P.m_pad + row] = ldexp(ss, 2 * P.ea[row]);
+      ++n_item;
+    }
+  }
+  f8_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    f8_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(F8_TMEM_COLS) : "memory");
+  }
+}
+
+// var_i = kss - sum over column tiles (fixed order: reproducible)
+__global__ void __launch_bounds__(256) f8_finish_kernel(const double* partial, long long m, long long m_pad, int CT, double kss, double* var) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double s = 0.0;
+  for (int ct = 0; ct < CT; ++ct) s += partial[(long long)ct * m_pad + i];
+  var[i] = kss - s;
+}
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" long long mgb_posterior_i8f_pack_bytes(long long n) {
+  if (n < 1) return 0;
+  const F8Geom g = f8_geom(n);
+  return 8 * g.np + g.b_bytes();
+}
+
+extern "C" int mgb_posterior_i8f_pack(const double* rinv, long long n, long long ld, void* packed, void* stream) {
+  if (!rinv || !packed || n < 1 || ld < n) return fail(MGB_ERR_ARG, "posterior_i8f_pack: bad argument");
+  if (n > 32768) return fail(MGB_ERR_ARG, "posterior_i8f_pack: n too large for exact int32 accumulation");
+  const F8Geom g = f8_geom(n);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double* sb = static_cast<double*>(packed);
+  signed char* B = static_cast<signed char*>(packed) + 8 * g.np;
+  MGB_TRY(check_cuda(cudaMemsetAsync(packed, 0, (size_t)mgb_posterior_i8f_pack_bytes(n), s), "cudaMemsetAsync"));
+  f8_slice_kernel<<<(unsigned)((g.np + 7) / 8), 256, 0, s>>>(rinv, ld, n, g.np, (int)n, g, 1, B, nullptr, sb, nullptr, 0.0, nullptr);
+  return after_launch("f8_slice_kernel (pack)");
+}
+
+static long long f8_ws_ea(long long m) { return f8_round_up(4 * f8_round_up(m, F8_BM), 256); }
+
+extern "C" long long mgb_posterior_i8f_workspace_bytes(long long m, long long n) {
+  if (m < 1 || n < 1) return 0;
+  const F8Geom g = f8_geom(n);
+  const long long m_pad = f8_round_up(m, F8_BM);
+  return f8_ws_ea(m) + f8_round_up(g.a_bytes(m), 256) + (long long)g.CT * m_pad * 8;
+}
+
+static int f8_reduce(const double* kstar, long long m, long long n, long long ldk, const void* packed, const double* alpha,
+                     double kss, double mean_const, double* mean, double* var, void* workspace, long long workspace_bytes,
+                     int* planes, void* stream) {
+  if (m == 0) return MGB_OK;
+  if (!kstar || !packed || !alpha || !mean || !var || !workspace || m < 0 || n < 1 || ldk < n)
+    return fail(MGB_ERR_ARG, "posterior_i8f_reduce: bad argument");
+  if (m > 0x7fffffffLL / 8 || n > 32768) return fail(MGB_ERR_ARG, "posterior_i8f_reduce: block too large");
+  if (workspace_bytes < mgb_posterior_i8f_workspace_bytes(m, n)) return fail(MGB_ERR_ARG, "posterior_i8f_reduce: workspace too small");
+  const F8Geom g = f8_geom(n);
+  const long long m_pad = f8_round_up(m, F8_BM);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* w = static_cast<char*>(workspace);
+  int* ea = reinterpret_cast<int*>(w);
+  w += f8_ws_ea(m);
+  signed char* A = reinterpret_cast<signed char*>(w);
+  w += f8_round_up(g.a_bytes(m), 256);
+  double* partial = reinterpret_cast<double*>(w);
+  f8_slice_kernel<<<(unsigned)((m_pad + 7) / 8), 256, 0, s>>>(kstar, ldk, m, m_pad, (int)n, g, 0, A, ea, nullptr, alpha, mean_const, mean);
+  MGB_TRY(after_launch("f8_slice_kernel"));
+  F8Params P;
+  P.A = A;
+  P.B = static_cast<const signed char*>(packed) + 8 * g.np;
+  P.ea = ea;
+  P.sb = static_cast<const double*>(packed);
+  P.partial = partial;
+  P.planes = planes;
+  P.m = m;
+  P.m_pad = m_pad;
+  P.n_rb = m_pad / F8_BM;
+  P.items = f8_round_up(P.n_rb, F8_GROUP) * g.CT;
+  P.g = g;
+  MGB_TRY(check_cuda(cudaFuncSetAttribute(f8_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F8_SMEM), "cudaFuncSetAttribute"));
+  const long long live = P.n_rb * g.CT;
+  const unsigned grid = (unsigned)std::min<long long>(device_sm_count(), live);
+  f8_posterior_kernel<<<grid, F8_THREADS, F8_SMEM, s>>>(P);
+  MGB_TRY(after_launch("f8_posterior_kernel"));
+  f8_finish_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(partial, m, m_pad, g.CT, kss, var);
+  return after_launch("f8_finish_kernel");
+}
+
+extern "C" int mgb_posterior_i8f_reduce(const double* kstar, long long m, long long n, long long ldk, const void* packed,
+                                        const double* alpha, double kss, double mean_const, double* mean, double* var,
+                                        void* workspace, long long workspace_bytes, void* stream) {
+  return f8_reduce(kstar, m, n, ldk, packed, alpha, kss, mean_const, mean, var, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" long long mgb_posterior_i8f_planes_bytes(long long m, long long n) {
+  if (m < 1 || n < 1) return 0;
+  const F8Geom g = f8_geom(n);
+  return f8_round_up(m, F8_BM) / F8_BM * g.CT * (long long)F8_S * F8_BM * F8_BN * 4;
+}
+
+extern "C" int mgb_posterior_i8f_reduce_debug(const double* kstar, long long m, long long n, long long ldk, const void* packed,
+                                              const double* alpha, double kss, double mean_const, double* mean, double* var,
+                                              void* workspace, long long workspace_bytes, int* planes, void* stream) {
+  if (!planes) return fail(MGB_ERR_ARG, "posterior_i8f_reduce_debug: planes is null");
+  return f8_reduce(kstar, m, n, ldk, packed, alpha, kss, mean_const, mean, var, workspace, workspace_bytes, planes, stream);
+}
