@@ -23,6 +23,8 @@
 // MMAs reading it have retired), tmem_full / tmem_empty between the issuer and the epilogue.
 // Work items (row block, column tile) are laid out so that 16 row blocks (their A slices: 73 MB at n = 5000) stay in
 // L2 while the column tiles sweep over them, longest k loops first, and dealt round-robin to the persistent CTAs.
+#include <cstdlib>
+
 #include "mgb_common.cuh"
 
 namespace mgb {
@@ -37,7 +39,6 @@ constexpr int F8_B_TILE = F8_BN * F8_BK;  // 8 KB
 constexpr int F8_A_STAGES = 6;
 constexpr int F8_B_STAGES = 2;
 constexpr int F8_THREADS = 192;
-constexpr int F8_GROUP = 16;              // row blocks per L2 group
 constexpr int F8_TMEM_COLS = 512;
 constexpr size_t F8_SMEM = 1024 + (size_t)F8_B_STAGES * F8_S * F8_B_TILE + (size_t)F8_A_STAGES * F8_A_TILE + 256;
 
@@ -138,16 +139,18 @@ __device__ __forceinline__ uint64_t f8_smem_desc(uint32_t saddr) {
 }
 // Instruction descriptor, kind::i8: D int32 (2 in [4, 6)), A and B signed 8-bit (1 in [7, 10) and [10, 13)), both
 // K-major (0 in bits 15, 16), N >> 3 in [17, 23), M >> 4 in [24, 29).
-constexpr uint32_t F8_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(F8_BN >> 3) << 17) | ((uint32_t)(F8_BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t f8_idesc(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(F8_BM >> 4) << 24);
+}
 
-__device__ __forceinline__ void f8_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void f8_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(F8_IDESC), "r"(accumulate)
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // mbarrier arrive once every tcgen05 operation issued so far by this thread has completed
@@ -197,6 +200,8 @@ struct F8Params {
   long long m, m_pad;
   long long n_rb;            // row blocks
   long long items;           // work items incl. the padding of the last group
+  int group;                 // row blocks per L2 group
+  int debug;                 // timing experiments (MGB_I8F_DEBUG): 1 = no copies, 2 = no MMAs (results are then garbage), 8 = k step outermost
   F8Geom g;
 };
 
@@ -206,12 +211,12 @@ struct F8Item {
   bool live;
 };
 __device__ __forceinline__ F8Item f8_item(const F8Params& P, long long it) {
-  const long long per_group = (long long)F8_GROUP * P.g.CT;
+  const long long per_group = (long long)P.group * P.g.CT;
   const long long grp = it / per_group;
   const int r = (int)(it % per_group);
   F8Item w;
-  w.ct = P.g.CT - 1 - r / F8_GROUP;              // longest k loops first
-  w.rb = grp * F8_GROUP + r % F8_GROUP;
+  w.ct = P.g.CT - 1 - r / P.group;               // longest k loops first
+  w.rb = grp * P.group + r % P.group;
   w.live = w.rb < P.n_rb;
   return w;
 }
@@ -265,14 +270,22 @@ __global__ void __launch_bounds__(F8_THREADS, 1) f8_posterior_kernel(const F8Par
         for (int kb = 0; kb < nkb; ++kb) {
           const uint32_t bs = b_it % F8_B_STAGES, bph = (b_it / F8_B_STAGES) & 1u;
           f8_mbar_spin(b_empty + bs, bph ^ 1u);
-          mbar_expect_tx(b_full + bs, F8_S * F8_B_TILE);
-          bulk_g2s(Bs + (size_t)bs * F8_S * F8_B_TILE, P.B + P.g.b_tile(w.ct, kb, 0), F8_S * F8_B_TILE, b_full + bs);
+          if (P.debug & 1) {
+            f8_mbar_arrive(b_full + bs);
+          } else {
+            mbar_expect_tx(b_full + bs, F8_S * F8_B_TILE);
+            bulk_g2s(Bs + (size_t)bs * F8_S * F8_B_TILE, P.B + P.g.b_tile(w.ct, kb, 0), F8_S * F8_B_TILE, b_full + bs);
+          }
           ++b_it;
           for (int p = 0; p < F8_S; ++p) {
             const uint32_t as = a_it % F8_A_STAGES, aph = (a_it / F8_A_STAGES) & 1u;
             f8_mbar_spin(a_empty + as, aph ^ 1u);
-            mbar_expect_tx(a_full + as, F8_A_TILE);
-            bulk_g2s(As + (size_t)as * F8_A_TILE, P.A + P.g.a_tile(w.rb, kb, p), F8_A_TILE, a_full + as);
+            if (P.debug & 1) {
+              f8_mbar_arrive(a_full + as);
+            } else {
+              mbar_expect_tx(a_full + as, F8_A_TILE);
+              bulk_g2s(As + (size_t)as * F8_A_TILE, P.A + P.g.a_tile(w.rb, kb, p), F8_A_TILE, a_full + as);
+            }
             ++a_it;
           }
         }
@@ -297,11 +310,32 @@ __global__ void __launch_bounds__(F8_THREADS, 1) f8_posterior_kernel(const F8Par
           f8_fence_after();
           if (lane == 0) {
             const uint32_t a_addr = smem_u32(As + (size_t)as * F8_A_TILE);
-            for (int q = 0; q < F8_S - p; ++q) {
+            // Planes p .. 6 are adjacent in tensor memory and the B tiles of a k-block are adjacent in shared memory
+            // (same swizzle pattern, 64 rows each): the 7 - p slice products of A_p are ONE MMA with N = 64 (7 - p)
+            // against the stacked tiles B_0 .. B_{6-p}, split in two where N would exceed 256 (10 MMAs per 32-byte
+            // k step instead of 28: the int8 MMA has a fixed cost per instruction of about 64 cycles, measured).
+            const int n_all = (P.debug & 2) ? 0 : F8_BN * (F8_S - p);
+            const int n0 = min(n_all, 256), n1 = n_all - n0;
+            const uint32_t d0 = tmem_base + (uint32_t)(p * F8_BN);
+            if (P.debug & 8) {
 #pragma unroll
               for (int ks = 0; ks < F8_BK / 32; ++ks) {
-                f8_mma(tmem_base + (uint32_t)((p + q) * F8_BN), f8_smem_desc(a_addr + ks * 32),
-                       f8_smem_desc(b_addr + q * F8_B_TILE + ks * 32), (kb | p | ks) != 0 ? 1u : 0u);
+                const uint32_t acc = (kb | p | ks) != 0 ? 1u : 0u;
+                const uint64_t ad = f8_smem_desc(a_addr + ks * 32);
+                if (n0 > 0) f8_mma(d0, ad, f8_smem_desc(b_addr + ks * 32), f8_idesc(n0), acc);
+                if (n1 > 0) f8_mma(d0 + 256u, ad, f8_smem_desc(b_addr + 4 * F8_B_TILE + ks * 32), f8_idesc(n1), acc);
+              }
+            } else {
+              if (n0 > 0) {
+#pragma unroll
+                for (int ks = 0; ks < F8_BK / 32; ++ks)
+                  f8_mma(d0, f8_smem_desc(a_addr + ks * 32), f8_smem_desc(b_addr + ks * 32), f8_idesc(n0), (kb | p | ks) != 0 ? 1u : 0u);
+              }
+              if (n1 > 0) {
+#pragma unroll
+                for (int ks = 0; ks < F8_BK / 32; ++ks)
+                  f8_mma(d0 + 256u, f8_smem_desc(a_addr + ks * 32), f8_smem_desc(b_addr + 4 * F8_B_TILE + ks * 32), f8_idesc(n1),
+                         (kb | p | ks) != 0 ? 1u : 0u);
               }
             }
             f8_commit(a_empty + as);                      // slot free once these MMAs have read it
@@ -403,6 +437,16 @@ extern "C" int mgb_posterior_i8f_pack(const double* rinv, long long n, long long
   return after_launch("f8_slice_kernel (pack)");
 }
 
+// Row blocks whose A slices are kept L2-resident while the column tiles sweep over them (MGB_I8F_GROUP overrides).
+static int f8_group() {
+  static const int g = [] {
+    const char* e = std::getenv("MGB_I8F_GROUP");
+    const int v = e ? std::atoi(e) : 0;
+    return v >= 1 && v <= 4096 ? v : 16;
+  }();
+  return g;
+}
+
 static long long f8_ws_ea(long long m) { return f8_round_up(4 * f8_round_up(m, F8_BM), 256); }
 
 extern "C" long long mgb_posterior_i8f_workspace_bytes(long long m, long long n) {
@@ -441,7 +485,12 @@ static int f8_reduce(const double* kstar, long long m, long long n, long long ld
   P.m = m;
   P.m_pad = m_pad;
   P.n_rb = m_pad / F8_BM;
-  P.items = f8_round_up(P.n_rb, F8_GROUP) * g.CT;
+  P.group = f8_group();
+  {
+    const char* e = std::getenv("MGB_I8F_DEBUG");
+    P.debug = e ? std::atoi(e) : 0;
+  }
+  P.items = f8_round_up(P.n_rb, P.group) * g.CT;
   P.g = g;
   MGB_TRY(check_cuda(cudaFuncSetAttribute(f8_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F8_SMEM), "cudaFuncSetAttribute"));
   const long long live = P.n_rb * g.CT;

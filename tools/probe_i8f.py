@@ -101,3 +101,5 @@ if __name__ == "__main__":
     if what in ("time", "all"):
         run(4096, 5000, False, reps=1)
         run(37888, 5000, False, reps=5)
+    if what == "one":
+        run(37888, 5000, False, reps=3)
