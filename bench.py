@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--train", dest="n", type=int, default=None, help="override training / column count")
     ap.add_argument("--posterior-path", default="fp64", choices=["fp64", "int8"],
                     help="default workload: fp64 = hand-written DMMA kernel (default); int8 = opt-in INT8 tensor-core path")
+    ap.add_argument("--int8-impl", default="fused", choices=["fused", "library"],
+                    help="--posterior-path int8: fused = this repo's tcgen05 kernel (csrc/int8_fused.cu); library = CUTLASS "
+                         "int8 GEMMs + recombination pass (csrc/int8_posterior.cu)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gram", action="store_true", help="default workload: skip the Gram-matrix leg (configs[0], [2], [3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -161,9 +164,10 @@ def run_posterior(args, rank, world, local):
     # rank 0 owns the fit; the other ranks receive the state every step (as after a refit in the BO loop)
     gp, kernel = posterior_problem(n, device)
     use_int8 = args.posterior_path == "int8"
-    if use_int8 and not lib.mgb_int8_available():
-        raise SystemExit("--posterior-path int8: libmgb was built without the CUTLASS headers")
+    if use_int8 and args.int8_impl == "library" and not lib.mgb_int8_available():
+        raise SystemExit("--posterior-path int8 --int8-impl library: libmgb was built without the CUTLASS headers")
     gp.int8 = use_int8
+    gp.int8_impl = args.int8_impl
     if rank == 0:
         gp.fit()
     sh = ShardedPosterior(compute=None) if world > 1 else None
@@ -228,8 +232,14 @@ def run_posterior(args, rank, world, local):
     if rank == 0:
         roof = posterior_roofline(gp, xc, n, lib)
         if use_int8:
-            roof = {"bound": "tensor", "kernel": "CUTLASS int8 GEMM (tcgen05 kind::i8), 35 launches per block of 32768 candidates",
-                    "achieved": value / world * 28 * 0.6 * 2.0 * n * n / 1e12, "unit": "TOP/s (int8, executed slice products over the "
+            fused = args.int8_impl == "fused"
+            # executed k extent per column: the exact triangle at 128 x 64 granularity (fused) or five column blocks
+            tri = sum((ct // 2 + 1) * 128 * 64 for ct in range((n + 63) // 64)) / float(n * n) if fused else 0.6
+            roof = {"bound": "tensor",
+                    "kernel": ("f8_posterior_kernel (this repo: tcgen05.mma kind::i8, planes in tensor memory, fused float64 "
+                               "recombination), 1 launch per block of 37888 candidates") if fused else
+                              "CUTLASS int8 GEMM (tcgen05 kind::i8), 35 launches per block of 32768 candidates",
+                    "achieved": value / world * 28 * tri * 2.0 * n * n / 1e12, "unit": "TOP/s (int8, executed slice products over the "
                     "whole step time of one GPU: slicing, recombination and the Gram kernel included)",
                     "peak": 2.0 * float(measured_peaks().get("bf16_tflops_sustained") or 1371.4),
                     "peak_source": "2 x the sustained bf16 rate of MEASURED_PEAKS.json (int8 dense = 2 x bf16 dense)",
@@ -238,8 +248,10 @@ def run_posterior(args, rank, world, local):
 
     # ---- opt-in INT8 tensor-core path on a bounded sample (rank 0, one GPU), with its parity against `value`'s path ---
     int8 = None
-    if rank == 0 and world == 1 and lib.mgb_int8_available() and m_local >= 65536 and not use_int8:
-        int8 = posterior_int8_sample(gp, xc[: min(m_local, 2 * 1024 * 1024)], value)
+    if rank == 0 and world == 1 and m_local >= 65536 and not use_int8:
+        int8 = posterior_int8_sample(gp, xc[: min(m_local, 2 * 1024 * 1024)], value, "fused")
+        if lib.mgb_int8_available():
+            int8["library_variant"] = posterior_int8_sample(gp, xc[: min(m_local, 1024 * 1024)], value, "library")
 
     # ---- end to end through the host-buffer C-ABI call -------------------------------------------
     e2e = None
@@ -274,12 +286,14 @@ def run_posterior(args, rank, world, local):
     return out
 
 
-def posterior_int8_sample(gp, xs, fp64_value):
-    """The opt-in INT8 path (materngabo_b200/csrc/int8_posterior.cu) on a sample of the same candidates: candidates/s
-    and the difference to the FP64 path's results on that sample.  Reported beside the headline, not as the headline:
-    its GEMM is a library kernel (CUTLASS int8, tcgen05 kind::i8); slicing and recombination are this repo's kernels."""
+def posterior_int8_sample(gp, xs, fp64_value, impl):
+    """The opt-in INT8 path on a sample of the same candidates: candidates/s and the difference to the FP64 path's results
+    on that sample.  Reported beside the headline, not as the headline (its error is ~1e-11 of max var against ~1e-14).
+    impl "fused": this repo's tcgen05 kernel (csrc/int8_fused.cu); "library": CUTLASS int8 GEMMs between this repo's
+    slicing and recombination kernels (csrc/int8_posterior.cu)."""
     mean0, var0 = gp.posterior(xs)
-    gp.int8 = True
+    gp.int8, gp.int8_impl = True, impl
+    gp._packed_i8 = None
     try:
         gp.posterior(xs[:65536])                                   # slices L^-1, allocates the workspace
         torch.cuda.synchronize()
@@ -291,15 +305,22 @@ def posterior_int8_sample(gp, xs, fp64_value):
     finally:
         gp.int8 = False
         gp._ws_i8 = None
+        gp._packed_i8 = None
     ms = e0.elapsed_time(e1)
     v = xs.shape[0] / (ms * 1e-3)
-    return {"value": v, "unit": "candidates/s", "sample_candidates": int(xs.shape[0]), "ms": ms,
+    notes = {"fused": "opt-in (ExactGPPosterior(int8=True) / MGB_POSTERIOR_PATH=int8): error-free 7-bit slicing of K* and L^-1; "
+                      "the 28 slice products, the float64 recombination and the sum of squares in ONE hand-written kernel "
+                      "(tcgen05.mma kind::i8, seven int32 planes of a 128 x 64 tile in tensor memory, operands pre-tiled "
+                      "in the tensor core's shared-memory image and staged by cp.async.bulk, exact triangular k range); "
+                      "parity bar 1e-10",
+             "library": "int8='library' / MGB_INT8_IMPL=library: the same slicing, 28 slice products as 7 x 5 int8 GEMMs "
+                        "(library kernel: CUTLASS collective builder, tcgen05 kind::i8) over column blocks of the "
+                        "triangular factor, float64 recombination pass over the int32 planes in HBM"}
+    return {"value": v, "unit": "candidates/s", "impl": impl, "sample_candidates": int(xs.shape[0]), "ms": ms,
             "ratio_to_fp64_path": v / fp64_value,
             "max_var_diff_rel_to_max_var": float((var1 - var0).abs().max() / var0.abs().max()),
             "max_mean_diff_rel_to_max_mean": float((mean1 - mean0).abs().max() / mean0.abs().max()),
-            "note": "opt-in (ExactGPPosterior(int8=True) / MGB_POSTERIOR_PATH=int8): error-free 7-bit slicing of K* and "
-                    "L^-1, 28 slice products as 7 x 5 int8 GEMMs (library kernel: CUTLASS collective builder, tcgen05 "
-                    "kind::i8) over column blocks of the triangular factor, float64 recombination; parity bar 1e-10"}
+            "note": notes[impl]}
 
 
 def posterior_roofline(gp, xc, n, lib):

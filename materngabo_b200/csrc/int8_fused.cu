@@ -143,19 +143,38 @@ __host__ __device__ constexpr uint32_t f8_idesc(int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(F8_BM >> 4) << 24);
 }
 
-__device__ __forceinline__ void f8_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// One lane of a converged warp (the issuing code stays warp-uniform, so the descriptors live in uniform registers).
+__device__ __forceinline__ bool f8_elect() {
+  uint32_t pred = 0;
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// Upper word of the shared-memory descriptor (constant), lower word = (address >> 4) | leading byte offset 1.
+constexpr uint32_t F8_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t f8_desc_from_lo(uint32_t lo) { return ((uint64_t)F8_DESC_HI << 32) | lo; }
+__device__ __forceinline__ uint32_t f8_desc_lo(uint32_t saddr) { return (saddr >> 4) | (1u << 16); }
+
+__device__ __forceinline__ void f8_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (f8_elect()) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 // mbarrier arrive once every tcgen05 operation issued so far by this thread has completed
 __device__ __forceinline__ void f8_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  if (f8_elect()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void f8_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void f8_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -201,7 +220,7 @@ struct F8Params {
   long long n_rb;            // row blocks
   long long items;           // work items incl. the padding of the last group
   int group;                 // row blocks per L2 group
-  int debug;                 // timing experiments (MGB_I8F_DEBUG): 1 = no copies, 2 = no MMAs (results are then garbage), 8 = k step outermost
+  int debug;                 // timing experiments (MGB_I8F_DEBUG): 1 = no copies, 2 = no MMAs (results are then garbage)
   F8Geom g;
 };
 
@@ -236,7 +255,7 @@ __global__ void __launch_bounds__(F8_THREADS, 1) f8_posterior_kernel(const F8Par
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;      // warp-uniform for the compiler
   if (threadIdx.x == 0) {
     for (int s = 0; s < F8_A_STAGES; ++s) {
       mbar_init(a_full + s, 1);
@@ -304,51 +323,43 @@ __global__ void __launch_bounds__(F8_THREADS, 1) f8_posterior_kernel(const F8Par
         const uint32_t bs = b_it % F8_B_STAGES, bph = (b_it / F8_B_STAGES) & 1u;
         f8_mbar_spin(b_full + bs, bph);
         const uint32_t b_addr = smem_u32(Bs + (size_t)bs * F8_S * F8_B_TILE);
+        // last k-block of an even column tile: columns [64 ct, 64 ct + 64) only meet k < 64 ct + 64, its first half
+        const int ks_end = (kb == nkb - 1 && (w.ct & 1) == 0) ? F8_BK / 64 : F8_BK / 32;
+        const uint32_t b_lo = f8_desc_lo(b_addr);
+        // Planes p .. 6 are adjacent in tensor memory and the B tiles of a k-block are adjacent in shared memory (same
+        // swizzle pattern, 64 rows each): the 7 - p slice products of A_p are ONE MMA with N = 64 (7 - p) against the
+        // stacked tiles B_0 .. B_{6-p}, split in two where N would exceed 256 - 10 MMAs per 32-byte k step instead of
+        // 28.  The whole warp runs this code (one elected lane issues): descriptors stay in uniform registers.
+#pragma unroll
         for (int p = 0; p < F8_S; ++p) {
           const uint32_t as = a_it % F8_A_STAGES, aph = (a_it / F8_A_STAGES) & 1u;
           f8_mbar_spin(a_full + as, aph);
           f8_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(As + (size_t)as * F8_A_TILE);
-            // Planes p .. 6 are adjacent in tensor memory and the B tiles of a k-block are adjacent in shared memory
-            // (same swizzle pattern, 64 rows each): the 7 - p slice products of A_p are ONE MMA with N = 64 (7 - p)
-            // against the stacked tiles B_0 .. B_{6-p}, split in two where N would exceed 256 (10 MMAs per 32-byte
-            // k step instead of 28: the int8 MMA has a fixed cost per instruction of about 64 cycles, measured).
-            const int n_all = (P.debug & 2) ? 0 : F8_BN * (F8_S - p);
-            const int n0 = min(n_all, 256), n1 = n_all - n0;
-            const uint32_t d0 = tmem_base + (uint32_t)(p * F8_BN);
-            if (P.debug & 8) {
+          const uint32_t a_lo = f8_desc_lo(smem_u32(As + (size_t)as * F8_A_TILE));
+          const int n_all = F8_BN * (F8_S - p);
+          const int n0 = n_all < 256 ? n_all : 256, n1 = n_all - n0;
+          const uint32_t d0 = tmem_base + (uint32_t)(p * F8_BN);
+          if (!(P.debug & 2)) {
+#pragma unroll
+            for (int ks = 0; ks < F8_BK / 32; ++ks) {
+              if (ks < ks_end) f8_mma(d0, f8_desc_from_lo(a_lo + 2 * ks), f8_desc_from_lo(b_lo + 2 * ks), f8_idesc(n0), (kb | p | ks) != 0 ? 1u : 0u);
+            }
+            if (n1 > 0) {
 #pragma unroll
               for (int ks = 0; ks < F8_BK / 32; ++ks) {
-                const uint32_t acc = (kb | p | ks) != 0 ? 1u : 0u;
-                const uint64_t ad = f8_smem_desc(a_addr + ks * 32);
-                if (n0 > 0) f8_mma(d0, ad, f8_smem_desc(b_addr + ks * 32), f8_idesc(n0), acc);
-                if (n1 > 0) f8_mma(d0 + 256u, ad, f8_smem_desc(b_addr + 4 * F8_B_TILE + ks * 32), f8_idesc(n1), acc);
-              }
-            } else {
-              if (n0 > 0) {
-#pragma unroll
-                for (int ks = 0; ks < F8_BK / 32; ++ks)
-                  f8_mma(d0, f8_smem_desc(a_addr + ks * 32), f8_smem_desc(b_addr + ks * 32), f8_idesc(n0), (kb | p | ks) != 0 ? 1u : 0u);
-              }
-              if (n1 > 0) {
-#pragma unroll
-                for (int ks = 0; ks < F8_BK / 32; ++ks)
-                  f8_mma(d0 + 256u, f8_smem_desc(a_addr + ks * 32), f8_smem_desc(b_addr + 4 * F8_B_TILE + ks * 32), f8_idesc(n1),
+                if (ks < ks_end)
+                  f8_mma(d0 + 256u, f8_desc_from_lo(a_lo + 2 * ks), f8_desc_from_lo(b_lo + (4 * F8_B_TILE >> 4) + 2 * ks), f8_idesc(n1),
                          (kb | p | ks) != 0 ? 1u : 0u);
               }
             }
-            f8_commit(a_empty + as);                      // slot free once these MMAs have read it
           }
-          __syncwarp();
+          f8_commit(a_empty + as);                        // slot free once these MMAs have read it
           ++a_it;
         }
-        if (lane == 0) f8_commit(b_empty + bs);
-        __syncwarp();
+        f8_commit(b_empty + bs);
         ++b_it;
       }
-      if (lane == 0) f8_commit(tmem_full);                // all seven planes of the tile are final
-      __syncwarp();
+      f8_commit(tmem_full);                               // all seven planes of the tile are final
       ++n_item;
     }
   } else {

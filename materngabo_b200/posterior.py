@@ -59,7 +59,8 @@ def _frozen_parameters(module):
             p.requires_grad_(True)
 
 
-INT8_CHUNK = 32768      # candidates per block of the INT8 path: 640 GEMM tiles per launch = 9 waves of 2-SM tile pairs
+INT8_CHUNK = 32768      # candidates per block of the library INT8 path: 640 GEMM tiles per launch = 9 waves of 2-SM tile pairs
+INT8_FUSED_CHUNK = 37888   # fused tcgen05 kernel: 296 row blocks of 128 = two per SM
 
 
 class ExactGPPosterior:
@@ -89,6 +90,11 @@ class ExactGPPosterior:
         # opt-in: the N^2 contraction on the INT8 tensor cores by error-free slicing (csrc/int8_posterior.cu; ~1e-11 of
         # max var instead of ~1e-14).  Default: the FP64 tensor-core kernel.  MGB_POSTERIOR_PATH=int8 turns it on globally.
         self.int8 = bool(int8) if int8 is not None else os.environ.get("MGB_POSTERIOR_PATH", "") == "int8"
+        # which INT8 implementation: "fused" = this repo's tcgen05 kernel (csrc/int8_fused.cu), "library" = CUTLASS int8
+        # GEMMs + recombination pass (csrc/int8_posterior.cu); int8="library" or MGB_INT8_IMPL=library selects the latter
+        self.int8_impl = int8 if isinstance(int8, str) else os.environ.get("MGB_INT8_IMPL", "fused")
+        if self.int8_impl not in ("fused", "library"):
+            raise ValueError("int8 implementation must be 'fused' or 'library', got %r" % (self.int8_impl,))
         self._packed = None
         self._packed_i8 = None
         self._ws = None
@@ -336,24 +342,37 @@ class ExactGPPosterior:
             raise RuntimeError("the INT8 path needs L^-1 of a local fit() or the sliced factor of a peer (load_state)")
         lib = _lib.load()
         n = self.rinv.shape[0]
-        self._packed_i8 = torch.empty(lib.mgb_posterior_int8_pack_bytes(n), dtype=torch.uint8, device=self.device)
+        pre = self._i8_prefix()
+        self._packed_i8 = torch.empty(getattr(lib, pre + "pack_bytes")(n), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(lib.mgb_posterior_int8_pack(_lib.ptr(self.rinv), n, self.rinv.stride(0), _lib.ptr(self._packed_i8),
-                                                   _lib.stream_ptr(self.device)), "mgb_posterior_int8_pack")
+            _lib.check(getattr(lib, pre + "pack")(_lib.ptr(self.rinv), n, self.rinv.stride(0), _lib.ptr(self._packed_i8),
+                                                  _lib.stream_ptr(self.device)), pre + "pack")
+
+    def _i8_prefix(self):
+        if self.int8_impl == "library":
+            if not _lib.load().mgb_int8_available():
+                raise _lib.MgbError("libmgb was built without the CUTLASS headers: the library INT8 path is not available")
+            return "mgb_posterior_int8_"
+        return "mgb_posterior_i8f_"
 
     def _posterior_int8(self, x, mean, var, chunk):
-        """Opt-in INT8 tensor-core path (csrc/int8_posterior.cu): row-major float64 kernel rows from the Gram kernel,
-        sliced into int8, seven int8 GEMMs against the sliced L^-1, recombined in float64.  ~1e-11 of max var."""
+        """Opt-in INT8 tensor-core path: row-major float64 kernel rows from the Gram kernel, cut into seven int8 slices,
+        slice products against the sliced L^-1 on the INT8 tensor cores, recombined in float64 (~1e-11 of max var).
+        int8_impl "fused": one hand-written tcgen05 kernel per block (csrc/int8_fused.cu); "library": seven CUTLASS GEMMs
+        per column block + a recombination pass (csrc/int8_posterior.cu)."""
         lib = _lib.load()
-        if not lib.mgb_int8_available():
-            raise _lib.MgbError("libmgb was built without the CUTLASS headers: the INT8 path is not available")
+        pre = self._i8_prefix()
         m, n = x.shape[0], self.train_prepared.shape[0]
         st = _lib.stream_ptr(self.device)
         self._ensure_packed_i8()
-        chunk = min(INT8_CHUNK, (m + 255) // 256 * 256)
-        need = lib.mgb_posterior_int8_workspace_bytes(chunk, n)
+        if self.int8_impl == "fused":
+            chunk = min(INT8_FUSED_CHUNK, (m + 127) // 128 * 128)
+        else:
+            chunk = min(INT8_CHUNK, (m + 255) // 256 * 256)
+        need = getattr(lib, pre + "workspace_bytes")(chunk, n)
         if self._ws_i8 is None or self._ws_i8.numel() < need:
             self._ws_i8 = torch.empty(need, dtype=torch.uint8, device=self.device)
+        reduce = getattr(lib, pre + "reduce")
         forward = None
         if not self.is_series:
             forward = self.kernel.forward
@@ -364,11 +383,10 @@ class ExactGPPosterior:
                     k = _ops.series_gram(self.spec, x[c0:c0 + mc], self.train_prepared, self.coef)   # carries the outputscale
                 else:
                     k = (self.outputscale * forward(x[c0:c0 + mc], self.train_prepared)).contiguous()
-                rc = lib.mgb_posterior_int8_reduce(_lib.ptr(k), mc, n, k.stride(0), _lib.ptr(self._packed_i8),
-                                                   _lib.ptr(self.alpha), float(self.kss_value), self.mean_const,
-                                                   _lib.ptr(mean[c0:]), _lib.ptr(var[c0:]), _lib.ptr(self._ws_i8),
-                                                   self._ws_i8.numel(), st)
-                _lib.check(rc, "mgb_posterior_int8_reduce")
+                rc = reduce(_lib.ptr(k), mc, n, k.stride(0), _lib.ptr(self._packed_i8), _lib.ptr(self.alpha),
+                            float(self.kss_value), self.mean_const, _lib.ptr(mean[c0:]), _lib.ptr(var[c0:]),
+                            _lib.ptr(self._ws_i8), self._ws_i8.numel(), st)
+                _lib.check(rc, pre + "reduce")
                 del k
         return mean, var
 

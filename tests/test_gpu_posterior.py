@@ -383,16 +383,29 @@ def test_baseline_train_size_chunk_consistency():
     assert torch.isfinite(mean).all() and (var > -1e-9).all() and (var <= 1.0 + 1e-9).all()
 
 
+INT8_IMPLS = ["fused", "library"]
+
+
+def _int8_or_skip(impl):
+    """"fused" (this repo's tcgen05 kernel) is always built; "library" needs the CUTLASS headers at build time."""
+    from materngabo_b200 import _lib
+
+    if impl == "library" and not _lib.load().mgb_int8_available():
+        pytest.skip("libmgb built without the CUTLASS headers")
+    return impl
+
+
+@pytest.mark.parametrize("impl", INT8_IMPLS)
 @pytest.mark.parametrize("n,m", [(300, 1000), (1000, 20000), (2100, 3001)])
-def test_int8_tensor_core_posterior_matches_the_fp64_path(n, m):
-    """Opt-in INT8 path (error-free 7-bit slicing, seven int8 GEMMs, float64 recombination) against the FP64
-    tensor-core kernel: variance to 1e-10 of max var (measured ~1e-11), mean to 1e-12 - including candidates 1e-3
-    away from training points, where the variance is a cancellation."""
-    from materngabo_b200 import _lib, kernels_sphere
+def test_int8_tensor_core_posterior_matches_the_fp64_path(n, m, impl):
+    """Opt-in INT8 path (error-free 7-bit slicing, 28 slice products on the INT8 tensor cores, float64 recombination;
+    "fused" = the hand-written tcgen05 kernel, "library" = CUTLASS GEMMs) against the FP64 tensor-core kernel: variance
+    to 1e-10 of max var (measured ~1e-11), mean to 1e-12 - including candidates 1e-3 away from training points, where
+    the variance is a cancellation."""
+    from materngabo_b200 import kernels_sphere
     from materngabo_b200.posterior import ExactGPPosterior
 
-    if not _lib.load().mgb_int8_available():
-        pytest.skip("libmgb built without the CUTLASS headers")
+    _int8_or_skip(impl)
     gen = torch.Generator().manual_seed(n)
     xt = torch.nn.functional.normalize(torch.randn(n, 11, generator=gen), dim=-1)
     xc = torch.nn.functional.normalize(torch.randn(m, 11, generator=gen), dim=-1)
@@ -403,7 +416,7 @@ def test_int8_tensor_core_posterior_matches_the_fp64_path(n, m):
     k.lengthscale = 0.5
     k = k.to(DEV)
     ref = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.3, noise=1e-2, mean_const=0.2).fit()
-    fast = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.3, noise=1e-2, mean_const=0.2, int8=True).fit()
+    fast = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.3, noise=1e-2, mean_const=0.2, int8=impl).fit()
     m0, v0 = ref.posterior(xc.to(DEV))
     m1, v1 = fast.posterior(xc.to(DEV))
     assert float((v1 - v0).abs().max() / v0.abs().max()) < 1e-10
@@ -411,13 +424,13 @@ def test_int8_tensor_core_posterior_matches_the_fp64_path(n, m):
     assert float(v0.min()) < 0.1 * float(v0.max())          # the near-training candidates are in the sample
 
 
-def test_int8_posterior_path_serves_the_quadrature_kernels_too():
+@pytest.mark.parametrize("impl", INT8_IMPLS)
+def test_int8_posterior_path_serves_the_quadrature_kernels_too(impl):
     """The INT8 contraction only needs the float64 kernel rows: a hyperbolic H^3 kernel through its own Gram kernel."""
-    from materngabo_b200 import _lib, kernels_hyperbolic as kh
+    from materngabo_b200 import kernels_hyperbolic as kh
     from materngabo_b200.posterior import ExactGPPosterior
 
-    if not _lib.load().mgb_int8_available():
-        pytest.skip("libmgb built without the CUTLASS headers")
+    _int8_or_skip(impl)
     gen = torch.Generator().manual_seed(7)
 
     def pts(k):
@@ -428,7 +441,7 @@ def test_int8_posterior_path_serves_the_quadrature_kernels_too():
     y = torch.sin(2 * xt[:, 1])
     k = kh.HyperbolicRiemannianMillsonIntegratedMaternKernel(dim=3, nu=2.5).to(DEV)
     ref = ExactGPPosterior(k, xt, y, outputscale=0.8, noise=1e-2).fit()
-    fast = ExactGPPosterior(k, xt, y, outputscale=0.8, noise=1e-2, int8=True).fit()
+    fast = ExactGPPosterior(k, xt, y, outputscale=0.8, noise=1e-2, int8=impl).fit()
     m0, v0 = ref.posterior(xc)
     m1, v1 = fast.posterior(xc)
     assert float((v1 - v0).abs().max() / v0.abs().max()) < 1e-10
@@ -438,14 +451,14 @@ def test_int8_posterior_path_serves_the_quadrature_kernels_too():
     assert me.numel() == 0 and ve.numel() == 0
 
 
-@pytest.mark.parametrize("int8", [False, True])
+@pytest.mark.parametrize("int8", [False, "fused", "library"])
 def test_posterior_host_matches_device_posterior(int8):
-    """Host-buffer call of the Python API (pinned candidates in, pinned mean / var out), both contraction paths."""
-    from materngabo_b200 import _lib, kernels_sphere
+    """Host-buffer call of the Python API (pinned candidates in, pinned mean / var out), all contraction paths."""
+    from materngabo_b200 import kernels_sphere
     from materngabo_b200.posterior import ExactGPPosterior
 
-    if int8 and not _lib.load().mgb_int8_available():
-        pytest.skip("libmgb built without the CUTLASS headers")
+    if int8:
+        _int8_or_skip(int8)
     gen = torch.Generator().manual_seed(3)
     xt = torch.nn.functional.normalize(torch.randn(400, 4, generator=gen), dim=-1)
     xc = torch.nn.functional.normalize(torch.randn(5000, 4, generator=gen), dim=-1)
@@ -532,17 +545,18 @@ def test_ragged_tail_block_generic_kernel_path():
     assert torch.isfinite(mean).all() and torch.isfinite(var).all()
 
 
+@pytest.mark.parametrize("impl", INT8_IMPLS)
 @pytest.mark.parametrize("noise", [1e-2, 1e-4, 1e-6])
-def test_int8_path_against_the_oracle_and_truth_at_the_headline_size(noise):
-    """The opt-in INT8 tensor-core contraction (library GEMM; slicing and recombination are this repo's kernels) against
-    the ORACLE and the long-double truth leg - not against the repo's own FP64 kernel - at n = 5000, incl. the
-    cancellation rows: 1e-10 of max|mean| / max var (measured ~2e-11 for the variance)."""
-    from materngabo_b200 import _lib, kernels_sphere
+def test_int8_path_against_the_oracle_and_truth_at_the_headline_size(noise, impl):
+    """The opt-in INT8 tensor-core contraction ("fused": the hand-written tcgen05 kernel; "library": CUTLASS GEMMs between
+    this repo's slicing and recombination kernels) against the ORACLE and the long-double truth leg - not against the
+    repo's own FP64 kernel - at n = 5000, incl. the cancellation rows: 1e-10 of max|mean| / max var (measured ~2e-11 for
+    the variance)."""
+    from materngabo_b200 import kernels_sphere
     from materngabo_b200.posterior import ExactGPPosterior
     from oracle import restated as R, truth
 
-    if not _lib.load().mgb_int8_available():
-        pytest.skip("libmgb built without the CUTLASS headers")
+    _int8_or_skip(impl)
     n, m, mt = 5000, 2048, 256
     gen = torch.Generator().manual_seed(6)
     xt = torch.nn.functional.normalize(torch.randn(n, 11, generator=gen), dim=-1)
@@ -552,7 +566,7 @@ def test_int8_path_against_the_oracle_and_truth_at_the_headline_size(noise):
     y = torch.sin(3.0 * xt[:, 0]) + 0.5 * xt[:, 1] * xt[:, 2]
     k = kernels_sphere.SphereRiemannianMaternKernel(dim=10, nu=2.5)
     k.lengthscale = 0.5
-    gp = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.0, noise=noise, int8=True).fit()
+    gp = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.0, noise=noise, int8=impl).fit()
     mg, vg = (t.cpu().numpy() for t in gp.posterior(xc.to(DEV)))
     kfn = lambda a, b: R.sphere_matern(a, b, 10, 2.5, 0.5)  # noqa: E731
     L, alpha = R.gp_fit(kfn, xt, y, 1.0, noise, 0.0)
@@ -564,3 +578,53 @@ def test_int8_path_against_the_oracle_and_truth_at_the_headline_size(noise):
     assert np.abs(vg - vo).max() <= 1e-10 * vscale
     assert np.abs(mg[sel] - mtr).max() <= 1e-10 * mscale
     assert np.abs(vg[sel] - vtr).max() <= 1e-10 * vscale
+
+
+@pytest.mark.parametrize("m,n", [(128, 64), (200, 300), (700, 1000), (300, 2100)])
+def test_fused_int8_kernel_accumulator_planes_are_exact(m, n):
+    """csrc/int8_fused.cu through the C-ABI debug entry point: the seven int32 planes C_d = sum_{p+q=d} A_p B_q^T that
+    the tcgen05 kernel leaves in tensor memory, against an int64 matmul of the same slices cut on the host - every entry
+    must be equal (integer arithmetic: bit-exact), for ragged m / n, the triangular k range and the padded rows."""
+    import numpy as np
+    from materngabo_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(m + n)
+    ks = ((torch.rand(m, n, generator=g, dtype=torch.float64) * 2 - 1) * torch.rand(m, 1, generator=g, dtype=torch.float64)).to(DEV)
+    rinv = (torch.tril(torch.randn(n, n, generator=g, dtype=torch.float64)) * 3.0).to(DEV)
+    alpha = torch.randn(n, generator=g, dtype=torch.float64).to(DEV)
+    pk = torch.empty(lib.mgb_posterior_i8f_pack_bytes(n), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(lib.mgb_posterior_i8f_workspace_bytes(m, n), dtype=torch.uint8, device=DEV)
+    planes = torch.zeros(lib.mgb_posterior_i8f_planes_bytes(m, n) // 4, dtype=torch.int32, device=DEV)
+    mean = torch.empty(m, dtype=torch.float64, device=DEV)
+    var = torch.empty(m, dtype=torch.float64, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.mgb_posterior_i8f_pack(rinv.data_ptr(), n, n, pk.data_ptr(), st), "pack")
+    _lib.check(lib.mgb_posterior_i8f_reduce_debug(ks.data_ptr(), m, n, n, pk.data_ptr(), alpha.data_ptr(), 2.5, 0.3, mean.data_ptr(),
+                                                  var.data_ptr(), ws.data_ptr(), ws.numel(), planes.data_ptr(), st), "reduce_debug")
+    torch.cuda.synchronize()
+
+    def slices(x):
+        mx = np.abs(x).max(axis=1)
+        e = np.zeros(x.shape[0], dtype=np.int64)
+        e[mx > 0] = np.frexp(mx[mx > 0])[1] + 1
+        r = np.ldexp(x, -e[:, None])
+        out = []
+        for _ in range(7):
+            t = r * 128.0
+            q = np.rint(t)
+            out.append(q.astype(np.int64))
+            r = t - q
+        return out
+
+    A, B = slices(ks.cpu().numpy()), slices(rinv.cpu().numpy())
+    n_rb, n_ct = (m + 127) // 128, (n + 63) // 64
+    got = planes.view(n_rb, n_ct, 7, 128, 64).cpu().numpy().astype(np.int64)
+    for d in range(7):
+        want = np.zeros((n_rb * 128, n_ct * 64), dtype=np.int64)
+        want[:m, :n] = sum(A[p] @ B[d - p].T for p in range(d + 1))
+        have = got[:, :, d].transpose(0, 2, 1, 3).reshape(n_rb * 128, n_ct * 64)
+        assert np.array_equal(have[:m], want[:m]), "plane %d" % d
+    v = ks @ rinv.T
+    assert float((var - (2.5 - (v * v).sum(-1))).abs().max()) < 1e-12 * float((v * v).sum(-1).max())
+    assert float((mean - (0.3 + ks @ alpha)).abs().max()) < 1e-12 * (1.0 + float((ks @ alpha).abs().max()))
