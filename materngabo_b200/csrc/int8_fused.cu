@@ -69,7 +69,10 @@ __device__ __forceinline__ int f8_swizzled(int r, int c16) { return (r >> 3) * 1
 // One warp per row: e = exponent with |row| 2^-e < 1/2, then S round-to-nearest slices of 7 bits, written into the
 // tiled operand image.  is_b = 0: K* rows (128-row tiles; also mean_i = mean_const + sum_j K*_ij alpha_j);
 // is_b = 1: rows of L^-1 (64-row tiles, lower triangle only, k-blocks beyond the tile's diagonal are never read).
-// Rows in [rows, rows_pad) are written as zeros.
+// Rows in [rows, rows_pad) are written as zeros.  Per iteration the warp takes 128 consecutive columns - lane l the four
+// columns 4 l .. 4 l + 3 (two 16-byte loads, 1 KB per warp) - and stores one 32-bit word per slice: the 32 words of a
+// warp are the 128 bytes of one (swizzled) tile row.  Rounding by the 1.5 * 2^52 trick: t = x + M is x rounded to an
+// integer in the low mantissa bits (|x| <= 64), t - M that integer as a double, x - (t - M) the exact remainder.
 __global__ void __launch_bounds__(256) f8_slice_kernel(const double* src, long long ld, long long rows, long long rows_pad, int cols,
                                                        F8Geom g, int is_b, signed char* dst, int* exps, double* scales,
                                                        const double* alpha, double mean_const, double* mean) {
@@ -79,6 +82,7 @@ __global__ void __launch_bounds__(256) f8_slice_kernel(const double* src, long l
   const bool valid = row < rows;
   const double* s = src + (valid ? row : 0) * ld;
   const int used = !valid ? 0 : (is_b ? (int)min((long long)cols, row + 1) : cols);
+  const bool vec = ((reinterpret_cast<uintptr_t>(s) & 15) == 0);      // 16-byte loads need an aligned row
   double mx = 0.0, mu = 0.0;
   if (alpha != nullptr) {
     for (int c = lane; c < used; c += 32) {
@@ -102,30 +106,38 @@ __global__ void __launch_bounds__(256) f8_slice_kernel(const double* src, long l
     if (exps != nullptr) exps[row] = e;
     if (scales != nullptr) scales[row] = ldexp(1.0, e);
   }
+  const double down = ldexp(1.0, -e);                // exact power of two
   const int tile_rows = is_b ? F8_BN : F8_BM;
   const long long tile_bytes = (long long)tile_rows * F8_BK;
   const long long rt = row / tile_rows;
   const int rr = (int)(row % tile_rows);
   const int kb_end = is_b ? min(g.KB, F8Geom::nkb((int)rt)) : g.KB;
-  signed char* base = dst + rt * g.KB * F8_S * tile_bytes;
-  for (long long c0 = 16 * lane; c0 < (long long)kb_end * F8_BK; c0 += 512) {
-    double r[16];
+  // this lane's word inside a tile row: 16-byte chunk lane / 4 (swizzled with the row), word lane % 4
+  signed char* base = dst + rt * g.KB * F8_S * tile_bytes + f8_swizzled(rr, lane >> 2) + ((lane & 3) << 2);
+  constexpr double kMagic = 6755399441055744.0;      // 1.5 * 2^52
+  for (int kb = 0; kb < kb_end; ++kb) {
+    const int c0 = kb * F8_BK + 4 * lane;
+    double r[4];
+    if (vec && c0 + 4 <= used) {
+      const double2 v0 = *reinterpret_cast<const double2*>(s + c0);
+      const double2 v1 = *reinterpret_cast<const double2*>(s + c0 + 2);
+      r[0] = v0.x * down; r[1] = v0.y * down; r[2] = v1.x * down; r[3] = v1.y * down;
+    } else {
 #pragma unroll
-    for (int t = 0; t < 16; ++t) r[t] = (c0 + t < used) ? ldexp(s[c0 + t], -e) : 0.0;
-    const int kb = (int)(c0 / F8_BK);
-    signed char* tile = base + (long long)kb * F8_S * tile_bytes + f8_swizzled(rr, (int)(c0 % F8_BK) >> 4);
-#pragma unroll 1
+      for (int t = 0; t < 4; ++t) r[t] = (c0 + t < used) ? s[c0 + t] * down : 0.0;
+    }
+    signed char* tile = base + (long long)kb * F8_S * tile_bytes;
+#pragma unroll
     for (int p = 0; p < F8_S; ++p) {
-      uint4 q;
-      signed char* qq = reinterpret_cast<signed char*>(&q);
+      unsigned word = 0;
 #pragma unroll
-      for (int t = 0; t < 16; ++t) {
+      for (int t = 0; t < 4; ++t) {
         const double x = r[t] * (double)(1 << F8_BITS);
-        const double qi = rint(x);
-        qq[t] = (signed char)(int)qi;
-        r[t] = x - qi;
+        const double tt = x + kMagic;
+        word |= ((unsigned)__double2loint(tt) & 0xffu) << (8 * t);
+        r[t] = x - (tt - kMagic);
       }
-      *reinterpret_cast<uint4*>(tile + p * tile_bytes) = q;
+      *reinterpret_cast<unsigned*>(tile + p * tile_bytes) = word;
     }
   }
 }
