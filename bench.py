@@ -384,12 +384,13 @@ def posterior_e2e(args, gp, rank, world, local, m_total, m_local, n, xc, dist):
     gpytorch keeps its prediction caches on the device between acq(X) calls - so each call moves candidates and results
     only."""
     device = torch.device("cuda", local)
-    if gp.int8:
+    if gp.int8 and gp.int8_impl != "fused":
         return posterior_e2e_int8(args, gp, rank, world, local, m_total, m_local, n, xc, dist)
     xc_h = xc.cpu().pin_memory()
     mean_h = torch.empty(m_local, dtype=F64).pin_memory()
     var_h = torch.empty(m_local, dtype=F64).pin_memory()
-    handle = gp.handle(gp.chunk)
+    handle = gp.handle(gp.chunk)          # INT8 mode (fused kernel) follows gp.int8: mgb_posterior_use_int8
+    via = "INT8 tensor-core contraction, csrc/int8_fused.cu" if handle.int8 else "FP64 DMMA kernel"
     steps = max(1, min(args.steps, 2))
     handle.eval_host(xc_h[: min(m_local, 4 * gp.chunk)].contiguous())       # warm-up
     if world > 1:
@@ -407,7 +408,7 @@ def posterior_e2e(args, gp, rank, world, local, m_total, m_local, n, xc, dist):
     return {"value": m_total / (dt / steps), "unit": "candidates/s", "h2d_bytes_per_step": 8 * m_local * 11,
             "d2h_bytes_per_step": 8 * 2 * m_local, "steps": steps,
             "api": "mgb_posterior_eval_host on a persistent handle (C-ABI, pinned host buffers, per rank; fitted state "
-                   "resident on the device)",
+                   "resident on the device; %s)" % via,
             "sample_mean0": float(mean_h[0]), "timer": "host wall clock around the synchronous C-ABI call, max over ranks"}
 
 

@@ -538,6 +538,13 @@ int mgb_posterior_create_from_device(const mgb_series_desc* desc, const double* 
                                      const double* coef_dev, const double* packed_dev, double kss_value,
                                      double mean_const, long long max_chunk, int device, mgb_posterior** out);
 long long mgb_posterior_chunk(const mgb_posterior* h);
+/* Opt-in INT8 tensor-core contraction for a handle (csrc/int8_fused.cu; ~1e-11 of max var instead of ~1e-14, ~2.5 x the
+ * candidates/s).  packed_i8_dev = the sliced factor written by mgb_posterior_i8f_pack, alpha_dev = n doubles; both on the
+ * handle's device, borrowed, and must outlive the handle (or the next call).  Both null = back to the FP64 kernel.
+ * A handle made by mgb_posterior_create with MGB_POSTERIOR_PATH=int8 in the environment slices its own copy of L^-1 and
+ * starts in this mode (the same switch as the Python host's ExactGPPosterior). */
+int mgb_posterior_use_int8(mgb_posterior* h, const void* packed_i8_dev, const double* alpha_dev);
+int mgb_posterior_is_int8(const mgb_posterior* h);
 int mgb_posterior_eval_host(mgb_posterior* h, const double* xc, long long m, double* mean, double* var);
 int mgb_posterior_eval_device(mgb_posterior* h, const double* xc_dev, long long m, long long ldc, double* mean_dev,
                               double* var_dev, void* stream);

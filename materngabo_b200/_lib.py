@@ -86,6 +86,8 @@ PROTOTYPES = {
     "mgb_posterior_int8_pack": (_I, [_P, _LL, _LL, _P, _P]),
     "mgb_posterior_int8_workspace_bytes": (_LL, [_LL, _LL]),
     "mgb_posterior_int8_reduce": (_I, [_P, _LL, _LL, _LL, _P, _P, _D, _D, _P, _P, _P, _LL, _P]),
+    "mgb_posterior_use_int8": (_I, [_P, _P, _P]),
+    "mgb_posterior_is_int8": (_I, [_P]),
     "mgb_posterior_i8f_pack_bytes": (_LL, [_LL]),
     "mgb_posterior_i8f_pack": (_I, [_P, _LL, _LL, _P, _P]),
     "mgb_posterior_i8f_workspace_bytes": (_LL, [_LL, _LL]),

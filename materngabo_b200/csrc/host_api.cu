@@ -3,6 +3,7 @@
 // device entry points as the torch-side bindings.  Candidate rows are double-buffered: the copy stream
 // uploads block b+1 and downloads results of block b-1 while the compute stream works on block b.
 #include "mgb_common.cuh"
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -177,6 +178,13 @@ struct mgb_posterior {
   long long stage_rows = 0;
   cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
   cudaEvent_t up[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, down[2] = {nullptr, nullptr};
+  // opt-in INT8 tensor-core contraction (csrc/int8_fused.cu): sliced L^-1, alpha, a row-major kernel-row block, workspace
+  bool int8 = false, owns_i8 = false;
+  void* d_pack8 = nullptr;
+  double* d_alpha = nullptr;
+  double* d_krows = nullptr;
+  void* d_ws8 = nullptr;
+  long long ws8_bytes = 0;
 };
 
 namespace mgb {
@@ -201,6 +209,12 @@ static void posterior_release(mgb_posterior* h) {
     if (h->down[b]) cudaEventDestroy(h->down[b]);
   }
   cudaFree(h->d_ws);
+  if (h->owns_i8) {
+    cudaFree(h->d_pack8);
+    cudaFree(h->d_alpha);
+  }
+  cudaFree(h->d_krows);
+  cudaFree(h->d_ws8);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->compute) cudaStreamDestroy(h->compute);
   if (h->h2d) cudaStreamDestroy(h->h2d);
@@ -234,6 +248,36 @@ static int posterior_common_init(mgb_posterior* h, long long max_chunk) {
   MGB_TRY(check_cuda(cudaStreamCreateWithFlags(&h->h2d, cudaStreamNonBlocking), "cudaStreamCreate"));
   return check_cuda(cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking), "cudaStreamCreate");
 }
+// INT8 mode of a handle: buffers for one block of kernel rows (row-major float64) and the fused kernel's workspace.
+static int posterior_int8_buffers(mgb_posterior* h) {
+  if (h->n > 32768) return fail(MGB_ERR_ARG, "posterior handle: the INT8 path needs n <= 32768");
+  if (!h->d_krows) MGB_TRY(dev_alloc(&h->d_krows, (size_t)(h->chunk * h->n)));
+  if (!h->d_ws8) {
+    h->ws8_bytes = mgb_posterior_i8f_workspace_bytes(h->chunk, h->n);
+    MGB_TRY(check_cuda(cudaMalloc(&h->d_ws8, (size_t)h->ws8_bytes), "cudaMalloc"));
+  }
+  return MGB_OK;
+}
+
+// mean / var of up to `chunk`-sized blocks of candidate rows already on the device, on `stream`
+static int posterior_eval_rows(mgb_posterior* h, const double* xc_dev, long long m, long long ldc, double* mean_dev, double* var_dev,
+                               long long chunk, void* stream) {
+  if (!h->int8)
+    return mgb_series_posterior(&h->desc, xc_dev, m, ldc, h->d_xt, h->n, h->ldt, h->d_coef, h->d_pack, h->kss, h->mean_const,
+                                mean_dev, var_dev, h->d_ws, h->ws_bytes, chunk, stream);
+  for (long long c0 = 0; c0 < m; c0 += h->chunk) {
+    const long long rows = m - c0 < h->chunk ? m - c0 : h->chunk;
+    MGB_TRY(mgb_series_gram_fwd(&h->desc, xc_dev + c0 * ldc, rows, ldc, h->d_xt, h->n, h->ldt, h->d_coef, h->d_krows, h->n, stream));
+    MGB_TRY(mgb_posterior_i8f_reduce(h->d_krows, rows, h->n, h->n, h->d_pack8, h->d_alpha, h->kss, h->mean_const, mean_dev + c0,
+                                     var_dev + c0, h->d_ws8, h->ws8_bytes, stream));
+  }
+  return MGB_OK;
+}
+
+static bool env_int8() {
+  const char* e = std::getenv("MGB_POSTERIOR_PATH");
+  return e && std::strcmp(e, "int8") == 0;
+}
 }  // namespace mgb
 
 extern "C" int mgb_posterior_create(const mgb_series_desc* desc, const double* xtrain, long long n, const double* coef,
@@ -264,6 +308,16 @@ extern "C" int mgb_posterior_create(const mgb_series_desc* desc, const double* x
     if ((rc = check_cuda(cudaMemcpyAsync(d_R, Rinv, sizeof(double) * n * n, cudaMemcpyHostToDevice, s), "H2D Rinv")) != MGB_OK) break;
     if ((rc = check_cuda(cudaMemcpyAsync(d_alpha, alpha, sizeof(double) * n, cudaMemcpyHostToDevice, s), "H2D alpha")) != MGB_OK) break;
     if ((rc = mgb_posterior_pack(d_R, n, n, d_alpha, h->d_pack, s)) != MGB_OK) break;
+    if (env_int8()) {
+      // MGB_POSTERIOR_PATH=int8: the handle also keeps the sliced factor and alpha and evaluates through int8_fused.cu
+      if ((rc = check_cuda(cudaMalloc(&h->d_pack8, (size_t)mgb_posterior_i8f_pack_bytes(n)), "cudaMalloc")) != MGB_OK) break;
+      h->owns_i8 = true;
+      if ((rc = mgb_posterior_i8f_pack(d_R, n, n, h->d_pack8, s)) != MGB_OK) break;
+      h->d_alpha = d_alpha;
+      d_alpha = nullptr;
+      if ((rc = posterior_int8_buffers(h)) != MGB_OK) break;
+      h->int8 = true;
+    }
     rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");
   } while (0);
   cudaFree(d_R);
@@ -309,14 +363,38 @@ extern "C" int mgb_posterior_destroy(mgb_posterior* h) {
 
 extern "C" long long mgb_posterior_chunk(const mgb_posterior* h) { return h ? h->chunk : 0; }
 
+extern "C" int mgb_posterior_use_int8(mgb_posterior* h, const void* packed_i8_dev, const double* alpha_dev) {
+  if (!h) return fail(MGB_ERR_ARG, "posterior_use_int8: null handle");
+  if (!packed_i8_dev && !alpha_dev) {      // back to the FP64 kernel
+    h->int8 = false;
+    return MGB_OK;
+  }
+  if (!packed_i8_dev || !alpha_dev) return fail(MGB_ERR_ARG, "posterior_use_int8: both the sliced factor and alpha are needed");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  MGB_TRY(check_cuda(cudaSetDevice(h->device), "cudaSetDevice"));
+  struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
+  if (h->owns_i8) {
+    cudaFree(h->d_pack8);
+    cudaFree(h->d_alpha);
+    h->owns_i8 = false;
+  }
+  h->d_pack8 = const_cast<void*>(packed_i8_dev);
+  h->d_alpha = const_cast<double*>(alpha_dev);
+  MGB_TRY(posterior_int8_buffers(h));
+  h->int8 = true;
+  return MGB_OK;
+}
+
+extern "C" int mgb_posterior_is_int8(const mgb_posterior* h) { return h && h->int8 ? 1 : 0; }
+
 extern "C" int mgb_posterior_eval_device(mgb_posterior* h, const double* xc_dev, long long m, long long ldc,
                                          double* mean_dev, double* var_dev, void* stream) {
   if (!h || m < 0) return fail(MGB_ERR_ARG, "posterior_eval_device: bad argument");
   if (m == 0) return MGB_OK;
   if (!xc_dev || !mean_dev || !var_dev || ldc < h->D) return fail(MGB_ERR_ARG, "posterior_eval_device: null pointer / bad ldc");
   const long long chunk = m < h->chunk ? (m + 127) / 128 * 128 : h->chunk;
-  return mgb_series_posterior(&h->desc, xc_dev, m, ldc, h->d_xt, h->n, h->ldt, h->d_coef, h->d_pack, h->kss, h->mean_const,
-                              mean_dev, var_dev, h->d_ws, h->ws_bytes, chunk, stream);
+  return posterior_eval_rows(h, xc_dev, m, ldc, mean_dev, var_dev, chunk, stream);
 }
 
 extern "C" int mgb_posterior_eval_host(mgb_posterior* h, const double* xc, long long m, double* mean, double* var) {
@@ -360,8 +438,7 @@ extern "C" int mgb_posterior_eval_host(mgb_posterior* h, const double* xc, long 
     const int buf = (int)(blk & 1);
     MGB_TRY(check_cuda(cudaStreamWaitEvent(h->compute, h->up[buf], 0), "cudaStreamWaitEvent"));
     if (blk >= 2) MGB_TRY(check_cuda(cudaStreamWaitEvent(h->compute, h->down[buf], 0), "cudaStreamWaitEvent"));  // results of blk-2 left
-    MGB_TRY(mgb_series_posterior(&h->desc, h->d_xc[buf], rows, D, h->d_xt, h->n, h->ldt, h->d_coef, h->d_pack, h->kss,
-                                 h->mean_const, h->d_out[buf], h->d_out[buf] + chunk, h->d_ws, h->ws_bytes, chunk, h->compute));
+    MGB_TRY(posterior_eval_rows(h, h->d_xc[buf], rows, D, h->d_out[buf], h->d_out[buf] + chunk, chunk, h->compute));
     MGB_TRY(check_cuda(cudaEventRecord(h->done[buf], h->compute), "cudaEventRecord"));
     if (blk + 1 < nblk) MGB_TRY(upload(blk + 1));
     MGB_TRY(check_cuda(cudaStreamWaitEvent(h->d2h, h->done[buf], 0), "cudaStreamWaitEvent"));

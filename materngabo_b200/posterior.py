@@ -603,6 +603,14 @@ class PosteriorHandle:
                                                   float(gp.mean_const), int(max_chunk), int(index), C.byref(h))
         _lib.check(rc, "mgb_posterior_create_from_device")
         self._h = h
+        self.int8 = False
+        if gp.int8 and gp.int8_impl == "fused":
+            # the handle evaluates through csrc/int8_fused.cu as well: it borrows the sliced factor and alpha
+            gp._ensure_packed_i8()
+            torch.cuda.current_stream(gp.device).synchronize()
+            self._keep = self._keep + (gp._packed_i8, gp.alpha)
+            _lib.check(lib.mgb_posterior_use_int8(h, _lib.ptr(gp._packed_i8), _lib.ptr(gp.alpha)), "mgb_posterior_use_int8")
+            self.int8 = True
 
     @property
     def chunk(self) -> int:

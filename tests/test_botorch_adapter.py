@@ -197,3 +197,60 @@ def test_persistent_handle_create_eval_many_destroy():
     assert lib.mgb_posterior_destroy(hp) == 0
     assert lib.mgb_posterior_destroy(None) == 0
     assert lib.mgb_posterior_eval_host(None, xq.ctypes.data, 300, mo.ctypes.data, vo.ctypes.data) == 1
+
+
+@pytest.mark.gpu
+def test_persistent_handle_in_int8_mode(monkeypatch):
+    """The handle's opt-in INT8 contraction (mgb_posterior_use_int8 -> csrc/int8_fused.cu): same answers as the Python
+    host's INT8 path bit for bit, 1e-10 of max var from the FP64 kernel and from the oracle; switchable back; and the
+    host-state constructor picks it up from MGB_POSTERIOR_PATH=int8."""
+    import ctypes as C
+
+    from materngabo_b200 import _lib
+    from materngabo_b200.posterior import ExactGPPosterior
+    from oracle import restated as R
+
+    dev = "cuda:0"
+    model, x, y = _model(dev, n=300, seed=9)
+    gen = torch.Generator().manual_seed(5)
+    xc = torch.nn.functional.normalize(torch.randn(9000, 4, generator=gen), dim=-1)
+    xc[:200] = torch.nn.functional.normalize(x[:200].cpu() + 1e-3 * torch.randn(200, 4, generator=gen), dim=-1)
+    ref = ExactGPPosterior.from_model(model)
+    m64, v64 = (t.cpu() for t in ref.posterior(xc.to(dev)))
+    gp = ExactGPPosterior.from_model(model, int8=True)
+    assert gp.int8 and gp.int8_impl == "fused"
+    m8, v8 = (t.cpu() for t in gp.posterior(xc.to(dev)))
+    vmax, mmax = float(v64.abs().max()), float(m64.abs().max())
+    assert float((v8 - v64).abs().max()) < 1e-10 * vmax and float((m8 - m64).abs().max()) < 1e-12 * mmax
+    kfn = lambda a, b: R.sphere_matern(a, b, 3, 2.5, 0.6)  # noqa: E731
+    mr, vr = R.gp_posterior(kfn, x.cpu(), y.cpu(), xc[:400], 1.7, 0.02, 0.3)
+    assert float((v8[:400] - vr).abs().max()) < 1e-10 * float(vr.abs().max())
+    assert float((m8[:400] - mr).abs().max()) < 1e-10 * float(mr.abs().max())
+    lib = _lib.load()
+    with gp.handle(max_chunk=4096) as h:
+        assert h.int8 and lib.mgb_posterior_is_int8(h._h) == 1
+        mh, vh = h.eval_host(xc[:137].contiguous())                      # latency path
+        assert float((vh - v64[:137]).abs().max()) < 1e-10 * vmax and float((mh - m64[:137]).abs().max()) < 1e-12 * mmax
+        mh, vh = h.eval_host(xc.pin_memory())                            # throughput path, ragged tail
+        assert float((vh - v64).abs().max()) < 1e-10 * vmax and float((mh - m64).abs().max()) < 1e-12 * mmax
+        assert lib.mgb_posterior_use_int8(h._h, None, None) == 0         # back to the FP64 kernel
+        assert lib.mgb_posterior_is_int8(h._h) == 0
+        mh, vh = h.eval_host(xc[:500].contiguous())
+        assert _same(mh, m64[:500]) and _same(vh, v64[:500])
+    # host-state constructor under MGB_POSTERIOR_PATH=int8
+    monkeypatch.setenv("MGB_POSTERIOR_PATH", "int8")
+    d = ref.spec.desc(ref.coef.shape[-1])
+    xt_h = np.ascontiguousarray(ref.train_prepared.cpu().numpy())
+    coef_h = np.ascontiguousarray(ref.coef.cpu().numpy())
+    rinv_h = np.ascontiguousarray(ref.rinv.cpu().numpy())
+    alpha_h = np.ascontiguousarray(ref.alpha.cpu().numpy())
+    hp = C.c_void_p()
+    rc = lib.mgb_posterior_create(C.byref(d), xt_h.ctypes.data, 300, coef_h.ctypes.data, rinv_h.ctypes.data, alpha_h.ctypes.data,
+                                  float(ref.kss_value), float(ref.mean_const), 2048, 0, C.byref(hp))
+    assert rc == 0, lib.mgb_last_error()
+    assert lib.mgb_posterior_is_int8(hp) == 1
+    xq = np.ascontiguousarray(xc[:3000].numpy())
+    mo, vo = np.empty(3000), np.empty(3000)
+    assert lib.mgb_posterior_eval_host(hp, xq.ctypes.data, 3000, mo.ctypes.data, vo.ctypes.data) == 0
+    assert np.abs(vo - v64[:3000].numpy()).max() < 1e-10 * vmax and np.abs(mo - m64[:3000].numpy()).max() < 1e-12 * mmax
+    assert lib.mgb_posterior_destroy(hp) == 0
