@@ -84,5 +84,5 @@ for name, base, x in cases:
     c = collections.Counter()
     for e in evs:
         c[e.name[:70]] += getattr(e, "device_time", 0)
-    for k, v in c.most_common(5):
+    for k, v in c.most_common(8):
         print("      %7.1f us  %s" % (v, k))
