@@ -290,6 +290,12 @@ _TRUNC = 1e-16      # dropped tail: sum |c_n| below this fraction of sum |c| (|T
 
 
 def _truncate(c: torch.Tensor) -> int:
+    """Terms to keep: the tail sum below _TRUNC of the total is dropped.  Device coefficients (mgb_circle_coef) arrive
+    with that rule already applied - their negligible tail is written as exact zeros by the kernel - so only the last
+    non-zero is looked up."""
+    if c.is_cuda:
+        nz = torch.nonzero(c.detach() != 0)
+        return max(int(nz.max().item()) + 1 if nz.numel() else 0, 2)
     mag = c.detach().abs().cpu()
     tail = torch.flip(torch.cumsum(torch.flip(mag, [0]), 0), [0])     # tail[k] = sum_{n >= k} |c_n|
     keep = int(torch.nonzero(tail > _TRUNC * tail[0]).max().item()) + 1

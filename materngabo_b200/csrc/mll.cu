@@ -512,11 +512,23 @@ __global__ void __launch_bounds__(CC_THREADS) circle_coef_kernel(CircleCoefParam
     red[tid] = acc;
   }
   __syncthreads();
+  // Device-side truncation (the host rule of _weights._truncate without its read-back): coefficients whose tail sum
+  // sum_{n >= k} |c_n| is not above 1e-16 of the total are written as exact zeros - |T_n| <= 1, so the kernel value moves
+  // by less than one ulp - and the Gram kernels skip trailing zeros (series_gram.cu: effective_terms).  Every thread sums
+  // its own tail from the far end (the order of the host's flipped cumsum).
+  const double S = red[0], c = v / S;
+  __syncthreads();                       // a[] is read above by the three summing threads
+  a[tid] = (tid < p.T) ? fabs(c) : 0.0;
+  __syncthreads();
+  double tail = 0.0;
+  for (int n = p.T - 1; n >= tid; --n) tail += a[n];
+  if (tid == 0) red[0] = tail;
+  __syncthreads();
   if (tid < p.T) {
-    const double S = red[0], c = v / S;
-    p.coef[tid] = c;
-    p.jac[tid] = (vk - c * red[1]) / S;
-    p.jac[p.T + tid] = (vn - c * red[2]) / S;
+    const bool live = tid < 2 || tail > 1e-16 * red[0];
+    p.coef[tid] = live ? c : 0.0;
+    p.jac[tid] = live ? (vk - c * red[1]) / S : 0.0;
+    p.jac[p.T + tid] = live ? (vn - c * red[2]) / S : 0.0;
   }
 }
 

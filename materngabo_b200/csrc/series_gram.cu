@@ -739,6 +739,24 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_warp(SeriesParams
   }
 }
 
+// Terms worth evaluating: trailing exact zeros of every factor's coefficient row are skipped (circle_coef_kernel writes
+// the negligible tail of a torus factor as zeros on the device, so a CUDA-graph-captured fit needs no host read to
+// truncate).  Warp-uniform; call with all lanes converged after the coefficients are in shared memory.
+__device__ __forceinline__ int effective_terms(const double* cfs, int F, int T) {
+  const int lane = threadIdx.x & 31;
+  int te = 1;
+  for (int f = 0; f < F; ++f) {
+    int last = 0;
+    for (int k0 = 0; k0 < T; k0 += 32) {
+      const int k = k0 + lane;
+      const unsigned b = __ballot_sync(0xffffffffu, k < T && cfs[f * T + k] != 0.0);
+      if (b) last = k0 + 31 - __clz(b);
+    }
+    te = max(te, last + 1);
+  }
+  return te;
+}
+
 // ---------------------------------------------------------------------------------------------
 // General path: F factors of runtime width W, T terms per factor, either basis; coefficients and the
 // transposed x2 panel in shared memory.  Each thread evaluates 2 columns x 2 rows per coefficient read.
@@ -809,6 +827,7 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_general(SeriesPar
     fence_mbar_init();
   }
   __syncthreads();
+  const int te = effective_terms(cfs, p.F, p.T);
 
   const long long col = cc * kTN + 2 * lane;
   const bool vec_ok = (col + 1 < p.n) && (p.tiled || (((p.ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.K) & 15u) == 0)));
@@ -858,7 +877,7 @@ __global__ void __launch_bounds__(kThreads, 2) series_gram_fwd_general(SeriesPar
 #pragma unroll
           for (int q = 0; q < NE; ++q) u[q] = clamp_exact(u[q], p.lo, p.hi);
         }
-        eval_n<BASIS, NE>(cfs + f * p.T, p.T, u, s);
+        eval_n<BASIS, NE>(cfs + f * p.T, te, u, s);
 #pragma unroll
         for (int q = 0; q < NE; ++q) prod[q] *= s[q];
       }
@@ -901,8 +920,131 @@ struct SeriesBwdParams {
 constexpr int kBwdThreads = 128;
 constexpr int kBwdMaxW = 32;
 
-// grid = (row groups, factors).  Block (g, f): warp w handles row i = 4g + w for factor f.
+// One row i of factor f against all columns, TACC coefficient accumulators in registers (te <= TACC terms are live).
 template <int TACC>
+__device__ __forceinline__ void series_bwd_row(const SeriesBwdParams& p, int te, const double* cfs, double* gc_blk, const double* xi,
+                                               long long i, int f) {
+  const int D = p.F * p.W;
+  const int lane = threadIdx.x & 31;
+  double acc[TACC];
+#pragma unroll
+  for (int k = 0; k < TACC; ++k) acc[k] = 0.0;
+  double gx[kBwdMaxW];
+#pragma unroll
+  for (int k = 0; k < kBwdMaxW; ++k) gx[k] = 0.0;
+  const bool want_coef = (p.gcoef != nullptr) && (p.order == 1);
+  const double* cf = cfs + f * p.T;
+
+  for (long long j0 = 0; j0 < p.nb; j0 += 32) {
+    const long long j = j0 + lane;
+    const bool valid = j < p.nb;
+    const long long jj = valid ? j : 0;
+    double go = valid ? p.G[i * p.gs_row + jj * p.gs_col] : 0.0;
+    const double* xj = p.xb + jj * p.ldb;
+    // product of the other factors' values
+    for (int h = 0; h < p.F; ++h) {
+      if (h == f) continue;
+      double dot = 0.0;
+      for (int k = 0; k < p.W; ++k) dot = fma(xi[h * p.W + k], xj[h * p.W + k], dot);
+      const double u = fmin(fmax(fma(dot, p.scale, p.shift), p.lo), p.hi);
+      const double* ch = cfs + h * p.T;
+      double s;
+      if (p.basis == MGB_BASIS_MONOMIAL) {
+        s = ch[te - 1];
+        for (int k = te - 2; k >= 0; --k) s = fma(s, u, ch[k]);
+      } else {
+        double t0 = 1.0, t1 = u;
+        s = ch[0] + ((te > 1) ? ch[1] * u : 0.0);
+        for (int k = 2; k < te; ++k) {
+          const double t2 = fma(2.0 * u, t1, -t0);
+          s = fma(ch[k], t2, s);
+          t0 = t1;
+          t1 = t2;
+        }
+      }
+      go *= s;
+    }
+    // this factor: basis values (for gcoef) and the order-th derivative (for gx)
+    double dot = 0.0;
+    for (int k = 0; k < p.W; ++k) dot = fma(xi[f * p.W + k], xj[f * p.W + k], dot);
+    const double raw = fma(dot, p.scale, p.shift);
+    const double u = fmin(fmax(raw, p.lo), p.hi);
+    const bool inside = (raw >= p.lo) && (raw <= p.hi);  // torch.clamp passes gradient on the boundary
+    double d1 = 0.0, d2 = 0.0;
+    if (p.basis == MGB_BASIS_MONOMIAL) {
+      double pw = 1.0, pw1 = 0.0, pw2 = 0.0;  // u^k, u^(k-1), u^(k-2)
+#pragma unroll
+      for (int k = 0; k < TACC; ++k) {
+        if (k < te) {
+          if (want_coef) acc[k] = fma(go, pw, acc[k]);
+          d1 = fma((double)k * cf[k], pw1, d1);
+          d2 = fma((double)(k * (k - 1)) * cf[k], pw2, d2);
+          pw2 = pw1;
+          pw1 = pw;
+          pw *= u;
+          if (k == 0) pw1 = 1.0;
+          if (k == 1) pw2 = 1.0;
+        }
+      }
+    } else {
+      double t0 = 1.0, t1 = u, a0 = 0.0, a1 = 1.0, b0 = 0.0, b1 = 0.0;
+      if (want_coef) {
+        acc[0] += go;
+        if (te > 1) acc[1] = fma(go, u, acc[1]);
+      }
+      d1 = (te > 1) ? cf[1] : 0.0;
+#pragma unroll
+      for (int k = 2; k < TACC; ++k) {
+        if (k < te) {
+          const double t2 = fma(2.0 * u, t1, -t0);
+          const double a2 = fma(2.0 * u, a1, 2.0 * t1 - a0);
+          const double b2 = fma(2.0 * u, b1, 4.0 * a1 - b0);
+          if (want_coef) acc[k] = fma(go, t2, acc[k]);
+          d1 = fma(cf[k], a2, d1);
+          d2 = fma(cf[k], b2, d2);
+          t0 = t1; t1 = t2; a0 = a1; a1 = a2; b0 = b1; b1 = b2;
+        }
+      }
+    }
+    if (p.gxa != nullptr && inside) {
+      const double w = go * ((p.order == 1) ? d1 * p.scale : d2 * p.scale * p.scale);
+#pragma unroll
+      for (int k = 0; k < kBwdMaxW; ++k)
+        if (k < p.W) gx[k] = fma(w, xj[f * p.W + k], gx[k]);
+    }
+  }
+  if (want_coef) {
+#pragma unroll
+    for (int k = 0; k < TACC; ++k) {
+      if (k < te) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) atomicAdd(gc_blk + k, v);
+      }
+    }
+  }
+  if (p.gxa != nullptr) {
+#pragma unroll
+    for (int k = 0; k < kBwdMaxW; ++k) {
+      if (k < p.W) {
+        const double v = warp_sum(gx[k]);
+        if (lane == 0) p.gxa[i * D + f * p.W + k] = v;
+      }
+    }
+  }
+}
+
+// The untruncated case (more than 64 live terms: accumulators in local memory) as a call, so that its stack frame does not
+// shape the register allocation of the common paths.
+template <int TACC>
+__device__ __noinline__ void series_bwd_row_big(const SeriesBwdParams& p, int te, const double* cfs, double* gc_blk, const double* xi,
+                                                long long i, int f) {
+  series_bwd_row<TACC>(p, te, cfs, gc_blk, xi, i, f);
+}
+
+// grid = (row groups, factors).  Block (g, f): warp w handles row i = 4g + w for factor f.  TMAX bounds the host's
+// n_terms; the live term count (trailing zero coefficients skipped) picks the accumulator count at run time, so a
+// truncated 201-term torus factor runs with 64 register accumulators instead of 256 spilled ones.
+template <int TMAX>
 __global__ void __launch_bounds__(kBwdThreads) series_gram_bwd_kernel(SeriesBwdParams p) {
   extern __shared__ double sm[];
   const int D = p.F * p.W;
@@ -919,116 +1061,14 @@ __global__ void __launch_bounds__(kBwdThreads) series_gram_bwd_kernel(SeriesBwdP
   if (row_ok)
     for (int k = lane; k < D; k += 32) xi[k] = p.xa[i * p.lda + k];
   __syncthreads();
-
-  double acc[TACC];
-#pragma unroll
-  for (int k = 0; k < TACC; ++k) acc[k] = 0.0;
-  double gx[kBwdMaxW];
-#pragma unroll
-  for (int k = 0; k < kBwdMaxW; ++k) gx[k] = 0.0;
-  const bool want_coef = (p.gcoef != nullptr) && (p.order == 1);
-  const double* cf = cfs + f * p.T;
-
+  const int te = effective_terms(cfs, p.F, p.T);
   if (row_ok) {
-    for (long long j0 = 0; j0 < p.nb; j0 += 32) {
-      const long long j = j0 + lane;
-      const bool valid = j < p.nb;
-      const long long jj = valid ? j : 0;
-      double go = valid ? p.G[i * p.gs_row + jj * p.gs_col] : 0.0;
-      const double* xj = p.xb + jj * p.ldb;
-      // product of the other factors' values
-      for (int h = 0; h < p.F; ++h) {
-        if (h == f) continue;
-        double dot = 0.0;
-        for (int k = 0; k < p.W; ++k) dot = fma(xi[h * p.W + k], xj[h * p.W + k], dot);
-        const double u = fmin(fmax(fma(dot, p.scale, p.shift), p.lo), p.hi);
-        const double* ch = cfs + h * p.T;
-        double s;
-        if (p.basis == MGB_BASIS_MONOMIAL) {
-          s = ch[p.T - 1];
-          for (int k = p.T - 2; k >= 0; --k) s = fma(s, u, ch[k]);
-        } else {
-          double t0 = 1.0, t1 = u;
-          s = ch[0] + ((p.T > 1) ? ch[1] * u : 0.0);
-          for (int k = 2; k < p.T; ++k) {
-            const double t2 = fma(2.0 * u, t1, -t0);
-            s = fma(ch[k], t2, s);
-            t0 = t1;
-            t1 = t2;
-          }
-        }
-        go *= s;
-      }
-      // this factor: basis values (for gcoef) and the order-th derivative (for gx)
-      double dot = 0.0;
-      for (int k = 0; k < p.W; ++k) dot = fma(xi[f * p.W + k], xj[f * p.W + k], dot);
-      const double raw = fma(dot, p.scale, p.shift);
-      const double u = fmin(fmax(raw, p.lo), p.hi);
-      const bool inside = (raw >= p.lo) && (raw <= p.hi);  // torch.clamp passes gradient on the boundary
-      double d1 = 0.0, d2 = 0.0;
-      if (p.basis == MGB_BASIS_MONOMIAL) {
-        double pw = 1.0, pw1 = 0.0, pw2 = 0.0;  // u^k, u^(k-1), u^(k-2)
-#pragma unroll
-        for (int k = 0; k < TACC; ++k) {
-          if (k < p.T) {
-            if (want_coef) acc[k] = fma(go, pw, acc[k]);
-            d1 = fma((double)k * cf[k], pw1, d1);
-            d2 = fma((double)(k * (k - 1)) * cf[k], pw2, d2);
-            pw2 = pw1;
-            pw1 = pw;
-            pw *= u;
-            if (k == 0) pw1 = 1.0;
-            if (k == 1) pw2 = 1.0;
-          }
-        }
-      } else {
-        double t0 = 1.0, t1 = u, a0 = 0.0, a1 = 1.0, b0 = 0.0, b1 = 0.0;
-        if (want_coef) {
-          acc[0] += go;
-          if (p.T > 1) acc[1] = fma(go, u, acc[1]);
-        }
-        d1 = (p.T > 1) ? cf[1] : 0.0;
-#pragma unroll
-        for (int k = 2; k < TACC; ++k) {
-          if (k < p.T) {
-            const double t2 = fma(2.0 * u, t1, -t0);
-            const double a2 = fma(2.0 * u, a1, 2.0 * t1 - a0);
-            const double b2 = fma(2.0 * u, b1, 4.0 * a1 - b0);
-            if (want_coef) acc[k] = fma(go, t2, acc[k]);
-            d1 = fma(cf[k], a2, d1);
-            d2 = fma(cf[k], b2, d2);
-            t0 = t1; t1 = t2; a0 = a1; a1 = a2; b0 = b1; b1 = b2;
-          }
-        }
-      }
-      if (p.gxa != nullptr && inside) {
-        const double w = go * ((p.order == 1) ? d1 * p.scale : d2 * p.scale * p.scale);
-#pragma unroll
-        for (int k = 0; k < kBwdMaxW; ++k)
-          if (k < p.W) gx[k] = fma(w, xj[f * p.W + k], gx[k]);
-      }
-    }
-    if (want_coef) {
-#pragma unroll
-      for (int k = 0; k < TACC; ++k) {
-        if (k < p.T) {
-          const double v = warp_sum(acc[k]);
-          if (lane == 0) atomicAdd(gc_blk + k, v);
-        }
-      }
-    }
-    if (p.gxa != nullptr) {
-#pragma unroll
-      for (int k = 0; k < kBwdMaxW; ++k) {
-        if (k < p.W) {
-          const double v = warp_sum(gx[k]);
-          if (lane == 0) p.gxa[i * D + f * p.W + k] = v;
-        }
-      }
-    }
+    if (TMAX > 64 && te > 64) series_bwd_row_big<TMAX>(p, te, cfs, gc_blk, xi, i, f);
+    else if (TMAX > 16 && te > 16) series_bwd_row<(TMAX < 64 ? TMAX : 64)>(p, te, cfs, gc_blk, xi, i, f);
+    else series_bwd_row<(TMAX < 16 ? TMAX : 16)>(p, te, cfs, gc_blk, xi, i, f);
   }
   __syncthreads();
-  if (want_coef)
+  if (p.gcoef != nullptr && p.order == 1)
     for (int e = threadIdx.x; e < p.T; e += blockDim.x) atomicAdd(p.gcoef + f * p.T + e, gc_blk[e]);
 }
 
