@@ -110,15 +110,16 @@ def _fused_mll(kernel, x, y, noise, mean_const, jitter):
     from . import _ops
     from .kernels_sphere import _series_on
 
-    base, scale = kernel, 1.0
-    if hasattr(kernel, "base_kernel") and hasattr(kernel, "outputscale"):
-        base, scale = kernel.base_kernel, kernel.outputscale
+    base, scaled = kernel, False
+    if hasattr(kernel, "base_kernel") and hasattr(type(kernel), "outputscale"):   # type(): hasattr on the instance would run the softplus
+        base, scaled = kernel.base_kernel, True
         if getattr(kernel, "active_dims", None) is not None:
             return None
     if not hasattr(base, "series") or getattr(base, "active_dims", None) is not None or x.dim() != 2:
         return None
     if hasattr(base, "_to_circles"):
         return None
+    scale = kernel.outputscale if scaled else 1.0
     spec, coef = _series_on(base, x.device)
     if spec.n_factors != 1 or x.shape[-1] != spec.factor_width:
         return None
@@ -137,7 +138,7 @@ def _dense_mll(kernel, x, y, noise, mean_const, jitter):
     if x.dim() != 2 or x.shape[0] > _ops.dense_large_max_n():
         return None
     base, scale = kernel, 1.0
-    if hasattr(kernel, "base_kernel") and hasattr(kernel, "outputscale") and getattr(kernel, "active_dims", None) is None:
+    if hasattr(kernel, "base_kernel") and hasattr(type(kernel), "outputscale") and getattr(kernel, "active_dims", None) is None:
         base, scale = kernel.base_kernel, kernel.outputscale
     k = base(x, x)
     if not torch.is_tensor(k):          # gpytorch lazy tensors

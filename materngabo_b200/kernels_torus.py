@@ -32,7 +32,7 @@ class _TorusKernel(Kernel):
         if self.dim > _lib.MAX_FACTORS:
             raise NotImplementedError("T^d with d > %d" % _lib.MAX_FACTORS)
         kernels = list(self.torus_kernel.kernels)
-        if sync_free and _weights.device_grids_enabled() and all(k.lengthscale.is_cuda for k in kernels):
+        if sync_free and _weights.device_grids_enabled() and all(k.raw_lengthscale.is_cuda for k in kernels):   # raw: no softplus launch
             # GP-fit sizes: every factor's 201 Chebyshev coefficients straight from the device (no truncation, no basis
             # decision, no lengthscale.item()): the marginal-likelihood step is then CUDA-graph capturable
             rows = [_weights.circle_coef_sync_free(k._coef_mode, k.lengthscale, getattr(k, "nu", None) if k._coef_mode == 0 else None,
@@ -44,7 +44,8 @@ class _TorusKernel(Kernel):
 
     def forward(self, x1, x2, diag=False, **params):
         _check_batch(self)
-        x1c, x2c = self._to_circles(x1), self._to_circles(x2)
+        x1c = self._to_circles(x1)
+        x2c = x1c if x2 is x1 else self._to_circles(x2)          # K(X, X) of the fit: one conversion
         if x1c.shape[-1] != 2 * self.dim or x2c.shape[-1] != 2 * self.dim:
             raise RuntimeError("T^%d points must be %d angles or %d circle coordinates" % (self.dim, self.dim, 2 * self.dim))
         fit_sized = (x1c.dim() == 2 and x2c.dim() == 2 and x1c.shape[0] * x2c.shape[0] < SYNC_FREE_MAX_ENTRIES
