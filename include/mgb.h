@@ -439,6 +439,14 @@ long long mgb_posterior_i8f_workspace_bytes(long long m, long long n);
 int mgb_posterior_i8f_reduce(const double* kstar, long long m, long long n, long long ldk, const void* packed,
                              const double* alpha, double kss, double mean_const, double* mean, double* var,
                              void* workspace, long long workspace_bytes, void* stream);
+/* Series kernels end to end on that kernel: candidates -> kernel rows -> slices -> contraction for one chunk of m
+ * candidates (the INT8 counterpart of mgb_series_posterior): Gram kernel into the workspace, slicing, contraction;
+ * workspace of mgb_series_posterior_i8f_workspace_bytes(m, n) bytes. */
+long long mgb_series_posterior_i8f_workspace_bytes(long long m, long long n);
+int mgb_series_posterior_i8f(const mgb_series_desc* desc, const double* xc, long long m, long long ldc, const double* xtrain,
+                             long long n, long long ldt, const double* coef, const void* packed, const double* alpha,
+                             double kss, double mean_const, double* mean, double* var, void* workspace,
+                             long long workspace_bytes, void* stream);
 long long mgb_posterior_i8f_planes_bytes(long long m, long long n);
 int mgb_posterior_i8f_reduce_debug(const double* kstar, long long m, long long n, long long ldk, const void* packed,
                                    const double* alpha, double kss, double mean_const, double* mean, double* var,

@@ -92,6 +92,8 @@ PROTOTYPES = {
     "mgb_posterior_i8f_pack": (_I, [_P, _LL, _LL, _P, _P]),
     "mgb_posterior_i8f_workspace_bytes": (_LL, [_LL, _LL]),
     "mgb_posterior_i8f_reduce": (_I, [_P, _LL, _LL, _LL, _P, _P, _D, _D, _P, _P, _P, _LL, _P]),
+    "mgb_series_posterior_i8f_workspace_bytes": (_LL, [_LL, _LL]),
+    "mgb_series_posterior_i8f": (_I, [_P, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P, _D, _D, _P, _P, _P, _LL, _P]),
     "mgb_posterior_i8f_planes_bytes": (_LL, [_LL, _LL]),
     "mgb_posterior_i8f_reduce_debug": (_I, [_P, _LL, _LL, _LL, _P, _P, _D, _D, _P, _P, _P, _LL, _P, _P]),
     "mgb_expected_improvement": (_I, [_P, _P, _LL, _D, _I, _P, _P]),

@@ -178,11 +178,10 @@ struct mgb_posterior {
   long long stage_rows = 0;
   cudaStream_t compute = nullptr, h2d = nullptr, d2h = nullptr;
   cudaEvent_t up[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, down[2] = {nullptr, nullptr};
-  // opt-in INT8 tensor-core contraction (csrc/int8_fused.cu): sliced L^-1, alpha, a row-major kernel-row block, workspace
+  // opt-in INT8 tensor-core contraction (csrc/int8_fused.cu): sliced L^-1, alpha, workspace
   bool int8 = false, owns_i8 = false;
   void* d_pack8 = nullptr;
   double* d_alpha = nullptr;
-  double* d_krows = nullptr;
   void* d_ws8 = nullptr;
   long long ws8_bytes = 0;
 };
@@ -213,7 +212,6 @@ static void posterior_release(mgb_posterior* h) {
     cudaFree(h->d_pack8);
     cudaFree(h->d_alpha);
   }
-  cudaFree(h->d_krows);
   cudaFree(h->d_ws8);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->compute) cudaStreamDestroy(h->compute);
@@ -248,12 +246,11 @@ static int posterior_common_init(mgb_posterior* h, long long max_chunk) {
   MGB_TRY(check_cuda(cudaStreamCreateWithFlags(&h->h2d, cudaStreamNonBlocking), "cudaStreamCreate"));
   return check_cuda(cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking), "cudaStreamCreate");
 }
-// INT8 mode of a handle: buffers for one block of kernel rows (row-major float64) and the fused kernel's workspace.
+// INT8 mode of a handle: the workspace of mgb_series_posterior_i8f for one chunk.
 static int posterior_int8_buffers(mgb_posterior* h) {
   if (h->n > 32768) return fail(MGB_ERR_ARG, "posterior handle: the INT8 path needs n <= 32768");
-  if (!h->d_krows) MGB_TRY(dev_alloc(&h->d_krows, (size_t)(h->chunk * h->n)));
   if (!h->d_ws8) {
-    h->ws8_bytes = mgb_posterior_i8f_workspace_bytes(h->chunk, h->n);
+    h->ws8_bytes = mgb_series_posterior_i8f_workspace_bytes(h->chunk, h->n);
     MGB_TRY(check_cuda(cudaMalloc(&h->d_ws8, (size_t)h->ws8_bytes), "cudaMalloc"));
   }
   return MGB_OK;
@@ -267,9 +264,8 @@ static int posterior_eval_rows(mgb_posterior* h, const double* xc_dev, long long
                                 mean_dev, var_dev, h->d_ws, h->ws_bytes, chunk, stream);
   for (long long c0 = 0; c0 < m; c0 += h->chunk) {
     const long long rows = m - c0 < h->chunk ? m - c0 : h->chunk;
-    MGB_TRY(mgb_series_gram_fwd(&h->desc, xc_dev + c0 * ldc, rows, ldc, h->d_xt, h->n, h->ldt, h->d_coef, h->d_krows, h->n, stream));
-    MGB_TRY(mgb_posterior_i8f_reduce(h->d_krows, rows, h->n, h->n, h->d_pack8, h->d_alpha, h->kss, h->mean_const, mean_dev + c0,
-                                     var_dev + c0, h->d_ws8, h->ws8_bytes, stream));
+    MGB_TRY(mgb_series_posterior_i8f(&h->desc, xc_dev + c0 * ldc, rows, ldc, h->d_xt, h->n, h->ldt, h->d_coef, h->d_pack8, h->d_alpha,
+                                     h->kss, h->mean_const, mean_dev + c0, var_dev + c0, h->d_ws8, h->ws8_bytes, stream));
   }
   return MGB_OK;
 }

@@ -69,18 +69,20 @@ __device__ __forceinline__ int f8_swizzled(int r, int c16) { return (r >> 3) * 1
 // One warp per row: e = exponent with |row| 2^-e < 1/2, then S round-to-nearest slices of 7 bits, written into the
 // tiled operand image.  is_b = 0: K* rows (128-row tiles; also mean_i = mean_const + sum_j K*_ij alpha_j);
 // is_b = 1: rows of L^-1 (64-row tiles, lower triangle only, k-blocks beyond the tile's diagonal are never read).
-// Rows in [rows, rows_pad) are written as zeros.  Per iteration the warp takes 128 consecutive columns - lane l the four
+// Rows in [rows, rows_pad) are written as zeros; row0 = position of src's first row in the operand.  Per iteration the warp takes 128 consecutive columns - lane l the four
 // columns 4 l .. 4 l + 3 (two 16-byte loads, 1 KB per warp) - and stores one 32-bit word per slice: the 32 words of a
 // warp are the 128 bytes of one (swizzled) tile row.  Rounding by the 1.5 * 2^52 trick: t = x + M is x rounded to an
 // integer in the low mantissa bits (|x| <= 64), t - M that integer as a double, x - (t - M) the exact remainder.
-__global__ void __launch_bounds__(256) f8_slice_kernel(const double* src, long long ld, long long rows, long long rows_pad, int cols,
-                                                       F8Geom g, int is_b, signed char* dst, int* exps, double* scales,
+__global__ void __launch_bounds__(256) f8_slice_kernel(const double* src, long long ld, long long row0, long long rows, long long rows_pad,
+                                                       int cols, F8Geom g, int is_b, signed char* dst, int* exps, double* scales,
                                                        const double* alpha, double mean_const, double* mean) {
+  // src holds rows [row0, row0 + rows) of the operand (a sub-block of the candidate chunk); rows up to rows_pad are padding
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows_pad) return;
-  const bool valid = row < rows;
-  const double* s = src + (valid ? row : 0) * ld;
+  const long long lrow = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (lrow >= rows_pad) return;
+  const long long row = row0 + lrow;
+  const bool valid = lrow < rows;
+  const double* s = src + (valid ? lrow : 0) * ld;
   const int used = !valid ? 0 : (is_b ? (int)min((long long)cols, row + 1) : cols);
   const bool vec = ((reinterpret_cast<uintptr_t>(s) & 15) == 0);      // 16-byte loads need an aligned row
   double mx = 0.0, mu = 0.0;
@@ -456,7 +458,7 @@ extern "C" int mgb_posterior_i8f_pack(const double* rinv, long long n, long long
   double* sb = static_cast<double*>(packed);
   signed char* B = static_cast<signed char*>(packed) + 8 * g.np;
   MGB_TRY(check_cuda(cudaMemsetAsync(packed, 0, (size_t)mgb_posterior_i8f_pack_bytes(n), s), "cudaMemsetAsync"));
-  f8_slice_kernel<<<(unsigned)((g.np + 7) / 8), 256, 0, s>>>(rinv, ld, n, g.np, (int)n, g, 1, B, nullptr, sb, nullptr, 0.0, nullptr);
+  f8_slice_kernel<<<(unsigned)((g.np + 7) / 8), 256, 0, s>>>(rinv, ld, 0, n, g.np, (int)n, g, 1, B, nullptr, sb, nullptr, 0.0, nullptr);
   return after_launch("f8_slice_kernel (pack)");
 }
 
@@ -476,34 +478,48 @@ extern "C" long long mgb_posterior_i8f_workspace_bytes(long long m, long long n)
   if (m < 1 || n < 1) return 0;
   const F8Geom g = f8_geom(n);
   const long long m_pad = f8_round_up(m, F8_BM);
-  return f8_ws_ea(m) + f8_round_up(g.a_bytes(m), 256) + (long long)g.CT * m_pad * 8;
+  return f8_ws_ea(m) + f8_round_up(g.a_bytes(m), 256) + f8_round_up((long long)g.CT * m_pad * 8, 256);
 }
 
-static int f8_reduce(const double* kstar, long long m, long long n, long long ldk, const void* packed, const double* alpha,
-                     double kss, double mean_const, double* mean, double* var, void* workspace, long long workspace_bytes,
-                     int* planes, void* stream) {
-  if (m == 0) return MGB_OK;
-  if (!kstar || !packed || !alpha || !mean || !var || !workspace || m < 0 || n < 1 || ldk < n)
-    return fail(MGB_ERR_ARG, "posterior_i8f_reduce: bad argument");
-  if (m > 0x7fffffffLL / 8 || n > 32768) return fail(MGB_ERR_ARG, "posterior_i8f_reduce: block too large");
-  if (workspace_bytes < mgb_posterior_i8f_workspace_bytes(m, n)) return fail(MGB_ERR_ARG, "posterior_i8f_reduce: workspace too small");
-  const F8Geom g = f8_geom(n);
+struct F8Workspace {
+  int* ea;
+  signed char* A;
+  double* partial;
+  double* krows;      // series entry point only: one sub-block of float64 kernel rows
+};
+
+static F8Workspace f8_carve(void* workspace, long long m, const F8Geom& g) {
+  F8Workspace w;
+  char* p = static_cast<char*>(workspace);
+  w.ea = reinterpret_cast<int*>(p);
+  p += f8_ws_ea(m);
+  w.A = reinterpret_cast<signed char*>(p);
+  p += f8_round_up(g.a_bytes(m), 256);
+  w.partial = reinterpret_cast<double*>(p);
+  p += f8_round_up((long long)g.CT * f8_round_up(m, F8_BM) * 8, 256);
+  w.krows = reinterpret_cast<double*>(p);
+  return w;
+}
+
+// rows [row0, row0 + rows) of K* -> slices; the last sub-block of a chunk also writes the zero rows up to the 128 boundary
+static int f8_slice_rows(const double* kstar, long long ldk, long long row0, long long rows, bool last, long long n, const F8Geom& g,
+                         const F8Workspace& w, const double* alpha, double mean_const, double* mean, cudaStream_t s) {
+  const long long rows_pad = last ? f8_round_up(row0 + rows, F8_BM) - row0 : rows;
+  f8_slice_kernel<<<(unsigned)((rows_pad + 7) / 8), 256, 0, s>>>(kstar, ldk, row0, rows, rows_pad, (int)n, g, 0, w.A, w.ea, nullptr, alpha,
+                                                                   mean_const, mean);
+  return after_launch("f8_slice_kernel");
+}
+
+// slices of m candidates (already in the workspace) x packed factor -> var
+static int f8_contract(long long m, long long n, const F8Geom& g, const F8Workspace& w, const void* packed, double kss, double* var,
+                       int* planes, cudaStream_t s) {
   const long long m_pad = f8_round_up(m, F8_BM);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  char* w = static_cast<char*>(workspace);
-  int* ea = reinterpret_cast<int*>(w);
-  w += f8_ws_ea(m);
-  signed char* A = reinterpret_cast<signed char*>(w);
-  w += f8_round_up(g.a_bytes(m), 256);
-  double* partial = reinterpret_cast<double*>(w);
-  f8_slice_kernel<<<(unsigned)((m_pad + 7) / 8), 256, 0, s>>>(kstar, ldk, m, m_pad, (int)n, g, 0, A, ea, nullptr, alpha, mean_const, mean);
-  MGB_TRY(after_launch("f8_slice_kernel"));
   F8Params P;
-  P.A = A;
+  P.A = w.A;
   P.B = static_cast<const signed char*>(packed) + 8 * g.np;
-  P.ea = ea;
+  P.ea = w.ea;
   P.sb = static_cast<const double*>(packed);
-  P.partial = partial;
+  P.partial = w.partial;
   P.planes = planes;
   P.m = m;
   P.m_pad = m_pad;
@@ -520,8 +536,23 @@ static int f8_reduce(const double* kstar, long long m, long long n, long long ld
   const unsigned grid = (unsigned)std::min<long long>(device_sm_count(), live);
   f8_posterior_kernel<<<grid, F8_THREADS, F8_SMEM, s>>>(P);
   MGB_TRY(after_launch("f8_posterior_kernel"));
-  f8_finish_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(partial, m, m_pad, g.CT, kss, var);
+  f8_finish_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(w.partial, m, m_pad, g.CT, kss, var);
   return after_launch("f8_finish_kernel");
+}
+
+static int f8_reduce(const double* kstar, long long m, long long n, long long ldk, const void* packed, const double* alpha,
+                     double kss, double mean_const, double* mean, double* var, void* workspace, long long workspace_bytes,
+                     int* planes, void* stream) {
+  if (m == 0) return MGB_OK;
+  if (!kstar || !packed || !alpha || !mean || !var || !workspace || m < 0 || n < 1 || ldk < n)
+    return fail(MGB_ERR_ARG, "posterior_i8f_reduce: bad argument");
+  if (m > 0x7fffffffLL / 8 || n > 32768) return fail(MGB_ERR_ARG, "posterior_i8f_reduce: block too large");
+  if (workspace_bytes < mgb_posterior_i8f_workspace_bytes(m, n)) return fail(MGB_ERR_ARG, "posterior_i8f_reduce: workspace too small");
+  const F8Geom g = f8_geom(n);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const F8Workspace w = f8_carve(workspace, m, g);
+  MGB_TRY(f8_slice_rows(kstar, ldk, 0, m, true, n, g, w, alpha, mean_const, mean, s));
+  return f8_contract(m, n, g, w, packed, kss, var, planes, s);
 }
 
 extern "C" int mgb_posterior_i8f_reduce(const double* kstar, long long m, long long n, long long ldk, const void* packed,
@@ -541,4 +572,46 @@ extern "C" int mgb_posterior_i8f_reduce_debug(const double* kstar, long long m, 
                                               void* workspace, long long workspace_bytes, int* planes, void* stream) {
   if (!planes) return fail(MGB_ERR_ARG, "posterior_i8f_reduce_debug: planes is null");
   return f8_reduce(kstar, m, n, ldk, packed, alpha, kss, mean_const, mean, var, workspace, workspace_bytes, planes, stream);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Series kernels end to end (mgb.h): candidates -> kernel rows -> slices -> contraction, for one chunk of m candidates.
+// MGB_I8F_SUB = rows per Gram + slicing sub-block (default: the whole chunk).  Sub-blocks small enough to keep the float64
+// kernel rows in L2 between the Gram kernel's writes and the slicing kernel's reads were measured and lost: 1280 rows
+// 3.29e6, 2560 rows 3.50e6, whole chunk 3.68e6 candidates/s (both kernels are sized for large launches).
+// ------------------------------------------------------------------------------------------------------------------
+static long long f8_sub_rows() {
+  static const long long v = [] {
+    const char* e = std::getenv("MGB_I8F_SUB");
+    const long long r = e ? std::atoll(e) : 0;
+    return r >= 128 ? r / 128 * 128 : (1LL << 40);
+  }();
+  return v;
+}
+
+extern "C" long long mgb_series_posterior_i8f_workspace_bytes(long long m, long long n) {
+  if (m < 1 || n < 1) return 0;
+  const long long sub = std::min<long long>(f8_sub_rows(), f8_round_up(m, F8_BM));
+  return mgb_posterior_i8f_workspace_bytes(m, n) + sub * n * 8;
+}
+
+extern "C" int mgb_series_posterior_i8f(const mgb_series_desc* desc, const double* xc, long long m, long long ldc, const double* xtrain,
+                                        long long n, long long ldt, const double* coef, const void* packed, const double* alpha,
+                                        double kss, double mean_const, double* mean, double* var, void* workspace,
+                                        long long workspace_bytes, void* stream) {
+  if (m == 0) return MGB_OK;
+  if (!desc || !xc || !xtrain || !coef || !packed || !alpha || !mean || !var || !workspace || m < 0 || n < 1)
+    return fail(MGB_ERR_ARG, "series_posterior_i8f: bad argument");
+  if (m > 0x7fffffffLL / 8 || n > 32768) return fail(MGB_ERR_ARG, "series_posterior_i8f: block too large");
+  if (workspace_bytes < mgb_series_posterior_i8f_workspace_bytes(m, n)) return fail(MGB_ERR_ARG, "series_posterior_i8f: workspace too small");
+  const F8Geom g = f8_geom(n);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const F8Workspace w = f8_carve(workspace, m, g);
+  const long long sub = std::min<long long>(f8_sub_rows(), f8_round_up(m, F8_BM));
+  for (long long r0 = 0; r0 < m; r0 += sub) {
+    const long long rows = std::min<long long>(sub, m - r0);
+    MGB_TRY(mgb_series_gram_fwd(desc, xc + r0 * ldc, rows, ldc, xtrain, n, ldt, coef, w.krows, n, stream));
+    MGB_TRY(f8_slice_rows(w.krows, n, r0, rows, r0 + rows >= m, n, g, w, alpha, mean_const, mean, s));
+  }
+  return f8_contract(m, n, g, w, packed, kss, var, nullptr, s);
 }

@@ -376,6 +376,23 @@ class ExactGPPosterior:
         forward = None
         if not self.is_series:
             forward = self.kernel.forward
+        if self.is_series and self.int8_impl == "fused":
+            # candidates -> kernel rows -> slices -> contraction in one C call per chunk (mgb_series_posterior_i8f)
+            need = lib.mgb_series_posterior_i8f_workspace_bytes(chunk, n)
+            if self._ws_i8 is None or self._ws_i8.numel() < need:
+                self._ws_i8 = torch.empty(need, dtype=torch.uint8, device=self.device)
+            d = self.spec.desc(self.coef.shape[-1])
+            with torch.cuda.device(self.device):
+                for c0 in range(0, m, chunk):
+                    mc = min(chunk, m - c0)
+                    xs = x[c0:c0 + mc]
+                    rc = lib.mgb_series_posterior_i8f(C.byref(d), _lib.ptr(xs), mc, xs.stride(0), _lib.ptr(self.train_prepared), n,
+                                                      self.train_prepared.stride(0), _lib.ptr(self.coef), _lib.ptr(self._packed_i8),
+                                                      _lib.ptr(self.alpha), float(self.kss_value), self.mean_const,
+                                                      _lib.ptr(mean[c0:]), _lib.ptr(var[c0:]), _lib.ptr(self._ws_i8),
+                                                      self._ws_i8.numel(), st)
+                    _lib.check(rc, "mgb_series_posterior_i8f")
+            return mean, var
         with torch.cuda.device(self.device):
             for c0 in range(0, m, chunk):
                 mc = min(chunk, m - c0)
