@@ -288,7 +288,8 @@ def run_posterior(args, rank, world, local):
 
 def posterior_int8_sample(gp, xs, fp64_value, impl):
     """The opt-in INT8 path on a sample of the same candidates: candidates/s and the difference to the FP64 path's results
-    on that sample.  Reported beside the headline, not as the headline (its error is ~1e-11 of max var against ~1e-14).
+    on that sample.  Reported beside the headline, not as the headline (north_star quotes the FP64 roof; error ~2e-13 of max var for the fused
+    kernel, ~2e-11 for the library variant, against ~1e-14 of the FP64 kernel).
     impl "fused": this repo's tcgen05 kernel (csrc/int8_fused.cu); "library": CUTLASS int8 GEMMs between this repo's
     slicing and recombination kernels (csrc/int8_posterior.cu)."""
     mean0, var0 = gp.posterior(xs)
@@ -308,7 +309,7 @@ def posterior_int8_sample(gp, xs, fp64_value, impl):
         gp._packed_i8 = None
     ms = e0.elapsed_time(e1)
     v = xs.shape[0] / (ms * 1e-3)
-    notes = {"fused": "opt-in (ExactGPPosterior(int8=True) / MGB_POSTERIOR_PATH=int8): error-free 7-bit slicing of K* and L^-1; "
+    notes = {"fused": "opt-in (ExactGPPosterior(int8=True) / MGB_POSTERIOR_PATH=int8): error-free 8-bit slicing of K* and L^-1 (carry pass keeps the digits in int8); "
                       "the 28 slice products, the float64 recombination and the sum of squares in ONE hand-written kernel "
                       "(tcgen05.mma kind::i8, seven int32 planes of a 128 x 64 tile in tensor memory, operands pre-tiled "
                       "in the tensor core's shared-memory image and staged by cp.async.bulk, exact triangular k range); "

@@ -430,7 +430,9 @@ int mgb_posterior_int8_reduce(const double* kstar, long long m, long long n, lon
 /* The same contraction in ONE hand-written tcgen05 kernel (csrc/int8_fused.cu): tcgen05.mma kind::i8 on 128-candidate x
  * 64-column tiles with the seven int32 planes in tensor memory, operands pre-tiled in the tensor core's shared-memory
  * image and staged with cp.async.bulk, exact triangular k range, float64 recombination and the sum of squares in the
- * epilogue (no int32 plane reaches HBM).  Same semantics and error as the mgb_posterior_int8_* calls; needs no CUTLASS.
+ * epilogue (no int32 plane reaches HBM).  Same semantics as the mgb_posterior_int8_* calls with 8-bit instead of 7-bit
+ * slices (a carry pass keeps the digits in int8): ~2e-13 of max var at n = 5000 instead of ~2e-11, n <= 16384 for exact
+ * int32 accumulation; needs no CUTLASS.
  * The _debug form additionally dumps the raw accumulators, planes[row block][column tile][7][128][64] int32
  * (mgb_posterior_i8f_planes_bytes(m, n) bytes), for the tests. */
 long long mgb_posterior_i8f_pack_bytes(long long n);
@@ -546,8 +548,8 @@ int mgb_posterior_create_from_device(const mgb_series_desc* desc, const double* 
                                      const double* coef_dev, const double* packed_dev, double kss_value,
                                      double mean_const, long long max_chunk, int device, mgb_posterior** out);
 long long mgb_posterior_chunk(const mgb_posterior* h);
-/* Opt-in INT8 tensor-core contraction for a handle (csrc/int8_fused.cu; ~1e-11 of max var instead of ~1e-14, ~2.5 x the
- * candidates/s).  packed_i8_dev = the sliced factor written by mgb_posterior_i8f_pack, alpha_dev = n doubles; both on the
+/* Opt-in INT8 tensor-core contraction for a handle (csrc/int8_fused.cu; ~2e-13 of max var instead of ~1e-14, ~2.7 x the
+ * candidates/s; n <= 16384).  packed_i8_dev = the sliced factor written by mgb_posterior_i8f_pack, alpha_dev = n doubles; both on the
  * handle's device, borrowed, and must outlive the handle (or the next call).  Both null = back to the FP64 kernel.
  * A handle made by mgb_posterior_create with MGB_POSTERIOR_PATH=int8 in the environment slices its own copy of L^-1 and
  * starts in this mode (the same switch as the Python host's ExactGPPosterior). */

@@ -248,7 +248,7 @@ static int posterior_common_init(mgb_posterior* h, long long max_chunk) {
 }
 // INT8 mode of a handle: the workspace of mgb_series_posterior_i8f for one chunk.
 static int posterior_int8_buffers(mgb_posterior* h) {
-  if (h->n > 32768) return fail(MGB_ERR_ARG, "posterior handle: the INT8 path needs n <= 32768");
+  if (h->n > 16384) return fail(MGB_ERR_ARG, "posterior handle: the INT8 path needs n <= 16384");
   if (!h->d_ws8) {
     h->ws8_bytes = mgb_series_posterior_i8f_workspace_bytes(h->chunk, h->n);
     MGB_TRY(check_cuda(cudaMalloc(&h->d_ws8, (size_t)h->ws8_bytes), "cudaMalloc"));

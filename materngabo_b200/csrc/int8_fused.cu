@@ -5,8 +5,11 @@
 //                                                                 model.posterior(X), manifold_optimize.py:195,254,337)
 //
 // Error-free slicing as in int8_posterior.cu: every row of K* and of L^-1 is scaled by a power of two and cut into
-// S = 7 signed 7-bit slices, a_ik = 2^ea_i sum_p A_p[i][k] 2^(-7 (p + 1)) (likewise b_jk), so that
-//      V_ij = 2^(ea_i + eb_j) sum_{d < 7} 2^(-7 (d + 2)) C_d[i][j],     C_d = sum_{p + q = d} A_p B_q^T   (int32, exact).
+// S = 7 signed 8-bit slices (round to nearest, a carry pass keeps every digit in [-128, 127]),
+// a_ik = 2^ea_i sum_p A_p[i][k] 2^(-8 (p + 1)) (likewise b_jk), so that
+//      V_ij = 2^(ea_i + eb_j) sum_{d < 7} 2^(-8 (d + 2)) C_d[i][j],     C_d = sum_{p + q = d} A_p B_q^T   (int32, exact:
+//      7 n 128^2 < 2^31 for n <= 16384).  56 bits per operand and 28 of the 49 slice products: the variance lands within
+//      ~1e-13 of max var of the exact result at n = 5000 (7-bit slices as in int8_posterior.cu: ~2e-11).
 // What differs from int8_posterior.cu (library GEMMs + a recombination pass over 7 int32 planes in HBM):
 //   * ONE kernel per candidate block.  A CTA owns a 128-candidate x 64-column tile of V; the seven planes C_0..C_6 of
 //     that tile live in tensor memory (7 x 64 = 448 of the 512 columns) for the whole k loop, the 28 slice products of a
@@ -30,7 +33,7 @@
 namespace mgb {
 
 constexpr int F8_S = 7;                   // slices
-constexpr int F8_BITS = 7;                // bits per slice
+constexpr int F8_BITS = 8;                // bits per slice: digits in [-128, 127] after the carry pass of the slicing kernel
 constexpr int F8_BM = 128;                // candidates per tile = UMMA M = TMEM lanes
 constexpr int F8_BN = 64;                 // columns per tile = UMMA N
 constexpr int F8_BK = 128;                // int8 per k-block = one swizzle row
@@ -40,6 +43,7 @@ constexpr int F8_A_STAGES = 6;
 constexpr int F8_B_STAGES = 2;
 constexpr int F8_THREADS = 192;
 constexpr int F8_TMEM_COLS = 512;
+constexpr long long F8_MAX_N = 16384;     // 7 n 128^2 < 2^31
 constexpr size_t F8_SMEM = 1024 + (size_t)F8_B_STAGES * F8_S * F8_B_TILE + (size_t)F8_A_STAGES * F8_A_TILE + 256;
 
 __host__ __device__ inline long long f8_round_up(long long v, long long m) { return (v + m - 1) / m * m; }
@@ -66,7 +70,7 @@ __host__ __device__ inline F8Geom f8_geom(long long n) {
 // eight rows are 1024 bytes, and the chunk index is XORed with the row index inside the group.
 __device__ __forceinline__ int f8_swizzled(int r, int c16) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4); }
 
-// One warp per row: e = exponent with |row| 2^-e < 1/2, then S round-to-nearest slices of 7 bits, written into the
+// One warp per row: e = exponent with |row| 2^-e <= 126/256, then S round-to-nearest slices of 8 bits, written into the
 // tiled operand image.  is_b = 0: K* rows (128-row tiles; also mean_i = mean_const + sum_j K*_ij alpha_j);
 // is_b = 1: rows of L^-1 (64-row tiles, lower triangle only, k-blocks beyond the tile's diagonal are never read).
 // Rows in [rows, rows_pad) are written as zeros; row0 = position of src's first row in the operand.  Per iteration the warp takes 128 consecutive columns - lane l the four
@@ -101,8 +105,8 @@ __global__ void __launch_bounds__(256) f8_slice_kernel(const double* src, long l
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   int e = 0;
   if (mx > 0.0) {
-    (void)frexp(mx, &e);
-    e += 1;
+    const double f = frexp(mx, &e);      // mx = f 2^e, f in [1/2, 1)
+    e += (f > 0.984375) ? 2 : 1;         // |row| 2^-e <= 126 / 256: the leading digit stays below 127 and can take a carry
   }
   if (lane == 0) {
     if (exps != nullptr) exps[row] = e;
@@ -129,16 +133,31 @@ __global__ void __launch_bounds__(256) f8_slice_kernel(const double* src, long l
       for (int t = 0; t < 4; ++t) r[t] = (c0 + t < used) ? s[c0 + t] * down : 0.0;
     }
     signed char* tile = base + (long long)kb * F8_S * tile_bytes;
+    int q[F8_S][4];
 #pragma unroll
     for (int p = 0; p < F8_S; ++p) {
-      unsigned word = 0;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const double x = r[t] * (double)(1 << F8_BITS);
         const double tt = x + kMagic;
-        word |= ((unsigned)__double2loint(tt) & 0xffu) << (8 * t);
+        q[p][t] = __double2loint(tt);            // round to nearest: [-128, 128]
         r[t] = x - (tt - kMagic);
       }
+    }
+    // a digit of +128 does not fit int8: write it as -128 and carry one into the next more significant digit
+#pragma unroll
+    for (int p = F8_S - 1; p >= 1; --p) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int c = (q[p][t] == 128) ? 1 : 0;
+        q[p][t] -= c << 8;
+        q[p - 1][t] += c;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < F8_S; ++p) {
+      const unsigned word = ((unsigned)q[p][0] & 0xffu) | (((unsigned)q[p][1] & 0xffu) << 8) | (((unsigned)q[p][2] & 0xffu) << 16) |
+                            (((unsigned)q[p][3] & 0xffu) << 24);
       *reinterpret_cast<unsigned*>(tile + p * tile_bytes) = word;
     }
   }
@@ -452,7 +471,7 @@ extern "C" long long mgb_posterior_i8f_pack_bytes(long long n) {
 
 extern "C" int mgb_posterior_i8f_pack(const double* rinv, long long n, long long ld, void* packed, void* stream) {
   if (!rinv || !packed || n < 1 || ld < n) return fail(MGB_ERR_ARG, "posterior_i8f_pack: bad argument");
-  if (n > 32768) return fail(MGB_ERR_ARG, "posterior_i8f_pack: n too large for exact int32 accumulation");
+  if (n > F8_MAX_N) return fail(MGB_ERR_ARG, "posterior_i8f_pack: n too large for exact int32 accumulation (16384)");
   const F8Geom g = f8_geom(n);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   double* sb = static_cast<double*>(packed);
@@ -546,7 +565,7 @@ static int f8_reduce(const double* kstar, long long m, long long n, long long ld
   if (m == 0) return MGB_OK;
   if (!kstar || !packed || !alpha || !mean || !var || !workspace || m < 0 || n < 1 || ldk < n)
     return fail(MGB_ERR_ARG, "posterior_i8f_reduce: bad argument");
-  if (m > 0x7fffffffLL / 8 || n > 32768) return fail(MGB_ERR_ARG, "posterior_i8f_reduce: block too large");
+  if (m > 0x7fffffffLL / 8 || n > F8_MAX_N) return fail(MGB_ERR_ARG, "posterior_i8f_reduce: block too large (n <= 16384)");
   if (workspace_bytes < mgb_posterior_i8f_workspace_bytes(m, n)) return fail(MGB_ERR_ARG, "posterior_i8f_reduce: workspace too small");
   const F8Geom g = f8_geom(n);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -602,7 +621,7 @@ extern "C" int mgb_series_posterior_i8f(const mgb_series_desc* desc, const doubl
   if (m == 0) return MGB_OK;
   if (!desc || !xc || !xtrain || !coef || !packed || !alpha || !mean || !var || !workspace || m < 0 || n < 1)
     return fail(MGB_ERR_ARG, "series_posterior_i8f: bad argument");
-  if (m > 0x7fffffffLL / 8 || n > 32768) return fail(MGB_ERR_ARG, "series_posterior_i8f: block too large");
+  if (m > 0x7fffffffLL / 8 || n > F8_MAX_N) return fail(MGB_ERR_ARG, "series_posterior_i8f: block too large (n <= 16384)");
   if (workspace_bytes < mgb_series_posterior_i8f_workspace_bytes(m, n)) return fail(MGB_ERR_ARG, "series_posterior_i8f: workspace too small");
   const F8Geom g = f8_geom(n);
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -87,7 +87,7 @@ class ExactGPPosterior:
         # (materngabo_b200/tabulated.py) instead of one quadrature per entry; the fit always uses the quadrature
         self.tabulate = bool(tabulate)
         self.device = train_x.device
-        # opt-in: the N^2 contraction on the INT8 tensor cores by error-free slicing (csrc/int8_posterior.cu; ~1e-11 of
+        # opt-in: the N^2 contraction on the INT8 tensor cores by error-free slicing (csrc/int8_fused.cu; ~2e-13 of
         # max var instead of ~1e-14).  Default: the FP64 tensor-core kernel.  MGB_POSTERIOR_PATH=int8 turns it on globally.
         self.int8 = bool(int8) if int8 is not None else os.environ.get("MGB_POSTERIOR_PATH", "") == "int8"
         # which INT8 implementation: "fused" = this repo's tcgen05 kernel (csrc/int8_fused.cu), "library" = CUTLASS int8
@@ -357,7 +357,8 @@ class ExactGPPosterior:
 
     def _posterior_int8(self, x, mean, var, chunk):
         """Opt-in INT8 tensor-core path: row-major float64 kernel rows from the Gram kernel, cut into seven int8 slices,
-        slice products against the sliced L^-1 on the INT8 tensor cores, recombined in float64 (~1e-11 of max var).
+        slice products against the sliced L^-1 on the INT8 tensor cores, recombined in float64 (fused: 8-bit slices,
+        ~2e-13 of max var; library: 7-bit slices, ~2e-11).
         int8_impl "fused": one hand-written tcgen05 kernel per block (csrc/int8_fused.cu); "library": seven CUTLASS GEMMs
         per column block + a recombination pass (csrc/int8_posterior.cu)."""
         lib = _lib.load()

@@ -398,9 +398,9 @@ def _int8_or_skip(impl):
 @pytest.mark.parametrize("impl", INT8_IMPLS)
 @pytest.mark.parametrize("n,m", [(300, 1000), (1000, 20000), (2100, 3001)])
 def test_int8_tensor_core_posterior_matches_the_fp64_path(n, m, impl):
-    """Opt-in INT8 path (error-free 7-bit slicing, 28 slice products on the INT8 tensor cores, float64 recombination;
+    """Opt-in INT8 path (error-free slicing, 28 slice products on the INT8 tensor cores, float64 recombination;
     "fused" = the hand-written tcgen05 kernel, "library" = CUTLASS GEMMs) against the FP64 tensor-core kernel: variance
-    to 1e-10 of max var (measured ~1e-11), mean to 1e-12 - including candidates 1e-3 away from training points, where
+    to 1e-10 of max var (measured ~1e-11 library / ~2e-13 fused, which is held to 5e-12 here), mean to 1e-12 - including candidates 1e-3 away from training points, where
     the variance is a cancellation."""
     from materngabo_b200 import kernels_sphere
     from materngabo_b200.posterior import ExactGPPosterior
@@ -419,7 +419,7 @@ def test_int8_tensor_core_posterior_matches_the_fp64_path(n, m, impl):
     fast = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.3, noise=1e-2, mean_const=0.2, int8=impl).fit()
     m0, v0 = ref.posterior(xc.to(DEV))
     m1, v1 = fast.posterior(xc.to(DEV))
-    assert float((v1 - v0).abs().max() / v0.abs().max()) < 1e-10
+    assert float((v1 - v0).abs().max() / v0.abs().max()) < (5e-12 if impl == "fused" else 1e-10)
     assert float((m1 - m0).abs().max() / m0.abs().max()) < 1e-12
     assert float(v0.min()) < 0.1 * float(v0.max())          # the near-training candidates are in the sample
 
@@ -505,7 +505,7 @@ def test_headline_size_parity_against_oracle_and_long_double_truth(noise):
     mscale, vscale = float(np.abs(mo).max()), float(vo.max())
     assert float(vo.min()) < 2.0 * noise                      # the cancellation rows are in the sample
     assert np.abs(mg - mo).max() <= 1e-10 * mscale
-    assert np.abs(vg - vo).max() <= 1e-10 * vscale
+    assert np.abs(vg - vo).max() <= (5e-12 if impl == "fused" else 1e-10) * vscale     # 8-bit slices: measured 2e-13
     assert np.abs(mg[s] - mtr).max() <= max(np.abs(mo[s] - mtr).max(), 1e-10 * mscale)
     assert np.abs(vg[s] - vtr).max() <= max(np.abs(vo[s] - vtr).max(), 1e-10 * vscale)
 
@@ -605,16 +605,23 @@ def test_fused_int8_kernel_accumulator_planes_are_exact(m, n):
     torch.cuda.synchronize()
 
     def slices(x):
+        """f8_slice_kernel on the host: exponent with |row| 2^-e <= 126/256, seven round-to-nearest 8-bit digits, carry pass."""
         mx = np.abs(x).max(axis=1)
         e = np.zeros(x.shape[0], dtype=np.int64)
-        e[mx > 0] = np.frexp(mx[mx > 0])[1] + 1
+        f, ex = np.frexp(mx[mx > 0])
+        e[mx > 0] = ex + np.where(f > 0.984375, 2, 1)
         r = np.ldexp(x, -e[:, None])
         out = []
         for _ in range(7):
-            t = r * 128.0
+            t = r * 256.0
             q = np.rint(t)
             out.append(q.astype(np.int64))
             r = t - q
+        for p in range(6, 0, -1):
+            c = out[p] == 128
+            out[p][c] = -128
+            out[p - 1][c] += 1
+        assert all(int(np.abs(o).max()) <= 128 and int(o.max()) <= 127 for o in out)
         return out
 
     A, B = slices(ks.cpu().numpy()), slices(rinv.cpu().numpy())

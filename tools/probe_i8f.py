@@ -12,15 +12,15 @@ import torch
 from materngabo_b200 import _lib
 
 F64 = torch.float64
-S, BITS = 7, 7
+S, BITS = 7, 8
 
 
 def slices_np(x):
-    """Rows of x -> (exponent e, S int slices) exactly as f8_slice_kernel does."""
+    """Rows of x -> (exponent e, S int slices) exactly as f8_slice_kernel does (8-bit digits, carry pass)."""
     mx = np.abs(x).max(axis=1)
     e = np.zeros(x.shape[0], dtype=np.int64)
-    nz = mx > 0
-    e[nz] = np.frexp(mx[nz])[1] + 1
+    f, ex = np.frexp(mx[mx > 0])
+    e[mx > 0] = ex + np.where(f > 0.984375, 2, 1)
     r = np.ldexp(x, -e[:, None])
     out = []
     for _ in range(S):
@@ -28,6 +28,10 @@ def slices_np(x):
         q = np.rint(t)
         out.append(q.astype(np.int64))
         r = t - q
+    for p in range(S - 1, 0, -1):
+        c = out[p] == 128
+        out[p][c] = -128
+        out[p - 1][c] += 1
     return e, out
 
 
