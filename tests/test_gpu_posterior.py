@@ -505,7 +505,7 @@ def test_headline_size_parity_against_oracle_and_long_double_truth(noise):
     mscale, vscale = float(np.abs(mo).max()), float(vo.max())
     assert float(vo.min()) < 2.0 * noise                      # the cancellation rows are in the sample
     assert np.abs(mg - mo).max() <= 1e-10 * mscale
-    assert np.abs(vg - vo).max() <= (5e-12 if impl == "fused" else 1e-10) * vscale     # 8-bit slices: measured 2e-13
+    assert np.abs(vg - vo).max() <= 1e-10 * vscale
     assert np.abs(mg[s] - mtr).max() <= max(np.abs(mo[s] - mtr).max(), 1e-10 * mscale)
     assert np.abs(vg[s] - vtr).max() <= max(np.abs(vo[s] - vtr).max(), 1e-10 * vscale)
 
@@ -575,7 +575,7 @@ def test_int8_path_against_the_oracle_and_truth_at_the_headline_size(noise, impl
     mtr, vtr = truth.sphere_matern_posterior(xt.numpy(), y.numpy(), xc[:mt].numpy(), 10, 2.5, 0.5, 1.0, noise)
     mscale, vscale = float(np.abs(mo).max()), float(vo.max())
     assert np.abs(mg - mo).max() <= 1e-10 * mscale
-    assert np.abs(vg - vo).max() <= 1e-10 * vscale
+    assert np.abs(vg - vo).max() <= (5e-12 if impl == "fused" else 1e-10) * vscale     # 8-bit slices: measured 2e-13
     assert np.abs(mg[sel] - mtr).max() <= 1e-10 * mscale
     assert np.abs(vg[sel] - vtr).max() <= 1e-10 * vscale
 
