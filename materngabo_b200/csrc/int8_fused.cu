@@ -138,10 +138,9 @@ __global__ void __launch_bounds__(256) f8_slice_kernel(const double* src, long l
     for (int p = 0; p < F8_S; ++p) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const double x = r[t] * (double)(1 << F8_BITS);
-        const double tt = x + kMagic;
+        const double tt = fma(r[t], (double)(1 << F8_BITS), kMagic);      // r 2^8 is exact: one rounding, to an integer
         q[p][t] = __double2loint(tt);            // round to nearest: [-128, 128]
-        r[t] = x - (tt - kMagic);
+        r[t] = fma(r[t], (double)(1 << F8_BITS), -(tt - kMagic));        // exact remainder
       }
     }
     // a digit of +128 does not fit int8: write it as -128 and carry one into the next more significant digit
@@ -159,6 +158,181 @@ __global__ void __launch_bounds__(256) f8_slice_kernel(const double* src, long l
       const unsigned word = ((unsigned)q[p][0] & 0xffu) | (((unsigned)q[p][1] & 0xffu) << 8) | (((unsigned)q[p][2] & 0xffu) << 16) |
                             (((unsigned)q[p][3] & 0xffu) << 24);
       *reinterpret_cast<unsigned*>(tile + p * tile_bytes) = word;
+    }
+  }
+}
+
+// Kernel rows straight into slices for single-factor monomial series kernels (sphere S^d, SO(3)): one CTA per
+// (128-candidate row block, 128-column k-block) evaluates K*[i][j] = p(clamp(scale <x_i, t_j>(^2) + shift)) from shared
+// memory panels and writes the block's seven 16 KB slice tiles - the float64 kernel rows never exist in HBM.  All rows
+// share one exponent (|p(u)| <= sum |coef_k| on |u| <= 1; a row far from every training point loses the bits its own
+// maximum would have gained, which the parity bar - relative to the largest variance - does not see).  Per (row, four
+// columns): W dot-product FMAs per column from a broadcast candidate value and two 16-byte training loads, Horner, then
+// the same digit extraction + carry pass as f8_slice_kernel.  The mean's k-block partial sums go to meanpart[kb][row]
+// (f8_finish_kernel adds them in a fixed order).
+constexpr int F8G_MAXW = 16, F8G_MAXT = 32, F8G_THREADS = 256;
+
+struct F8GramParams {
+  const double* xc; long long m, ldc;        // candidates
+  const double* xt; long long n, ldt;        // training points
+  const double* coef; const double* alpha;
+  int W, T, square;
+  double scale, shift, lo, hi;
+  signed char* A; int* ea; double* meanpart;
+  long long m_pad;
+  F8Geom g;
+};
+
+// WT / TT > 0: width and term count at compile time (unrolled dot products and Horner); 0: run-time loops.
+template <int WT, int TT>
+__global__ void __launch_bounds__(F8G_THREADS) f8_gram_slice_kernel(const F8GramParams p) {
+  __shared__ __align__(16) double xts[F8G_MAXW][F8_BK];      // training panel, transposed: [k][column]
+  __shared__ __align__(16) double xcs[F8_BM][F8G_MAXW];      // candidate rows
+  __shared__ double cfs[F8G_MAXT];
+  __shared__ double als[F8_BK];
+  const int W = WT > 0 ? WT : p.W, T = TT > 0 ? TT : p.T;
+  const int kb = blockIdx.x;
+  const long long rb = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int e = threadIdx.x; e < W * F8_BK; e += F8G_THREADS) {
+    const int c = e / W, k = e - c * W;
+    const long long j = (long long)kb * F8_BK + c;
+    xts[k][c] = (j < p.n) ? p.xt[j * p.ldt + k] : 0.0;
+  }
+  for (int e = threadIdx.x; e < W * F8_BM; e += F8G_THREADS) {
+    const int r = e / W, k = e - r * W;
+    const long long i = rb * F8_BM + r;
+    xcs[r][k] = (i < p.m) ? p.xc[i * p.ldc + k] : 0.0;
+  }
+  for (int e = threadIdx.x; e < T; e += F8G_THREADS) cfs[e] = p.coef[e];
+  for (int e = threadIdx.x; e < F8_BK; e += F8G_THREADS) {
+    const long long j = (long long)kb * F8_BK + e;
+    als[e] = (j < p.n) ? p.alpha[j] : 0.0;
+  }
+  __syncthreads();
+  double cf[TT > 0 ? TT : 1];
+  double bound = 0.0;
+  for (int k = 0; k < T; ++k) bound += fabs(cfs[k]);
+  if (TT > 0) {
+#pragma unroll
+    for (int k = 0; k < TT; ++k) cf[k] = cfs[k];
+  }
+  int e2 = 0;
+  if (bound > 0.0) {
+    const double f = frexp(bound, &e2);
+    e2 += (f > 0.984375) ? 2 : 1;
+  }
+  const double down = ldexp(1.0, -e2);
+  constexpr double kMagic = 6755399441055744.0;      // 1.5 * 2^52
+  const long long tile_bytes = (long long)F8_BM * F8_BK;
+  signed char* tile0 = p.A + p.g.a_tile(rb, kb, 0) + ((lane & 3) << 2);
+  const int c0 = 4 * lane;
+  double al4[4];
+  bool colok[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    al4[t] = als[c0 + t];
+    colok[t] = (long long)kb * F8_BK + c0 + t < p.n;
+  }
+  constexpr int RPT = 2;                               // rows per iteration: eight independent chains per lane
+  for (int r0 = RPT * warp; r0 < F8_BM; r0 += RPT * (F8G_THREADS / 32)) {
+    double d[RPT][4];
+#pragma unroll
+    for (int h = 0; h < RPT; ++h)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) d[h][t] = 0.0;
+#pragma unroll
+    for (int k = 0; k < (WT > 0 ? WT : F8G_MAXW); ++k) {
+      if (k < W) {
+        const double2 t01 = *reinterpret_cast<const double2*>(&xts[k][c0]);
+        const double2 t23 = *reinterpret_cast<const double2*>(&xts[k][c0 + 2]);
+#pragma unroll
+        for (int h = 0; h < RPT; ++h) {
+          const double v = xcs[r0 + h][k];
+          d[h][0] = fma(v, t01.x, d[h][0]);
+          d[h][1] = fma(v, t01.y, d[h][1]);
+          d[h][2] = fma(v, t23.x, d[h][2]);
+          d[h][3] = fma(v, t23.y, d[h][3]);
+        }
+      }
+    }
+    double kv[RPT][4];
+#pragma unroll
+    for (int h = 0; h < RPT; ++h) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        double u = fma(p.square ? d[h][t] * d[h][t] : d[h][t], p.scale, p.shift);
+        u = (u < p.lo) ? p.lo : ((u > p.hi) ? p.hi : u);
+        kv[h][t] = u;
+      }
+    }
+    if (TT > 0) {
+      double sacc[RPT][4];
+#pragma unroll
+      for (int h = 0; h < RPT; ++h)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) sacc[h][t] = cf[TT - 1];
+#pragma unroll
+      for (int k = TT - 2; k >= 0; --k)
+#pragma unroll
+        for (int h = 0; h < RPT; ++h)
+#pragma unroll
+          for (int t = 0; t < 4; ++t) sacc[h][t] = fma(sacc[h][t], kv[h][t], cf[k]);
+#pragma unroll
+      for (int h = 0; h < RPT; ++h)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) kv[h][t] = sacc[h][t];
+    } else {
+#pragma unroll
+      for (int h = 0; h < RPT; ++h)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          double sv = cfs[T - 1];
+          for (int k = T - 2; k >= 0; --k) sv = fma(sv, kv[h][t], cfs[k]);
+          kv[h][t] = sv;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < RPT; ++h) {
+      const int r = r0 + h;
+      const long long i = rb * F8_BM + r;
+      const bool rowok = i < p.m;
+      double mu = 0.0, rr[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const double kval = (rowok && colok[t]) ? kv[h][t] : 0.0;
+        mu = fma(kval, al4[t], mu);
+        rr[t] = kval * down;
+      }
+      mu = warp_sum(mu);
+      if (lane == 0 && rowok) p.meanpart[(long long)kb * p.m_pad + i] = mu;
+      if (kb == 0 && lane == 0) p.ea[i] = e2;
+      int q[F8_S][4];
+#pragma unroll
+      for (int s7 = 0; s7 < F8_S; ++s7) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const double tt = fma(rr[t], (double)(1 << F8_BITS), kMagic);
+          q[s7][t] = __double2loint(tt);
+          rr[t] = fma(rr[t], (double)(1 << F8_BITS), -(tt - kMagic));
+        }
+      }
+#pragma unroll
+      for (int s7 = F8_S - 1; s7 >= 1; --s7) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int c = (q[s7][t] == 128) ? 1 : 0;
+          q[s7][t] -= c << 8;
+          q[s7 - 1][t] += c;
+        }
+      }
+      signed char* dst = tile0 + f8_swizzled(r, lane >> 2);
+#pragma unroll
+      for (int s7 = 0; s7 < F8_S; ++s7) {
+        const unsigned word = ((unsigned)q[s7][0] & 0xffu) | (((unsigned)q[s7][1] & 0xffu) << 8) | (((unsigned)q[s7][2] & 0xffu) << 16) |
+                              (((unsigned)q[s7][3] & 0xffu) << 24);
+        *reinterpret_cast<unsigned*>(dst + s7 * tile_bytes) = word;
+      }
     }
   }
 }
@@ -451,12 +625,18 @@ __global__ void __launch_bounds__(F8_THREADS, 1) f8_posterior_kernel(const F8Par
 }
 
 // var_i = kss - sum over column tiles (fixed order: reproducible)
-__global__ void __launch_bounds__(256) f8_finish_kernel(const double* partial, long long m, long long m_pad, int CT, double kss, double* var) {
+__global__ void __launch_bounds__(256) f8_finish_kernel(const double* partial, long long m, long long m_pad, int CT, double kss, double* var,
+                                                        const double* meanpart, int KB, double mean_const, double* mean) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   double s = 0.0;
   for (int ct = 0; ct < CT; ++ct) s += partial[(long long)ct * m_pad + i];
   var[i] = kss - s;
+  if (meanpart != nullptr) {       // f8_gram_slice_kernel's k-block partial sums of K* alpha
+    double mu = 0.0;
+    for (int kb = 0; kb < KB; ++kb) mu += meanpart[(long long)kb * m_pad + i];
+    mean[i] = mean_const + mu;
+  }
 }
 
 }  // namespace mgb
@@ -504,7 +684,8 @@ struct F8Workspace {
   int* ea;
   signed char* A;
   double* partial;
-  double* krows;      // series entry point only: one sub-block of float64 kernel rows
+  double* meanpart;   // series entry point, fused Gram + slicing: [k-block][m_pad] partial sums of K* alpha
+  double* krows;      // series entry point, two-kernel route: one sub-block of float64 kernel rows
 };
 
 static F8Workspace f8_carve(void* workspace, long long m, const F8Geom& g) {
@@ -516,6 +697,8 @@ static F8Workspace f8_carve(void* workspace, long long m, const F8Geom& g) {
   p += f8_round_up(g.a_bytes(m), 256);
   w.partial = reinterpret_cast<double*>(p);
   p += f8_round_up((long long)g.CT * f8_round_up(m, F8_BM) * 8, 256);
+  w.meanpart = reinterpret_cast<double*>(p);
+  p += f8_round_up((long long)g.KB * f8_round_up(m, F8_BM) * 8, 256);
   w.krows = reinterpret_cast<double*>(p);
   return w;
 }
@@ -531,7 +714,7 @@ static int f8_slice_rows(const double* kstar, long long ldk, long long row0, lon
 
 // slices of m candidates (already in the workspace) x packed factor -> var
 static int f8_contract(long long m, long long n, const F8Geom& g, const F8Workspace& w, const void* packed, double kss, double* var,
-                       int* planes, cudaStream_t s) {
+                       int* planes, cudaStream_t s, const double* meanpart = nullptr, double mean_const = 0.0, double* mean = nullptr) {
   const long long m_pad = f8_round_up(m, F8_BM);
   F8Params P;
   P.A = w.A;
@@ -555,7 +738,7 @@ static int f8_contract(long long m, long long n, const F8Geom& g, const F8Worksp
   const unsigned grid = (unsigned)std::min<long long>(device_sm_count(), live);
   f8_posterior_kernel<<<grid, F8_THREADS, F8_SMEM, s>>>(P);
   MGB_TRY(after_launch("f8_posterior_kernel"));
-  f8_finish_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(w.partial, m, m_pad, g.CT, kss, var);
+  f8_finish_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(w.partial, m, m_pad, g.CT, kss, var, meanpart, g.KB, mean_const, mean);
   return after_launch("f8_finish_kernel");
 }
 
@@ -611,7 +794,17 @@ static long long f8_sub_rows() {
 extern "C" long long mgb_series_posterior_i8f_workspace_bytes(long long m, long long n) {
   if (m < 1 || n < 1) return 0;
   const long long sub = std::min<long long>(f8_sub_rows(), f8_round_up(m, F8_BM));
-  return mgb_posterior_i8f_workspace_bytes(m, n) + sub * n * 8;
+  const F8Geom g = f8_geom(n);
+  return mgb_posterior_i8f_workspace_bytes(m, n) + f8_round_up((long long)g.KB * f8_round_up(m, F8_BM) * 8, 256) + sub * n * 8;
+}
+
+// f8_gram_slice_kernel serves single-factor monomial series of moderate width (MGB_I8F_GRAM=0: two-kernel route)
+static bool f8_gram_fusable(const mgb_series_desc* d) {
+  static const bool enabled = [] {
+    const char* e = std::getenv("MGB_I8F_GRAM");
+    return !(e && e[0] == '0');
+  }();
+  return enabled && d->n_factors == 1 && d->basis == MGB_BASIS_MONOMIAL && d->factor_width <= F8G_MAXW && d->n_terms <= F8G_MAXT;
 }
 
 extern "C" int mgb_series_posterior_i8f(const mgb_series_desc* desc, const double* xc, long long m, long long ldc, const double* xtrain,
@@ -626,6 +819,25 @@ extern "C" int mgb_series_posterior_i8f(const mgb_series_desc* desc, const doubl
   const F8Geom g = f8_geom(n);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const F8Workspace w = f8_carve(workspace, m, g);
+  if (f8_gram_fusable(desc)) {
+    const long long m_pad = f8_round_up(m, F8_BM);
+    F8GramParams q;
+    q.xc = xc; q.m = m; q.ldc = ldc;
+    q.xt = xtrain; q.n = n; q.ldt = ldt;
+    q.coef = coef; q.alpha = alpha;
+    q.W = desc->factor_width; q.T = desc->n_terms; q.square = desc->pair_square;
+    q.scale = desc->scale; q.shift = desc->shift; q.lo = desc->lo; q.hi = desc->hi;
+    q.A = w.A; q.ea = w.ea; q.meanpart = w.meanpart;
+    q.m_pad = m_pad;
+    q.g = g;
+    const dim3 grid((unsigned)g.KB, (unsigned)(m_pad / F8_BM));
+    if (q.W == 11 && q.T == 10) f8_gram_slice_kernel<11, 10><<<grid, F8G_THREADS, 0, s>>>(q);        // S^10
+    else if (q.W == 4 && q.T == 10) f8_gram_slice_kernel<4, 10><<<grid, F8G_THREADS, 0, s>>>(q);     // S^3, SO(3) quaternions
+    else if (q.W == 3 && q.T == 10) f8_gram_slice_kernel<3, 10><<<grid, F8G_THREADS, 0, s>>>(q);     // S^2
+    else f8_gram_slice_kernel<0, 0><<<grid, F8G_THREADS, 0, s>>>(q);
+    MGB_TRY(after_launch("f8_gram_slice_kernel"));
+    return f8_contract(m, n, g, w, packed, kss, var, nullptr, s, w.meanpart, mean_const, mean);
+  }
   const long long sub = std::min<long long>(f8_sub_rows(), f8_round_up(m, F8_BM));
   for (long long r0 = 0; r0 < m; r0 += sub) {
     const long long rows = std::min<long long>(sub, m - r0);
