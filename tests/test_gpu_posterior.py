@@ -580,10 +580,10 @@ def test_int8_path_against_the_oracle_and_truth_at_the_headline_size(noise, impl
     assert np.abs(vg[sel] - vtr).max() <= 1e-10 * vscale
 
 
-@pytest.mark.parametrize("m,n", [(128, 64), (200, 300), (700, 1000), (300, 2100)])
+@pytest.mark.parametrize("m,n", [(128, 64), (200, 300), (700, 1000), (300, 2100), (130, 5000), (129, 8192)])
 def test_fused_int8_kernel_accumulator_planes_are_exact(m, n):
     """csrc/int8_fused.cu through the C-ABI debug entry point: the seven int32 planes C_d = sum_{p+q=d} A_p B_q^T that
-    the tcgen05 kernel leaves in tensor memory, against an int64 matmul of the same slices cut on the host - every entry
+    the tcgen05 kernel leaves in tensor memory, against an exact integer matmul of the same slices cut on the host - every entry
     must be equal (integer arithmetic: bit-exact), for ragged m / n, the triangular k range and the padded rows."""
     import numpy as np
     from materngabo_b200 import _lib
@@ -629,7 +629,8 @@ def test_fused_int8_kernel_accumulator_planes_are_exact(m, n):
     got = planes.view(n_rb, n_ct, 7, 128, 64).cpu().numpy().astype(np.int64)
     for d in range(7):
         want = np.zeros((n_rb * 128, n_ct * 64), dtype=np.int64)
-        want[:m, :n] = sum(A[p] @ B[d - p].T for p in range(d + 1))
+        # float64 BLAS on integer-valued matrices: exact below 2^53 (the int32 accumulators stay below 2^31)
+        want[:m, :n] = np.rint(sum(A[p].astype(np.float64) @ B[d - p].T.astype(np.float64) for p in range(d + 1))).astype(np.int64)
         have = got[:, :, d].transpose(0, 2, 1, 3).reshape(n_rb * 128, n_ct * 64)
         assert np.array_equal(have[:m], want[:m]), "plane %d" % d
     v = ks @ rinv.T
