@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(256) f8_slice_kernel(const double* src, long l
 // Kernel rows straight into slices for single-factor monomial series kernels (sphere S^d, SO(3)): one CTA per
 // (128-candidate row block, 128-column k-block) evaluates K*[i][j] = p(clamp(scale <x_i, t_j>(^2) + shift)) from shared
 // memory panels and writes the block's seven 16 KB slice tiles - the float64 kernel rows never exist in HBM.  All rows
-// share one exponent (|p(u)| <= sum |coef_k| on |u| <= 1; a row far from every training point loses the bits its own
-// maximum would have gained, which the parity bar - relative to the largest variance - does not see).  Per (row, four
+// share one exponent (from sup |p| on [lo, hi]; a row far from every training point loses the bits its own maximum would
+// have gained, which the parity bar - relative to the largest variance - does not see).  Per (row, four
 // columns): W dot-product FMAs per column from a broadcast candidate value and two 16-byte training loads, Horner, then
 // the same digit extraction + carry pass as f8_slice_kernel.  The mean's k-block partial sums go to meanpart[kb][row]
 // (f8_finish_kernel adds them in a fixed order).
@@ -211,8 +211,26 @@ __global__ void __launch_bounds__(F8G_THREADS) f8_gram_slice_kernel(const F8Gram
   }
   __syncthreads();
   double cf[TT > 0 ? TT : 1];
+  // One exponent for every row from sup |p| on [lo, hi]: thread t evaluates p at the t-th of 256 Chebyshev nodes of the
+  // interval, and for a polynomial of degree < 32 the supremum is below max_t |p(u_t)| / cos(pi 31 / 512) (Ehlich -
+  // Zeller), so 1.25 x the sampled maximum is a bound.  (sum |coef_k| would be up to 100 x too large at small
+  // lengthscales - the monomial coefficients cancel - and cost 7 of the 56 bits.)
+  __shared__ double wmax[F8G_THREADS / 32];
+  {
+    const double mid = 0.5 * (p.hi + p.lo), half = 0.5 * (p.hi - p.lo);
+    const double u = fma(half, cospi((threadIdx.x + 0.5) / (double)F8G_THREADS), mid);
+    double sv = cfs[T - 1];
+    for (int k = T - 2; k >= 0; --k) sv = fma(sv, u, cfs[k]);
+    sv = fabs(sv);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sv = fmax(sv, __shfl_xor_sync(0xffffffffu, sv, o));
+    if (lane == 0) wmax[warp] = sv;
+  }
+  __syncthreads();
   double bound = 0.0;
-  for (int k = 0; k < T; ++k) bound += fabs(cfs[k]);
+#pragma unroll
+  for (int w8 = 0; w8 < F8G_THREADS / 32; ++w8) bound = fmax(bound, wmax[w8]);
+  bound *= 1.25;
   if (TT > 0) {
 #pragma unroll
     for (int k = 0; k < TT; ++k) cf[k] = cfs[k];

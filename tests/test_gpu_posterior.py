@@ -636,3 +636,30 @@ def test_fused_int8_kernel_accumulator_planes_are_exact(m, n):
     v = ks @ rinv.T
     assert float((var - (2.5 - (v * v).sum(-1))).abs().max()) < 1e-12 * float((v * v).sum(-1).max())
     assert float((mean - (0.3 + ks @ alpha)).abs().max()) < 1e-12 * (1.0 + float((ks @ alpha).abs().max()))
+
+
+@pytest.mark.parametrize("dim,ls", [(2, 0.1), (3, 0.05), (10, 0.1)])
+def test_fused_int8_path_at_small_lengthscales(dim, ls):
+    """f8_gram_slice_kernel shares one exponent between all rows, taken from sup |p| on [lo, hi]: at small lengthscales the
+    monomial coefficients of the series cancel (sum |coef| is 10 - 100 x the kernel's maximum), which must not cost
+    accuracy - still within 5e-12 of max var of the FP64 kernel."""
+    from materngabo_b200 import kernels_sphere
+    from materngabo_b200.posterior import ExactGPPosterior
+
+    gen = torch.Generator().manual_seed(dim)
+    n, m = 700, 3000
+    xt = torch.nn.functional.normalize(torch.randn(n, dim + 1, generator=gen), dim=-1)
+    xc = torch.nn.functional.normalize(torch.randn(m, dim + 1, generator=gen), dim=-1)
+    xc[:300] = torch.nn.functional.normalize(xt[:300] + 1e-3 * torch.randn(300, dim + 1, generator=gen), dim=-1)
+    y = torch.sin(3 * xt[:, 0])
+    k = kernels_sphere.SphereRiemannianMaternKernel(dim=dim, nu=2.5)
+    k.lengthscale = ls
+    k = k.to(DEV)
+    ref = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.1, noise=1e-3).fit()
+    fast = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.1, noise=1e-3, int8=True).fit()
+    m0, v0 = ref.posterior(xc.to(DEV))
+    m1, v1 = fast.posterior(xc.to(DEV))
+    # 700 points cover S^2 / S^3 densely for a 10-term (finite-rank) kernel: every variance is a cancellation from the
+    # prior variance 1.1 down to ~1e-4, so the scale of the comparison is the prior variance
+    assert float((v1 - v0).abs().max()) < 5e-12 * 1.1
+    assert float((m1 - m0).abs().max() / m0.abs().max()) < 1e-12
