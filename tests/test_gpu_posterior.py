@@ -663,3 +663,36 @@ def test_fused_int8_path_at_small_lengthscales(dim, ls):
     # prior variance 1.1 down to ~1e-4, so the scale of the comparison is the prior variance
     assert float((v1 - v0).abs().max()) < 5e-12 * 1.1
     assert float((m1 - m0).abs().max() / m0.abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("which", ["so3", "torus"])
+def test_fused_int8_path_on_other_series_kernels(which):
+    """mgb_series_posterior_i8f beyond the sphere: SO(3) (single-factor monomial series: kernel rows computed and sliced by
+    f8_gram_slice_kernel, generic width / term count) and the torus T^2 (two Chebyshev factors: Gram kernel + slicing
+    kernel route) against the FP64 tensor-core kernel."""
+    from materngabo_b200 import kernels_so, kernels_torus
+    from materngabo_b200.posterior import ExactGPPosterior
+
+    gen = torch.Generator().manual_seed(11)
+    n, m = 400, 2500
+    if which == "so3":
+        def rot(cnt):
+            q, _ = torch.linalg.qr(torch.randn(cnt, 3, 3, generator=gen, dtype=torch.float64))
+            q[:, :, 0] *= torch.sign(torch.linalg.det(q)).unsqueeze(-1)
+            return q.reshape(cnt, 9)
+        xt, xc = rot(n), rot(m)
+        k = kernels_so.SORiemannianMaternKernel(dim=3, nu=2.5)
+    else:
+        xt = torch.rand(n, 2, generator=gen, dtype=torch.float64) * 6.283185307179586
+        xc = torch.rand(m, 2, generator=gen, dtype=torch.float64) * 6.283185307179586
+        k = kernels_torus.TorusProductOfManifoldsRiemannianMaternKernel(dim=2, nu=2.5)
+    k.lengthscale = 0.6
+    k = k.to(DEV)
+    y = torch.sin(2 * xt[:, 0]) + 0.3 * xt[:, 1]
+    ref = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=0.9, noise=1e-2).fit()
+    fast = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=0.9, noise=1e-2, int8=True).fit()
+    assert fast.is_series
+    m0, v0 = ref.posterior(xc.to(DEV))
+    m1, v1 = fast.posterior(xc.to(DEV))
+    assert float((v1 - v0).abs().max()) < 5e-12 * 0.9
+    assert float((m1 - m0).abs().max()) < 1e-12 * float(m0.abs().max())
