@@ -18,6 +18,8 @@
 // parameter chain (coef as a function of the lengthscale / smoothness) stays in torch autograd, as everywhere else.
 #include "mgb_common.cuh"
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 namespace mgb {
 
@@ -379,6 +381,235 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_kernel(MllParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same marginal likelihood and gradients through the symmetric sweep (Gauss-Jordan on the full n x n matrix in
+// shared memory) instead of Cholesky -> triangular inverse -> U U^T: sweeping pivot k
+//     d = m_kk;   m_kk <- -1/d;   m_ik, m_ki <- m_ik / d;   m_ij <- m_ij - m_ik m_kj / d   (i, j != k)
+// for k = 0 .. n-1 turns Kt into -Kt^-1, the pivots are the squared Cholesky diagonal (log-determinant, positive
+// definiteness flag), and every step is one rank-one update of all n^2 entries, which live in the REGISTERS of the 512
+// threads (thread (warp, lane) owns rows warp + 16 a and columns lane + 32 c): one barrier per pivot, independent FMAs,
+// no triangular dependency chains.  Used for the gradient modes (series and dense) up to n = 128 (RA x CA <= 8 x 4
+// doubles per thread); beyond that and for the fit mode, which must hand out L^-1, series_mll_kernel.
+// ------------------------------------------------------------------------------------------------
+template <int RA, int CA>
+__global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_sweep_kernel(MllParams p) {
+  extern __shared__ __align__(16) double sm[];
+  const int n = p.n;
+  double* M = sm;                 // n x n row-major: -Kt^-1 once the sweeps are done
+  double* xs = M + n * n;         // n * W
+  double* cfs = xs + n * p.W;     // T
+  double* ry = cfs + p.T;         // y - mean
+  double* al = ry + n;            // alpha
+  double* ck = al + n;            // column k before its sweep, two buffers of n + 1 (the last entry: 1 / pivot)
+  double* dg = ck + 2 * (n + 1);  // pivots
+  double* acc = dg + n;           // 4 + T block accumulators
+  __shared__ int bad;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double s = p.hyper[0], noise = p.hyper[1], mean = p.hyper[2];
+
+  for (int e = tid; e < n * p.W; e += MLL_THREADS) xs[e] = p.x[(long long)(e / p.W) * p.ld + (e % p.W)];
+  for (int e = tid; e < p.T; e += MLL_THREADS) cfs[e] = p.coef[e];
+  for (int e = tid; e < n; e += MLL_THREADS) ry[e] = p.y[e] - mean;
+  for (int e = tid; e < 4 + p.T; e += MLL_THREADS) acc[e] = 0.0;
+  if (tid == 0) bad = 0;
+  __syncthreads();
+
+  // ---- 1. Kt in registers: thread (ty = warp, tx = lane) owns the entries (ty + 16 a, tx + 32 c), a < RA, c < CA ------
+  double m[RA][CA];
+#pragma unroll
+  for (int a = 0; a < RA; ++a) {
+#pragma unroll
+    for (int c = 0; c < CA; ++c) {
+      const int i = warp + MLL_WARPS * a, j = lane + 32 * c;
+      double v = 0.0;
+      if (i < n && j < n) {
+        double kij;
+        if (p.Kin != nullptr) {
+          kij = p.Kin[(long long)max(i, j) * p.ldk + min(i, j)];      // the lower triangle is the reference
+        } else {
+          bool inside;
+          const double u = pair_u(p, xs, max(i, j), min(i, j), inside);
+          kij = series_value(p, cfs, u);
+        }
+        v = s * kij + ((i == j) ? noise : 0.0);
+      }
+      m[a][c] = v;
+    }
+  }
+
+  // ---- 2. sweep every pivot.  Row k (= column k, by symmetry) is published through shared memory by the warp that owns
+  // it - all lanes, CA stores each - and gives every thread its column factors m_kj; the row factors m_ik of a thread's
+  // own rows sit in its own warp (lane k % 32) and come by shuffle.  One barrier per pivot (two alternating buffers),
+  // then RA x CA independent FMAs per thread; the pivot row / column are patched afterwards.  The pivot loop is split as
+  // k = 32 kc + 16 kh + kq with kc, kh unrolled, so that the register indices of the pivot column (kc) and pivot row
+  // (2 kc + kh) are compile-time constants - no register selects in the loop body.
+#pragma unroll
+  for (int kc = 0; kc < CA; ++kc) {
+#pragma unroll
+    for (int kh = 0; kh < 2; ++kh) {
+      constexpr int KQ = MLL_WARPS;                     // 16 pivots per (kc, kh): pivot row in warp kq, register row ka
+      const int ka = 2 * kc + kh;
+      if (ka < RA) {
+        for (int kq = 0; kq < KQ; ++kq) {
+          const int k = 32 * kc + 16 * kh + kq;
+          if (k >= n) break;
+          const int kl = k & 31;
+          double* cb = ck + (k & 1) * (n + 1);
+          if (warp == kq) {
+#pragma unroll
+            for (int c = 0; c < CA; ++c) {
+              const int j = lane + 32 * c;
+              if (j < n) cb[j] = m[ka][c];
+            }
+          }
+          __syncthreads();
+          const double d = cb[k];
+          if (tid == 0) {
+            dg[k] = d;
+            if (!(d > 0.0) && bad == 0) bad = k + 1;    // not positive definite: flagged, NaN / garbage propagates
+          }
+          const double dinv = 1.0 / d;
+          double cj[CA];
+#pragma unroll
+          for (int c = 0; c < CA; ++c) {
+            const int j = lane + 32 * c;
+            cj[c] = (j < n) ? cb[j] : 0.0;
+          }
+#pragma unroll
+          for (int a = 0; a < RA; ++a) {
+            const double f = __shfl_sync(0xffffffffu, m[a][kc], kl) * dinv;      // m_ik / d for the thread's row i
+#pragma unroll
+            for (int c = 0; c < CA; ++c) m[a][c] = fma(-f, cj[c], m[a][c]);
+            if (lane == kl) m[a][kc] = f;                                          // pivot column
+          }
+          if (warp == kq) {                                                        // pivot row
+#pragma unroll
+            for (int c = 0; c < CA; ++c) m[ka][c] = cj[c] * dinv;
+            if (lane == kl) m[ka][kc] = -dinv;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < RA; ++a) {
+#pragma unroll
+    for (int c = 0; c < CA; ++c) {
+      const int i = warp + MLL_WARPS * a, j = lane + 32 * c;
+      if (i < n && j < n) M[i * n + j] = m[a][c];
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. alpha = Kt^-1 ry = -(M ry), quadratic form, log-determinant, dnll/dmean ---------------------------
+  {
+    double quad = 0.0, gmean = 0.0, logdet = 0.0;
+    for (int i = warp; i < n; i += MLL_WARPS) {
+      const double* row = M + i * n;
+      double a = 0.0;
+      for (int j = lane; j < n; j += 32) a = fma(row[j], ry[j], a);
+      a = -warp_sum(a);
+      if (lane == 0) {
+        al[i] = a;
+        quad = fma(ry[i], a, quad);
+        gmean -= a;
+        logdet += 0.5 * log(dg[i]);          // pivot = L_ii^2
+      }
+    }
+    if (lane == 0) {
+      atomicAdd(acc + 0, 0.5 * quad + logdet);
+      atomicAdd(acc + 3, gmean);
+    }
+  }
+  __syncthreads();
+  // weights w_ij = (i == j ? 1/2 : 1) (Kt^-1_ij - alpha_i alpha_j), j <= i, straight from M
+  auto weight = [&](int i, int j) { return ((i == j) ? 0.5 : 1.0) * (-M[i * n + j] - al[i] * al[j]); };
+
+  if (p.Kin != nullptr) {
+    // ---- dense mode: G = dnll/dKin = s/2 (Kt^-1 - alpha alpha^T) as a full symmetric matrix; dnll/ds, dnll/dnoise
+    double gs = 0.0, gn = 0.0;
+    for (int i = warp; i < n; i += MLL_WARPS) {
+      for (int j = lane; j <= i; j += 32) {
+        const double w = weight(i, j);
+        gs = fma(w, p.Kin[(long long)i * p.ldk + j], gs);
+        if (i == j) gn += w;
+        const double g = s * ((i == j) ? w : 0.5 * w);
+        p.Gout[(long long)i * p.ldg + j] = g;
+        p.Gout[(long long)j * p.ldg + i] = g;
+      }
+    }
+    gs = warp_sum(gs);
+    gn = warp_sum(gn);
+    if (lane == 0) {
+      atomicAdd(acc + 1, gs);
+      atomicAdd(acc + 2, gn);
+    }
+    __syncthreads();
+    for (int e = tid; e < 4; e += MLL_THREADS) p.out[e] = acc[e] + ((e == 0) ? 0.5 * n * 1.8378770664093453 : 0.0);
+    if (tid == 0 && p.status) *p.status = bad;
+    return;
+  }
+
+  // ---- series mode: gradient reductions over the pairs --------------------------------------------------
+  for (int c0 = 0; c0 < p.T; c0 += MLL_TCHUNK) {
+    double gk[MLL_TCHUNK];
+#pragma unroll
+    for (int q = 0; q < MLL_TCHUNK; ++q) gk[q] = 0.0;
+    double gs = 0.0, gn = 0.0;
+    for (int i = warp; i < n; i += MLL_WARPS) {
+      for (int j = lane; j <= i; j += 32) {
+        const double w = weight(i, j);
+        bool inside;
+        const double u = pair_u(p, xs, i, j, inside);
+        if (c0 == 0) {
+          gs = fma(w, series_value(p, cfs, u), gs);
+          if (i == j) gn += w;
+        }
+        if (p.basis == MGB_BASIS_MONOMIAL) {
+          double pw = 1.0;
+          for (int k = 0; k < c0; ++k) pw *= u;
+#pragma unroll
+          for (int q = 0; q < MLL_TCHUNK; ++q) {
+            if (c0 + q < p.T) gk[q] = fma(w, pw, gk[q]);
+            pw *= u;
+          }
+        } else {
+          double t0 = 1.0, t1 = u;
+          for (int k = 0; k < c0; ++k) {
+            const double t2 = fma(2.0 * u, t1, -t0);
+            t0 = t1;
+            t1 = t2;
+          }
+#pragma unroll
+          for (int q = 0; q < MLL_TCHUNK; ++q) {
+            if (c0 + q < p.T) gk[q] = fma(w, t0, gk[q]);
+            const double t2 = fma(2.0 * u, t1, -t0);
+            t0 = t1;
+            t1 = t2;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < MLL_TCHUNK; ++q) {
+      const double v = warp_sum(gk[q]);
+      if (lane == 0 && c0 + q < p.T) atomicAdd(acc + 4 + c0 + q, s * v);
+    }
+    if (c0 == 0) {
+      gs = warp_sum(gs);
+      gn = warp_sum(gn);
+      if (lane == 0) {
+        atomicAdd(acc + 1, gs);
+        atomicAdd(acc + 2, gn);
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 4 + p.T; e += MLL_THREADS)
+    p.out[e] = acc[e] + ((e == 0) ? 0.5 * n * 1.8378770664093453 : 0.0);   // + n/2 log(2 pi)
+  if (tid == 0 && p.status) *p.status = bad;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Spectral coefficients of the sphere / SO(3) series kernels and their Jacobian in ONE launch.
 //   a_n   = c_n f(lambda_n; kappa, nu),   f = ((b + lambda) / b)^-(nu + h), b = 2 nu / kappa^2   (Matern, mode 0)
 //                                         f = exp(-kappa^2 lambda / 2)                            (heat, mode 1)
@@ -657,6 +888,32 @@ extern "C" long long mgb_series_mll_single_cta_max_n(int factor_width, int n_ter
   return 0;
 }
 
+// gradient modes: the sweep kernel (MGB_MLL_PATH=chol: the Cholesky-based kernel, kept for comparison)
+static int launch_mll_grad(const MllParams& p, size_t smem, cudaStream_t s, const char* what) {
+  static const bool chol = [] {
+    const char* e = getenv("MGB_MLL_PATH");
+    return e && strcmp(e, "chol") == 0;
+  }();
+  if (chol || p.n > 128) {
+    if (smem > 48 * 1024)
+      MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
+    series_mll_kernel<<<1, MLL_THREADS, smem, s>>>(p);
+  } else if (p.n <= 64) {
+    if (smem > 48 * 1024)
+      MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_sweep_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
+    series_mll_sweep_kernel<4, 2><<<1, MLL_THREADS, smem, s>>>(p);
+  } else if (p.n <= 96) {
+    if (smem > 48 * 1024)
+      MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_sweep_kernel<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
+    series_mll_sweep_kernel<6, 3><<<1, MLL_THREADS, smem, s>>>(p);
+  } else {
+    if (smem > 48 * 1024)
+      MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_sweep_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
+    series_mll_sweep_kernel<8, 4><<<1, MLL_THREADS, smem, s>>>(p);
+  }
+  return after_launch(what);
+}
+
 extern "C" int mgb_series_mll(const mgb_series_desc* d, const double* x, long long n, long long ld, const double* y,
                               const double* coef, const double* hyper, double* out, int* status, void* stream) {
   if (!d || !x || !y || !coef || !hyper || !out) return fail(MGB_ERR_ARG, "series_mll: null pointer");
@@ -670,11 +927,7 @@ extern "C" int mgb_series_mll(const mgb_series_desc* d, const double* x, long lo
   MllParams p{x, (int)n, ld, y, coef, hyper, out, status, d->factor_width, d->n_terms, d->basis,
               d->scale, d->shift, d->lo, d->hi, nullptr, nullptr, nullptr, 0};
   const size_t smem = sizeof(double) * (size_t)(n * (n + 1) + n * d->factor_width + d->n_terms + 5 * n + 4 + d->n_terms);
-  if (smem > 48 * 1024)
-    MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                       "cudaFuncSetAttribute"));
-  series_mll_kernel<<<1, MLL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
-  return after_launch("series_mll_kernel");
+  return launch_mll_grad(p, smem, static_cast<cudaStream_t>(stream), "series_mll kernel");
 }
 
 extern "C" int mgb_dense_mll(const double* K, long long n, long long ldk, const double* y, const double* hyper, double* out,
@@ -686,11 +939,7 @@ extern "C" int mgb_dense_mll(const double* K, long long n, long long ldk, const 
   p.n = (int)n; p.y = y; p.hyper = hyper; p.out = out; p.status = status;
   p.Kin = K; p.ldk = ldk; p.Gout = G; p.ldg = ldg;
   const size_t smem = sizeof(double) * (size_t)(n * (n + 1) + 5 * n + 4);
-  if (smem > 48 * 1024)
-    MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                       "cudaFuncSetAttribute"));
-  series_mll_kernel<<<1, MLL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
-  return after_launch("series_mll_kernel (dense)");
+  return launch_mll_grad(p, smem, static_cast<cudaStream_t>(stream), "series_mll kernel (dense)");
 }
 
 extern "C" int mgb_circle_coef(int mode, int n_terms, const double* t, const double* tw, int P, const double* kappa,
