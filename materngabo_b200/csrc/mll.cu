@@ -399,8 +399,8 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_sweep_kernel(MllPar
   double* cfs = xs + n * p.W;     // T
   double* ry = cfs + p.T;         // y - mean
   double* al = ry + n;            // alpha
-  double* ck = al + n;            // column k before its sweep, two buffers of n + 1 (the last entry: 1 / pivot)
-  double* dg = ck + 2 * (n + 1);  // pivots
+  double* ck = al + n;            // row k before its sweep: two buffers of 32 CA doubles (zero beyond n)
+  double* dg = ck + 2 * 32 * CA;  // pivots
   double* acc = dg + n;           // 4 + T block accumulators
   __shared__ int bad;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -410,6 +410,7 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_sweep_kernel(MllPar
   for (int e = tid; e < p.T; e += MLL_THREADS) cfs[e] = p.coef[e];
   for (int e = tid; e < n; e += MLL_THREADS) ry[e] = p.y[e] - mean;
   for (int e = tid; e < 4 + p.T; e += MLL_THREADS) acc[e] = 0.0;
+  for (int e = tid; e < 2 * 32 * CA; e += MLL_THREADS) ck[e] = 0.0;
   if (tid == 0) bad = 0;
   __syncthreads();
 
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_sweep_kernel(MllPar
           const int k = 32 * kc + 16 * kh + kq;
           if (k >= n) break;
           const int kl = k & 31;
-          double* cb = ck + (k & 1) * (n + 1);
+          double* cb = ck + (k & 1) * (32 * CA);
           if (warp == kq) {
 #pragma unroll
             for (int c = 0; c < CA; ++c) {
@@ -470,10 +471,7 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_sweep_kernel(MllPar
           const double dinv = 1.0 / d;
           double cj[CA];
 #pragma unroll
-          for (int c = 0; c < CA; ++c) {
-            const int j = lane + 32 * c;
-            cj[c] = (j < n) ? cb[j] : 0.0;
-          }
+          for (int c = 0; c < CA; ++c) cj[c] = cb[lane + 32 * c];                 // zero beyond n
 #pragma unroll
           for (int a = 0; a < RA; ++a) {
             const double f = __shfl_sync(0xffffffffu, m[a][kc], kl) * dinv;      // m_ik / d for the thread's row i
@@ -889,6 +887,17 @@ extern "C" long long mgb_series_mll_single_cta_max_n(int factor_width, int n_ter
 }
 
 // gradient modes: the sweep kernel (MGB_MLL_PATH=chol: the Cholesky-based kernel, kept for comparison)
+template <int RA, int CA>
+static int launch_sweep(const MllParams& p, cudaStream_t s) {
+  const size_t n = (size_t)p.n;
+  const size_t smem = sizeof(double) * (n * n + n * p.W + p.T + 3 * n + 2 * 32 * CA + 4 + p.T);
+  if (smem > 48 * 1024)
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_sweep_kernel<RA, CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute"));
+  series_mll_sweep_kernel<RA, CA><<<1, MLL_THREADS, smem, s>>>(p);
+  return MGB_OK;
+}
+
 static int launch_mll_grad(const MllParams& p, size_t smem, cudaStream_t s, const char* what) {
   static const bool chol = [] {
     const char* e = getenv("MGB_MLL_PATH");
@@ -898,18 +907,18 @@ static int launch_mll_grad(const MllParams& p, size_t smem, cudaStream_t s, cons
     if (smem > 48 * 1024)
       MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
     series_mll_kernel<<<1, MLL_THREADS, smem, s>>>(p);
+  } else if (p.n <= 32) {
+    MGB_TRY((launch_sweep<2, 1>(p, s)));
   } else if (p.n <= 64) {
-    if (smem > 48 * 1024)
-      MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_sweep_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
-    series_mll_sweep_kernel<4, 2><<<1, MLL_THREADS, smem, s>>>(p);
+    MGB_TRY((launch_sweep<4, 2>(p, s)));
+  } else if (p.n <= 80) {
+    MGB_TRY((launch_sweep<5, 3>(p, s)));
   } else if (p.n <= 96) {
-    if (smem > 48 * 1024)
-      MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_sweep_kernel<6, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
-    series_mll_sweep_kernel<6, 3><<<1, MLL_THREADS, smem, s>>>(p);
+    MGB_TRY((launch_sweep<6, 3>(p, s)));
+  } else if (p.n <= 112) {
+    MGB_TRY((launch_sweep<7, 4>(p, s)));
   } else {
-    if (smem > 48 * 1024)
-      MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_sweep_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"));
-    series_mll_sweep_kernel<8, 4><<<1, MLL_THREADS, smem, s>>>(p);
+    MGB_TRY((launch_sweep<8, 4>(p, s)));
   }
   return after_launch(what);
 }
