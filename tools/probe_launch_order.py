@@ -1,4 +1,4 @@
-"""Ordered device launches of one MLL step (N = 100) on a chosen manifold: python tools/probe_launch_order.py torus|spd2|h2"""
+"""Ordered device launches of one MLL step (N = 100) on a chosen manifold: python tools/probe_launch_order.py sphere|torus|spd2|h2"""
 import os
 import sys
 
@@ -6,7 +6,7 @@ sys.path.insert(0, os.getcwd())
 import torch
 
 torch.set_default_dtype(torch.float64)
-from materngabo_b200 import kernels_hyperbolic as kh, kernels_spd as ksp, kernels_torus as kt
+from materngabo_b200 import kernels_hyperbolic as kh, kernels_spd as ksp, kernels_sphere as ks, kernels_torus as kt
 from materngabo_b200.gpytorch_compat import ScaleKernel
 from materngabo_b200.graphs import exact_mll
 from torch.profiler import ProfilerActivity, profile
@@ -14,7 +14,9 @@ from torch.profiler import ProfilerActivity, profile
 which = sys.argv[1] if len(sys.argv) > 1 else "torus"
 gen = torch.Generator().manual_seed(0)
 n = 100
-if which == "torus":
+if which == "sphere":
+    base, x = ks.SphereRiemannianMaternKernel(dim=3, nu=2.5), torch.nn.functional.normalize(torch.randn(n, 4, generator=gen), dim=-1)
+elif which == "torus":
     base, x = kt.TorusProductOfManifoldsRiemannianMaternKernel(dim=3, nu=2.5), torch.rand(n, 3, generator=gen) * 6.28
 elif which == "spd2":
     a = torch.randn(n, 2, 2, generator=gen)
