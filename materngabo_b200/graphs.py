@@ -104,6 +104,25 @@ def _scalar(v, like):
     return torch.full((), float(v), dtype=F64, device=like.device)
 
 
+_CONST_TAILS = {}
+
+
+def _hyper(scale, noise, mean_const, jitter, like):
+    """[outputscale, noise + jitter, mean] as one float64 device vector for the MLL kernels.  When noise and mean are plain
+    numbers their pair is built once per (values, device) and reused (no fill / add / stack launches per evaluation; the
+    first call happens in the warm-up before a graph capture)."""
+    if not torch.is_tensor(noise) and not torch.is_tensor(mean_const):
+        key = (float(noise) + float(jitter), float(mean_const), str(like.device))
+        tail = _CONST_TAILS.get(key)
+        if tail is None:
+            if len(_CONST_TAILS) > 256:
+                _CONST_TAILS.clear()
+            tail = torch.tensor([key[0], key[1]], dtype=F64).to(like.device)
+            _CONST_TAILS[key] = tail
+        return torch.cat([_scalar(scale, like).reshape(1), tail])
+    return torch.stack([_scalar(scale, like), _scalar(noise, like) + jitter, _scalar(mean_const, like)])
+
+
 def _fused_mll(kernel, x, y, noise, mean_const, jitter):
     """(loss, info) through the single-CTA kernel csrc/mll.cu, or None when the problem does not qualify
     (not a single-factor series kernel, active_dims, batch dimensions, n above the shared-memory limit)."""
@@ -125,7 +144,7 @@ def _fused_mll(kernel, x, y, noise, mean_const, jitter):
         return None
     if x.shape[0] > _ops.dense_large_max_n():
         return None
-    hyper = torch.stack([_scalar(scale, x), _scalar(noise, x) + jitter, _scalar(mean_const, x)])
+    hyper = _hyper(scale, noise, mean_const, jitter, x)
     nll, info = _ops.series_mll(spec, x, y, coef, hyper)
     return nll / x.shape[0], info
 
@@ -143,7 +162,7 @@ def _dense_mll(kernel, x, y, noise, mean_const, jitter):
     k = base(x, x)
     if not torch.is_tensor(k):          # gpytorch lazy tensors
         k = k.to_dense() if hasattr(k, "to_dense") else k.evaluate()
-    hyper = torch.stack([_scalar(scale, x), _scalar(noise, x) + jitter, _scalar(mean_const, x)])
+    hyper = _hyper(scale, noise, mean_const, jitter, x)
     nll, info = _ops.dense_mll(k, y, hyper)
     return nll / x.shape[0], info
 
