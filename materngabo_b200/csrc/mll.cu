@@ -386,20 +386,20 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_kernel(MllParams p)
 //     d = m_kk;   m_kk <- -1/d;   m_ik, m_ki <- m_ik / d;   m_ij <- m_ij - m_ik m_kj / d   (i, j != k)
 // for k = 0 .. n-1 turns Kt into -Kt^-1, the pivots are the squared Cholesky diagonal (log-determinant, positive
 // definiteness flag), and every step is one rank-one update of all n^2 entries, which live in the REGISTERS of the 512
-// threads (thread (warp, lane) owns rows warp + 16 a and columns lane + 32 c): one barrier per pivot, independent FMAs,
-// no triangular dependency chains.  Used for the gradient modes (series and dense) up to n = 128 (RA x CA <= 8 x 4
+// threads (thread (warp, lane) owns rows warp + 16 a and columns lane + 32 c) from the Gram evaluation to the gradient
+// contractions - there is no n x n array in shared memory: one barrier per pivot, independent FMAs, no triangular
+// dependency chains.  Used for the gradient modes (series and dense) up to n = 128 (RA x CA <= 8 x 4
 // doubles per thread); beyond that and for the fit mode, which must hand out L^-1, series_mll_kernel.
 // ------------------------------------------------------------------------------------------------
-template <int RA, int CA>
+template <int RA, int CA, bool SERIES>
 __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_sweep_kernel(MllParams p) {
   extern __shared__ __align__(16) double sm[];
   const int n = p.n;
-  double* M = sm;                 // n x n row-major: -Kt^-1 once the sweeps are done
-  double* xs = M + n * n;         // n * W
+  double* xs = sm;                // n * W
   double* cfs = xs + n * p.W;     // T
-  double* ry = cfs + p.T;         // y - mean
-  double* al = ry + n;            // alpha
-  double* ck = al + n;            // row k before its sweep: two buffers of 32 CA doubles (zero beyond n)
+  double* ry = cfs + p.T;         // y - mean, zero up to 32 CA
+  double* al = ry + 32 * CA;      // alpha, zero up to max(16 RA, 32 CA) = 32 CA
+  double* ck = al + 32 * CA;      // row k before its sweep: two buffers of 32 CA doubles (zero beyond n)
   double* dg = ck + 2 * 32 * CA;  // pivots
   double* acc = dg + n;           // 4 + T block accumulators
   __shared__ int bad;
@@ -408,32 +408,68 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_sweep_kernel(MllPar
 
   for (int e = tid; e < n * p.W; e += MLL_THREADS) xs[e] = p.x[(long long)(e / p.W) * p.ld + (e % p.W)];
   for (int e = tid; e < p.T; e += MLL_THREADS) cfs[e] = p.coef[e];
-  for (int e = tid; e < n; e += MLL_THREADS) ry[e] = p.y[e] - mean;
+  for (int e = tid; e < 32 * CA; e += MLL_THREADS) {
+    ry[e] = (e < n) ? p.y[e] - mean : 0.0;
+    al[e] = 0.0;
+  }
   for (int e = tid; e < 4 + p.T; e += MLL_THREADS) acc[e] = 0.0;
   for (int e = tid; e < 2 * 32 * CA; e += MLL_THREADS) ck[e] = 0.0;
   if (tid == 0) bad = 0;
   __syncthreads();
 
-  // ---- 1. Kt in registers: thread (ty = warp, tx = lane) owns the entries (ty + 16 a, tx + 32 c), a < RA, c < CA ------
+  // Thread (warp, lane) owns the entries (i_a, j_c) = (warp + 16 a, lane + 32 c), a < RA, c < CA, of the FULL symmetric
+  // matrix, in registers for the whole kernel.  Pair scalars u_ij of a register row: W broadcast loads of x_i against
+  // CA loads of x_j (rows clamped to n - 1: those entries are masked out afterwards).
+  constexpr bool series = SERIES;                 // false: dense mode (p.Kin != nullptr)
+  const bool mono = (p.basis == MGB_BASIS_MONOMIAL);
+  auto row_u = [&](int a, double (&u)[CA]) {
+    const int i = min(warp + MLL_WARPS * a, n - 1);
+#pragma unroll
+    for (int c = 0; c < CA; ++c) u[c] = 0.0;
+    for (int k = 0; k < p.W; ++k) {
+      const double xi = xs[i * p.W + k];
+#pragma unroll
+      for (int c = 0; c < CA; ++c) u[c] = fma(xi, xs[min(lane + 32 * c, n - 1) * p.W + k], u[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < CA; ++c) {
+      const double raw = fma(u[c], p.scale, p.shift);
+      u[c] = (raw < p.lo) ? p.lo : ((raw > p.hi) ? p.hi : raw);
+    }
+  };
+
+  // ---- 1. Kt ----------------------------------------------------------------------------------------------
   double m[RA][CA];
 #pragma unroll
   for (int a = 0; a < RA; ++a) {
+    const int i = warp + MLL_WARPS * a;
+    double kv[CA];
+    if (series) {
+      double u[CA];
+      row_u(a, u);
+      if (mono) {
+#pragma unroll
+        for (int c = 0; c < CA; ++c) kv[c] = cfs[p.T - 1];
+        for (int k = p.T - 2; k >= 0; --k) {
+          const double ckf = cfs[k];
+#pragma unroll
+          for (int c = 0; c < CA; ++c) kv[c] = fma(kv[c], u[c], ckf);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CA; ++c) kv[c] = series_value(p, cfs, u[c]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CA; ++c) {
+        const int j = lane + 32 * c;
+        kv[c] = (i < n && j < n) ? p.Kin[(long long)max(i, j) * p.ldk + min(i, j)] : 0.0;      // the lower triangle is the reference
+      }
+    }
 #pragma unroll
     for (int c = 0; c < CA; ++c) {
-      const int i = warp + MLL_WARPS * a, j = lane + 32 * c;
-      double v = 0.0;
-      if (i < n && j < n) {
-        double kij;
-        if (p.Kin != nullptr) {
-          kij = p.Kin[(long long)max(i, j) * p.ldk + min(i, j)];      // the lower triangle is the reference
-        } else {
-          bool inside;
-          const double u = pair_u(p, xs, max(i, j), min(i, j), inside);
-          kij = series_value(p, cfs, u);
-        }
-        v = s * kij + ((i == j) ? noise : 0.0);
-      }
-      m[a][c] = v;
+      const int j = lane + 32 * c;
+      m[a][c] = (i < n && j < n) ? s * kv[c] + ((i == j) ? noise : 0.0) : 0.0;
     }
   }
 
@@ -488,51 +524,56 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_sweep_kernel(MllPar
       }
     }
   }
-#pragma unroll
-  for (int a = 0; a < RA; ++a) {
-#pragma unroll
-    for (int c = 0; c < CA; ++c) {
-      const int i = warp + MLL_WARPS * a, j = lane + 32 * c;
-      if (i < n && j < n) M[i * n + j] = m[a][c];
-    }
-  }
-  __syncthreads();
 
-  // ---- 3. alpha = Kt^-1 ry = -(M ry), quadratic form, log-determinant, dnll/dmean ---------------------------
+  // ---- 3. alpha = Kt^-1 ry = -(M ry) from the registers, quadratic form, log-determinant, dnll/dmean -------------
   {
-    double quad = 0.0, gmean = 0.0, logdet = 0.0;
-    for (int i = warp; i < n; i += MLL_WARPS) {
-      const double* row = M + i * n;
-      double a = 0.0;
-      for (int j = lane; j < n; j += 32) a = fma(row[j], ry[j], a);
-      a = -warp_sum(a);
-      if (lane == 0) {
-        al[i] = a;
-        quad = fma(ry[i], a, quad);
-        gmean -= a;
-        logdet += 0.5 * log(dg[i]);          // pivot = L_ii^2
+    double ryj[CA];
+#pragma unroll
+    for (int c = 0; c < CA; ++c) ryj[c] = ry[lane + 32 * c];
+    double quad = 0.0, gmean = 0.0;
+#pragma unroll
+    for (int a = 0; a < RA; ++a) {
+      const int i = warp + MLL_WARPS * a;
+      double part = 0.0;
+#pragma unroll
+      for (int c = 0; c < CA; ++c) part = fma(m[a][c], ryj[c], part);
+      part = -warp_sum(part);
+      if (lane == 0 && i < n) {
+        al[i] = part;
+        quad = fma(ry[i], part, quad);
+        gmean -= part;
       }
     }
+    double logdet = (tid < n) ? 0.5 * log(dg[tid]) : 0.0;          // pivot = L_ii^2
+    logdet = warp_sum(logdet);
     if (lane == 0) {
       atomicAdd(acc + 0, 0.5 * quad + logdet);
       atomicAdd(acc + 3, gmean);
     }
   }
   __syncthreads();
-  // weights w_ij = (i == j ? 1/2 : 1) (Kt^-1_ij - alpha_i alpha_j), j <= i, straight from M
-  auto weight = [&](int i, int j) { return ((i == j) ? 0.5 : 1.0) * (-M[i * n + j] - al[i] * al[j]); };
+  // weights over the FULL matrix: wf_ij = 1/2 (Kt^-1_ij - alpha_i alpha_j); sum over all (i, j) = the lower-triangle sum
+  // with the diagonal halved
+  double alj[CA];
+#pragma unroll
+  for (int c = 0; c < CA; ++c) alj[c] = al[lane + 32 * c];
 
-  if (p.Kin != nullptr) {
-    // ---- dense mode: G = dnll/dKin = s/2 (Kt^-1 - alpha alpha^T) as a full symmetric matrix; dnll/ds, dnll/dnoise
+  if constexpr (!series) {
+    // ---- dense mode: G = dnll/dKin = s wf as a full symmetric matrix; dnll/ds = sum wf Kin, dnll/dnoise = tr wf
     double gs = 0.0, gn = 0.0;
-    for (int i = warp; i < n; i += MLL_WARPS) {
-      for (int j = lane; j <= i; j += 32) {
-        const double w = weight(i, j);
-        gs = fma(w, p.Kin[(long long)i * p.ldk + j], gs);
-        if (i == j) gn += w;
-        const double g = s * ((i == j) ? w : 0.5 * w);
-        p.Gout[(long long)i * p.ldg + j] = g;
-        p.Gout[(long long)j * p.ldg + i] = g;
+#pragma unroll
+    for (int a = 0; a < RA; ++a) {
+      const int i = warp + MLL_WARPS * a;
+      const double ali = al[min(i, 32 * CA - 1)];
+#pragma unroll
+      for (int c = 0; c < CA; ++c) {
+        const int j = lane + 32 * c;
+        if (i < n && j < n) {
+          const double wf = 0.5 * (-m[a][c] - ali * alj[c]);
+          gs = fma(wf, p.Kin[(long long)max(i, j) * p.ldk + min(i, j)], gs);
+          if (i == j) gn += wf;
+          p.Gout[(long long)i * p.ldg + j] = s * wf;
+        }
       }
     }
     gs = warp_sum(gs);
@@ -545,42 +586,78 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_sweep_kernel(MllPar
     for (int e = tid; e < 4; e += MLL_THREADS) p.out[e] = acc[e] + ((e == 0) ? 0.5 * n * 1.8378770664093453 : 0.0);
     if (tid == 0 && p.status) *p.status = bad;
     return;
-  }
+  } else {
 
-  // ---- series mode: gradient reductions over the pairs --------------------------------------------------
-  for (int c0 = 0; c0 < p.T; c0 += MLL_TCHUNK) {
-    double gk[MLL_TCHUNK];
+  // ---- series mode: dnll/dcoef_k = s sum wf phi_k(u), dnll/ds = sum wf K, dnll/dnoise = tr wf, one register row at a time
+  constexpr int SWCH = 8;                         // coefficient gradients per pass (register budget)
+  for (int c0 = 0; c0 < p.T; c0 += SWCH) {
+    double gk[SWCH];
 #pragma unroll
-    for (int q = 0; q < MLL_TCHUNK; ++q) gk[q] = 0.0;
+    for (int q = 0; q < SWCH; ++q) gk[q] = 0.0;
     double gs = 0.0, gn = 0.0;
-    for (int i = warp; i < n; i += MLL_WARPS) {
-      for (int j = lane; j <= i; j += 32) {
-        const double w = weight(i, j);
-        bool inside;
-        const double u = pair_u(p, xs, i, j, inside);
-        if (c0 == 0) {
-          gs = fma(w, series_value(p, cfs, u), gs);
-          if (i == j) gn += w;
-        }
-        if (p.basis == MGB_BASIS_MONOMIAL) {
-          double pw = 1.0;
-          for (int k = 0; k < c0; ++k) pw *= u;
 #pragma unroll
-          for (int q = 0; q < MLL_TCHUNK; ++q) {
-            if (c0 + q < p.T) gk[q] = fma(w, pw, gk[q]);
-            pw *= u;
+    for (int a = 0; a < RA; ++a) {
+      const int i = warp + MLL_WARPS * a;
+      const double ali = al[min(i, 32 * CA - 1)];
+      double u[CA], wf[CA];
+      row_u(a, u);
+#pragma unroll
+      for (int c = 0; c < CA; ++c) {
+        const int j = lane + 32 * c;
+        wf[c] = (i < n && j < n) ? 0.5 * (-m[a][c] - ali * alj[c]) : 0.0;
+        if (c0 == 0 && i == j) gn += wf[c];
+      }
+      if (mono) {
+        double pw[CA], val[CA];
+#pragma unroll
+        for (int c = 0; c < CA; ++c) {
+          pw[c] = 1.0;
+          val[c] = 0.0;
+        }
+        if (c0 == 0) {                      // K_ij = sum_k coef_k u^k rides along with the powers of the first chunk
+          for (int k = 0; k < p.T; ++k) {
+            const double ckf = cfs[k];
+#pragma unroll
+            for (int c = 0; c < CA; ++c) {
+              val[c] = fma(ckf, pw[c], val[c]);
+              pw[c] *= u[c];
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < CA; ++c) {
+            gs = fma(wf[c], val[c], gs);
+            pw[c] = 1.0;
           }
         } else {
-          double t0 = 1.0, t1 = u;
           for (int k = 0; k < c0; ++k) {
-            const double t2 = fma(2.0 * u, t1, -t0);
+#pragma unroll
+            for (int c = 0; c < CA; ++c) pw[c] *= u[c];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < SWCH; ++q) {
+          if (c0 + q < p.T) {
+#pragma unroll
+            for (int c = 0; c < CA; ++c) {
+              gk[q] = fma(wf[c], pw[c], gk[q]);
+              pw[c] *= u[c];
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CA; ++c) {
+          if (c0 == 0) gs = fma(wf[c], series_value(p, cfs, u[c]), gs);
+          double t0 = 1.0, t1 = u[c];
+          for (int k = 0; k < c0; ++k) {
+            const double t2 = fma(2.0 * u[c], t1, -t0);
             t0 = t1;
             t1 = t2;
           }
 #pragma unroll
-          for (int q = 0; q < MLL_TCHUNK; ++q) {
-            if (c0 + q < p.T) gk[q] = fma(w, t0, gk[q]);
-            const double t2 = fma(2.0 * u, t1, -t0);
+          for (int q = 0; q < SWCH; ++q) {
+            if (c0 + q < p.T) gk[q] = fma(wf[c], t0, gk[q]);
+            const double t2 = fma(2.0 * u[c], t1, -t0);
             t0 = t1;
             t1 = t2;
           }
@@ -588,7 +665,7 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_sweep_kernel(MllPar
       }
     }
 #pragma unroll
-    for (int q = 0; q < MLL_TCHUNK; ++q) {
+    for (int q = 0; q < SWCH; ++q) {
       const double v = warp_sum(gk[q]);
       if (lane == 0 && c0 + q < p.T) atomicAdd(acc + 4 + c0 + q, s * v);
     }
@@ -605,6 +682,7 @@ __global__ void __launch_bounds__(MLL_THREADS, 1) series_mll_sweep_kernel(MllPar
   for (int e = tid; e < 4 + p.T; e += MLL_THREADS)
     p.out[e] = acc[e] + ((e == 0) ? 0.5 * n * 1.8378770664093453 : 0.0);   // + n/2 log(2 pi)
   if (tid == 0 && p.status) *p.status = bad;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -887,15 +965,20 @@ extern "C" long long mgb_series_mll_single_cta_max_n(int factor_width, int n_ter
 }
 
 // gradient modes: the sweep kernel (MGB_MLL_PATH=chol: the Cholesky-based kernel, kept for comparison)
+template <int RA, int CA, bool SERIES>
+static int launch_sweep_mode(const MllParams& p, size_t smem, cudaStream_t s) {
+  if (smem > 48 * 1024)
+    MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_sweep_kernel<RA, CA, SERIES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                       "cudaFuncSetAttribute"));
+  series_mll_sweep_kernel<RA, CA, SERIES><<<1, MLL_THREADS, smem, s>>>(p);
+  return MGB_OK;
+}
+
 template <int RA, int CA>
 static int launch_sweep(const MllParams& p, cudaStream_t s) {
   const size_t n = (size_t)p.n;
-  const size_t smem = sizeof(double) * (n * n + n * p.W + p.T + 3 * n + 2 * 32 * CA + 4 + p.T);
-  if (smem > 48 * 1024)
-    MGB_TRY(check_cuda(cudaFuncSetAttribute(series_mll_sweep_kernel<RA, CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                       "cudaFuncSetAttribute"));
-  series_mll_sweep_kernel<RA, CA><<<1, MLL_THREADS, smem, s>>>(p);
-  return MGB_OK;
+  const size_t smem = sizeof(double) * (n * p.W + p.T + 4 * 32 * CA + n + 4 + p.T);      // no n x n array: the matrix lives in registers
+  return (p.Kin == nullptr) ? launch_sweep_mode<RA, CA, true>(p, smem, s) : launch_sweep_mode<RA, CA, false>(p, smem, s);
 }
 
 static int launch_mll_grad(const MllParams& p, size_t smem, cudaStream_t s, const char* what) {
