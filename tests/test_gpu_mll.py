@@ -21,7 +21,7 @@ def _close(a, b, rtol):
     return float((a - b).abs().max()) <= rtol * float(b.abs().max()) + 1e-12
 
 
-@pytest.mark.parametrize("n", [1, 2, 37, 100, 160])
+@pytest.mark.parametrize("n", [1, 2, 33, 37, 70, 90, 100, 113, 128, 129, 160])     # every size class of the sweep kernel + the Cholesky kernel beyond 128
 def test_fused_mll_matches_unfused_and_oracle(n):
     from materngabo_b200 import kernels_sphere
     from materngabo_b200.gpytorch_compat import ScaleKernel
@@ -136,7 +136,7 @@ def _spd_points(n, gen):
     return torch.stack([s[:, 0, 0], s[:, 1, 1], s[:, 0, 1] * 2 ** 0.5], -1)
 
 
-@pytest.mark.parametrize("which,n", [("torus", 60), ("h2", 100), ("h3", 37), ("spd2", 100), ("spd2", 1), ("h2", 164)])
+@pytest.mark.parametrize("which,n", [("torus", 60), ("h2", 100), ("h3", 37), ("h3", 75), ("h3", 96), ("h3", 120), ("spd2", 100), ("spd2", 1), ("h2", 164)])
 def test_dense_mll_matches_unfused_path_on_every_other_manifold(which, n):
     """Kernels without the single-factor series form go through their own Gram kernel + ONE launch of the CTA kernel
     in dense mode (mgb_dense_mll): value and gradients to every raw hyper-parameter, the noise and the mean against
