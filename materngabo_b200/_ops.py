@@ -203,11 +203,13 @@ class SeriesMLL(torch.autograd.Function):
         lib = _lib.load()
         t = coef.shape[-1]
         out = torch.empty(4 + t, dtype=F64, device=x.device)
-        status = torch.zeros(1, dtype=torch.int32, device=x.device)
         d = spec.desc(t)
         n = x.shape[0]
+        single = n <= lib.mgb_series_mll_single_cta_max_n(spec.factor_width, int(t))
+        # the single-CTA kernels always write the flag: no fill launch for it
+        status = (torch.empty if single else torch.zeros)(1, dtype=torch.int32, device=x.device)
         with torch.cuda.device(x.device):
-            if n <= lib.mgb_series_mll_single_cta_max_n(spec.factor_width, int(t)):
+            if single:
                 rc = lib.mgb_series_mll(C.byref(d), _lib.ptr(x), n, x.stride(0), _lib.ptr(y), _lib.ptr(coef),
                                         _lib.ptr(hyper), _lib.ptr(out), _lib.ptr(status), _lib.stream_ptr(x.device))
             else:       # multi-CTA path: Gram kernel + cooperative Cholesky + triangular inverse + gradient contraction
@@ -225,8 +227,9 @@ class SeriesMLL(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g, _gs):
         (out,) = ctx.saved_tensors
-        gcoef = (g * out[4:]).reshape(ctx.coef_shape) if ctx.needs_input_grad[3] else None
-        ghyper = g * out[1:4] if ctx.needs_input_grad[4] else None
+        scaled = g * out[1:]                       # one launch for both gradient blocks
+        gcoef = scaled[3:].reshape(ctx.coef_shape) if ctx.needs_input_grad[3] else None
+        ghyper = scaled[:3] if ctx.needs_input_grad[4] else None
         return None, None, None, gcoef, ghyper
 
 
@@ -256,9 +259,10 @@ class DenseMLL(torch.autograd.Function):
         n = k.shape[0]
         out = torch.empty(4, dtype=F64, device=k.device)
         g = torch.empty((n, n), dtype=F64, device=k.device)
-        status = torch.zeros(1, dtype=torch.int32, device=k.device)
+        single = n <= lib.mgb_series_mll_single_cta_max_n(0, 0)
+        status = (torch.empty if single else torch.zeros)(1, dtype=torch.int32, device=k.device)
         with torch.cuda.device(k.device):
-            if n <= lib.mgb_series_mll_single_cta_max_n(0, 0):
+            if single:
                 rc = lib.mgb_dense_mll(_lib.ptr(k), n, k.stride(0), _lib.ptr(y), _lib.ptr(hyper), _lib.ptr(out), _lib.ptr(g), n,
                                        _lib.ptr(status), _lib.stream_ptr(k.device))
             else:
