@@ -454,6 +454,25 @@ int mgb_posterior_i8f_reduce_debug(const double* kstar, long long m, long long n
                                    const double* alpha, double kss, double mean_const, double* mean, double* var,
                                    void* workspace, long long workspace_bytes, int* planes, void* stream);
 
+/* Series Gram matrix with the inner products on the INT8 tensor cores (csrc/series_i8.cu; same contract and the same
+ * reference lines as mgb_series_gram_fwd: kernel_utils/kernels_sphere.py:102-139,188-224,343-384, kernels_so.py:305-362
+ * with dim = 3).  Single-factor monomial series with <= 12 terms and rows <= 16 wide (mgb_series_gram_i8_supported):
+ * every row of x1 / x2 is cut into seven signed 8-bit digits (error-free up to 2^-57 of the row's largest entry), the
+ * seven int32 planes of digit products come out of tcgen05.mma kind::i8 into tensor memory, the epilogue recombines them
+ * exactly in 64-bit integers and rounds ONCE to float64 (the inner product is at least as accurate as the float64
+ * kernel's FMA chain), then scale / shift, the reference's clamp and Horner run on the FP64 pipe as before.
+ * Rows with a NaN / Inf / |x| >= 1e300 entry give NaN rows / columns.  workspace: 256-byte aligned,
+ * >= mgb_series_gram_i8_workspace_bytes(n) bytes (the stacked operand image of x2); K: ldk >= n. */
+int mgb_series_gram_i8_supported(const mgb_series_desc* desc);
+long long mgb_series_gram_i8_workspace_bytes(long long n);
+int mgb_series_gram_fwd_i8(const mgb_series_desc* desc, const double* x1, long long m, long long ld1, const double* x2,
+                           long long n, long long ld2, const double* coef, double* K, long long ldk, void* workspace,
+                           long long workspace_bytes, void* stream);
+/* test hook: also writes the raw accumulator planes [row panel][column tile][7][128][32] (int32; n <= 4096) */
+int mgb_series_gram_fwd_i8_debug(const mgb_series_desc* desc, const double* x1, long long m, long long ld1, const double* x2,
+                                 long long n, long long ld2, const double* coef, double* K, long long ldk, void* workspace,
+                                 long long workspace_bytes, int* planes, void* stream);
+
 /* Analytic EI from posterior means / variances (botorch ExpectedImprovement: sigma = sqrt(max(var, 1e-9)),
  * u = +-(mean - best_f) / sigma, EI = sigma (phi(u) + u Phi(u))), elementwise over m candidates. */
 int mgb_expected_improvement(const double* mean, const double* var, long long m, double best_f, int maximize,

@@ -14,7 +14,7 @@ import torch
 from . import build as _build
 
 MGB_OK = 0
-MGB_VERSION = 201      # must equal mgb_version() (csrc/runtime.cu): bumped whenever a signature changes
+MGB_VERSION = 202      # must equal mgb_version() (csrc/runtime.cu): bumped whenever a signature changes
 BASIS_MONOMIAL = 0
 BASIS_CHEBYSHEV = 1
 MAX_FACTORS = 16
@@ -96,6 +96,10 @@ PROTOTYPES = {
     "mgb_series_posterior_i8f": (_I, [_P, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P, _D, _D, _P, _P, _P, _LL, _P]),
     "mgb_posterior_i8f_planes_bytes": (_LL, [_LL, _LL]),
     "mgb_posterior_i8f_reduce_debug": (_I, [_P, _LL, _LL, _LL, _P, _P, _D, _D, _P, _P, _P, _LL, _P, _P]),
+    "mgb_series_gram_i8_supported": (_I, [_DESC]),
+    "mgb_series_gram_i8_workspace_bytes": (_LL, [_LL]),
+    "mgb_series_gram_fwd_i8": (_I, [_DESC, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _LL, _P, _LL, _P]),
+    "mgb_series_gram_fwd_i8_debug": (_I, [_DESC, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _LL, _P, _LL, _P, _P]),
     "mgb_expected_improvement": (_I, [_P, _P, _LL, _D, _I, _P, _P]),
     "mgb_pair_scalars": (_I, [_I, _I, _P, _LL, _LL, _P, _LL, _LL, _P, _P, _P]),
     "mgb_spectral_coef": (_I, [_I, _I, _I, _P, _P, _P, _P, _D, _P, _P, _P, _P, _P]),

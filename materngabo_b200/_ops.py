@@ -10,6 +10,7 @@ of the reference need (pymanopt_addons/tools/autodiff/_pytorch.py:92-116).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -44,9 +45,51 @@ def _c2d(t: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 # spectral series
 # --------------------------------------------------------------------------------------------------
+# Which forward kernel serves a single-factor monomial series block (sphere, SO(3)): MGB_GRAM_PATH =
+#   fp64 (default): the float64 kernels (DMMA / DFMA inner products);
+#   int8: the INT8 tensor-core kernel (csrc/series_i8.cu) whenever it applies.  Opt-in: it is exact (inner products
+#   rounded once; tests/test_gpu_series_i8.py) but measured SLOWER on B200 - 3.6e11 entries/s against 5.3e11 (S^10,
+#   1 M x 2 k, sustained): unpacking seven int32 planes costs more issue slots than the inner product costs FP64 slots
+#   (DESIGN.md section 11).
+def _gram_path() -> str:
+    v = os.environ.get("MGB_GRAM_PATH", "fp64").lower()
+    if v not in ("fp64", "int8"):
+        raise ValueError("MGB_GRAM_PATH must be fp64 or int8 (got %r)" % v)
+    return v
+
+
+def series_gram_i8(spec, x1, x2, coef, planes: bool = False):
+    """K(x1, x2) of a single-factor monomial series kernel through mgb_series_gram_fwd_i8 (inner products on the INT8
+    tensor cores, error-free digit slicing).  planes=True (tests): also returns the raw int32 accumulator planes
+    [row panel][column tile][7][128][32]."""
+    lib = _lib.load()
+    m, n = x1.shape[0], x2.shape[0]
+    d = spec.desc(coef.shape[-1])
+    if not lib.mgb_series_gram_i8_supported(C.byref(d)):
+        raise _lib.MgbError("series_gram_i8: single-factor monomial series with <= 12 terms and rows <= 16 wide only")
+    k = torch.empty((m, n), dtype=F64, device=x1.device)
+    ws = torch.empty(max(int(lib.mgb_series_gram_i8_workspace_bytes(n)), 256), dtype=torch.uint8, device=x1.device)
+    with torch.cuda.device(x1.device):
+        if planes:
+            pl = torch.zeros(((m + 127) // 128, (n + 31) // 32, 7, 128, 32), dtype=torch.int32, device=x1.device)
+            rc = lib.mgb_series_gram_fwd_i8_debug(C.byref(d), _lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0),
+                                                  _lib.ptr(coef), _lib.ptr(k), max(n, 1), _lib.ptr(ws), ws.numel(), _lib.ptr(pl),
+                                                  _lib.stream_ptr(x1.device))
+        else:
+            rc = lib.mgb_series_gram_fwd_i8(C.byref(d), _lib.ptr(x1), m, x1.stride(0), _lib.ptr(x2), n, x2.stride(0),
+                                            _lib.ptr(coef), _lib.ptr(k), max(n, 1), _lib.ptr(ws), ws.numel(),
+                                            _lib.stream_ptr(x1.device))
+    _lib.check(rc, "mgb_series_gram_fwd_i8")
+    return (k, pl) if planes else k
+
+
 def _series_fwd_raw(spec, x1, x2, coef):
     lib = _lib.load()
     m, n = x1.shape[0], x2.shape[0]
+    if _gram_path() == "int8" and m > 0 and n > 0:
+        d8 = spec.desc(coef.shape[-1])
+        if lib.mgb_series_gram_i8_supported(C.byref(d8)):
+            return series_gram_i8(spec, x1, x2, coef)
     k = torch.empty((m, n), dtype=F64, device=x1.device)
     d = spec.desc(coef.shape[-1])
     with torch.cuda.device(x1.device):

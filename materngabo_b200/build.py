@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmgb.so")
 SOURCES = ["runtime.cu", "series_gram.cu", "son_gram.cu", "spd_eigh.cu", "quad_gram.cu", "quad_profile.cu", "posterior.cu", "mll.cu", "dense_spd.cu", "acquisition.cu", "host_api.cu",
-           "int8_posterior.cu", "int8_fused.cu"]
+           "int8_posterior.cu", "int8_fused.cu", "series_i8.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

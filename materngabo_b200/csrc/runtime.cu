@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) mixed_peak_kernel(double* out, int iters,
 using namespace mgb;
 
 extern "C" const char* mgb_last_error(void) { return g_err; }
-extern "C" int mgb_version(void) { return 201; }
+extern "C" int mgb_version(void) { return 202; }
 extern "C" long long mgb_launch_count(void) { return g_launches.load(); }
 
 extern "C" int mgb_fp64_peak(int kind, int repeats, double* tflops, double* elapsed_ms) {

@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from materngabo_b200 import _lib, build
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -65,3 +67,34 @@ def test_int8_path_size_queries_need_no_gpu():
     ws = lib.mgb_posterior_int8_workspace_bytes(m, 5000)
     assert ws == 4 * m + m * 7 * 1024 * 15 + 7 * m * 5120 * 4 + (1 << 20)
     assert lib.mgb_posterior_int8_workspace_bytes(0, 5000) == 0
+
+
+def test_int8_gram_path_size_queries_need_no_gpu():
+    """Host-side arithmetic of the opt-in INT8 tensor-core series Gram kernel (csrc/series_i8.cu): one stacked operand
+    tile (7 planes x 32 columns x 128 bytes) per 32 training points plus one exponent word per (padded) column."""
+    import ctypes as C
+
+    from materngabo_b200 import _lib, _ops
+
+    lib = _lib.load()
+    assert lib.mgb_series_gram_i8_workspace_bytes(0) == 0
+    assert lib.mgb_series_gram_i8_workspace_bytes(2000) == 63 * 7 * 32 * 128 + 2016 * 4 + 128      # exponent words padded to 256 bytes
+    assert lib.mgb_series_gram_i8_workspace_bytes(32) == 7 * 32 * 128 + 256
+    sphere = _ops.SeriesSpec(1, 11, 0, 1.0, 0.0, -1.0, 1.0).desc(10)
+    torus = _ops.SeriesSpec(10, 2, 1, 1.0, 0.0, -1.0, 1.0).desc(40)
+    wide = _ops.SeriesSpec(1, 17, 0, 1.0, 0.0, -1.0, 1.0).desc(10)
+    long_series = _ops.SeriesSpec(1, 3, 0, 1.0, 0.0, -1.0, 1.0).desc(13)
+    assert lib.mgb_series_gram_i8_supported(C.byref(sphere)) == 1
+    assert [lib.mgb_series_gram_i8_supported(C.byref(d)) for d in (torus, wide, long_series)] == [0, 0, 0]
+
+
+def test_gram_path_knob_is_validated(monkeypatch):
+    from materngabo_b200 import _ops
+
+    monkeypatch.setenv("MGB_GRAM_PATH", "int8")
+    assert _ops._gram_path() == "int8"
+    monkeypatch.setenv("MGB_GRAM_PATH", "fast")
+    with pytest.raises(ValueError):
+        _ops._gram_path()
+    monkeypatch.delenv("MGB_GRAM_PATH")
+    assert _ops._gram_path() == "fp64"
