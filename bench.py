@@ -49,8 +49,10 @@ def parse():
     ap.add_argument("--workload", default="posterior-s10")
     ap.add_argument("--cands", dest="m", type=int, default=None, help="override candidate / row count")
     ap.add_argument("--train", dest="n", type=int, default=None, help="override training / column count")
-    ap.add_argument("--posterior-path", default="fp64", choices=["fp64", "int8"],
-                    help="default workload: fp64 = hand-written DMMA kernel (default); int8 = opt-in INT8 tensor-core path")
+    ap.add_argument("--posterior-path", default="auto", choices=["auto", "fp64", "int8"],
+                    help="default workload: auto = what ExactGPPosterior picks by itself (MGB_POSTERIOR_PATH=auto: the INT8 "
+                         "tensor-core contraction from 16384 candidates x 1024..16384 training points on, else the FP64 DMMA "
+                         "kernel); fp64 / int8 force one of them")
     ap.add_argument("--int8-impl", default="fused", choices=["fused", "library"],
                     help="--posterior-path int8: fused = this repo's tcgen05 kernel (csrc/int8_fused.cu); library = CUTLASS "
                          "int8 GEMMs + recombination pass (csrc/int8_posterior.cu)")
@@ -151,6 +153,7 @@ def flops_per_candidate(n):
 def run_posterior(args, rank, world, local):
     import torch.distributed as dist
     from materngabo_b200 import _lib
+    from materngabo_b200 import posterior as posterior_mod
     from materngabo_b200.posterior import ExactGPPosterior, ShardedPosterior, shard_bounds
 
     device = torch.device("cuda", local)
@@ -163,11 +166,17 @@ def run_posterior(args, rank, world, local):
 
     # rank 0 owns the fit; the other ranks receive the state every step (as after a refit in the BO loop)
     gp, kernel = posterior_problem(n, device)
-    use_int8 = args.posterior_path == "int8"
+    gp.int8_impl = args.int8_impl
+    if args.posterior_path == "auto":
+        gp.int8 = "auto"
+        # the rule of ExactGPPosterior._int8_for on the per-rank share, evaluated identically on every rank
+        use_int8 = bool(gp.int8) and (m_total // world) >= posterior_mod.INT8_AUTO_MIN_M and args.int8_impl == "fused"
+        gp.int8 = use_int8
+    else:
+        use_int8 = args.posterior_path == "int8"
+        gp.int8 = use_int8
     if use_int8 and args.int8_impl == "library" and not lib.mgb_int8_available():
         raise SystemExit("--posterior-path int8 --int8-impl library: libmgb was built without the CUTLASS headers")
-    gp.int8 = use_int8
-    gp.int8_impl = args.int8_impl
     if rank == 0:
         gp.fit()
     sh = ShardedPosterior(compute=None) if world > 1 else None
@@ -175,10 +184,12 @@ def run_posterior(args, rank, world, local):
     xc = unit_rows(m_local, 11, gen, device)                      # this rank's candidate rows, HBM resident
     spec, coef0 = kernel.series()
     # shapes of the fitted state, known on every rank from n and the kernel: the broadcast is one flat NCCL transfer
-    state_meta = None
-    if not use_int8:
-        state_meta = {"train": ((n, 11), F64), "coef": (tuple(coef0.shape), F64),
-                      "packed": ((lib.mgb_posterior_pack_bytes(n) // 8,), F64)}
+    state_meta = {"train": ((n, 11), F64), "coef": (tuple(coef0.shape), F64),
+                  "packed": ((lib.mgb_posterior_pack_bytes(n) // 8,), F64)}
+    if use_int8:
+        pre = "mgb_posterior_i8f_" if args.int8_impl == "fused" else "mgb_posterior_int8_"
+        state_meta["packed_i8"] = ((int(getattr(lib, pre + "pack_bytes")(n)),), torch.uint8)
+        state_meta["alpha"] = ((n,), F64)
 
     def step():
         if world > 1:
@@ -227,6 +238,36 @@ def run_posterior(args, rank, world, local):
     value = m_total / (ms_per_step * 1e-3)
     checksum = float(mean[: min(1000, mean.numel())].sum() + var[: min(1000, var.numel())].sum())
 
+    # ---- INT8 headline: the SAME workload on the FP64 DMMA kernel (all ranks), a bounded number of steps, and the
+    # difference between the two paths' results over every candidate of the timed step ---------------------------
+    fp64_path = None
+    if use_int8:
+        mean_i8, var_i8 = mean.clone(), var.clone()
+        gp.int8 = False
+        fsteps = max(1, min(args.steps, 3))
+        step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(fsteps):
+            mean_f, var_f = step()
+        f1.record()
+        barrier()
+        tf_ = torch.tensor([f0.elapsed_time(f1)], dtype=F64, device=device)
+        if world > 1:
+            dist.all_reduce(tf_, op=dist.ReduceOp.MAX)
+        fms = float(tf_[0]) / fsteps
+        fp64_path = {"value": m_total / (fms * 1e-3), "unit": "candidates/s", "steps": fsteps, "ms_per_step": fms,
+                     "ratio_headline_to_fp64_path": value / (m_total / (fms * 1e-3)),
+                     "max_var_diff_rel_to_max_var": float((var_i8 - var_f).abs().max() / var_f.abs().max()),
+                     "max_mean_diff_rel_to_max_mean": float((mean_i8 - mean_f).abs().max() / mean_f.abs().max()),
+                     "compared_candidates": int(mean_f.numel()),
+                     "note": "the whole workload of the headline (same candidates, same sharding, same step()) on "
+                             "posterior_reduce_kernel (FP64 DMMA m8n8k4), timed right after it; the differences are taken over "
+                             "every candidate of the last timed step of each path (parity bar of the tests: 1e-10)"}
+        del mean_i8, var_i8, mean_f, var_f
+        gp.int8 = True
+
     # ---- per-kernel roofline pass (rank 0): events around every posterior_reduce launch -----------
     roof = None
     if rank == 0:
@@ -243,8 +284,19 @@ def run_posterior(args, rank, world, local):
                     "whole step time of one GPU: slicing, recombination and the Gram kernel included)",
                     "peak": 2.0 * float(measured_peaks().get("bf16_tflops_sustained") or 1371.4),
                     "peak_source": "2 x the sustained bf16 rate of MEASURED_PEAKS.json (int8 dense = 2 x bf16 dense)",
-                    "traffic": None, "fp64_kernel": roof}
+                    "traffic": (6.524901e9 + 28.624128e6) if (fused and n == 5000) else None,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one f8_posterior_kernel launch (37888 candidates "
+                                      "x 5000 training points; ncu --set full, profiles/r02_ncu_f8_posterior.txt); algorithmic "
+                                      "operand bytes per launch: A slices 1.36e9 + triangular B slices 0.9e8",
+                    "ncu": "tensor pipe active 79 %, 81 % of the int8 tensor peak at the realised clock (1 kW power cap)",
+                    "fp64_kernel": roof}
             roof["frac"] = roof["achieved"] / roof["peak"]
+            # north_star asks for the fraction of the FP64 roof: the float64 work of the step (SURVEY.md 8d flops per
+            # candidate) over the FP64 tensor peak measured in this run - above 1 because the contraction is emulated
+            # exactly on the int8 tensor cores instead of running on the FP64 pipe
+            roof["fp64_equivalent"] = {"achieved": value / world * flops_per_candidate(n) / 1e12, "unit": "TFLOP/s (float64-equivalent)",
+                                       "peak": roof["fp64_kernel"]["peak"],
+                                       "frac": value / world * flops_per_candidate(n) / 1e12 / roof["fp64_kernel"]["peak"]}
 
     # ---- opt-in INT8 tensor-core path on a bounded sample (rank 0, one GPU), with its parity against `value`'s path ---
     int8 = None
@@ -271,8 +323,12 @@ def run_posterior(args, rank, world, local):
         out = {
             "metric": "posterior_cands_per_sec", "value": value, "unit": "candidates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "posterior_path": args.posterior_path,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64+i8" if use_int8 else "f64", "data": "synthetic",
+            "dtype_detail": ("inputs, kernel rows and outputs float64; the N^2 contraction as exact products of 8-bit digits "
+                             "(56 bits per operand, int32 accumulation, tcgen05 kind::i8) recombined in float64 - "
+                             "see fp64_path for the difference to the FP64 kernel on every candidate") if use_int8 else
+                            "float64 throughout (FP64 DMMA tensor-core kernel)",
+            "posterior_path": "int8" if use_int8 else "fp64", "posterior_path_requested": args.posterior_path,
             "config": {"workload": "S^10 Riemannian Matern nu=2.5 kappa=0.5 T=10 exact-GP posterior mean/var, "
                                    "%d candidates x %d training points, candidate rows sharded over %d GPU(s); "
                                    "BASELINE.json configs[4]" % (m_total, n, world),
@@ -281,7 +337,7 @@ def run_posterior(args, rank, world, local):
                                     "(chunk buffer %.2f GB > 126 MB L2)" % (8e-9 * m_total * n / world,
                                                                             8e-9 * gp.chunk * n)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e,
-            "checksum": checksum, "int8_path": int8, "gram": gram,
+            "checksum": checksum, "int8_path": int8, "fp64_path": fp64_path, "gram": gram,
         }
     return out
 

@@ -61,6 +61,18 @@ def _frozen_parameters(module):
 
 INT8_CHUNK = 32768      # candidates per block of the library INT8 path: 640 GEMM tiles per launch = 9 waves of 2-SM tile pairs
 INT8_FUSED_CHUNK = 37888   # fused tcgen05 kernel: 296 row blocks of 128 = two per SM
+# MGB_POSTERIOR_PATH=auto (the default): the INT8 tensor-core contraction serves calls with at least INT8_AUTO_MIN_M
+# candidates against INT8_AUTO_MIN_N .. INT8_AUTO_MAX_N training points (series kernels, fused implementation); smaller
+# calls - the BO loop's hundreds of candidates against ~100 points - stay on the FP64 DMMA kernel, which has no
+# per-fit slicing pass.  int32 accumulation of the digit products is exact up to n = 16384.
+INT8_AUTO_MIN_N, INT8_AUTO_MAX_N, INT8_AUTO_MIN_M = 1024, 16384, 16384
+
+
+def _int8_mode_from_env() -> str:
+    v = os.environ.get("MGB_POSTERIOR_PATH", "auto").lower()
+    if v not in ("auto", "fp64", "int8"):
+        raise ValueError("MGB_POSTERIOR_PATH must be auto, fp64 or int8 (got %r)" % v)
+    return {"auto": "auto", "fp64": "off", "int8": "on"}[v]
 
 
 class ExactGPPosterior:
@@ -87,12 +99,19 @@ class ExactGPPosterior:
         # (materngabo_b200/tabulated.py) instead of one quadrature per entry; the fit always uses the quadrature
         self.tabulate = bool(tabulate)
         self.device = train_x.device
-        # opt-in: the N^2 contraction on the INT8 tensor cores by error-free slicing (csrc/int8_fused.cu; ~2e-13 of
-        # max var instead of ~1e-14).  Default: the FP64 tensor-core kernel.  MGB_POSTERIOR_PATH=int8 turns it on globally.
-        self.int8 = bool(int8) if int8 is not None else os.environ.get("MGB_POSTERIOR_PATH", "") == "int8"
+        # The N^2 contraction on the INT8 tensor cores by error-free slicing (csrc/int8_fused.cu: 56-bit operands, exact
+        # int32 digit products, float64 recombination; ~3e-13 of max var from the FP64 kernel's ~1e-14, parity bar 1e-10).
+        # int8 = True / False forces it on / off, "auto" or None (-> MGB_POSTERIOR_PATH, default auto) lets the call
+        # size decide (INT8_AUTO_* above).
+        if int8 is None:
+            self._int8_mode = _int8_mode_from_env()
+        elif isinstance(int8, str):
+            self._int8_mode = "auto" if int8 == "auto" else "on"
+        else:
+            self._int8_mode = "on" if int8 else "off"
         # which INT8 implementation: "fused" = this repo's tcgen05 kernel (csrc/int8_fused.cu), "library" = CUTLASS int8
         # GEMMs + recombination pass (csrc/int8_posterior.cu); int8="library" or MGB_INT8_IMPL=library selects the latter
-        self.int8_impl = int8 if isinstance(int8, str) else os.environ.get("MGB_INT8_IMPL", "fused")
+        self.int8_impl = int8 if isinstance(int8, str) and int8 != "auto" else os.environ.get("MGB_INT8_IMPL", "fused")
         if self.int8_impl not in ("fused", "library"):
             raise ValueError("int8 implementation must be 'fused' or 'library', got %r" % (self.int8_impl,))
         self._packed = None
@@ -104,6 +123,28 @@ class ExactGPPosterior:
         self.kss_value = None
 
     # ---- one-off N x N work ------------------------------------------------------------------
+    @property
+    def int8(self) -> bool:
+        """True when large calls go through the INT8 tensor-core contraction (always, in the forced mode)."""
+        if self._int8_mode != "auto":
+            return self._int8_mode == "on"
+        n = self.train_x.shape[0]
+        return self.int8_impl == "fused" and self.is_series and INT8_AUTO_MIN_N <= n <= INT8_AUTO_MAX_N
+
+    @int8.setter
+    def int8(self, value):
+        self._int8_mode = "auto" if value == "auto" else ("on" if value else "off")
+
+    def _int8_for(self, m: int) -> bool:
+        """Does a call with m candidates take the INT8 path?"""
+        if not self.int8:
+            return False
+        if self._int8_mode == "on":
+            return True
+        # auto: large calls only, and only where the sliced factor exists or can be made (a peer rank that received the
+        # FP64 state alone keeps the FP64 kernel)
+        return m >= INT8_AUTO_MIN_M and (self._packed_i8 is not None or getattr(self, "rinv", None) is not None)
+
     @property
     def is_series(self):
         return hasattr(self.kernel, "series")
@@ -280,7 +321,7 @@ class ExactGPPosterior:
             return mean, var
         lib = _lib.load()
         chunk = min(self.chunk, (m + 127) // 128 * 128)
-        if self.int8:
+        if self._int8_for(m):
             return self._posterior_int8(x, mean, var, chunk)
         if not self.is_series:
             return self._posterior_generic(x, mean, var, chunk)
@@ -622,13 +663,30 @@ class PosteriorHandle:
         _lib.check(rc, "mgb_posterior_create_from_device")
         self._h = h
         self.int8 = False
-        if gp.int8 and gp.int8_impl == "fused":
+        self._i8_state = None
+        self._i8_auto = gp._int8_mode == "auto"          # auto: calls below INT8_AUTO_MIN_M candidates use the FP64 kernel
+        if gp.int8 and gp.int8_impl == "fused" and (not self._i8_auto or getattr(gp, "rinv", None) is not None
+                                                    or gp._packed_i8 is not None):
             # the handle evaluates through csrc/int8_fused.cu as well: it borrows the sliced factor and alpha
             gp._ensure_packed_i8()
             torch.cuda.current_stream(gp.device).synchronize()
-            self._keep = self._keep + (gp._packed_i8, gp.alpha)
-            _lib.check(lib.mgb_posterior_use_int8(h, _lib.ptr(gp._packed_i8), _lib.ptr(gp.alpha)), "mgb_posterior_use_int8")
-            self.int8 = True
+            self._i8_state = (gp._packed_i8, gp.alpha)
+            self._keep = self._keep + self._i8_state
+            self._set_int8(True)
+
+    def _set_int8(self, on: bool):
+        if on == self.int8:
+            return
+        if on:
+            rc = self._lib.mgb_posterior_use_int8(self._h, _lib.ptr(self._i8_state[0]), _lib.ptr(self._i8_state[1]))
+        else:
+            rc = self._lib.mgb_posterior_use_int8(self._h, None, None)
+        _lib.check(rc, "mgb_posterior_use_int8")
+        self.int8 = on
+
+    def _select_path(self, m: int):
+        if self._i8_auto and self._i8_state is not None:
+            self._set_int8(m >= INT8_AUTO_MIN_M)
 
     @property
     def chunk(self) -> int:
@@ -642,6 +700,7 @@ class PosteriorHandle:
         if x.is_cuda or x.dtype != F64 or x.dim() != 2 or x.shape[1] != self.width or not x.is_contiguous():
             raise ValueError("eval_host expects a contiguous (m, %d) float64 host array" % self.width)
         m = x.shape[0]
+        self._select_path(m)
         mean = mean_host if mean_host is not None else torch.empty(m, dtype=F64)
         var = var_host if var_host is not None else torch.empty(m, dtype=F64)
         rc = self._lib.mgb_posterior_eval_host(self._h, C.c_void_p(x.data_ptr()), m, C.c_void_p(mean.data_ptr()),
@@ -654,6 +713,7 @@ class PosteriorHandle:
             raise RuntimeError("handle destroyed")
         _lib.require_cuda_f64(x)
         m = x.shape[0]
+        self._select_path(m)
         mean = torch.empty(m, dtype=F64, device=x.device)
         var = torch.empty(m, dtype=F64, device=x.device)
         with torch.cuda.device(x.device):
@@ -790,7 +850,9 @@ class ShardedPosterior:
         cache = self.__dict__.setdefault("_flat_cache", {})
         for dtype, items in by_dtype.items():
             sizes = [int(math.prod(shape)) for _, shape in items]
-            total = sum(sizes)
+            # every tensor starts 512 bytes apart at least: the packed operands are read with 16-byte bulk copies
+            pads = [(sz + 511) // 512 * 512 for sz in sizes]
+            total = sum(pads)
             key = (str(dtype), total, str(dev))
             flat = cache.get(key)
             if flat is None:
@@ -798,14 +860,14 @@ class ShardedPosterior:
                 cache[key] = flat
             if self.rank == src:
                 off = 0
-                for (name, shape), sz in zip(items, sizes):
+                for (name, shape), sz, pad in zip(items, sizes, pads):
                     flat[off:off + sz].copy_(tensors[name].reshape(-1))
-                    off += sz
+                    off += pad
             dist.broadcast(flat, src=src, group=self.group)
             off = 0
-            for (name, shape), sz in zip(items, sizes):
+            for (name, shape), sz, pad in zip(items, sizes, pads):
                 out[name] = tensors[name] if self.rank == src else flat[off:off + sz].view(shape)
-                off += sz
+                off += pad
         return out
 
     def _default_device(self):

@@ -71,6 +71,28 @@ def test_our_arm_json_line_on_the_gpu():
 
 
 @pytest.mark.gpu
+def test_default_path_picks_the_int8_contraction_at_large_sizes_and_carries_the_fp64_measurement():
+    """--posterior-path auto (the default) with >= 16384 candidates x >= 1024 training points: the headline runs on the
+    INT8 tensor-core contraction, the same workload on the FP64 kernel and the difference between the two result sets
+    over every candidate are part of the line."""
+    r = _run(["--steps", "1", "--warmup", "3", "--cands", "200000", "--train", "2048", "--no-cpu-baseline"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["posterior_path"] == "int8" and d["posterior_path_requested"] == "auto" and d["dtype"] == "f64+i8"
+    f = d["fp64_path"]
+    assert f["value"] > 0 and f["compared_candidates"] == 200000
+    assert f["max_var_diff_rel_to_max_var"] < 1e-10 and f["max_mean_diff_rel_to_max_mean"] < 1e-10
+    roof = d["roofline"]
+    assert roof["bound"] == "tensor" and roof["fp64_kernel"]["frac"] > 0 and roof["fp64_equivalent"]["frac"] > 0
+    assert "csrc/int8_fused.cu" in d["e2e"]["api"] and d["e2e"]["value"] > 0
+    r = _run(["--steps", "1", "--warmup", "3", "--cands", "200000", "--train", "2048", "--no-cpu-baseline", "--posterior-path", "fp64",
+              "--no-e2e"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["posterior_path"] == "fp64" and d["dtype"] == "f64" and d["fp64_path"] is None
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("workload,rows,cols", [("config1-s2", 500, 500), ("gram-so3", 4096, 512), ("gram-t10", 4096, 256),
                                                 ("gram-h2", 256, 256), ("gram-spd2", 256, 256), ("gram-spd3", 256, 256),
                                                 ("gram-h2-table", 4096, 512), ("gram-so5", 512, 256)])

@@ -354,8 +354,12 @@ def test_fused_acquisition_torus():
     assert rel_err(ei, val) < 1e-11 and rel_err(grad, ga) < 1e-9 and rel_err(hvp, ha) < 1e-8
 
 
-def test_baseline_train_size_chunk_consistency():
-    """BASELINE configs[4] geometry (S^10, 5000 training points) beyond what the oracle finishes in seconds:
+@pytest.mark.parametrize("int8", [False, "auto"])
+def test_baseline_train_size_chunk_consistency(int8):
+    """int8 = False: the FP64 DMMA kernel on every call; "auto" (the default): the 80000-candidate call runs on the INT8
+    tensor-core contraction, the 8-row and 300-row calls on the FP64 kernel - the row-by-row comparison then also holds
+    the two paths against each other.
+    BASELINE configs[4] geometry (S^10, 5000 training points) beyond what the oracle finishes in seconds:
     size-independent properties - rows taken from different 37888-candidate chunks agree with the same rows evaluated
     alone, training inputs reproduce the noise-level variance bound, and a sample of rows agrees with the oracle."""
     from materngabo_b200 import kernels_sphere
@@ -369,7 +373,8 @@ def test_baseline_train_size_chunk_consistency():
     y = torch.sin(3.0 * xt[:, 0]) + 0.5 * xt[:, 1] * xt[:, 2]
     k = kernels_sphere.SphereRiemannianMaternKernel(dim=10, nu=2.5)
     k.lengthscale = 0.5
-    gp = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.0, noise=1e-2).fit()
+    gp = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), outputscale=1.0, noise=1e-2, int8=int8).fit()
+    assert gp._int8_for(m) == (int8 == "auto") and not gp._int8_for(8)
     mean, var = gp.posterior(xc.to(DEV))
     rows = torch.tensor([0, 127, 128, 37887, 37888, 75775, 75776, m - 1])
     ms, vs = gp.posterior(xc[rows].to(DEV))
@@ -696,3 +701,47 @@ def test_fused_int8_path_on_other_series_kernels(which):
     m1, v1 = fast.posterior(xc.to(DEV))
     assert float((v1 - v0).abs().max()) < 5e-12 * 0.9
     assert float((m1 - m0).abs().max()) < 1e-12 * float(m0.abs().max())
+
+
+def test_auto_mode_picks_the_path_by_call_size_on_the_model_and_on_the_handle(monkeypatch):
+    """MGB_POSTERIOR_PATH=auto (default): >= 16384 candidates against 1024 .. 16384 training points -> INT8 tensor-core
+    contraction, anything smaller -> FP64 DMMA kernel; the persistent C-ABI handle switches per call the same way."""
+    from materngabo_b200 import _lib, kernels_sphere as ks
+    from materngabo_b200.posterior import ExactGPPosterior, INT8_AUTO_MIN_M
+
+    monkeypatch.delenv("MGB_POSTERIOR_PATH", raising=False)
+    gen = torch.Generator().manual_seed(5)
+    xt = _unit(torch.randn(1100, 4, generator=gen))
+    xc = _unit(torch.randn(INT8_AUTO_MIN_M + 300, 4, generator=gen)).to(DEV)
+    y = torch.sin(3 * xt[:, 0])
+    k = ks.SphereRiemannianMaternKernel(dim=3, nu=2.5)
+    k.lengthscale = 0.5
+    gp = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), noise=1e-2).fit()
+    assert gp._int8_mode == "auto" and gp.int8 and gp._int8_for(xc.shape[0]) and not gp._int8_for(500)
+    small = ExactGPPosterior(k, xt[:500].to(DEV), y[:500].to(DEV), noise=1e-2).fit()
+    assert not small.int8 and not small._int8_for(10 ** 6)                     # below 1024 training points: FP64 only
+    ref = ExactGPPosterior(k, xt.to(DEV), y.to(DEV), noise=1e-2, int8=False).fit()
+    m8, v8 = gp.posterior(xc)                                                  # INT8
+    mf, vf = ref.posterior(xc)                                                 # FP64
+    assert gp._packed_i8 is not None and ref._packed_i8 is None
+    assert rel_err(m8, mf) < 1e-11 and float((v8 - vf).abs().max()) < 1e-11 * float(vf.abs().max())
+    ms, vs = gp.posterior(xc[:500])                                            # FP64 inside the auto model
+    assert rel_err(ms, mf[:500]) < 1e-13 and float((vs - vf[:500]).abs().max()) < 1e-13 * float(vf.abs().max())   # FP64 kernel both times
+    assert float((vs - v8[:500]).abs().max()) > 0.0                          # and not the INT8 results
+    lib = _lib.load()
+    with gp.handle() as h:
+        a = h.eval_device(xc[:500])
+        assert not h.int8 and lib.mgb_posterior_is_int8(h._h) == 0
+        b = h.eval_device(xc)
+        assert h.int8 and lib.mgb_posterior_is_int8(h._h) == 1
+        c = h.eval_device(xc[:500])
+        assert not h.int8
+    assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    assert rel_err(b[0], mf) < 1e-11 and float((b[1] - vf).abs().max()) < 1e-11 * float(vf.abs().max())
+    monkeypatch.setenv("MGB_POSTERIOR_PATH", "fp64")
+    assert not ExactGPPosterior(k, xt.to(DEV), y.to(DEV)).int8
+    monkeypatch.setenv("MGB_POSTERIOR_PATH", "int8")
+    assert ExactGPPosterior(k, xt[:50].to(DEV), y[:50].to(DEV)).int8
+    monkeypatch.setenv("MGB_POSTERIOR_PATH", "fast")
+    with pytest.raises(ValueError):
+        ExactGPPosterior(k, xt.to(DEV), y.to(DEV))
