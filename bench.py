@@ -184,16 +184,19 @@ def run_posterior(args, rank, world, local):
     xc = unit_rows(m_local, 11, gen, device)                      # this rank's candidate rows, HBM resident
     spec, coef0 = kernel.series()
     # shapes of the fitted state, known on every rank from n and the kernel: the broadcast is one flat NCCL transfer
-    state_meta = {"train": ((n, 11), F64), "coef": (tuple(coef0.shape), F64),
-                  "packed": ((lib.mgb_posterior_pack_bytes(n) // 8,), F64)}
+    meta_fp64 = {"train": ((n, 11), F64), "coef": (tuple(coef0.shape), F64),
+                 "packed": ((lib.mgb_posterior_pack_bytes(n) // 8,), F64)}
+    meta_int8 = dict(meta_fp64)
     if use_int8:
         pre = "mgb_posterior_i8f_" if args.int8_impl == "fused" else "mgb_posterior_int8_"
-        state_meta["packed_i8"] = ((int(getattr(lib, pre + "pack_bytes")(n)),), torch.uint8)
-        state_meta["alpha"] = ((n,), F64)
+        meta_int8["packed_i8"] = ((int(getattr(lib, pre + "pack_bytes")(n)),), torch.uint8)
+        meta_int8["alpha"] = ((n,), F64)
 
     def step():
         if world > 1:
-            state = sh.broadcast_state(gp.state() if rank == 0 else {"like": xc[:0]}, src=0, meta=state_meta)
+            # gp.int8 is set identically on every rank (headline path, then the FP64 pass): the state that travels follows it
+            state = sh.broadcast_state(gp.state() if rank == 0 else {"like": xc[:0]}, src=0,
+                                       meta=meta_int8 if gp.int8 else meta_fp64)
             if rank != 0:
                 gp.load_state(spec, state["train"], state["packed"], state["coef"],
                               _self_k(spec, state["coef"]), state.get("packed_i8"), state.get("alpha"))
@@ -1232,7 +1235,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a step is seconds at most: a rank that waits minutes for a peer is a bug, not a slow collective
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=240))
     try:
         if args.workload == "posterior-s10":
             out = run_posterior(args, rank, world, local)
@@ -1254,11 +1259,19 @@ def main():
             elif "cpu_baseline" not in out:
                 out["cpu_baseline"] = None
             print(json.dumps(out), flush=True)
-    finally:
+    except BaseException:
         if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-            dist.destroy_process_group()
+            # the peers are (or will be) waiting in a collective for this rank: report and take the job down now instead
+            # of meeting them in a barrier that can never complete
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            os._exit(1)
+        raise
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
