@@ -56,6 +56,20 @@ def _worker(rank, world, port, m, out_dir):
         for _ in range(2):
             flat_state = sh.broadcast_state(state if rank == 0 else {"like": torch.zeros(0)}, src=0, meta=meta)
             assert all(torch.equal(flat_state[k], state[k]) for k in meta)
+        # mixed dtypes and odd sizes (the INT8 state: sliced factor as bytes beside the float64 tensors, two meta tables
+        # used alternately as bench.py does for its INT8 and FP64 passes): every tensor starts 512 elements apart
+        sliced = (torch.arange(1001, dtype=torch.int64) % 251).to(torch.uint8)
+        meta_i8 = dict(meta, packed_i8=((1001,), torch.uint8), odd=((7,), torch.float64))
+        full = dict(state, packed_i8=sliced, odd=torch.arange(7, dtype=torch.float64)) if rank == 0 else {"like": torch.zeros(0)}
+        for use_i8 in (True, False, True):
+            got = sh.broadcast_state(full if rank == 0 else {"like": torch.zeros(0)}, src=0, meta=meta_i8 if use_i8 else meta)
+            assert set(got) == set(meta_i8 if use_i8 else meta)
+            assert all(torch.equal(got[k], state[k]) for k in meta)
+            if use_i8:
+                assert torch.equal(got["packed_i8"], sliced) and torch.equal(got["odd"], torch.arange(7, dtype=torch.float64))
+                if rank != 0:          # views of one flat buffer per dtype, 512 elements (4096 bytes of float64) apart at least
+                    f64 = sorted(got[k].data_ptr() for k in got if got[k].dtype == torch.float64)
+                    assert all((b - a) % 4096 == 0 for a, b in zip(f64, f64[1:]))
         sh.compute = lambda x: R.gp_predict(kfn, state["train"], state["L"], state["alpha"], x, 1.0, 0.0)
         lo, hi = shard_bounds(m, world, rank)
         mean, var = sh.evaluate(xc[lo:hi], gather=True)
