@@ -7,14 +7,18 @@
 // its W + T FMA slots per entry on the inner product: 12 of 21 for S^10 and for SO(3) in trace form.  Under sustained
 // load the board sits at its power cap and that kernel reaches 64 % (S^10) of the HBM-write roof.  Here the inner
 // product leaves the FP64 pipe: 3 + (T - 1) FP64 instructions per entry remain (two to recombine, one scale / shift,
-// Horner), the rest is integer work and tensor-core time that is two orders of magnitude below its roof.
+// Horner), the rest is integer work and tensor-core time that is an order of magnitude below its roof.
+// MEASURED (1 M x 2 k, one B200): exact - planes equal to an integer matmul, K within 2 - 5e-16 of a long-double evaluation -
+// but 3.6e11 entries/s on S^2, S^10 and SO(3) alike against 5.3 - 6.5e11 for the float64 kernels: recombining seven
+// overlapping 21-bit planes takes ~10 integer instructions per entry, which is more issue time than the FP64 slots it
+// saves.  Opt-in (MGB_GRAM_PATH=int8); the float64 kernels stay the default.
 //
 // Error-free slicing (Ozaki scheme, as in int8_fused.cu): every row is scaled by a power of two 2^-e (|x| 2^-e <=
 // 126/256) and cut into S = 7 signed 8-bit digits (round to nearest + carry pass), x = 2^e sum_p d_p 2^(-8 (p + 1)) up
 // to 2^(e - 57), so
 //      <x, y> = 2^(ea + eb) sum_{s < 7} 2^(-8 (s + 2)) P_s,     P_s = sum_{p + q = s} <d_p(x), d_q(y)>   (int32, exact)
-// with the products of p + q >= 7 dropped (<= 6 W 2^14 2^-72 2^(ea + eb) ~ 3e-16 2^(ea + eb) for W = 16; measured against the float64
-// kernel: a few 1e-16).  The seven planes come out of ONE small GEMM per tile: an operand row of x is its digit vectors
+// with the products of p + q >= 7 dropped (<= 6 W 2^14 2^-72 2^(ea + eb) ~ 3e-16 2^(ea + eb) for W = 16; measured
+// against the float64 kernel: a few 1e-16).  The seven planes come out of ONE small GEMM per tile: an operand row of x is its digit vectors
 // side by side, [d_0 | d_1 | ... | d_6 | 0] (eight 16-byte chunks, W <= 16 int8 each: one 128-byte swizzle row), and the
 // B operand row of (plane s, column j) is [d_s(y_j) | d_{s-1}(y_j) | ... | d_0(y_j) | 0 ...]: the K = 128 contraction
 // of the two is exactly P_s.  Chunk pair a = 0 .. 3 (one K = 32 MMA step) only meets planes s >= 2 a, which are adjacent
@@ -24,9 +28,10 @@
 //   warp 0      B producer: one cp.async.bulk per stacked B tile (28 KB, pre-built by g8_slice_b_kernel) into a 4-deep ring
 //   warp 1      MMA issuer (one elected lane), accumulators double-buffered in tensor memory (2 x 224 columns)
 //   warp 2      A slicer: digits of the next row panel straight into the swizzled shared-memory operand image
-//   warps 4-19  epilogue (32 rows x 8 columns of a tile each): tcgen05.ld (thread = row), integer recombination of the planes into two exact 64-bit sums,
+//   warps 4-19  epilogue (32 rows x 8 columns of a tile each): tcgen05.ld (thread = row; the next tile's loads are issued
+//               before this tile's Horner phase), integer recombination of the planes into two exact 64-bit sums,
 //               magic-number conversion, two FMAs -> the correctly rounded inner product, scale / shift, clamp (integer
-//               test, exact slow path), Horner, transpose through shared memory, 128-byte streaming stores.
+//               test, exact slow path), Horner, transpose through shared memory, 64-byte row segments as streaming stores.
 #include "mgb_tcgen05.cuh"
 
 #include <cstring>
