@@ -323,24 +323,30 @@ __global__ void __launch_bounds__(F8G_THREADS) f8_gram_slice_kernel(const F8Gram
       mu = warp_sum(mu);
       if (lane == 0 && rowok) p.meanpart[(long long)kb * p.m_pad + i] = mu;
       if (kb == 0 && lane == 0) p.ea[i] = e2;
+      // Digits on the integer pipe (the FP64 pipe is this kernel's bound): r 2^56 as two exact integers - the leading 32
+      // bits (|r| 2^32 <= 126 2^24 fits int32) and the following 24 of the exact remainder, 4 FP64 instructions instead of
+      // three per digit - then balanced base-256 digits from the least significant end: the digit is the low byte read as
+      // int8, what is left is (v + 128) >> 8, and the leftover of the lower word carries into the upper one.  Only the low
+      // byte of q[s][t] is used below.
       int q[F8_S][4];
 #pragma unroll
-      for (int s7 = 0; s7 < F8_S; ++s7) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const double tt = fma(rr[t], (double)(1 << F8_BITS), kMagic);
-          q[s7][t] = __double2loint(tt);
-          rr[t] = fma(rr[t], (double)(1 << F8_BITS), -(tt - kMagic));
-        }
-      }
-#pragma unroll
-      for (int s7 = F8_S - 1; s7 >= 1; --s7) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int c = (q[s7][t] == 128) ? 1 : 0;
-          q[s7][t] -= c << 8;
-          q[s7 - 1][t] += c;
-        }
+      for (int t = 0; t < 4; ++t) {
+        const double t1 = fma(rr[t], 4294967296.0, kMagic);                         // round(r 2^32)
+        int hi4 = __double2loint(t1);
+        const double rem = fma(rr[t], 4294967296.0, -(t1 - kMagic));                // exact, |rem| <= 1/2
+        int lo3 = __double2loint(fma(rem, 16777216.0, kMagic));                     // round(rem 2^24), |lo3| <= 2^23
+        q[6][t] = lo3;
+        lo3 = (lo3 + 128) >> 8;
+        q[5][t] = lo3;
+        lo3 = (lo3 + 128) >> 8;
+        q[4][t] = lo3;
+        hi4 += (lo3 + 128) >> 8;
+        q[3][t] = hi4;
+        hi4 = (hi4 + 128) >> 8;
+        q[2][t] = hi4;
+        hi4 = (hi4 + 128) >> 8;
+        q[1][t] = hi4;
+        q[0][t] = (hi4 + 128) >> 8;
       }
       signed char* dst = tile0 + f8_swizzled(r, lane >> 2);
 #pragma unroll
