@@ -4,6 +4,7 @@ import sys
 
 d = [json.loads(ln) for ln in open(sys.argv[1]) if ln.startswith("{")][-1]
 print("value", d["value"], "e2e", (d.get("e2e") or {}).get("value"), "roofline.frac", (d.get("roofline") or {}).get("frac"))
+print("gram_cool_down", d.get("gram_cool_down"))
 for k, v in (d.get("gram") or {}).items():
     if "error" in v:
         print(k, "ERROR", v["error"])
