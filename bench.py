@@ -322,15 +322,18 @@ def run_posterior(args, rank, world, local):
             # the same achieved figure against the other denominators one could choose (MEASURED_PEAKS.json has no int8 entry):
             # 2 x the measured bf16 BURST rate, and the hardware's int8 issue rate (ncu: 16384 int8 ops / cycle / SM,
             # sm__ops_path_tensor_op_utcimma_src_int8 peak_sustained) at the SM clock realised under this run's power cap
-            burst = measured_peaks().get("bf16_tflops")
-            sms = torch.cuda.get_device_properties(device).multi_processor_count
-            mhz = (clocks or {}).get("sm_mhz")
-            roof["other_denominators"] = {
-                "2x_measured_bf16_burst": {"peak": 2.0 * burst, "frac": roof["achieved"] / (2.0 * burst)} if burst else None,
-                "hw_int8_rate_at_realised_clock": {"peak": 16384.0 * sms * mhz * 1e6 / 1e12, "sm_mhz": mhz,
-                                                   "frac": roof["achieved"] / (16384.0 * sms * mhz * 1e6 / 1e12)} if mhz else None,
-                "note": "achieved counts the executed slice products over the WHOLE step (slicing kernel and launch gaps included); "
-                        "f8_posterior_kernel alone: 81 % of the hardware rate at its realised clock (ncu)"}
+            try:
+                burst = measured_peaks().get("bf16_tflops")
+                sms = torch.cuda.get_device_properties(device).multi_processor_count
+                mhz = (clocks or {}).get("sm_mhz")
+                roof["other_denominators"] = {
+                    "2x_measured_bf16_burst": {"peak": 2.0 * burst, "frac": roof["achieved"] / (2.0 * burst)} if burst else None,
+                    "hw_int8_rate_at_realised_clock": {"peak": 16384.0 * sms * mhz * 1e6 / 1e12, "sm_mhz": mhz,
+                                                       "frac": roof["achieved"] / (16384.0 * sms * mhz * 1e6 / 1e12)} if mhz else None,
+                    "note": "achieved counts the executed slice products over the WHOLE step (slicing kernel and launch gaps included); "
+                            "f8_posterior_kernel alone: 81 % of the hardware rate at its realised clock (ncu)"}
+            except Exception as exc:      # extra information only: never lose the line over it
+                roof["other_denominators"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
             # north_star asks for the fraction of the FP64 roof: the float64 work of the step (SURVEY.md 8d flops per
             # candidate) over the FP64 tensor peak measured in this run - above 1 because the contraction is emulated
             # exactly on the int8 tensor cores instead of running on the FP64 pipe
