@@ -14,8 +14,11 @@ one box (strong scaling, one process per GPU, NCCL only for the state broadcast 
   python bench.py --workload tr-step         trust-region inner step on every manifold: fused kernels vs autograd
 
 Rank 0 prints ONE JSON line.  ``value`` = candidates/s with inputs resident in HBM; ``e2e`` = the same through
-the host-buffer C-ABI call (pinned host inputs, H2D + D2H inside the timed region).  The oracle is used only
-by the cpu_baseline / --impl reference legs.
+the host-buffer C-ABI call (pinned host inputs, H2D + D2H inside the timed region).  The posterior runs on the
+path the library picks by itself (--posterior-path auto: at the default size the INT8 tensor-core contraction,
+``dtype`` "f64+i8"); the line then also carries ``fp64_path`` - the whole workload on the FP64 DMMA kernel and
+the largest difference between the two result sets over every candidate - and ``roofline.fp64_kernel``.
+--posterior-path fp64 | int8 force one path.  The oracle is used only by the cpu_baseline / --impl reference legs.
 """
 from __future__ import annotations
 
