@@ -20,7 +20,7 @@ import os
 import contextlib
 import ctypes as C
 import math
-from typing import Callable, Optional
+from typing import Callable, Optional, Union
 
 import torch
 
@@ -86,7 +86,7 @@ class ExactGPPosterior:
 
     def __init__(self, kernel, train_x: torch.Tensor, train_y: torch.Tensor, outputscale: float = 1.0,
                  noise: float = 1e-2, mean_const: float = 0.0, chunk: int = DEFAULT_CHUNK, tabulate: bool = False,
-                 int8: Optional[bool] = None):
+                 int8: Optional[Union[bool, str]] = None):
         _lib.require_cuda_f64(train_x, train_y)
         self.kernel = kernel
         self.train_x = train_x.contiguous()
