@@ -64,7 +64,9 @@ INT8_FUSED_CHUNK = 37888   # fused tcgen05 kernel: 296 row blocks of 128 = two p
 # MGB_POSTERIOR_PATH=auto (the default): the INT8 tensor-core contraction serves calls with at least INT8_AUTO_MIN_M
 # candidates against INT8_AUTO_MIN_N .. INT8_AUTO_MAX_N training points (series kernels, fused implementation); smaller
 # calls - the BO loop's hundreds of candidates against ~100 points - stay on the FP64 DMMA kernel, which has no
-# per-fit slicing pass.  int32 accumulation of the digit products is exact up to n = 16384.
+# per-fit slicing pass.  int32 accumulation of the digit products is exact up to n = 16384.  Measured ratios INT8 / FP64:
+# 2.8 at 200 k x 2048, 2.5 at 1 M x 2048 per GPU, 2.7 at 10 M x 5000 (bench.py fp64_path); the lower edges are
+# conservative round numbers, not tuned break-even points.
 INT8_AUTO_MIN_N, INT8_AUTO_MAX_N, INT8_AUTO_MIN_M = 1024, 16384, 16384
 
 
