@@ -81,3 +81,35 @@ def test_plane_bounds_leave_room_in_int32_and_in_the_recombination_words():
     assert p[3] * 2 ** 24 + p[4] * 2 ** 16 + p[5] * 2 ** 8 + p[6] < 2 ** 51
     # int8_fused.cu: 7 n 128^2 < 2^31 up to n = 16384 (its stated limit)
     assert 7 * 16384 * 128 * 128 < 2 ** 31 <= 7 * 18725 * 128 * 128
+
+
+def test_stacked_operand_rows_contract_to_the_planes_with_four_k_steps():
+    """series_i8.cu's GEMM plan in numpy: an A row is its digit vectors side by side [d_0 | ... | d_6 | 0] (eight chunks of
+    16), the B row of (plane s, column j) is [d_s(y_j) | d_(s-1)(y_j) | ... | d_0(y_j) | 0 ...]; K step a contracts the
+    chunk pair (2a, 2a + 1) and is issued only against planes s >= 2a (the rows it skips hold zeros in that pair).  The
+    accumulated result must be P_s = sum_{p + q = s} <d_p(x), d_q(y)> for every plane."""
+    rng = np.random.default_rng(3)
+    w, m, n = 11, 9, 13
+    x = rng.uniform(-0.49, 0.49, (m, w))
+    y = rng.uniform(-0.49, 0.49, (n, w))
+    dx = np.stack([digits_integer_scheme(x[:, k]) for k in range(w)], axis=-1)      # [7][m][w]
+    dy = np.stack([digits_integer_scheme(y[:, k]) for k in range(w)], axis=-1)      # [7][n][w]
+    a_rows = np.zeros((m, 8, 16), dtype=np.int64)
+    a_rows[:, :7, :w] = dx.transpose(1, 0, 2)
+    b_rows = np.zeros((7, n, 8, 16), dtype=np.int64)                                # [plane][column][chunk][16]
+    for s in range(7):
+        for c in range(s + 1):
+            b_rows[s, :, c, :w] = dy[s - c]
+    acc = np.zeros((7, m, n), dtype=np.int64)
+    for a in range(4):                                                              # one K = 32 MMA per chunk pair
+        for s in range(2 * a, 7):                                                   # N = 32 (7 - 2a) stacked rows
+            acc[s] += np.einsum("ick,jck->ij", a_rows[:, 2 * a:2 * a + 2], b_rows[s, :, 2 * a:2 * a + 2])
+        assert not b_rows[:2 * a, :, 2 * a:2 * a + 2].any()                         # what the shortened MMAs skip is zero
+    want = np.zeros_like(acc)
+    for p in range(7):
+        for q in range(7 - p):
+            want[p + q] += dx[p] @ dy[q].T
+    assert np.array_equal(acc, want)
+    # and the planes recombine to the inner product: sum_s P_s 2^(-8 (s + 2)) = <x, y> up to the dropped products
+    u = sum(want[s].astype(np.longdouble) * np.longdouble(2.0) ** (-8 * (s + 2)) for s in range(7))
+    assert float(np.abs(u - x.astype(np.longdouble) @ y.astype(np.longdouble).T).max()) < 6 * w * 2.0 ** 14 * 2.0 ** -72 + w * 2.0 ** -56
